@@ -1,0 +1,216 @@
+/*
+ * plpslam_b200.h -- C ABI of libplpslam_b200.so
+ *
+ * B200-native (sm_100a) replacement for the per-frame hot path of
+ * Structure-PLP-SLAM.  The reference has no FFI: its "operator API" is the
+ * public methods of a handful of C++ classes.  Each
+ * entry point below names the reference method it replaces (file:line under
+ * /root/reference/src/PLPSLAM).  The reference-side adapters that marshal
+ * data::frame / data::keyframe into these PODs are shown in INTEGRATION.md and
+ * shipped as headers under structure-plp-slam_b200/host/.
+ *
+ * Conventions
+ *   - plain C types only, no exceptions cross this boundary; every function
+ *     returns a plp_status and plp_last_error() gives the message;
+ *   - "host" entry points take host pointers and perform the H2D/D2H copies
+ *     themselves; "_dev" entry points take device pointers (already resident in
+ *     HBM) and enqueue work on the context stream without synchronising;
+ *   - there is NO CPU fallback: if no CUDA device is usable every compute entry
+ *     point returns PLP_ERR_NO_DEVICE.
+ *   - all batched entry points have the batch (frames / problems) as the
+ *     leading dimension of every array.
+ */
+#ifndef PLPSLAM_B200_H
+#define PLPSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLP_API __attribute__((visibility("default")))
+
+typedef enum plp_status {
+    PLP_OK = 0,
+    PLP_ERR_INVALID = 1,   /* bad argument (null pointer, negative size, ...)      */
+    PLP_ERR_NO_DEVICE = 2, /* no usable CUDA device -- never falls back to the CPU */
+    PLP_ERR_CUDA = 3,      /* a CUDA runtime call failed, see plp_last_error()     */
+    PLP_ERR_CAPACITY = 4,  /* an input exceeds the capacity the handle was made for */
+    PLP_ERR_NCCL = 5
+} plp_status;
+
+/* ------------------------------------------------------------------------ */
+/* context                                                                  */
+/* ------------------------------------------------------------------------ */
+typedef struct plp_ctx plp_ctx; /* one per (thread, device): stream + scratch */
+
+PLP_API const char *plp_last_error(void);
+PLP_API int plp_version(void);
+PLP_API int plp_device_count(void);
+PLP_API plp_status plp_ctx_create(int device, plp_ctx **out);
+PLP_API void plp_ctx_destroy(plp_ctx *ctx);
+PLP_API plp_status plp_ctx_sync(plp_ctx *ctx);
+/* cudaStream_t of the context as an opaque pointer (for event timing by the harness) */
+PLP_API void *plp_ctx_stream(plp_ctx *ctx);
+/* device-memory helpers so that non-CUDA hosts (ctypes, cgo, ...) can keep data resident */
+PLP_API plp_status plp_dev_alloc(plp_ctx *ctx, size_t bytes, void **out);
+PLP_API plp_status plp_dev_free(plp_ctx *ctx, void *ptr);
+PLP_API plp_status plp_dev_upload(plp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+PLP_API plp_status plp_dev_download(plp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+PLP_API plp_status plp_host_alloc_pinned(size_t bytes, void **out);
+PLP_API plp_status plp_host_free_pinned(void *ptr);
+/* number of kernels this library has launched since the context was created */
+PLP_API uint64_t plp_ctx_launch_count(plp_ctx *ctx);
+
+/* ------------------------------------------------------------------------ */
+/* 256-bit Hamming  (match/base.h:43-93)                                    */
+/* ------------------------------------------------------------------------ */
+#define PLP_HAMMING_DIST_THR_LOW 50   /* match/base.h:38 */
+#define PLP_HAMMING_DIST_THR_HIGH 100 /* match/base.h:39 */
+#define PLP_MAX_HAMMING_DIST 256      /* match/base.h:40 */
+
+/* dist[i*nb + j] = popcount(a[i] xor b[j]) over 32-byte rows; replaces
+ * compute_descriptor_distance_32/_64 (match/base.h:43-93) evaluated over a block. */
+PLP_API plp_status plp_hamming_matrix(plp_ctx *ctx, const uint8_t *desc_a, int na,
+                                      const uint8_t *desc_b, int nb, uint16_t *dist_out);
+
+/* Exact 1-NN over 32-byte rows; replaces BinaryDescriptorMatcher::match(query, train, matches)
+ * (feature/line_descriptor/binary_descriptor_matcher.cpp:197-254).  Ties resolve to the
+ * lowest train index.  nn_idx[i] = -1 when nt == 0. */
+PLP_API plp_status plp_hamming_nn(plp_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train,
+                                  int nt, int32_t *nn_idx, uint16_t *nn_dist);
+
+/* ------------------------------------------------------------------------ */
+/* frame features as the matchers see them                                   */
+/* ------------------------------------------------------------------------ */
+typedef struct plp_grid {
+    /* camera::base grid (camera/base.h:91,147-160; camera/perspective.cc:53-56) */
+    float min_x, min_y; /* img_bounds_.min_x_/min_y_ */
+    double inv_cell_width, inv_cell_height;
+    int32_t num_cols, num_rows; /* 64 x 48 */
+} plp_grid;
+
+typedef struct plp_frame_points {
+    int32_t n;              /* frame::num_keypts_                                      */
+    const float *x;         /* undist_keypts_[i].pt.x                                  */
+    const float *y;         /* undist_keypts_[i].pt.y                                  */
+    const int32_t *octave;  /* undist_keypts_[i].octave                                */
+    const float *angle;     /* undist_keypts_[i].angle (deg); may be NULL if unused    */
+    const float *x_right;   /* stereo_x_right_[i] (<0: monocular); NULL == all -1      */
+    const uint8_t *desc;    /* descriptors_.row(i), n x 32                             */
+    const uint8_t *claimed; /* landmarks_[i] && landmarks_[i]->has_observation(); NULL == none */
+} plp_frame_points;
+
+typedef struct plp_frame_lines {
+    int32_t n;             /* frame::_num_keylines                                     */
+    const float *sx, *sy;  /* _keylsd[i].getStartPoint()                               */
+    const float *ex, *ey;  /* _keylsd[i].getEndPoint()                                 */
+    const int32_t *octave; /* _keylsd[i].octave                                        */
+    /* level the reference compares in the ratio test: it reads undist_keypts_[i].octave
+     * (match/projection.cc:170,175 -- a point octave at a line index); the adapter passes
+     * exactly that array so the behaviour is unchanged. */
+    const int32_t *ratio_level;
+    const float *x_right_sp, *x_right_ep; /* _stereo_x_right_cooresponding_to_keylines; NULL == none */
+    const uint8_t *desc;                  /* _lbd_descr.row(i), n x 32                */
+    const uint8_t *claimed;               /* _landmarks_line[i] && has_observation()   */
+} plp_frame_lines;
+
+typedef struct plp_camera {
+    /* camera::perspective (camera/perspective.cc:40-56,190-209) */
+    double fx, fy, cx, cy;
+    double focal_x_baseline; /* bf; <= 0 for monocular */
+    double true_baseline;
+    float min_x, max_x, min_y, max_y; /* img_bounds_ */
+    int32_t setup_type;               /* 0 Monocular, 1 Stereo, 2 RGBD (camera/base.h setup_type_t) */
+} plp_camera;
+
+/* ------------------------------------------------------------------------ */
+/* projection matchers (match/projection.cc)                                 */
+/* ------------------------------------------------------------------------ */
+
+/* projection::match_frame_and_landmarks (match/projection.cc:37-121).
+ * One query per local landmark that passed frame::can_observe, in the order of
+ * `local_landmarks`.  best_idx_out[q] = keypoint index written to frm.landmarks_ or -1.
+ * Sequential "skip already claimed keypoints" semantics are reproduced exactly. */
+typedef struct plp_landmark_queries {
+    int32_t m;
+    const float *reproj_x, *reproj_y; /* reproj_in_tracking_                    */
+    const float *x_right;             /* x_right_in_tracking_                   */
+    const int32_t *scale_level;       /* scale_level_in_tracking_               */
+    const uint8_t *desc;              /* landmark::get_descriptor(), m x 32     */
+    const uint8_t *valid;             /* is_observable_in_tracking_ && !will_be_erased(); NULL == all */
+} plp_landmark_queries;
+
+PLP_API plp_status plp_match_frame_and_landmarks(plp_ctx *ctx, const plp_frame_points *frm,
+                                                 const plp_grid *grid, const float *scale_factors,
+                                                 int num_levels, const plp_landmark_queries *q,
+                                                 float margin, float lowe_ratio,
+                                                 int32_t *best_idx_out, uint32_t *num_matches_out);
+
+/* projection::match_current_and_last_frames (match/projection.cc:214-358).
+ * Inputs are the last frame's keypoints that own a landmark: world position, octave, angle,
+ * descriptor of the landmark; `valid` = lm != nullptr && !outlier_flags_.
+ * matched_last_idx_out[n_curr]: index into the last-frame arrays assigned to each current
+ * keypoint (curr_frm.landmarks_) after the orientation check, or -1. */
+typedef struct plp_last_frame_points {
+    int32_t n;
+    const double *pos_w;   /* n x 3, lm->get_pos_in_world()               */
+    const int32_t *octave; /* last_frm.keypts_[i].octave                  */
+    const float *angle;    /* last_frm.undist_keypts_[i].angle            */
+    const uint8_t *desc;   /* lm->get_descriptor(), n x 32                */
+    const uint8_t *valid;  /* lm && !last_frm.outlier_flags_[i]           */
+} plp_last_frame_points;
+
+PLP_API plp_status plp_match_current_and_last_frames(
+    plp_ctx *ctx, const plp_frame_points *curr, const plp_grid *grid, const float *scale_factors,
+    int num_levels, const plp_camera *cam, const double *pose_cw_curr /*4x4 row-major*/,
+    const double *pose_cw_last /*4x4 row-major*/, const plp_last_frame_points *last, float margin,
+    int check_orientation, int32_t *matched_last_idx_out, uint32_t *num_matches_out);
+
+/* projection::match_frame_and_landmarks_line (match/projection.cc:124-212) */
+typedef struct plp_line_queries {
+    int32_t m;
+    const float *sp_x, *sp_y, *ep_x, *ep_y; /* _reproj_in_tracking_sp / _ep      */
+    const int32_t *scale_level;             /* _scale_level_in_tracking          */
+    const uint8_t *desc;
+    const uint8_t *valid;
+} plp_line_queries;
+
+PLP_API plp_status plp_match_frame_and_landmarks_line(plp_ctx *ctx, const plp_frame_lines *frm,
+                                                      const float *scale_factors_lsd,
+                                                      int num_levels_lsd, const plp_line_queries *q,
+                                                      float margin, float lowe_ratio,
+                                                      int32_t *best_idx_out,
+                                                      uint32_t *num_matches_out);
+
+/* projection::match_current_and_last_frames_line (match/projection.cc:361-527) */
+typedef struct plp_last_frame_lines {
+    int32_t n;
+    const double *pos_w;   /* n x 6, Line::get_pos_in_world(): (sp, ep)    */
+    const int32_t *octave; /* last_frm._keylsd[i].octave                   */
+    const uint8_t *desc;
+    const uint8_t *valid; /* lm_line && !last_frm._outlier_flags_line[i]   */
+} plp_last_frame_lines;
+
+PLP_API plp_status plp_match_current_and_last_frames_line(
+    plp_ctx *ctx, const plp_frame_lines *curr, const float *scale_factors_lsd, int num_levels_lsd,
+    const plp_camera *cam, const double *pose_cw_curr, const double *pose_cw_last,
+    const plp_last_frame_lines *last, float margin, int32_t *matched_last_idx_out,
+    uint32_t *num_matches_out);
+
+/* robust::brute_force_match (match/robust.cc:257-385).
+ * frame = "1", keyframe = "2".  kf_valid[j] = lm_2 && !lm_2->will_be_erased().
+ * matched_kf_idx_in_frm_out[n_frm] = matched_indices_2_in_1 after the orientation check. */
+PLP_API plp_status plp_match_brute_force(plp_ctx *ctx, const uint8_t *frm_desc,
+                                         const float *frm_angle, int n_frm,
+                                         const uint8_t *kf_desc, const float *kf_angle,
+                                         const uint8_t *kf_valid, int n_kf, float lowe_ratio,
+                                         int check_orientation, int32_t *matched_kf_idx_in_frm_out,
+                                         uint32_t *num_matches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLPSLAM_B200_H */

@@ -1,0 +1,551 @@
+// oracle/match.cc -- CPU restatement of the Hamming matchers (TEST INFRASTRUCTURE ONLY).
+// Follows /root/reference/src/PLPSLAM/match/{base.h,angle_checker.h,projection.cc,robust.cc},
+// data/common.{h,cc} and camera/perspective.cc; see oracle.h for the pinning status.
+#include "oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+namespace {
+
+// OpenCV scalar helpers (cvFloor/cvCeil/cvRound; cvRound = round-half-even)
+inline int cvFloor(double v) {
+    int i = (int)v;
+    return i - (i > v);
+}
+inline int cvCeil(double v) {
+    int i = (int)v;
+    return i + (i < v);
+}
+inline int cvRoundF(float v) { return (int)std::lrintf(v); }
+
+constexpr unsigned HAMMING_DIST_THR_LOW = 50;    // match/base.h:38
+constexpr unsigned HAMMING_DIST_THR_HIGH = 100;  // match/base.h:39
+constexpr unsigned MAX_HAMMING_DIST = 256;       // match/base.h:40
+
+// match/angle_checker.h:86-175 with the oracle's stable bin ranking
+struct AngleChecker {
+    unsigned histogram_length;
+    float inv_histogram_length;
+    unsigned num_bins_thr;
+    std::vector<std::vector<int>> hist;
+    AngleChecker(unsigned len = 30, unsigned thr = 3)
+        : histogram_length(len), inv_histogram_length(1.0f / len), num_bins_thr(thr), hist(len) {}
+    void append(float delta_angle, int match) {
+        // angle_checker.h:100-113
+        if (delta_angle < 0.0) delta_angle += 360.0;
+        if (360.0 <= delta_angle) delta_angle -= 360.0;
+        const auto bin = static_cast<unsigned>(cvRoundF(delta_angle * inv_histogram_length));
+        hist.at(bin).push_back(match);
+    }
+    std::vector<unsigned> ranked_bins() const {
+        // angle_checker.h:163-175 (std::sort by size desc; ties made stable: bin index asc)
+        std::vector<unsigned> idx(hist.size());
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(),
+                         [this](unsigned a, unsigned b) { return hist[a].size() > hist[b].size(); });
+        return idx;
+    }
+    std::vector<int> collect(bool want_valid) const {
+        // angle_checker.h:115-161
+        std::vector<int> out;
+        const auto bins = ranked_bins();
+        for (unsigned bin = 0; bin < histogram_length; ++bin) {
+            const bool is_valid =
+                std::any_of(bins.begin(), bins.begin() + num_bins_thr, [bin](unsigned i) { return bin == i; });
+            if (is_valid == want_valid) out.insert(out.end(), hist[bin].begin(), hist[bin].end());
+        }
+        return out;
+    }
+};
+
+// data/common.cc:205-231
+struct Grid {
+    const orc_grid *g;
+    std::vector<std::vector<std::vector<unsigned>>> cells;
+    Grid(const orc_grid *g_, const float *x, const float *y, int n) : g(g_) {
+        cells.resize(g->num_cols);
+        for (auto &col : cells) col.resize(g->num_rows);
+        for (int idx = 0; idx < n; ++idx) {
+            int cx, cy;
+            if (orc_get_cell_indices(g, x[idx], y[idx], &cx, &cy)) cells[cx][cy].push_back(idx);
+        }
+    }
+    // data/common.cc:241-313
+    std::vector<unsigned> query(const float *x, const float *y, const int32_t *octave, float ref_x,
+                                float ref_y, float margin, int min_level, int max_level) const {
+        std::vector<unsigned> indices;
+        const int min_cell_idx_x = std::max(0, cvFloor((ref_x - g->min_x - margin) * g->inv_cell_width));
+        if (g->num_cols <= min_cell_idx_x) return indices;
+        const int max_cell_idx_x =
+            std::min(g->num_cols - 1, cvCeil((ref_x - g->min_x + margin) * g->inv_cell_width));
+        if (max_cell_idx_x < 0) return indices;
+        const int min_cell_idx_y = std::max(0, cvFloor((ref_y - g->min_y - margin) * g->inv_cell_height));
+        if (g->num_rows <= min_cell_idx_y) return indices;
+        const int max_cell_idx_y =
+            std::min(g->num_rows - 1, cvCeil((ref_y - g->min_y + margin) * g->inv_cell_height));
+        if (max_cell_idx_y < 0) return indices;
+        const bool check_level = (0 < min_level) || (0 <= max_level);
+        for (int cx = min_cell_idx_x; cx <= max_cell_idx_x; ++cx) {
+            for (int cy = min_cell_idx_y; cy <= max_cell_idx_y; ++cy) {
+                for (unsigned idx : cells[cx][cy]) {
+                    if (check_level) {
+                        if (octave[idx] < min_level) continue;
+                        if (0 <= max_level && max_level < octave[idx]) continue;
+                    }
+                    const float dist_x = x[idx] - ref_x;
+                    const float dist_y = y[idx] - ref_y;
+                    if (std::abs(dist_x) < margin && std::abs(dist_y) < margin) indices.push_back(idx);
+                }
+            }
+        }
+        return indices;
+    }
+};
+
+// data/common.cc:315-364
+std::vector<unsigned> keylines_in_cell(int n, const float *sx, const float *sy, const float *ex,
+                                       const float *ey, const int32_t *octave, float ref_x1,
+                                       float ref_y1, float ref_x2, float ref_y2, float margin,
+                                       int min_level, int max_level) {
+    std::vector<unsigned> indices;
+    // Vec3_t point_sp{ref_x1, ref_y1, 1.0}.cross(point_ep) in double
+    const double ax = ref_x1, ay = ref_y1, bx = ref_x2, by = ref_y2;
+    const double l0 = ay * 1.0 - 1.0 * by;
+    const double l1 = 1.0 * bx - ax * 1.0;
+    const double l2 = ax * by - ay * bx;
+    const bool check_level = (0 < min_level) || (0 <= max_level);
+    for (int i = 0; i < n; ++i) {
+        const double den = std::sqrt(l0 * l0 + l1 * l1);
+        const float distance_sp = (float)((sx[i] * l0 + sy[i] * l1 + l2) / den);
+        const float distance_ep = (float)((ex[i] * l0 + ey[i] * l1 + l2) / den);
+        if (std::abs(distance_sp) > margin || std::abs(distance_ep) > margin) continue;
+        if (check_level) {
+            if (octave[i] < min_level) continue;
+            if (max_level > 0 && octave[i] > max_level) continue;
+        }
+        indices.push_back(i);
+    }
+    return indices;
+}
+
+struct Pose {
+    double R[9];
+    double t[3];
+    explicit Pose(const double *T) {
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) R[r * 3 + c] = T[r * 4 + c];
+            t[r] = T[r * 4 + 3];
+        }
+    }
+};
+
+// projection.cc:220-238 : forward/backward assumption
+void motion_assumption(const orc_camera *cam, const Pose &cw, const Pose &lw, bool *fwd, bool *bwd) {
+    // trans_wc = -rot_cw^T * trans_cw ; trans_lc = rot_lw * trans_wc + trans_lw
+    double twc[3];
+    for (int r = 0; r < 3; ++r)
+        twc[r] = -(cw.R[0 * 3 + r] * cw.t[0] + cw.R[1 * 3 + r] * cw.t[1] + cw.R[2 * 3 + r] * cw.t[2]);
+    const double tlc_z = lw.R[6] * twc[0] + lw.R[7] * twc[1] + lw.R[8] * twc[2] + lw.t[2];
+    const bool mono = cam->setup_type == 0;
+    *fwd = mono ? false : tlc_z > cam->true_baseline;
+    *bwd = mono ? false : -tlc_z > cam->true_baseline;
+}
+
+}  // namespace
+
+extern "C" {
+
+unsigned orc_hamming_32(const uint8_t *a, const uint8_t *b) {
+    // match/base.h:43-67 (SWAR popcount over 8 x u32)
+    constexpr uint32_t mask_1 = 0x55555555U, mask_2 = 0x33333333U, mask_3 = 0x0F0F0F0FU, mask_4 = 0x01010101U;
+    uint32_t pa[8], pb[8];
+    std::memcpy(pa, a, 32);
+    std::memcpy(pb, b, 32);
+    unsigned dist = 0;
+    for (unsigned i = 0; i < 8; ++i) {
+        auto v = pa[i] ^ pb[i];
+        v -= ((v >> 1) & mask_1);
+        v = (v & mask_2) + ((v >> 2) & mask_2);
+        dist += (((v + (v >> 4)) & mask_3) * mask_4) >> 24;
+    }
+    return dist;
+}
+
+unsigned orc_hamming_64(const uint8_t *a, const uint8_t *b) {
+    // match/base.h:70-93
+    constexpr uint64_t mask_1 = 0x5555555555555555UL, mask_2 = 0x3333333333333333UL,
+                       mask_3 = 0x0F0F0F0F0F0F0F0FUL, mask_4 = 0x0101010101010101UL;
+    uint64_t pa[4], pb[4];
+    std::memcpy(pa, a, 32);
+    std::memcpy(pb, b, 32);
+    unsigned dist = 0;
+    for (unsigned i = 0; i < 4; ++i) {
+        auto v = pa[i] ^ pb[i];
+        v -= (v >> 1) & mask_1;
+        v = (v & mask_2) + ((v >> 2) & mask_2);
+        dist += (unsigned)((((v + (v >> 4)) & mask_3) * mask_4) >> 56);
+    }
+    return dist;
+}
+
+void orc_hamming_matrix(const uint8_t *a, int na, const uint8_t *b, int nb, uint16_t *out) {
+    for (int i = 0; i < na; ++i)
+        for (int j = 0; j < nb; ++j) out[(size_t)i * nb + j] = (uint16_t)orc_hamming_32(a + 32 * i, b + 32 * j);
+}
+
+void orc_hamming_nn(const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *idx, uint16_t *dist) {
+    // binary_descriptor_matcher.cpp:197-254 semantics: exact 1-NN (ties -> lowest train index)
+    for (int i = 0; i < nq; ++i) {
+        int best = -1;
+        unsigned bd = 1u << 30;
+        for (int j = 0; j < nt; ++j) {
+            const unsigned d = orc_hamming_32(q + 32 * i, t + 32 * j);
+            if (d < bd) {
+                bd = d;
+                best = j;
+            }
+        }
+        idx[i] = best;
+        dist[i] = (uint16_t)(best < 0 ? 0xFFFF : bd);
+    }
+}
+
+int orc_angle_checker_invalid(const float *delta_angles, const int32_t *matches, int n, int histogram_length,
+                              int num_bins_thr, int32_t *invalid_out) {
+    AngleChecker ac(histogram_length, num_bins_thr);
+    for (int i = 0; i < n; ++i) ac.append(delta_angles[i], matches[i]);
+    const auto v = ac.collect(false);
+    std::copy(v.begin(), v.end(), invalid_out);
+    return (int)v.size();
+}
+
+int orc_angle_checker_valid(const float *delta_angles, const int32_t *matches, int n, int histogram_length,
+                            int num_bins_thr, int32_t *valid_out) {
+    AngleChecker ac(histogram_length, num_bins_thr);
+    for (int i = 0; i < n; ++i) ac.append(delta_angles[i], matches[i]);
+    const auto v = ac.collect(true);
+    std::copy(v.begin(), v.end(), valid_out);
+    return (int)v.size();
+}
+
+int orc_get_cell_indices(const orc_grid *g, float x, float y, int *cx, int *cy) {
+    // data/common.h:104-109
+    *cx = cvFloor((x - g->min_x) * g->inv_cell_width);
+    *cy = cvFloor((y - g->min_y) * g->inv_cell_height);
+    return (0 <= *cx && *cx < g->num_cols && 0 <= *cy && *cy < g->num_rows);
+}
+
+int orc_get_keypoints_in_cell(const orc_grid *g, const float *x, const float *y, const int32_t *octave, int n,
+                              float ref_x, float ref_y, float margin, int min_level, int max_level,
+                              int32_t *indices_out) {
+    Grid grid(g, x, y, n);
+    const auto v = grid.query(x, y, octave, ref_x, ref_y, margin, min_level, max_level);
+    for (size_t i = 0; i < v.size(); ++i) indices_out[i] = (int32_t)v[i];
+    return (int)v.size();
+}
+
+int orc_reproject_to_image(const orc_camera *cam, const double *R, const double *t, const double *pos_w,
+                           double *reproj, float *x_right) {
+    // camera/perspective.cc:190-209
+    const double pc0 = R[0] * pos_w[0] + R[1] * pos_w[1] + R[2] * pos_w[2] + t[0];
+    const double pc1 = R[3] * pos_w[0] + R[4] * pos_w[1] + R[5] * pos_w[2] + t[1];
+    const double pc2 = R[6] * pos_w[0] + R[7] * pos_w[1] + R[8] * pos_w[2] + t[2];
+    if (pc2 <= 0.0) return 0;
+    const double z_inv = 1.0 / pc2;
+    reproj[0] = cam->fx * pc0 * z_inv + cam->cx;
+    reproj[1] = cam->fy * pc1 * z_inv + cam->cy;
+    *x_right = (float)(reproj[0] - cam->focal_x_baseline * z_inv);
+    return (cam->min_x < reproj[0] && reproj[0] < cam->max_x && cam->min_y < reproj[1] && reproj[1] < cam->max_y);
+}
+
+unsigned orc_match_frame_and_landmarks(const orc_grid *g, int n, const float *x, const float *y,
+                                       const int32_t *octave, const float *x_right, const uint8_t *desc,
+                                       const uint8_t *claimed_in, const float *scale_factors, int num_levels,
+                                       int m, const float *reproj_x, const float *reproj_y,
+                                       const float *q_x_right, const int32_t *scale_level,
+                                       const uint8_t *q_desc, const uint8_t *q_valid, float margin,
+                                       float lowe_ratio, int32_t *best_idx_out) {
+    // match/projection.cc:37-121
+    (void)num_levels;
+    Grid grid(g, x, y, n);
+    std::vector<uint8_t> claimed(n, 0);
+    if (claimed_in) claimed.assign(claimed_in, claimed_in + n);
+    unsigned num_matches = 0;
+    for (int q = 0; q < m; ++q) {
+        best_idx_out[q] = -1;
+        if (q_valid && !q_valid[q]) continue;
+        const int pred_scale_level = scale_level[q];
+        const auto indices = grid.query(x, y, octave, reproj_x[q], reproj_y[q],
+                                        margin * scale_factors[pred_scale_level], pred_scale_level - 1,
+                                        pred_scale_level);
+        if (indices.empty()) continue;
+        unsigned best_hamm_dist = MAX_HAMMING_DIST, second_best_hamm_dist = MAX_HAMMING_DIST;
+        int best_scale_level = -1, second_best_scale_level = -1, best_idx = -1;
+        for (const auto idx : indices) {
+            if (claimed[idx]) continue;
+            if (x_right && 0 < x_right[idx]) {
+                const auto reproj_error = std::abs(q_x_right[q] - x_right[idx]);
+                if (margin * scale_factors[pred_scale_level] < reproj_error) continue;
+            }
+            const auto dist = orc_hamming_32(q_desc + 32 * q, desc + 32 * idx);
+            if (dist < best_hamm_dist) {
+                second_best_hamm_dist = best_hamm_dist;
+                best_hamm_dist = dist;
+                second_best_scale_level = best_scale_level;
+                best_scale_level = octave[idx];
+                best_idx = idx;
+            } else if (dist < second_best_hamm_dist) {
+                second_best_scale_level = octave[idx];
+                second_best_hamm_dist = dist;
+            }
+        }
+        if (best_hamm_dist <= HAMMING_DIST_THR_HIGH) {
+            if (best_scale_level == second_best_scale_level && best_hamm_dist > lowe_ratio * second_best_hamm_dist)
+                continue;
+            best_idx_out[q] = best_idx;
+            claimed[best_idx] = 1;  // frm.landmarks_.at(best_idx) = local_lm (local landmarks have observations)
+            ++num_matches;
+        }
+    }
+    return num_matches;
+}
+
+unsigned orc_match_current_and_last_frames(const orc_grid *g, int n, const float *x, const float *y,
+                                           const int32_t *octave, const float *angle, const float *x_right,
+                                           const uint8_t *desc, const uint8_t *claimed_in,
+                                           const float *scale_factors, int num_levels, const orc_camera *cam,
+                                           const double *pose_cw_curr, const double *pose_cw_last, int n_last,
+                                           const double *pos_w, const int32_t *last_octave,
+                                           const float *last_angle, const uint8_t *last_desc,
+                                           const uint8_t *last_valid, float margin, int check_orientation,
+                                           int32_t *matched_last_idx_out) {
+    // match/projection.cc:214-358
+    Grid grid(g, x, y, n);
+    std::vector<uint8_t> claimed(n, 0);
+    if (claimed_in) claimed.assign(claimed_in, claimed_in + n);
+    for (int i = 0; i < n; ++i) matched_last_idx_out[i] = -1;
+    const Pose cw(pose_cw_curr), lw(pose_cw_last);
+    bool assume_forward, assume_backward;
+    motion_assumption(cam, cw, lw, &assume_forward, &assume_backward);
+    AngleChecker angle_checker;
+    unsigned num_matches = 0;
+    for (int idx_last = 0; idx_last < n_last; ++idx_last) {
+        if (last_valid && !last_valid[idx_last]) continue;
+        double reproj[2];
+        float xr;
+        if (!orc_reproject_to_image(cam, cw.R, cw.t, pos_w + 3 * idx_last, reproj, &xr)) continue;
+        const int last_scale_level = last_octave[idx_last];
+        const float radius = margin * scale_factors[last_scale_level];
+        std::vector<unsigned> indices;
+        if (assume_forward)
+            indices = grid.query(x, y, octave, (float)reproj[0], (float)reproj[1], radius, last_scale_level,
+                                 num_levels - 1);
+        else if (assume_backward)
+            indices = grid.query(x, y, octave, (float)reproj[0], (float)reproj[1], radius, 0, last_scale_level);
+        else
+            indices = grid.query(x, y, octave, (float)reproj[0], (float)reproj[1], radius, last_scale_level - 1,
+                                 last_scale_level + 1);
+        if (indices.empty()) continue;
+        unsigned best_hamm_dist = MAX_HAMMING_DIST;
+        int best_idx = -1;
+        for (const auto curr_idx : indices) {
+            if (claimed[curr_idx]) continue;
+            if (x_right && x_right[curr_idx] > 0) {
+                const float reproj_error = std::fabs(xr - x_right[curr_idx]);
+                if (radius < reproj_error) continue;
+            }
+            const auto hamm_dist = orc_hamming_32(last_desc + 32 * idx_last, desc + 32 * curr_idx);
+            if (hamm_dist < best_hamm_dist) {
+                best_hamm_dist = hamm_dist;
+                best_idx = curr_idx;
+            }
+        }
+        if (HAMMING_DIST_THR_HIGH < best_hamm_dist) continue;
+        matched_last_idx_out[best_idx] = idx_last;
+        claimed[best_idx] = 1;
+        ++num_matches;
+        if (check_orientation) {
+            const auto delta_angle = last_angle[idx_last] - angle[best_idx];
+            angle_checker.append(delta_angle, best_idx);
+        }
+    }
+    if (check_orientation) {
+        for (const auto invalid_idx : angle_checker.collect(false)) {
+            matched_last_idx_out[invalid_idx] = -1;
+            --num_matches;
+        }
+    }
+    return num_matches;
+}
+
+unsigned orc_match_frame_and_landmarks_line(int n, const float *sx, const float *sy, const float *ex,
+                                            const float *ey, const int32_t *octave,
+                                            const int32_t *ratio_level, const uint8_t *desc,
+                                            const uint8_t *claimed_in, const float *scale_factors_lsd,
+                                            int num_levels_lsd, int m, const float *sp_x, const float *sp_y,
+                                            const float *ep_x, const float *ep_y, const int32_t *scale_level,
+                                            const uint8_t *q_desc, const uint8_t *q_valid, float margin,
+                                            float lowe_ratio, int32_t *best_idx_out) {
+    // match/projection.cc:124-212
+    (void)num_levels_lsd;
+    std::vector<uint8_t> claimed(n, 0);
+    if (claimed_in) claimed.assign(claimed_in, claimed_in + n);
+    unsigned num_matches = 0;
+    for (int q = 0; q < m; ++q) {
+        best_idx_out[q] = -1;
+        if (q_valid && !q_valid[q]) continue;
+        const int pred_scale_level = scale_level[q];
+        const auto indices =
+            keylines_in_cell(n, sx, sy, ex, ey, octave, sp_x[q], sp_y[q], ep_x[q], ep_y[q],
+                             margin * scale_factors_lsd[pred_scale_level], pred_scale_level - 1, pred_scale_level);
+        if (indices.empty()) continue;
+        unsigned best_hamm_dist = MAX_HAMMING_DIST, second_best_hamm_dist = MAX_HAMMING_DIST;
+        int best_scale_level = -1, second_best_scale_level = -1, best_idx = -1;
+        for (const auto idx : indices) {
+            if (claimed[idx]) continue;
+            const auto dist = orc_hamming_32(q_desc + 32 * q, desc + 32 * idx);
+            if (dist < best_hamm_dist) {
+                second_best_hamm_dist = best_hamm_dist;
+                best_hamm_dist = dist;
+                second_best_scale_level = best_scale_level;
+                best_scale_level = ratio_level[idx];
+                best_idx = idx;
+            } else if (dist < second_best_hamm_dist) {
+                second_best_scale_level = ratio_level[idx];
+                second_best_hamm_dist = dist;
+            }
+        }
+        if (best_hamm_dist <= HAMMING_DIST_THR_HIGH) {
+            if (best_scale_level == second_best_scale_level && best_hamm_dist > lowe_ratio * second_best_hamm_dist)
+                continue;
+            best_idx_out[q] = best_idx;
+            claimed[best_idx] = 1;
+            ++num_matches;
+        }
+    }
+    return num_matches;
+}
+
+unsigned orc_match_current_and_last_frames_line(int n, const float *sx, const float *sy, const float *ex,
+                                                const float *ey, const int32_t *octave,
+                                                const float *x_right_sp, const float *x_right_ep,
+                                                const uint8_t *desc, const uint8_t *claimed_in,
+                                                const float *scale_factors_lsd, int num_levels_lsd,
+                                                const orc_camera *cam, const double *pose_cw_curr,
+                                                const double *pose_cw_last, int n_last, const double *pos_w,
+                                                const int32_t *last_octave, const uint8_t *last_desc,
+                                                const uint8_t *last_valid, float margin,
+                                                int32_t *matched_last_idx_out) {
+    // match/projection.cc:361-527
+    std::vector<uint8_t> claimed(n, 0);
+    if (claimed_in) claimed.assign(claimed_in, claimed_in + n);
+    for (int i = 0; i < n; ++i) matched_last_idx_out[i] = -1;
+    const Pose cw(pose_cw_curr), lw(pose_cw_last);
+    bool assume_forward, assume_backward;
+    motion_assumption(cam, cw, lw, &assume_forward, &assume_backward);
+    unsigned num_matches = 0;
+    for (int idx_last = 0; idx_last < n_last; ++idx_last) {
+        if (last_valid && !last_valid[idx_last]) continue;
+        const double *pw = pos_w + 6 * idx_last;
+        double reproj_sp[2], reproj_ep[2];
+        float xr_sp, xr_ep;
+        const bool in_sp = orc_reproject_to_image(cam, cw.R, cw.t, pw, reproj_sp, &xr_sp);
+        const bool in_ep = orc_reproject_to_image(cam, cw.R, cw.t, pw + 3, reproj_ep, &xr_ep);
+        if (!in_sp && !in_ep) continue;
+        if (!in_sp || !in_ep) {
+            const double mp[3] = {0.5 * (pw[0] + pw[3]), 0.5 * (pw[1] + pw[4]), 0.5 * (pw[2] + pw[5])};
+            double reproj_mp[2];
+            float xr_mp;
+            if (!orc_reproject_to_image(cam, cw.R, cw.t, mp, reproj_mp, &xr_mp)) continue;
+        }
+        // NB: when an endpoint is behind the camera (z<=0) the reference leaves reproj_* uninitialised
+        // (camera/perspective.cc:196-199); the oracle and the kernels define it as 0 in that case.
+        const int last_scale_level = last_octave[idx_last];
+        const float radius = margin * scale_factors_lsd[last_scale_level];
+        int min_level, max_level;
+        if (assume_forward) {
+            min_level = last_scale_level;
+            max_level = num_levels_lsd;
+        } else if (assume_backward) {
+            min_level = 0;
+            max_level = last_scale_level + 1;
+        } else {
+            min_level = last_scale_level - 1;
+            max_level = last_scale_level + 1;
+        }
+        const auto indices = keylines_in_cell(n, sx, sy, ex, ey, octave, (float)reproj_sp[0], (float)reproj_sp[1],
+                                              (float)reproj_ep[0], (float)reproj_ep[1], radius, min_level, max_level);
+        if (indices.empty()) continue;
+        unsigned best_hamm_dist = MAX_HAMMING_DIST;
+        int best_idx = -1;
+        for (const auto curr_idx : indices) {
+            if (claimed[curr_idx]) continue;
+            if (cam->setup_type == 2 && x_right_sp && x_right_ep) {
+                if (x_right_sp[curr_idx] > 0 && x_right_ep[curr_idx] > 0) {
+                    const float e_sp = std::fabs(xr_sp - x_right_sp[curr_idx]);
+                    const float e_ep = std::fabs(xr_ep - x_right_ep[curr_idx]);
+                    if (radius < e_sp || radius < e_ep) continue;
+                }
+            }
+            const auto hamm_dist = orc_hamming_32(last_desc + 32 * idx_last, desc + 32 * curr_idx);
+            if (hamm_dist < best_hamm_dist) {
+                best_hamm_dist = hamm_dist;
+                best_idx = curr_idx;
+            }
+        }
+        if (HAMMING_DIST_THR_HIGH < best_hamm_dist) continue;
+        matched_last_idx_out[best_idx] = idx_last;
+        claimed[best_idx] = 1;
+        ++num_matches;
+    }
+    return num_matches;
+}
+
+unsigned orc_brute_force_match(const uint8_t *frm_desc, const float *frm_angle, int n_frm,
+                               const uint8_t *kf_desc, const float *kf_angle, const uint8_t *kf_valid, int n_kf,
+                               float lowe_ratio, int check_orientation, int32_t *matched) {
+    // match/robust.cc:257-385
+    unsigned num_matches = 0;
+    AngleChecker angle_checker;
+    for (int i = 0; i < n_frm; ++i) matched[i] = -1;
+    std::vector<uint8_t> already(n_frm, 0);
+    for (int idx_2 = 0; idx_2 < n_kf; ++idx_2) {
+        if (kf_valid && !kf_valid[idx_2]) continue;
+        unsigned best_hamm_dist = MAX_HAMMING_DIST, second_best_hamm_dist = MAX_HAMMING_DIST;
+        int best_idx_1 = -1;
+        for (int idx_1 = 0; idx_1 < n_frm; ++idx_1) {
+            if (already[idx_1]) continue;
+            const auto hamm_dist = orc_hamming_32(kf_desc + 32 * idx_2, frm_desc + 32 * idx_1);
+            if (hamm_dist < best_hamm_dist) {
+                second_best_hamm_dist = best_hamm_dist;
+                best_hamm_dist = hamm_dist;
+                best_idx_1 = idx_1;
+            } else if (hamm_dist < second_best_hamm_dist) {
+                second_best_hamm_dist = hamm_dist;
+            }
+        }
+        if (HAMMING_DIST_THR_LOW < best_hamm_dist) continue;
+        if (best_idx_1 < 0) continue;
+        if (lowe_ratio * second_best_hamm_dist < static_cast<float>(best_hamm_dist)) continue;
+        matched[best_idx_1] = idx_2;
+        already[best_idx_1] = 1;
+        if (check_orientation) {
+            const auto delta_angle = frm_angle[best_idx_1] - kf_angle[idx_2];
+            angle_checker.append(delta_angle, best_idx_1);
+        }
+        ++num_matches;
+    }
+    if (check_orientation) {
+        for (const auto invalid_idx_1 : angle_checker.collect(false)) {
+            matched[invalid_idx_1] = -1;
+            --num_matches;
+        }
+    }
+    return num_matches;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+/*
+ * oracle.h -- CPU restatement of the Structure-PLP-SLAM hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * This library is the parity checker for libplpslam_b200.so.  It is a plain, sequential
+ * C++17 restatement of the reference algorithms, each function citing the reference file:line
+ * it follows (paths relative to /root/reference/src/PLPSLAM).  Only tests/, bench.py's
+ * cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load it; the product
+ * (structure-plp-slam_b200/) never does.
+ *
+ * Pinning status (see DESIGN.md "Oracle"):
+ *   - Hamming, scale tables, angle checker, cell indices, trig: pinned by the reference's own
+ *     known-answer tests (test/PLPSLAM/match/base.cc etc.), restated in tests/.
+ *   - OpenCV primitives (resize, FAST, GaussianBlur, fastAtan2, Sobel): pinned bit-exactly
+ *     against cv2 4.13 (the third-party library the reference calls) in tests/.
+ *   - g2o Levenberg-Marquardt / Schur / Huber semantics: PARITY UNPINNED -- no g2o source or
+ *     binary exists in this environment; restated from the published algorithm and anchored on
+ *     the reference's call sites only.
+ *
+ * Determinism rules where the reference is under-determined: IEEE-754 without FMA contraction
+ * (-ffp-contract=off), cvRound = round-half-even, quadtree ties broken by node creation order,
+ * angle-histogram ties by (size desc, bin asc), unordered_map iteration replaced by ascending id.
+ */
+#ifndef PLP_ORACLE_H
+#define PLP_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- match/base.h:43-93 ------------------------------------------------------------ */
+unsigned orc_hamming_32(const uint8_t *a, const uint8_t *b);
+unsigned orc_hamming_64(const uint8_t *a, const uint8_t *b);
+void orc_hamming_matrix(const uint8_t *a, int na, const uint8_t *b, int nb, uint16_t *out);
+void orc_hamming_nn(const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *idx, uint16_t *dist);
+
+/* ---- match/angle_checker.h:86-175 -------------------------------------------------- */
+/* returns number of invalid matches written to invalid_out (capacity n) */
+int orc_angle_checker_invalid(const float *delta_angles, const int32_t *matches, int n,
+                              int histogram_length, int num_bins_thr, int32_t *invalid_out);
+int orc_angle_checker_valid(const float *delta_angles, const int32_t *matches, int n,
+                            int histogram_length, int num_bins_thr, int32_t *valid_out);
+
+/* ---- data/common.h:104-109, data/common.cc:205-313 ----------------------------------- */
+typedef struct orc_grid {
+    float min_x, min_y;
+    double inv_cell_width, inv_cell_height;
+    int32_t num_cols, num_rows;
+} orc_grid;
+int orc_get_cell_indices(const orc_grid *g, float x, float y, int *cx, int *cy);
+/* builds the grid over (x,y), then returns the indices in traversal order; returns count */
+int orc_get_keypoints_in_cell(const orc_grid *g, const float *x, const float *y,
+                              const int32_t *octave, int n, float ref_x, float ref_y, float margin,
+                              int min_level, int max_level, int32_t *indices_out);
+
+typedef struct orc_camera {
+    double fx, fy, cx, cy;
+    double focal_x_baseline;
+    double true_baseline;
+    float min_x, max_x, min_y, max_y;
+    int32_t setup_type;
+} orc_camera;
+/* camera/perspective.cc:190-209 */
+int orc_reproject_to_image(const orc_camera *cam, const double *rot_cw /*3x3 row-major*/,
+                           const double *trans_cw, const double *pos_w, double *reproj /*2*/,
+                           float *x_right);
+
+/* ---- match/projection.cc:37-121 ------------------------------------------------------ */
+unsigned orc_match_frame_and_landmarks(const orc_grid *g, int n, const float *x, const float *y,
+                                       const int32_t *octave, const float *x_right,
+                                       const uint8_t *desc, const uint8_t *claimed,
+                                       const float *scale_factors, int num_levels, int m,
+                                       const float *reproj_x, const float *reproj_y,
+                                       const float *q_x_right, const int32_t *scale_level,
+                                       const uint8_t *q_desc, const uint8_t *q_valid, float margin,
+                                       float lowe_ratio, int32_t *best_idx_out);
+
+/* ---- match/projection.cc:214-358 ----------------------------------------------------- */
+unsigned orc_match_current_and_last_frames(
+    const orc_grid *g, int n, const float *x, const float *y, const int32_t *octave,
+    const float *angle, const float *x_right, const uint8_t *desc, const uint8_t *claimed,
+    const float *scale_factors, int num_levels, const orc_camera *cam, const double *pose_cw_curr,
+    const double *pose_cw_last, int n_last, const double *pos_w, const int32_t *last_octave,
+    const float *last_angle, const uint8_t *last_desc, const uint8_t *last_valid, float margin,
+    int check_orientation, int32_t *matched_last_idx_out);
+
+/* ---- match/projection.cc:124-212 ----------------------------------------------------- */
+unsigned orc_match_frame_and_landmarks_line(int n, const float *sx, const float *sy,
+                                            const float *ex, const float *ey,
+                                            const int32_t *octave, const int32_t *ratio_level,
+                                            const uint8_t *desc, const uint8_t *claimed,
+                                            const float *scale_factors_lsd, int num_levels_lsd,
+                                            int m, const float *sp_x, const float *sp_y,
+                                            const float *ep_x, const float *ep_y,
+                                            const int32_t *scale_level, const uint8_t *q_desc,
+                                            const uint8_t *q_valid, float margin, float lowe_ratio,
+                                            int32_t *best_idx_out);
+
+/* ---- match/projection.cc:361-527 ----------------------------------------------------- */
+unsigned orc_match_current_and_last_frames_line(
+    int n, const float *sx, const float *sy, const float *ex, const float *ey,
+    const int32_t *octave, const float *x_right_sp, const float *x_right_ep, const uint8_t *desc,
+    const uint8_t *claimed, const float *scale_factors_lsd, int num_levels_lsd,
+    const orc_camera *cam, const double *pose_cw_curr, const double *pose_cw_last, int n_last,
+    const double *pos_w /*n_last x 6*/, const int32_t *last_octave, const uint8_t *last_desc,
+    const uint8_t *last_valid, float margin, int32_t *matched_last_idx_out);
+
+/* ---- match/robust.cc:257-385 --------------------------------------------------------- */
+unsigned orc_brute_force_match(const uint8_t *frm_desc, const float *frm_angle, int n_frm,
+                               const uint8_t *kf_desc, const float *kf_angle,
+                               const uint8_t *kf_valid, int n_kf, float lowe_ratio,
+                               int check_orientation, int32_t *matched_kf_idx_in_frm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,279 @@
+"""ctypes binding of libplpslam_b200.so -- mirrors the reference operator classes by name.
+
+Only marshals numpy arrays into the PODs of include/plpslam_b200.h.  No compute happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+
+class PlpError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _HERE / "libplpslam_b200.so"
+
+
+def declared_symbols() -> list[str]:
+    """Every PLP_API function declared in include/plpslam_b200.h."""
+    hdr = (_HERE.parent / "include" / "plpslam_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"PLP_API[^;{]*?\b(plp_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; fails loudly when it has not been built (no CPU fallback)."""
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not p.exists():
+            raise PlpError(
+                f"{p} is missing: build it with `python structure-plp-slam_b200/build.py` "
+                "(or __graft_entry__.build()); there is no CPU fallback"
+            )
+        _LIB = C.CDLL(str(p))
+        _LIB.plp_last_error.restype = C.c_char_p
+        _LIB.plp_ctx_stream.restype = C.c_void_p
+        _LIB.plp_ctx_launch_count.restype = C.c_uint64
+    return _LIB
+
+
+# ----------------------------------------------------------------------------- PODs
+class Grid(C.Structure):
+    _fields_ = [("min_x", C.c_float), ("min_y", C.c_float), ("inv_cell_width", C.c_double),
+                ("inv_cell_height", C.c_double), ("num_cols", C.c_int32), ("num_rows", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("focal_x_baseline", C.c_double), ("true_baseline", C.c_double),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("setup_type", C.c_int32)]
+
+
+_P = C.c_void_p
+
+
+class FramePoints(C.Structure):
+    _fields_ = [("n", C.c_int32), ("x", _P), ("y", _P), ("octave", _P), ("angle", _P), ("x_right", _P),
+                ("desc", _P), ("claimed", _P)]
+
+
+class FrameLines(C.Structure):
+    _fields_ = [("n", C.c_int32), ("sx", _P), ("sy", _P), ("ex", _P), ("ey", _P), ("octave", _P),
+                ("ratio_level", _P), ("x_right_sp", _P), ("x_right_ep", _P), ("desc", _P), ("claimed", _P)]
+
+
+class LandmarkQueries(C.Structure):
+    _fields_ = [("m", C.c_int32), ("reproj_x", _P), ("reproj_y", _P), ("x_right", _P), ("scale_level", _P),
+                ("desc", _P), ("valid", _P)]
+
+
+class LastFramePoints(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pos_w", _P), ("octave", _P), ("angle", _P), ("desc", _P), ("valid", _P)]
+
+
+class LineQueries(C.Structure):
+    _fields_ = [("m", C.c_int32), ("sp_x", _P), ("sp_y", _P), ("ep_x", _P), ("ep_y", _P), ("scale_level", _P),
+                ("desc", _P), ("valid", _P)]
+
+
+class LastFrameLines(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pos_w", _P), ("octave", _P), ("desc", _P), ("valid", _P)]
+
+
+# ----------------------------------------------------------------------------- helpers
+class _Keep:
+    """Keeps converted numpy arrays alive for the duration of a call."""
+
+    def __init__(self):
+        self.refs = []
+
+    def arr(self, a, dtype, allow_none=True):
+        if a is None:
+            if not allow_none:
+                raise PlpError("required array is None")
+            return None
+        a = np.ascontiguousarray(a, dtype=dtype)
+        self.refs.append(a)
+        return a.ctypes.data_as(_P)
+
+
+def make_grid(cols: int, rows: int, num_cols: int = 64, num_rows: int = 48, min_x=0.0, min_y=0.0,
+              max_x=None, max_y=None) -> Grid:
+    """camera::perspective ctor (camera/perspective.cc:53-56) for an undistorted camera."""
+    max_x = float(cols) if max_x is None else max_x
+    max_y = float(rows) if max_y is None else max_y
+    fmin_x, fmax_x = np.float32(min_x), np.float32(max_x)
+    fmin_y, fmax_y = np.float32(min_y), np.float32(max_y)
+    return Grid(float(fmin_x), float(fmin_y), float(num_cols) / float(np.float32(fmax_x - fmin_x)),
+                float(num_rows) / float(np.float32(fmax_y - fmin_y)), num_cols, num_rows)
+
+
+def make_camera(fx, fy, cx, cy, cols, rows, bf=-1.0, setup_type=0) -> Camera:
+    return Camera(fx, fy, cx, cy, bf, (bf / fx) if bf > 0 else -1.0, 0.0, float(cols), 0.0, float(rows), setup_type)
+
+
+class Context:
+    """One plp_ctx (device + stream).  Methods are named after the reference methods they replace."""
+
+    def __init__(self, device: int = 0):
+        self._lib = lib()
+        h = C.c_void_p()
+        self._h = None
+        self._check(self._lib.plp_ctx_create(C.c_int(device), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h is not None:
+            self._lib.plp_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status: int):
+        if status != 0:
+            raise PlpError(f"plp status {status}: {self._lib.plp_last_error().decode()}")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        self._check(self._lib.plp_ctx_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.plp_ctx_launch_count(self._h))
+
+    # ------------------------------------------------------------------ match/base.h
+    def hamming_matrix(self, a, b):
+        k = _Keep()
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.zeros((a.shape[0], b.shape[0]), np.uint16)
+        self._check(self._lib.plp_hamming_matrix(self._h, k.arr(a, np.uint8), C.c_int(a.shape[0]),
+                                                 k.arr(b, np.uint8), C.c_int(b.shape[0]), out.ctypes.data_as(_P)))
+        return out
+
+    def hamming_nn(self, query, train):
+        k = _Keep()
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        idx = np.zeros(q.shape[0], np.int32)
+        dist = np.zeros(q.shape[0], np.uint16)
+        self._check(self._lib.plp_hamming_nn(self._h, k.arr(q, np.uint8), C.c_int(q.shape[0]), k.arr(t, np.uint8),
+                                             C.c_int(t.shape[0]), idx.ctypes.data_as(_P), dist.ctypes.data_as(_P)))
+        return idx, dist
+
+    # ------------------------------------------------------------------ match::projection
+    @staticmethod
+    def _frame_points(k, x, y, octave, desc, angle=None, x_right=None, claimed=None):
+        n = len(x)
+        return FramePoints(n, k.arr(x, np.float32), k.arr(y, np.float32), k.arr(octave, np.int32),
+                           k.arr(angle, np.float32), k.arr(x_right, np.float32), k.arr(desc, np.uint8),
+                           k.arr(claimed, np.uint8))
+
+    def match_frame_and_landmarks(self, grid, scale_factors, frm, queries, margin, lowe_ratio=0.6):
+        """projection::match_frame_and_landmarks. frm/queries are dicts of arrays."""
+        k = _Keep()
+        fp = self._frame_points(k, frm["x"], frm["y"], frm["octave"], frm["desc"], frm.get("angle"),
+                                frm.get("x_right"), frm.get("claimed"))
+        m = len(queries["reproj_x"])
+        q = LandmarkQueries(m, k.arr(queries["reproj_x"], np.float32), k.arr(queries["reproj_y"], np.float32),
+                            k.arr(queries.get("x_right"), np.float32), k.arr(queries["scale_level"], np.int32),
+                            k.arr(queries["desc"], np.uint8), k.arr(queries.get("valid"), np.uint8))
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        best = np.full(m, -2, np.int32)
+        num = C.c_uint32(0)
+        self._check(self._lib.plp_match_frame_and_landmarks(
+            self._h, C.byref(fp), C.byref(grid), sf.ctypes.data_as(_P), C.c_int(len(sf)), C.byref(q),
+            C.c_float(margin), C.c_float(lowe_ratio), best.ctypes.data_as(_P), C.byref(num)))
+        return best, int(num.value)
+
+    def match_current_and_last_frames(self, grid, scale_factors, cam, curr, pose_cw_curr, pose_cw_last, last,
+                                      margin, check_orientation=True):
+        k = _Keep()
+        fp = self._frame_points(k, curr["x"], curr["y"], curr["octave"], curr["desc"], curr.get("angle"),
+                                curr.get("x_right"), curr.get("claimed"))
+        n_last = len(last["octave"])
+        lp = LastFramePoints(n_last, k.arr(last["pos_w"], np.float64), k.arr(last["octave"], np.int32),
+                             k.arr(last.get("angle"), np.float32), k.arr(last["desc"], np.uint8),
+                             k.arr(last.get("valid"), np.uint8))
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        Tc = np.ascontiguousarray(pose_cw_curr, np.float64).reshape(4, 4)
+        Tl = np.ascontiguousarray(pose_cw_last, np.float64).reshape(4, 4)
+        matched = np.full(fp.n, -2, np.int32)
+        num = C.c_uint32(0)
+        self._check(self._lib.plp_match_current_and_last_frames(
+            self._h, C.byref(fp), C.byref(grid), sf.ctypes.data_as(_P), C.c_int(len(sf)), C.byref(cam),
+            Tc.ctypes.data_as(_P), Tl.ctypes.data_as(_P), C.byref(lp), C.c_float(margin),
+            C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P), C.byref(num)))
+        return matched, int(num.value)
+
+    @staticmethod
+    def _frame_lines(k, f):
+        n = len(f["sx"])
+        return FrameLines(n, k.arr(f["sx"], np.float32), k.arr(f["sy"], np.float32), k.arr(f["ex"], np.float32),
+                          k.arr(f["ey"], np.float32), k.arr(f["octave"], np.int32),
+                          k.arr(f.get("ratio_level"), np.int32), k.arr(f.get("x_right_sp"), np.float32),
+                          k.arr(f.get("x_right_ep"), np.float32), k.arr(f["desc"], np.uint8),
+                          k.arr(f.get("claimed"), np.uint8))
+
+    def match_frame_and_landmarks_line(self, scale_factors_lsd, frm, queries, margin, lowe_ratio=0.6):
+        k = _Keep()
+        fl = self._frame_lines(k, frm)
+        m = len(queries["sp_x"])
+        q = LineQueries(m, k.arr(queries["sp_x"], np.float32), k.arr(queries["sp_y"], np.float32),
+                        k.arr(queries["ep_x"], np.float32), k.arr(queries["ep_y"], np.float32),
+                        k.arr(queries["scale_level"], np.int32), k.arr(queries["desc"], np.uint8),
+                        k.arr(queries.get("valid"), np.uint8))
+        sf = np.ascontiguousarray(scale_factors_lsd, np.float32)
+        best = np.full(m, -2, np.int32)
+        num = C.c_uint32(0)
+        self._check(self._lib.plp_match_frame_and_landmarks_line(
+            self._h, C.byref(fl), sf.ctypes.data_as(_P), C.c_int(len(sf)), C.byref(q), C.c_float(margin),
+            C.c_float(lowe_ratio), best.ctypes.data_as(_P), C.byref(num)))
+        return best, int(num.value)
+
+    def match_current_and_last_frames_line(self, scale_factors_lsd, cam, curr, pose_cw_curr, pose_cw_last, last,
+                                           margin):
+        k = _Keep()
+        fl = self._frame_lines(k, curr)
+        n_last = len(last["octave"])
+        ll = LastFrameLines(n_last, k.arr(last["pos_w"], np.float64), k.arr(last["octave"], np.int32),
+                            k.arr(last["desc"], np.uint8), k.arr(last.get("valid"), np.uint8))
+        sf = np.ascontiguousarray(scale_factors_lsd, np.float32)
+        Tc = np.ascontiguousarray(pose_cw_curr, np.float64).reshape(4, 4)
+        Tl = np.ascontiguousarray(pose_cw_last, np.float64).reshape(4, 4)
+        matched = np.full(fl.n, -2, np.int32)
+        num = C.c_uint32(0)
+        self._check(self._lib.plp_match_current_and_last_frames_line(
+            self._h, C.byref(fl), sf.ctypes.data_as(_P), C.c_int(len(sf)), C.byref(cam), Tc.ctypes.data_as(_P),
+            Tl.ctypes.data_as(_P), C.byref(ll), C.c_float(margin), matched.ctypes.data_as(_P), C.byref(num)))
+        return matched, int(num.value)
+
+    # ------------------------------------------------------------------ match::robust
+    def brute_force_match(self, frm_desc, frm_angle, kf_desc, kf_angle, kf_valid=None, lowe_ratio=0.8,
+                          check_orientation=False):
+        k = _Keep()
+        fd = np.ascontiguousarray(frm_desc, np.uint8).reshape(-1, 32)
+        kd = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32)
+        matched = np.full(fd.shape[0], -2, np.int32)
+        num = C.c_uint32(0)
+        self._check(self._lib.plp_match_brute_force(
+            self._h, k.arr(fd, np.uint8), k.arr(frm_angle, np.float32), C.c_int(fd.shape[0]), k.arr(kd, np.uint8),
+            k.arr(kf_angle, np.float32), k.arr(kf_valid, np.uint8), C.c_int(kd.shape[0]), C.c_float(lowe_ratio),
+            C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P), C.byref(num)))
+        return matched, int(num.value)

@@ -1,0 +1,115 @@
+// common.cuh -- context, error plumbing and small device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/plpslam_b200.h"
+
+namespace plp {
+
+// thread-local last error message (never throws across the C ABI)
+void set_error(const char *fmt, ...);
+
+struct ScratchBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace plp
+
+struct plp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    uint64_t launches = 0;  // kernels launched by this library on this context
+    // growable device scratch areas (index = purpose), never shrunk
+    plp::ScratchBuf scratch[8];
+    // growable pinned host staging area
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+namespace plp {
+
+plp_status ctx_scratch(plp_ctx *ctx, int slot, size_t bytes, void **out);
+plp_status ctx_pinned(plp_ctx *ctx, size_t bytes, void **out);
+
+#define PLP_CUDA_TRY(expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            plp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                        \
+            return PLP_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define PLP_TRY(expr)                     \
+    do {                                  \
+        plp_status _s = (expr);           \
+        if (_s != PLP_OK) return _s;      \
+    } while (0)
+
+#define PLP_REQUIRE(cond, msg)                                     \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            plp::set_error("invalid argument: %s (%s)", msg, #cond); \
+            return PLP_ERR_INVALID;                                \
+        }                                                          \
+    } while (0)
+
+// every kernel launch goes through this so gpu_launches can be reported honestly
+#define PLP_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+    do {                                                                         \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+        (ctx)->launches++;                                                       \
+    } while (0)
+
+#define PLP_CHECK_LAUNCH()                                                              \
+    do {                                                                                \
+        cudaError_t _e = cudaGetLastError();                                            \
+        if (_e != cudaSuccess) {                                                        \
+            plp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),  \
+                           __FILE__, __LINE__);                                         \
+            return PLP_ERR_CUDA;                                                        \
+        }                                                                               \
+    } while (0)
+
+// ---- device helpers -------------------------------------------------------
+
+// 256-bit Hamming distance between two descriptors held as 8 x u32
+__device__ __forceinline__ int hamming256(const uint32_t a[8], const uint32_t b[8]) {
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d += __popc(a[i] ^ b[i]);
+    return d;
+}
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0,
+                                          const uint4 b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// cvFloor / cvCeil / cvRound for float and double (OpenCV semantics: floor, ceil, round-half-even)
+__host__ __device__ __forceinline__ int cv_floor(double v) {
+    int i = (int)v;
+    return i - (i > v);
+}
+__host__ __device__ __forceinline__ int cv_ceil(double v) {
+    int i = (int)v;
+    return i + (i < v);
+}
+__device__ __forceinline__ int cv_round_f(float v) { return __float2int_rn(v); }
+__device__ __forceinline__ int cv_round_d(double v) { return __double2int_rn(v); }
+
+template <typename T>
+__host__ __device__ __forceinline__ T div_up(T a, T b) {
+    return (a + b - 1) / b;
+}
+
+}  // namespace plp

@@ -1,0 +1,149 @@
+// context.cu -- plp_ctx lifetime, error string, device-memory helpers of the C ABI.
+#include "common.cuh"
+
+namespace plp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+plp_status ctx_scratch(plp_ctx *ctx, int slot, size_t bytes, void **out) {
+    ScratchBuf &b = ctx->scratch[slot];
+    if (b.bytes < bytes) {
+        if (b.ptr) {
+            PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            PLP_CUDA_TRY(cudaFree(b.ptr));
+            b.ptr = nullptr;
+            b.bytes = 0;
+        }
+        size_t want = bytes + bytes / 2 + 256;
+        PLP_CUDA_TRY(cudaMalloc(&b.ptr, want));
+        b.bytes = want;
+    }
+    *out = b.ptr;
+    return PLP_OK;
+}
+
+plp_status ctx_pinned(plp_ctx *ctx, size_t bytes, void **out) {
+    if (ctx->pinned_bytes < bytes) {
+        if (ctx->pinned) {
+            PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            PLP_CUDA_TRY(cudaFreeHost(ctx->pinned));
+            ctx->pinned = nullptr;
+            ctx->pinned_bytes = 0;
+        }
+        size_t want = bytes + bytes / 2 + 256;
+        PLP_CUDA_TRY(cudaMallocHost(&ctx->pinned, want));
+        ctx->pinned_bytes = want;
+    }
+    *out = ctx->pinned;
+    return PLP_OK;
+}
+
+}  // namespace plp
+
+extern "C" {
+
+const char *plp_last_error(void) { return plp::g_err; }
+
+int plp_version(void) { return 100; }
+
+int plp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+plp_status plp_ctx_create(int device, plp_ctx **out) {
+    PLP_REQUIRE(out != nullptr, "out");
+    *out = nullptr;
+    int n = plp_device_count();
+    if (n <= 0 || device < 0 || device >= n) {
+        plp::set_error("no usable CUDA device (count=%d, requested=%d): this library has no CPU fallback", n,
+                       device);
+        return PLP_ERR_NO_DEVICE;
+    }
+    PLP_CUDA_TRY(cudaSetDevice(device));
+    plp_ctx *c = new plp_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    PLP_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    PLP_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return PLP_OK;
+}
+
+void plp_ctx_destroy(plp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->scratch)
+        if (b.ptr) cudaFree(b.ptr);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+plp_status plp_ctx_sync(plp_ctx *ctx) {
+    PLP_REQUIRE(ctx != nullptr, "ctx");
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PLP_OK;
+}
+
+void *plp_ctx_stream(plp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+uint64_t plp_ctx_launch_count(plp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+plp_status plp_dev_alloc(plp_ctx *ctx, size_t bytes, void **out) {
+    PLP_REQUIRE(ctx != nullptr && out != nullptr, "ctx/out");
+    PLP_CUDA_TRY(cudaSetDevice(ctx->device));
+    PLP_CUDA_TRY(cudaMalloc(out, bytes ? bytes : 1));
+    return PLP_OK;
+}
+
+plp_status plp_dev_free(plp_ctx *ctx, void *ptr) {
+    PLP_REQUIRE(ctx != nullptr, "ctx");
+    if (ptr) {
+        PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        PLP_CUDA_TRY(cudaFree(ptr));
+    }
+    return PLP_OK;
+}
+
+plp_status plp_dev_upload(plp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    PLP_REQUIRE(ctx != nullptr, "ctx");
+    if (bytes == 0) return PLP_OK;
+    PLP_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PLP_OK;
+}
+
+plp_status plp_dev_download(plp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    PLP_REQUIRE(ctx != nullptr, "ctx");
+    if (bytes == 0) return PLP_OK;
+    PLP_CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PLP_OK;
+}
+
+plp_status plp_host_alloc_pinned(size_t bytes, void **out) {
+    PLP_REQUIRE(out != nullptr, "out");
+    PLP_CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+    return PLP_OK;
+}
+
+plp_status plp_host_free_pinned(void *ptr) {
+    if (ptr) PLP_CUDA_TRY(cudaFreeHost(ptr));
+    return PLP_OK;
+}
+
+}  // extern "C"

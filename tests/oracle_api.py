@@ -1,0 +1,209 @@
+"""ctypes wrapper of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY (never imported by the product)."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+_P = C.c_void_p
+
+
+class OGrid(C.Structure):
+    _fields_ = [("min_x", C.c_float), ("min_y", C.c_float), ("inv_cell_width", C.c_double),
+                ("inv_cell_height", C.c_double), ("num_cols", C.c_int32), ("num_rows", C.c_int32)]
+
+
+class OCamera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("focal_x_baseline", C.c_double), ("true_baseline", C.c_double),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("setup_type", C.c_int32)]
+
+
+def build_oracle():
+    srcs = list(ORACLE_DIR.glob("*.cc")) + list(ORACLE_DIR.glob("*.h")) + list(ORACLE_DIR.glob("*.inc"))
+    so = ORACLE_DIR / "liboracle.so"
+    if so.exists() and all(so.stat().st_mtime >= s.stat().st_mtime for s in srcs):
+        return so
+    res = subprocess.run(["make", "-C", str(ORACLE_DIR), "-j8"], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+    return so
+
+
+def _a(x, dt):
+    if x is None:
+        return None, None
+    x = np.ascontiguousarray(x, dt)
+    return x, x.ctypes.data_as(_P)
+
+
+def as_grid(g) -> OGrid:
+    return OGrid(g.min_x, g.min_y, g.inv_cell_width, g.inv_cell_height, g.num_cols, g.num_rows)
+
+
+def as_camera(c) -> OCamera:
+    return OCamera(c.fx, c.fy, c.cx, c.cy, c.focal_x_baseline, c.true_baseline, c.min_x, c.max_x, c.min_y, c.max_y,
+                   c.setup_type)
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(str(build_oracle()))
+        L = self.lib
+        for f in ("orc_hamming_32", "orc_hamming_64", "orc_match_frame_and_landmarks",
+                  "orc_match_current_and_last_frames", "orc_match_frame_and_landmarks_line",
+                  "orc_match_current_and_last_frames_line", "orc_brute_force_match"):
+            getattr(L, f).restype = C.c_uint
+
+    # ---- match/base.h
+    def hamming_32(self, a, b):
+        a, pa = _a(a, np.uint8)
+        b, pb = _a(b, np.uint8)
+        return int(self.lib.orc_hamming_32(pa, pb))
+
+    def hamming_64(self, a, b):
+        a, pa = _a(a, np.uint8)
+        b, pb = _a(b, np.uint8)
+        return int(self.lib.orc_hamming_64(pa, pb))
+
+    def hamming_matrix(self, a, b):
+        a, pa = _a(np.asarray(a).reshape(-1, 32), np.uint8)
+        b, pb = _a(np.asarray(b).reshape(-1, 32), np.uint8)
+        out = np.zeros((a.shape[0], b.shape[0]), np.uint16)
+        self.lib.orc_hamming_matrix(pa, C.c_int(a.shape[0]), pb, C.c_int(b.shape[0]), out.ctypes.data_as(_P))
+        return out
+
+    def hamming_nn(self, q, t):
+        q, pq = _a(np.asarray(q).reshape(-1, 32), np.uint8)
+        t, pt = _a(np.asarray(t).reshape(-1, 32), np.uint8)
+        idx = np.zeros(q.shape[0], np.int32)
+        dist = np.zeros(q.shape[0], np.uint16)
+        self.lib.orc_hamming_nn(pq, C.c_int(q.shape[0]), pt, C.c_int(t.shape[0]), idx.ctypes.data_as(_P),
+                                dist.ctypes.data_as(_P))
+        return idx, dist
+
+    # ---- angle checker
+    def angle_checker(self, deltas, matches, hist_len=30, num_bins=3, valid=False):
+        d, pd = _a(deltas, np.float32)
+        m, pm = _a(matches, np.int32)
+        out = np.zeros(len(d), np.int32)
+        fn = self.lib.orc_angle_checker_valid if valid else self.lib.orc_angle_checker_invalid
+        n = fn(pd, pm, C.c_int(len(d)), C.c_int(hist_len), C.c_int(num_bins), out.ctypes.data_as(_P))
+        return out[:n].copy()
+
+    # ---- grid
+    def get_cell_indices(self, grid, x, y):
+        cx, cy = C.c_int(), C.c_int()
+        ok = self.lib.orc_get_cell_indices(C.byref(as_grid(grid)), C.c_float(x), C.c_float(y), C.byref(cx), C.byref(cy))
+        return bool(ok), cx.value, cy.value
+
+    def get_keypoints_in_cell(self, grid, x, y, octave, ref_x, ref_y, margin, min_level, max_level):
+        x, px = _a(x, np.float32)
+        y, py = _a(y, np.float32)
+        o, po = _a(octave, np.int32)
+        out = np.zeros(len(x), np.int32)
+        n = self.lib.orc_get_keypoints_in_cell(C.byref(as_grid(grid)), px, py, po, C.c_int(len(x)), C.c_float(ref_x),
+                                               C.c_float(ref_y), C.c_float(margin), C.c_int(min_level),
+                                               C.c_int(max_level), out.ctypes.data_as(_P))
+        return out[:n].copy()
+
+    # ---- projection matchers
+    def match_frame_and_landmarks(self, grid, scale_factors, frm, q, margin, lowe_ratio=0.6):
+        keep = []
+
+        def A(v, dt):
+            arr, p = _a(v, dt)
+            keep.append(arr)
+            return p
+        n, m = len(frm["x"]), len(q["reproj_x"])
+        best = np.full(m, -2, np.int32)
+        sf, psf = _a(scale_factors, np.float32)
+        num = self.lib.orc_match_frame_and_landmarks(
+            C.byref(as_grid(grid)), C.c_int(n), A(frm["x"], np.float32), A(frm["y"], np.float32),
+            A(frm["octave"], np.int32), A(frm.get("x_right"), np.float32), A(frm["desc"], np.uint8),
+            A(frm.get("claimed"), np.uint8), psf, C.c_int(len(sf)), C.c_int(m), A(q["reproj_x"], np.float32),
+            A(q["reproj_y"], np.float32), A(q.get("x_right", np.zeros(m)), np.float32), A(q["scale_level"], np.int32),
+            A(q["desc"], np.uint8), A(q.get("valid"), np.uint8), C.c_float(margin), C.c_float(lowe_ratio),
+            best.ctypes.data_as(_P))
+        return best, int(num)
+
+    def match_current_and_last_frames(self, grid, scale_factors, cam, curr, Tc, Tl, last, margin,
+                                      check_orientation=True):
+        keep = []
+
+        def A(v, dt):
+            arr, p = _a(v, dt)
+            keep.append(arr)
+            return p
+        n, m = len(curr["x"]), len(last["octave"])
+        matched = np.full(n, -2, np.int32)
+        sf, psf = _a(scale_factors, np.float32)
+        num = self.lib.orc_match_current_and_last_frames(
+            C.byref(as_grid(grid)), C.c_int(n), A(curr["x"], np.float32), A(curr["y"], np.float32),
+            A(curr["octave"], np.int32), A(curr.get("angle"), np.float32), A(curr.get("x_right"), np.float32),
+            A(curr["desc"], np.uint8), A(curr.get("claimed"), np.uint8), psf, C.c_int(len(sf)),
+            C.byref(as_camera(cam)), A(np.asarray(Tc).reshape(16), np.float64), A(np.asarray(Tl).reshape(16), np.float64),
+            C.c_int(m), A(last["pos_w"], np.float64), A(last["octave"], np.int32), A(last.get("angle"), np.float32),
+            A(last["desc"], np.uint8), A(last.get("valid"), np.uint8), C.c_float(margin),
+            C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P))
+        return matched, int(num)
+
+    def match_frame_and_landmarks_line(self, scale_factors, frm, q, margin, lowe_ratio=0.6):
+        keep = []
+
+        def A(v, dt):
+            arr, p = _a(v, dt)
+            keep.append(arr)
+            return p
+        n, m = len(frm["sx"]), len(q["sp_x"])
+        best = np.full(m, -2, np.int32)
+        sf, psf = _a(scale_factors, np.float32)
+        rl = frm.get("ratio_level")
+        if rl is None:
+            rl = frm["octave"]
+        num = self.lib.orc_match_frame_and_landmarks_line(
+            C.c_int(n), A(frm["sx"], np.float32), A(frm["sy"], np.float32), A(frm["ex"], np.float32),
+            A(frm["ey"], np.float32), A(frm["octave"], np.int32), A(rl, np.int32), A(frm["desc"], np.uint8),
+            A(frm.get("claimed"), np.uint8), psf, C.c_int(len(sf)), C.c_int(m), A(q["sp_x"], np.float32),
+            A(q["sp_y"], np.float32), A(q["ep_x"], np.float32), A(q["ep_y"], np.float32),
+            A(q["scale_level"], np.int32), A(q["desc"], np.uint8), A(q.get("valid"), np.uint8), C.c_float(margin),
+            C.c_float(lowe_ratio), best.ctypes.data_as(_P))
+        return best, int(num)
+
+    def match_current_and_last_frames_line(self, scale_factors, cam, curr, Tc, Tl, last, margin):
+        keep = []
+
+        def A(v, dt):
+            arr, p = _a(v, dt)
+            keep.append(arr)
+            return p
+        n, m = len(curr["sx"]), len(last["octave"])
+        matched = np.full(n, -2, np.int32)
+        sf, psf = _a(scale_factors, np.float32)
+        num = self.lib.orc_match_current_and_last_frames_line(
+            C.c_int(n), A(curr["sx"], np.float32), A(curr["sy"], np.float32), A(curr["ex"], np.float32),
+            A(curr["ey"], np.float32), A(curr["octave"], np.int32), A(curr.get("x_right_sp"), np.float32),
+            A(curr.get("x_right_ep"), np.float32), A(curr["desc"], np.uint8), A(curr.get("claimed"), np.uint8), psf,
+            C.c_int(len(sf)), C.byref(as_camera(cam)), A(np.asarray(Tc).reshape(16), np.float64),
+            A(np.asarray(Tl).reshape(16), np.float64), C.c_int(m), A(last["pos_w"], np.float64),
+            A(last["octave"], np.int32), A(last["desc"], np.uint8), A(last.get("valid"), np.uint8), C.c_float(margin),
+            matched.ctypes.data_as(_P))
+        return matched, int(num)
+
+    def brute_force_match(self, frm_desc, frm_angle, kf_desc, kf_angle, kf_valid=None, lowe_ratio=0.8,
+                          check_orientation=False):
+        fd, pfd = _a(np.asarray(frm_desc).reshape(-1, 32), np.uint8)
+        kd, pkd = _a(np.asarray(kf_desc).reshape(-1, 32), np.uint8)
+        fa, pfa = _a(frm_angle, np.float32)
+        ka, pka = _a(kf_angle, np.float32)
+        kv, pkv = _a(kf_valid, np.uint8)
+        matched = np.full(fd.shape[0], -2, np.int32)
+        num = self.lib.orc_brute_force_match(pfd, pfa, C.c_int(fd.shape[0]), pkd, pka, pkv, C.c_int(kd.shape[0]),
+                                             C.c_float(lowe_ratio), C.c_int(1 if check_orientation else 0),
+                                             matched.ctypes.data_as(_P))
+        return matched, int(num)

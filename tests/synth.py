@@ -1,0 +1,185 @@
+"""Seeded synthetic inputs shared by the parity tests and bench.py (no reference data needed)."""
+from __future__ import annotations
+
+import numpy as np
+
+FX, FY, CX, CY = 535.4, 539.2, 320.1, 247.6  # TUM fr3 intrinsics (example/tum_rgbd/TUM_RGBD_mono_3.yaml)
+COLS, ROWS = 640, 480
+BF = 47.906
+
+
+def scale_factors(num_levels=8, sf=1.2):
+    out = np.ones(num_levels, np.float32)
+    for i in range(1, num_levels):
+        out[i] = np.float32(sf) * out[i - 1]
+    return out
+
+
+def rand_desc(rng, n):
+    return rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+
+
+def flip_bits(rng, desc, nbits):
+    """Flip `nbits` random bits (per row) of 32-byte descriptors."""
+    out = desc.copy()
+    n = desc.shape[0]
+    for i in range(n):
+        k = int(nbits[i]) if np.ndim(nbits) else int(nbits)
+        if k <= 0:
+            continue
+        pos = rng.choice(256, size=k, replace=False)
+        for p in pos:
+            out[i, p >> 3] ^= np.uint8(1 << (p & 7))
+    return out
+
+
+def so3_exp(w):
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th**2 * (K @ K)
+
+
+def make_pose(rng, rot_sigma=0.02, trans_sigma=0.05):
+    T = np.eye(4)
+    T[:3, :3] = so3_exp(rng.normal(0, rot_sigma, 3))
+    T[:3, 3] = rng.normal(0, trans_sigma, 3)
+    return T
+
+
+def project(T, X, fx=FX, fy=FY, cx=CX, cy=CY):
+    Xc = X @ T[:3, :3].T + T[:3, 3]
+    z = Xc[:, 2]
+    return np.stack([fx * Xc[:, 0] / z + cx, fy * Xc[:, 1] / z + cy], 1), z
+
+
+def make_tracking_scene(seed, n_last=1000, n_extra=300, stereo=False, num_levels=8, dup_frac=0.15):
+    """A last frame with landmarks and a current frame that re-observes most of them.
+
+    Returns (curr, last, Tc, Tl): dicts in the layout of Context.match_current_and_last_frames.
+    Keypoint coordinates are level-grid values (integer * scale factor) like real ORB output, and a
+    fraction of current keypoints are near-duplicates so that claims/ties actually occur.
+    """
+    rng = np.random.default_rng(seed)
+    sf = scale_factors(num_levels)
+    Tl = np.eye(4)
+    Tc = make_pose(rng, 0.01, 0.03)
+    X = np.stack([rng.uniform(-4, 4, n_last), rng.uniform(-3, 3, n_last), rng.uniform(2, 12, n_last)], 1)
+    last_oct = rng.integers(0, num_levels, n_last).astype(np.int32)
+    last_desc = rand_desc(rng, n_last)
+    last_angle = rng.uniform(0, 360, n_last).astype(np.float32)
+    last_valid = (rng.random(n_last) > 0.1).astype(np.uint8)
+
+    uv, z = project(Tc, X)
+    # current keypoints: re-observations (with pixel noise, on the level grid) + duplicates + clutter
+    oct_c = np.clip(last_oct + rng.integers(-1, 2, n_last), 0, num_levels - 1).astype(np.int32)
+    noise = rng.normal(0, 1.5, (n_last, 2)) * sf[oct_c][:, None]
+    pts = uv + noise
+    s = sf[oct_c][:, None].astype(np.float32)
+    pts = (np.round(pts / s) * s).astype(np.float32)
+    desc_c = flip_bits(rng, last_desc, rng.integers(5, 60, n_last))
+    ang_c = (last_angle + rng.normal(0, 4, n_last)).astype(np.float32) % np.float32(360)
+    # a few wildly rotated ones to exercise the orientation histogram
+    wild = rng.random(n_last) < 0.08
+    ang_c[wild] = rng.uniform(0, 360, wild.sum()).astype(np.float32)
+    keep = rng.random(n_last) > 0.15
+    xs, ys, octs, descs, angs = [pts[keep, 0]], [pts[keep, 1]], [oct_c[keep]], [desc_c[keep]], [ang_c[keep]]
+    # duplicates: same cell, same or near-equal descriptors (ties on distance!)
+    nd = int(dup_frac * keep.sum())
+    src = rng.choice(np.nonzero(keep)[0], nd, replace=False)
+    dpts = pts[src] + (rng.integers(-2, 3, (nd, 2)) * sf[oct_c[src]][:, None]).astype(np.float32)
+    ddesc = desc_c[src].copy()
+    mod = rng.random(nd) < 0.5
+    ddesc[mod] = flip_bits(rng, ddesc[mod], rng.integers(1, 4, mod.sum()))
+    xs.append(dpts[:, 0]); ys.append(dpts[:, 1]); octs.append(oct_c[src]); descs.append(ddesc); angs.append(ang_c[src])
+    # clutter
+    xs.append(rng.uniform(-5, COLS + 5, n_extra).astype(np.float32))
+    ys.append(rng.uniform(-5, ROWS + 5, n_extra).astype(np.float32))
+    octs.append(rng.integers(0, num_levels, n_extra).astype(np.int32))
+    descs.append(rand_desc(rng, n_extra))
+    angs.append(rng.uniform(0, 360, n_extra).astype(np.float32))
+    x = np.concatenate(xs).astype(np.float32)
+    y = np.concatenate(ys).astype(np.float32)
+    perm = rng.permutation(len(x))
+    curr = dict(x=x[perm], y=y[perm], octave=np.concatenate(octs)[perm].astype(np.int32),
+                desc=np.concatenate(descs)[perm], angle=np.concatenate(angs)[perm].astype(np.float32))
+    n = len(x)
+    curr["claimed"] = (rng.random(n) < 0.05).astype(np.uint8)
+    if stereo:
+        xr = np.full(n, -1.0, np.float32)
+        has = rng.random(n) < 0.7
+        xr[has] = (curr["x"][has] - rng.uniform(2, 40, has.sum())).astype(np.float32)
+        curr["x_right"] = xr
+    last = dict(pos_w=X, octave=last_oct, angle=last_angle, desc=last_desc, valid=last_valid)
+    return curr, last, Tc, Tl
+
+
+def make_landmark_queries(seed, curr, m=1500, num_levels=8):
+    """Local-map queries for match_frame_and_landmarks built around existing keypoints."""
+    rng = np.random.default_rng(seed + 7919)
+    sf = scale_factors(num_levels)
+    n = len(curr["x"])
+    src = rng.integers(0, n, m)
+    lvl = np.clip(curr["octave"][src] + rng.integers(0, 2, m), 0, num_levels - 1).astype(np.int32)
+    rx = (curr["x"][src] + rng.normal(0, 2.0, m) * sf[lvl]).astype(np.float32)
+    ry = (curr["y"][src] + rng.normal(0, 2.0, m) * sf[lvl]).astype(np.float32)
+    desc = flip_bits(rng, curr["desc"][src], rng.integers(0, 70, m))
+    q = dict(reproj_x=rx, reproj_y=ry, scale_level=lvl, desc=desc, valid=(rng.random(m) > 0.1).astype(np.uint8))
+    if "x_right" in curr:
+        q["x_right"] = (rx - rng.uniform(2, 40, m)).astype(np.float32)
+    return q
+
+
+def make_line_scene(seed, n_last=200, n_extra=60, num_levels=1):
+    """Keylines for the *_line matchers."""
+    rng = np.random.default_rng(seed)
+    Tl = np.eye(4)
+    Tc = make_pose(rng, 0.01, 0.03)
+    P0 = np.stack([rng.uniform(-4, 4, n_last), rng.uniform(-3, 3, n_last), rng.uniform(2, 10, n_last)], 1)
+    d = rng.normal(0, 1, (n_last, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    P1 = P0 + d * rng.uniform(0.5, 3.0, (n_last, 1))
+    # push a few endpoints behind the camera / out of the image
+    far = rng.random(n_last) < 0.1
+    P1[far, 2] -= 15
+    pos_w = np.concatenate([P0, P1], 1)
+    last_desc = rand_desc(rng, n_last)
+    last = dict(pos_w=pos_w, octave=np.zeros(n_last, np.int32), desc=last_desc,
+                valid=(rng.random(n_last) > 0.1).astype(np.uint8))
+    a, _ = project(Tc, P0)
+    b, _ = project(Tc, P1)
+    keep = rng.random(n_last) > 0.2
+    sx = a[keep, 0] + rng.normal(0, 1.0, keep.sum())
+    sy = a[keep, 1] + rng.normal(0, 1.0, keep.sum())
+    ex = b[keep, 0] + rng.normal(0, 1.0, keep.sum())
+    ey = b[keep, 1] + rng.normal(0, 1.0, keep.sum())
+    desc = flip_bits(rng, last_desc[keep], rng.integers(5, 60, keep.sum()))
+    # duplicates
+    nd = keep.sum() // 5
+    src = rng.integers(0, keep.sum(), nd)
+    sx = np.concatenate([sx, sx[src] + rng.normal(0, 0.5, nd), rng.uniform(0, COLS, n_extra)])
+    sy = np.concatenate([sy, sy[src] + rng.normal(0, 0.5, nd), rng.uniform(0, ROWS, n_extra)])
+    ex = np.concatenate([ex, ex[src] + rng.normal(0, 0.5, nd), rng.uniform(0, COLS, n_extra)])
+    ey = np.concatenate([ey, ey[src] + rng.normal(0, 0.5, nd), rng.uniform(0, ROWS, n_extra)])
+    desc = np.concatenate([desc, desc[src], rand_desc(rng, n_extra)])
+    n = len(sx)
+    perm = rng.permutation(n)
+    curr = dict(sx=sx[perm].astype(np.float32), sy=sy[perm].astype(np.float32), ex=ex[perm].astype(np.float32),
+                ey=ey[perm].astype(np.float32), octave=np.zeros(n, np.int32), desc=desc[perm],
+                claimed=(rng.random(n) < 0.05).astype(np.uint8),
+                ratio_level=rng.integers(0, 3, n).astype(np.int32))
+    return curr, last, Tc, Tl
+
+
+def make_line_queries(seed, curr, m=300):
+    rng = np.random.default_rng(seed + 104729)
+    n = len(curr["sx"])
+    src = rng.integers(0, n, m)
+    q = dict(sp_x=(curr["sx"][src] + rng.normal(0, 1.5, m)).astype(np.float32),
+             sp_y=(curr["sy"][src] + rng.normal(0, 1.5, m)).astype(np.float32),
+             ep_x=(curr["ex"][src] + rng.normal(0, 1.5, m)).astype(np.float32),
+             ep_y=(curr["ey"][src] + rng.normal(0, 1.5, m)).astype(np.float32),
+             scale_level=np.zeros(m, np.int32), desc=flip_bits(rng, curr["desc"][src], rng.integers(0, 70, m)),
+             valid=(rng.random(m) > 0.1).astype(np.uint8))
+    return q
