@@ -24,6 +24,7 @@
 #define PLP_ORACLE_H
 #include <stdint.h>
 #include <stddef.h>
+#include "orb.h"
 
 #ifdef __cplusplus
 extern "C" {

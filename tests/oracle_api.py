@@ -207,3 +207,162 @@ class Oracle:
                                              C.c_float(lowe_ratio), C.c_int(1 if check_orientation else 0),
                                              matched.ctypes.data_as(_P))
         return matched, int(num)
+
+
+# ======================================================================== ORB (oracle/orb.cc)
+class OKeyPoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+
+class OOrbParams(C.Structure):
+    _fields_ = [("max_num_keypts", C.c_uint32), ("scale_factor", C.c_float), ("num_levels", C.c_uint32),
+                ("ini_fast_thr", C.c_uint32), ("min_fast_thr", C.c_uint32)]
+
+
+def orb_params(max_kp=1000, sf=1.2, levels=8, ini=20, mn=7):
+    return OOrbParams(max_kp, sf, levels, ini, mn)
+
+
+def _orb_init(self):
+    L = self.lib
+    L.orc_fast_atan2.restype = C.c_float
+    L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+    L.orc_util_cos.restype = C.c_float
+    L.orc_util_cos.argtypes = [C.c_float]
+    L.orc_util_sin.restype = C.c_float
+    L.orc_util_sin.argtypes = [C.c_float]
+    L.orc_orb_ic_angle.restype = C.c_float
+
+
+def _resize_linear(self, src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    self.lib.orc_resize_linear(src.ctypes.data_as(_P), C.c_int(src.shape[1]), C.c_int(src.shape[0]),
+                               C.c_int(src.strides[0]), dst.ctypes.data_as(_P), C.c_int(dw), C.c_int(dh), C.c_int(dw))
+    return dst
+
+
+def _fast(self, img, thr, nonmax=True):
+    """cv::FAST on an ROI given as a (possibly strided) uint8 2-D view."""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    cap = img.shape[0] * img.shape[1]
+    out = np.zeros(max(cap, 1), KP_DTYPE)
+    n = self.lib.orc_fast9_16(C.c_void_p(img.ctypes.data), C.c_int(img.shape[1]), C.c_int(img.shape[0]),
+                              C.c_int(img.strides[0]), C.c_int(thr), C.c_int(1 if nonmax else 0),
+                              out.ctypes.data_as(_P), C.c_int(cap))
+    return out[:n].copy()
+
+
+def _blur7(self, img):
+    img = np.ascontiguousarray(img, np.uint8)
+    dst = np.zeros_like(img)
+    self.lib.orc_gaussian_blur_7x7(img.ctypes.data_as(_P), C.c_int(img.shape[1]), C.c_int(img.shape[0]),
+                                   C.c_int(img.shape[1]), dst.ctypes.data_as(_P), C.c_int(img.shape[1]))
+    return dst
+
+
+def _blur5(self, img):
+    img = np.ascontiguousarray(img, np.uint8)
+    dst = np.zeros_like(img)
+    self.lib.orc_gaussian_blur_5x5(img.ctypes.data_as(_P), C.c_int(img.shape[1]), C.c_int(img.shape[0]),
+                                   C.c_int(img.shape[1]), dst.ctypes.data_as(_P), C.c_int(img.shape[1]))
+    return dst
+
+
+def _orb_tables(self, p):
+    L = p.num_levels
+    sf, isf, ls, ils = (np.zeros(L, np.float32) for _ in range(4))
+    nk = np.zeros(L, np.uint32)
+    um = np.zeros(16, np.int32)
+    self.lib.orc_orb_tables(C.byref(p), sf.ctypes.data_as(_P), isf.ctypes.data_as(_P), ls.ctypes.data_as(_P),
+                            ils.ctypes.data_as(_P), nk.ctypes.data_as(_P), um.ctypes.data_as(_P))
+    return dict(scale_factors=sf, inv_scale_factors=isf, level_sigma_sq=ls, inv_level_sigma_sq=ils,
+                num_keypts_per_level=nk, u_max=um)
+
+
+def _orb_level_sizes(self, p, rows, cols):
+    w = np.zeros(p.num_levels, np.int32)
+    h = np.zeros(p.num_levels, np.int32)
+    self.lib.orc_orb_level_sizes(C.byref(p), C.c_int(rows), C.c_int(cols), w.ctypes.data_as(_P), h.ctypes.data_as(_P))
+    return w, h
+
+
+def _orb_distribute(self, p, cands, min_x, max_x, min_y, max_y, num_keypts):
+    cands = np.ascontiguousarray(cands, KP_DTYPE)
+    out = np.zeros(max(len(cands), 1), KP_DTYPE)
+    n = self.lib.orc_orb_distribute(C.byref(p), cands.ctypes.data_as(_P), C.c_int(len(cands)), C.c_int(min_x),
+                                    C.c_int(max_x), C.c_int(min_y), C.c_int(max_y), C.c_uint(num_keypts),
+                                    out.ctypes.data_as(_P))
+    return out[:n].copy()
+
+
+def _orb_ic_angle(self, p, img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    return float(self.lib.orc_orb_ic_angle(C.byref(p), img.ctypes.data_as(_P), C.c_int(img.shape[1]),
+                                           C.c_int(img.shape[0]), C.c_float(x), C.c_float(y)))
+
+
+def _orb_describe(self, p, blurred, kp):
+    blurred = np.ascontiguousarray(blurred, np.uint8)
+    k = np.ascontiguousarray(kp, KP_DTYPE).reshape(1)
+    d = np.zeros(32, np.uint8)
+    self.lib.orc_orb_describe(C.byref(p), blurred.ctypes.data_as(_P), C.c_int(blurred.shape[1]),
+                              C.c_int(blurred.shape[0]), k.ctypes.data_as(_P), d.ctypes.data_as(_P))
+    return d
+
+
+def _orb_extract(self, p, img, mask=None, debug=False):
+    img = np.ascontiguousarray(img, np.uint8)
+    rows, cols = img.shape
+    cap = int(p.max_num_keypts) * 2 + 64
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    w, h = self.orb_level_sizes(p, rows, cols)
+    pyr = np.zeros(int((w.astype(np.int64) * h).sum()), np.uint8)
+    cands_cap = 400000
+    cands = np.zeros(cands_cap if debug else 1, KP_DTYPE)
+    cpl = np.zeros(p.num_levels, np.int32)
+    kpl = np.zeros(p.num_levels, np.int32)
+    mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    n = self.lib.orc_orb_extract(C.byref(p), img.ctypes.data_as(_P), C.c_int(rows), C.c_int(cols), C.c_int(cols),
+                                 None if mk is None else mk.ctypes.data_as(_P),
+                                 C.c_int(0 if mk is None else mk.shape[1]), kps.ctypes.data_as(_P),
+                                 desc.ctypes.data_as(_P), C.c_int(cap), pyr.ctypes.data_as(_P),
+                                 cands.ctypes.data_as(_P) if debug else None, C.c_int(cands_cap if debug else 0),
+                                 cpl.ctypes.data_as(_P), kpl.ctypes.data_as(_P))
+    assert n >= 0
+    res = dict(kps=kps[:n].copy(), desc=desc[:n].copy(), kps_per_level=kpl, cands_per_level=cpl)
+    levels, off = [], 0
+    for l in range(p.num_levels):
+        levels.append(pyr[off:off + int(w[l]) * int(h[l])].reshape(int(h[l]), int(w[l])))
+        off += int(w[l]) * int(h[l])
+    res["pyramid"] = levels
+    if debug:
+        res["cands"] = cands[:int(cpl.sum())].copy()
+    return res
+
+
+Oracle.resize_linear = _resize_linear
+Oracle.fast = _fast
+Oracle.blur7 = _blur7
+Oracle.blur5 = _blur5
+Oracle.orb_tables = _orb_tables
+Oracle.orb_level_sizes = _orb_level_sizes
+Oracle.orb_distribute = _orb_distribute
+Oracle.orb_ic_angle = _orb_ic_angle
+Oracle.orb_describe = _orb_describe
+Oracle.orb_extract = _orb_extract
+_old_init = Oracle.__init__
+
+
+def _new_init(self):
+    _old_init(self)
+    _orb_init(self)
+
+
+Oracle.__init__ = _new_init

@@ -183,3 +183,56 @@ def make_line_queries(seed, curr, m=300):
              scale_level=np.zeros(m, np.int32), desc=flip_bits(rng, curr["desc"][src], rng.integers(0, 70, m)),
              valid=(rng.random(m) > 0.1).astype(np.uint8))
     return q
+
+
+# ------------------------------------------------------------------------------------- images
+def make_texture(seed, h=480, w=640, n_rect=400, n_blob=2000):
+    """Seeded textured scene: random-contrast rectangles (axis-aligned + rotated) and Gaussian blobs over
+    1/f noise: > 1000 FAST corners per level budget, line-rich."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    # 1/f noise
+    f = np.fft.fft2(rng.normal(0, 1, (h, w)))
+    fy = np.fft.fftfreq(h)[:, None]
+    fx = np.fft.fftfreq(w)[None, :]
+    rad = np.sqrt(fx * fx + fy * fy)
+    rad[0, 0] = 1.0
+    img = np.real(np.fft.ifft2(f / rad))
+    img = (img - img.min()) / (img.max() - img.min()) * 90.0 + 80.0
+    img = img.astype(np.float32)
+    sc = max(h, w) / 640.0
+    for _ in range(n_rect):
+        cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+        rw, rh = rng.uniform(8, 90) * sc, rng.uniform(8, 90) * sc
+        ang = rng.uniform(0, 180) if rng.random() < 0.5 else 0.0
+        box = cv2.boxPoints(((float(cx), float(cy)), (float(rw), float(rh)), float(ang)))
+        val = float(rng.uniform(0, 255))
+        a = float(rng.uniform(0.4, 1.0))
+        layer = img.copy()
+        cv2.fillPoly(layer, [np.round(box).astype(np.int32)], val)
+        img = (1 - a) * img + a * layer
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    for _ in range(n_blob):
+        cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+        s = rng.uniform(1.0, 3.5) * sc
+        amp = rng.uniform(-90, 90)
+        x0, x1 = int(max(0, cx - 4 * s)), int(min(w, cx + 4 * s + 1))
+        y0, y1 = int(max(0, cy - 4 * s)), int(min(h, cy + 4 * s + 1))
+        if x1 <= x0 or y1 <= y0:
+            continue
+        g = np.exp(-((xx[y0:y1, x0:x1] - cx) ** 2 + (yy[y0:y1, x0:x1] - cy) ** 2) / (2 * s * s))
+        img[y0:y1, x0:x1] += (amp * g).astype(np.float32)
+    return np.clip(np.round(img), 0, 255).astype(np.uint8)
+
+
+def make_toy_corner_image(variant=1):
+    """The toy images of test/PLPSLAM/feature/orb_extractor.cc:27-83 (white image, one anti-aliased black
+    rectangle).  Returns (image, corner_xy)."""
+    import cv2
+    if variant == 1:  # extract_toy_sample_1
+        img = np.full((600, 600), 255, np.uint8)
+        cv2.rectangle(img, (300, 300), (600, 600), 0, -1, cv2.LINE_AA)
+        return img, (300, 300)
+    img = np.full((2000, 2000), 255, np.uint8)  # extract_toy_sample_2
+    cv2.rectangle(img, (0, 0), (1800, 1800), 0, -1, cv2.LINE_AA)
+    return img, (1800, 1800)
