@@ -210,6 +210,67 @@ PLP_API plp_status plp_match_brute_force(plp_ctx *ctx, const uint8_t *frm_desc,
                                          int check_orientation, int32_t *matched_kf_idx_in_frm_out,
                                          uint32_t *num_matches_out);
 
+/* ------------------------------------------------------------------------ */
+/* ORB extraction  (feature/orb_extractor.{h,cc})                            */
+/* ------------------------------------------------------------------------ */
+typedef struct plp_orb_params { /* feature/orb_params.h:39-70 */
+    uint32_t max_num_keypts;
+    float scale_factor;
+    uint32_t num_levels;
+    uint32_t ini_fast_thr;
+    uint32_t min_fast_thr;
+} plp_orb_params;
+
+typedef struct plp_keypoint { /* binary layout of cv::KeyPoint (28 bytes) */
+    float x, y;               /* pt */
+    float size, angle, response;
+    int32_t octave, class_id;
+} plp_keypoint;
+
+typedef struct plp_image_view { /* one pyramid level, device memory */
+    const uint8_t *data;
+    int32_t rows, cols;
+    size_t step;
+} plp_image_view;
+
+typedef struct plp_orb plp_orb; /* one per orb_extractor instance (never re-entered, frame.cc:456-457) */
+
+/* orb_extractor::orb_extractor(const orb_params&) (orb_extractor.cc:66-71, initialize() :235-287).
+ * The handle is specialised for one image size and a maximum batch of frames. */
+PLP_API plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, int cols,
+                                  int max_batch, plp_orb **out);
+PLP_API void plp_orb_destroy(plp_orb *orb);
+/* keypoint capacity per frame of the output arrays (the quadtree may exceed max_num_keypts) */
+PLP_API int plp_orb_capacity(const plp_orb *orb);
+/* orb_extractor::get_scale_factors / get_inv_scale_factors / get_level_sigma_sq / get_inv_level_sigma_sq
+ * (orb_extractor.cc:215-233); each array has num_levels entries. */
+PLP_API plp_status plp_orb_get_tables(const plp_orb *orb, float *scale_factors, float *inv_scale_factors,
+                                      float *level_sigma_sq, float *inv_level_sigma_sq,
+                                      uint32_t *num_keypts_per_level);
+
+/* orb_extractor::extract(in_image, in_image_mask, keypts, out_descriptors) (orb_extractor.cc:73-160).
+ * Host pointers.  mask may be NULL (image mask or the rectangle mask of orb_extractor.cc:297-313, which the
+ * adapter rasterises exactly like the reference).  Empty image (rows*cols == 0 or img == NULL) -> *n_out = 0,
+ * PLP_OK, like the silent return at orb_extractor.cc:76-79.  kp_out/desc_out must hold plp_orb_capacity()
+ * entries. */
+PLP_API plp_status plp_orb_extract(plp_orb *orb, const uint8_t *img, int rows, int cols, size_t step,
+                                   const uint8_t *mask, size_t mask_step, plp_keypoint *kp_out,
+                                   uint8_t *desc_out, int *n_out);
+/* Same for a batch of `batch` equally sized frames stored back to back (frame stride rows*step). */
+PLP_API plp_status plp_orb_extract_batch(plp_orb *orb, const uint8_t *imgs, int batch, size_t step,
+                                         plp_keypoint *kp_out, uint8_t *desc_out, int32_t *n_out);
+/* Device-resident variant: d_imgs (batch x rows x step) stays in HBM; results are written to device arrays
+ * of batch x capacity entries; no synchronisation.  d_status[b] != 0 flags a capacity overflow in frame b. */
+PLP_API plp_status plp_orb_extract_batch_dev(plp_orb *orb, const uint8_t *d_imgs, int batch, size_t step,
+                                             plp_keypoint *d_kp_out, uint8_t *d_desc_out,
+                                             int32_t *d_n_out, int32_t *d_status);
+/* orb_extractor::image_pyramid_ (orb_extractor.h:101) of frame b of the most recent extraction. */
+PLP_API plp_status plp_orb_get_pyramid(const plp_orb *orb, int b, int level, plp_image_view *out);
+/* debug/parity taps of the most recent extraction (host copies): FAST candidates of one level in the
+ * reference's cell order, coordinates relative to the 19-px border (orb_extractor.cc:424-434). */
+PLP_API plp_status plp_orb_debug_candidates(plp_orb *orb, int b, int level, plp_keypoint *out, int cap,
+                                            int *n_out);
+
 #ifdef __cplusplus
 }
 #endif

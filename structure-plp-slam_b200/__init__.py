@@ -9,6 +9,8 @@ The directory name contains '-' so it is loaded by path (see ``load_package`` in
 """
 from .capi import (  # noqa: F401
     Context,
+    OrbExtractor,
+    KP_DTYPE,
     PlpError,
     lib,
     lib_path,

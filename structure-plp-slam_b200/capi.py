@@ -90,6 +90,20 @@ class LastFrameLines(C.Structure):
     _fields_ = [("n", C.c_int32), ("pos_w", _P), ("octave", _P), ("desc", _P), ("valid", _P)]
 
 
+class OrbParams(C.Structure):
+    _fields_ = [("max_num_keypts", C.c_uint32), ("scale_factor", C.c_float), ("num_levels", C.c_uint32),
+                ("ini_fast_thr", C.c_uint32), ("min_fast_thr", C.c_uint32)]
+
+
+class ImageView(C.Structure):
+    _fields_ = [("data", _P), ("rows", C.c_int32), ("cols", C.c_int32), ("step", C.c_size_t)]
+
+
+# binary layout of plp_keypoint / cv::KeyPoint
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+
 # ----------------------------------------------------------------------------- helpers
 class _Keep:
     """Keeps converted numpy arrays alive for the duration of a call."""
@@ -277,3 +291,90 @@ class Context:
             k.arr(kf_angle, np.float32), k.arr(kf_valid, np.uint8), C.c_int(kd.shape[0]), C.c_float(lowe_ratio),
             C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P), C.byref(num)))
         return matched, int(num.value)
+
+
+class OrbExtractor:
+    """feature::orb_extractor (feature/orb_extractor.h:46-98) backed by plp_orb."""
+
+    def __init__(self, ctx: Context, rows: int, cols: int, max_num_keypts=1000, scale_factor=1.2, num_levels=8,
+                 ini_fast_thr=20, min_fast_thr=7, max_batch=1):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        self.rows, self.cols, self.max_batch = rows, cols, max_batch
+        self.params = OrbParams(max_num_keypts, scale_factor, num_levels, ini_fast_thr, min_fast_thr)
+        h = C.c_void_p()
+        self._h = None
+        ctx._check(self._lib.plp_orb_create(ctx.handle, C.byref(self.params), C.c_int(rows), C.c_int(cols),
+                                            C.c_int(max_batch), C.byref(h)))
+        self._h = h
+        self.capacity = int(self._lib.plp_orb_capacity(self._h))
+        L = num_levels
+        self.scale_factors, self.inv_scale_factors = np.zeros(L, np.float32), np.zeros(L, np.float32)
+        self.level_sigma_sq, self.inv_level_sigma_sq = np.zeros(L, np.float32), np.zeros(L, np.float32)
+        self.num_keypts_per_level = np.zeros(L, np.uint32)
+        ctx._check(self._lib.plp_orb_get_tables(self._h, self.scale_factors.ctypes.data_as(_P),
+                                                self.inv_scale_factors.ctypes.data_as(_P),
+                                                self.level_sigma_sq.ctypes.data_as(_P),
+                                                self.inv_level_sigma_sq.ctypes.data_as(_P),
+                                                self.num_keypts_per_level.ctypes.data_as(_P)))
+
+    def close(self):
+        if self._h is not None:
+            self._lib.plp_orb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def extract(self, img, mask=None):
+        """orb_extractor::extract -> (keypoints[KP_DTYPE], descriptors[n,32])."""
+        if img is None or img.size == 0:
+            n = C.c_int(-1)
+            self._ctx._check(self._lib.plp_orb_extract(self._h, None, 0, 0, C.c_size_t(0), None, C.c_size_t(0), None,
+                                                       None, C.byref(n)))
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        img = np.ascontiguousarray(img, np.uint8)
+        kps = np.zeros(self.capacity, KP_DTYPE)
+        desc = np.zeros((self.capacity, 32), np.uint8)
+        n = C.c_int(0)
+        mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        self._ctx._check(self._lib.plp_orb_extract(
+            self._h, img.ctypes.data_as(_P), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_size_t(img.strides[0]),
+            None if mk is None else mk.ctypes.data_as(_P), C.c_size_t(0 if mk is None else mk.strides[0]),
+            kps.ctypes.data_as(_P), desc.ctypes.data_as(_P), C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, imgs):
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        B = imgs.shape[0]
+        kps = np.zeros((B, self.capacity), KP_DTYPE)
+        desc = np.zeros((B, self.capacity, 32), np.uint8)
+        n = np.zeros(B, np.int32)
+        self._ctx._check(self._lib.plp_orb_extract_batch(self._h, imgs.ctypes.data_as(_P), C.c_int(B),
+                                                         C.c_size_t(imgs.strides[1]), kps.ctypes.data_as(_P),
+                                                         desc.ctypes.data_as(_P), n.ctypes.data_as(_P)))
+        return [(kps[b, :n[b]].copy(), desc[b, :n[b]].copy()) for b in range(B)]
+
+    def pyramid_level(self, b: int, level: int) -> np.ndarray:
+        """orb_extractor::image_pyramid_[level] of frame b of the last extraction (downloaded)."""
+        v = ImageView()
+        self._ctx._check(self._lib.plp_orb_get_pyramid(self._h, C.c_int(b), C.c_int(level), C.byref(v)))
+        buf = np.zeros((v.rows, v.step), np.uint8)
+        self._ctx._check(self._lib.plp_dev_download(self._ctx.handle, buf.ctypes.data_as(_P), C.c_void_p(v.data),
+                                                    C.c_size_t(v.rows * v.step)))
+        return buf[:, :v.cols].copy()
+
+    def debug_candidates(self, b: int, level: int) -> np.ndarray:
+        cap = 70000
+        out = np.zeros(cap, KP_DTYPE)
+        n = C.c_int(0)
+        self._ctx._check(self._lib.plp_orb_debug_candidates(self._h, C.c_int(b), C.c_int(level),
+                                                            out.ctypes.data_as(_P), C.c_int(cap), C.byref(n)))
+        return out[:min(n.value, cap)].copy()

@@ -1,0 +1,1459 @@
+// orb.cu -- ORB extraction on sm_100a: pyramid -> per-cell FAST -> quadtree selection -> orientation ->
+// 7x7 Gaussian -> steered BRIEF.  Replaces feature::orb_extractor::extract (feature/orb_extractor.cc:73-160
+// and the helpers it calls, orb_extractor_node.cc:31-80, util/trigonometric.h:42-78) bit-exactly.
+//
+// Batched from day one: every kernel has the frame index as its outermost grid dimension, so one launch
+// covers `batch` frames.  10 launches per batch:
+//   7 x pyr_resize_kernel     level l from level l-1 (chained like orb_extractor.cc:315-326), OpenCV's
+//                             11-bit fixed-point bilinear
+//   1 x fast_cells_kernel     one CTA per 64-px cell (6-px overlap, orb_extractor.cc:338-437): tile -> smem,
+//                             FAST-9/16 score, 3x3 NMS at the initial threshold, fallback to the minimum
+//                             threshold if the cell is empty, ordered compaction (row-major inside the cell)
+//   1 x quadtree_kernel       one CTA per (level, frame): data-parallel formulation of
+//                             distribute_keypoints_via_tree (see tools/quadtree_parallel_model.py)
+//   1 x describe_kernel       one warp per keypoint: intensity-centroid angle, 45x45 patch -> separable Q8
+//                             Gaussian in smem -> 256 steered comparisons, one descriptor byte per lane
+// Compiled with -fmad=false: the f32 steering must round exactly like the oracle (no FMA).
+#include "common.cuh"
+#include "brief_pattern.inc"
+
+namespace plp {
+
+namespace {
+
+constexpr int kMaxLevels = 16;
+constexpr int kPatchRadius = 19;   // orb_extractor.h:161 orb_patch_radius_
+constexpr int kHalfPatch = 15;     // orb_extractor.h:158 fast_half_patch_size_
+constexpr int kCellSize = 64;      // orb_extractor.cc:339
+constexpr int kOverlap = 6;        // orb_extractor.cc:338
+constexpr int kCellCap = 1024;     // max NMS survivors of a 64x64 tested area
+constexpr int kTilePitch = 80;
+constexpr int kTileRows = 70;
+
+struct LevelInfo {
+    int w, h, pitch;
+    size_t offset;        // byte offset of the level inside one frame's pyramid block (levels >= 1)
+    int cells_x, cells_y; // number of cell columns/rows visited (orb_extractor.cc:356-357)
+    int cell_base;        // index of this level's first cell in the per-frame cell list
+    int num_cells;
+    int budget;           // num_keypts_per_level_
+    int slot_base;        // first output slot of this level (per-level keypoint lists)
+    int slot_cap;
+    float scale_factor;
+    float size;           // keypoint size = (unsigned)(31 * scale)
+};
+
+struct CellDesc {
+    short level, i, j, pad;
+    short min_x, min_y, max_x, max_y;
+};
+
+struct LevelKp {  // quadtree output, level coordinates (border already added)
+    short x, y;
+    int response;
+};
+
+struct OrbDev {
+    int num_levels, rows, cols;
+    int num_cells;       // per frame
+    int total_slots;     // per frame
+    int out_cap;         // per frame capacity of the final kp/desc arrays
+    int ini_thr, min_thr;
+    LevelInfo lv[kMaxLevels];
+    int u_max[16];
+    // per-batch inputs
+    const uint8_t *img0;  // level 0 = the caller's images
+    size_t img0_step, img0_frame_stride;
+    const uint8_t *mask;  // optional, level-0 resolution, shared by the batch
+    size_t mask_step;
+    // device work areas
+    uint8_t *pyr;  // batch x pyr_frame_bytes (levels >= 1)
+    size_t pyr_frame_bytes;
+    const CellDesc *cells;
+    uint32_t *cell_buf;   // batch x num_cells x kCellCap packed (x:11 | y:10 | score:8)
+    int *cell_cnt;        // batch x num_cells
+    LevelKp *lvl_kp;      // batch x total_slots
+    int *lvl_cnt;         // batch x num_levels
+    uint8_t *qt_scratch;  // global fallback work area of the quadtree kernel
+    size_t qt_scratch_per_job;
+    int *status;          // batch: != 0 on capacity overflow
+};
+
+__device__ __forceinline__ const uint8_t *level_ptr(const OrbDev &P, int b, int l) {
+    return l == 0 ? P.img0 + (size_t)b * P.img0_frame_stride : P.pyr + (size_t)b * P.pyr_frame_bytes + P.lv[l].offset;
+}
+__device__ __forceinline__ int level_pitch(const OrbDev &P, int l) { return l == 0 ? (int)P.img0_step : P.lv[l].pitch; }
+
+// =====================================================================================================
+// 1. pyramid: cv::resize(INTER_LINEAR) fixed-point model
+// =====================================================================================================
+// tables: per destination column {sx0, sx1, a0, a1}, per destination row {sy0, sy1, b0, b1}
+__global__ void pyr_resize_kernel(OrbDev P, int l, const short4 *__restrict__ xtab, const short4 *__restrict__ ytab) {
+    const int b = blockIdx.y;
+    const int dw = P.lv[l].w, dh = P.lv[l].h, dpitch = P.lv[l].pitch;
+    const int quads = (dw + 3) >> 2;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= quads * dh) return;
+    const int y = q / quads, x0 = (q - y * quads) * 4;
+    const uint8_t *src = level_ptr(P, b, l - 1);
+    const int spitch = level_pitch(P, l - 1);
+    uint8_t *dst = const_cast<uint8_t *>(level_ptr(P, b, l));
+    const short4 yt = ytab[y];
+    const uint8_t *S0 = src + (size_t)yt.x * spitch, *S1 = src + (size_t)yt.y * spitch;
+    const int b0 = yt.z, b1 = yt.w;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x0 + k;
+        if (x < dw) {
+            const short4 xt = xtab[x];
+            const int r0 = S0[xt.x] * xt.z + S0[xt.y] * xt.w;
+            const int r1 = S1[xt.x] * xt.z + S1[xt.y] * xt.w;
+            const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            packed |= (uint32_t)(v & 0xff) << (8 * k);
+        }
+    }
+    // pitch is a multiple of 64 so the 4-byte store is aligned; pad bytes past dw are never read
+    *reinterpret_cast<uint32_t *>(dst + (size_t)y * dpitch + x0) = packed;
+}
+
+// =====================================================================================================
+// 2. FAST-9/16 per cell
+// =====================================================================================================
+// ring offsets
+__constant__ int kRingDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+__constant__ int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+// m = max over the sixteen 9-arcs of min(arc differences), both polarities; returns 0 early when the pixel
+// cannot be a corner at threshold `t` (then m <= t and the caller stores score 0).
+__device__ __forceinline__ int fast_m(const uint8_t *p, int t) {
+    const int v = p[0];
+    int d[16];
+    // a 9-arc always contains ring pixel 0 or 8, and 4 or 12
+    d[0] = v - p[3 * kTilePitch];
+    d[8] = v - p[-3 * kTilePitch];
+    if (abs(d[0]) <= t && abs(d[8]) <= t) return 0;
+    d[4] = v - p[3];
+    d[12] = v - p[-3];
+    if (abs(d[4]) <= t && abs(d[12]) <= t) return 0;
+    d[1] = v - p[3 * kTilePitch + 1];
+    d[2] = v - p[2 * kTilePitch + 2];
+    d[3] = v - p[1 * kTilePitch + 3];
+    d[5] = v - p[-1 * kTilePitch + 3];
+    d[6] = v - p[-2 * kTilePitch + 2];
+    d[7] = v - p[-3 * kTilePitch + 1];
+    d[9] = v - p[-3 * kTilePitch - 1];
+    d[10] = v - p[-2 * kTilePitch - 2];
+    d[11] = v - p[-1 * kTilePitch - 3];
+    d[13] = v - p[1 * kTilePitch - 3];
+    d[14] = v - p[2 * kTilePitch - 2];
+    d[15] = v - p[3 * kTilePitch - 1];
+    unsigned dark = 0, bright = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        dark |= (unsigned)(d[k] > t) << k;
+        bright |= (unsigned)(d[k] < -t) << k;
+    }
+    dark |= dark << 16;
+    bright |= bright << 16;
+    unsigned a = dark & (dark >> 1);
+    a &= a >> 2;
+    a &= a >> 4;
+    a &= dark >> 8;
+    unsigned c = bright & (bright >> 1);
+    c &= c >> 2;
+    c &= c >> 4;
+    c &= bright >> 8;
+    if (((a | c) & 0xffffu) == 0) return 0;
+    // exact score: sliding window min / max of length 9 over the circular ring (doubling)
+    int mn2[16], mx2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mn2[k] = min(d[k], d[(k + 1) & 15]);
+        mx2[k] = max(d[k], d[(k + 1) & 15]);
+    }
+    int mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
+        mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+    }
+    int best = -255;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+        best = max(best, max(mn9, -mx9));
+    }
+    return best;
+}
+
+__device__ __forceinline__ bool masked(const OrbDev &P, unsigned y, unsigned x, float scale) {
+    // orb_extractor.cc:333-336 is_in_mask
+    return P.mask[(size_t)(int)(y * scale) * P.mask_step + (int)(x * scale)] == 0;
+}
+
+__global__ void __launch_bounds__(256) fast_cells_kernel(OrbDev P) {
+    __shared__ __align__(16) uint8_t tile[kTileRows * kTilePitch];
+    __shared__ __align__(16) uint8_t score[kTileRows * kTilePitch];
+    __shared__ int warp_sums[8];
+    __shared__ int s_total[2];
+    const int b = blockIdx.y, ci = blockIdx.x, tid = threadIdx.x;
+    const CellDesc cell = P.cells[ci];
+    const int l = cell.level;
+    const int w = cell.max_x - cell.min_x, h = cell.max_y - cell.min_y;
+    int *cnt_out = P.cell_cnt + (size_t)b * P.num_cells + ci;
+    uint32_t *buf = P.cell_buf + ((size_t)b * P.num_cells + ci) * kCellCap;
+    const float scale = P.lv[l].scale_factor;
+    bool skip = (w < 7 || h < 7);
+    if (!skip && P.mask) {  // orb_extractor.cc:395-401
+        skip = masked(P, cell.min_y, cell.min_x, scale) || masked(P, cell.max_y, cell.min_x, scale) ||
+               masked(P, cell.min_y, cell.max_x, scale) || masked(P, cell.max_y, cell.max_x, scale);
+    }
+    if (skip) {
+        if (tid == 0) *cnt_out = 0;
+        return;
+    }
+    const uint8_t *img = level_ptr(P, b, l);
+    const int pitch = level_pitch(P, l);
+    for (int idx = tid; idx < w * h; idx += 256) {
+        const int y = idx / w, x = idx - y * w;
+        tile[y * kTilePitch + x] = img[(size_t)(cell.min_y + y) * pitch + cell.min_x + x];
+    }
+    for (int idx = tid; idx < kTileRows * kTilePitch / 4; idx += 256) reinterpret_cast<uint32_t *>(score)[idx] = 0;
+    __syncthreads();
+    const int tw = w - 6, th = h - 6, total = tw * th;
+    for (int p = tid; p < total; p += 256) {
+        const int y = 3 + p / tw, x = 3 + p % tw;
+        const int m = fast_m(tile + y * kTilePitch + x, P.min_thr);
+        score[y * kTilePitch + x] = (m > P.min_thr) ? (uint8_t)(m - 1) : (uint8_t)0;
+    }
+    __syncthreads();
+    // NMS at both thresholds; each thread owns a contiguous row-major run so the output stays ordered
+    const int per = (total + 255) / 256;  // <= 16
+    const int p0 = tid * per, p1 = min(total, p0 + per);
+    unsigned flagsA = 0, flagsB = 0;
+    const int ini = P.ini_thr;
+    for (int p = p0; p < p1; ++p) {
+        const int y = 3 + p / tw, x = 3 + p % tw;
+        const uint8_t *s = score + y * kTilePitch + x;
+        const int sc = s[0];
+        if (sc == 0) continue;
+        bool keepB = true, keepA = (sc >= ini);
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (dx == 0 && dy == 0) continue;
+                const int nb = s[dy * kTilePitch + dx];
+                keepB = keepB && (sc > nb);
+                keepA = keepA && (sc > (nb >= ini ? nb : 0));
+            }
+        flagsA |= (unsigned)keepA << (p - p0);
+        flagsB |= (unsigned)keepB << (p - p0);
+    }
+    // does the initial threshold yield anything? (orb_extractor.cc:404-412)
+    const int anyA = __syncthreads_or(flagsA != 0);
+    unsigned flags = anyA ? flagsA : flagsB;
+    if (P.mask && flags) {  // orb_extractor.cc:429
+        for (int p = p0; p < p1; ++p) {
+            if (!((flags >> (p - p0)) & 1)) continue;
+            const int y = 3 + p / tw, x = 3 + p % tw;
+            const float kx = (float)x + (float)(cell.j * kCellSize), ky = (float)y + (float)(cell.i * kCellSize);
+            if (masked(P, (unsigned)((float)kPatchRadius + ky), (unsigned)((float)kPatchRadius + kx), scale))
+                flags &= ~(1u << (p - p0));
+        }
+    }
+    // block exclusive scan of popc(flags)
+    const int mine = __popc(flags);
+    int incl = mine;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int k = 0; k < 8; ++k) {
+            const int v = warp_sums[k];
+            warp_sums[k] = acc;
+            acc += v;
+        }
+        s_total[0] = acc;
+    }
+    __syncthreads();
+    int pos = warp_sums[warp] + incl - mine;
+    for (int p = p0; p < p1; ++p) {
+        if (!((flags >> (p - p0)) & 1)) continue;
+        const int y = 3 + p / tw, x = 3 + p % tw;
+        const int sc = score[y * kTilePitch + x];
+        const int lx = x + cell.j * kCellSize, ly = y + cell.i * kCellSize;  // relative to the 19-px border
+        if (pos < kCellCap) buf[pos] = (uint32_t)lx | ((uint32_t)ly << 11) | ((uint32_t)sc << 21);
+        ++pos;
+    }
+    if (tid == 0) *cnt_out = min(s_total[0], kCellCap);
+}
+
+// =====================================================================================================
+// 3. quadtree keypoint distribution (orb_extractor.cc:468-685), array formulation
+// =====================================================================================================
+constexpr int kQtThreads = 512;
+constexpr int kNodeCap = 2048;      // >= 4 * budget + 8
+constexpr int kQtSmemCands = 8192;  // candidates per level handled entirely in shared memory
+
+struct QtArrays {
+    uint32_t *cand;             // packed candidates in gather order
+    unsigned short *perm[2];    // permutation (indices into cand), ping-pong
+    unsigned short *owner[2];   // list position of the node owning each perm slot, ping-pong
+};
+
+struct QtNodes {  // struct of arrays in list order
+    short4 *rect;              // bx, by, ex, ey
+    unsigned short *start;     // segment start in perm
+    unsigned short *cnt;
+    uint8_t *leaf;
+};
+
+__device__ __forceinline__ int cand_x(uint32_t c) { return (int)(c & 0x7ff); }
+__device__ __forceinline__ int cand_y(uint32_t c) { return (int)((c >> 11) & 0x3ff); }
+__device__ __forceinline__ int cand_score(uint32_t c) { return (int)(c >> 21); }
+
+// block-wide exclusive scan of `v` (one value per thread); returns the exclusive prefix, *total = sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int *smem_warp /*[17]*/, int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // protect smem_warp reuse
+    if (lane == 31) smem_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int s = lane < (kQtThreads / 32) ? smem_warp[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        if (lane < (kQtThreads / 32)) smem_warp[lane] = si - s;
+        if (lane == (kQtThreads / 32) - 1) smem_warp[16] = si;
+    }
+    __syncthreads();
+    *total = smem_warp[16];
+    return smem_warp[warp] + incl - v;
+}
+
+// exclusive scan over an int array of length n in shared memory (in place); returns the total
+__device__ int block_scan_array(int *data, int n, int *smem_warp) {
+    const int per = (n + kQtThreads - 1) / kQtThreads;
+    const int i0 = min(n, (int)threadIdx.x * per), i1 = min(n, i0 + per);
+    int sum = 0;
+    for (int i = i0; i < i1; ++i) sum += data[i];
+    int total;
+    int run = block_exclusive_scan(sum, smem_warp, &total);
+    for (int i = i0; i < i1; ++i) {
+        const int v = data[i];
+        data[i] = run;
+        run += v;
+    }
+    __syncthreads();
+    return total;
+}
+
+// child class of a keypoint inside node rect (orb_extractor_node.cc:67-78)
+__device__ __forceinline__ int classify(const short4 r, uint32_t c) {
+    const unsigned half_x = (unsigned)cv_ceil((r.z - r.x) / 2.0);
+    const unsigned half_y = (unsigned)cv_ceil((r.w - r.y) / 2.0);
+    int q = 0;
+    if ((float)((unsigned)r.x + half_x) <= (float)cand_x(c)) q += 1;
+    if ((float)((unsigned)r.y + half_y) <= (float)cand_y(c)) q += 2;
+    return q;
+}
+
+__device__ __forceinline__ short4 child_rect(const short4 r, int q) {
+    const int half_x = cv_ceil((r.z - r.x) / 2.0), half_y = cv_ceil((r.w - r.y) / 2.0);
+    short4 c;
+    c.x = (q & 1) ? (short)(r.x + half_x) : r.x;
+    c.z = (q & 1) ? r.z : (short)(r.x + half_x);
+    c.y = (q & 2) ? (short)(r.y + half_y) : r.y;
+    c.w = (q & 2) ? r.w : (short)(r.y + half_y);
+    return c;
+}
+
+// Segmented scan of per-element class counters.  For every perm slot i whose node is selected (sel[owner]),
+// computes rank[i] = number of earlier slots of the same node with the same class, and per node the four
+// class totals tot[node*4 + q].  cls/rank are written to `cls_rank` (class in bits 14-15, rank in 0-13... kept
+// as two arrays for clarity).
+__device__ void segmented_class_scan(const QtArrays &A, int cur, int n, const QtNodes &N, const uint8_t *sel,
+                                     unsigned short *rank, uint8_t *cls, unsigned short *tot,
+                                     unsigned long long *carry_tail, uint8_t *carry_head) {
+    const int tid = threadIdx.x;
+    const int per = (n + kQtThreads - 1) / kQtThreads;
+    const int i0 = min(n, tid * per), i1 = min(n, i0 + per);
+    const unsigned short *perm = A.perm[cur], *owner = A.owner[cur];
+    // pass 1: local tail since the last segment head in this chunk
+    unsigned long long acc = 0;
+    bool head = false;
+    int prev_owner = (i0 > 0 && i0 < n) ? owner[i0 - 1] : -1;
+    for (int i = i0; i < i1; ++i) {
+        const int o = owner[i];
+        if (o != prev_owner) {
+            head = true;
+            acc = 0;
+        }
+        prev_owner = o;
+        int q = 0;
+        if (sel[o]) q = classify(N.rect[o], A.cand[perm[i]]);
+        cls[i] = (uint8_t)q;
+        if (sel[o]) acc += 1ull << (16 * q);
+    }
+    // the first element of a chunk starts a new segment iff its owner differs from the previous slot's owner;
+    // that case is covered above because prev_owner was initialised from owner[i0-1].
+    carry_tail[tid] = acc;
+    carry_head[tid] = head ? 1 : 0;
+    __syncthreads();
+    // pass 2: carry-in per thread = segmented exclusive scan over the 512 (tail, head) pairs, done by warp 0:
+    // each lane folds 16 consecutive entries, the 32 lane aggregates are scanned with shuffles.
+    if (tid < 32) {
+        constexpr int kPer = kQtThreads / 32;
+        unsigned long long run = 0;
+        bool hf = false;
+        for (int t = tid * kPer; t < (tid + 1) * kPer; ++t) {
+            const bool h = carry_head[t] != 0;
+            run = h ? carry_tail[t] : run + carry_tail[t];
+            hf = hf || h;
+        }
+        unsigned long long v = run;
+        int f = hf ? 1 : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long pv = __shfl_up_sync(0xffffffffu, v, o);
+            const int pf = __shfl_up_sync(0xffffffffu, f, o);
+            if (tid >= o) {
+                if (!f) v += pv;
+                f |= pf;
+            }
+        }
+        unsigned long long carry = __shfl_up_sync(0xffffffffu, v, 1);
+        if (tid == 0) carry = 0;
+        run = carry;
+        for (int t = tid * kPer; t < (tid + 1) * kPer; ++t) {
+            const bool h = carry_head[t] != 0;
+            const unsigned long long tail = carry_tail[t];
+            carry_tail[t] = run;  // carry-in of thread t
+            run = h ? tail : run + tail;
+        }
+    }
+    __syncthreads();
+    // pass 3: ranks and node totals
+    acc = carry_tail[tid];
+    prev_owner = (i0 > 0 && i0 < n) ? owner[i0 - 1] : -1;
+    for (int i = i0; i < i1; ++i) {
+        const int o = owner[i];
+        if (o != prev_owner) acc = 0;
+        prev_owner = o;
+        const int q = cls[i];
+        if (sel[o]) {
+            rank[i] = (unsigned short)((acc >> (16 * q)) & 0xffff);
+            acc += 1ull << (16 * q);
+        }
+        const bool last = (i + 1 == n) || (owner[i + 1] != o);
+        if (last && sel[o]) {
+            tot[o * 4 + 0] = (unsigned short)(acc & 0xffff);
+            tot[o * 4 + 1] = (unsigned short)((acc >> 16) & 0xffff);
+            tot[o * 4 + 2] = (unsigned short)((acc >> 32) & 0xffff);
+            tot[o * 4 + 3] = (unsigned short)((acc >> 48) & 0xffff);
+        }
+    }
+    __syncthreads();
+}
+
+struct QtShared {
+    short4 rect[2][kNodeCap];
+    unsigned short start[2][kNodeCap];
+    unsigned short cnt[2][kNodeCap];
+    uint8_t leaf[2][kNodeCap];
+    uint8_t sel[kNodeCap];
+    unsigned short tot[kNodeCap * 4];
+    int newpos[kNodeCap];      // list position of the first (front-most) child / of the kept node
+    int scan[kNodeCap];        // scratch for scans over the list
+    unsigned short pool[2][kNodeCap];
+    unsigned short pool_sorted[kNodeCap];
+    unsigned long long carry_tail[kQtThreads];
+    uint8_t carry_head[kQtThreads];
+    int warp_tmp[17];
+    int misc[8];
+};
+
+// Applies the division of all nodes with sel[p] != 0 of list `cur_n` (length len): builds the new list
+// (children of processed nodes in front, later-processed first, classes reversed; then the untouched nodes in
+// order), partitions the keypoints, builds the new pool (children with more than one keypoint, creation
+// order).  `order`: processing rank of each selected node (for phase 1 it is the list order).  Returns the
+// new list length.  proc_rank[p] (in S.scan) must hold the processing rank for selected nodes.
+__device__ int apply_division(QtShared &S, QtArrays &A, int &cur, int n_cand, int &cur_n, int len, int num_proc,
+                              const unsigned short *proc_list /* selected nodes in processing order */,
+                              unsigned short *rank, uint8_t *cls, int *pool_len_out, int pool_dst) {
+    const int tid = threadIdx.x;
+    const int nxt_n = cur_n ^ 1;
+    // children count per processed node, in processing order -> S.scan[k]
+    for (int k = tid; k < num_proc; k += kQtThreads) {
+        const int p = proc_list[k];
+        const unsigned short *t = S.tot + p * 4;
+        S.scan[k] = (t[0] > 0) + (t[1] > 0) + (t[2] > 0) + (t[3] > 0);
+    }
+    __syncthreads();
+    const int total_children = block_scan_array(S.scan, num_proc, S.warp_tmp);  // exclusive prefix over k
+    // kept nodes: positions after all children, in list order
+    for (int p = tid; p < len; p += kQtThreads) S.newpos[p] = S.sel[p] ? 0 : 1;
+    __syncthreads();
+    // exclusive scan of kept flags over the list
+    {
+        // reuse block_scan_array on newpos
+    }
+    const int kept = block_scan_array(S.newpos, len, S.warp_tmp);
+    const int new_len = total_children + kept;
+    // pool flags per child in creation order: creation index = prefix(k) + r ; count children with cnt > 1
+    // first write nodes
+    for (int p = tid; p < len; p += kQtThreads) {
+        if (!S.sel[p]) {
+            const int pos = total_children + S.newpos[p];
+            S.rect[nxt_n][pos] = S.rect[cur_n][p];
+            S.start[nxt_n][pos] = S.start[cur_n][p];
+            S.cnt[nxt_n][pos] = S.cnt[cur_n][p];
+            S.leaf[nxt_n][pos] = S.leaf[cur_n][p];
+            S.newpos[p] = pos;
+        }
+    }
+    __syncthreads();
+    // children: processed node k has prefix S.scan[k] children before it (in processing order); its children
+    // occupy list positions [total_children - S.scan[k] - nch, total_children - S.scan[k]) with class order
+    // reversed (orb_extractor.cc:639-657 pushes to the front).
+    for (int k = tid; k < num_proc; k += kQtThreads) {
+        const int p = proc_list[k];
+        const unsigned short *t = S.tot + p * 4;
+        const int nch = (t[0] > 0) + (t[1] > 0) + (t[2] > 0) + (t[3] > 0);
+        const int base = total_children - S.scan[k] - nch;
+        const short4 r = S.rect[cur_n][p];
+        int o = S.start[cur_n][p];
+        int rnk = 0;
+        for (int q = 0; q < 4; ++q) {
+            if (t[q] == 0) continue;
+            const int pos = base + (nch - 1 - rnk);
+            S.rect[nxt_n][pos] = child_rect(r, q);
+            S.start[nxt_n][pos] = (unsigned short)o;
+            S.cnt[nxt_n][pos] = t[q];
+            S.leaf[nxt_n][pos] = 0;
+            o += t[q];
+            ++rnk;
+        }
+        S.newpos[p] = base;  // front-most child position; class q child = base + (nch-1-rank_q)
+    }
+    __syncthreads();
+    // keypoints: stable 4-way partition inside each processed node, owner update for everybody
+    {
+        const unsigned short *perm = A.perm[cur], *owner = A.owner[cur];
+        unsigned short *perm2 = A.perm[cur ^ 1], *owner2 = A.owner[cur ^ 1];
+        for (int i = tid; i < n_cand; i += kQtThreads) {
+            const int o = owner[i];
+            if (S.sel[o]) {
+                const unsigned short *t = S.tot + o * 4;
+                const int q = cls[i];
+                int off = 0, rnk = 0;
+                for (int c = 0; c < q; ++c) {
+                    off += t[c];
+                    rnk += (t[c] > 0);
+                }
+                const int nch = (t[0] > 0) + (t[1] > 0) + (t[2] > 0) + (t[3] > 0);
+                const int dst = S.start[cur_n][o] + off + rank[i];
+                perm2[dst] = perm[i];
+                owner2[dst] = (unsigned short)(S.newpos[o] + (nch - 1 - rnk));
+            } else {
+                perm2[i] = perm[i];
+                owner2[i] = (unsigned short)S.newpos[o];
+            }
+        }
+    }
+    __syncthreads();
+    // new pool: children with cnt > 1 in creation order (processing order, classes ascending)
+    for (int k = tid; k < num_proc; k += kQtThreads) {
+        const unsigned short *t = S.tot + proc_list[k] * 4;
+        S.scan[k] = (t[0] > 1) + (t[1] > 1) + (t[2] > 1) + (t[3] > 1);
+    }
+    __syncthreads();
+    // need the children-prefix again for positions: recompute nch prefix into S.newpos-independent scratch
+    const int pool_len = block_scan_array(S.scan, num_proc, S.warp_tmp);
+    for (int k = tid; k < num_proc; k += kQtThreads) {
+        const int p = proc_list[k];
+        const unsigned short *t = S.tot + p * 4;
+        const int nch = (t[0] > 0) + (t[1] > 0) + (t[2] > 0) + (t[3] > 0);
+        int w = S.scan[k], rnk = 0;
+        for (int q = 0; q < 4; ++q) {
+            if (t[q] == 0) continue;
+            if (t[q] > 1) S.pool[pool_dst][w++] = (unsigned short)(S.newpos[p] + (nch - 1 - rnk));
+            ++rnk;
+        }
+    }
+    __syncthreads();
+    *pool_len_out = pool_len;
+    cur ^= 1;
+    cur_n = nxt_n;
+    return new_len;
+}
+
+__global__ void __launch_bounds__(kQtThreads, 1) quadtree_kernel(OrbDev P) {
+    extern __shared__ __align__(16) uint8_t qsmem[];
+    QtShared &S = *reinterpret_cast<QtShared *>(qsmem);
+    const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const LevelInfo &LV = P.lv[l];
+    int *lvl_cnt = P.lvl_cnt + (size_t)b * P.num_levels + l;
+    LevelKp *out = P.lvl_kp + (size_t)b * P.total_slots + LV.slot_base;
+
+    // ---- gather candidates of this level in cell order (prefix over cell counts)
+    const int *cc = P.cell_cnt + (size_t)b * P.num_cells + LV.cell_base;
+    for (int c = tid; c < LV.num_cells; c += kQtThreads) S.scan[c] = cc[c];
+    __syncthreads();
+    int n = block_scan_array(S.scan, LV.num_cells, S.warp_tmp);
+    if (n == 0) {
+        if (tid == 0) *lvl_cnt = 0;
+        return;
+    }
+    if (n > 65535) {
+        n = 65535;
+        if (tid == 0) P.status[b] = 1;
+    }
+    // work arrays: shared memory when they fit, else the global scratch block of this (frame, level)
+    QtArrays A;
+    unsigned short *rank;
+    uint8_t *cls;
+    {
+        uint8_t *base;
+        if (n <= kQtSmemCands) {
+            base = qsmem + ((sizeof(QtShared) + 15) & ~(size_t)15);
+        } else {
+            base = P.qt_scratch + ((size_t)b * P.num_levels + l) * P.qt_scratch_per_job;
+        }
+        const size_t cap = n <= kQtSmemCands ? kQtSmemCands : 65536;
+        A.cand = reinterpret_cast<uint32_t *>(base);
+        base += cap * 4;
+        A.perm[0] = reinterpret_cast<unsigned short *>(base);
+        base += cap * 2;
+        A.perm[1] = reinterpret_cast<unsigned short *>(base);
+        base += cap * 2;
+        A.owner[0] = reinterpret_cast<unsigned short *>(base);
+        base += cap * 2;
+        A.owner[1] = reinterpret_cast<unsigned short *>(base);
+        base += cap * 2;
+        rank = reinterpret_cast<unsigned short *>(base);
+        base += cap * 2;
+        cls = base;
+    }
+    {
+        const uint32_t *cb = P.cell_buf + ((size_t)b * P.num_cells + LV.cell_base) * kCellCap;
+        for (int c = 0; c < LV.num_cells; ++c) {
+            const int o = S.scan[c], k = cc[c];
+            for (int i = tid; i < k; i += kQtThreads)
+                if (o + i < n) A.cand[o + i] = cb[(size_t)c * kCellCap + i];
+        }
+    }
+    __syncthreads();
+
+    // ---- initialize_nodes (orb_extractor.cc:557-637)
+    const int min_x = kPatchRadius, max_x = LV.w - kPatchRadius, min_y = kPatchRadius, max_y = LV.h - kPatchRadius;
+    const double ratio = (double)(max_x - min_x) / (max_y - min_y);
+    int gx, gy;
+    double dx, dy;
+    if (ratio > 1) {
+        gx = (int)round(ratio);
+        gy = 1;
+        dx = (double)(max_x - min_x) / gx;
+        dy = max_y - min_y;
+    } else {
+        gx = 1;
+        gy = (int)round(1 / ratio);
+        dx = max_x - min_y;  // sic, orb_extractor.cc:580
+        dy = (double)(max_y - min_y) / gy;
+    }
+    const int g = gx * gy;  // number of initial nodes (small)
+    int cur = 0, cur_n = 0, len = 0;
+    {
+        // stable counting sort of the candidates by initial node
+        int *cnts = S.scan;  // g entries
+        for (int i = tid; i < g; i += kQtThreads) cnts[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += kQtThreads) {
+            const uint32_t c = A.cand[i];
+            const unsigned ix = (unsigned)((float)cand_x(c) / dx), iy = (unsigned)((float)cand_y(c) / dy);
+            int node = (int)(ix + iy * gx);
+            node = min(node, g - 1);
+            cls[i] = 0;
+            A.owner[0][i] = (unsigned short)node;  // temporarily the initial node index
+            atomicAdd(&cnts[node], 1);
+        }
+        __syncthreads();
+        // node offsets + list (thread 0; g is tiny)
+        if (tid == 0) {
+            int off = 0, pos = 0;
+            for (int i = 0; i < g; ++i) {
+                const int c = cnts[i];
+                S.newpos[i] = off;  // segment start of initial node i
+                if (c > 0) {
+                    const int ix = i % gx, iy = i / gx;
+                    short4 r;
+                    r.x = (short)(int)(dx * ix);
+                    r.y = (short)(int)(dy * iy);
+                    r.z = (short)(int)(dx * (ix + 1));
+                    r.w = (short)(int)(dy * (iy + 1));
+                    S.rect[0][pos] = r;
+                    S.start[0][pos] = (unsigned short)off;
+                    S.cnt[0][pos] = (unsigned short)c;
+                    S.leaf[0][pos] = (c == 1);
+                    S.tot[i] = (unsigned short)pos;  // initial node -> list position
+                    ++pos;
+                }
+                off += c;
+            }
+            S.misc[0] = pos;
+        }
+        __syncthreads();
+        len = S.misc[0];
+        // stable placement: rank of element i inside its initial node = #earlier elements of the same node.
+        // g is tiny, so do one ordered pass per initial node with a block scan of flags.
+        for (int node = 0; node < g; ++node) {
+            if (cnts[node] == 0) continue;
+            const int per = (n + kQtThreads - 1) / kQtThreads;
+            const int i0 = min(n, tid * per), i1 = min(n, i0 + per);
+            int c = 0;
+            for (int i = i0; i < i1; ++i) c += (A.owner[0][i] == node);
+            int tot;
+            int run = block_exclusive_scan(c, S.warp_tmp, &tot);
+            const int base = S.newpos[node];
+            const unsigned short lp = S.tot[node];
+            for (int i = i0; i < i1; ++i)
+                if (A.owner[0][i] == node) {
+                    A.perm[1][base + run] = (unsigned short)i;
+                    A.owner[1][base + run] = lp;
+                    ++run;
+                }
+            __syncthreads();
+        }
+        cur = 1;
+    }
+    const int budget = LV.budget;
+    int pool_len = 0, pool_cur = 0;
+    bool filled = false;
+    unsigned short *proc_list = S.pool_sorted;
+
+    // ---- phase 1 (orb_extractor.cc:482-518)
+    while (true) {
+        const int prev = len;
+        for (int p = tid; p < len; p += kQtThreads) S.sel[p] = S.leaf[cur_n][p] ? 0 : 1;
+        __syncthreads();
+        // processing order = list order of the selected nodes
+        for (int p = tid; p < len; p += kQtThreads) S.scan[p] = S.sel[p];
+        __syncthreads();
+        const int num_proc = block_scan_array(S.scan, len, S.warp_tmp);
+        for (int p = tid; p < len; p += kQtThreads)
+            if (S.sel[p]) proc_list[S.scan[p]] = (unsigned short)p;
+        __syncthreads();
+        segmented_class_scan(A, cur, n, QtNodes{S.rect[cur_n], S.start[cur_n], S.cnt[cur_n], S.leaf[cur_n]}, S.sel,
+                             rank, cls, S.tot, S.carry_tail, S.carry_head);
+        // would the new list overflow the node arrays?
+        len = apply_division(S, A, cur, n, cur_n, len, num_proc, proc_list, rank, cls, &pool_len, pool_cur);
+        if (budget <= len || len == prev) {
+            filled = true;
+            break;
+        }
+        if (budget < len + pool_len) break;
+    }
+    // ---- phase 2 (orb_extractor.cc:520-552)
+    while (!filled) {
+        const int prev = len;
+        const unsigned short *pool = S.pool[pool_cur];
+        for (int p = tid; p < len; p += kQtThreads) S.sel[p] = 0;
+        __syncthreads();
+        for (int k = tid; k < pool_len; k += kQtThreads) S.sel[pool[k]] = 1;
+        __syncthreads();
+        segmented_class_scan(A, cur, n, QtNodes{S.rect[cur_n], S.start[cur_n], S.cnt[cur_n], S.leaf[cur_n]}, S.sel,
+                             rank, cls, S.tot, S.carry_tail, S.carry_head);
+        // sort the pool by (cnt desc, creation desc): rank sort
+        for (int k = tid; k < pool_len; k += kQtThreads) {
+            const int ck = S.cnt[cur_n][pool[k]];
+            int r = 0;
+            for (int j = 0; j < pool_len; ++j) {
+                const int cj = S.cnt[cur_n][pool[j]];
+                r += (cj > ck) || (cj == ck && j > k);
+            }
+            proc_list[r] = pool[k];
+        }
+        __syncthreads();
+        // cut: first t with prev + sum_{i<=t}(nch_i - 1) >= budget
+        for (int k = tid; k < pool_len; k += kQtThreads) {
+            const unsigned short *t = S.tot + proc_list[k] * 4;
+            S.scan[k] = (t[0] > 0) + (t[1] > 0) + (t[2] > 0) + (t[3] > 0) - 1;
+        }
+        if (tid == 0) {
+            S.misc[1] = pool_len;
+            S.misc[2] = 0;
+        }
+        __syncthreads();
+        block_scan_array(S.scan, pool_len, S.warp_tmp);  // exclusive prefix of (nch-1)
+        for (int k = tid; k < pool_len; k += kQtThreads) {
+            const unsigned short *t = S.tot + proc_list[k] * 4;
+            const int inc = (t[0] > 0) + (t[1] > 0) + (t[2] > 0) + (t[3] > 0) - 1;
+            if (prev + S.scan[k] + inc >= budget) {  // list size after dividing the k-th pool node
+                atomicMin(&S.misc[1], k + 1);
+                S.misc[2] = 1;
+            }
+        }
+        __syncthreads();
+        const int num_proc = S.misc[1];
+        const bool reached = S.misc[2] != 0;
+        __syncthreads();
+        // only the first num_proc pool nodes are divided
+        for (int k = num_proc + tid; k < pool_len; k += kQtThreads) S.sel[proc_list[k]] = 0;
+        __syncthreads();
+        len = apply_division(S, A, cur, n, cur_n, len, num_proc, proc_list, rank, cls, &pool_len, pool_cur ^ 1);
+        pool_cur ^= 1;
+        if (reached) filled = true;
+        if (filled || budget <= len || len == prev) break;
+    }
+
+    // ---- find_keypoints_with_max_response (orb_extractor.cc:659-685): first maximum wins
+    const int n_out = min(len, LV.slot_cap);
+    if (len > LV.slot_cap && tid == 0) P.status[b] = 3;
+    for (int p = tid; p < n_out; p += kQtThreads) {
+        const int st = S.start[cur_n][p], c = S.cnt[cur_n][p];
+        uint32_t best = A.cand[A.perm[cur][st]];
+        for (int k = 1; k < c; ++k) {
+            const uint32_t v = A.cand[A.perm[cur][st + k]];
+            if (cand_score(v) > cand_score(best)) best = v;
+        }
+        LevelKp kp;
+        kp.x = (short)(cand_x(best) + kPatchRadius);  // orb_extractor.cc:450-454
+        kp.y = (short)(cand_y(best) + kPatchRadius);
+        kp.response = cand_score(best);
+        out[p] = kp;
+    }
+    if (tid == 0) *lvl_cnt = n_out;
+}
+
+// =====================================================================================================
+// 4. orientation + blur + steered BRIEF, one warp per keypoint
+// =====================================================================================================
+constexpr int kDescWarps = 4;
+constexpr int kSrcDim = 45, kSrcPitch = 48;   // 39 + 2*3
+constexpr int kBlurDim = 39, kBlurPitch = 40;
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (p < 0) p = -p;
+    if (p >= len) p = 2 * (len - 1) - p;
+    return p;
+}
+
+// cv::fastAtan2, f32, no FMA
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
+                p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, ax + (float)2.2204460492503131e-16);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = __fdiv_rn(ax, ay + (float)2.2204460492503131e-16);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// util/trigonometric.h:42-78
+__device__ __forceinline__ float poly_cos(float v) {
+    const float c1 = 0.99940307f, c2 = -0.49558072f, c3 = 0.03679168f;
+    const float v2 = v * v;
+    return c1 + v2 * (c2 + c3 * v2);
+}
+__device__ __forceinline__ float util_cos(float v) {
+    const float PI = 3.14159265358979f, PI_2 = PI / 2.0f, TWO_PI = 2.0f * PI, INV_TWO_PI = 1.0f / TWO_PI,
+                THREE_PI_2 = 3.0f * PI_2;
+    v = v - (float)cv_floor((double)(v * INV_TWO_PI)) * TWO_PI;
+    v = (0.0f < v) ? v : -v;
+    if (v < PI_2) return poly_cos(v);
+    if (v < PI) return -poly_cos(PI - v);
+    if (v < THREE_PI_2) return -poly_cos(v - PI);
+    return poly_cos(TWO_PI - v);
+}
+__device__ __forceinline__ float util_sin(float v) {
+    const float PI_2 = 3.14159265358979f / 2.0f;
+    return util_cos(PI_2 - v);
+}
+
+__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp_keypoint *__restrict__ kp_out,
+                                                                    uint8_t *__restrict__ desc_out,
+                                                                    int32_t *__restrict__ n_out) {
+    __shared__ __align__(16) uint8_t s_src[kDescWarps][kSrcDim * kSrcPitch];
+    __shared__ __align__(16) unsigned short s_h[kDescWarps][kSrcDim * kBlurPitch];
+    __shared__ __align__(16) uint8_t s_blur[kDescWarps][kBlurDim * kBlurPitch];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * kDescWarps + warp;
+    const int *lvl_cnt = P.lvl_cnt + (size_t)b * P.num_levels;
+    // total keypoints of the frame (level-major output order, orb_extractor.cc:137-159)
+    int total = 0;
+    for (int l = 0; l < P.num_levels; ++l) total += lvl_cnt[l];
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_out[b] = min(total, P.out_cap);
+    if (slot >= P.total_slots) return;
+    int l = 0;
+    while (l + 1 < P.num_levels && slot >= P.lv[l + 1].slot_base) ++l;
+    const int idx = slot - P.lv[l].slot_base;
+    if (idx >= lvl_cnt[l]) return;
+    int out_pos = idx;
+    for (int k = 0; k < l; ++k) out_pos += lvl_cnt[k];
+    if (out_pos >= P.out_cap) return;
+    const LevelKp kp = P.lvl_kp[(size_t)b * P.total_slots + slot];
+    const uint8_t *img = level_ptr(P, b, l);
+    const int pitch = level_pitch(P, l), W = P.lv[l].w, H = P.lv[l].h;
+    const int cx = kp.x, cy = kp.y;
+
+    // ---- ic_angle (orb_extractor.cc:708-735): integer moments over the radius-15 disc
+    int m10 = 0, m01 = 0;
+    {
+        const int u = lane - kHalfPatch;  // lanes 0..30 -> u = -15..15
+        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+            const int d = P.u_max[v < 0 ? -v : v];
+            if (lane < 31 && u >= -d && u <= d) {
+                const int val = img[(size_t)(cy + v) * pitch + cx + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- 45x45 source patch (reflect-101 at the image border), separable Q8 Gaussian 7x7 sigma 2
+    uint8_t *src = s_src[warp];
+    unsigned short *hbuf = s_h[warp];
+    uint8_t *blur = s_blur[warp];
+    for (int i = lane; i < kSrcDim * kSrcDim; i += 32) {
+        const int py = i / kSrcDim, px = i - py * kSrcDim;
+        const int gy = reflect101(cy - 22 + py, H), gx = reflect101(cx - 22 + px, W);
+        src[py * kSrcPitch + px] = img[(size_t)gy * pitch + gx];
+    }
+    __syncwarp();
+    for (int i = lane; i < kSrcDim * kBlurDim; i += 32) {
+        const int py = i / kBlurDim, px = i - py * kBlurDim;
+        const uint8_t *s = src + py * kSrcPitch + px;
+        const int acc = 18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3];
+        hbuf[py * kBlurPitch + px] = (unsigned short)acc;
+    }
+    __syncwarp();
+    for (int i = lane; i < kBlurDim * kBlurDim; i += 32) {
+        const int py = i / kBlurDim, px = i - py * kBlurDim;
+        const unsigned short *hcol = hbuf + py * kBlurPitch + px;
+        const unsigned acc = 18u * (hcol[0] + hcol[6 * kBlurPitch]) + 34u * (hcol[kBlurPitch] + hcol[5 * kBlurPitch]) +
+                             48u * (hcol[2 * kBlurPitch] + hcol[4 * kBlurPitch]) + 56u * hcol[3 * kBlurPitch];
+        blur[py * kBlurPitch + px] = (uint8_t)((acc + 32768u) >> 16);
+    }
+    __syncwarp();
+
+    // ---- steered BRIEF (orb_extractor.cc:747-807): lane i produces descriptor byte i
+    const float ang_rad = (float)((double)angle * 3.14159265358979323846 / 180.0);
+    const float ca = util_cos(ang_rad), sa = util_sin(ang_rad);
+    const uint8_t *center = blur + 19 * kBlurPitch + 19;
+    int val = 0;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const int k = lane * 8 + bit;
+        const float x1 = (float)kBriefX1[k], y1 = (float)kBriefY1[k], x2 = (float)kBriefX2[k], y2 = (float)kBriefY2[k];
+        const int r1 = __float2int_rn(x1 * sa + y1 * ca), c1 = __float2int_rn(x1 * ca - y1 * sa);
+        const int r2 = __float2int_rn(x2 * sa + y2 * ca), c2 = __float2int_rn(x2 * ca - y2 * sa);
+        val |= (center[r1 * kBlurPitch + c1] < center[r2 * kBlurPitch + c2]) << bit;
+    }
+    desc_out[((size_t)b * P.out_cap + out_pos) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        plp_keypoint o;
+        const float s = P.lv[l].scale_factor;
+        o.x = l == 0 ? (float)cx : (float)cx * s;  // orb_extractor.cc:695-706
+        o.y = l == 0 ? (float)cy : (float)cy * s;
+        o.size = P.lv[l].size;
+        o.angle = angle;
+        o.response = (float)kp.response;
+        o.octave = l;
+        o.class_id = -1;
+        kp_out[(size_t)b * P.out_cap + out_pos] = o;
+    }
+}
+
+}  // namespace
+
+}  // namespace plp
+
+// =========================================================================================================
+// handle + C ABI
+// =========================================================================================================
+using namespace plp;
+
+struct plp_orb {
+    plp_ctx *ctx = nullptr;
+    plp_orb_params params;
+    int rows = 0, cols = 0, max_batch = 0;
+    OrbDev dev;  // device pointers filled in at create
+    std::vector<float> scale_factors, inv_scale_factors, level_sigma_sq, inv_level_sigma_sq;
+    std::vector<uint32_t> num_keypts_per_level;
+    std::vector<CellDesc> cells;
+    short4 *d_xtab[kMaxLevels] = {nullptr};
+    short4 *d_ytab[kMaxLevels] = {nullptr};
+    CellDesc *d_cells = nullptr;
+    uint8_t *d_pyr = nullptr;
+    uint8_t *d_img = nullptr;  // staging for host-pointer extraction (max_batch frames)
+    uint8_t *d_mask = nullptr;
+    uint32_t *d_cell_buf = nullptr;
+    int *d_cell_cnt = nullptr;
+    LevelKp *d_lvl_kp = nullptr;
+    int *d_lvl_cnt = nullptr;
+    uint8_t *d_qt_scratch = nullptr;
+    int *d_status = nullptr;
+    plp_keypoint *d_kp = nullptr;
+    uint8_t *d_desc = nullptr;
+    int32_t *d_n = nullptr;
+    size_t qt_smem = 0;
+    int last_batch = 0;
+    const uint8_t *last_img0 = nullptr;
+    size_t last_step = 0;
+};
+
+static int cv_round_host(double v) { return (int)lrint(v); }
+
+static void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<short4> &xt, std::vector<short4> &yt) {
+    // cv::resize INTER_LINEAR 8U: 11-bit coefficients, rounded half-to-even
+    const double inv_scale_x = (double)dw / sw, inv_scale_y = (double)dh / sh;
+    const double scale_x = 1. / inv_scale_x, scale_y = 1. / inv_scale_y;
+    xt.resize(dw);
+    yt.resize(dh);
+    for (int dx = 0; dx < dw; ++dx) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = cv_floor(fx);
+        fx -= sx;
+        if (sx < 0) {
+            fx = 0;
+            sx = 0;
+        }
+        if (sx >= sw - 1) {
+            fx = 0;
+            sx = sw - 1;
+        }
+        short4 t;
+        t.x = (short)sx;
+        t.y = (short)std::min(sx + 1, sw - 1);
+        t.z = (short)lrintf((1.f - fx) * 2048);
+        t.w = (short)lrintf(fx * 2048);
+        xt[dx] = t;
+    }
+    for (int dy = 0; dy < dh; ++dy) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = cv_floor(fy);
+        fy -= sy;
+        short4 t;
+        t.x = (short)std::min(std::max(sy, 0), sh - 1);
+        t.y = (short)std::min(std::max(sy + 1, 0), sh - 1);
+        t.z = (short)lrintf((1.f - fy) * 2048);
+        t.w = (short)lrintf(fy * 2048);
+        yt[dy] = t;
+    }
+}
+
+extern "C" {
+
+void plp_orb_destroy(plp_orb *o) {
+    if (!o) return;
+    cudaSetDevice(o->ctx->device);
+    cudaStreamSynchronize(o->ctx->stream);
+    for (int l = 0; l < kMaxLevels; ++l) {
+        if (o->d_xtab[l]) cudaFree(o->d_xtab[l]);
+        if (o->d_ytab[l]) cudaFree(o->d_ytab[l]);
+    }
+    void *ptrs[] = {o->d_cells, o->d_pyr, o->d_img, o->d_mask, o->d_cell_buf, o->d_cell_cnt, o->d_lvl_kp,
+                    o->d_lvl_cnt, o->d_qt_scratch, o->d_status, o->d_kp, o->d_desc, o->d_n};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete o;
+}
+
+plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, int cols, int max_batch,
+                          plp_orb **out) {
+    PLP_REQUIRE(ctx && params && out, "null pointer");
+    *out = nullptr;
+    PLP_REQUIRE(rows > 0 && cols > 0 && max_batch > 0, "image size / batch");
+    PLP_REQUIRE(params->num_levels >= 1 && params->num_levels <= kMaxLevels, "num_levels in [1,16]");
+    PLP_REQUIRE(params->scale_factor > 1.0f || params->num_levels == 1, "scale_factor > 1");
+    PLP_REQUIRE(cols <= 2047 + 2 * kPatchRadius && rows <= 1023 + 2 * kPatchRadius,
+                "image larger than 2085 x 1061 (packed candidate coordinates)");
+    PLP_REQUIRE(params->ini_fast_thr < 255 && params->min_fast_thr >= 1 && params->min_fast_thr <= params->ini_fast_thr,
+                "FAST thresholds: 1 <= min <= ini < 255");
+    PLP_CUDA_TRY(cudaSetDevice(ctx->device));
+    plp_orb *o = new plp_orb();
+    o->ctx = ctx;
+    o->params = *params;
+    o->rows = rows;
+    o->cols = cols;
+    o->max_batch = max_batch;
+    const unsigned L = params->num_levels;
+    // ---- orb_params.cc:86-128 scale tables
+    o->scale_factors.assign(L, 1.0f);
+    o->inv_scale_factors.assign(L, 1.0f);
+    o->level_sigma_sq.assign(L, 1.0f);
+    o->inv_level_sigma_sq.assign(L, 1.0f);
+    for (unsigned l = 1; l < L; ++l) o->scale_factors[l] = params->scale_factor * o->scale_factors[l - 1];
+    for (unsigned l = 1; l < L; ++l) o->inv_scale_factors[l] = (1.0f / params->scale_factor) * o->inv_scale_factors[l - 1];
+    {
+        float s = 1.0f;
+        for (unsigned l = 1; l < L; ++l) {
+            s = params->scale_factor * s;
+            o->level_sigma_sq[l] = s * s;
+            o->inv_level_sigma_sq[l] = 1.0f / (s * s);
+        }
+    }
+    // ---- orb_extractor.cc:244-253 per-level budget
+    o->num_keypts_per_level.resize(L);
+    {
+        double desired = params->max_num_keypts * (1.0 - 1.0 / params->scale_factor) /
+                         (1.0 - std::pow(1.0 / params->scale_factor, static_cast<double>(L)));
+        if (L == 1) desired = params->max_num_keypts;
+        unsigned total = 0;
+        for (unsigned l = 0; l + 1 < L; ++l) {
+            o->num_keypts_per_level[l] = (unsigned)std::round(desired);
+            total += o->num_keypts_per_level[l];
+            desired *= 1.0 / params->scale_factor;
+        }
+        o->num_keypts_per_level[L - 1] = (unsigned)std::max((int)params->max_num_keypts - (int)total, 0);
+    }
+    OrbDev &D = o->dev;
+    memset(&D, 0, sizeof(D));
+    D.num_levels = (int)L;
+    D.rows = rows;
+    D.cols = cols;
+    D.ini_thr = (int)params->ini_fast_thr;
+    D.min_thr = (int)params->min_fast_thr;
+    // ---- orb_extractor.cc:270-286 u_max
+    {
+        const unsigned vmax = (unsigned)std::floor(kHalfPatch * std::sqrt(2.0) / 2 + 1);
+        const unsigned vmin = (unsigned)std::ceil(kHalfPatch * std::sqrt(2.0) / 2);
+        for (unsigned v = 0; v <= vmax; ++v)
+            D.u_max[v] = (int)std::round(std::sqrt((double)kHalfPatch * kHalfPatch - (double)v * v));
+        for (unsigned v = kHalfPatch, v0 = 0; vmin <= v; --v) {
+            while (D.u_max[v0] == D.u_max[v0 + 1]) ++v0;
+            D.u_max[v] = (int)v0;
+            ++v0;
+        }
+    }
+    // ---- level geometry, cells (orb_extractor.cc:344-392)
+    size_t pyr_bytes = 0;
+    int slot_base = 0, cell_base = 0;
+    plp_status st = PLP_OK;
+    for (unsigned l = 0; l < L; ++l) {
+        LevelInfo &V = D.lv[l];
+        if (l == 0) {
+            V.w = cols;
+            V.h = rows;
+        } else {
+            const double scale = o->scale_factors[l];
+            V.w = (int)std::round(cols * 1.0 / scale);
+            V.h = (int)std::round(rows * 1.0 / scale);
+        }
+        V.pitch = (V.w + 63) & ~63;
+        V.offset = pyr_bytes;
+        if (l > 0) pyr_bytes += (size_t)V.pitch * V.h + 256;
+        pyr_bytes = (pyr_bytes + 255) & ~(size_t)255;
+        V.budget = (int)o->num_keypts_per_level[l];
+        V.scale_factor = o->scale_factors[l];
+        V.size = (float)(unsigned)(31 * o->scale_factors[l]);
+        V.slot_base = slot_base;
+        {
+            // initial nodes of the quadtree (orb_extractor.cc:561-582): one sweep can quadruple them
+            int g0 = 1;
+            if (V.w > 2 * kPatchRadius && V.h > 2 * kPatchRadius) {
+                const double ratio = (double)(V.w - 2 * kPatchRadius) / (V.h - 2 * kPatchRadius);
+                g0 = ratio > 1 ? (int)std::round(ratio) : (int)std::round(1 / ratio);
+            }
+            V.slot_cap = 4 * std::max(V.budget, g0) + 8;
+        }
+        slot_base += V.slot_cap;
+        V.cell_base = cell_base;
+        V.num_cells = 0;
+        if (V.slot_cap > kNodeCap) {
+            set_error("orb: level %u budget %d exceeds the quadtree node capacity", l, V.budget);
+            st = PLP_ERR_CAPACITY;
+        }
+        if (V.w > 2 * kPatchRadius && V.h > 2 * kPatchRadius && V.w >= 1 && V.h >= 1) {
+            const unsigned min_bx = kPatchRadius, min_by = kPatchRadius;
+            const unsigned max_bx = V.w - kPatchRadius, max_by = V.h - kPatchRadius;
+            const unsigned width = max_bx - min_bx, height = max_by - min_by;
+            const unsigned ncols = width / kCellSize + 1, nrows = height / kCellSize + 1;
+            V.cells_x = (int)ncols;
+            V.cells_y = (int)nrows;
+            for (unsigned i = 0; i < nrows; ++i) {
+                const unsigned min_y = min_by + i * kCellSize;
+                if (max_by - kOverlap <= min_y || max_by < kOverlap) continue;
+                unsigned max_y = min_y + kCellSize + kOverlap;
+                if (max_by < max_y) max_y = max_by;
+                for (unsigned j = 0; j < ncols; ++j) {
+                    const unsigned min_x = min_bx + j * kCellSize;
+                    if (max_bx - kOverlap <= min_x || max_bx < kOverlap) continue;
+                    unsigned max_x = min_x + kCellSize + kOverlap;
+                    if (max_bx < max_x) max_x = max_bx;
+                    CellDesc c;
+                    c.level = (short)l;
+                    c.i = (short)i;
+                    c.j = (short)j;
+                    c.pad = 0;
+                    c.min_x = (short)min_x;
+                    c.min_y = (short)min_y;
+                    c.max_x = (short)max_x;
+                    c.max_y = (short)max_y;
+                    o->cells.push_back(c);
+                    V.num_cells++;
+                }
+            }
+        }
+        cell_base += V.num_cells;
+    }
+    if (st != PLP_OK) {
+        delete o;
+        return st;
+    }
+    D.num_cells = cell_base;
+    D.total_slots = slot_base;
+    D.out_cap = slot_base;
+    D.pyr_frame_bytes = pyr_bytes ? pyr_bytes : 256;
+    const size_t B = (size_t)max_batch;
+    // ---- device allocations
+#define ORB_ALLOC(ptr, bytes)                                              \
+    do {                                                                   \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes) ? (bytes) : 256); \
+        if (e_ != cudaSuccess) {                                           \
+            set_error("orb: cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); \
+            plp_orb_destroy(o);                                            \
+            return PLP_ERR_CUDA;                                           \
+        }                                                                  \
+    } while (0)
+    for (unsigned l = 1; l < L; ++l) {
+        std::vector<short4> xt, yt;
+        build_resize_tables(D.lv[l - 1].w, D.lv[l - 1].h, D.lv[l].w, D.lv[l].h, xt, yt);
+        ORB_ALLOC(o->d_xtab[l], xt.size() * sizeof(short4));
+        ORB_ALLOC(o->d_ytab[l], yt.size() * sizeof(short4));
+        cudaMemcpy(o->d_xtab[l], xt.data(), xt.size() * sizeof(short4), cudaMemcpyHostToDevice);
+        cudaMemcpy(o->d_ytab[l], yt.data(), yt.size() * sizeof(short4), cudaMemcpyHostToDevice);
+    }
+    ORB_ALLOC(o->d_cells, o->cells.size() * sizeof(CellDesc));
+    if (!o->cells.empty())
+        cudaMemcpy(o->d_cells, o->cells.data(), o->cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice);
+    ORB_ALLOC(o->d_pyr, B * D.pyr_frame_bytes);
+    ORB_ALLOC(o->d_img, B * (size_t)rows * cols);
+    ORB_ALLOC(o->d_mask, (size_t)rows * cols);
+    ORB_ALLOC(o->d_cell_buf, B * (size_t)D.num_cells * kCellCap * sizeof(uint32_t));
+    ORB_ALLOC(o->d_cell_cnt, B * (size_t)D.num_cells * sizeof(int));
+    ORB_ALLOC(o->d_lvl_kp, B * (size_t)D.total_slots * sizeof(LevelKp));
+    ORB_ALLOC(o->d_lvl_cnt, B * L * sizeof(int));
+    D.qt_scratch_per_job = (size_t)65536 * (4 + 2 * 5 + 1) + 256;
+    ORB_ALLOC(o->d_qt_scratch, B * L * D.qt_scratch_per_job);
+    ORB_ALLOC(o->d_status, B * sizeof(int));
+    ORB_ALLOC(o->d_kp, B * (size_t)D.out_cap * sizeof(plp_keypoint));
+    ORB_ALLOC(o->d_desc, B * (size_t)D.out_cap * 32);
+    ORB_ALLOC(o->d_n, B * sizeof(int32_t));
+#undef ORB_ALLOC
+    D.pyr = o->d_pyr;
+    D.cells = o->d_cells;
+    D.cell_buf = o->d_cell_buf;
+    D.cell_cnt = o->d_cell_cnt;
+    D.lvl_kp = o->d_lvl_kp;
+    D.lvl_cnt = o->d_lvl_cnt;
+    D.qt_scratch = o->d_qt_scratch;
+    D.status = o->d_status;
+    o->qt_smem = ((sizeof(QtShared) + 15) & ~(size_t)15) + (size_t)kQtSmemCands * (4 + 2 * 5 + 1) + 64;
+    cudaError_t e = cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->qt_smem);
+    if (e != cudaSuccess) {
+        set_error("orb: quadtree kernel needs %zu bytes of shared memory: %s", o->qt_smem, cudaGetErrorString(e));
+        plp_orb_destroy(o);
+        return PLP_ERR_CUDA;
+    }
+    *out = o;
+    return PLP_OK;
+}
+
+int plp_orb_capacity(const plp_orb *o) { return o ? o->dev.out_cap : 0; }
+
+plp_status plp_orb_get_tables(const plp_orb *o, float *sf, float *isf, float *ls, float *ils, uint32_t *nk) {
+    PLP_REQUIRE(o, "orb");
+    for (int l = 0; l < o->dev.num_levels; ++l) {
+        if (sf) sf[l] = o->scale_factors[l];
+        if (isf) isf[l] = o->inv_scale_factors[l];
+        if (ls) ls[l] = o->level_sigma_sq[l];
+        if (ils) ils[l] = o->inv_level_sigma_sq[l];
+        if (nk) nk[l] = o->num_keypts_per_level[l];
+    }
+    return PLP_OK;
+}
+
+static plp_status orb_run(plp_orb *o, const uint8_t *d_imgs, int batch, size_t step, const uint8_t *d_mask,
+                          size_t mask_step, plp_keypoint *d_kp, uint8_t *d_desc, int32_t *d_n, int32_t *d_status) {
+    plp_ctx *ctx = o->ctx;
+    OrbDev D = o->dev;
+    D.img0 = d_imgs;
+    D.img0_step = step;
+    D.img0_frame_stride = step * (size_t)o->rows;
+    D.mask = d_mask;
+    D.mask_step = mask_step;
+    D.status = d_status ? d_status : o->d_status;
+    o->last_batch = batch;
+    o->last_img0 = d_imgs;
+    o->last_step = step;
+    PLP_CUDA_TRY(cudaMemsetAsync(D.status, 0, (size_t)batch * sizeof(int), ctx->stream));
+    for (int l = 1; l < D.num_levels; ++l) {
+        const int quads = ((D.lv[l].w + 3) >> 2) * D.lv[l].h;
+        if (quads <= 0) continue;
+        dim3 grid(div_up(quads, 256), batch);
+        PLP_LAUNCH(ctx, pyr_resize_kernel, grid, 256, 0, D, l, o->d_xtab[l], o->d_ytab[l]);
+    }
+    if (D.num_cells > 0) {
+        dim3 grid(D.num_cells, batch);
+        PLP_LAUNCH(ctx, fast_cells_kernel, grid, 256, 0, D);
+    }
+    {
+        dim3 grid(D.num_levels, batch);
+        PLP_LAUNCH(ctx, quadtree_kernel, grid, kQtThreads, o->qt_smem, D);
+    }
+    {
+        dim3 grid(div_up(D.total_slots, kDescWarps), batch);
+        PLP_LAUNCH(ctx, describe_kernel, grid, kDescWarps * 32, 0, D, d_kp, d_desc, d_n);
+    }
+    PLP_CHECK_LAUNCH();
+    return PLP_OK;
+}
+
+plp_status plp_orb_extract_batch_dev(plp_orb *o, const uint8_t *d_imgs, int batch, size_t step, plp_keypoint *d_kp,
+                                     uint8_t *d_desc, int32_t *d_n, int32_t *d_status) {
+    PLP_REQUIRE(o && d_imgs && d_kp && d_desc && d_n, "null pointer");
+    PLP_REQUIRE(batch >= 1 && batch <= o->max_batch, "batch exceeds the handle's max_batch");
+    PLP_REQUIRE(step >= (size_t)o->cols, "step < cols");
+    PLP_CUDA_TRY(cudaSetDevice(o->ctx->device));
+    return orb_run(o, d_imgs, batch, step, nullptr, 0, d_kp, d_desc, d_n, d_status);
+}
+
+static plp_status orb_extract_host(plp_orb *o, const uint8_t *imgs, int batch, size_t step, const uint8_t *mask,
+                                   size_t mask_step, plp_keypoint *kp_out, uint8_t *desc_out, int32_t *n_out) {
+    plp_ctx *ctx = o->ctx;
+    PLP_CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t rows = o->rows, cols = o->cols;
+    PLP_CUDA_TRY(cudaMemcpy2DAsync(o->d_img, cols, imgs, step, cols, rows * (size_t)batch, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+    const uint8_t *d_mask = nullptr;
+    if (mask) {
+        PLP_CUDA_TRY(cudaMemcpy2DAsync(o->d_mask, cols, mask, mask_step, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
+        d_mask = o->d_mask;
+    }
+    PLP_TRY(orb_run(o, o->d_img, batch, cols, d_mask, cols, o->d_kp, o->d_desc, o->d_n, nullptr));
+    const size_t cap = o->dev.out_cap;
+    PLP_CUDA_TRY(cudaMemcpyAsync(n_out, o->d_n, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaMemcpyAsync(kp_out, o->d_kp, (size_t)batch * cap * sizeof(plp_keypoint), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    PLP_CUDA_TRY(cudaMemcpyAsync(desc_out, o->d_desc, (size_t)batch * cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int> status(batch);
+    PLP_CUDA_TRY(cudaMemcpyAsync(status.data(), o->d_status, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < batch; ++b)
+        if (status[b] != 0) {
+            set_error("orb: capacity overflow in frame %d (code %d)", b, status[b]);
+            return PLP_ERR_CAPACITY;
+        }
+    return PLP_OK;
+}
+
+plp_status plp_orb_extract(plp_orb *o, const uint8_t *img, int rows, int cols, size_t step, const uint8_t *mask,
+                           size_t mask_step, plp_keypoint *kp_out, uint8_t *desc_out, int *n_out) {
+    PLP_REQUIRE(o && n_out, "null pointer");
+    *n_out = 0;
+    if (!img || rows == 0 || cols == 0) return PLP_OK;  // orb_extractor.cc:76-79
+    PLP_REQUIRE(rows == o->rows && cols == o->cols, "image size differs from the handle's");
+    PLP_REQUIRE(kp_out && desc_out, "null output");
+    PLP_REQUIRE(step >= (size_t)cols && (!mask || mask_step >= (size_t)cols), "step < cols");
+    int32_t n = 0;
+    PLP_TRY(orb_extract_host(o, img, 1, step, mask, mask_step, kp_out, desc_out, &n));
+    *n_out = n;
+    return PLP_OK;
+}
+
+plp_status plp_orb_extract_batch(plp_orb *o, const uint8_t *imgs, int batch, size_t step, plp_keypoint *kp_out,
+                                 uint8_t *desc_out, int32_t *n_out) {
+    PLP_REQUIRE(o && imgs && kp_out && desc_out && n_out, "null pointer");
+    PLP_REQUIRE(batch >= 1 && batch <= o->max_batch, "batch exceeds the handle's max_batch");
+    PLP_REQUIRE(step >= (size_t)o->cols, "step < cols");
+    return orb_extract_host(o, imgs, batch, step, nullptr, 0, kp_out, desc_out, n_out);
+}
+
+plp_status plp_orb_get_pyramid(const plp_orb *o, int b, int level, plp_image_view *out) {
+    PLP_REQUIRE(o && out, "null pointer");
+    PLP_REQUIRE(b >= 0 && b < o->last_batch && level >= 0 && level < o->dev.num_levels, "index");
+    const LevelInfo &V = o->dev.lv[level];
+    out->rows = V.h;
+    out->cols = V.w;
+    if (level == 0) {
+        out->data = o->last_img0 + (size_t)b * o->last_step * o->rows;
+        out->step = o->last_step;
+    } else {
+        out->data = o->d_pyr + (size_t)b * o->dev.pyr_frame_bytes + V.offset;
+        out->step = V.pitch;
+    }
+    return PLP_OK;
+}
+
+plp_status plp_orb_debug_candidates(plp_orb *o, int b, int level, plp_keypoint *out, int cap, int *n_out) {
+    PLP_REQUIRE(o && out && n_out, "null pointer");
+    PLP_REQUIRE(b >= 0 && b < o->last_batch && level >= 0 && level < o->dev.num_levels, "index");
+    plp_ctx *ctx = o->ctx;
+    PLP_CUDA_TRY(cudaSetDevice(ctx->device));
+    const LevelInfo &V = o->dev.lv[level];
+    std::vector<int> cnt(V.num_cells);
+    std::vector<uint32_t> buf((size_t)V.num_cells * kCellCap);
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (V.num_cells) {
+        PLP_CUDA_TRY(cudaMemcpy(cnt.data(), o->d_cell_cnt + (size_t)b * o->dev.num_cells + V.cell_base,
+                                cnt.size() * 4, cudaMemcpyDeviceToHost));
+        PLP_CUDA_TRY(cudaMemcpy(buf.data(), o->d_cell_buf + ((size_t)b * o->dev.num_cells + V.cell_base) * kCellCap,
+                                buf.size() * 4, cudaMemcpyDeviceToHost));
+    }
+    int n = 0;
+    for (int c = 0; c < V.num_cells; ++c)
+        for (int k = 0; k < cnt[c]; ++k) {
+            if (n < cap) {
+                const uint32_t v = buf[(size_t)c * kCellCap + k];
+                plp_keypoint kp;
+                kp.x = (float)(v & 0x7ff);
+                kp.y = (float)((v >> 11) & 0x3ff);
+                kp.size = 7.f;
+                kp.angle = -1.f;
+                kp.response = (float)(v >> 21);
+                kp.octave = 0;
+                kp.class_id = -1;
+                out[n] = kp;
+            }
+            ++n;
+        }
+    *n_out = n;
+    return PLP_OK;
+}
+
+}  // extern "C"
