@@ -165,25 +165,30 @@ __device__ __forceinline__ int fast_m(const uint8_t *p, int t) {
     c &= c >> 4;
     c &= bright >> 8;
     if (((a | c) & 0xffffu) == 0) return 0;
-    // exact score: sliding window min / max of length 9 over the circular ring (doubling)
-    int mn2[16], mx2[16];
+    // exact score: sliding-window minimum of length 9 over the circular ring (doubling), once on d = v - ring
+    // (dark arcs) and once on e = ring - v (bright arcs).  NB: written with minima only -- ptxas 12.9 for
+    // sm_100a miscompiles max(a, -max(...)) (drops the negation when fusing into VIMNMX3), see DESIGN.md.
+    int e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = -d[k];
+    int d2[16], e2[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        mn2[k] = min(d[k], d[(k + 1) & 15]);
-        mx2[k] = max(d[k], d[(k + 1) & 15]);
+        d2[k] = min(d[k], d[(k + 1) & 15]);
+        e2[k] = min(e[k], e[(k + 1) & 15]);
     }
-    int mn4[16], mx4[16];
+    int d4[16], e4[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
-        mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+        d4[k] = min(d2[k], d2[(k + 2) & 15]);
+        e4[k] = min(e2[k], e2[(k + 2) & 15]);
     }
     int best = -255;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(mn9, -mx9));
+        const int d9 = min(min(d4[k], d4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int e9 = min(min(e4[k], e4[(k + 4) & 15]), e[(k + 8) & 15]);
+        best = max(best, max(d9, e9));
     }
     return best;
 }
