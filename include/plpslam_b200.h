@@ -271,6 +271,55 @@ PLP_API plp_status plp_orb_get_pyramid(const plp_orb *orb, int b, int level, plp
 PLP_API plp_status plp_orb_debug_candidates(plp_orb *orb, int b, int level, plp_keypoint *out, int cap,
                                             int *n_out);
 
+/* ------------------------------------------------------------------------ */
+/* motion-only BA  (optimize/pose_optimizer.cc, pose_optimizer_extended_line.cc) */
+/* ------------------------------------------------------------------------ */
+typedef struct plp_pt_obs { /* one matched keypoint (pose_optimizer.cc:126-151) */
+    double pos_w[3];        /* lm->get_pos_in_world()                                  */
+    float obs_x, obs_y;     /* undist_keypts_[idx].pt                                  */
+    float x_right;          /* stereo_x_right_[idx]; < 0 => monocular 2-D edge         */
+    float inv_sigma_sq;     /* inv_level_sigma_sq_[undist_keypt.octave]                */
+} plp_pt_obs;
+
+typedef struct plp_line_obs { /* one matched keyline (pose_optimizer_extended_line.cc:160-188) */
+    double plucker[6];        /* Line::get_PlueckerCoord(): (n, d), data/landmark_line.cc:60-77 */
+    float sp_x, sp_y, ep_x, ep_y; /* _keylsd[idx].getStartPoint()/getEndPoint()          */
+    float inv_sigma_sq;       /* _inv_level_sigma_sq_lsd[keyline.octave]                 */
+    float pad;
+} plp_line_obs;
+
+typedef struct plp_pose_opt_cfg {
+    int32_t num_trials;    /* 4  (optimize/pose_optimizer.h:46) */
+    int32_t num_each_iter; /* 10 */
+} plp_pose_opt_cfg;
+
+/* optimize::pose_optimizer::optimize(data::frame&) (pose_optimizer.cc:53-229) when n_lines == 0 and
+ * pose_optimizer_extended_line::optimize (pose_optimizer_extended_line.cc:62-305) otherwise.
+ * pts/lines hold only the keypoints/keylines that own a landmark (the adapter keeps the index map).
+ * Returns through n_inliers_out the reference's return value (num_init_obs - num_bad_obs); when fewer than
+ * 5 point observations are given the pose is left untouched and 0 is returned (pose_optimizer.cc:153-156). */
+PLP_API plp_status plp_pose_optimize(plp_ctx *ctx, const plp_camera *cam, const double *T_cw_in /*4x4*/,
+                                     const plp_pt_obs *pts, int n_pts, const plp_line_obs *lines, int n_lines,
+                                     const plp_pose_opt_cfg *cfg, double *T_cw_out /*4x4*/, uint8_t *pt_outlier,
+                                     uint8_t *line_outlier, int32_t *n_inliers_out);
+
+/* Batched: frame b owns pts[pt_offsets[b] .. pt_offsets[b+1]) and lines[line_offsets[b] .. line_offsets[b+1]).
+ * Host pointers; one launch for the whole batch (one CTA per frame). */
+PLP_API plp_status plp_pose_optimize_batch(plp_ctx *ctx, const plp_camera *cam, int batch, const double *T_cw_in,
+                                           const plp_pt_obs *pts, const int32_t *pt_offsets,
+                                           const plp_line_obs *lines, const int32_t *line_offsets,
+                                           const plp_pose_opt_cfg *cfg, double *T_cw_out, uint8_t *pt_outlier,
+                                           uint8_t *line_outlier, int32_t *n_inliers_out);
+/* Device-resident variant of the batched call (all pointers in HBM, no synchronisation).
+ * d_lm_iters_out (optional, batch entries) receives the number of LM iterations executed per frame. */
+PLP_API plp_status plp_pose_optimize_batch_dev(plp_ctx *ctx, const plp_camera *cam, int batch,
+                                               const double *d_T_cw_in, const plp_pt_obs *d_pts,
+                                               const int32_t *d_pt_offsets, const plp_line_obs *d_lines,
+                                               const int32_t *d_line_offsets, int max_edges_per_frame,
+                                               const plp_pose_opt_cfg *cfg, double *d_T_cw_out,
+                                               uint8_t *d_pt_outlier, uint8_t *d_line_outlier,
+                                               int32_t *d_n_inliers_out, int32_t *d_lm_iters_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,8 @@ from .capi import (  # noqa: F401
     Context,
     OrbExtractor,
     KP_DTYPE,
+    PT_OBS_DTYPE,
+    LINE_OBS_DTYPE,
     PlpError,
     lib,
     lib_path,

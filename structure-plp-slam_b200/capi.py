@@ -99,6 +99,16 @@ class ImageView(C.Structure):
     _fields_ = [("data", _P), ("rows", C.c_int32), ("cols", C.c_int32), ("step", C.c_size_t)]
 
 
+PT_OBS_DTYPE = np.dtype([("pos_w", "<f8", 3), ("obs_x", "<f4"), ("obs_y", "<f4"), ("x_right", "<f4"),
+                         ("inv_sigma_sq", "<f4")])
+LINE_OBS_DTYPE = np.dtype([("plucker", "<f8", 6), ("sp_x", "<f4"), ("sp_y", "<f4"), ("ep_x", "<f4"), ("ep_y", "<f4"),
+                           ("inv_sigma_sq", "<f4"), ("pad", "<f4")])
+
+
+class PoseOptCfg(C.Structure):
+    _fields_ = [("num_trials", C.c_int32), ("num_each_iter", C.c_int32)]
+
+
 # binary layout of plp_keypoint / cv::KeyPoint
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                      ("octave", "<i4"), ("class_id", "<i4")])
@@ -277,6 +287,38 @@ class Context:
             self._h, C.byref(fl), sf.ctypes.data_as(_P), C.c_int(len(sf)), C.byref(cam), Tc.ctypes.data_as(_P),
             Tl.ctypes.data_as(_P), C.byref(ll), C.c_float(margin), matched.ctypes.data_as(_P), C.byref(num)))
         return matched, int(num.value)
+
+    # ------------------------------------------------------------------ optimize::pose_optimizer
+    def pose_optimize(self, cam, T_cw, pts, lines=None, num_trials=4, num_each_iter=10):
+        """pose_optimizer::optimize / pose_optimizer_extended_line::optimize for one frame."""
+        r = self.pose_optimize_batch(cam, [T_cw], [pts], None if lines is None else [lines], num_trials, num_each_iter)
+        return r[0][0], r[1][0], (None if lines is None else r[2][0]), int(r[3][0])
+
+    def pose_optimize_batch(self, cam, T_cws, pts_list, lines_list=None, num_trials=4, num_each_iter=10):
+        B = len(pts_list)
+        T_in = np.ascontiguousarray(np.stack([np.asarray(t, np.float64).reshape(4, 4) for t in T_cws]))
+        pts = np.ascontiguousarray(np.concatenate([np.asarray(p, PT_OBS_DTYPE) for p in pts_list]) if B else
+                                   np.zeros(0, PT_OBS_DTYPE))
+        po = np.zeros(B + 1, np.int32)
+        po[1:] = np.cumsum([len(p) for p in pts_list])
+        has_lines = lines_list is not None and sum(len(l) for l in lines_list) > 0
+        if has_lines:
+            lines = np.ascontiguousarray(np.concatenate([np.asarray(l, LINE_OBS_DTYPE) for l in lines_list]))
+            lo = np.zeros(B + 1, np.int32)
+            lo[1:] = np.cumsum([len(l) for l in lines_list])
+        T_out = np.zeros((B, 4, 4), np.float64)
+        pout = np.zeros(max(len(pts), 1), np.uint8)
+        lout = np.zeros(max(len(lines) if has_lines else 0, 1), np.uint8)
+        ninl = np.zeros(B, np.int32)
+        cfg = PoseOptCfg(num_trials, num_each_iter)
+        self._check(self._lib.plp_pose_optimize_batch(
+            self._h, C.byref(cam), C.c_int(B), T_in.ctypes.data_as(_P), pts.ctypes.data_as(_P), po.ctypes.data_as(_P),
+            lines.ctypes.data_as(_P) if has_lines else None, lo.ctypes.data_as(_P) if has_lines else None,
+            C.byref(cfg), T_out.ctypes.data_as(_P), pout.ctypes.data_as(_P), lout.ctypes.data_as(_P),
+            ninl.ctypes.data_as(_P)))
+        p_split = [pout[po[b]:po[b + 1]].copy() for b in range(B)]
+        l_split = [lout[lo[b]:lo[b + 1]].copy() for b in range(B)] if has_lines else None
+        return T_out, p_split, l_split, ninl
 
     # ------------------------------------------------------------------ match::robust
     def brute_force_match(self, frm_desc, frm_angle, kf_desc, kf_angle, kf_valid=None, lowe_ratio=0.8,

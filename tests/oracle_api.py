@@ -366,3 +366,35 @@ def _new_init(self):
 
 
 Oracle.__init__ = _new_init
+
+
+# ======================================================================== pose optimiser (oracle/pose_opt.cc)
+class OPoseCam(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("focal_x_baseline", C.c_double), ("setup_type", C.c_int32)]
+
+
+PT_OBS_DTYPE = np.dtype([("pos_w", "<f8", 3), ("obs_x", "<f4"), ("obs_y", "<f4"), ("x_right", "<f4"),
+                         ("inv_sigma_sq", "<f4")])
+LINE_OBS_DTYPE = np.dtype([("plucker", "<f8", 6), ("sp_x", "<f4"), ("sp_y", "<f4"), ("ep_x", "<f4"), ("ep_y", "<f4"),
+                           ("inv_sigma_sq", "<f4"), ("pad", "<f4")])
+
+
+def _pose_optimize(self, cam, T_cw, pts, lines=None, num_trials=4, num_each_iter=10):
+    pc = OPoseCam(cam.fx, cam.fy, cam.cx, cam.cy, cam.focal_x_baseline, cam.setup_type)
+    T_in = np.ascontiguousarray(np.asarray(T_cw, np.float64).reshape(16))
+    pts = np.ascontiguousarray(pts, PT_OBS_DTYPE)
+    nl = 0 if lines is None else len(lines)
+    ln = np.ascontiguousarray(lines if nl else np.zeros(1, LINE_OBS_DTYPE), LINE_OBS_DTYPE)
+    T_out = np.zeros(16, np.float64)
+    pout = np.zeros(max(len(pts), 1), np.uint8)
+    lout = np.zeros(max(nl, 1), np.uint8)
+    iters = C.c_int(0)
+    n = self.lib.orc_pose_optimize(C.byref(pc), T_in.ctypes.data_as(_P), pts.ctypes.data_as(_P), C.c_int(len(pts)),
+                                   ln.ctypes.data_as(_P), C.c_int(nl), C.c_int(num_trials), C.c_int(num_each_iter),
+                                   T_out.ctypes.data_as(_P), pout.ctypes.data_as(_P), lout.ctypes.data_as(_P),
+                                   C.byref(iters))
+    return T_out.reshape(4, 4), pout[:len(pts)].copy(), (lout[:nl].copy() if lines is not None else None), int(n), iters.value
+
+
+Oracle.pose_optimize = _pose_optimize

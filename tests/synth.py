@@ -236,3 +236,67 @@ def make_toy_corner_image(variant=1):
     img = np.full((2000, 2000), 255, np.uint8)  # extract_toy_sample_2
     cv2.rectangle(img, (0, 0), (1800, 1800), 0, -1, cv2.LINE_AA)
     return img, (1800, 1800)
+
+
+# ------------------------------------------------------------------------------------- pose optimiser
+def inv_level_sigma_sq(num_levels=8, sf=1.2):
+    out = np.ones(num_levels, np.float32)
+    s = np.float32(1.0)
+    for i in range(1, num_levels):
+        s = np.float32(sf) * s
+        out[i] = np.float32(1.0) / (s * s)
+    return out
+
+
+def plucker_from_endpoints(P, Q):
+    """Line::set_pos_in_world (data/landmark_line.cc:60-77): (q x p, p - q)."""
+    return np.concatenate([np.cross(Q, P), P - Q], axis=-1)
+
+
+def make_pose_opt_scene(seed, n_pts=1000, n_lines=200, outlier_frac=0.15, stereo=False, pose_sigma=(0.02, 0.05)):
+    """points in front of the camera, octave-dependent pixel noise, gross
+    outliers, perturbed initial pose.  Returns (T_gt, T_init, pts, lines) in the C-ABI layouts."""
+    rng = np.random.default_rng(seed)
+    T_gt = make_pose(rng, 0.2, 0.5)
+    sf = scale_factors()
+    isig = inv_level_sigma_sq()
+    Xc = np.stack([rng.uniform(-5, 5, n_pts), rng.uniform(-5, 5, n_pts), rng.uniform(2, 12, n_pts)], 1)
+    R, t = T_gt[:3, :3], T_gt[:3, 3]
+    Xw = (Xc - t) @ R  # R^T (Xc - t)
+    octave = rng.choice(8, n_pts, p=np.array([217, 181, 151, 126, 105, 87, 73, 60]) / 1000.0)
+    uv = np.stack([FX * Xc[:, 0] / Xc[:, 2] + CX, FY * Xc[:, 1] / Xc[:, 2] + CY], 1)
+    uv += rng.normal(0, 1.0, (n_pts, 2)) * sf[octave][:, None]
+    out = rng.random(n_pts) < outlier_frac
+    uv[out] = np.stack([rng.uniform(0, COLS, out.sum()), rng.uniform(0, ROWS, out.sum())], 1)
+    pts = np.zeros(n_pts, np.dtype([("pos_w", "<f8", 3), ("obs_x", "<f4"), ("obs_y", "<f4"), ("x_right", "<f4"),
+                                    ("inv_sigma_sq", "<f4")]))
+    pts["pos_w"] = Xw
+    pts["obs_x"], pts["obs_y"] = uv[:, 0], uv[:, 1]
+    pts["x_right"] = -1.0
+    if stereo:
+        has = rng.random(n_pts) < 0.7
+        xr = uv[:, 0] - BF / Xc[:, 2] + rng.normal(0, 1.0, n_pts) * sf[octave]
+        pts["x_right"][has] = xr[has]
+    pts["inv_sigma_sq"] = isig[octave]
+    lines = np.zeros(n_lines, np.dtype([("plucker", "<f8", 6), ("sp_x", "<f4"), ("sp_y", "<f4"), ("ep_x", "<f4"),
+                                        ("ep_y", "<f4"), ("inv_sigma_sq", "<f4"), ("pad", "<f4")]))
+    if n_lines:
+        Pc = np.stack([rng.uniform(-4, 4, n_lines), rng.uniform(-3, 3, n_lines), rng.uniform(3, 10, n_lines)], 1)
+        d = rng.normal(0, 1, (n_lines, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        d[:, 2] *= 0.3
+        Qc = Pc + d * rng.uniform(0.5, 3.0, (n_lines, 1))
+        Pw, Qw = (Pc - t) @ R, (Qc - t) @ R
+        lines["plucker"] = plucker_from_endpoints(Pw, Qw)
+        sp = np.stack([FX * Pc[:, 0] / Pc[:, 2] + CX, FY * Pc[:, 1] / Pc[:, 2] + CY], 1) + rng.normal(0, 1.0, (n_lines, 2))
+        ep = np.stack([FX * Qc[:, 0] / Qc[:, 2] + CX, FY * Qc[:, 1] / Qc[:, 2] + CY], 1) + rng.normal(0, 1.0, (n_lines, 2))
+        lo = rng.random(n_lines) < outlier_frac
+        sp[lo] += rng.normal(0, 40, (lo.sum(), 2))
+        lines["sp_x"], lines["sp_y"], lines["ep_x"], lines["ep_y"] = sp[:, 0], sp[:, 1], ep[:, 0], ep[:, 1]
+        lines["inv_sigma_sq"] = 1.0
+    xi = np.concatenate([rng.normal(0, pose_sigma[0], 3), rng.normal(0, pose_sigma[1], 3)])
+    dT = np.eye(4)
+    dT[:3, :3] = so3_exp(xi[:3])
+    dT[:3, 3] = xi[3:]
+    T_init = dT @ T_gt
+    return T_gt, T_init, pts, lines
