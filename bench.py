@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Structure-PLP-SLAM hot path.
+
+Metric (BASELINE.json): frames/s through extract + match + pose-opt on synthetic 640x480 sequences
+(8-level ORB pyramid, ~1000 kp/frame).  A "step" = one pass of the front-end
+    orb_extractor::extract -> frame_tracker::motion_based_track
+      (match_current_and_last_frames [+ widened retry] -> pose_optimizer::optimize -> discard_outliers)
+over one batch of independent frames (frames shard over GPUs with no collective).
+
+  value     : device-resident throughput (images already in HBM when the timed region starts)
+  e2e       : same metric through the public batched API with HOST buffers: pinned H2D of the step's images and
+              D2H of the step's poses / inlier counts inside the timed region
+  roofline  : dominant kernel's algorithmic bytes per launch / its mean launch time (CUDA events on the
+              launching stream) vs the measured HBM peak
+  cpu_baseline / --impl reference : the CPU oracle port of the same path on the host cores (the reference's
+              own binary cannot be built here: no C++ OpenCV / Eigen / g2o), bounded sample.
+
+Launch:  python bench.py --gpus N --steps K --warmup W          (N>1: via torch.distributed.run, one rank per GPU)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "frames_per_sec_extract_match_poseopt"
+UNIT = "frames/s"
+ROWS, COLS = 480, 640
+WORKLOAD = "ORB extract + Hamming match + pose-opt, 640x480, 8-level pyramid, 1000 kp/frame (BASELINE configs[1]+[2])"
+# algorithmic bytes per frame of the extraction path; per-kernel split in DESIGN.md
+PYR_PX = 950532
+ALG_BYTES = {
+    "fast_cells_kernel": PYR_PX,  # every pyramid level read once for FAST (+ candidates out, negligible)
+    "pyr_resize_kernel": None,    # per level, filled below
+    "describe_kernel": PYR_PX + 60 * 1200,
+    "quadtree_kernel": 8 * 11000 + 8 * 1200,
+}
+
+
+def _load_pkg():
+    if "plpslam_b200" in sys.modules:
+        return sys.modules["plpslam_b200"]
+    pkg = ROOT / "structure-plp-slam_b200"
+    spec = importlib.util.spec_from_file_location("plpslam_b200", pkg / "__init__.py",
+                                                  submodule_search_locations=[str(pkg)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["plpslam_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def build_inputs(batch: int, seed: int):
+    """`batch` independent tracking problems from a few rendered planar sequences (tests/scene.py)."""
+    import oracle_api
+    import scene
+    n_seq_frames = 33
+    seqs = []
+    frames, t_idx = [], []
+    s = 0
+    while len(frames) < batch:
+        seq = scene.PlanarSequence(seed=seed + 17 * s, n_frames=n_seq_frames)
+        seqs.append(seq)
+        for t in range(1, n_seq_frames):
+            if len(frames) < batch:
+                frames.append(seq.frames[t])
+                t_idx.append((s, t))
+        s += 1
+    return seqs, np.stack(frames), t_idx
+
+
+def setup_front_end(pkg, ctx, batch, seed):
+    """Render frames, extract the 'last' frames once (untimed) to obtain landmark sets, upload everything."""
+    import synth
+    from plpslam_b200.tracking import FrontEnd
+    cam = pkg.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, COLS, ROWS)
+    fe = FrontEnd(ctx, ROWS, COLS, cam, max_batch=batch)
+    seqs, frames, t_idx = build_inputs(batch, seed)
+    # last-frame landmarks: extract frame t-1 of every problem on the GPU (setup, untimed)
+    last_imgs = np.stack([seqs[s].frames[t - 1] for (s, t) in t_idx])
+    fe.upload_images(last_imgs)
+    fe.extract(batch)
+    ctx.sync()
+    kps = fe.download_keypoints(batch)
+    rng = np.random.default_rng(seed)
+    lasts = [seqs[s].last_frame_landmarks(t - 1, kps[b][0], kps[b][1]) for b, (s, t) in enumerate(t_idx)]
+    preds = np.stack([seqs[s].predicted_pose(t, rng) for (s, t) in t_idx])
+    pose_last = np.stack([seqs[s].poses[t - 1] for (s, t) in t_idx])
+    fe.set_last_frames(lasts, preds, pose_last)
+    fe.upload_images(frames)
+    gt = np.stack([seqs[s].poses[t] for (s, t) in t_idx])
+    return fe, frames, dict(seqs=seqs, t_idx=t_idx, lasts=lasts, preds=preds, gt=gt)
+
+
+def cpu_port_frames(frames, aux, idxs, threads):
+    """The oracle port of the same path (extract -> match -> pose-opt) on `threads` host threads."""
+    import oracle_api
+    import synth
+    pkg = _load_pkg()
+    orc = oracle_api.Oracle()
+    p = oracle_api.orb_params()
+    grid = pkg.capi.make_grid(COLS, ROWS)
+    cam = pkg.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, COLS, ROWS)
+    sf, isig = synth.scale_factors(), synth.inv_level_sigma_sq()
+
+    def one(b):
+        r = orc.orb_extract(p, frames[b])
+        k = r["kps"]
+        last = aux["lasts"][b]
+        s, t = aux["t_idx"][b]
+        curr = dict(x=k["x"], y=k["y"], octave=k["octave"], angle=k["angle"], desc=r["desc"])
+        Tp = aux["preds"][b]
+        Tl = aux["seqs"][s].poses[t - 1]
+        m, nm = orc.match_current_and_last_frames(grid, sf, cam, curr, Tp, Tl, last, 20.0, True)
+        if nm < 20:
+            m, nm = orc.match_current_and_last_frames(grid, sf, cam, curr, Tp, Tl, last, 40.0, True)
+        idx = np.nonzero(m >= 0)[0]
+        pts = np.zeros(len(idx), oracle_api.PT_OBS_DTYPE)
+        pts["pos_w"] = last["pos_w"][m[idx]]
+        pts["obs_x"], pts["obs_y"] = k["x"][idx], k["y"][idx]
+        pts["x_right"] = -1.0
+        pts["inv_sigma_sq"] = isig[k["octave"][idx]]
+        T, pout, _, n_inl, _ = orc.pose_optimize(cam, Tp, pts)
+        return n_inl
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        out = [one(b) for b in idxs]
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            out = list(ex.map(one, idxs))
+    dt = time.perf_counter() - t0
+    return len(idxs) / dt, dt, out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path (oracle port; the reference binary cannot be built here)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample per step: 2 frames per host thread (capped), same workload/config as the GPU arm
+    per_step = int(min(256, max(16, 2 * cores)))
+    seqs, frames, t_idx = build_inputs(per_step, args.seed)
+    import oracle_api
+    import synth
+    orc = oracle_api.Oracle()
+    p = oracle_api.orb_params()
+    rng = np.random.default_rng(args.seed)
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        kps = list(ex.map(lambda st: orc.orb_extract(p, seqs[st[0]].frames[st[1] - 1]), t_idx))
+    lasts = [seqs[s].last_frame_landmarks(t - 1, kps[b]["kps"], kps[b]["desc"]) for b, (s, t) in enumerate(t_idx)]
+    preds = np.stack([seqs[s].predicted_pose(t, rng) for (s, t) in t_idx])
+    aux = dict(seqs=seqs, t_idx=t_idx, lasts=lasts, preds=preds)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_frames(frames, aux, list(range(min(per_step, cores))), cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_frames(frames, aux, list(range(per_step)), cores)
+    dt = time.perf_counter() - t0
+    fps = args.steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": per_step,
+                   "note": "reference binary unbuildable here (no C++ OpenCV/Eigen/g2o); CPU oracle port, frames spread over host threads"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} frames/step x {args.steps} steps"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 307 KB > 126 MB L2)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    pkg = _load_pkg()
+    ctx = pkg.Context(local_rank)
+    lib = pkg.lib()
+    B = args.batch
+    fe, frames, aux = setup_front_end(pkg, ctx, B, args.seed + 1000 * rank)
+    stream = torch.cuda.ExternalStream(lib.plp_ctx_stream(ctx.handle), device=f"cuda:{local_rank}")
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---------------- value: device-resident ------------------------------------------------------------
+    for _ in range(args.warmup):
+        fe.step(B)
+    barrier()
+    launches0 = ctx.launch_count()
+    with ClockSampler(local_rank) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            fe.step(B)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    res = fe.download_tracking(B)
+    ok = int((res["num_valid"] >= 20).sum())
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---------------- e2e: host buffers, copies inside the timed region ----------------------------------
+    pinned = C.c_void_p()
+    ctx._check(lib.plp_host_alloc_pinned(C.c_size_t(frames.nbytes), C.byref(pinned)))
+    C.memmove(pinned, frames.ctypes.data, frames.nbytes)
+    d2h_bytes = B * (128 + 4 + 4)
+
+    def e2e_step():
+        ctx._check(lib.plp_dev_upload(ctx.handle, fe.d_imgs.ptr, pinned, C.c_size_t(frames.nbytes)))
+        fe.step(B)
+        fe.d_pose.download(np.float64, (B, 4, 4))
+        fe.d_num_valid.download(np.int32, (B,))
+        fe.d_n_inl.download(np.int32, (B,))
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record(stream)
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    # ---------------- roofline: per-kernel event timing over the same steps ------------------------------
+    ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 1))
+    for _ in range(args.steps):
+        fe.step(B)
+    buf = C.create_string_buffer(1 << 16)
+    ctx._check(lib.plp_ctx_kernel_timing_report(ctx.handle, buf, C.c_size_t(len(buf))))
+    ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 0))
+    kt = json.loads(buf.value.decode())
+    total_ms = sum(v["total_ms"] for v in kt.values())
+    shares = {k: round(v["total_ms"] / total_ms, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["total_ms"])}
+    dom = max(kt.items(), key=lambda kv: kv[1]["total_ms"])
+    peak, peak_src = _peaks()
+    dom_name = dom[0]
+    per_launch_ms = dom[1]["total_ms"] / dom[1]["count"]
+    alg = ALG_BYTES.get(dom_name)
+    if alg is None:
+        alg = PYR_PX
+    alg_bytes_launch = alg * B
+    achieved = alg_bytes_launch / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": per_launch_ms,
+                "kernel_time_shares": shares,
+                "how": "CUDA events around every launch on the launching stream over a repeat of the timed steps"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "image": f"{COLS}x{ROWS}",
+                       "orb": {"max_num_keypts": 1000, "scale_factor": 1.2, "num_levels": 8, "ini_fast_thr": 20, "min_fast_thr": 7},
+                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                       "l2": "inputs larger than L2 (batch x 307 KB images)",
+                       "tracked_ok_frames": ok},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes), "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_sample = int(min(B, max(32, 2 * cores)))
+            fps_mt, dt_mt, _ = cpu_port_frames(frames, aux, list(range(n_sample)), cores)
+            fps_1, dt_1, _ = cpu_port_frames(frames, aux, list(range(min(8, n_sample))), 1)
+            line["cpu_baseline"] = {"value": fps_mt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_sample} frames of the same workload over {cores} host threads ({dt_mt:.1f} s)",
+                                    "single_thread_value": fps_1}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,10 @@ PLP_API plp_status plp_host_alloc_pinned(size_t bytes, void **out);
 PLP_API plp_status plp_host_free_pinned(void *ptr);
 /* number of kernels this library has launched since the context was created */
 PLP_API uint64_t plp_ctx_launch_count(plp_ctx *ctx);
+/* per-kernel device timing (CUDA events on the context stream around every launch); the report is a JSON object
+ * {kernel_name: {count, total_ms}} of the launches since timing was enabled.  For measurement only. */
+PLP_API plp_status plp_ctx_kernel_timing(plp_ctx *ctx, int enable);
+PLP_API plp_status plp_ctx_kernel_timing_report(plp_ctx *ctx, char *buf, size_t buf_bytes);
 
 /* ------------------------------------------------------------------------ */
 /* 256-bit Hamming  (match/base.h:43-93)                                    */
@@ -319,6 +323,41 @@ PLP_API plp_status plp_pose_optimize_batch_dev(plp_ctx *ctx, const plp_camera *c
                                                const plp_pose_opt_cfg *cfg, double *d_T_cw_out,
                                                uint8_t *d_pt_outlier, uint8_t *d_line_outlier,
                                                int32_t *d_n_inliers_out, int32_t *d_lm_iters_out);
+
+/* ------------------------------------------------------------------------ */
+/* frame-batched tracking front-end (module/frame_tracker.cc:52-124)         */
+/* ------------------------------------------------------------------------ */
+/* frame_tracker::motion_based_track for a batch of independent (current frame, last-frame landmarks, predicted
+ * pose) triples, chained on the device after plp_orb_extract_batch_dev: match_current_and_last_frames (margin,
+ * retried with 2*margin below 20 matches) -> pose_optimizer::optimize -> discard_outliers.  Monocular. */
+typedef struct plp_tracker plp_tracker;
+
+typedef struct plp_track_last { /* device pointers; frame b owns [offsets[b], offsets[b+1]) */
+    const double *pos_w;        /* x 3: lm->get_pos_in_world() of the last frame's landmarks        */
+    const int32_t *octave;      /* last_frm.keypts_[i].octave                                        */
+    const float *angle;         /* last_frm.undist_keypts_[i].angle                                  */
+    const uint8_t *desc;        /* x 32                                                              */
+    const uint8_t *valid;       /* lm && !outlier_flags_ ; may be NULL                               */
+    const int32_t *offsets;     /* batch + 1                                                         */
+    const double *pose_pred;    /* batch x 16: velocity * last_frm.cam_pose_cw_ (frame_tracker.cc:58) */
+    const double *pose_last;    /* batch x 16: last_frm.cam_pose_cw_                                 */
+} plp_track_last;
+
+PLP_API plp_status plp_tracker_create(plp_ctx *ctx, const plp_camera *cam, const plp_grid *grid,
+                                      const float *scale_factors, const float *inv_level_sigma_sq,
+                                      int num_levels, int max_batch, int kp_capacity, int max_last_points,
+                                      plp_tracker **out);
+PLP_API void plp_tracker_destroy(plp_tracker *t);
+/* d_kp/d_desc/d_n_kp: the arrays written by plp_orb_extract_batch_dev (batch x kp_capacity entries).
+ * Outputs (device): matched_out[batch x kp_capacity] = last-frame landmark index kept on each keypoint after
+ * discard_outliers (-1: none); pose_out[batch x 16]; num_valid_out[batch] (tracking succeeded iff >= 20);
+ * n_inliers_out[batch] = pose_optimizer return value; lm_iters_out[batch] = LM iterations executed. */
+PLP_API plp_status plp_tracker_motion_track_batch_dev(plp_tracker *t, int batch, const plp_keypoint *d_kp,
+                                                      const uint8_t *d_desc, const int32_t *d_n_kp,
+                                                      const plp_track_last *last, float margin,
+                                                      int32_t *d_matched_out, double *d_pose_out,
+                                                      int32_t *d_num_valid_out, int32_t *d_n_inliers_out,
+                                                      int32_t *d_lm_iters_out);
 
 #ifdef __cplusplus
 }

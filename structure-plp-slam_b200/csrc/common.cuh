@@ -31,10 +31,19 @@ struct plp_ctx {
     // growable pinned host staging area
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    // optional per-kernel timing (bench.py roofline leg): CUDA events recorded around every launch
+    bool timing = false;
+    struct TimedLaunch {
+        const char *name;
+        cudaEvent_t start, stop;
+    };
+    std::vector<TimedLaunch> timed;
 };
 
 namespace plp {
 
+void timing_begin(plp_ctx *ctx, const char *name);
+void timing_end(plp_ctx *ctx);
 plp_status ctx_scratch(plp_ctx *ctx, int slot, size_t bytes, void **out);
 plp_status ctx_pinned(plp_ctx *ctx, size_t bytes, void **out);
 
@@ -65,7 +74,9 @@ plp_status ctx_pinned(plp_ctx *ctx, size_t bytes, void **out);
 // every kernel launch goes through this so gpu_launches can be reported honestly
 #define PLP_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
     do {                                                                         \
+        if ((ctx)->timing) plp::timing_begin((ctx), #kernel);                    \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+        if ((ctx)->timing) plp::timing_end((ctx));                               \
         (ctx)->launches++;                                                       \
     } while (0)
 

@@ -12,6 +12,17 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+void timing_begin(plp_ctx *ctx, const char *name) {
+    plp_ctx::TimedLaunch t;
+    t.name = name;
+    cudaEventCreate(&t.start);
+    cudaEventCreate(&t.stop);
+    cudaEventRecord(t.start, ctx->stream);
+    ctx->timed.push_back(t);
+}
+
+void timing_end(plp_ctx *ctx) { cudaEventRecord(ctx->timed.back().stop, ctx->stream); }
+
 plp_status ctx_scratch(plp_ctx *ctx, int slot, size_t bytes, void **out) {
     ScratchBuf &b = ctx->scratch[slot];
     if (b.bytes < bytes) {
@@ -102,6 +113,49 @@ plp_status plp_ctx_sync(plp_ctx *ctx) {
 void *plp_ctx_stream(plp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 uint64_t plp_ctx_launch_count(plp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+plp_status plp_ctx_kernel_timing(plp_ctx *ctx, int enable) {
+    PLP_REQUIRE(ctx != nullptr, "ctx");
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (auto &t : ctx->timed) {
+        cudaEventDestroy(t.start);
+        cudaEventDestroy(t.stop);
+    }
+    ctx->timed.clear();
+    ctx->timing = enable != 0;
+    return PLP_OK;
+}
+
+plp_status plp_ctx_kernel_timing_report(plp_ctx *ctx, char *buf, size_t buf_bytes) {
+    PLP_REQUIRE(ctx != nullptr && buf != nullptr && buf_bytes > 2, "ctx/buf");
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    struct Agg {
+        const char *name;
+        double ms;
+        long count;
+    };
+    std::vector<Agg> agg;
+    for (auto &t : ctx->timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.start, t.stop) != cudaSuccess) continue;
+        bool found = false;
+        for (auto &a : agg)
+            if (strcmp(a.name, t.name) == 0) {
+                a.ms += ms;
+                a.count++;
+                found = true;
+                break;
+            }
+        if (!found) agg.push_back({t.name, ms, 1});
+    }
+    size_t off = 0;
+    off += snprintf(buf + off, buf_bytes - off, "{");
+    for (size_t i = 0; i < agg.size() && off + 160 < buf_bytes; ++i)
+        off += snprintf(buf + off, buf_bytes - off, "%s\"%s\": {\"count\": %ld, \"total_ms\": %.6f}", i ? ", " : "",
+                        agg[i].name, agg[i].count, agg[i].ms);
+    snprintf(buf + off, buf_bytes - off, "}");
+    return PLP_OK;
+}
 
 plp_status plp_dev_alloc(plp_ctx *ctx, size_t bytes, void **out) {
     PLP_REQUIRE(ctx != nullptr && out != nullptr, "ctx/out");

@@ -140,7 +140,7 @@ __global__ void project_points_kernel(const ProjectJob *__restrict__ jobs, plp_c
                                       const float *__restrict__ scale_factors, int num_levels, float margin) {
     const ProjectJob &J = jobs[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= J.n_last) return;
+    if (i >= J.n_last) return;  // also skips disabled jobs (n_last < 0)
     bool valid = J.valid ? (J.valid[i] != 0) : true;
     const int lvl = J.octave[i];
     Reproj r = reproject(cam, J.pose_cw, J.pos_w + 3 * (size_t)i);
@@ -257,8 +257,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                        float lowe_ratio, int check_orientation) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const PointMatchJob &J = jobs[blockIdx.x];
+    if (J.m < 0) return;  // job disabled (e.g. the widened-margin retry is not needed for this frame)
     PointSmem S = carve_point_smem(smem_raw, cap, grid.num_cols);
     const int tid = threadIdx.x;
+    if (J.n > cap) {  // more keypoints than the shared-memory tables hold: report "no matches" loudly (0xffffffff)
+        if (J.matched_out)
+            for (int i = tid; i < J.n; i += kThreads) J.matched_out[i] = -1;
+        if (J.best_idx_out)
+            for (int q = tid; q < J.m; q += kThreads) J.best_idx_out[q] = -1;
+        if (tid == 0 && J.num_matches) *J.num_matches = 0xffffffffu;
+        return;
+    }
     const int n = J.n, m = J.m;
     const int cells = grid.num_cols * grid.num_rows;
 

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "pack.cuh"
 #include "se3.cuh"
+#include "pose_kernels.cuh"
 
 namespace plp {
 
@@ -30,19 +31,6 @@ constexpr int kPoThreads = 256;
 constexpr int kPoWarps = kPoThreads / 32;
 constexpr int kPoMaxEdges = 6144;  // points + lines per frame (shared-memory bound)
 constexpr int kRed = 28;           // 21 (upper H) + 6 (b) + 1 (chi2)
-
-struct PoseJob {
-    const double *T_in;   // 16
-    const plp_pt_obs *pts;
-    int n_pts;
-    const plp_line_obs *lines;
-    int n_lines;
-    double *T_out;        // 16
-    uint8_t *pt_outlier;
-    uint8_t *line_outlier;
-    int32_t *n_inliers;
-    int32_t *lm_iters;    // may be null
-};
 
 struct PoShared {
     se3::Pose est, trial;
@@ -395,6 +383,8 @@ __global__ void build_pose_jobs_kernel(PoseJob *jobs, int batch, const double *T
     jobs[b] = J;
 }
 
+}  // namespace
+
 size_t pose_smem_bytes(int max_edges) {
     return ((sizeof(PoShared) + 15) & ~(size_t)15) + (size_t)max_edges * 9 + 64;
 }
@@ -413,7 +403,6 @@ plp_status launch_pose_opt(plp_ctx *ctx, const PoseJob *d_jobs, int batch, int m
     return PLP_OK;
 }
 
-}  // namespace
 
 }  // namespace plp
 

@@ -1,0 +1,148 @@
+"""Device-resident batched front-end: ORB extraction + motion-based tracking without leaving HBM.
+
+Thin ctypes layer over plp_orb_extract_batch_dev + plp_tracker_motion_track_batch_dev; used by bench.py and
+the pipeline parity tests.  No compute here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .capi import KP_DTYPE, Context, OrbExtractor, PlpError, _P, make_camera, make_grid  # noqa: F401
+
+
+class TrackLast(C.Structure):
+    _fields_ = [("pos_w", _P), ("octave", _P), ("angle", _P), ("desc", _P), ("valid", _P), ("offsets", _P),
+                ("pose_pred", _P), ("pose_last", _P)]
+
+
+class DeviceBuffer:
+    """A cudaMalloc'ed block owned through the C ABI (plp_dev_alloc / plp_dev_free)."""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self._ctx = ctx
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        ctx._check(ctx._lib.plp_dev_alloc(ctx.handle, C.c_size_t(max(self.nbytes, 1)), C.byref(p)))
+        self.ptr = p
+
+    @classmethod
+    def from_array(cls, ctx: Context, arr: np.ndarray) -> "DeviceBuffer":
+        arr = np.ascontiguousarray(arr)
+        buf = cls(ctx, arr.nbytes)
+        buf.upload(arr)
+        return buf
+
+    def upload(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self._ctx._check(self._ctx._lib.plp_dev_upload(self._ctx.handle, self.ptr, arr.ctypes.data_as(_P),
+                                                       C.c_size_t(arr.nbytes)))
+
+    def download(self, dtype, shape) -> np.ndarray:
+        out = np.zeros(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        self._ctx._check(self._ctx._lib.plp_dev_download(self._ctx.handle, out.ctypes.data_as(_P), self.ptr,
+                                                         C.c_size_t(out.nbytes)))
+        return out
+
+    def free(self):
+        if self.ptr is not None:
+            self._ctx._lib.plp_dev_free(self._ctx.handle, self.ptr)
+            self.ptr = None
+
+
+class FrontEnd:
+    """extract (orb_extractor::extract) -> motion_based_track for a batch of frames, all on the device."""
+
+    def __init__(self, ctx: Context, rows: int, cols: int, cam, max_batch: int, max_last_points: int = 4096,
+                 max_num_keypts=1000, scale_factor=1.2, num_levels=8, ini_fast_thr=20, min_fast_thr=7):
+        self.ctx = ctx
+        self.lib = ctx._lib
+        self.rows, self.cols, self.max_batch = rows, cols, max_batch
+        self.cam = cam
+        self.grid = make_grid(cols, rows)
+        self.orb = OrbExtractor(ctx, rows, cols, max_num_keypts, scale_factor, num_levels, ini_fast_thr, min_fast_thr,
+                                max_batch=max_batch)
+        self.cap = self.orb.capacity
+        self.max_last = max_last_points
+        h = C.c_void_p()
+        sf = np.ascontiguousarray(self.orb.scale_factors, np.float32)
+        isig = np.ascontiguousarray(self.orb.inv_level_sigma_sq, np.float32)
+        ctx._check(self.lib.plp_tracker_create(ctx.handle, C.byref(cam), C.byref(self.grid), sf.ctypes.data_as(_P),
+                                               isig.ctypes.data_as(_P), C.c_int(num_levels), C.c_int(max_batch),
+                                               C.c_int(self.cap), C.c_int(max_last_points), C.byref(h)))
+        self._trk = h
+        B = max_batch
+        self.d_imgs = DeviceBuffer(ctx, B * rows * cols)
+        self.d_kp = DeviceBuffer(ctx, B * self.cap * KP_DTYPE.itemsize)
+        self.d_desc = DeviceBuffer(ctx, B * self.cap * 32)
+        self.d_n = DeviceBuffer(ctx, B * 4)
+        self.d_status = DeviceBuffer(ctx, B * 4)
+        self.d_matched = DeviceBuffer(ctx, B * self.cap * 4)
+        self.d_pose = DeviceBuffer(ctx, B * 128)
+        self.d_num_valid = DeviceBuffer(ctx, B * 4)
+        self.d_n_inl = DeviceBuffer(ctx, B * 4)
+        self.d_lm = DeviceBuffer(ctx, B * 4)
+        self._last_bufs = []
+        self._last = None
+
+    def close(self):
+        if self._trk is not None:
+            self.lib.plp_tracker_destroy(self._trk)
+            self._trk = None
+        self.orb.close()
+
+    # -- inputs ---------------------------------------------------------------------------------------
+    def upload_images(self, imgs: np.ndarray):
+        self.d_imgs.upload(np.ascontiguousarray(imgs, np.uint8))
+
+    def set_last_frames(self, last_list, pose_pred, pose_last):
+        """last_list[b]: dict(pos_w[m,3], octave[m], angle[m], desc[m,32], valid[m]|None)."""
+        for b in self._last_bufs:
+            b.free()
+        offs = np.zeros(len(last_list) + 1, np.int32)
+        offs[1:] = np.cumsum([len(l["octave"]) for l in last_list])
+        assert max(np.diff(offs)) <= self.max_last
+        cat = lambda k, dt: np.ascontiguousarray(np.concatenate([np.asarray(l[k], dt) for l in last_list]))
+        arrays = [cat("pos_w", np.float64), cat("octave", np.int32), cat("angle", np.float32), cat("desc", np.uint8),
+                  np.ascontiguousarray(np.concatenate([np.asarray(l.get("valid") if l.get("valid") is not None else
+                                                                  np.ones(len(l["octave"]), np.uint8), np.uint8)
+                                                       for l in last_list])),
+                  offs, np.ascontiguousarray(pose_pred, np.float64), np.ascontiguousarray(pose_last, np.float64)]
+        self._last_bufs = [DeviceBuffer.from_array(self.ctx, a) for a in arrays]
+        self._last = TrackLast(*[b.ptr for b in self._last_bufs])
+
+    # -- the hot path (no host synchronisation) ---------------------------------------------------------
+    def extract(self, batch: int):
+        self.ctx._check(self.lib.plp_orb_extract_batch_dev(self.orb.handle, self.d_imgs.ptr, C.c_int(batch),
+                                                          C.c_size_t(self.cols), self.d_kp.ptr, self.d_desc.ptr,
+                                                          self.d_n.ptr, self.d_status.ptr))
+
+    def track(self, batch: int, margin: float = 20.0):
+        self.ctx._check(self.lib.plp_tracker_motion_track_batch_dev(
+            self._trk, C.c_int(batch), self.d_kp.ptr, self.d_desc.ptr, self.d_n.ptr, C.byref(self._last),
+            C.c_float(margin), self.d_matched.ptr, self.d_pose.ptr, self.d_num_valid.ptr, self.d_n_inl.ptr,
+            self.d_lm.ptr))
+
+    def step(self, batch: int, margin: float = 20.0):
+        self.extract(batch)
+        self.track(batch, margin)
+
+    # -- results --------------------------------------------------------------------------------------
+    def download_keypoints(self, batch: int):
+        n = self.d_n.download(np.int32, (batch,))
+        kp = self.d_kp.download(KP_DTYPE, (self.max_batch, self.cap))[:batch]
+        desc = self.d_desc.download(np.uint8, (self.max_batch, self.cap, 32))[:batch]
+        return [(kp[b, :n[b]].copy(), desc[b, :n[b]].copy()) for b in range(batch)]
+
+    def download_tracking(self, batch: int):
+        n = self.d_n.download(np.int32, (batch,))
+        matched = self.d_matched.download(np.int32, (self.max_batch, self.cap))[:batch]
+        return dict(matched=[matched[b, :n[b]].copy() for b in range(batch)],
+                    pose=self.d_pose.download(np.float64, (batch, 4, 4)),
+                    num_valid=self.d_num_valid.download(np.int32, (batch,)),
+                    n_inliers=self.d_n_inl.download(np.int32, (batch,)),
+                    lm_iters=self.d_lm.download(np.int32, (batch,)),
+                    status=self.d_status.download(np.int32, (batch,)))

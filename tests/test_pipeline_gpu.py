@@ -1,0 +1,67 @@
+"""GPU parity of the device-resident batched front-end (extract -> motion_based_track) against the oracle chain
+orb_extract -> match_current_and_last_frames (+ widened retry) -> pose_optimize -> discard_outliers."""
+import numpy as np
+import pytest
+
+import oracle_api
+import scene
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_track(orc, plp, seq, res, t, T_pred, margin=20.0):
+    grid = plp.capi.make_grid(seq.cols, seq.rows)
+    cam = plp.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, seq.cols, seq.rows)
+    sf, isig = synth.scale_factors(), synth.inv_level_sigma_sq()
+    last = seq.last_frame_landmarks(t - 1, res[t - 1]["kps"], res[t - 1]["desc"])
+    k = res[t]["kps"]
+    curr = dict(x=k["x"], y=k["y"], octave=k["octave"], angle=k["angle"], desc=res[t]["desc"])
+    # module/frame_tracker.cc:63-77
+    m, nm = orc.match_current_and_last_frames(grid, sf, cam, curr, T_pred, seq.poses[t - 1], last, margin, True)
+    if nm < 20:
+        m, nm = orc.match_current_and_last_frames(grid, sf, cam, curr, T_pred, seq.poses[t - 1], last, 2 * margin, True)
+    if nm < 20:
+        return np.full(len(k), -1, np.int32), T_pred, 0, 0
+    idx = np.nonzero(m >= 0)[0]
+    pts = np.zeros(len(idx), oracle_api.PT_OBS_DTYPE)
+    pts["pos_w"] = last["pos_w"][m[idx]]
+    pts["obs_x"], pts["obs_y"] = k["x"][idx], k["y"][idx]
+    pts["x_right"] = -1.0
+    pts["inv_sigma_sq"] = isig[k["octave"][idx]]
+    T, pout, _, n_inl, _ = orc.pose_optimize(cam, T_pred, pts)
+    m = m.copy()
+    m[idx[pout != 0]] = -1  # discard_outliers (frame_tracker.cc:253-283)
+    return m, T, int((m >= 0).sum()), n_inl
+
+
+@pytest.mark.parametrize("margin,pred_sigma", [(20.0, (0.003, 0.01)), (3.0, (0.02, 0.06))])
+def test_front_end_matches_oracle_chain(ctx, orc, plp, margin, pred_sigma):
+    from plpslam_b200.tracking import FrontEnd
+    B = 5
+    seq = scene.PlanarSequence(seed=7, n_frames=B + 1)
+    p = oracle_api.orb_params()
+    res = [orc.orb_extract(p, f) for f in seq.frames]
+    cam = plp.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, seq.cols, seq.rows)
+    fe = FrontEnd(ctx, seq.rows, seq.cols, cam, max_batch=8)
+    rng = np.random.default_rng(3)
+    preds = [seq.predicted_pose(t, rng, *pred_sigma) for t in range(1, B + 1)]
+    lasts = [seq.last_frame_landmarks(t - 1, res[t - 1]["kps"], res[t - 1]["desc"]) for t in range(1, B + 1)]
+    fe.upload_images(seq.frames[1:B + 1])
+    fe.set_last_frames(lasts, np.stack(preds), np.stack(seq.poses[0:B]))
+    fe.step(B, margin)
+    kps = fe.download_keypoints(B)
+    out = fe.download_tracking(B)
+    assert not out["status"].any()
+    retried = 0
+    for b in range(B):
+        t = b + 1
+        # extraction identical to the oracle's
+        assert np.array_equal(kps[b][0], res[t]["kps"]) and np.array_equal(kps[b][1], res[t]["desc"])
+        m, T, nv, n_inl = _oracle_track(orc, plp, seq, res, t, preds[b], margin)
+        assert np.array_equal(out["matched"][b], m), f"frame {b}"
+        assert out["num_valid"][b] == nv and out["n_inliers"][b] == n_inl
+        rel = np.linalg.norm(out["pose"][b] - T) / np.linalg.norm(T)
+        assert rel < 1e-4, rel
+        assert nv >= 20
+    fe.close()
