@@ -63,5 +63,6 @@ def test_front_end_matches_oracle_chain(ctx, orc, plp, margin, pred_sigma):
         assert out["num_valid"][b] == nv and out["n_inliers"][b] == n_inl
         rel = np.linalg.norm(out["pose"][b] - T) / np.linalg.norm(T)
         assert rel < 1e-4, rel
-        assert nv >= 20
+        if margin >= 20.0:
+            assert nv >= 20  # the easy case really tracks; the hard case exercises the retry / failure branches
     fe.close()
