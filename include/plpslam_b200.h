@@ -359,6 +359,73 @@ PLP_API plp_status plp_tracker_motion_track_batch_dev(plp_tracker *t, int batch,
                                                       int32_t *d_num_valid_out, int32_t *d_n_inliers_out,
                                                       int32_t *d_lm_iters_out);
 
+/* ------------------------------------------------------------------------ */
+/* local bundle adjustment (optimize/local_bundle_adjuster*.cc)               */
+/* ------------------------------------------------------------------------ */
+/* The graph the reference gathers at local_bundle_adjuster.cc:72-272 (pointer-graph walk, stays in the adapter):
+ * keyframes = local + fixed, local point / line landmarks, one edge per observation, optional point-to-plane
+ * edges (local_bundle_adjuster_extended_plane.cc:309-345).  Edges must be grouped by ascending landmark index
+ * (that is the order in which the reference creates them). */
+typedef struct plp_ba_problem {
+    double fx, fy, cx, cy, focal_x_baseline;
+    int32_t setup_type; /* 0 Monocular: point-edge Huber delta sqrt(5.991), else sqrt(7.815) */
+    int32_t n_kf;
+    const double *kf_pose_cw; /* n_kf x 16 row-major */
+    const uint8_t *kf_fixed;  /* keyframe id == 0 or "fixed keyframe" (local_bundle_adjuster.cc:197-213) */
+    int32_t n_pts;
+    const double *pt_pos_w; /* n_pts x 3 */
+    int32_t n_pt_edges;
+    const int32_t *pt_edge_kf, *pt_edge_lm;
+    const float *pt_edge_obs;          /* x 3: undist_keypt.pt.x, .y, stereo_x_right (< 0: monocular edge) */
+    const float *pt_edge_inv_sigma_sq; /* inv_level_sigma_sq_[octave] */
+    int32_t n_lines;
+    const double *line_plucker; /* n_lines x 6, Line::get_PlueckerCoord() */
+    int32_t n_line_edges;
+    const int32_t *line_edge_kf, *line_edge_lm;
+    const float *line_edge_obs; /* x 4: keyline start / end point */
+    const float *line_edge_inv_sigma_sq;
+    int32_t n_plane_edges; /* at most one per point landmark */
+    const int32_t *plane_edge_lm;
+    const double *plane_edge_fn; /* x 4: plane (n, d) */
+} plp_ba_problem;
+
+typedef struct plp_ba_cfg {
+    int32_t num_first_iter;  /* 5  (optimize/local_bundle_adjuster.h:47-49) */
+    int32_t num_second_iter; /* 10 */
+    int32_t num_ctas;        /* landmark shards per GPU; 0 = automatic */
+} plp_ba_cfg;
+
+typedef struct plp_ba_result {
+    double *kf_pose_cw;         /* n_kf x 16 (fixed keyframes are returned unchanged) */
+    double *pt_pos_w;           /* n_pts x 3 */
+    double *line_plucker;       /* n_lines x 6 */
+    uint8_t *pt_edge_outlier;   /* outlier_observations (local_bundle_adjuster.cc:342-372) */
+    uint8_t *line_edge_outlier; /* outlier_observations_line */
+    int32_t iters_first, iters_second, lm_tries;
+    double final_chi2;
+} plp_ba_result;
+
+typedef struct plp_ba plp_ba;           /* a problem resident on one GPU */
+typedef struct plp_ba_comm plp_ba_comm; /* NCCL communicator for landmark-sharded multi-GPU BA */
+
+/* local_bundle_adjuster[_extended_line|_extended_plane]::optimize(curr_keyfrm, force_stop_flag) after the gather.
+ * force_stop may be NULL; it is polled between chunks of LM iterations (mapping_module.cc:159-164). */
+PLP_API plp_status plp_local_ba(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg *cfg,
+                                volatile const uint8_t *force_stop, plp_ba_result *r);
+/* split form: upload once, solve (repeatable), destroy.  With `comm`, `p` holds THIS RANK's block of landmarks
+ * (all keyframes, its points/lines and their edges); every rank calls the same functions. */
+PLP_API plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg *cfg, plp_ba_comm *comm,
+                                 plp_ba **out);
+PLP_API plp_status plp_ba_solve(plp_ba *ba, volatile const uint8_t *force_stop, plp_ba_result *r);
+PLP_API void plp_ba_destroy(plp_ba *ba);
+/* benchmark hook: run `tries` LM tries (linearise + Schur + solve + update + accept/reject) from the initial state */
+PLP_API plp_status plp_ba_bench_tries(plp_ba *ba, int tries, int32_t *iters_done, int32_t *tries_done);
+
+/* multi-GPU: rank 0 creates a 128-byte id, the launcher broadcasts it, every rank joins */
+PLP_API plp_status plp_ba_comm_unique_id(uint8_t id_out[128]);
+PLP_API plp_status plp_ba_comm_init(plp_ctx *ctx, const uint8_t id[128], int world, int rank, plp_ba_comm **out);
+PLP_API void plp_ba_comm_destroy(plp_ba_comm *comm);
+
 #ifdef __cplusplus
 }
 #endif

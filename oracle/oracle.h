@@ -25,6 +25,8 @@
 #include <stdint.h>
 #include <stddef.h>
 #include "orb.h"
+#include "pose_opt.h"
+#include "local_ba.h"
 
 #ifdef __cplusplus
 extern "C" {

@@ -1,0 +1,982 @@
+// local_ba.cu -- Schur-complement Levenberg-Marquardt local bundle adjustment on sm_100a (FP64).
+//
+// Replaces optimize::local_bundle_adjuster::optimize (optimize/local_bundle_adjuster.cc:160-410),
+// local_bundle_adjuster_extended_line::optimize (optimize/local_bundle_adjuster_extended_line.cc:190-640) and
+// local_bundle_adjuster_extended_plane::optimize (optimize/local_bundle_adjuster_extended_plane.cc:300-430) from
+// the point where the graph has been gathered: SE3 keyframe vertices (some fixed), marginalised point (3-dof,
+// additive) and line (4-dof orthonormal Pluecker) landmark vertices, one binary reprojection edge per observation
+// (Huber in the first optimize(5), none in the second optimize(10), outliers = chi2 > 5.991|7.815 or depth <= 0),
+// optional unary point-to-plane edges.  g2o's BlockSolver + OptimizationAlgorithmLevenberg are restated.
+//
+// Work decomposition (one LM "try" = 5 small kernels, no host synchronisation inside an optimize() chunk):
+//   ba_decide_kernel   1 CTA    accept/reject of the previous try (rho test), lambda / nu update, iteration count
+//   ba_linearize_kernel G CTAs  landmark-sharded: one warp per landmark evaluates its edges (residual, Jacobians,
+//                               Huber weight), forms Hll, bl, (Hll+lambda I)^-1 and the per-edge blocks
+//                               W = Hpl, Y = W Dinv; the CTA then accumulates its share of the reduced camera
+//                               system S = Hpp - sum_l Hpl Dinv Hpl^T in SHARED MEMORY WITHOUT ATOMICS: every thread
+//                               owns a fixed set of S entries and loops over the landmarks of the batch
+//                               (deterministic summation order)
+//   ba_reduce_kernel   n CTAs   sums the G per-CTA partial systems into the packed vector
+//                               [S upper blocks | g | bp | chi2 | max-diag slots]   <- the ONLY data a multi-GPU run
+//                               exchanges: one ncclAllReduce(sum) of this vector per try (ba_nccl.cu)
+//   ba_solve_kernel    1 CTA    dense Cholesky of the 6N x 6N reduced system in shared memory, dp, trial poses
+//   ba_update_kernel   G CTAs   back-substitution dl = Dinv (bl - W^T dp), trial landmarks, errors at the trial
+//                               state (kept even if the step is rejected, like g2o), chi2 / scale partial sums
+// Linearisation is recomputed on every try (also after a rejection) instead of being cached: the numbers are
+// identical and it removes all bookkeeping.  Numeric Jacobians (delta = 1e-9 central differences) are used where
+// the reference has no linearizeOplus (line edges, plane edges), see g2o BaseBinaryEdge::linearizeOplus.
+#include "common.cuh"
+#include "pack.cuh"
+#include "se3.cuh"
+#include "ba_kernels.cuh"
+
+namespace plp {
+
+namespace {
+
+using se3::Pose;
+
+constexpr int kBaThreads = 512;
+constexpr int kBaWarps = kBaThreads / 32;
+constexpr int kPool = 96;        // per-batch pool of (free keyframe, landmark) blocks
+constexpr double kDelta = 1e-9;  // g2o numeric Jacobian step
+
+// ---------------------------------------------------------------------------------------------------------
+// Line3D (optimize/g2o/line3d.h:57-207): Pluecker (w, d) <-> orthonormal (U in SO3, W in SO2)
+// ---------------------------------------------------------------------------------------------------------
+__device__ void line_oplus(const double *L, const double *v, double *out) {
+    // toOrthonormal (line3d.h:137-157)
+    const double mx = sqrt(L[3] * L[3] + L[4] * L[4] + L[5] * L[5]);  // |d|
+    const double my = sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);  // |w|
+    const double wn = 1.0 / sqrt(mx * mx + my * my);
+    double W[4] = {my * wn, -mx * wn, mx * wn, my * wn};
+    const double mn = 1.0 / my, dn = 1.0 / mx;
+    const double cx = L[1] * L[5] - L[2] * L[4], cy = L[2] * L[3] - L[0] * L[5], cz = L[0] * L[4] - L[1] * L[3];
+    const double cn = 1.0 / sqrt(cx * cx + cy * cy + cz * cz);
+    double U[9] = {L[0] * mn, L[3] * dn, cx * cn, L[1] * mn, L[4] * dn, cy * cn, L[2] * mn, L[5] * dn, cz * cn};
+    // update (line3d.h:171-186)
+    const double c = cos(v[3]), s = sin(v[3]);
+    double qw = sqrt(1 - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2])), qx = v[0], qy = v[1], qz = v[2];
+    const double qn = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+    qw /= qn;
+    qx /= qn;
+    qy /= qn;
+    qz /= qn;
+    double Ru[9];
+    se3::quat_to_R(qw, qx, qy, qz, Ru);
+    double U2[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) U2[i * 3 + j] = U[i * 3] * Ru[j] + U[i * 3 + 1] * Ru[3 + j] + U[i * 3 + 2] * Ru[6 + j];
+    const double W0 = W[0] * c + W[1] * s, W2 = W[2] * c + W[3] * s;
+    // fromOrthonormal (line3d.h:116-134) + normalize (twice, as in oplus)
+    double o[6] = {U2[0] * W0, U2[3] * W0, U2[6] * W0, U2[1] * W2, U2[4] * W2, U2[7] * W2};
+    for (int rep = 0; rep < 2; ++rep) {
+        const double n = 1.0 / sqrt(o[3] * o[3] + o[4] * o[4] + o[5] * o[5]);
+        for (int k = 0; k < 6; ++k) o[k] *= n;
+    }
+    for (int k = 0; k < 6; ++k) out[k] = o[k];
+}
+
+// reproj_edge_line3d::depth_is_positive_via_endpoints_trimming (reproj_edge_line3d_orthonormal.h:97-177)
+__device__ bool line_depth_positive(const se3::Cam &c, const Pose &P, const double *L, const float *obs) {
+    const double *R = P.R, *t = P.t;
+    double Rn[3], Rd[3];
+    for (int r = 0; r < 3; ++r) {
+        Rn[r] = R[r * 3] * L[0] + R[r * 3 + 1] * L[1] + R[r * 3 + 2] * L[2];
+        Rd[r] = R[r * 3] * L[3] + R[r * 3 + 1] * L[4] + R[r * 3 + 2] * L[5];
+    }
+    const double lc0 = Rn[0] + (t[1] * Rd[2] - t[2] * Rd[1]), lc1 = Rn[1] + (t[2] * Rd[0] - t[0] * Rd[2]);
+    const double lc2 = Rn[2] + (t[0] * Rd[1] - t[1] * Rd[0]);
+    const double l1 = c.fy * lc0, l2 = c.fx * lc1, l3 = -c.fy * c.cx * lc0 - c.fx * c.cy * lc1 + c.fx * c.fy * lc2;
+    const double sp0 = obs[0], sp1 = obs[1], ep0 = obs[2], ep1 = obs[3];
+    const double x_sp = -(sp1 - (l2 / l1) * sp0 + (l3 / l2)) * ((l1 * l2) / (l1 * l1 + l2 * l2));
+    const double y_sp = -(l1 / l2) * x_sp - (l3 / l2);
+    const double x_ep = -(ep1 - (l2 / l1) * ep0 + (l3 / l2)) * ((l1 * l2) / (l1 * l1 + l2 * l2));
+    const double y_ep = -(l1 / l2) * x_ep - (l3 / l2);
+    const double y_0sp = sp1 - (l2 / l1) * sp0, y_0ep = ep1 - (l2 / l1) * ep0;
+    double Pm[12];
+    const double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1};
+    for (int r = 0; r < 3; ++r)
+        for (int col = 0; col < 4; ++col) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += K[r * 3 + k] * (col < 3 ? R[k * 3 + col] : t[k]);
+            Pm[r * 4 + col] = s;
+        }
+    double depth[2];
+    for (int which = 0; which < 2; ++which) {
+        const double xc = which ? x_ep : x_sp, yc = which ? y_ep : y_sp, y0 = which ? y_0ep : y_0sp;
+        // line through (xc, yc, 1) and (0, y0, 1)
+        const double a0 = yc * 1.0 - 1.0 * y0, a1 = 1.0 * 0.0 - xc * 1.0, a2 = xc * y0 - yc * 0.0;
+        double pl[4];
+        for (int col = 0; col < 4; ++col) pl[col] = Pm[col] * a0 + Pm[4 + col] * a1 + Pm[8 + col] * a2;
+        // [m]x pl.head<3> + d pl[3] ; -d . pl.head<3>
+        const double X0 = (-L[2] * pl[1] + L[1] * pl[2]) + L[3] * pl[3];
+        const double X1 = (L[2] * pl[0] - L[0] * pl[2]) + L[4] * pl[3];
+        const double X2 = (-L[1] * pl[0] + L[0] * pl[1]) + L[5] * pl[3];
+        const double X3 = -(L[3] * pl[0] + L[4] * pl[1] + L[5] * pl[2]);
+        depth[which] = R[6] * (X0 / X3) + R[7] * (X1 / X3) + R[8] * (X2 / X3) + t[2] * 1.0;
+    }
+    return 0 < depth[0] && 0 < depth[1];
+}
+
+// inverse of a small symmetric matrix (D = 3 or 4) by Gauss-Jordan with partial pivoting
+__device__ bool inv_small(const double *A, int D, double *Ai) {
+    double M[16], I[16];
+    for (int i = 0; i < D * D; ++i) {
+        M[i] = A[i];
+        I[i] = 0;
+    }
+    for (int i = 0; i < D; ++i) I[i * D + i] = 1;
+    for (int c = 0; c < D; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < D; ++r)
+            if (fabs(M[r * D + c]) > fabs(M[piv * D + c])) piv = r;
+        if (M[piv * D + c] == 0.0) return false;
+        if (piv != c)
+            for (int k = 0; k < D; ++k) {
+                double tmp = M[c * D + k];
+                M[c * D + k] = M[piv * D + k];
+                M[piv * D + k] = tmp;
+                tmp = I[c * D + k];
+                I[c * D + k] = I[piv * D + k];
+                I[piv * D + k] = tmp;
+            }
+        const double d = 1.0 / M[c * D + c];
+        for (int k = 0; k < D; ++k) {
+            M[c * D + k] *= d;
+            I[c * D + k] *= d;
+        }
+        for (int r = 0; r < D; ++r) {
+            if (r == c) continue;
+            const double f = M[r * D + c];
+            for (int k = 0; k < D; ++k) {
+                M[r * D + k] -= f * M[c * D + k];
+                I[r * D + k] -= f * I[c * D + k];
+            }
+        }
+    }
+    for (int i = 0; i < D * D; ++i) Ai[i] = I[i];
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// edge evaluation shared by linearize / update / classify
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double eval_pt(const se3::Cam &cam, const Pose &P, const double *X, const float *obs, double info,
+                                          double *e, double *pc) {
+    const bool stereo = !(obs[2] < 0);
+    se3::map_point(P.R, P.t, X, pc);
+    const double o[3] = {(double)obs[0], (double)obs[1], (double)obs[2]};
+    se3::point_error(cam, pc, o, stereo, e);
+    return e[0] * (info * e[0]) + e[1] * (info * e[1]) + (stereo ? e[2] * (info * e[2]) : 0.0);
+}
+__device__ __forceinline__ double eval_ln(const se3::Cam &cam, const Pose &P, const double *L, const float *obs, double info,
+                                          double *e) {
+    const double o[4] = {(double)obs[0], (double)obs[1], (double)obs[2], (double)obs[3]};
+    se3::line_error(cam, P.R, P.t, L, o, e);
+    return e[0] * (info * e[0]) + e[1] * (info * e[1]);
+}
+__device__ __forceinline__ double eval_plane(const double *X, const double *fn) {
+    return (X[0] * fn[0] + X[1] * fn[1] + X[2] * fn[2] + fn[3]) / sqrt(fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2]);
+}
+
+struct BaPoolEntry {
+    double W[24];   // Hpl block, 6 x D row-major
+    double Y[24];   // W * Dinv
+    double A[21];   // Jp^T w Jp, upper triangle row-wise
+    double bpe[6];  // -Jp^T w e
+    double gpe[6];  // bpe - W * (Dinv bl)
+};
+
+struct BaSmem {
+    BaPoolEntry pool[kPool];
+    double pert_line[kBaWarps][8][6];  // per warp: the 8 perturbed lines of its landmark
+    double hll[kBaWarps][16], bl[kBaWarps][4], dinv[kBaWarps][16], dl[kBaWarps][4];
+    short slot[kBaWarps][kBaMaxFree];  // landmark-in-batch x free keyframe -> pool index (-1: none)
+    int pool_base[kBaWarps + 1];
+    int warp_cnt[kBaWarps];
+    double red[kBaWarps][2];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// =========================================================================================================
+// ba_linearize_kernel
+// =========================================================================================================
+__global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
+    extern __shared__ __align__(16) uint8_t ba_smem_raw[];
+    const BaState &ST = *B.state;
+    if (ST.phase == kBaDone) return;
+    BaSmem &S = *reinterpret_cast<BaSmem *>(ba_smem_raw);
+    const int nS = B.n_pairs * 36, n6 = 6 * B.n_free;
+    double *Ssm = reinterpret_cast<double *>(ba_smem_raw + ((sizeof(BaSmem) + 15) & ~(size_t)15));
+    double *gsm = Ssm + nS, *bpsm = gsm + n6;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool init_mode = ST.phase == kBaNeedInit;  // only max diag(H) is wanted
+    const double lambda = init_mode ? 0.0 : ST.lambda;
+    const bool robust = ST.robust != 0;
+    const int cur = ST.cur;
+    const Pose *poses = B.poses[cur];
+    const double *pts = B.pts[cur], *lines = B.lines[cur];
+    const se3::Cam cam{B.fx, B.fy, B.cx, B.cy, B.bf};
+    for (int i = tid; i < nS + 2 * n6; i += kBaThreads) Ssm[i] = 0.0;
+    double chi_acc = 0.0, maxdiag = 0.0;
+    const int lm_begin = B.cta_ranges[blockIdx.x], lm_end = B.cta_ranges[blockIdx.x + 1];
+    const int LB = B.batch_landmarks;  // landmarks per batch (<= kBaWarps), LB * max_free_degree <= kPool
+    __syncthreads();
+
+    for (int batch0 = lm_begin; batch0 < lm_end; batch0 += LB) {
+        const int lmb = warp;  // this warp's landmark inside the batch
+        const int lm = batch0 + lmb;
+        const bool has_lm = lmb < LB && lm < lm_end;
+        // ---- slot table reset, count free active edges per landmark for the pool layout
+        for (int i = tid; i < kBaWarps * kBaMaxFree; i += kBaThreads) (&S.slot[0][0])[i] = -1;
+        int e0 = 0, e1 = 0, D = 3;
+        bool is_line = false;
+        if (has_lm) {
+            is_line = lm >= B.n_pts;
+            D = is_line ? 4 : 3;
+            const int *off = is_line ? B.ln_off : B.pt_off;
+            const int li = is_line ? lm - B.n_pts : lm;
+            e0 = off[li];
+            e1 = off[li + 1];
+        }
+        const int *ekf = is_line ? B.ln_kf : B.pt_kf;
+        const uint8_t *elevel = is_line ? B.ln_level : B.pt_level;
+        int nfree = 0;
+        for (int e = e0 + lane; e < e1; e += 32) nfree += (elevel[e] == 0 && B.kf_hidx[ekf[e]] >= 0) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nfree += __shfl_xor_sync(0xffffffffu, nfree, o);
+        if (lane == 0) S.warp_cnt[warp] = has_lm ? nfree : 0;
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int w = 0; w < kBaWarps; ++w) {
+                S.pool_base[w] = acc;
+                acc += S.warp_cnt[w];
+            }
+            S.pool_base[kBaWarps] = acc;
+        }
+        __syncthreads();
+        // ---- phase 1: one warp per landmark
+        if (has_lm) {
+            const int li = is_line ? lm - B.n_pts : lm;
+            const double *Lm = is_line ? lines + 6 * (size_t)li : nullptr;
+            const double *X = is_line ? nullptr : pts + 3 * (size_t)li;
+            if (is_line && lane < 8) {  // perturbed lines for the numeric Jacobian w.r.t. the line vertex
+                double v[4] = {0, 0, 0, 0};
+                v[lane >> 1] = (lane & 1) ? -kDelta : kDelta;
+                line_oplus(Lm, v, S.pert_line[warp][lane]);
+            }
+            __syncwarp();
+            double hll[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, bl[4] = {0, 0, 0, 0};  // upper triangle of Hll (D<=4)
+            bool any_active = false;
+            int pool_cursor = S.pool_base[warp];
+            for (int ebase = e0; ebase < e1; ebase += 32) {
+                const int e = ebase + lane;
+                const bool in = e < e1;
+                const bool active = in && elevel[e] == 0;
+                double Jp[18], Jl[12], r[3] = {0, 0, 0}, w = 0;
+                int Rr = 2, h = -1;
+                if (active) {
+                    const int k = ekf[e];
+                    h = B.kf_hidx[k];
+                    const Pose &P = poses[k];
+                    double chi2;
+                    if (!is_line) {
+                        const float *obs = B.pt_obs + 3 * (size_t)e;
+                        const double info = B.pt_info[e];
+                        double pc[3];
+                        chi2 = eval_pt(cam, P, X, obs, info, r, pc);
+                        const bool stereo = !(obs[2] < 0);
+                        Rr = stereo ? 3 : 2;
+                        se3::point_jac_pose(cam, pc, stereo, Jp);
+                        double Jl9[9];
+                        se3::point_jac_landmark(cam, P.R, pc, stereo, Jl9);
+                        for (int q = 0; q < 9; ++q) Jl[q] = Jl9[q];
+                        w = info;
+                        B.pt_chi2[e] = chi2;
+                        double rho0 = chi2, rho1 = 1.0;
+                        if (robust) se3::huber(chi2, B.delta_pt, rho0, rho1);
+                        chi_acc += rho0;
+                        w *= rho1;
+                    } else {
+                        const float *obs = B.ln_obs + 4 * (size_t)e;
+                        const double info = B.ln_info[e];
+                        chi2 = eval_ln(cam, P, Lm, obs, info, r);
+                        const double scalar = 1.0 / (2 * kDelta);
+                        const Pose *pp = B.pert_pose + 12 * (size_t)k;
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) {
+                            double ep[2], em[2];
+                            eval_ln(cam, pp[2 * d], Lm, obs, info, ep);
+                            eval_ln(cam, pp[2 * d + 1], Lm, obs, info, em);
+                            Jp[d] = scalar * (ep[0] - em[0]);
+                            Jp[6 + d] = scalar * (ep[1] - em[1]);
+                        }
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) {
+                            double ep[2], em[2];
+                            eval_ln(cam, P, S.pert_line[warp][2 * d], obs, info, ep);
+                            eval_ln(cam, P, S.pert_line[warp][2 * d + 1], obs, info, em);
+                            Jl[d] = scalar * (ep[0] - em[0]);
+                            Jl[4 + d] = scalar * (ep[1] - em[1]);
+                        }
+                        w = info;
+                        B.ln_chi2[e] = chi2;
+                        double rho0 = chi2, rho1 = 1.0;
+                        if (robust) se3::huber(chi2, B.delta_ln, rho0, rho1);
+                        chi_acc += rho0;
+                        w *= rho1;
+                    }
+                    // landmark block contributions
+                    int q = 0;
+                    for (int a = 0; a < D; ++a) {
+                        for (int c = a; c < D; ++c) {
+                            double s = 0;
+                            for (int rr = 0; rr < Rr; ++rr) s += Jl[rr * D + a] * w * Jl[rr * D + c];
+                            hll[q++] += s;
+                        }
+                        double s = 0;
+                        for (int rr = 0; rr < Rr; ++rr) s += Jl[rr * D + a] * (-w * r[rr]);
+                        bl[a] += s;
+                    }
+                }
+                any_active = any_active || __any_sync(0xffffffffu, active);
+                // free-keyframe edges get a pool entry (stable order = edge order)
+                const bool freee = active && h >= 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, freee);
+                if (freee) {
+                    const int pi = pool_cursor + __popc(bal & ((1u << lane) - 1));
+                    BaPoolEntry &pe = S.pool[pi];
+                    for (int a = 0; a < 6; ++a) {
+                        for (int c = 0; c < D; ++c) {
+                            double s = 0;
+                            for (int rr = 0; rr < Rr; ++rr) s += Jp[rr * 6 + a] * w * Jl[rr * D + c];
+                            pe.W[a * D + c] = s;
+                        }
+                        double s = 0;
+                        for (int rr = 0; rr < Rr; ++rr) s += Jp[rr * 6 + a] * (-w * r[rr]);
+                        pe.bpe[a] = s;
+                    }
+                    int q = 0;
+                    for (int a = 0; a < 6; ++a)
+                        for (int c = a; c < 6; ++c) {
+                            double s = 0;
+                            for (int rr = 0; rr < Rr; ++rr) s += Jp[rr * 6 + a] * w * Jp[rr * 6 + c];
+                            pe.A[q++] = s;
+                        }
+                    S.slot[lmb][h] = (short)pi;
+                    // W is needed again by the back-substitution
+                    double *Wg = (is_line ? B.ln_W : B.pt_W) + 24 * (size_t)e;
+                    for (int q2 = 0; q2 < 6 * D; ++q2) Wg[q2] = pe.W[q2];
+                }
+                pool_cursor += __popc(bal);
+            }
+            // plane edge (unary, numeric Jacobian; Huber delta = 1 in both phases)
+            if (!is_line && lane == 0) {
+                const int pe_i = B.pt_plane ? B.pt_plane[li] : -1;
+                if (pe_i >= 0) {
+                    const double *fn = B.pl_fn + 4 * (size_t)pe_i;
+                    const double err = eval_plane(X, fn);
+                    double Jn[3];
+                    for (int d = 0; d < 3; ++d) {
+                        double Xp[3] = {X[0], X[1], X[2]}, Xm[3] = {X[0], X[1], X[2]};
+                        Xp[d] += kDelta;
+                        Xm[d] -= kDelta;
+                        Jn[d] = (1.0 / (2 * kDelta)) * (eval_plane(Xp, fn) - eval_plane(Xm, fn));
+                    }
+                    double rho0, rho1;
+                    se3::huber(err * err, 1.0, rho0, rho1);
+                    chi_acc += rho0;
+                    B.pl_err[pe_i] = err;
+                    int q = 0;
+                    for (int a = 0; a < 3; ++a) {
+                        for (int c = a; c < 3; ++c) hll[q++] += Jn[a] * rho1 * Jn[c];
+                        bl[a] += Jn[a] * (-rho1 * err);
+                    }
+                    any_active = true;
+                }
+            }
+            any_active = __any_sync(0xffffffffu, any_active);
+            // reduce Hll / bl over the lanes
+            const int nh = D * (D + 1) / 2;
+            for (int q = 0; q < nh; ++q) hll[q] = warp_sum(hll[q]);
+            for (int a = 0; a < D; ++a) bl[a] = warp_sum(bl[a]);
+            if (lane == 0) {
+                double H[16];
+                int q = 0;
+                for (int a = 0; a < D; ++a)
+                    for (int c = a; c < D; ++c) {
+                        H[a * D + c] = hll[q];
+                        H[c * D + a] = hll[q];
+                        ++q;
+                    }
+                if (any_active)
+                    for (int a = 0; a < D; ++a) maxdiag = fmax(maxdiag, fabs(H[a * D + a]));
+                for (int a = 0; a < D; ++a) H[a * D + a] += lambda;
+                double Di[16];
+                bool ok = any_active && !init_mode && inv_small(H, D, Di);
+                if (!ok)
+                    for (int i = 0; i < 16; ++i) Di[i] = 0.0;
+                double *Dg = (is_line ? B.ln_Dinv + 16 * (size_t)li : B.pt_Dinv + 16 * (size_t)li);
+                double *bg = (is_line ? B.ln_bl + 4 * (size_t)li : B.pt_bl + 4 * (size_t)li);
+                for (int i = 0; i < D * D; ++i) {
+                    S.dinv[warp][i] = Di[i];
+                    Dg[i] = Di[i];
+                }
+                for (int a = 0; a < D; ++a) {
+                    double s = 0;
+                    for (int c = 0; c < D; ++c) s += Di[a * D + c] * bl[c];
+                    S.dl[warp][a] = s;
+                    S.bl[warp][a] = bl[a];
+                    bg[a] = bl[a];
+                }
+                (is_line ? B.ln_active : B.pt_active)[li] = (any_active && (ok || init_mode)) ? 1 : 0;
+            }
+            __syncwarp();
+            // Y = W Dinv, gpe = bpe - W dl for this landmark's pool entries
+            const int pb = S.pool_base[warp], pn = S.warp_cnt[warp];
+            for (int pi = pb + lane; pi < pb + pn; pi += 32) {
+                BaPoolEntry &pe = S.pool[pi];
+                for (int a = 0; a < 6; ++a) {
+                    double gs = pe.bpe[a];
+                    for (int c = 0; c < D; ++c) {
+                        double s = 0;
+                        for (int k = 0; k < D; ++k) s += pe.W[a * D + k] * S.dinv[warp][k * D + c];
+                        pe.Y[a * D + c] = s;
+                        gs -= pe.W[a * D + c] * S.dl[warp][c];
+                    }
+                    pe.gpe[a] = gs;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: every thread owns fixed entries of S / g / bp (no atomics, fixed summation order)
+        const int nb = min(LB, lm_end - batch0);
+        for (int ent = tid; ent < nS; ent += kBaThreads) {
+            const int p = ent / 36, rc = ent - p * 36, r = rc / 6, c = rc - r * 6;
+            const int bi = B.pair_bi[p], bj = B.pair_bj[p];
+            double acc = 0.0;
+            for (int lb = 0; lb < nb; ++lb) {
+                const int si = S.slot[lb][bi];
+                if (si < 0) continue;
+                const int sj = S.slot[lb][bj];
+                if (sj < 0) continue;
+                const int Dl = (batch0 + lb) >= B.n_pts ? 4 : 3;
+                const BaPoolEntry &pi = S.pool[si], &pj = S.pool[sj];
+                double s = 0;
+                for (int m = 0; m < Dl; ++m) s += pi.Y[r * Dl + m] * pj.W[c * Dl + m];
+                acc -= s;
+                if (bi == bj) {
+                    const int a = r < c ? r : c, b2 = r < c ? c : r;
+                    acc += pi.A[a * 6 - a * (a - 1) / 2 + (b2 - a)];
+                }
+            }
+            Ssm[ent] += acc;
+        }
+        for (int ent = tid; ent < n6; ent += kBaThreads) {
+            const int bi = ent / 6, r = ent - bi * 6;
+            double ga = 0.0, ba = 0.0;
+            for (int lb = 0; lb < nb; ++lb) {
+                const int si = S.slot[lb][bi];
+                if (si < 0) continue;
+                ga += S.pool[si].gpe[r];
+                ba += S.pool[si].bpe[r];
+            }
+            gsm[ent] += ga;
+            bpsm[ent] += ba;
+        }
+        __syncthreads();
+    }
+    // ---- per-CTA partial system + chi2 / max-diag
+    double *out = B.partial + (size_t)blockIdx.x * B.packed_len;
+    for (int i = tid; i < nS + 2 * n6; i += kBaThreads) out[i] = Ssm[i];
+    chi_acc = warp_sum(chi_acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxdiag = fmax(maxdiag, __shfl_xor_sync(0xffffffffu, maxdiag, o));
+    if (lane == 0) {
+        S.red[warp][0] = chi_acc;
+        S.red[warp][1] = maxdiag;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double c = 0, m = 0;
+        for (int w = 0; w < kBaWarps; ++w) {
+            c += S.red[w][0];
+            m = fmax(m, S.red[w][1]);
+        }
+        out[nS + 2 * n6] = c;
+        out[nS + 2 * n6 + 1] = m;
+    }
+}
+
+// =========================================================================================================
+// ba_reduce_kernel: packed = sum over CTAs of the partial systems; max-diag goes to this rank's one-hot slot
+// =========================================================================================================
+__global__ void ba_reduce_kernel(BaDev B) {
+    if (B.state->phase == kBaDone) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_sum = B.n_pairs * 36 + 12 * B.n_free + 1;
+    if (i < n_sum) {
+        double s = 0;
+        for (int g = 0; g < B.num_ctas; ++g) s += B.partial[(size_t)g * B.packed_len + i];
+        B.packed[i] = s;
+    } else if (i == n_sum) {
+        double m = 0;
+        for (int g = 0; g < B.num_ctas; ++g) m = fmax(m, B.partial[(size_t)g * B.packed_len + n_sum]);
+        // max diag of the pose blocks = diagonal of the diagonal S blocks in init mode (no Schur term yet)
+        for (int w = 0; w < B.world; ++w) B.packed[n_sum + w] = (w == B.rank) ? m : 0.0;
+    }
+}
+
+// =========================================================================================================
+// ba_solve_kernel: 6N x 6N Cholesky in shared memory (packed lower triangle)
+// =========================================================================================================
+constexpr int kSolveThreads = 1024;
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
+
+__global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
+    extern __shared__ __align__(16) double solve_smem[];
+    BaState &ST = *B.state;
+    if (ST.phase == kBaDone) return;
+    const int tid = threadIdx.x;
+    const int N = B.n_free, n = 6 * N, nS = B.n_pairs * 36;
+    const double *packed = B.packed;
+    if (ST.phase == kBaNeedInit) {  // computeLambdaInit: tau * max diag over every active vertex
+        if (tid == 0) {
+            double md = 0;
+            for (int w = 0; w < B.world; ++w) md = fmax(md, packed[nS + 2 * n + 1 + w]);
+            for (int p = 0; p < B.n_pairs; ++p)
+                if (B.pair_bi[p] == B.pair_bj[p])
+                    for (int a = 0; a < 6; ++a) md = fmax(md, fabs(packed[p * 36 + a * 7]));
+            ST.lambda = 1e-5 * md;
+            ST.ni = 2;
+            ST.phase = kBaRunning;
+            ST.iter_start = 1;
+            ST.have_trial = 0;
+        }
+        return;
+    }
+    double *L = solve_smem;               // n(n+1)/2
+    double *rhs = L + (size_t)n * (n + 1) / 2;  // n
+    double *x = rhs + n;                  // n
+    __shared__ int s_ok;
+    const double lambda = ST.lambda;
+    for (int p = tid; p < B.n_pairs * 36; p += kSolveThreads) {
+        const int pr = p / 36, rc = p - pr * 36, r = rc / 6, c = rc - r * 6;
+        const int bi = B.pair_bi[pr], bj = B.pair_bj[pr];
+        const int gi = bi * 6 + r, gj = bj * 6 + c;
+        double v = packed[p];
+        if (bi == bj) {
+            if (c > r) continue;  // lower part of the (symmetric) diagonal block
+            if (r == c) v += lambda;
+            L[tri(gi, gj)] = v;
+        } else {
+            L[tri(gj, gi)] = v;  // bi < bj: entry (gi, gj) of the upper part -> (gj, gi) of the lower part
+        }
+    }
+    for (int i = tid; i < n; i += kSolveThreads) rhs[i] = packed[nS + i];
+    if (tid == 0) s_ok = 1;
+    __syncthreads();
+    // right-looking Cholesky
+    for (int j = 0; j < n; ++j) {
+        const double djj = L[tri(j, j)];
+        if (!(djj > 0.0) || !isfinite(djj)) {
+            if (tid == 0) s_ok = 0;
+            break;
+        }
+        const double d = sqrt(djj);
+        __syncthreads();
+        for (int i = j + tid; i < n; i += kSolveThreads) L[tri(i, j)] = (i == j) ? d : L[tri(i, j)] / d;
+        __syncthreads();
+        // trailing update: L[i][k] -= L[i][j] * L[k][j] for j < k <= i
+        const int m = n - j - 1;
+        const int cnt = m * (m + 1) / 2;
+        for (int q = tid; q < cnt; q += kSolveThreads) {
+            // q -> (a, b) with b <= a in the m x m trailing triangle
+            int a = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+            while ((a + 1) * (a + 2) / 2 <= q) ++a;
+            while (a * (a + 1) / 2 > q) --a;
+            const int b2 = q - a * (a + 1) / 2;
+            const int i = j + 1 + a, k = j + 1 + b2;
+            L[tri(i, k)] -= L[tri(i, j)] * L[tri(k, j)];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const int ok = s_ok;
+    // substitutions by one warp (column oriented)
+    if (tid < 32 && ok) {
+        for (int j = 0; j < n; ++j) {
+            const double xj = rhs[j] / L[tri(j, j)];
+            __syncwarp();
+            if (tid == 0) rhs[j] = xj;
+            for (int i = j + 1 + tid; i < n; i += 32) rhs[i] -= L[tri(i, j)] * xj;
+            __syncwarp();
+        }
+        for (int j = n - 1; j >= 0; --j) {
+            const double xj = rhs[j] / L[tri(j, j)];
+            __syncwarp();
+            if (tid == 0) x[j] = xj;
+            for (int i = tid; i < j; i += 32) rhs[i] -= L[tri(j, i)] * xj;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (!ok)
+        for (int i = tid; i < n; i += kSolveThreads) x[i] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kSolveThreads) B.dp[i] = x[i];
+    // trial poses, perturbed trial poses are produced when (if) the step is accepted
+    const int cur = ST.cur;
+    for (int k = tid; k < B.n_kf; k += kSolveThreads) {
+        const int h = B.kf_hidx[k];
+        Pose P = B.poses[cur][k];
+        if (h >= 0 && ok) P = se3::oplus(P, x + 6 * h);
+        B.poses[cur ^ 1][k] = P;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (ST.iter_start) {  // currentChi = activeRobustChi2() at the start of an iteration
+            ST.current_chi = packed[nS + 2 * n];
+            ST.qmax = 0;
+            ST.iter_start = 0;
+        }
+        double sc = 0;
+        for (int i = 0; i < n; ++i) sc += x[i] * (lambda * x[i] + packed[nS + n + i]);
+        ST.scale_pose = sc;
+        ST.ok2 = ok;
+        ST.have_trial = 1;
+    }
+}
+
+// =========================================================================================================
+// ba_update_kernel: back-substitution, trial landmarks, trial errors
+// =========================================================================================================
+__global__ void __launch_bounds__(kBaThreads, 1) ba_update_kernel(BaDev B) {
+    const BaState &ST = *B.state;
+    if (ST.phase == kBaDone || !ST.have_trial) return;
+    __shared__ double s_dp[6 * kBaMaxFree];
+    __shared__ double s_red[kBaWarps][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cur = ST.cur, nxt = cur ^ 1;
+    const double lambda = ST.lambda;
+    const bool robust = ST.robust != 0, ok2 = ST.ok2 != 0;
+    const se3::Cam cam{B.fx, B.fy, B.cx, B.cy, B.bf};
+    for (int i = tid; i < 6 * B.n_free; i += kBaThreads) s_dp[i] = B.dp[i];
+    __syncthreads();
+    const Pose *tposes = B.poses[nxt];
+    double chi_acc = 0.0, scale_acc = 0.0;
+    const int lm_begin = B.cta_ranges[blockIdx.x], lm_end = B.cta_ranges[blockIdx.x + 1];
+    for (int lm = lm_begin + warp; lm < lm_end; lm += kBaWarps) {
+        const bool is_line = lm >= B.n_pts;
+        const int D = is_line ? 4 : 3;
+        const int li = is_line ? lm - B.n_pts : lm;
+        const int *off = is_line ? B.ln_off : B.pt_off;
+        const int e0 = off[li], e1 = off[li + 1];
+        const int *ekf = is_line ? B.ln_kf : B.pt_kf;
+        const uint8_t *elevel = is_line ? B.ln_level : B.pt_level;
+        const bool act = (is_line ? B.ln_active : B.pt_active)[li] != 0;
+        // cl = bl - sum_e W_e^T dp_h(e)
+        double cl[4] = {0, 0, 0, 0};
+        if (act && ok2) {
+            for (int e = e0 + lane; e < e1; e += 32) {
+                if (elevel[e]) continue;
+                const int h = B.kf_hidx[ekf[e]];
+                if (h < 0) continue;
+                const double *W = (is_line ? B.ln_W : B.pt_W) + 24 * (size_t)e;
+                for (int c = 0; c < D; ++c) {
+                    double s = 0;
+                    for (int a = 0; a < 6; ++a) s += W[a * D + c] * s_dp[6 * h + a];
+                    cl[c] -= s;
+                }
+            }
+        }
+        for (int c = 0; c < D; ++c) cl[c] = warp_sum(cl[c]);
+        double dl[4] = {0, 0, 0, 0};
+        const double *bl = (is_line ? B.ln_bl + 4 * (size_t)li : B.pt_bl + 4 * (size_t)li);
+        if (act && ok2) {
+            const double *Di = (is_line ? B.ln_Dinv + 16 * (size_t)li : B.pt_Dinv + 16 * (size_t)li);
+            for (int a = 0; a < D; ++a) {
+                double s = 0;
+                for (int c = 0; c < D; ++c) s += Di[a * D + c] * (bl[c] + cl[c]);
+                dl[a] = s;
+            }
+            if (lane == 0)
+                for (int a = 0; a < D; ++a) scale_acc += dl[a] * (lambda * dl[a] + bl[a]);
+        }
+        // trial landmark
+        double Xt[6];
+        if (!is_line) {
+            const double *X = B.pts[cur] + 3 * (size_t)li;
+            for (int a = 0; a < 3; ++a) Xt[a] = X[a] + dl[a];
+            if (lane == 0)
+                for (int a = 0; a < 3; ++a) B.pts[nxt][3 * (size_t)li + a] = Xt[a];
+        } else {
+            const double *Lc = B.lines[cur] + 6 * (size_t)li;
+            if (act && ok2)
+                line_oplus(Lc, dl, Xt);
+            else
+                for (int a = 0; a < 6; ++a) Xt[a] = Lc[a];
+            if (lane == 0)
+                for (int a = 0; a < 6; ++a) B.lines[nxt][6 * (size_t)li + a] = Xt[a];
+        }
+        // errors at the trial state for the active edges (they stay even if the step is rejected)
+        for (int e = e0 + lane; e < e1; e += 32) {
+            if (elevel[e]) continue;
+            const Pose &P = tposes[ekf[e]];
+            double r[3], chi2;
+            if (!is_line) {
+                double pc[3];
+                chi2 = eval_pt(cam, P, Xt, B.pt_obs + 3 * (size_t)e, B.pt_info[e], r, pc);
+                B.pt_chi2[e] = chi2;
+                double rho0 = chi2, rho1;
+                if (robust) se3::huber(chi2, B.delta_pt, rho0, rho1);
+                chi_acc += rho0;
+            } else {
+                chi2 = eval_ln(cam, P, Xt, B.ln_obs + 4 * (size_t)e, B.ln_info[e], r);
+                B.ln_chi2[e] = chi2;
+                double rho0 = chi2, rho1;
+                if (robust) se3::huber(chi2, B.delta_ln, rho0, rho1);
+                chi_acc += rho0;
+            }
+        }
+        if (!is_line && lane == 0 && B.pt_plane) {
+            const int pe_i = B.pt_plane[li];
+            if (pe_i >= 0) {
+                const double err = eval_plane(Xt, B.pl_fn + 4 * (size_t)pe_i);
+                B.pl_err[pe_i] = err;
+                double rho0, rho1;
+                se3::huber(err * err, 1.0, rho0, rho1);
+                chi_acc += rho0;
+            }
+        }
+    }
+    chi_acc = warp_sum(chi_acc);
+    scale_acc = warp_sum(scale_acc);
+    if (lane == 0) {
+        s_red[warp][0] = chi_acc;
+        s_red[warp][1] = scale_acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double c = 0, s = 0;
+        for (int w = 0; w < kBaWarps; ++w) {
+            c += s_red[w][0];
+            s += s_red[w][1];
+        }
+        B.trial_partial[2 * blockIdx.x] = c;
+        B.trial_partial[2 * blockIdx.x + 1] = s;
+    }
+}
+
+// local reduction of the trial partials (then all-reduced over ranks in multi-GPU runs)
+__global__ void ba_trial_reduce_kernel(BaDev B) {
+    const BaState &ST = *B.state;
+    if (ST.phase == kBaDone || !ST.have_trial) return;
+    if (threadIdx.x == 0) {
+        double c = 0, s = 0;
+        for (int g = 0; g < B.num_ctas; ++g) {
+            c += B.trial_partial[2 * g];
+            s += B.trial_partial[2 * g + 1];
+        }
+        B.trial_sum[0] = c;
+        B.trial_sum[1] = s;
+    }
+}
+
+// =========================================================================================================
+// ba_decide_kernel: OptimizationAlgorithmLevenberg accept / reject + SparseOptimizer::optimize loop control
+// =========================================================================================================
+__global__ void ba_decide_kernel(BaDev B) {
+    BaState &ST = *B.state;
+    if (ST.phase == kBaDone) return;
+    if (ST.have_trial) {
+        if (threadIdx.x == 0) {
+            double temp_chi = B.trial_sum[0];
+            if (!ST.ok2) temp_chi = 1.7976931348623157e308;
+            double rho = ST.current_chi - temp_chi;
+            const double scale = ST.scale_pose + B.trial_sum[1] + 1e-3;
+            rho /= scale;
+            bool lambda_finite = true;
+            ST.tries++;
+            if (rho > 0 && isfinite(temp_chi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = fmin(alpha, 2. / 3.);
+                ST.lambda *= fmax(1. / 3., alpha);
+                ST.ni = 2;
+                ST.current_chi = temp_chi;
+                ST.cur ^= 1;  // commit the trial state
+                ST.accepted = 1;
+            } else {
+                ST.lambda *= ST.ni;
+                ST.ni *= 2;
+                ST.accepted = 0;
+                if (!isfinite(ST.lambda)) lambda_finite = false;
+            }
+            if (lambda_finite) ST.qmax++;
+            ST.rho = rho;
+            const bool again = lambda_finite && rho < 0 && ST.qmax < 10;
+            if (!again) {  // the LM iteration is over
+                ST.it++;
+                ST.iter_start = 1;
+                const bool terminate = (ST.qmax == 10 || rho == 0 || !lambda_finite);
+                if (terminate || ST.it >= ST.max_it) ST.phase = kBaDone;
+            }
+            ST.have_trial = 0;
+        }
+    }
+    __syncthreads();
+    // numeric-Jacobian support: perturbed poses of the (possibly new) current estimate
+    if (B.n_ln_edges > 0 && ST.phase != kBaDone) {
+        const int cur = ST.cur;
+        for (int i = threadIdx.x; i < B.n_kf * 12; i += blockDim.x) {
+            const int k = i / 12, d = i - k * 12;
+            double u[6] = {0, 0, 0, 0, 0, 0};
+            u[d >> 1] = (d & 1) ? -kDelta : kDelta;
+            B.pert_pose[i] = se3::oplus(B.poses[cur][k], u);
+        }
+    }
+}
+
+// =========================================================================================================
+// classification between / after the two optimize() calls (local_bundle_adjuster.cc:303-372)
+// =========================================================================================================
+__global__ void ba_classify_kernel(BaDev B, int set_levels) {
+    const BaState &ST = *B.state;
+    const int cur = ST.cur;
+    const se3::Cam cam{B.fx, B.fy, B.cx, B.cy, B.bf};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double chi_sq_2D = (double)5.99146f, chi_sq_3D = (double)7.81473f;
+    if (i < B.n_pt_edges) {
+        const float *obs = B.pt_obs + 3 * (size_t)i;
+        const bool stereo = !(obs[2] < 0);
+        double pc[3];
+        se3::map_point(B.poses[cur][B.pt_kf[i]].R, B.poses[cur][B.pt_kf[i]].t, B.pts[cur] + 3 * (size_t)B.pt_lm[i], pc);
+        const bool out = (stereo ? chi_sq_3D : chi_sq_2D) < B.pt_chi2[i] || !(0.0 < pc[2]);
+        if (set_levels) {
+            if (out) B.pt_level[i] = 1;
+        } else {
+            B.pt_outlier[i] = out ? 1 : 0;
+        }
+    } else if (i < B.n_pt_edges + B.n_ln_edges) {
+        const int e = i - B.n_pt_edges;
+        const bool out = chi_sq_2D < B.ln_chi2[e] ||
+                         !line_depth_positive(cam, B.poses[cur][B.ln_kf[e]], B.lines[cur] + 6 * (size_t)B.ln_lm[e],
+                                              B.ln_obs + 4 * (size_t)e);
+        if (set_levels) {
+            if (out) B.ln_level[e] = 1;
+        } else {
+            B.ln_outlier[e] = out ? 1 : 0;
+        }
+    }
+}
+
+__global__ void ba_init_poses_kernel(BaDev B, const double *T_in) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= B.n_kf) return;
+    const Pose P = se3::from_matrix(T_in + 16 * (size_t)k);
+    B.poses[0][k] = P;
+    B.poses[1][k] = P;
+}
+
+__global__ void ba_export_kernel(BaDev B, double *T_out, double *pts_out, double *lines_out) {
+    const int cur = B.state->cur;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.n_kf) {
+        double T[16];
+        se3::to_matrix(B.poses[cur][i], T);
+        for (int k = 0; k < 16; ++k) T_out[16 * (size_t)i + k] = T[k];
+    }
+    if (i < 3 * B.n_pts) pts_out[i] = B.pts[cur][i];
+    if (i < 6 * B.n_lines) lines_out[i] = B.lines[cur][i];
+}
+
+__global__ void ba_set_state_kernel(BaDev B, int max_it, int robust, int reset_cur) {
+    BaState &ST = *B.state;
+    ST.phase = kBaNeedInit;
+    ST.it = 0;
+    ST.max_it = max_it;
+    ST.qmax = 0;
+    ST.iter_start = 1;
+    ST.have_trial = 0;
+    ST.ok2 = 0;
+    ST.robust = robust;
+    ST.lambda = 0;
+    ST.ni = 2;
+    ST.rho = 0;
+    ST.accepted = 0;
+    if (reset_cur) {
+        ST.cur = 0;
+        ST.tries = 0;
+        ST.current_chi = 0;
+    }
+}
+
+}  // namespace
+
+size_t ba_linearize_smem(int n_free, int n_pairs) {
+    return ((sizeof(BaSmem) + 15) & ~(size_t)15) + (size_t)(n_pairs * 36 + 12 * n_free) * 8 + 64;
+}
+size_t ba_solve_smem(int n_free) {
+    const size_t n = 6 * (size_t)n_free;
+    return (n * (n + 1) / 2 + 2 * n) * 8 + 64;
+}
+
+plp_status ba_prepare_kernels(int n_free, int n_pairs) {
+    PLP_CUDA_TRY(cudaFuncSetAttribute(ba_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)ba_linearize_smem(n_free, n_pairs)));
+    PLP_CUDA_TRY(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_solve_smem(n_free)));
+    return PLP_OK;
+}
+
+// one LM try on the context stream; `between` (may be null) is called where the multi-GPU path all-reduces
+plp_status ba_launch_try(plp_ctx *ctx, const BaDev &B, BaCollective *coll) {
+    PLP_LAUNCH(ctx, ba_decide_kernel, 1, 256, 0, B);
+    PLP_LAUNCH(ctx, ba_linearize_kernel, B.num_ctas, kBaThreads, ba_linearize_smem(B.n_free, B.n_pairs), B);
+    PLP_LAUNCH(ctx, ba_reduce_kernel, div_up(B.packed_sum_len + 1, 256), 256, 0, B);
+    if (coll) PLP_TRY(coll->all_reduce(B.packed, B.packed_sum_len + B.world));
+    PLP_LAUNCH(ctx, ba_solve_kernel, 1, kSolveThreads, ba_solve_smem(B.n_free), B);
+    PLP_LAUNCH(ctx, ba_update_kernel, B.num_ctas, kBaThreads, 0, B);
+    PLP_LAUNCH(ctx, ba_trial_reduce_kernel, 1, 32, 0, B);
+    if (coll) PLP_TRY(coll->all_reduce(B.trial_sum, 2));
+    PLP_CHECK_LAUNCH();
+    return PLP_OK;
+}
+
+plp_status ba_launch_decide(plp_ctx *ctx, const BaDev &B) {
+    PLP_LAUNCH(ctx, ba_decide_kernel, 1, 256, 0, B);
+    PLP_CHECK_LAUNCH();
+    return PLP_OK;
+}
+plp_status ba_launch_set_state(plp_ctx *ctx, const BaDev &B, int max_it, int robust, int reset_cur) {
+    PLP_LAUNCH(ctx, ba_set_state_kernel, 1, 1, 0, B, max_it, robust, reset_cur);
+    PLP_CHECK_LAUNCH();
+    return PLP_OK;
+}
+plp_status ba_launch_classify(plp_ctx *ctx, const BaDev &B, int set_levels) {
+    const int n = B.n_pt_edges + B.n_ln_edges;
+    if (n > 0) PLP_LAUNCH(ctx, ba_classify_kernel, div_up(n, 256), 256, 0, B, set_levels);
+    PLP_CHECK_LAUNCH();
+    return PLP_OK;
+}
+plp_status ba_launch_init_poses(plp_ctx *ctx, const BaDev &B, const double *d_T_in) {
+    PLP_LAUNCH(ctx, ba_init_poses_kernel, div_up(B.n_kf, 64), 64, 0, B, d_T_in);
+    PLP_CHECK_LAUNCH();
+    return PLP_OK;
+}
+plp_status ba_launch_export(plp_ctx *ctx, const BaDev &B, double *d_T_out, double *d_pts_out, double *d_lines_out) {
+    int n = B.n_kf;
+    n = max(n, 3 * B.n_pts);
+    n = max(n, 6 * B.n_lines);
+    PLP_LAUNCH(ctx, ba_export_kernel, div_up(n, 256), 256, 0, B, d_T_out, d_pts_out, d_lines_out);
+    PLP_CHECK_LAUNCH();
+    return PLP_OK;
+}
+
+}  // namespace plp

@@ -1,0 +1,76 @@
+"""GPU parity of the local bundle adjuster through the C ABI vs the oracle.  Tolerance (north_star): optimised
+poses / landmarks within 1e-4 relative, identical outlier flags on >= 99.9 % of the edges."""
+import numpy as np
+import pytest
+
+import ba_data
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve_gpu(ctx, plp, prob, **kw):
+    from plpslam_b200.ba import LocalBA
+    st = prob.struct()
+    ba = LocalBA(ctx, st, (len(prob.kf_fixed), len(prob.pt_pos_w), len(prob.line_plucker), len(prob.pt_edge_kf),
+                           len(prob.line_edge_kf)), **kw)
+    out = ba.solve()
+    ba.close()
+    return out
+
+
+def _compare(g, o, prob, tol=1e-4):
+    free = prob.kf_fixed == 0
+    rel_pose = np.linalg.norm(g["kf_pose_cw"] - o.kf_pose_cw) / np.linalg.norm(o.kf_pose_cw)
+    assert rel_pose < tol, rel_pose
+    assert np.array_equal(g["kf_pose_cw"][~free], prob.kf_pose_cw[~free].reshape(-1, 4, 4)) or \
+        np.allclose(g["kf_pose_cw"][~free], prob.kf_pose_cw[~free].reshape(-1, 4, 4), atol=1e-12)
+    rel_pts = np.linalg.norm(g["pt_pos_w"] - o.pt_pos_w, axis=1) / np.linalg.norm(o.pt_pos_w, axis=1)
+    assert np.quantile(rel_pts, 0.999) < tol, rel_pts.max()
+    if len(o.line_plucker):
+        # Pluecker lines are homogeneous: compare after the reference's normalisation (|d| = 1)
+        rel_ln = np.linalg.norm(g["line_plucker"] - o.line_plucker, axis=1) / np.linalg.norm(o.line_plucker, axis=1)
+        assert np.quantile(rel_ln, 0.999) < tol, rel_ln.max()
+        mism = int((g["line_edge_outlier"] != o.line_edge_outlier).sum())
+        assert mism <= max(1, int(1e-3 * len(o.line_edge_outlier))), mism
+    mism = int((g["pt_edge_outlier"] != o.pt_edge_outlier).sum())
+    assert mism <= max(1, int(1e-3 * len(o.pt_edge_outlier))), mism
+    assert g["iters_first"] == o.iters_first and g["iters_second"] == o.iters_second
+    assert g["lm_tries"] == o.lm_tries
+    assert abs(g["final_chi2"] - o.final_chi2) <= 1e-6 * abs(o.final_chi2)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_points_only_small(ctx, orc, plp, seed):
+    prob = ba_data.make_ba_problem(seed, n_local=6, n_fixed=3, n_points=300, n_lines=0, n_plane_pts=0)
+    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob)
+
+
+@pytest.mark.parametrize("seed,stereo", [(0, False), (1, True), (2, False)])
+def test_points_lines_planes_medium(ctx, orc, plp, seed, stereo):
+    prob = ba_data.make_ba_problem(10 + seed, n_local=10, n_fixed=5, n_points=800, n_lines=150, n_plane_pts=60, stereo=stereo)
+    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob)
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_config4_full_size(ctx, orc, plp, stereo):
+    # BASELINE config 4: 20 local + 10 fixed keyframes, 4000 points + 800 lines, 200 plane-owned points
+    prob = ba_data.make_ba_problem(42, stereo=stereo)
+    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob)
+
+
+def test_shard_count_does_not_change_the_result(ctx, orc, plp):
+    prob = ba_data.make_ba_problem(7, n_local=8, n_fixed=4, n_points=600, n_lines=100, n_plane_pts=30)
+    o = ba_data.oracle_local_ba(orc, prob)
+    for ctas in (1, 3, 32, 148):
+        _compare(_solve_gpu(ctx, plp, prob, num_ctas=ctas), o, prob)
+
+
+def test_force_stop_before_start_returns_input(ctx, plp):
+    from plpslam_b200.ba import LocalBA
+    prob = ba_data.make_ba_problem(3, n_local=5, n_fixed=2, n_points=100, n_lines=0, n_plane_pts=0)
+    st = prob.struct()
+    ba = LocalBA(ctx, st, (len(prob.kf_fixed), len(prob.pt_pos_w), 0, len(prob.pt_edge_kf), 0))
+    out = ba.solve(force_stop=np.ones(1, np.uint8))  # local_bundle_adjuster.cc:276-282
+    ba.close()
+    assert np.allclose(out["kf_pose_cw"], prob.kf_pose_cw.reshape(-1, 4, 4), atol=1e-12)
+    assert np.array_equal(out["pt_pos_w"], prob.pt_pos_w) and out["iters_first"] == 0
