@@ -196,6 +196,79 @@ def cpu_port_frames(frames, aux, idxs, threads):
     return len(idxs) / dt, dt, out
 
 
+def bench_ba(pkg, ctx, stream, rank, world, steps, warmup):
+    """Second BASELINE metric: local-BA LM iterations/s on config 4 (20 local + 10 fixed KF, 4000 points + 800 lines
+    + 200 plane-owned points, ~29 k edges), landmark-sharded over `world` GPUs with one NCCL all-reduce of the packed
+    reduced camera system per LM try (strong scaling: the problem size is fixed)."""
+    import torch
+    import torch.distributed as dist
+    import ba_data
+    from plpslam_b200.ba import BaComm, LocalBA, shard_boundaries, shard_edges
+    prob = ba_data.make_ba_problem(42)
+    comm = None
+    if world > 1:
+        uid = [BaComm.unique_id(ctx) if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = BaComm(ctx, uid[0], world, rank)
+        sub = prob.shard(world, rank, shard_boundaries, shard_edges)
+    else:
+        sub = prob
+    st = sub.struct()
+    ba = LocalBA(ctx, st, (len(sub.kf_fixed), len(sub.pt_pos_w), len(sub.line_plucker), len(sub.pt_edge_kf),
+                           len(sub.line_edge_kf)), comm=comm)
+    tries_per_step = 15  # one full local BA = 5 + 10 LM iterations
+    for _ in range(max(warmup, 3)):
+        ba.bench_tries(tries_per_step)
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    done = 0
+    for _ in range(steps):
+        it, tr = ba.bench_tries(tries_per_step)
+        done += tr
+    e1.record(stream)
+    ctx.sync()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=torch.cuda.current_device())
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # full solve latency (upload excluded, result download included)
+    t0 = time.perf_counter()
+    out = ba.solve()
+    solve_ms = 1e3 * (time.perf_counter() - t0)
+    ba.close()
+    if comm:
+        comm.close()
+    edges = len(prob.pt_edge_kf) + len(prob.line_edge_kf) + len(prob.plane_edge_lm)
+    alg_bytes = edges * 32 + len(prob.pt_pos_w) * 48 + len(prob.line_plucker) * 96 + len(prob.kf_fixed) * 112
+    return {"metric": "local_ba_lm_iterations_per_sec", "value": done / (ms * 1e-3), "unit": "LM iterations/s",
+            "scaling": "strong", "lm_tries_timed": done, "ms_per_lm_iteration": ms / max(done, 1),
+            "full_solve_ms": solve_ms, "solve_iters": [out["iters_first"], out["iters_second"], out["lm_tries"]],
+            "config": {"workload": "local_bundle_adjuster 20 local + 10 fixed KF, 4000 points + 800 lines + 200 plane edges",
+                       "edges": edges, "parallelism": f"landmark-sharded over {world} GPU(s), 1 packed all-reduce per LM try"},
+            "algorithmic_bytes_per_iteration": alg_bytes,
+            "hbm_roofline_frac": (alg_bytes / (ms * 1e-3 / max(done, 1))) / 1e9 / _peaks()[0]}
+
+
+def bench_ba_cpu(n_solves=3):
+    """CPU oracle port of the same local BA (single thread)."""
+    import ba_data
+    import oracle_api
+    orc = oracle_api.Oracle()
+    prob = ba_data.make_ba_problem(42)
+    t0 = time.perf_counter()
+    tries = 0
+    for _ in range(n_solves):
+        r = ba_data.oracle_local_ba(orc, prob)
+        tries += r.lm_tries
+    dt = time.perf_counter() - t0
+    return {"value": tries / dt, "unit": "LM iterations/s", "cores": 1, "kind": "port",
+            "sample": f"{n_solves} full local-BA solves ({tries} LM tries, {dt:.1f} s)"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU implementation of the path (oracle port; the reference binary cannot be built here)."""
     if rank != 0:
@@ -243,6 +316,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ba", action="store_true", help="skip the local-BA metric")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -348,6 +422,10 @@ def main():
                 "kernel_time_shares": shares,
                 "how": "CUDA events around every launch on the launching stream over a repeat of the timed steps"}
 
+    ba_res = None
+    if not args.no_ba:
+        ba_res = bench_ba(pkg, ctx, stream, rank, world, steps=max(args.steps, 5), warmup=args.warmup)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -371,6 +449,10 @@ def main():
             line["cpu_baseline"] = {"value": fps_mt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_sample} frames of the same workload over {cores} host threads ({dt_mt:.1f} s)",
                                     "single_thread_value": fps_1}
+        if ba_res is not None:
+            if world == 1 and not args.no_cpu_baseline:
+                ba_res["cpu_baseline"] = bench_ba_cpu()
+            line["local_ba"] = ba_res
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -94,3 +94,22 @@ class LocalBA:
         if self._h is not None:
             self._lib.plp_ba_destroy(self._h)
             self._h = None
+
+
+def shard_boundaries(edges_per_landmark, world: int):
+    """Contiguous landmark blocks balanced by edge count: returns world+1 boundaries."""
+    w = np.asarray(edges_per_landmark, np.int64) + 1
+    cum = np.concatenate([[0], np.cumsum(w)])
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(cum, cum[-1] * r / world)))
+    bounds.append(len(w))
+    return [min(max(b, 0), len(w)) for b in bounds]
+
+
+def shard_edges(edge_lm, lm_begin: int, lm_end: int):
+    """Indices of the (landmark-sorted) edges owned by the landmark block [lm_begin, lm_end) and their local
+    landmark indices."""
+    edge_lm = np.asarray(edge_lm)
+    sel = np.nonzero((edge_lm >= lm_begin) & (edge_lm < lm_end))[0]
+    return sel, (edge_lm[sel] - lm_begin).astype(np.int32)

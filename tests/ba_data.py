@@ -52,6 +52,24 @@ class BAProblem:
         self.plane_edge_fn = np.ascontiguousarray(kw.get("plane_edge_fn", z(np.float64, 0, 4)), np.float64)
         self.gt = kw.get("gt")
 
+    def shard(self, world: int, rank: int, shard_boundaries, shard_edges):
+        """This rank's block of landmarks (all keyframes replicated) for landmark-sharded multi-GPU BA."""
+        n_pts, n_lines = len(self.pt_pos_w), len(self.line_plucker)
+        pb = shard_boundaries(np.bincount(self.pt_edge_lm, minlength=n_pts), world)
+        lb = shard_boundaries(np.bincount(self.line_edge_lm, minlength=n_lines) if n_lines else np.zeros(0, int), world)
+        p0, p1, l0, l1 = pb[rank], pb[rank + 1], lb[rank], lb[rank + 1]
+        pe, pe_lm = shard_edges(self.pt_edge_lm, p0, p1)
+        le, le_lm = shard_edges(self.line_edge_lm, l0, l1)
+        pl = np.nonzero((self.plane_edge_lm >= p0) & (self.plane_edge_lm < p1))[0]
+        sub = BAProblem(stereo=self.stereo, kf_pose_cw=self.kf_pose_cw, kf_fixed=self.kf_fixed,
+                        pt_pos_w=self.pt_pos_w[p0:p1], pt_edge_kf=self.pt_edge_kf[pe], pt_edge_lm=pe_lm,
+                        pt_edge_obs=self.pt_edge_obs[pe], pt_edge_inv_sigma_sq=self.pt_edge_inv_sigma_sq[pe],
+                        line_plucker=self.line_plucker[l0:l1], line_edge_kf=self.line_edge_kf[le], line_edge_lm=le_lm,
+                        line_edge_obs=self.line_edge_obs[le], line_edge_inv_sigma_sq=self.line_edge_inv_sigma_sq[le],
+                        plane_edge_lm=(self.plane_edge_lm[pl] - p0).astype(np.int32), plane_edge_fn=self.plane_edge_fn[pl])
+        sub.block = dict(pts=(p0, p1), lines=(l0, l1), pt_edges=pe, line_edges=le)
+        return sub
+
     @staticmethod
     def _p(a):
         return a.ctypes.data_as(_P) if a.size else None
