@@ -31,9 +31,6 @@ FILE_FLAGS = {
     "orb.cu": NO_FMA,
     "lines.cu": NO_FMA,
     "stereo.cu": NO_FMA,
-    # the reference differentiates line / plane edges numerically with delta = 1e-9 (g2o); the difference quotient
-    # amplifies round-off by ~1e7, so the BA kernels evaluate residuals with the oracle's IEEE mul/add sequence
-    "local_ba.cu": NO_FMA,
 }
 
 
