@@ -535,7 +535,7 @@ __global__ void ba_reduce_kernel(BaDev B) {
 }
 
 // =========================================================================================================
-// ba_solve_kernel: 6N x 6N Cholesky in shared memory (packed lower triangle)
+// ba_solve_kernel: 6N x 6N LDL^T in shared memory (packed lower triangle)
 // =========================================================================================================
 constexpr int kSolveThreads = 1024;
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
@@ -583,47 +583,42 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
     for (int i = tid; i < n; i += kSolveThreads) rhs[i] = packed[nS + i];
     if (tid == 0) s_ok = 1;
     __syncthreads();
-    // right-looking Cholesky
-    for (int j = 0; j < n; ++j) {
-        const double djj = L[tri(j, j)];
-        if (!(djj > 0.0) || !isfinite(djj)) {
-            if (tid == 0) s_ok = 0;
-            break;
+    // LDL^T, right-looking, ONE barrier per column: at step j the (unscaled) column c_i = A[i][j] and the pivot d_j
+    // are only read while the trailing triangle (k > j) is only written.  One warp per row, lanes over the columns
+    // (contiguous in the packed lower triangle).
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = kSolveThreads / 32;
+        for (int j = 0; j < n; ++j) {
+            const double dj = L[tri(j, j)];
+            if (!(dj > 0.0) || !isfinite(dj)) {  // not positive definite (uniform branch)
+                if (tid == 0) s_ok = 0;
+                break;
+            }
+            const double inv = 1.0 / dj;
+            for (int i = j + 1 + warp; i < n; i += nwarps) {
+                const double ci = L[tri(i, j)] * inv;
+                const int base = tri(i, 0);
+                for (int k = j + 1 + lane; k <= i; k += 32) L[base + k] -= ci * L[tri(k, j)];
+            }
+            __syncthreads();
         }
-        const double d = sqrt(djj);
-        __syncthreads();
-        for (int i = j + tid; i < n; i += kSolveThreads) L[tri(i, j)] = (i == j) ? d : L[tri(i, j)] / d;
-        __syncthreads();
-        // trailing update: L[i][k] -= L[i][j] * L[k][j] for j < k <= i
-        const int m = n - j - 1;
-        const int cnt = m * (m + 1) / 2;
-        for (int q = tid; q < cnt; q += kSolveThreads) {
-            // q -> (a, b) with b <= a in the m x m trailing triangle
-            int a = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
-            while ((a + 1) * (a + 2) / 2 <= q) ++a;
-            while (a * (a + 1) / 2 > q) --a;
-            const int b2 = q - a * (a + 1) / 2;
-            const int i = j + 1 + a, k = j + 1 + b2;
-            L[tri(i, k)] -= L[tri(i, j)] * L[tri(k, j)];
-        }
-        __syncthreads();
     }
     __syncthreads();
     const int ok = s_ok;
-    // substitutions by one warp (column oriented)
+    // substitutions by one warp: L z = b, y = D^-1 z, L^T x = y   (l_ij = L[i][j] / d_j)
     if (tid < 32 && ok) {
         for (int j = 0; j < n; ++j) {
-            const double xj = rhs[j] / L[tri(j, j)];
-            __syncwarp();
-            if (tid == 0) rhs[j] = xj;
-            for (int i = j + 1 + tid; i < n; i += 32) rhs[i] -= L[tri(i, j)] * xj;
+            const double zj = rhs[j];
+            const double f = zj / L[tri(j, j)];
+            for (int i = j + 1 + tid; i < n; i += 32) rhs[i] -= L[tri(i, j)] * f;
             __syncwarp();
         }
+        for (int j = tid; j < n; j += 32) rhs[j] /= L[tri(j, j)];
+        __syncwarp();
         for (int j = n - 1; j >= 0; --j) {
-            const double xj = rhs[j] / L[tri(j, j)];
-            __syncwarp();
+            const double xj = rhs[j];
             if (tid == 0) x[j] = xj;
-            for (int i = tid; i < j; i += 32) rhs[i] -= L[tri(j, i)] * xj;
+            for (int i = tid; i < j; i += 32) rhs[i] -= (L[tri(j, i)] / L[tri(i, i)]) * xj;
             __syncwarp();
         }
     }

@@ -217,6 +217,7 @@ struct PointSmem {
     int *col_start;  // num_cols + 2
     int *hist;       // kHistLen
     uint8_t *bin_valid;
+    uint8_t *colchg;  // per grid column: did an owner change there in the last round?
     int *flags;  // [0] changed, [1] num accepted, [2] num invalid, [3] num in grid
 };
 
@@ -245,11 +246,12 @@ __device__ __forceinline__ PointSmem carve_point_smem(uint8_t *base, int cap, in
     s.flags = reinterpret_cast<int *>(base);
     base += 4 * 4;
     s.bin_valid = base;
+    s.colchg = base + 32;
     return s;
 }
 
 static size_t point_smem_bytes(int cap, int num_cols) {
-    return (size_t)cap * (32 + 7 * 4) + (size_t)(num_cols + 2) * 4 + kHistLen * 4 + 16 + 32;
+    return (size_t)cap * (32 + 7 * 4) + (size_t)(num_cols + 2) * 4 + kHistLen * 4 + 16 + 32 + (size_t)(num_cols + 16);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         S.y[p] = J.y[i];
         S.xr[p] = J.x_right ? J.x_right[i] : -1.0f;
         const int cl = J.claimed ? (J.claimed[i] != 0) : 0;
-        S.meta[p] = (J.octave[i] & 0xff) | (cy << 8) | (cl << 16);
+        S.meta[p] = (J.octave[i] & 0xff) | (cy << 8) | (cl << 16) | ((k / grid.num_rows) << 17);
         uint4 d0, d1;
         load_desc(J.desc + 32 * (size_t)i, d0, d1);
         S.desc[2 * p] = d0;
@@ -340,6 +342,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                 // data/common.cc:249-272
                 const int min_cx = max(0, cv_floor((double)(ref_x - grid.min_x - r) * grid.inv_cell_width));
                 const int max_cx = min(grid.num_cols - 1, cv_ceil((double)(ref_x - grid.min_x + r) * grid.inv_cell_width));
+                if (round > 0) {
+                    // a query's result depends only on the owners inside its column span: if none of them changed
+                    // in the previous round the previous choice stands (it only re-issues its claim)
+                    bool dirty = false;
+                    for (int c = min_cx; c <= max_cx; ++c) dirty = dirty || S.colchg[c];
+                    if (!dirty) {
+                        choice = J.choice[q];
+                        if (choice >= 0) atomicMin(&owner_next[choice], q);
+                        continue;
+                    }
+                }
                 const int min_cy = max(0, cv_floor((double)(ref_y - grid.min_y - r) * grid.inv_cell_height));
                 const int max_cy = min(grid.num_rows - 1, cv_ceil((double)(ref_y - grid.min_y + r) * grid.inv_cell_height));
                 if (min_cx < grid.num_cols && max_cx >= 0 && min_cy < grid.num_rows && max_cy >= 0) {
@@ -391,8 +404,13 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (choice >= 0) atomicMin(&owner_next[choice], q);
         }
         __syncthreads();
+        for (int c = tid; c < grid.num_cols; c += kThreads) S.colchg[c] = 0;
+        __syncthreads();
         for (int p = tid; p < n_in; p += kThreads)
-            if (owner_next[p] != owner_prev[p]) S.flags[0] = 1;
+            if (owner_next[p] != owner_prev[p]) {
+                S.flags[0] = 1;
+                S.colchg[(S.meta[p] >> 17) & 0x3fff] = 1;
+            }
         __syncthreads();
         const int changed = S.flags[0];
         __syncthreads();
@@ -663,7 +681,7 @@ plp_status launch_point_match(plp_ctx *ctx, const PointMatchJob *d_jobs, int num
         set_error("window matcher: %d keypoints exceed the per-frame capacity %d", max_n, kMatchMaxPoints);
         return PLP_ERR_CAPACITY;
     }
-    if (grid.num_rows > 255 || grid.num_cols < 1 || grid.num_rows < 1) {
+    if (grid.num_rows > 255 || grid.num_cols < 1 || grid.num_cols > 16383 || grid.num_rows < 1) {
         set_error("window matcher: unsupported grid %d x %d", grid.num_cols, grid.num_rows);
         return PLP_ERR_INVALID;
     }

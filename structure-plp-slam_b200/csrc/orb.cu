@@ -33,6 +33,7 @@ constexpr int kTileRows = 70;
 struct LevelInfo {
     int w, h, pitch;
     size_t offset;        // byte offset of the level inside one frame's pyramid block (levels >= 1)
+    size_t blur_offset;   // byte offset of the level inside one frame's blurred-pyramid block (all levels)
     int cells_x, cells_y; // number of cell columns/rows visited (orb_extractor.cc:356-357)
     int cell_base;        // index of this level's first cell in the per-frame cell list
     int num_cells;
@@ -46,6 +47,10 @@ struct LevelInfo {
 struct CellDesc {
     short level, i, j, pad;
     short min_x, min_y, max_x, max_y;
+};
+
+struct BlurTile {  // one 64 x 32 output tile of the Gaussian-blurred pyramid
+    short level, x0, y0, pad;
 };
 
 struct LevelKp {  // quadtree output, level coordinates (border already added)
@@ -69,6 +74,10 @@ struct OrbDev {
     // device work areas
     uint8_t *pyr;  // batch x pyr_frame_bytes (levels >= 1)
     size_t pyr_frame_bytes;
+    uint8_t *blur;  // batch x blur_frame_bytes: GaussianBlur(7x7, sigma 2) of every level (orb_extractor.cc:148-149)
+    size_t blur_frame_bytes;
+    const BlurTile *blur_tiles;
+    int num_blur_tiles;
     const CellDesc *cells;
     uint32_t *cell_buf;   // batch x num_cells x kCellCap packed (x:11 | y:10 | score:8)
     int *cell_cnt;        // batch x num_cells
@@ -903,12 +912,52 @@ __device__ __forceinline__ float util_sin(float v) {
     return util_cos(PI_2 - v);
 }
 
+// cv::GaussianBlur(level, 7x7, sigma 2, BORDER_REFLECT_101) of every pyramid level (orb_extractor.cc:148-149) in
+// OpenCV's fixed-point form: Q8 kernel [18 34 48 56 48 34 18], exact integer passes, (v + 32768) >> 16.
+// One CTA per 64 x 32 output tile: 70 x 38 source tile -> smem, horizontal pass (u16), vertical pass, 32-bit stores.
+constexpr int kBtW = 64, kBtH = 32;
+__global__ void __launch_bounds__(256) blur_tiles_kernel(OrbDev P) {
+    __shared__ __align__(16) uint8_t s_src[(kBtH + 6) * 72];
+    __shared__ __align__(16) unsigned short s_h[(kBtH + 6) * kBtW];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const BlurTile t = P.blur_tiles[blockIdx.x];
+    const int l = t.level, W = P.lv[l].w, H = P.lv[l].h;
+    const uint8_t *img = level_ptr(P, b, l);
+    const int pitch = level_pitch(P, l);
+    for (int i = tid; i < (kBtH + 6) * 70; i += 256) {
+        const int py = i / 70, px = i - py * 70;
+        // rows / columns past the image edge + 3 only feed outputs that are never stored: clamp before reflecting
+        const int gy = reflect101(min(t.y0 - 3 + py, H + 2), H), gx = reflect101(min(t.x0 - 3 + px, W + 2), W);
+        s_src[py * 72 + px] = img[(size_t)gy * pitch + gx];
+    }
+    __syncthreads();
+    for (int i = tid; i < (kBtH + 6) * kBtW; i += 256) {
+        const int py = i / kBtW, px = i - py * kBtW;
+        const uint8_t *s = s_src + py * 72 + px;
+        s_h[i] = (unsigned short)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+    }
+    __syncthreads();
+    uint8_t *dst = P.blur + (size_t)b * P.blur_frame_bytes + P.lv[l].blur_offset;
+    const int dpitch = P.lv[l].pitch;
+    for (int i = tid; i < kBtH * kBtW / 4; i += 256) {
+        const int py = i / (kBtW / 4), px = (i - py * (kBtW / 4)) * 4;
+        if (t.y0 + py >= H || t.x0 + px >= W) continue;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned short *h = s_h + py * kBtW + px + k;
+            const unsigned acc = 18u * (h[0] + h[6 * kBtW]) + 34u * (h[kBtW] + h[5 * kBtW]) + 48u * (h[2 * kBtW] + h[4 * kBtW]) +
+                                 56u * h[3 * kBtW];
+            packed |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        // pitch is a multiple of 64: aligned 4-byte store; bytes past the image width are padding
+        *reinterpret_cast<uint32_t *>(dst + (size_t)(t.y0 + py) * dpitch + t.x0 + px) = packed;
+    }
+}
+
 __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp_keypoint *__restrict__ kp_out,
                                                                     uint8_t *__restrict__ desc_out,
                                                                     int32_t *__restrict__ n_out) {
-    __shared__ __align__(16) uint8_t s_src[kDescWarps][kSrcDim * kSrcPitch];
-    __shared__ __align__(16) unsigned short s_h[kDescWarps][kSrcDim * kBlurPitch];
-    __shared__ __align__(16) uint8_t s_blur[kDescWarps][kBlurDim * kBlurPitch];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * kDescWarps + warp;
     const int *lvl_cnt = P.lvl_cnt + (size_t)b * P.num_levels;
@@ -949,36 +998,14 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- 45x45 source patch (reflect-101 at the image border), separable Q8 Gaussian 7x7 sigma 2
-    uint8_t *src = s_src[warp];
-    unsigned short *hbuf = s_h[warp];
-    uint8_t *blur = s_blur[warp];
-    for (int i = lane; i < kSrcDim * kSrcDim; i += 32) {
-        const int py = i / kSrcDim, px = i - py * kSrcDim;
-        const int gy = reflect101(cy - 22 + py, H), gx = reflect101(cx - 22 + px, W);
-        src[py * kSrcPitch + px] = img[(size_t)gy * pitch + gx];
-    }
-    __syncwarp();
-    for (int i = lane; i < kSrcDim * kBlurDim; i += 32) {
-        const int py = i / kBlurDim, px = i - py * kBlurDim;
-        const uint8_t *s = src + py * kSrcPitch + px;
-        const int acc = 18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3];
-        hbuf[py * kBlurPitch + px] = (unsigned short)acc;
-    }
-    __syncwarp();
-    for (int i = lane; i < kBlurDim * kBlurDim; i += 32) {
-        const int py = i / kBlurDim, px = i - py * kBlurDim;
-        const unsigned short *hcol = hbuf + py * kBlurPitch + px;
-        const unsigned acc = 18u * (hcol[0] + hcol[6 * kBlurPitch]) + 34u * (hcol[kBlurPitch] + hcol[5 * kBlurPitch]) +
-                             48u * (hcol[2 * kBlurPitch] + hcol[4 * kBlurPitch]) + 56u * hcol[3 * kBlurPitch];
-        blur[py * kBlurPitch + px] = (uint8_t)((acc + 32768u) >> 16);
-    }
-    __syncwarp();
-
-    // ---- steered BRIEF (orb_extractor.cc:747-807): lane i produces descriptor byte i
+    // ---- steered BRIEF (orb_extractor.cc:747-807) on the Gaussian-blurred level (blur_tiles_kernel): lane i
+    //      produces descriptor byte i; the 16 byte gathers of a lane fall inside a 37 x 37 window (L1-resident)
     const float ang_rad = (float)((double)angle * 3.14159265358979323846 / 180.0);
     const float ca = util_cos(ang_rad), sa = util_sin(ang_rad);
-    const uint8_t *center = blur + 19 * kBlurPitch + 19;
+    const int bpitch = P.lv[l].pitch;
+    const uint8_t *center = P.blur + (size_t)b * P.blur_frame_bytes + P.lv[l].blur_offset + (size_t)cy * bpitch + cx;
+    (void)W;
+    (void)H;
     int val = 0;
 #pragma unroll
     for (int bit = 0; bit < 8; ++bit) {
@@ -986,7 +1013,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
         const float x1 = (float)kBriefX1[k], y1 = (float)kBriefY1[k], x2 = (float)kBriefX2[k], y2 = (float)kBriefY2[k];
         const int r1 = __float2int_rn(x1 * sa + y1 * ca), c1 = __float2int_rn(x1 * ca - y1 * sa);
         const int r2 = __float2int_rn(x2 * sa + y2 * ca), c2 = __float2int_rn(x2 * ca - y2 * sa);
-        val |= (center[r1 * kBlurPitch + c1] < center[r2 * kBlurPitch + c2]) << bit;
+        val |= (__ldg(center + r1 * bpitch + c1) < __ldg(center + r2 * bpitch + c2)) << bit;
     }
     desc_out[((size_t)b * P.out_cap + out_pos) * 32 + lane] = (uint8_t)val;
     if (lane == 0) {
@@ -1024,6 +1051,9 @@ struct plp_orb {
     short4 *d_ytab[kMaxLevels] = {nullptr};
     CellDesc *d_cells = nullptr;
     uint8_t *d_pyr = nullptr;
+    uint8_t *d_blur = nullptr;
+    BlurTile *d_blur_tiles = nullptr;
+    std::vector<BlurTile> blur_tiles;
     uint8_t *d_img = nullptr;  // staging for host-pointer extraction (max_batch frames)
     uint8_t *d_mask = nullptr;
     uint32_t *d_cell_buf = nullptr;
@@ -1091,7 +1121,7 @@ void plp_orb_destroy(plp_orb *o) {
         if (o->d_xtab[l]) cudaFree(o->d_xtab[l]);
         if (o->d_ytab[l]) cudaFree(o->d_ytab[l]);
     }
-    void *ptrs[] = {o->d_cells, o->d_pyr, o->d_img, o->d_mask, o->d_cell_buf, o->d_cell_cnt, o->d_lvl_kp,
+    void *ptrs[] = {o->d_blur, o->d_blur_tiles, o->d_cells, o->d_pyr, o->d_img, o->d_mask, o->d_cell_buf, o->d_cell_cnt, o->d_lvl_kp,
                     o->d_lvl_cnt, o->d_qt_scratch, o->d_status, o->d_kp, o->d_desc, o->d_n};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1166,7 +1196,7 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
         }
     }
     // ---- level geometry, cells (orb_extractor.cc:344-392)
-    size_t pyr_bytes = 0;
+    size_t pyr_bytes = 0, blur_bytes = 0;
     int slot_base = 0, cell_base = 0;
     plp_status st = PLP_OK;
     for (unsigned l = 0; l < L; ++l) {
@@ -1183,6 +1213,11 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
         V.offset = pyr_bytes;
         if (l > 0) pyr_bytes += (size_t)V.pitch * V.h + 256;
         pyr_bytes = (pyr_bytes + 255) & ~(size_t)255;
+        V.blur_offset = blur_bytes;
+        blur_bytes += (size_t)V.pitch * V.h + 256;
+        blur_bytes = (blur_bytes + 255) & ~(size_t)255;
+        for (int y0 = 0; y0 < V.h; y0 += kBtH)
+            for (int x0 = 0; x0 < V.w; x0 += kBtW) o->blur_tiles.push_back(BlurTile{(short)l, (short)x0, (short)y0, 0});
         V.budget = (int)o->num_keypts_per_level[l];
         V.scale_factor = o->scale_factors[l];
         V.size = (float)(unsigned)(31 * o->scale_factors[l]);
@@ -1244,6 +1279,8 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
     D.total_slots = slot_base;
     D.out_cap = slot_base;
     D.pyr_frame_bytes = pyr_bytes ? pyr_bytes : 256;
+    D.blur_frame_bytes = blur_bytes ? blur_bytes : 256;
+    D.num_blur_tiles = (int)o->blur_tiles.size();
     const size_t B = (size_t)max_batch;
     // ---- device allocations
 #define ORB_ALLOC(ptr, bytes)                                              \
@@ -1267,6 +1304,10 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
     if (!o->cells.empty())
         cudaMemcpy(o->d_cells, o->cells.data(), o->cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice);
     ORB_ALLOC(o->d_pyr, B * D.pyr_frame_bytes);
+    ORB_ALLOC(o->d_blur, B * D.blur_frame_bytes);
+    ORB_ALLOC(o->d_blur_tiles, o->blur_tiles.size() * sizeof(BlurTile));
+    if (!o->blur_tiles.empty())
+        cudaMemcpy(o->d_blur_tiles, o->blur_tiles.data(), o->blur_tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice);
     ORB_ALLOC(o->d_img, B * (size_t)rows * cols);
     ORB_ALLOC(o->d_mask, (size_t)rows * cols);
     ORB_ALLOC(o->d_cell_buf, B * (size_t)D.num_cells * kCellCap * sizeof(uint32_t));
@@ -1281,6 +1322,8 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
     ORB_ALLOC(o->d_n, B * sizeof(int32_t));
 #undef ORB_ALLOC
     D.pyr = o->d_pyr;
+    D.blur = o->d_blur;
+    D.blur_tiles = o->d_blur_tiles;
     D.cells = o->d_cells;
     D.cell_buf = o->d_cell_buf;
     D.cell_cnt = o->d_cell_cnt;
@@ -1336,6 +1379,10 @@ static plp_status orb_run(plp_orb *o, const uint8_t *d_imgs, int batch, size_t s
     if (D.num_cells > 0) {
         dim3 grid(D.num_cells, batch);
         PLP_LAUNCH(ctx, fast_cells_kernel, grid, 256, 0, D);
+    }
+    if (D.num_blur_tiles > 0) {
+        dim3 grid(D.num_blur_tiles, batch);
+        PLP_LAUNCH(ctx, blur_tiles_kernel, grid, 256, 0, D);
     }
     {
         dim3 grid(D.num_levels, batch);
