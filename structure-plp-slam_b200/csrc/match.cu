@@ -214,14 +214,14 @@ struct PointSmem {
     int *meta;      // octave (bits 0-7, signed) | cell_y (8-15) | claimed (16)
     int *orig;      // original index of the keypoint at each sorted position
     int *owner_a, *owner_b;
-    int *col_start;  // num_cols + 2
+    int *col_start;  // cell start table: num_cols * num_rows + 2
     int *hist;       // kHistLen
     uint8_t *bin_valid;
     uint8_t *colchg;  // per grid column: did an owner change there in the last round?
     int *flags;  // [0] changed, [1] num accepted, [2] num invalid, [3] num in grid
 };
 
-__device__ __forceinline__ PointSmem carve_point_smem(uint8_t *base, int cap, int num_cols) {
+__device__ __forceinline__ PointSmem carve_point_smem(uint8_t *base, int cap, int num_cols, int num_rows) {
     PointSmem s;
     s.desc = reinterpret_cast<uint4 *>(base);
     base += (size_t)cap * 32;
@@ -240,7 +240,7 @@ __device__ __forceinline__ PointSmem carve_point_smem(uint8_t *base, int cap, in
     s.owner_b = reinterpret_cast<int *>(base);
     base += (size_t)cap * 4;
     s.col_start = reinterpret_cast<int *>(base);
-    base += (size_t)(num_cols + 2) * 4;
+    base += (size_t)(num_cols * num_rows + 2) * 4;
     s.hist = reinterpret_cast<int *>(base);
     base += kHistLen * 4;
     s.flags = reinterpret_cast<int *>(base);
@@ -250,8 +250,8 @@ __device__ __forceinline__ PointSmem carve_point_smem(uint8_t *base, int cap, in
     return s;
 }
 
-static size_t point_smem_bytes(int cap, int num_cols) {
-    return (size_t)cap * (32 + 7 * 4) + (size_t)(num_cols + 2) * 4 + kHistLen * 4 + 16 + 32 + (size_t)(num_cols + 16);
+static size_t point_smem_bytes(int cap, int num_cols, int num_rows) {
+    return (size_t)cap * (32 + 7 * 4) + (size_t)(num_cols * num_rows + 2) * 4 + kHistLen * 4 + 16 + 32 + (size_t)(num_cols + 16);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const PointMatchJob &J = jobs[blockIdx.x];
     if (J.m < 0) return;  // job disabled (e.g. the widened-margin retry is not needed for this frame)
-    PointSmem S = carve_point_smem(smem_raw, cap, grid.num_cols);
+    PointSmem S = carve_point_smem(smem_raw, cap, grid.num_cols, grid.num_rows);
     const int tid = threadIdx.x;
     if (J.n > cap) {  // more keypoints than the shared-memory tables hold: report "no matches" loudly (0xffffffff)
         if (J.matched_out)
@@ -315,14 +315,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         S.desc[2 * p] = d0;
         S.desc[2 * p + 1] = d1;
     }
-    // column start table: col_start[c] = number of in-grid keypoints with cell_x < c
-    for (int c = tid; c <= grid.num_cols + 1; c += kThreads) {
-        int cnt = 0;
-        const int lim = c * grid.num_rows;
-        for (int j = 0; j < n; ++j) cnt += (key[j] < lim && key[j] < cells);
-        S.col_start[c] = cnt;
-    }
     __syncthreads();  // key[] (owner_a) no longer needed after this point
+    // cell start table over the sorted keypoints: cell_start[k] = first sorted position whose cell key >= k
+    // (k = cell_x * num_rows + cell_y), so the cells [min_cy, max_cy] of one grid column are ONE contiguous span
+    for (int p = tid; p <= n_in; p += kThreads) {
+        const int kp = p < n_in ? ((S.meta[p] >> 17) & 0x3fff) * grid.num_rows + ((S.meta[p] >> 8) & 0xff) : cells;
+        const int kprev = p > 0 ? ((S.meta[p - 1] >> 17) & 0x3fff) * grid.num_rows + ((S.meta[p - 1] >> 8) & 0xff) : -1;
+        for (int k = kprev + 1; k <= kp; ++k) S.col_start[k] = p;
+    }
+    __syncthreads();
 
     int *owner_prev = S.owner_a, *owner_next = S.owner_b;
     for (int p = tid; p < n_in; p += kThreads) {
@@ -332,8 +333,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     __syncthreads();
 
     // ---- 4. fixed-point iteration of the sequential greedy assignment
+    // One WARP per query: lanes stride the candidates of the window's cells (per grid column the cells
+    // [min_cy, max_cy] are one contiguous span of the sorted arrays), each lane keeps its two smallest keys
+    // key = (distance << 40 | sorted position << 8 | octave), i.e. top-2 by (distance, traversal order) -- exactly
+    // the reference's strict-'<' scan -- and the 32 partial top-2 lists are merged with shuffles.
+    const int lane = tid & 31, warp = tid >> 5, nwarps = kThreads / 32;
     for (int round = 0; round <= m; ++round) {
-        for (int q = tid; q < m; q += kThreads) {
+        for (int q = warp; q < m; q += nwarps) {
             int choice = -1;
             const bool valid = J.qvalid ? (J.qvalid[q] != 0) : true;
             if (valid) {
@@ -346,10 +352,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                     // a query's result depends only on the owners inside its column span: if none of them changed
                     // in the previous round the previous choice stands (it only re-issues its claim)
                     bool dirty = false;
-                    for (int c = min_cx; c <= max_cx; ++c) dirty = dirty || S.colchg[c];
-                    if (!dirty) {
-                        choice = J.choice[q];
-                        if (choice >= 0) atomicMin(&owner_next[choice], q);
+                    for (int c = min_cx + lane; c <= max_cx; c += 32) dirty = dirty || S.colchg[c];
+                    if (!__any_sync(0xffffffffu, dirty)) {
+                        if (lane == 0) {
+                            choice = J.choice[q];
+                            if (choice >= 0) atomicMin(&owner_next[choice], q);
+                        }
                         continue;
                     }
                 }
@@ -360,48 +368,65 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const float qxr = J.qxr ? J.qxr[q] : 0.0f;
                     uint4 q0, q1;
                     load_desc(J.qdesc + 32 * (size_t)q, q0, q1);
-                    unsigned best = PLP_MAX_HAMMING_DIST, second = PLP_MAX_HAMMING_DIST;
-                    int best_lvl = -1, second_lvl = -1, best_p = -1;
-                    const int p_end = S.col_start[max_cx + 1];
-                    for (int p = S.col_start[min_cx]; p < p_end; ++p) {
-                        const int meta = S.meta[p];
-                        const int cy = (meta >> 8) & 0xff;
-                        if (cy < min_cy || cy > max_cy) continue;
-                        const int oct = (int)(signed char)(meta & 0xff);
-                        if (check_level) {
-                            if (oct < min_level) continue;
-                            if (0 <= max_level && max_level < oct) continue;
-                        }
-                        const float dx = S.x[p] - ref_x, dy = S.y[p] - ref_y;
-                        if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
-                        if ((meta >> 16) & 1) continue;       // already has a landmark with observations
-                        if (owner_prev[p] < q) continue;      // claimed by an earlier query
-                        const float xr = S.xr[p];
-                        if (0 < xr) {                         // projection.cc:76-83 / 310-317
-                            const float err = fabsf(qxr - xr);
-                            if (r < err) continue;
-                        }
-                        const unsigned d = (unsigned)hamming256(q0, q1, S.desc[2 * p], S.desc[2 * p + 1]);
-                        if (d < best) {
-                            second = best;
-                            best = d;
-                            second_lvl = best_lvl;
-                            best_lvl = oct;
-                            best_p = p;
-                        } else if (d < second) {
-                            second_lvl = oct;
-                            second = d;
+                    unsigned long long k1 = ~0ull, k2 = ~0ull;
+                    for (int c = min_cx; c <= max_cx; ++c) {
+                        const int p_begin = S.col_start[c * grid.num_rows + min_cy];
+                        const int p_end = S.col_start[c * grid.num_rows + max_cy + 1];
+                        for (int p = p_begin + lane; p < p_end; p += 32) {
+                            const int meta = S.meta[p];
+                            const int oct = (int)(signed char)(meta & 0xff);
+                            if (check_level) {
+                                if (oct < min_level) continue;
+                                if (0 <= max_level && max_level < oct) continue;
+                            }
+                            const float dx = S.x[p] - ref_x, dy = S.y[p] - ref_y;
+                            if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
+                            if ((meta >> 16) & 1) continue;   // already has a landmark with observations
+                            if (owner_prev[p] < q) continue;  // claimed by an earlier query
+                            const float xr = S.xr[p];
+                            if (0 < xr) {  // projection.cc:76-83 / 310-317
+                                const float err = fabsf(qxr - xr);
+                                if (r < err) continue;
+                            }
+                            const unsigned d = (unsigned)hamming256(q0, q1, S.desc[2 * p], S.desc[2 * p + 1]);
+                            if (d >= PLP_MAX_HAMMING_DIST) continue;  // can never replace the initial best / second
+                            const unsigned long long key =
+                                ((unsigned long long)d << 40) | ((unsigned long long)(unsigned)p << 8) | (unsigned)(oct & 0xff);
+                            if (key < k1) {
+                                k2 = k1;
+                                k1 = key;
+                            } else if (key < k2) {
+                                k2 = key;
+                            }
                         }
                     }
-                    if (best_p >= 0 && best <= PLP_HAMMING_DIST_THR_HIGH) {
-                        bool ok = true;
-                        if (ratio_test && best_lvl == second_lvl && (float)best > lowe_ratio * (float)second) ok = false;
-                        if (ok) choice = best_p;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+                        const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+                        const unsigned long long lo = k1 < o1 ? k1 : o1, hi = k1 < o1 ? o1 : k1;
+                        const unsigned long long s2 = k2 < o2 ? k2 : o2;
+                        k1 = lo;
+                        k2 = hi < s2 ? hi : s2;
+                    }
+                    if (k1 != ~0ull) {
+                        const unsigned best = (unsigned)(k1 >> 40);
+                        const int best_p = (int)((k1 >> 8) & 0xffffffffull);
+                        const int best_lvl = (int)(signed char)(k1 & 0xff);
+                        const unsigned second = k2 != ~0ull ? (unsigned)(k2 >> 40) : (unsigned)PLP_MAX_HAMMING_DIST;
+                        const int second_lvl = k2 != ~0ull ? (int)(signed char)(k2 & 0xff) : -1;
+                        if (best <= PLP_HAMMING_DIST_THR_HIGH) {
+                            bool ok = true;
+                            if (ratio_test && best_lvl == second_lvl && (float)best > lowe_ratio * (float)second) ok = false;
+                            if (ok) choice = best_p;
+                        }
                     }
                 }
             }
-            J.choice[q] = choice;
-            if (choice >= 0) atomicMin(&owner_next[choice], q);
+            if (lane == 0) {
+                J.choice[q] = choice;
+                if (choice >= 0) atomicMin(&owner_next[choice], q);
+            }
         }
         __syncthreads();
         for (int c = tid; c < grid.num_cols; c += kThreads) S.colchg[c] = 0;
@@ -686,7 +711,7 @@ plp_status launch_point_match(plp_ctx *ctx, const PointMatchJob *d_jobs, int num
         return PLP_ERR_INVALID;
     }
     const int cap = max_n < 64 ? 64 : ((max_n + 63) / 64) * 64;
-    const size_t smem = point_smem_bytes(cap, grid.num_cols);
+    const size_t smem = point_smem_bytes(cap, grid.num_cols, grid.num_rows);
     PLP_CUDA_TRY(cudaFuncSetAttribute(point_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PLP_LAUNCH(ctx, point_match_kernel, num_jobs, kThreads, smem, d_jobs, grid, cap, ratio_test, lowe_ratio,
                check_orientation);

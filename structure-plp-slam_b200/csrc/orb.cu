@@ -237,38 +237,39 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(OrbDev P) {
     for (int idx = tid; idx < kTileRows * kTilePitch / 4; idx += 256) reinterpret_cast<uint32_t *>(score)[idx] = 0;
     __syncthreads();
     const int tw = w - 6, th = h - 6, total = tw * th;
-    for (int p = tid; p < total; p += 256) {
-        const int y = 3 + p / tw, x = 3 + p % tw;
-        const int m = fast_m(tile + y * kTilePitch + x, P.min_thr);
-        score[y * kTilePitch + x] = (m > P.min_thr) ? (uint8_t)(m - 1) : (uint8_t)0;
-    }
-    __syncthreads();
-    // NMS at both thresholds; each thread owns a contiguous row-major run so the output stays ordered
+    // each thread owns a contiguous row-major run of tested pixels so that the output stays ordered
     const int per = (total + 255) / 256;  // <= 16
     const int p0 = tid * per, p1 = min(total, p0 + per);
-    unsigned flagsA = 0, flagsB = 0;
-    const int ini = P.ini_thr;
-    for (int p = p0; p < p1; ++p) {
-        const int y = 3 + p / tw, x = 3 + p % tw;
-        const uint8_t *s = score + y * kTilePitch + x;
-        const int sc = s[0];
-        if (sc == 0) continue;
-        bool keepB = true, keepA = (sc >= ini);
+    unsigned flags = 0;
+    // cv::FAST(cell, ini_thr) first; only if the cell yields nothing, again with min_thr (orb_extractor.cc:404-412).
+    // The score of a corner (m - 1) does not depend on the threshold, non-corners score 0 in the NMS buffer.
+    for (int pass = 0; pass < 2; ++pass) {
+        const int thr = pass == 0 ? P.ini_thr : P.min_thr;
+        for (int p = tid; p < total; p += 256) {
+            const int y = 3 + p / tw, x = 3 + p % tw;
+            const int m = fast_m(tile + y * kTilePitch + x, thr);
+            score[y * kTilePitch + x] = (m > thr) ? (uint8_t)(m - 1) : (uint8_t)0;
+        }
+        __syncthreads();
+        flags = 0;
+        for (int p = p0; p < p1; ++p) {
+            const int y = 3 + p / tw, x = 3 + p % tw;
+            const uint8_t *s = score + y * kTilePitch + x;
+            const int sc = s[0];
+            if (sc == 0) continue;
+            bool keep = true;
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
+            for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (dx == 0 && dy == 0) continue;
-                const int nb = s[dy * kTilePitch + dx];
-                keepB = keepB && (sc > nb);
-                keepA = keepA && (sc > (nb >= ini ? nb : 0));
-            }
-        flagsA |= (unsigned)keepA << (p - p0);
-        flagsB |= (unsigned)keepB << (p - p0);
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (dx == 0 && dy == 0) continue;
+                    keep = keep && (sc > (int)s[dy * kTilePitch + dx]);
+                }
+            flags |= (unsigned)keep << (p - p0);
+        }
+        const int any = __syncthreads_or(flags != 0);  // also orders the score-map reads before the next pass
+        if (any || P.min_thr == P.ini_thr) break;
     }
-    // does the initial threshold yield anything? (orb_extractor.cc:404-412)
-    const int anyA = __syncthreads_or(flagsA != 0);
-    unsigned flags = anyA ? flagsA : flagsB;
     if (P.mask && flags) {  // orb_extractor.cc:429
         for (int p = p0; p < p1; ++p) {
             if (!((flags >> (p - p0)) & 1)) continue;
