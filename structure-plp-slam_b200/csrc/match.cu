@@ -332,83 +332,147 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     __syncthreads();
 
-    // ---- 4. fixed-point iteration of the sequential greedy assignment
+    // ---- 4. the sequential greedy assignment, in parallel
     // One WARP per query: lanes stride the candidates of the window's cells (per grid column the cells
     // [min_cy, max_cy] are one contiguous span of the sorted arrays), each lane keeps its two smallest keys
     // key = (distance << 40 | sorted position << 8 | octave), i.e. top-2 by (distance, traversal order) -- exactly
     // the reference's strict-'<' scan -- and the 32 partial top-2 lists are merged with shuffles.
     const int lane = tid & 31, warp = tid >> 5, nwarps = kThreads / 32;
-    for (int round = 0; round <= m; ++round) {
-        for (int q = warp; q < m; q += nwarps) {
-            int choice = -1;
-            const bool valid = J.qvalid ? (J.qvalid[q] != 0) : true;
-            if (valid) {
-                const float ref_x = J.qx[q], ref_y = J.qy[q], r = J.qradius[q];
-                const int min_level = J.qmin[q], max_level = J.qmax[q];
-                // data/common.cc:249-272
-                const int min_cx = max(0, cv_floor((double)(ref_x - grid.min_x - r) * grid.inv_cell_width));
-                const int max_cx = min(grid.num_cols - 1, cv_ceil((double)(ref_x - grid.min_x + r) * grid.inv_cell_width));
-                if (round > 0) {
-                    // a query's result depends only on the owners inside its column span: if none of them changed
-                    // in the previous round the previous choice stands (it only re-issues its claim)
-                    bool dirty = false;
-                    for (int c = min_cx + lane; c <= max_cx; c += 32) dirty = dirty || S.colchg[c];
-                    if (!__any_sync(0xffffffffu, dirty)) {
-                        if (lane == 0) {
-                            choice = J.choice[q];
-                            if (choice >= 0) atomicMin(&owner_next[choice], q);
-                        }
-                        continue;
+    // scan(q, owner, has_floor, floor): top-2 keys among q's window candidates that are not pre-claimed, not owned
+    // by a smaller query (when `owner` is given) and strictly after `floor` in (distance, order) (when has_floor)
+    auto scan = [&](int q, const int *owner, bool has_floor, unsigned long long floor, unsigned long long &k1,
+                    unsigned long long &k2) {
+        k1 = ~0ull;
+        k2 = ~0ull;
+        const float ref_x = J.qx[q], ref_y = J.qy[q], r = J.qradius[q];
+        const int min_level = J.qmin[q], max_level = J.qmax[q];
+        // data/common.cc:249-272
+        const int min_cx = max(0, cv_floor((double)(ref_x - grid.min_x - r) * grid.inv_cell_width));
+        const int max_cx = min(grid.num_cols - 1, cv_ceil((double)(ref_x - grid.min_x + r) * grid.inv_cell_width));
+        const int min_cy = max(0, cv_floor((double)(ref_y - grid.min_y - r) * grid.inv_cell_height));
+        const int max_cy = min(grid.num_rows - 1, cv_ceil((double)(ref_y - grid.min_y + r) * grid.inv_cell_height));
+        if (min_cx < grid.num_cols && max_cx >= 0 && min_cy < grid.num_rows && max_cy >= 0) {
+            const bool check_level = (0 < min_level) || (0 <= max_level);
+            const float qxr = J.qxr ? J.qxr[q] : 0.0f;
+            uint4 q0, q1;
+            load_desc(J.qdesc + 32 * (size_t)q, q0, q1);
+            for (int c = min_cx; c <= max_cx; ++c) {
+                const int p_begin = S.col_start[c * grid.num_rows + min_cy];
+                const int p_end = S.col_start[c * grid.num_rows + max_cy + 1];
+                for (int p = p_begin + lane; p < p_end; p += 32) {
+                    const int meta = S.meta[p];
+                    const int oct = (int)(signed char)(meta & 0xff);
+                    if (check_level) {
+                        if (oct < min_level) continue;
+                        if (0 <= max_level && max_level < oct) continue;
+                    }
+                    const float dx = S.x[p] - ref_x, dy = S.y[p] - ref_y;
+                    if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
+                    if ((meta >> 16) & 1) continue;          // already has a landmark with observations
+                    if (owner && owner[p] < q) continue;     // claimed by an earlier query
+                    const float xr = S.xr[p];
+                    if (0 < xr) {  // projection.cc:76-83 / 310-317
+                        const float err = fabsf(qxr - xr);
+                        if (r < err) continue;
+                    }
+                    const unsigned d = (unsigned)hamming256(q0, q1, S.desc[2 * p], S.desc[2 * p + 1]);
+                    if (d >= PLP_MAX_HAMMING_DIST) continue;  // can never replace the initial best / second
+                    const unsigned long long key =
+                        ((unsigned long long)d << 40) | ((unsigned long long)(unsigned)p << 8) | (unsigned)(oct & 0xff);
+                    if (has_floor && key <= floor) continue;
+                    if (key < k1) {
+                        k2 = k1;
+                        k1 = key;
+                    } else if (key < k2) {
+                        k2 = key;
                     }
                 }
-                const int min_cy = max(0, cv_floor((double)(ref_y - grid.min_y - r) * grid.inv_cell_height));
-                const int max_cy = min(grid.num_rows - 1, cv_ceil((double)(ref_y - grid.min_y + r) * grid.inv_cell_height));
-                if (min_cx < grid.num_cols && max_cx >= 0 && min_cy < grid.num_rows && max_cy >= 0) {
-                    const bool check_level = (0 < min_level) || (0 <= max_level);
-                    const float qxr = J.qxr ? J.qxr[q] : 0.0f;
-                    uint4 q0, q1;
-                    load_desc(J.qdesc + 32 * (size_t)q, q0, q1);
-                    unsigned long long k1 = ~0ull, k2 = ~0ull;
-                    for (int c = min_cx; c <= max_cx; ++c) {
-                        const int p_begin = S.col_start[c * grid.num_rows + min_cy];
-                        const int p_end = S.col_start[c * grid.num_rows + max_cy + 1];
-                        for (int p = p_begin + lane; p < p_end; p += 32) {
-                            const int meta = S.meta[p];
-                            const int oct = (int)(signed char)(meta & 0xff);
-                            if (check_level) {
-                                if (oct < min_level) continue;
-                                if (0 <= max_level && max_level < oct) continue;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+            const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+            const unsigned long long lo = k1 < o1 ? k1 : o1, hi = k1 < o1 ? o1 : k1;
+            const unsigned long long s2 = k2 < o2 ? k2 : o2;
+            k1 = lo;
+            k2 = hi < s2 ? hi : s2;
+        }
+    };
+
+    if (!ratio_test) {
+        // No ratio test (match_current_and_last_frames): "best unclaimed candidate, queries served in index order"
+        // is a serial dictatorship = the unique stable matching when every keypoint prefers the smallest query
+        // index.  Deferred acceptance reaches it with work proportional to the number of conflicts: every query
+        // proposes to its best candidate; a keypoint keeps its smallest proposer; only bumped queries re-propose
+        // to their next candidate in (distance, order).
+        int *owner = owner_prev;  // min proposer so far; never reset
+        for (int q = warp; q < m; q += nwarps) {
+            int choice = -1;
+            if (J.qvalid ? (J.qvalid[q] != 0) : true) {
+                unsigned long long k1, k2;
+                scan(q, nullptr, false, 0ull, k1, k2);
+                if (k1 != ~0ull && (unsigned)(k1 >> 40) <= PLP_HAMMING_DIST_THR_HIGH) choice = (int)((k1 >> 8) & 0xffffffffull);
+            }
+            if (lane == 0) {
+                J.choice[q] = choice;
+                if (choice >= 0) atomicMin(&owner[choice], q);
+            }
+        }
+        __syncthreads();
+        for (int round = 0; round <= m; ++round) {
+            for (int q = warp; q < m; q += nwarps) {
+                const int c = J.choice[q];
+                if (c < 0 || owner[c] == q) continue;  // still holding its proposal (or exhausted)
+                // bumped by a smaller query: next candidate after the lost one
+                uint4 q0, q1;
+                load_desc(J.qdesc + 32 * (size_t)q, q0, q1);
+                const unsigned dc = (unsigned)hamming256(q0, q1, S.desc[2 * c], S.desc[2 * c + 1]);
+                const unsigned long long floor =
+                    ((unsigned long long)dc << 40) | ((unsigned long long)(unsigned)c << 8) | (unsigned)(S.meta[c] & 0xff);
+                unsigned long long k1, k2;
+                scan(q, nullptr, true, floor, k1, k2);
+                int choice = -1;
+                if (k1 != ~0ull && (unsigned)(k1 >> 40) <= PLP_HAMMING_DIST_THR_HIGH) choice = (int)((k1 >> 8) & 0xffffffffull);
+                if (lane == 0) {
+                    J.choice[q] = choice;
+                    if (choice >= 0) atomicMin(&owner[choice], q);
+                    S.flags[0] = 1;
+                }
+            }
+            __syncthreads();
+            const int changed = S.flags[0];
+            __syncthreads();
+            if (!changed) break;
+            if (tid == 0) S.flags[0] = 0;
+            __syncthreads();
+        }
+    } else {
+        // Ratio test (match_frame_and_landmarks): acceptance depends on the second-best AVAILABLE candidate, so we
+        // iterate choice[q] = f(claims of queries < q) to its (unique) fixed point.
+        for (int round = 0; round <= m; ++round) {
+            for (int q = warp; q < m; q += nwarps) {
+                int choice = -1;
+                const bool valid = J.qvalid ? (J.qvalid[q] != 0) : true;
+                if (valid) {
+                    if (round > 0) {
+                        // a query's result depends only on the owners inside its column span: if none of them changed
+                        // in the previous round the previous choice stands (it only re-issues its claim)
+                        const float ref_x = J.qx[q], r = J.qradius[q];
+                        const int min_cx = max(0, cv_floor((double)(ref_x - grid.min_x - r) * grid.inv_cell_width));
+                        const int max_cx = min(grid.num_cols - 1, cv_ceil((double)(ref_x - grid.min_x + r) * grid.inv_cell_width));
+                        bool dirty = false;
+                        for (int c = min_cx + lane; c <= max_cx; c += 32) dirty = dirty || S.colchg[c];
+                        if (!__any_sync(0xffffffffu, dirty)) {
+                            if (lane == 0) {
+                                choice = J.choice[q];
+                                if (choice >= 0) atomicMin(&owner_next[choice], q);
                             }
-                            const float dx = S.x[p] - ref_x, dy = S.y[p] - ref_y;
-                            if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
-                            if ((meta >> 16) & 1) continue;   // already has a landmark with observations
-                            if (owner_prev[p] < q) continue;  // claimed by an earlier query
-                            const float xr = S.xr[p];
-                            if (0 < xr) {  // projection.cc:76-83 / 310-317
-                                const float err = fabsf(qxr - xr);
-                                if (r < err) continue;
-                            }
-                            const unsigned d = (unsigned)hamming256(q0, q1, S.desc[2 * p], S.desc[2 * p + 1]);
-                            if (d >= PLP_MAX_HAMMING_DIST) continue;  // can never replace the initial best / second
-                            const unsigned long long key =
-                                ((unsigned long long)d << 40) | ((unsigned long long)(unsigned)p << 8) | (unsigned)(oct & 0xff);
-                            if (key < k1) {
-                                k2 = k1;
-                                k1 = key;
-                            } else if (key < k2) {
-                                k2 = key;
-                            }
+                            continue;
                         }
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o);
-                        const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, k2, o);
-                        const unsigned long long lo = k1 < o1 ? k1 : o1, hi = k1 < o1 ? o1 : k1;
-                        const unsigned long long s2 = k2 < o2 ? k2 : o2;
-                        k1 = lo;
-                        k2 = hi < s2 ? hi : s2;
-                    }
+                    unsigned long long k1, k2;
+                    scan(q, owner_prev, false, 0ull, k1, k2);
                     if (k1 != ~0ull) {
                         const unsigned best = (unsigned)(k1 >> 40);
                         const int best_p = (int)((k1 >> 8) & 0xffffffffull);
@@ -417,37 +481,37 @@ __global__ void __launch_bounds__(kThreads, 1)
                         const int second_lvl = k2 != ~0ull ? (int)(signed char)(k2 & 0xff) : -1;
                         if (best <= PLP_HAMMING_DIST_THR_HIGH) {
                             bool ok = true;
-                            if (ratio_test && best_lvl == second_lvl && (float)best > lowe_ratio * (float)second) ok = false;
+                            if (best_lvl == second_lvl && (float)best > lowe_ratio * (float)second) ok = false;
                             if (ok) choice = best_p;
                         }
                     }
                 }
+                if (lane == 0) {
+                    J.choice[q] = choice;
+                    if (choice >= 0) atomicMin(&owner_next[choice], q);
+                }
             }
-            if (lane == 0) {
-                J.choice[q] = choice;
-                if (choice >= 0) atomicMin(&owner_next[choice], q);
-            }
+            __syncthreads();
+            for (int c = tid; c < grid.num_cols; c += kThreads) S.colchg[c] = 0;
+            __syncthreads();
+            for (int p = tid; p < n_in; p += kThreads)
+                if (owner_next[p] != owner_prev[p]) {
+                    S.flags[0] = 1;
+                    S.colchg[(S.meta[p] >> 17) & 0x3fff] = 1;
+                }
+            __syncthreads();
+            const int changed = S.flags[0];
+            __syncthreads();
+            if (!changed) break;
+            if (tid == 0) S.flags[0] = 0;
+            int *t = owner_prev;
+            owner_prev = owner_next;
+            owner_next = t;
+            for (int p = tid; p < n_in; p += kThreads) owner_next[p] = 0x7fffffff;
+            __syncthreads();
         }
-        __syncthreads();
-        for (int c = tid; c < grid.num_cols; c += kThreads) S.colchg[c] = 0;
-        __syncthreads();
-        for (int p = tid; p < n_in; p += kThreads)
-            if (owner_next[p] != owner_prev[p]) {
-                S.flags[0] = 1;
-                S.colchg[(S.meta[p] >> 17) & 0x3fff] = 1;
-            }
-        __syncthreads();
-        const int changed = S.flags[0];
-        __syncthreads();
-        if (!changed) break;
-        if (tid == 0) S.flags[0] = 0;
-        int *t = owner_prev;
-        owner_prev = owner_next;
-        owner_next = t;
-        for (int p = tid; p < n_in; p += kThreads) owner_next[p] = 0x7fffffff;
-        __syncthreads();
     }
-    // owner_prev == owner_next: choice[] is the sequential result
+    // choice[] now holds the sequential result
 
     // ---- 5. orientation histogram (projection.cc:337-354) and outputs
     for (int b = tid; b < kHistLen; b += kThreads) S.hist[b] = 0;
