@@ -135,6 +135,18 @@ __constant__ int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1,
 
 // m = max over the sixteen 9-arcs of min(arc differences), both polarities; returns 0 early when the pixel
 // cannot be a corner at threshold `t` (then m <= t and the caller stores score 0).
+// Necessary condition for a FAST-9 corner: a 9-arc covers at least two ADJACENT compass pixels (0, 4, 8, 12), which
+// must then all be darker (or all brighter) than the centre by more than t.
+__device__ __forceinline__ bool fast_compass(const uint8_t *p, int t) {
+    const int v = p[0];
+    const int d0 = v - p[3 * kTilePitch], d4 = v - p[3], d8 = v - p[-3 * kTilePitch], d12 = v - p[-3];
+    const unsigned dk = (unsigned)(d0 > t) | ((unsigned)(d4 > t) << 1) | ((unsigned)(d8 > t) << 2) | ((unsigned)(d12 > t) << 3);
+    const unsigned br = (unsigned)(d0 < -t) | ((unsigned)(d4 < -t) << 1) | ((unsigned)(d8 < -t) << 2) | ((unsigned)(d12 < -t) << 3);
+    // adjacent pairs on the 4-cycle: (0,1) (1,2) (2,3) (3,0)
+    const unsigned dk2 = dk & ((dk >> 1) | (dk << 3)), br2 = br & ((br >> 1) | (br << 3));
+    return ((dk2 | br2) & 0xfu) != 0;
+}
+
 __device__ __forceinline__ int fast_m(const uint8_t *p, int t) {
     const int v = p[0];
     int d[16];
@@ -212,6 +224,8 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(OrbDev P) {
     __shared__ __align__(16) uint8_t score[kTileRows * kTilePitch];
     __shared__ int warp_sums[8];
     __shared__ int s_total[2];
+    __shared__ unsigned short s_list[4096];  // tested pixels that survive the compass pretest
+    __shared__ int s_nsurv;
     const int b = blockIdx.y, ci = blockIdx.x, tid = threadIdx.x;
     const CellDesc cell = P.cells[ci];
     const int l = cell.level;
@@ -245,10 +259,32 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(OrbDev P) {
     // The score of a corner (m - 1) does not depend on the threshold, non-corners score 0 in the NMS buffer.
     for (int pass = 0; pass < 2; ++pass) {
         const int thr = pass == 0 ? P.ini_thr : P.min_thr;
-        for (int p = tid; p < total; p += 256) {
+        // phase A (uniform, cheap): compass pretest on every tested pixel, survivors are compacted so that the
+        // expensive arc test below runs on full warps instead of diverging inside them
+        if (tid == 0) s_nsurv = 0;
+        __syncthreads();
+        for (int base = 0; base < total; base += 256) {
+            const int p = base + tid;
+            bool surv = false;
+            if (p < total) {
+                const int y = 3 + p / tw, x = 3 + p % tw;
+                score[y * kTilePitch + x] = 0;
+                surv = fast_compass(tile + y * kTilePitch + x, thr);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, surv);
+            int wbase = 0;
+            if ((tid & 31) == 0 && bal) wbase = atomicAdd(&s_nsurv, __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (surv) s_list[wbase + __popc(bal & ((1u << (tid & 31)) - 1))] = (unsigned short)p;
+        }
+        __syncthreads();
+        // phase B: exact arc test / score for the survivors
+        const int nsurv = s_nsurv;
+        for (int i = tid; i < nsurv; i += 256) {
+            const int p = s_list[i];
             const int y = 3 + p / tw, x = 3 + p % tw;
             const int m = fast_m(tile + y * kTilePitch + x, thr);
-            score[y * kTilePitch + x] = (m > thr) ? (uint8_t)(m - 1) : (uint8_t)0;
+            if (m > thr) score[y * kTilePitch + x] = (uint8_t)(m - 1);
         }
         __syncthreads();
         flags = 0;
@@ -960,33 +996,37 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
                                                                     uint8_t *__restrict__ desc_out,
                                                                     int32_t *__restrict__ n_out) {
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * kDescWarps + warp;
     const int *lvl_cnt = P.lvl_cnt + (size_t)b * P.num_levels;
     // total keypoints of the frame (level-major output order, orb_extractor.cc:137-159)
     int total = 0;
     for (int l = 0; l < P.num_levels; ++l) total += lvl_cnt[l];
-    if (blockIdx.x == 0 && threadIdx.x == 0) n_out[b] = min(total, P.out_cap);
-    if (slot >= P.total_slots) return;
-    int l = 0;
-    while (l + 1 < P.num_levels && slot >= P.lv[l + 1].slot_base) ++l;
-    const int idx = slot - P.lv[l].slot_base;
-    if (idx >= lvl_cnt[l]) return;
-    int out_pos = idx;
-    for (int k = 0; k < l; ++k) out_pos += lvl_cnt[k];
-    if (out_pos >= P.out_cap) return;
-    const LevelKp kp = P.lvl_kp[(size_t)b * P.total_slots + slot];
+    total = min(total, P.out_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_out[b] = total;
+    // warps stride the ACTUAL keypoints of the frame (the slot space is 4x larger than what is normally used)
+    for (int out_pos = blockIdx.x * kDescWarps + warp; out_pos < total; out_pos += gridDim.x * kDescWarps) {
+    int l = 0, idx = out_pos;
+    while (idx >= lvl_cnt[l]) {
+        idx -= lvl_cnt[l];
+        ++l;
+    }
+    const LevelKp kp = P.lvl_kp[(size_t)b * P.total_slots + P.lv[l].slot_base + idx];
     const uint8_t *img = level_ptr(P, b, l);
     const int pitch = level_pitch(P, l), W = P.lv[l].w, H = P.lv[l].h;
     const int cx = kp.x, cy = kp.y;
 
-    // ---- ic_angle (orb_extractor.cc:708-735): integer moments over the radius-15 disc
+    // ---- ic_angle (orb_extractor.cc:708-735): integer moments over the radius-15 disc; lanes = columns, the 31 row
+    //      loads are fully unrolled (u_max of orb_extractor.cc:270-286 for the fixed half patch size 15)
     int m10 = 0, m01 = 0;
     {
+        constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
         const int u = lane - kHalfPatch;  // lanes 0..30 -> u = -15..15
+        const int au = u < 0 ? -u : u;
+        const uint8_t *c0 = img + (size_t)cy * pitch + cx + u;
+#pragma unroll
         for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-            const int d = P.u_max[v < 0 ? -v : v];
-            if (lane < 31 && u >= -d && u <= d) {
-                const int val = img[(size_t)(cy + v) * pitch + cx + u];
+            const int d = kUmax[v < 0 ? -v : v];
+            if (lane < 31 && au <= d) {
+                const int val = __ldg(c0 + v * pitch);
                 m10 += u * val;
                 m01 += v * val;
             }
@@ -1029,6 +1069,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
         o.class_id = -1;
         kp_out[(size_t)b * P.out_cap + out_pos] = o;
     }
+    }  // keypoint loop
 }
 
 }  // namespace
@@ -1390,7 +1431,8 @@ static plp_status orb_run(plp_orb *o, const uint8_t *d_imgs, int batch, size_t s
         PLP_LAUNCH(ctx, quadtree_kernel, grid, kQtThreads, o->qt_smem, D);
     }
     {
-        dim3 grid(div_up(D.total_slots, kDescWarps), batch);
+        const int kp_est = std::max(256, (int)(3 * o->params.max_num_keypts / 2));  // warps stride the rest
+        dim3 grid(div_up(std::min(D.total_slots, kp_est), kDescWarps), batch);
         PLP_LAUNCH(ctx, describe_kernel, grid, kDescWarps * 32, 0, D, d_kp, d_desc, d_n);
     }
     PLP_CHECK_LAUNCH();
