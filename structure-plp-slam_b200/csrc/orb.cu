@@ -222,10 +222,11 @@ __device__ __forceinline__ bool masked(const OrbDev &P, unsigned y, unsigned x, 
 __global__ void __launch_bounds__(256) fast_cells_kernel(OrbDev P) {
     __shared__ __align__(16) uint8_t tile[kTileRows * kTilePitch];
     __shared__ __align__(16) uint8_t score[kTileRows * kTilePitch];
-    __shared__ int warp_sums[8];
     __shared__ int s_total[2];
-    __shared__ unsigned short s_list[4096];  // tested pixels that survive the compass pretest
+    __shared__ unsigned short s_list[4096];  // tile offsets of the pixels that survive the compass pretest
     __shared__ int s_nsurv;
+    __shared__ unsigned s_rowbits[128];  // NMS survivors: one 32-bit mask per (tested row, 32-column half)
+    __shared__ int s_rowbase[128];
     const int b = blockIdx.y, ci = blockIdx.x, tid = threadIdx.x;
     const CellDesc cell = P.cells[ci];
     const int l = cell.level;
@@ -244,17 +245,18 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(OrbDev P) {
     }
     const uint8_t *img = level_ptr(P, b, l);
     const int pitch = level_pitch(P, l);
-    for (int idx = tid; idx < w * h; idx += 256) {
-        const int y = idx / w, x = idx - y * w;
-        tile[y * kTilePitch + x] = img[(size_t)(cell.min_y + y) * pitch + cell.min_x + x];
+    const int lane = tid & 31, warp = tid >> 5;
+    // tile load: one warp per row, lanes stride the <= 70 columns (coalesced)
+    for (int y = warp; y < h; y += 8) {
+        const uint8_t *src = img + (size_t)(cell.min_y + y) * pitch + cell.min_x;
+        for (int x = lane; x < w; x += 32) tile[y * kTilePitch + x] = src[x];
     }
     for (int idx = tid; idx < kTileRows * kTilePitch / 4; idx += 256) reinterpret_cast<uint32_t *>(score)[idx] = 0;
     __syncthreads();
-    const int tw = w - 6, th = h - 6, total = tw * th;
-    // each thread owns a contiguous row-major run of tested pixels so that the output stays ordered
-    const int per = (total + 255) / 256;  // <= 16
-    const int p0 = tid * per, p1 = min(total, p0 + per);
-    unsigned flags = 0;
+    // tested area: rows 3 .. h-4, columns 3 .. w-4 (<= 64 x 64).  Work mapping everywhere below: one warp per
+    // (row, 32-column half), so no integer division is needed and ballots give row-major ordered bit masks.
+    const int tw = w - 6, th = h - 6;
+    const int halves = tw > 32 ? 2 : 1;
     // cv::FAST(cell, ini_thr) first; only if the cell yields nothing, again with min_thr (orb_extractor.cc:404-412).
     // The score of a corner (m - 1) does not depend on the threshold, non-corners score 0 in the NMS buffer.
     for (int pass = 0; pass < 2; ++pass) {
@@ -263,87 +265,102 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(OrbDev P) {
         // expensive arc test below runs on full warps instead of diverging inside them
         if (tid == 0) s_nsurv = 0;
         __syncthreads();
-        for (int base = 0; base < total; base += 256) {
-            const int p = base + tid;
+        for (int job = warp; job < th * halves; job += 8) {
+            const int ry = job / halves, hx = job - ry * halves;  // halves is 1 or 2: cheap
+            const int y = 3 + ry, x = 3 + hx * 32 + lane;
             bool surv = false;
-            if (p < total) {
-                const int y = 3 + p / tw, x = 3 + p % tw;
+            if (x < 3 + tw) {
                 score[y * kTilePitch + x] = 0;
                 surv = fast_compass(tile + y * kTilePitch + x, thr);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, surv);
             int wbase = 0;
-            if ((tid & 31) == 0 && bal) wbase = atomicAdd(&s_nsurv, __popc(bal));
+            if (lane == 0 && bal) wbase = atomicAdd(&s_nsurv, __popc(bal));
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (surv) s_list[wbase + __popc(bal & ((1u << (tid & 31)) - 1))] = (unsigned short)p;
+            if (surv) s_list[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)(y * kTilePitch + x);
         }
         __syncthreads();
         // phase B: exact arc test / score for the survivors
         const int nsurv = s_nsurv;
         for (int i = tid; i < nsurv; i += 256) {
-            const int p = s_list[i];
-            const int y = 3 + p / tw, x = 3 + p % tw;
-            const int m = fast_m(tile + y * kTilePitch + x, thr);
-            if (m > thr) score[y * kTilePitch + x] = (uint8_t)(m - 1);
+            const int off = s_list[i];
+            const int m = fast_m(tile + off, thr);
+            if (m > thr) score[off] = (uint8_t)(m - 1);
         }
         __syncthreads();
-        flags = 0;
-        for (int p = p0; p < p1; ++p) {
-            const int y = 3 + p / tw, x = 3 + p % tw;
-            const uint8_t *s = score + y * kTilePitch + x;
-            const int sc = s[0];
-            if (sc == 0) continue;
-            bool keep = true;
+        // 3x3 non-maximum suppression -> one 32-bit mask per (row, half)
+        bool any_local = false;
+        for (int job = warp; job < th * halves; job += 8) {
+            const int ry = job / halves, hx = job - ry * halves;
+            const int y = 3 + ry, x = 3 + hx * 32 + lane;
+            bool keep = false;
+            if (x < 3 + tw) {
+                const uint8_t *sp = score + y * kTilePitch + x;
+                const int sc = sp[0];
+                if (sc != 0) {
+                    keep = true;
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
+                    for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    if (dx == 0 && dy == 0) continue;
-                    keep = keep && (sc > (int)s[dy * kTilePitch + dx]);
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            if (dx == 0 && dy == 0) continue;
+                            keep = keep && (sc > (int)sp[dy * kTilePitch + dx]);
+                        }
                 }
-            flags |= (unsigned)keep << (p - p0);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_rowbits[ry * 2 + hx] = bal;
+            any_local = any_local || bal != 0;
         }
-        const int any = __syncthreads_or(flags != 0);  // also orders the score-map reads before the next pass
+        const int any = __syncthreads_or(any_local);  // also orders the score-map reads before the next pass
         if (any || P.min_thr == P.ini_thr) break;
     }
-    if (P.mask && flags) {  // orb_extractor.cc:429
-        for (int p = p0; p < p1; ++p) {
-            if (!((flags >> (p - p0)) & 1)) continue;
-            const int y = 3 + p / tw, x = 3 + p % tw;
-            const float kx = (float)x + (float)(cell.j * kCellSize), ky = (float)y + (float)(cell.i * kCellSize);
-            if (masked(P, (unsigned)((float)kPatchRadius + ky), (unsigned)((float)kPatchRadius + kx), scale))
-                flags &= ~(1u << (p - p0));
+    // per-keypoint mask test (orb_extractor.cc:429), then ordered (row-major) compaction
+    if (P.mask) {
+        for (int job = warp; job < th * halves; job += 8) {
+            const int ry = job / halves, hx = job - ry * halves;
+            const int y = 3 + ry, x = 3 + hx * 32 + lane;
+            unsigned bits = s_rowbits[ry * 2 + hx];
+            bool drop = false;
+            if ((bits >> lane) & 1) {
+                const float kx = (float)x + (float)(cell.j * kCellSize), ky = (float)y + (float)(cell.i * kCellSize);
+                drop = masked(P, (unsigned)((float)kPatchRadius + ky), (unsigned)((float)kPatchRadius + kx), scale);
+            }
+            const unsigned dropbal = __ballot_sync(0xffffffffu, drop);
+            if (lane == 0) s_rowbits[ry * 2 + hx] = bits & ~dropbal;
         }
+        __syncthreads();
     }
-    // block exclusive scan of popc(flags)
-    const int mine = __popc(flags);
-    int incl = mine;
-    const int lane = tid & 31, warp = tid >> 5;
+    // exclusive prefix of the per-(row, half) counts (<= 128 entries) by warp 0
+    if (warp == 0) {
+        int run = 0;
+        const int njobs = th * halves;
+        for (int base = 0; base < njobs; base += 32) {
+            const int jdx = base + lane;
+            const int ry = jdx / halves, hx = jdx - ry * halves;
+            const int c = jdx < njobs ? __popc(s_rowbits[ry * 2 + hx]) : 0;
+            int incl = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int k = 0; k < 8; ++k) {
-            const int v = warp_sums[k];
-            warp_sums[k] = acc;
-            acc += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (jdx < njobs) s_rowbase[jdx] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
-        s_total[0] = acc;
+        if (lane == 0) s_total[0] = run;
     }
     __syncthreads();
-    int pos = warp_sums[warp] + incl - mine;
-    for (int p = p0; p < p1; ++p) {
-        if (!((flags >> (p - p0)) & 1)) continue;
-        const int y = 3 + p / tw, x = 3 + p % tw;
-        const int sc = score[y * kTilePitch + x];
-        const int lx = x + cell.j * kCellSize, ly = y + cell.i * kCellSize;  // relative to the 19-px border
-        if (pos < kCellCap) buf[pos] = (uint32_t)lx | ((uint32_t)ly << 11) | ((uint32_t)sc << 21);
-        ++pos;
+    for (int job = warp; job < th * halves; job += 8) {
+        const int ry = job / halves, hx = job - ry * halves;
+        const int y = 3 + ry, x = 3 + hx * 32 + lane;
+        const unsigned bits = s_rowbits[ry * 2 + hx];
+        if ((bits >> lane) & 1) {
+            const int pos = s_rowbase[job] + __popc(bits & ((1u << lane) - 1));
+            const int sc = score[y * kTilePitch + x];
+            const int lx = x + cell.j * kCellSize, ly = y + cell.i * kCellSize;  // relative to the 19-px border
+            if (pos < kCellCap) buf[pos] = (uint32_t)lx | ((uint32_t)ly << 11) | ((uint32_t)sc << 21);
+        }
     }
     if (tid == 0) *cnt_out = min(s_total[0], kCellCap);
 }
@@ -995,6 +1012,7 @@ __global__ void __launch_bounds__(256) blur_tiles_kernel(OrbDev P) {
 __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp_keypoint *__restrict__ kp_out,
                                                                     uint8_t *__restrict__ desc_out,
                                                                     int32_t *__restrict__ n_out) {
+    __shared__ __align__(16) uint8_t s_win[kDescWarps][kBlurDim * kBlurPitch];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int *lvl_cnt = P.lvl_cnt + (size_t)b * P.num_levels;
     // total keypoints of the frame (level-major output order, orb_extractor.cc:137-159)
@@ -1044,9 +1062,19 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
     const float ang_rad = (float)((double)angle * 3.14159265358979323846 / 180.0);
     const float ca = util_cos(ang_rad), sa = util_sin(ang_rad);
     const int bpitch = P.lv[l].pitch;
-    const uint8_t *center = P.blur + (size_t)b * P.blur_frame_bytes + P.lv[l].blur_offset + (size_t)cy * bpitch + cx;
+    const uint8_t *bsrc = P.blur + (size_t)b * P.blur_frame_bytes + P.lv[l].blur_offset + (size_t)(cy - 19) * bpitch + (cx - 19);
     (void)W;
     (void)H;
+    // stage the 39 x 39 blurred window with coalesced row loads, then gather the 512 samples from shared memory
+    uint8_t *win = s_win[warp];
+    __syncwarp();
+#pragma unroll 13
+    for (int r = 0; r < kBlurDim; ++r) {
+        win[r * kBlurPitch + lane] = __ldg(bsrc + r * bpitch + lane);
+        if (lane < kBlurDim - 32) win[r * kBlurPitch + 32 + lane] = __ldg(bsrc + r * bpitch + 32 + lane);
+    }
+    __syncwarp();
+    const uint8_t *center = win + 19 * kBlurPitch + 19;
     int val = 0;
 #pragma unroll
     for (int bit = 0; bit < 8; ++bit) {
@@ -1054,7 +1082,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
         const float x1 = (float)kBriefX1[k], y1 = (float)kBriefY1[k], x2 = (float)kBriefX2[k], y2 = (float)kBriefY2[k];
         const int r1 = __float2int_rn(x1 * sa + y1 * ca), c1 = __float2int_rn(x1 * ca - y1 * sa);
         const int r2 = __float2int_rn(x2 * sa + y2 * ca), c2 = __float2int_rn(x2 * ca - y2 * sa);
-        val |= (__ldg(center + r1 * bpitch + c1) < __ldg(center + r2 * bpitch + c2)) << bit;
+        val |= (center[r1 * kBlurPitch + c1] < center[r2 * kBlurPitch + c2]) << bit;
     }
     desc_out[((size_t)b * P.out_cap + out_pos) * 32 + lane] = (uint8_t)val;
     if (lane == 0) {
