@@ -1014,22 +1014,43 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
                                                                     int32_t *__restrict__ n_out) {
     __shared__ __align__(16) uint8_t s_win[kDescWarps][kBlurDim * kBlurPitch];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int *lvl_cnt = P.lvl_cnt + (size_t)b * P.num_levels;
+    // per-level lookups staged once per block (dynamic indexing of the by-value parameter struct costs a constant-bank
+    // load per use, and the per-keypoint level search re-read lvl_cnt from global memory)
+    __shared__ int s_cum[kMaxLevels + 1];
+    __shared__ const uint8_t *s_img[kMaxLevels], *s_blur[kMaxLevels];
+    __shared__ int s_pitch[kMaxLevels], s_bpitch[kMaxLevels], s_slot[kMaxLevels];
+    __shared__ float s_scale[kMaxLevels], s_size[kMaxLevels];
+    if (threadIdx.x == 0) {
+        const int *lvl_cnt = P.lvl_cnt + (size_t)b * P.num_levels;
+        int acc = 0;
+        for (int l = 0; l < P.num_levels; ++l) {
+            s_cum[l] = acc;
+            acc += lvl_cnt[l];
+        }
+        for (int l = P.num_levels; l <= kMaxLevels; ++l) s_cum[l] = acc;
+    }
+    if (threadIdx.x < P.num_levels) {
+        const int l = threadIdx.x;
+        s_img[l] = level_ptr(P, b, l);
+        s_pitch[l] = level_pitch(P, l);
+        s_blur[l] = P.blur + (size_t)b * P.blur_frame_bytes + P.lv[l].blur_offset;
+        s_bpitch[l] = P.lv[l].pitch;
+        s_slot[l] = P.lv[l].slot_base;
+        s_scale[l] = P.lv[l].scale_factor;
+        s_size[l] = P.lv[l].size;
+    }
+    __syncthreads();
     // total keypoints of the frame (level-major output order, orb_extractor.cc:137-159)
-    int total = 0;
-    for (int l = 0; l < P.num_levels; ++l) total += lvl_cnt[l];
-    total = min(total, P.out_cap);
+    const int total = min(s_cum[kMaxLevels], P.out_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) n_out[b] = total;
+    const LevelKp *frame_kp = P.lvl_kp + (size_t)b * P.total_slots;
     // warps stride the ACTUAL keypoints of the frame (the slot space is 4x larger than what is normally used)
     for (int out_pos = blockIdx.x * kDescWarps + warp; out_pos < total; out_pos += gridDim.x * kDescWarps) {
-    int l = 0, idx = out_pos;
-    while (idx >= lvl_cnt[l]) {
-        idx -= lvl_cnt[l];
-        ++l;
-    }
-    const LevelKp kp = P.lvl_kp[(size_t)b * P.total_slots + P.lv[l].slot_base + idx];
-    const uint8_t *img = level_ptr(P, b, l);
-    const int pitch = level_pitch(P, l), W = P.lv[l].w, H = P.lv[l].h;
+    int l = 0;
+    while (out_pos >= s_cum[l + 1]) ++l;
+    const LevelKp kp = frame_kp[s_slot[l] + out_pos - s_cum[l]];
+    const uint8_t *img = s_img[l];
+    const int pitch = s_pitch[l];
     const int cx = kp.x, cy = kp.y;
 
     // ---- ic_angle (orb_extractor.cc:708-735): integer moments over the radius-15 disc; lanes = columns, the 31 row
@@ -1061,10 +1082,8 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
     //      produces descriptor byte i; the 16 byte gathers of a lane fall inside a 37 x 37 window (L1-resident)
     const float ang_rad = (float)((double)angle * 3.14159265358979323846 / 180.0);
     const float ca = util_cos(ang_rad), sa = util_sin(ang_rad);
-    const int bpitch = P.lv[l].pitch;
-    const uint8_t *bsrc = P.blur + (size_t)b * P.blur_frame_bytes + P.lv[l].blur_offset + (size_t)(cy - 19) * bpitch + (cx - 19);
-    (void)W;
-    (void)H;
+    const int bpitch = s_bpitch[l];
+    const uint8_t *bsrc = s_blur[l] + (size_t)(cy - 19) * bpitch + (cx - 19);
     // stage the 39 x 39 blurred window with coalesced row loads, then gather the 512 samples from shared memory
     uint8_t *win = s_win[warp];
     __syncwarp();
@@ -1076,10 +1095,17 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
     __syncwarp();
     const uint8_t *center = win + 19 * kBlurPitch + 19;
     int val = 0;
+    // the lane's 8 test pairs: 8 consecutive int8 per table = one 64-bit load each (the tables live in global
+    // memory: lane-dependent indices into __constant__ memory would serialise)
+    const uint2 px1 = __ldg(reinterpret_cast<const uint2 *>(kBriefX1) + lane), py1 = __ldg(reinterpret_cast<const uint2 *>(kBriefY1) + lane);
+    const uint2 px2 = __ldg(reinterpret_cast<const uint2 *>(kBriefX2) + lane), py2 = __ldg(reinterpret_cast<const uint2 *>(kBriefY2) + lane);
 #pragma unroll
     for (int bit = 0; bit < 8; ++bit) {
-        const int k = lane * 8 + bit;
-        const float x1 = (float)kBriefX1[k], y1 = (float)kBriefY1[k], x2 = (float)kBriefX2[k], y2 = (float)kBriefY2[k];
+        const int sh = (bit & 3) * 8;
+        const float x1 = (float)(signed char)(((bit < 4 ? px1.x : px1.y) >> sh) & 0xff);
+        const float y1 = (float)(signed char)(((bit < 4 ? py1.x : py1.y) >> sh) & 0xff);
+        const float x2 = (float)(signed char)(((bit < 4 ? px2.x : px2.y) >> sh) & 0xff);
+        const float y2 = (float)(signed char)(((bit < 4 ? py2.x : py2.y) >> sh) & 0xff);
         const int r1 = __float2int_rn(x1 * sa + y1 * ca), c1 = __float2int_rn(x1 * ca - y1 * sa);
         const int r2 = __float2int_rn(x2 * sa + y2 * ca), c2 = __float2int_rn(x2 * ca - y2 * sa);
         val |= (center[r1 * kBlurPitch + c1] < center[r2 * kBlurPitch + c2]) << bit;
@@ -1087,10 +1113,10 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
     desc_out[((size_t)b * P.out_cap + out_pos) * 32 + lane] = (uint8_t)val;
     if (lane == 0) {
         plp_keypoint o;
-        const float s = P.lv[l].scale_factor;
+        const float s = s_scale[l];
         o.x = l == 0 ? (float)cx : (float)cx * s;  // orb_extractor.cc:695-706
         o.y = l == 0 ? (float)cy : (float)cy * s;
-        o.size = P.lv[l].size;
+        o.size = s_size[l];
         o.angle = angle;
         o.response = (float)kp.response;
         o.octave = l;
