@@ -34,9 +34,12 @@ typedef struct orc_keyline { /* cv::line_descriptor::KeyLine, descriptor_custom.
  *                 introsort leaves) -- used to pin this restatement against cv2 4.13.
  * libm_float: 1 = cosf/sinf of glibc where cv calls cos(float)/sin(float); 0 = evaluate in double, round to float
  *                 (the determinism rule the CUDA path can follow). */
+/* sum_order:  0 = sequential double sums and swap-remove compaction as lsd.cpp writes them; 1 = 32 strided partial sums
+ *                 combined by an xor tree and order-preserving compaction (what a warp computes) -- the CUDA path. */
 typedef struct orc_lsd_config {
     int32_t seed_order;
     int32_t libm_float;
+    int32_t sum_order;
 } orc_lsd_config;
 
 /* GaussianBlur(11x11, sigma 1.2) fixed-point + resize(0.5, INTER_LINEAR_EXACT): the image LSD works on */
@@ -53,8 +56,8 @@ int orc_lsd_keylines(const uint8_t *img, int w, int h, int step, const orc_lsd_c
 /* cv::Sobel(3x3, CV_16S) of the GaussianBlur(5x5, 1) image (binary_descriptor_custom.cpp:347-395) */
 void orc_lbd_gradients(const uint8_t *img, int w, int h, int step, int16_t *dx, int16_t *dy);
 /* BinaryDescriptor::compute (binary_descriptor_custom.cpp:518-679, 1018-1364); desc_float (72 per line) optional */
-void orc_lbd_compute(const uint8_t *img, int w, int h, int step, const orc_keyline *kl, int n, uint8_t *desc,
-                     float *desc_float);
+void orc_lbd_compute(const uint8_t *img, int w, int h, int step, const orc_keyline *kl, int n, int libm_float,
+                     uint8_t *desc, float *desc_float);
 /* LineFeatureTracker::extract_LSD_LBD (line_extractor.cc:88-160): keylines with octave 0 and length >= 60, their LBD
  * rows and 2-D line functions; returns the count (or -needed if cap is too small) */
 int orc_line_extract(const uint8_t *img, int w, int h, int step, const orc_lsd_config *cfg, orc_keyline *kl_out,

@@ -27,6 +27,7 @@
 #include "orb.h"
 #include "pose_opt.h"
 #include "local_ba.h"
+#include "lines.h"
 
 #ifdef __cplusplus
 extern "C" {
