@@ -276,6 +276,52 @@ PLP_API plp_status plp_orb_debug_candidates(plp_orb *orb, int b, int level, plp_
                                             int *n_out);
 
 /* ------------------------------------------------------------------------ */
+/* LSD + LBD line extraction  (feature/line_extractor.{h,cc},                */
+/* feature/line_descriptor/{LSDDetector_custom,binary_descriptor_custom}.cpp) */
+/* ------------------------------------------------------------------------ */
+typedef struct plp_keyline { /* binary layout of cv::line_descriptor::KeyLine (descriptor_custom.hpp:105-199, 68 bytes) */
+    float angle;             /* atan2(endPointY - startPointY, endPointX - startPointX)        */
+    int32_t class_id;        /* running index over the segments longer than min_length          */
+    int32_t octave;          /* always 0: the reference detects on one octave (line_extractor.cc:54) */
+    float pt_x, pt_y;        /* midpoint                                                        */
+    float response;          /* lineLength / max(cols, rows)                                    */
+    float size;
+    float start_x, start_y, end_x, end_y;
+    float s_oct_x, s_oct_y, e_oct_x, e_oct_y;
+    float line_length;
+    int32_t num_pixels;      /* cv::LineIterator count                                          */
+} plp_keyline;
+
+typedef struct plp_line plp_line; /* one per LineFeatureTracker instance; fixed image size and maximum batch */
+
+/* LineFeatureTracker::LineFeatureTracker(camera::base*) (line_extractor.cc:50-58); LSD options are the ones
+ * extract_LSD_LBD hard-codes (line_extractor.cc:113-122): refine 1, scale 0.5, sigma_scale 0.6, quant 2, ang_th 22.5,
+ * log_eps 1, density_th 0.6, n_bins 1024, min_length 0.125 * min(cols, rows). */
+PLP_API plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_line **out);
+PLP_API void plp_line_destroy(plp_line *h);
+/* keyline capacity per frame of the output arrays */
+PLP_API int plp_line_capacity(const plp_line *h);
+/* LineFeatureTracker::extract_LSD_LBD(img, frame_keylsd, frame_lbd_descr, keyline_functions) (line_extractor.cc:88-160).
+ * Host pointers.  kl_out / lbd_out (x 32 bytes) / fn_out (x 3 doubles: the 2-D line function sp x ep / |(l0, l1)|,
+ * line_extractor.cc:147-159) must hold plp_line_capacity() entries.  The identity remap the reference rebuilds every
+ * frame (line_extractor.cc:60-86, 103) returns the input bit for bit and is skipped.  An image without a segment
+ * longer than min_length yields *n_out = 0. */
+PLP_API plp_status plp_line_extract(plp_line *h, const uint8_t *img, int rows, int cols, size_t step,
+                                    plp_keyline *kl_out, uint8_t *lbd_out, double *fn_out, int *n_out);
+/* Same for `batch` equally sized frames stored back to back (frame stride rows*step). */
+PLP_API plp_status plp_line_extract_batch(plp_line *h, const uint8_t *imgs, int batch, size_t step,
+                                          plp_keyline *kl_out, uint8_t *lbd_out, double *fn_out, int32_t *n_out);
+/* Device-resident variant: no synchronisation; d_status[b] != 0 flags a capacity overflow in frame b. */
+PLP_API plp_status plp_line_extract_batch_dev(plp_line *h, const uint8_t *d_imgs, int batch, size_t step,
+                                              plp_keyline *d_kl_out, uint8_t *d_lbd_out, double *d_fn_out,
+                                              int32_t *d_n_out, int32_t *d_status);
+/* parity taps of the most recent extraction (host copies): the raw cv::LineSegmentDetector segments of frame b
+ * (x1, y1, x2, y2 in detection order), the half-resolution image LSD works on, and the 72-float LBD vectors. */
+PLP_API plp_status plp_line_debug_segments(plp_line *h, int b, float *segs_out, int cap, int *n_out);
+PLP_API plp_status plp_line_debug_scaled(plp_line *h, int b, uint8_t *out /* (rows/2) x (cols/2) */);
+PLP_API plp_status plp_line_debug_lbd_float(plp_line *h, int b, float *out /* n x 72 */, int cap);
+
+/* ------------------------------------------------------------------------ */
 /* motion-only BA  (optimize/pose_optimizer.cc, pose_optimizer_extended_line.cc) */
 /* ------------------------------------------------------------------------ */
 typedef struct plp_pt_obs { /* one matched keypoint (pose_optimizer.cc:126-151) */

@@ -10,7 +10,9 @@ The directory name contains '-' so it is loaded by path (see ``load_package`` in
 from .capi import (  # noqa: F401
     Context,
     OrbExtractor,
+    LineFeatureTracker,
     KP_DTYPE,
+    KEYLINE_DTYPE,
     PT_OBS_DTYPE,
     LINE_OBS_DTYPE,
     PlpError,

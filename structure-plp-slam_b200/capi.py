@@ -420,3 +420,83 @@ class OrbExtractor:
         self._ctx._check(self._lib.plp_orb_debug_candidates(self._h, C.c_int(b), C.c_int(level),
                                                             out.ctypes.data_as(_P), C.c_int(cap), C.byref(n)))
         return out[:min(n.value, cap)].copy()
+
+
+# binary layout of plp_keyline / cv::line_descriptor::KeyLine (descriptor_custom.hpp:105-199)
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+                          ("response", "<f4"), ("size", "<f4"), ("start_x", "<f4"), ("start_y", "<f4"),
+                          ("end_x", "<f4"), ("end_y", "<f4"), ("s_oct_x", "<f4"), ("s_oct_y", "<f4"),
+                          ("e_oct_x", "<f4"), ("e_oct_y", "<f4"), ("line_length", "<f4"), ("num_pixels", "<i4")])
+
+
+class LineFeatureTracker:
+    """feature::LineFeatureTracker (feature/line_extractor.h:62-108) backed by plp_line."""
+
+    def __init__(self, ctx: Context, rows: int, cols: int, max_batch=1):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        self.rows, self.cols, self.max_batch = rows, cols, max_batch
+        h = C.c_void_p()
+        self._h = None
+        ctx._check(self._lib.plp_line_create(ctx.handle, C.c_int(rows), C.c_int(cols), C.c_int(max_batch), C.byref(h)))
+        self._h = h
+        self.capacity = int(self._lib.plp_line_capacity(self._h))
+
+    def close(self):
+        if self._h is not None:
+            self._lib.plp_line_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def extract_LSD_LBD(self, img):
+        """LineFeatureTracker::extract_LSD_LBD -> (keylines[KEYLINE_DTYPE], lbd[n,32], line functions[n,3])."""
+        img = np.asarray(img, np.uint8)
+        if img.ndim != 2 or img.strides[1] != 1:
+            img = np.ascontiguousarray(img)
+        kl = np.zeros(self.capacity, KEYLINE_DTYPE)
+        lbd = np.zeros((self.capacity, 32), np.uint8)
+        fn = np.zeros((self.capacity, 3), np.float64)
+        n = C.c_int(0)
+        self._ctx._check(self._lib.plp_line_extract(
+            self._h, img.ctypes.data_as(_P), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_size_t(img.strides[0]),
+            kl.ctypes.data_as(_P), lbd.ctypes.data_as(_P), fn.ctypes.data_as(_P), C.byref(n)))
+        return kl[:n.value].copy(), lbd[:n.value].copy(), fn[:n.value].copy()
+
+    def extract_batch(self, imgs):
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        B = imgs.shape[0]
+        kl = np.zeros((B, self.capacity), KEYLINE_DTYPE)
+        lbd = np.zeros((B, self.capacity, 32), np.uint8)
+        fn = np.zeros((B, self.capacity, 3), np.float64)
+        n = np.zeros(B, np.int32)
+        self._ctx._check(self._lib.plp_line_extract_batch(
+            self._h, imgs.ctypes.data_as(_P), C.c_int(B), C.c_size_t(imgs.strides[1]), kl.ctypes.data_as(_P),
+            lbd.ctypes.data_as(_P), fn.ctypes.data_as(_P), n.ctypes.data_as(_P)))
+        return [(kl[b, :n[b]].copy(), lbd[b, :n[b]].copy(), fn[b, :n[b]].copy()) for b in range(B)]
+
+    def debug_segments(self, b: int) -> np.ndarray:
+        cap = 20000
+        out = np.zeros((cap, 4), np.float32)
+        n = C.c_int(0)
+        self._ctx._check(self._lib.plp_line_debug_segments(self._h, C.c_int(b), out.ctypes.data_as(_P), C.c_int(cap),
+                                                           C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_scaled(self, b: int) -> np.ndarray:
+        out = np.zeros((int(round(self.rows * 0.5)), int(round(self.cols * 0.5))), np.uint8)
+        self._ctx._check(self._lib.plp_line_debug_scaled(self._h, C.c_int(b), out.ctypes.data_as(_P)))
+        return out
+
+    def debug_lbd_float(self, b: int, n: int) -> np.ndarray:
+        out = np.zeros((max(n, 1), 72), np.float32)
+        self._ctx._check(self._lib.plp_line_debug_lbd_float(self._h, C.c_int(b), out.ctypes.data_as(_P), C.c_int(n)))
+        return out[:n].copy()

@@ -398,3 +398,92 @@ def _pose_optimize(self, cam, T_cw, pts, lines=None, num_trials=4, num_each_iter
 
 
 Oracle.pose_optimize = _pose_optimize
+
+
+# ======================================================================== line front end (oracle/lines.cc)
+class OLsdCfg(C.Structure):
+    _fields_ = [("seed_order", C.c_int32), ("libm_float", C.c_int32), ("sum_order", C.c_int32)]
+
+
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+                          ("response", "<f4"), ("size", "<f4"), ("start_x", "<f4"), ("start_y", "<f4"),
+                          ("end_x", "<f4"), ("end_y", "<f4"), ("s_oct_x", "<f4"), ("s_oct_y", "<f4"),
+                          ("e_oct_x", "<f4"), ("e_oct_y", "<f4"), ("line_length", "<f4"), ("num_pixels", "<i4")])
+
+LSD_DET = (0, 0, 1)   # the determinism rules the CUDA path implements (see oracle/lines.cc)
+LSD_CV = (0, 1, 0)    # libm + sequential sums, as lsd.cpp is written
+
+
+def _lsd_scaled(self, img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((int(round(h * 0.5)), int(round(w * 0.5))), np.uint8)
+    self.lib.orc_lsd_scaled_image(img.ctypes.data_as(_P), C.c_int(w), C.c_int(h), C.c_int(w), out.ctypes.data_as(_P))
+    return out
+
+
+def _lsd_detect(self, img, mode=LSD_DET):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = 30000
+    out = np.zeros((cap, 4), np.float32)
+    cfg = OLsdCfg(*mode)
+    n = self.lib.orc_lsd_detect(img.ctypes.data_as(_P), C.c_int(w), C.c_int(h), C.c_int(w), C.byref(cfg),
+                                out.ctypes.data_as(_P), C.c_int(cap))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def _lsd_keylines(self, img, min_length, mode=LSD_DET):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = 30000
+    out = np.zeros(cap, KEYLINE_DTYPE)
+    cfg = OLsdCfg(*mode)
+    n = self.lib.orc_lsd_keylines(img.ctypes.data_as(_P), C.c_int(w), C.c_int(h), C.c_int(w), C.byref(cfg),
+                                  C.c_double(min_length), out.ctypes.data_as(_P), C.c_int(cap))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def _lbd_gradients(self, img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    dx, dy = np.zeros((h, w), np.int16), np.zeros((h, w), np.int16)
+    self.lib.orc_lbd_gradients(img.ctypes.data_as(_P), C.c_int(w), C.c_int(h), C.c_int(w), dx.ctypes.data_as(_P),
+                               dy.ctypes.data_as(_P))
+    return dx, dy
+
+
+def _lbd_compute(self, img, keylines, libm=0):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    n = len(kl)
+    desc = np.zeros((max(n, 1), 32), np.uint8)
+    fl = np.zeros((max(n, 1), 72), np.float32)
+    self.lib.orc_lbd_compute(img.ctypes.data_as(_P), C.c_int(w), C.c_int(h), C.c_int(w), kl.ctypes.data_as(_P),
+                             C.c_int(n), C.c_int(libm), desc.ctypes.data_as(_P), fl.ctypes.data_as(_P))
+    return desc[:n].copy(), fl[:n].copy()
+
+
+def _line_extract(self, img, mode=LSD_DET):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = 8192
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    lbd = np.zeros((cap, 32), np.uint8)
+    fn = np.zeros((cap, 3), np.float64)
+    cfg = OLsdCfg(*mode)
+    n = self.lib.orc_line_extract(img.ctypes.data_as(_P), C.c_int(w), C.c_int(h), C.c_int(w), C.byref(cfg),
+                                  kl.ctypes.data_as(_P), lbd.ctypes.data_as(_P), fn.ctypes.data_as(_P), C.c_int(cap))
+    assert n >= 0
+    return kl[:n].copy(), lbd[:n].copy(), fn[:n].copy()
+
+
+Oracle.lsd_scaled = _lsd_scaled
+Oracle.lsd_detect = _lsd_detect
+Oracle.lsd_keylines = _lsd_keylines
+Oracle.lbd_gradients = _lbd_gradients
+Oracle.lbd_compute = _lbd_compute
+Oracle.line_extract = _line_extract

@@ -23,4 +23,14 @@ def run(pkg, ctx, orc):
     To, po, lo, no, _ = orc.pose_optimize(cam, T_init, pts, lines)
     Tg, pg, lg, ng = ctx.pose_optimize(cam, T_init, pts, lines)
     assert np.linalg.norm(Tg - To) / np.linalg.norm(To) < 1e-4 and ng == no and np.array_equal(pg, po)
+    # LSD + LBD line extraction of one small frame, bit-exact vs the oracle
+    limg = synth.make_line_image(7, 240, 320, n_patch=16)
+    trk = pkg.LineFeatureTracker(ctx, 240, 320)
+    kl, lbd, fn = trk.extract_LSD_LBD(limg)
+    okl, olbd, ofn = orc.line_extract(limg)
+    assert len(kl) == len(okl) > 3 and np.array_equal(lbd, olbd) and np.array_equal(fn, ofn), "line extraction differs"
+    for f in ("start_x", "start_y", "end_x", "end_y", "angle", "num_pixels"):
+        assert np.array_equal(kl[f], okl[f]), f"KeyLine field {f} differs from the oracle"
+    trk.close()
+    print(f"smoke extras ok: {len(kl)} LSD/LBD lines bit-exact")
     print(f"smoke extras ok: {len(kps)} ORB keypoints bit-exact, pose-opt inliers {ng}")

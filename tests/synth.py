@@ -300,3 +300,35 @@ def make_pose_opt_scene(seed, n_pts=1000, n_lines=200, outlier_frac=0.15, stereo
     dT[:3, 3] = xi[3:]
     T_init = dT @ T_gt
     return T_gt, T_init, pts, lines
+
+
+def make_line_image(seed, h=480, w=640, n_patch=44, noise=2.0):
+    """Seeded line-rich scene (the benchmark images must be line-rich to reach the ~200 line
+    features per frame of BASELINE.json): rotated patches of parallel stripes (facades, shelves, floor boards) with
+    random grey levels painted over a smooth ramp, anti-aliased, plus sensor noise."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = 110.0 + 40.0 * np.sin(xx / w * 2.1 + rng.uniform(0, 3)) + 30.0 * np.cos(yy / h * 1.7 + rng.uniform(0, 3))
+    img = img.astype(np.float32)
+    sc = max(h, w) / 640.0
+    for _ in range(n_patch):
+        cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+        length = rng.uniform(90, 260) * sc
+        n_str = int(rng.integers(3, 8))
+        widths = rng.uniform(9, 24, n_str) * sc
+        ang = rng.uniform(0, np.pi)
+        ca, sa = np.cos(ang), np.sin(ang)
+        off = -widths.sum() / 2
+        base = float(rng.uniform(20, 235))
+        for k in range(n_str):
+            val = float(np.clip(base + (1 if k % 2 else -1) * rng.uniform(35, 110), 5, 250))
+            u0, u1 = -length / 2, length / 2
+            v0, v1 = off, off + widths[k]
+            off = v1
+            q = np.array([[u0, v0], [u1, v0], [u1, v1], [u0, v1]])
+            pts = np.stack([cx + q[:, 0] * ca - q[:, 1] * sa, cy + q[:, 0] * sa + q[:, 1] * ca], 1)
+            cv2.fillPoly(img, [np.round(pts * 16).astype(np.int32)], val, lineType=cv2.LINE_AA, shift=4)
+    img = cv2.GaussianBlur(img, (0, 0), 0.8)
+    img += rng.normal(0, noise, (h, w)).astype(np.float32)
+    return np.clip(np.round(img), 0, 255).astype(np.uint8)
