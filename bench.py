@@ -196,6 +196,140 @@ def cpu_port_frames(frames, aux, idxs, threads):
     return len(idxs) / dt, dt, out
 
 
+def build_line_frames(batch: int, seed: int):
+    """`batch` distinct 640x480 line-rich frames: a few rendered scenes (tests/synth.make_line_image), each shifted by a
+    different offset so that no two frames of a batch are equal."""
+    import synth
+    n_base = min(batch, 12)
+    base = [synth.make_line_image(seed + i, ROWS, COLS) for i in range(n_base)]
+    rng = np.random.default_rng(seed)
+    out = np.empty((batch, ROWS, COLS), np.uint8)
+    for b in range(batch):
+        dx, dy = (0, 0) if b < n_base else (int(rng.integers(-60, 61)), int(rng.integers(-40, 41)))
+        out[b] = np.roll(base[b % n_base], (dy, dx), axis=(0, 1))
+    return out
+
+
+# SURVEY 8(d): remap is skipped (identity); per frame the line front end must read the image twice (LSD scale pass and
+# LBD blur+Sobel pass), write + read the half-resolution image, write the per-pixel level-line record once (16 B at
+# quarter resolution) and the int16 gradient pair once (4 B per pixel), and read both back at least once.
+def line_alg_bytes(rows, cols):
+    px, spx = rows * cols, (rows // 2) * (cols // 2)
+    return 2 * px + 2 * spx + 2 * 16 * spx + 2 * 4 * px
+
+
+def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_baseline):
+    """LSD + LBD extraction (line_extractor.cc:88-160) of `batch` frames per step, device-resident; frames shard over
+    ranks with no collective."""
+    import torch
+    import torch.distributed as dist
+    from plpslam_b200.tracking import DeviceBuffer
+    lib = pkg.lib()
+    frames = build_line_frames(batch, seed + 1000 * rank)
+    trk = pkg.LineFeatureTracker(ctx, ROWS, COLS, max_batch=batch)
+    cap = trk.capacity
+    d_imgs = DeviceBuffer.from_array(ctx, frames)
+    d_kl = DeviceBuffer(ctx, batch * cap * pkg.KEYLINE_DTYPE.itemsize)
+    d_lbd = DeviceBuffer(ctx, batch * cap * 32)
+    d_fn = DeviceBuffer(ctx, batch * cap * 24)
+    d_n = DeviceBuffer(ctx, batch * 4)
+    d_st = DeviceBuffer(ctx, batch * 4)
+
+    def step():
+        ctx._check(lib.plp_line_extract_batch_dev(trk.handle, d_imgs.ptr, C.c_int(batch), C.c_size_t(COLS), d_kl.ptr,
+                                                  d_lbd.ptr, d_fn.ptr, d_n.ptr, d_st.ptr))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=torch.cuda.current_device())
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    n = d_n.download(np.int32, (batch,))
+    st = d_st.download(np.int32, (batch,))
+    assert not st.any(), "line extraction capacity overflow"
+    # e2e: pinned host frames in, keylines / descriptors / line functions out, through the host entry point
+    kl = np.zeros((batch, cap), pkg.KEYLINE_DTYPE)
+    lbd = np.zeros((batch, cap, 32), np.uint8)
+    fn = np.zeros((batch, cap, 3), np.float64)
+    nn = np.zeros(batch, np.int32)
+
+    def e2e_step():
+        ctx._check(lib.plp_line_extract_batch(trk.handle, frames.ctypes.data_as(C.c_void_p), C.c_int(batch),
+                                              C.c_size_t(COLS), kl.ctypes.data_as(C.c_void_p), lbd.ctypes.data_as(C.c_void_p),
+                                              fn.ctypes.data_as(C.c_void_p), nn.ctypes.data_as(C.c_void_p)))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(2, steps // 3)):
+        e2e_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / max(2, steps // 3)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=torch.cuda.current_device())
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    # per-kernel shares
+    ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 1))
+    for _ in range(min(steps, 3)):
+        step()
+    buf = C.create_string_buffer(1 << 16)
+    ctx._check(lib.plp_ctx_kernel_timing_report(ctx.handle, buf, C.c_size_t(len(buf))))
+    ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 0))
+    kt = json.loads(buf.value.decode())
+    tot = sum(v["total_ms"] for v in kt.values())
+    shares = {k: round(v["total_ms"] / tot, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["total_ms"])}
+    per_launch = {k: round(v["total_ms"] / v["count"], 4) for k, v in kt.items()}
+    peak, _ = _peaks()
+    alg = line_alg_bytes(ROWS, COLS) * batch
+    res = {"metric": "frames_per_sec_lsd_lbd_extract", "value": world * batch * steps / (ms * 1e-3), "unit": "frames/s",
+           "ms_per_step": ms / steps, "scaling": "weak",
+           "config": {"workload": "LSD (refine 1, scale 0.5) + LBD line extraction, 640x480, lines >= 60 px kept",
+                      "frames_per_step_per_gpu": batch, "mean_keylines_per_frame": float(n.mean()),
+                      "l2": "per-step working set (3.8 MB/frame of intermediates) larger than L2"},
+           "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
+                   "d2h_bytes_per_step": int(kl.nbytes + lbd.nbytes + fn.nbytes + nn.nbytes)},
+           "gpu_launches": int(launches), "kernel_time_shares": shares, "ms_per_launch": per_launch,
+           "algorithmic_bytes_per_step": alg, "hbm_roofline_frac": alg / (ms / steps * 1e-3) / 1e9 / peak}
+    if cpu_baseline and rank == 0:
+        import oracle_api
+        orc = oracle_api.Oracle()
+        cores = os.cpu_count() or 1
+        ns = int(min(batch, max(32, 2 * cores)))
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            list(ex.map(lambda b: orc.line_extract(frames[b]), range(ns)))
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        for b in range(8):
+            orc.line_extract(frames[b])
+        d1 = time.perf_counter() - t1
+        res["cpu_baseline"] = {"value": ns / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+                               "sample": f"{ns} frames over {cores} host threads ({dt:.2f} s)",
+                               "single_thread_value": 8 / d1}
+    trk.close()
+    for d in (d_imgs, d_kl, d_lbd, d_fn, d_n, d_st):
+        d.free()
+    return res
+
+
 def bench_ba(pkg, ctx, stream, rank, world, steps, warmup):
     """Second BASELINE metric: local-BA LM iterations/s on config 4 (20 local + 10 fixed KF, 4000 points + 800 lines
     + 200 plane-owned points, ~29 k edges), landmark-sharded over `world` GPUs with one NCCL all-reduce of the packed
@@ -317,6 +451,9 @@ def main():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true", help="skip the local-BA metric")
+    ap.add_argument("--no-lines", action="store_true", help="skip the LSD+LBD line front-end metric")
+    ap.add_argument("--only-lines", action="store_true", help="development: run only the line front-end leg")
+    ap.add_argument("--line-batch", type=int, default=512, help="frames per step per GPU of the line front-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -337,8 +474,14 @@ def main():
     ctx = pkg.Context(local_rank)
     lib = pkg.lib()
     B = args.batch
-    fe, frames, aux = setup_front_end(pkg, ctx, B, args.seed + 1000 * rank)
     stream = torch.cuda.ExternalStream(lib.plp_ctx_stream(ctx.handle), device=f"cuda:{local_rank}")
+    if args.only_lines:
+        r = bench_lines(pkg, ctx, stream, rank, world, args.steps, args.warmup, args.line_batch, args.seed,
+                        world == 1 and not args.no_cpu_baseline)
+        if rank == 0:
+            print(json.dumps(r))
+        return
+    fe, frames, aux = setup_front_end(pkg, ctx, B, args.seed + 1000 * rank)
 
     def barrier():
         ctx.sync()
@@ -426,6 +569,11 @@ def main():
     if not args.no_ba:
         ba_res = bench_ba(pkg, ctx, stream, rank, world, steps=max(args.steps, 5), warmup=args.warmup)
 
+    lines_res = None
+    if not args.no_lines:
+        lines_res = bench_lines(pkg, ctx, stream, rank, world, args.steps, args.warmup, args.line_batch, args.seed,
+                                world == 1 and not args.no_cpu_baseline)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -453,6 +601,8 @@ def main():
             if world == 1 and not args.no_cpu_baseline:
                 ba_res["cpu_baseline"] = bench_ba_cpu()
             line["local_ba"] = ba_res
+        if lines_res is not None:
+            line["line_frontend"] = lines_res
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

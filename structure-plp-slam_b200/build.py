@@ -48,7 +48,7 @@ def _stamp(src: Path, flags) -> str:
 
 
 def _compile(src: Path, verbose: bool) -> Path:
-    flags = ARCH + COMMON + FILE_FLAGS.get(src.name, [])
+    flags = ARCH + COMMON + FILE_FLAGS.get(src.name, []) + os.environ.get("PLP_EXTRA_NVCC_FLAGS", "").split()
     obj = OBJ / (src.stem + ".o")
     stamp_file = OBJ / (src.stem + ".stamp")
     stamp = _stamp(src, flags)

@@ -30,13 +30,10 @@ using namespace plp;
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr uint32_t kUsed = 0x80000000u;
-constexpr uint32_t kNotDef = 0xffffffffu;
 constexpr double kDegToRads = 0.017453292519943295769236907684;
 constexpr double kPi = 3.14159265358979323846;
 constexpr double k3_2Pi = 4.71238898038;  // literals of lsd.cpp
 constexpr double k2Pi = 6.28318530718;
-constexpr int kRing = 2048;       // BFS queue window kept in shared memory (entries)
 constexpr int kBins = 1024;
 constexpr int kSortWarps = 32;
 constexpr int kBands = 9, kBandWidth = 7, kLspHeight = kBands * kBandWidth;
@@ -51,13 +48,11 @@ struct LineDev {
     const uint8_t *img;
     size_t img_step, img_frame_stride;
     uint8_t *scaled;     // npx
-    uint4 *rec;          // npx x {angle bits | used flag, cos bits, sin bits, gx^2+gy^2}
-    int *kmax;           // per frame: max gx^2+gy^2 over defined pixels
+    const float4 *cstab; // (2*510+1)^2 x {deg, cos, sin} by (gx, gy), shared by all frames
+    int kthr;            // level-line angle defined  <=>  gx^2+gy^2 > kthr  (norm > rho)
     uint32_t *order;     // npx packed (y<<16|x) seeds, bin desc / raster asc
     int *nseeds;
-    uint32_t *reg_xy;    // npx region list
-    int *reg_k;
-    uint32_t *reg_a;
+    uint32_t *reg_xy;    // npx: region entries beyond the shared-memory window
     float4 *segs;        // seg_cap
     int *nseg;
     short2 *grad;        // w*h Sobel (dx, dy) of the 5x5-blurred frame
@@ -82,16 +77,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale, p5 = 0.1555786518463281f * scale,
                 p7 = -0.04432655554792128f * scale;
     const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-    if (ax >= ay) {
-        c = ay / (ax + 2.220446049250313e-16f);
-        c2 = c * c;
-        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
-    } else {
-        c = ax / (ay + 2.220446049250313e-16f);
-        c2 = c * c;
-        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
-    }
+    // branch-free form of `if (ax >= ay) c = ay / (ax + eps) else c = ax / (ay + eps)`: one division for all lanes
+    const bool steep = !(ax >= ay);
+    const float mn = steep ? ax : ay, mx = steep ? ay : ax;
+    const float c = mn / (mx + 2.220446049250313e-16f);
+    const float c2 = c * c;
+    float a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    if (steep) a = 90.f - a;
     if (x < 0) a = 180.f - a;
     if (y < 0) a = 360.f - a;
     return a;
@@ -143,66 +135,66 @@ __global__ void __launch_bounds__(256) lsd_scale_kernel(LineDev D) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K2: ll_angle: 2x2 gradient, level-line angle (cv::fastAtan2, degrees) or NOTDEF, cos/sin of the angle for the region
-//     angle accumulation, squared gradient norm; per-frame maximum.
+// ll_angle helpers.  The level-line field is never materialised: every consumer recomputes the 2x2 gradient from the
+// half-resolution image (4 byte reads), which is what lets one frame's working set (image + `used` bitmap) live in
+// shared memory.  (gx, gy) in [-510, 510]^2 determines the angle, hence cos/sin come from a table indexed by (gx, gy)
+// that is built once per handle and shared by every frame (8.3 MB, L2 resident).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lsd_gradient_kernel(LineDev D) {
-    const int b = blockIdx.y;
+constexpr int kGRange = 510, kGDim = 2 * kGRange + 1;
+
+__device__ __forceinline__ void grad_at(const uint8_t *img, int sw, int idx, int &gx, int &gy) {
+    const int a = img[idx], bq = img[idx + 1], c = img[idx + sw], d = img[idx + sw + 1];
+    const int DA = d - a, BC = bq - c;
+    gx = DA + BC;
+    gy = DA - BC;
+}
+
+// table entry: level-line angle in degrees (cv::fastAtan2(gx, -gy)) and cos / sin of float(angle) as lsd.cpp
+// accumulates them: `sumdx += cos(float(angle))`
+__global__ void __launch_bounds__(256) lsd_cs_table_kernel(float4 *tab) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int kloc = 0;
-    if (i < D.npx) {
-        const int y = i / D.sw, x = i - y * D.sw;
-        uint4 r = make_uint4(kNotDef, 0, 0, 0);
-        if (x < D.sw - 1 && y < D.sh - 1) {
-            const uint8_t *s = D.scaled + (size_t)b * D.npx + i;
-            const int DA = (int)s[D.sw + 1] - (int)s[0];
-            const int BC = (int)s[1] - (int)s[D.sw];
-            const int gx = DA + BC, gy = DA - BC;
-            const int k = gx * gx + gy * gy;
-            r.w = (uint32_t)k;
-            const double norm = sqrt((double)k / 4.0);
-            if (!(norm <= D.rho)) {
-                const float deg = fast_atan2_deg((float)gx, (float)-gy);
-                r.x = __float_as_uint(deg);  // >= 0: the sign bit is free for the `used` flag
-                const double a = (double)deg * kDegToRads;
-                const float af = (float)a;  // lsd.cpp: cos(float(angle)), evaluated in double, stored to float
-                r.y = __float_as_uint((float)det_cos((double)af));
-                r.z = __float_as_uint((float)det_sin((double)af));
-                kloc = k;
-            }
-        }
-        D.rec[(size_t)b * D.npx + i] = r;
-    }
-    // block max -> one atomic
-    for (int off = 16; off >= 1; off >>= 1) kloc = max(kloc, __shfl_xor_sync(kFull, kloc, off));
-    __shared__ int s_max[8];
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = kloc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int m = 0;
-        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) m = max(m, s_max[wv]);
-        if (m > 0) atomicMax(&D.kmax[b], m);
-    }
+    if (i >= kGDim * kGDim) return;
+    const int gy = i / kGDim - kGRange, gx = i - (gy + kGRange) * kGDim - kGRange;
+    const float deg = fast_atan2_deg((float)gx, (float)-gy);
+    const double a = (double)deg * kDegToRads;
+    const float af = (float)a;
+    tab[i] = make_float4(deg, (float)det_cos((double)af), (float)det_sin((double)af), 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // K3: pseudo-ordering of the seeds: bin = int(modgrad * 1023 / max_grad), descending bins, raster order inside a bin.
-//     One CTA (32 warps) per frame: each warp owns a contiguous raster range -> per-warp histograms, a scan over
-//     (bin desc, warp asc), then a stable scatter with __match_any ranks.
+//     One CTA (32 warps) per frame: frame maximum, then each warp owns a contiguous raster range -> per-warp
+//     histograms, a scan over (bin desc, warp asc), and a stable scatter with __match_any ranks.
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int seed_k(const uint8_t *img, int sw, int sh, int i, int kthr) {
+    const int y = i / sw, x = i - y * sw;
+    if (x >= sw - 1 || y >= sh - 1) return -1;
+    int gx, gy;
+    grad_at(img, sw, i, gx, gy);
+    const int k = gx * gx + gy * gy;
+    return k > kthr ? k : -1;  // norm <= rho  <=>  k <= kthr
+}
+
 __global__ void __launch_bounds__(kSortWarps * 32) lsd_sort_kernel(LineDev D) {
     extern __shared__ uint32_t s_dyn[];
     uint32_t *hist = s_dyn;                        // [kSortWarps][kBins]: counts, then running start offsets
     uint32_t *base = s_dyn + kSortWarps * kBins;   // [kBins] first output slot of each bin
     __shared__ uint32_t s_scan[kBins];
     __shared__ uint32_t s_warp_tot[32];
+    __shared__ int s_kmax[32];
     const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint4 *rec = D.rec + (size_t)b * D.npx;
-    const int kmax = D.kmax[b];
-    const double max_grad = kmax > 0 ? sqrt((double)kmax / 4.0) : -1.0;
-    const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
+    const uint8_t *img = D.scaled + (size_t)b * D.npx;
+    // frame maximum of the squared norm over the defined pixels
+    int kloc = 0;
+    for (int i = threadIdx.x; i < D.npx; i += blockDim.x) kloc = max(kloc, seed_k(img, D.sw, D.sh, i, D.kthr));
+    for (int off = 16; off >= 1; off >>= 1) kloc = max(kloc, __shfl_xor_sync(kFull, kloc, off));
+    if (lane == 0) s_kmax[wid] = kloc;
     for (int i = threadIdx.x; i < kSortWarps * kBins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
+    int kmax = 0;
+    for (int wv = 0; wv < kSortWarps; ++wv) kmax = max(kmax, s_kmax[wv]);
+    const double max_grad = kmax > 0 ? sqrt((double)kmax / 4.0) : -1.0;
+    const double bin_coef = (max_grad > 0) ? (double)(kBins - 1) / max_grad : 0.0;
     const int per_warp = ((D.npx + kSortWarps * 32 - 1) / (kSortWarps * 32)) * 32;
     const int beg = wid * per_warp, end = min(beg + per_warp, D.npx);
     uint32_t *myhist = hist + wid * kBins;
@@ -211,8 +203,8 @@ __global__ void __launch_bounds__(kSortWarps * 32) lsd_sort_kernel(LineDev D) {
         const int i = i0 + lane;
         int bin = -1;
         if (i < end) {
-            const uint4 r = rec[i];
-            if (r.x != kNotDef) bin = (int)(sqrt((double)(int)r.w / 4.0) * bin_coef);
+            const int k = seed_k(img, D.sw, D.sh, i, D.kthr);
+            if (k >= 0) bin = (int)(sqrt((double)k / 4.0) * bin_coef);
         }
         const unsigned act = __ballot_sync(kFull, bin >= 0);
         if (bin >= 0) {
@@ -264,8 +256,8 @@ __global__ void __launch_bounds__(kSortWarps * 32) lsd_sort_kernel(LineDev D) {
         const int i = i0 + lane;
         int bin = -1;
         if (i < end) {
-            const uint4 r = rec[i];
-            if (r.x != kNotDef) bin = (int)(sqrt((double)(int)r.w / 4.0) * bin_coef);
+            const int k = seed_k(img, D.sw, D.sh, i, D.kthr);
+            if (k >= 0) bin = (int)(sqrt((double)k / 4.0) * bin_coef);
         }
         const unsigned act = __ballot_sync(kFull, bin >= 0);
         if (bin >= 0) {
@@ -282,21 +274,33 @@ __global__ void __launch_bounds__(kSortWarps * 32) lsd_sort_kernel(LineDev D) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K4: region growing + rectangle + refinement: one warp per frame
+// K4: region growing + rectangle + refinement: one warp per frame; half-resolution image, `used` bitmap and the region
+//     list (= BFS queue) in shared memory.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kRegCap = 6144;  // region entries kept in shared memory; longer regions spill to global memory
+
 struct Rect {
     double x1, y1, x2, y2, width;
 };
 
 struct Grow {  // per-warp state
-    int sw, sh;
+    int sw, sh, kthr;
     double density_th;
-    uint4 *rec;
-    uint32_t *rxy;
-    int *rk;
-    uint32_t *ra;
-    uint32_t *ring;
+    const uint8_t *img;    // shared: half-resolution image
+    uint32_t *used;        // shared: bitmap
+    uint32_t *reg;         // shared: first kRegCap region entries (packed y<<16|x)
+    uint32_t *reg_ovf;     // global: all entries beyond kRegCap (indexed by absolute position)
+    const float4 *tab;     // global: {deg, cos, sin} by (gx, gy)
     int lane;
+#ifdef PLP_LSD_PROF
+    long long *pc;         // [0] iterations [1] rounds [2] cycles load phase [3] cycles resolve phase [4] on-demand loads
+#endif
+    __device__ __forceinline__ uint32_t get(int e) const { return e < kRegCap ? reg[e] : reg_ovf[e]; }
+    __device__ __forceinline__ void put(int e, uint32_t v) const {
+        if (e < kRegCap) reg[e] = v;
+        else reg_ovf[e] = v;
+    }
+    __device__ __forceinline__ bool is_used(int idx) const { return (used[idx >> 5] >> (idx & 31)) & 1u; }
 };
 
 __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) {
@@ -322,67 +326,112 @@ __device__ __forceinline__ double warp_min(double p) {
     return p;
 }
 
-// lsd.cpp region_grow.  Returns the region size; the region lives in G.rxy / G.rk / G.ra.
-__device__ int region_grow(const Grow &G, uint32_t seed_xy, uint32_t seed_abits, int seed_k, double prec,
-                           double &reg_angle_out) {
-    const int sw = G.sw, sh = G.sh, lane = G.lane;
-    double reg_angle = (double)__uint_as_float(seed_abits) * kDegToRads;
+// immutable data of one neighbour pixel (does not depend on the `used` map)
+struct Nb {
+    int nidx;     // -1: outside / no gradient defined
+    uint32_t xy;
+    float4 t;     // {deg, cos, sin}
+};
+
+// neighbour jj (0..7, centre skipped) of queue entry e
+__device__ __forceinline__ Nb load_nb(const Grow &G, int e, int ddx, int ddy) {
+    Nb r;
+    r.nidx = -1;
+    r.xy = 0;
+    r.t = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t pxy = G.get(e);
+    const int nx = (int)(pxy & 0xffff) + ddx, ny = (int)(pxy >> 16) + ddy;
+    // the last row / column carry no gradient (NOTDEF)
+    if (nx >= 0 && nx < G.sw - 1 && ny >= 0 && ny < G.sh - 1) {
+        const int idx = ny * G.sw + nx;
+        int gx, gy;
+        grad_at(G.img, G.sw, idx, gx, gy);
+        if (gx * gx + gy * gy > G.kthr) {
+            r.nidx = idx;
+            r.xy = ((uint32_t)ny << 16) | (uint32_t)nx;
+            r.t = G.tab[(gy + kGRange) * kGDim + gx + kGRange];
+        }
+    }
+    return r;
+}
+
+// lsd.cpp region_grow.  Returns the region size; the region list lives in G.reg (+ overflow).
+// 32 lanes = 4 queue entries x 8 neighbours, in the scalar visiting order (entry, then yy, then xx).  The immutable data
+// of the next four entries is fetched while the current four are resolved; every candidate lane keeps the region sums
+// and angle it WOULD produce if it were accepted next, so an acceptance is one shuffle away.
+__device__ int region_grow(const Grow &G, uint32_t seed_xy, float seed_deg, double prec, double &reg_angle_out) {
+    const int sw = G.sw, lane = G.lane;
+    double reg_angle = (double)seed_deg * kDegToRads;
     float sumdx = (float)det_cos(reg_angle);
     float sumdy = (float)det_sin(reg_angle);
     if (lane == 0) {
-        const int sx = seed_xy & 0xffff, sy = seed_xy >> 16;
-        G.rec[sy * sw + sx].x = seed_abits | kUsed;
-        G.rxy[0] = seed_xy;
-        G.rk[0] = seed_k;
-        G.ra[0] = seed_abits;
-        G.ring[0] = seed_xy;
+        const int sidx = (int)(seed_xy >> 16) * sw + (int)(seed_xy & 0xffff);
+        G.used[sidx >> 5] |= 1u << (sidx & 31);
+        G.reg[0] = seed_xy;
     }
     __syncwarp();
     int n = 1, i = 0;
-    const int g = lane / 9, j = lane - 9 * g;
+    const int g = lane >> 3, jj = lane & 7;
+    const int j = jj + (jj >= 4);  // skip the centre
     const int ddx = j % 3 - 1, ddy = j / 3 - 1;
+    Nb cur;
+    cur.nidx = -1;
+    cur.xy = 0;
+    cur.t = make_float4(0.f, 0.f, 0.f, 0.f);
+    int loaded = 0;  // groups of `cur` that hold valid data
     while (i < n) {
-        const int take = min(3, n - i);
-        const bool valid = (lane < 27) && (g < take) && (j != 4);
-        int nx = 0, ny = 0, nidx = 0;
-        uint4 r = make_uint4(kNotDef, 0, 0, 0);
-        bool cand = false;
-        if (valid) {
-            const int pi = i + g;
-            const uint32_t pxy = (n - pi <= kRing) ? G.ring[pi & (kRing - 1)] : G.rxy[pi];
-            nx = (int)(pxy & 0xffff) + ddx;
-            ny = (int)(pxy >> 16) + ddy;
-            if (nx >= 0 && nx < sw && ny >= 0 && ny < sh) {
-                nidx = ny * sw + nx;
-                r = G.rec[nidx];
-                cand = !(r.x & kUsed);
-            }
-        }
-        const double a = (double)__uint_as_float(r.x) * kDegToRads;
+        const int take = min(4, n - i);
+#ifdef PLP_LSD_PROF
+        const long long tl0 = clock64();
+        G.pc[0]++;
+        if (loaded < take) G.pc[4]++;
+#endif
+        if (g >= loaded && g < take) cur = load_nb(G, i + g, ddx, ddy);  // entries that were not known one round ago
+        // prefetch the entries already known for the next round
+        const int nxt_avail = min(4, n - (i + take));
+        Nb nxt;
+        nxt.nidx = -1;
+        nxt.xy = 0;
+        nxt.t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < nxt_avail) nxt = load_nb(G, i + take + g, ddx, ddy);
+        // resolve the current entries
+#ifdef PLP_LSD_PROF
+        const long long tl1 = clock64();
+        G.pc[2] += tl1 - tl0;
+#endif
+        bool cand = (g < take) && (cur.nidx >= 0) && !G.is_used(cur.nidx);
+        const double a = (double)cur.t.x * kDegToRads;
+        float my_sdx = sumdx + cur.t.y, my_sdy = sumdy + cur.t.z;
+        double my_theta = (double)fast_atan2_deg(my_sdy, my_sdx) * kDegToRads;
         for (;;) {
             const bool al = cand && is_aligned(a, reg_angle, prec);
             const unsigned m = __ballot_sync(kFull, al);
             if (!m) break;
+#ifdef PLP_LSD_PROF
+            G.pc[1]++;
+#endif
             const int l = __ffs(m) - 1;
-            const float c = __shfl_sync(kFull, __uint_as_float(r.y), l);
-            const float s = __shfl_sync(kFull, __uint_as_float(r.z), l);
-            const int q = __shfl_sync(kFull, nidx, l);
-            sumdx += c;
-            sumdy += s;
-            reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRads;
+            sumdx = __shfl_sync(kFull, my_sdx, l);
+            sumdy = __shfl_sync(kFull, my_sdy, l);
+            reg_angle = __shfl_sync(kFull, my_theta, l);
+            const int q = __shfl_sync(kFull, cur.nidx, l);
             if (lane == l) {
-                G.rec[nidx].x = r.x | kUsed;
-                const uint32_t xy = ((uint32_t)ny << 16) | (uint32_t)nx;
-                G.rxy[n] = xy;
-                G.rk[n] = (int)r.w;
-                G.ra[n] = r.x;
-                G.ring[n & (kRing - 1)] = xy;
+                G.used[cur.nidx >> 5] |= 1u << (cur.nidx & 31);
+                G.put(n, cur.xy);
             }
             ++n;
-            cand = cand && (lane > l) && (nidx != q);
+            cand = cand && (lane > l) && (cur.nidx != q);
+            my_sdx = sumdx + cur.t.y;
+            my_sdy = sumdy + cur.t.z;
+            my_theta = (double)fast_atan2_deg(my_sdy, my_sdx) * kDegToRads;
         }
         __syncwarp();
+#ifdef PLP_LSD_PROF
+        G.pc[3] += clock64() - tl1;
+#endif
         i += take;
+        cur = nxt;
+        loaded = nxt_avail;
     }
     reg_angle_out = reg_angle;
     return n;
@@ -397,14 +446,20 @@ __device__ __forceinline__ double angle_diff_signed(double a, double b) {
 __device__ __forceinline__ double dist2(double x1, double y1, double x2, double y2) {
     return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);
 }
+// modgrad of a region pixel, recomputed from the image
+__device__ __forceinline__ double px_weight(const Grow &G, uint32_t xy) {
+    int gx, gy;
+    grad_at(G.img, G.sw, (int)(xy >> 16) * G.sw + (int)(xy & 0xffff), gx, gy);
+    return sqrt((double)(gx * gx + gy * gy) / 4.0);
+}
 
 // lsd.cpp region2rect + get_theta
 __device__ void region2rect(const Grow &G, int n, double reg_angle, double prec, Rect &R) {
     const int lane = G.lane;
     double sx = 0, sy = 0, ss = 0;
     for (int i = lane; i < n; i += 32) {
-        const uint32_t xy = G.rxy[i];
-        const double wgt = sqrt((double)G.rk[i] / 4.0);
+        const uint32_t xy = G.get(i);
+        const double wgt = px_weight(G, xy);
         sx += (double)(int)(xy & 0xffff) * wgt;
         sy += (double)(int)(xy >> 16) * wgt;
         ss += wgt;
@@ -415,8 +470,8 @@ __device__ void region2rect(const Grow &G, int n, double reg_angle, double prec,
     const double x = sx / ss, y = sy / ss;
     double ixx = 0, iyy = 0, ixy = 0;
     for (int i = lane; i < n; i += 32) {
-        const uint32_t xy = G.rxy[i];
-        const double wgt = sqrt((double)G.rk[i] / 4.0);
+        const uint32_t xy = G.get(i);
+        const double wgt = px_weight(G, xy);
         const double dx = (double)(int)(xy & 0xffff) - x, dy = (double)(int)(xy >> 16) - y;
         ixx += dy * dy * wgt;
         iyy += dx * dx * wgt;
@@ -431,7 +486,7 @@ __device__ void region2rect(const Grow &G, int n, double reg_angle, double prec,
     const double dx = det_cos(theta), dy = det_sin(theta);
     double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
     for (int i = lane; i < n; i += 32) {
-        const uint32_t xy = G.rxy[i];
+        const uint32_t xy = G.get(i);
         const double rdx = (double)(int)(xy & 0xffff) - x, rdy = (double)(int)(xy >> 16) - y;
         const double l = rdx * dx + rdy * dy;
         const double wv = -rdx * dy + rdy * dx;
@@ -457,23 +512,25 @@ __device__ __forceinline__ double rect_density(int n, const Rect &R) {
 }
 
 // lsd.cpp refine + reduce_region_radius; n is updated; returns false when the region is rejected
-__device__ bool refine(const Grow &G, int &n, double reg_angle, double prec, Rect &R) {
+__device__ bool refine(const Grow &G, int &n, float seed_deg, double reg_angle, double prec, Rect &R) {
     const int lane = G.lane, sw = G.sw;
     double density = rect_density(n, R);
     if (density >= G.density_th) return true;
-    const uint32_t seed_xy = G.rxy[0], seed_a = G.ra[0];
-    const int seed_k = G.rk[0];
+    const uint32_t seed_xy = G.reg[0];
     const double xc = (double)(int)(seed_xy & 0xffff), yc = (double)(int)(seed_xy >> 16);
-    const double ang_c = (double)__uint_as_float(seed_a) * kDegToRads;
+    const double ang_c = (double)seed_deg * kDegToRads;
     double sum = 0, s_sum = 0;
     int cnt = 0;
     for (int i = lane; i < n; i += 32) {
-        const uint32_t xy = G.rxy[i];
+        const uint32_t xy = G.get(i);
         const int px = xy & 0xffff, py = xy >> 16;
-        const uint32_t ab = G.ra[i];
-        G.rec[py * sw + px].x = ab;  // NOTUSED again
+        const int pidx = py * sw + px;
+        atomicAnd(&G.used[pidx >> 5], ~(1u << (pidx & 31)));  // NOTUSED again
         if (sqrt(dist2(xc, yc, (double)px, (double)py)) < R.width) {
-            const double d = angle_diff_signed((double)__uint_as_float(ab) * kDegToRads, ang_c);
+            int gx, gy;
+            grad_at(G.img, sw, pidx, gx, gy);
+            const double ang = (double)fast_atan2_deg((float)gx, (float)-gy) * kDegToRads;
+            const double d = angle_diff_signed(ang, ang_c);
             sum += d;
             s_sum += d * d;
             ++cnt;
@@ -485,7 +542,7 @@ __device__ bool refine(const Grow &G, int &n, double reg_angle, double prec, Rec
     const double mean_angle = sum / (double)cnt;
     const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
     __syncwarp();
-    n = region_grow(G, seed_xy, seed_a, seed_k, tau, reg_angle);
+    n = region_grow(G, seed_xy, seed_deg, tau, reg_angle);
     if (n < 2) return false;
     region2rect(G, n, reg_angle, prec, R);
     density = rect_density(n, R);
@@ -498,25 +555,20 @@ __device__ bool refine(const Grow &G, int &n, double reg_angle, double prec, Rec
         int o = 0;
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + lane;
-            uint32_t xy = 0, ab = 0;
-            int kk = 0;
+            uint32_t xy = 0;
             bool keep = false;
             if (i < n) {
-                xy = G.rxy[i];
-                kk = G.rk[i];
-                ab = G.ra[i];
+                xy = G.get(i);
                 const int px = xy & 0xffff, py = xy >> 16;
                 keep = !(dist2(xc, yc, (double)px, (double)py) > rad_sq);
-                if (!keep) G.rec[py * sw + px].x = ab;
+                if (!keep) {
+                    const int pidx = py * sw + px;
+                    atomicAnd(&G.used[pidx >> 5], ~(1u << (pidx & 31)));
+                }
             }
             const unsigned km = __ballot_sync(kFull, keep);
             __syncwarp();
-            if (keep) {
-                const int pos = o + __popc(km & ((1u << lane) - 1));
-                G.rxy[pos] = xy;
-                G.rk[pos] = kk;
-                G.ra[pos] = ab;
-            }
+            if (keep) G.put(o + __popc(km & ((1u << lane) - 1)), xy);
             o += __popc(km);
             __syncwarp();
         }
@@ -528,18 +580,54 @@ __device__ bool refine(const Grow &G, int &n, double reg_angle, double prec, Rec
     return true;
 }
 
+#ifdef PLP_LSD_PROF
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, t0) prof[slot] += clock64() - (t0)
+#else
+#define PROF_T(var)
+#define PROF_ADD(slot, t0)
+#endif
+
 __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
-    __shared__ uint32_t s_ring[kRing];
+    extern __shared__ uint4 s_grow[];
+#ifdef PLP_LSD_PROF
+    long long prof[6] = {0, 0, 0, 0, 0, 0};
+    long long cnt_regions = 0, cnt_px = 0, cnt_refine = 0;
+    __shared__ long long s_pc[8];
+    for (int q = 0; q < 8; ++q) s_pc[q] = 0;
+    const long long t_start = clock64();
+#endif
+    uint8_t *s_img = reinterpret_cast<uint8_t *>(s_grow);
+    const int img_bytes = (D.npx + 15) & ~15;
+    uint32_t *s_used = reinterpret_cast<uint32_t *>(s_img + img_bytes);
+    const int used_words = (D.npx + 31) >> 5;
+    uint32_t *s_reg = s_used + ((used_words + 3) & ~3);
     const int b = blockIdx.x, lane = threadIdx.x;
+    {  // stage the frame: the allocation is padded to 16 bytes per frame? no: copy bytes with 4-byte words where aligned
+        const uint8_t *src = D.scaled + (size_t)b * D.npx;
+        if (((size_t)src & 15) == 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            for (int i = lane; i < D.npx / 16; i += 32) s_grow[i] = s4[i];
+            for (int i = (D.npx / 16) * 16 + lane; i < D.npx; i += 32) s_img[i] = src[i];
+        } else {
+            for (int i = lane; i < D.npx; i += 32) s_img[i] = src[i];
+        }
+        for (int i = lane; i < used_words; i += 32) s_used[i] = 0;
+    }
+    __syncwarp();
     Grow G;
     G.sw = D.sw;
     G.sh = D.sh;
+    G.kthr = D.kthr;
     G.density_th = D.density_th;
-    G.rec = D.rec + (size_t)b * D.npx;
-    G.rxy = D.reg_xy + (size_t)b * D.npx;
-    G.rk = D.reg_k + (size_t)b * D.npx;
-    G.ra = D.reg_a + (size_t)b * D.npx;
-    G.ring = s_ring;
+    G.img = s_img;
+    G.used = s_used;
+    G.reg = s_reg;
+    G.reg_ovf = D.reg_xy + (size_t)b * D.npx;
+    G.tab = D.cstab;
+#ifdef PLP_LSD_PROF
+    G.pc = s_pc;
+#endif
     G.lane = lane;
     const uint32_t *order = D.order + (size_t)b * D.npx;
     float4 *segs = D.segs + (size_t)b * D.seg_cap;
@@ -550,19 +638,34 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
         const int s = s0 + lane;
         const uint32_t oxy = s < nseeds ? order[s] : 0;
         const int oidx = (int)(oxy >> 16) * sw + (int)(oxy & 0xffff);
-        uint32_t v = s < nseeds ? G.rec[oidx].x : kNotDef;
-        unsigned m = __ballot_sync(kFull, !(v & kUsed));
+        unsigned m = __ballot_sync(kFull, s < nseeds && !((s_used[oidx >> 5] >> (oidx & 31)) & 1u));
         while (m) {
             const int l = __ffs(m) - 1;
             const uint32_t seed_xy = __shfl_sync(kFull, oxy, l);
             const int sidx = __shfl_sync(kFull, oidx, l);
-            const uint4 sr = G.rec[sidx];
+            int gx, gy;
+            grad_at(s_img, sw, sidx, gx, gy);
+            const float seed_deg = fast_atan2_deg((float)gx, (float)-gy);
             double reg_angle;
-            int n = region_grow(G, seed_xy, sr.x, (int)sr.w, D.prec, reg_angle);
+            PROF_T(t0);
+            int n = region_grow(G, seed_xy, seed_deg, D.prec, reg_angle);
+            PROF_ADD(0, t0);
+#ifdef PLP_LSD_PROF
+            cnt_regions++;
+            cnt_px += n;
+#endif
             if (n >= D.min_reg_size) {
                 Rect R;
+                PROF_T(t1);
                 region2rect(G, n, reg_angle, D.prec, R);
-                if (refine(G, n, reg_angle, D.prec, R)) {
+                PROF_ADD(1, t1);
+                PROF_T(t2);
+                const bool okr = refine(G, n, seed_deg, reg_angle, D.prec, R);
+                PROF_ADD(2, t2);
+#ifdef PLP_LSD_PROF
+                cnt_refine++;
+#endif
+                if (okr) {
                     if (nseg < D.seg_cap) {
                         if (lane == 0) {
                             // + 0.5 offset, then / scale (0.5)
@@ -576,11 +679,15 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
                 }
             }
             __syncwarp();
-            v = s < nseeds ? G.rec[oidx].x : kNotDef;
-            m = __ballot_sync(kFull, !(v & kUsed)) & ~((2u << l) - 1u);
+            m = __ballot_sync(kFull, s < nseeds && !((s_used[oidx >> 5] >> (oidx & 31)) & 1u)) & ~((2u << l) - 1u);
         }
     }
     if (lane == 0) D.nseg[b] = min(nseg, D.seg_cap);
+#ifdef PLP_LSD_PROF
+    if (lane == 0 && b == 0)
+        printf("[lsd prof] total %lld grow %lld rect %lld refine %lld | seeds %d regions %lld px %lld big %lld segs %d | iters %lld rounds %lld load-cyc %lld resolve-cyc %lld ondemand %lld\n",
+               clock64() - t_start, prof[0], prof[1], prof[2], nseeds, cnt_regions, cnt_px, cnt_refine, nseg, s_pc[0], s_pc[1], s_pc[2], s_pc[3], s_pc[4]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -851,7 +958,8 @@ struct plp_line {
     uint8_t *d_lbd = nullptr;
     double *d_fn = nullptr;
     int32_t *d_n = nullptr;
-    size_t sort_smem = 0;
+    size_t sort_smem = 0, grow_smem = 0;
+    float4 *d_cstab = nullptr;
     std::vector<void *> owned;
 };
 
@@ -878,17 +986,12 @@ static plp_status line_run(plp_line *h, const uint8_t *d_imgs, int batch, size_t
     if (d_status) D.status = d_status;
     h->last_batch = batch;
     PLP_CUDA_TRY(cudaMemsetAsync(D.status, 0, (size_t)batch * sizeof(int), ctx->stream));
-    PLP_CUDA_TRY(cudaMemsetAsync(D.kmax, 0, (size_t)batch * sizeof(int), ctx->stream));
     {
         dim3 grid(div_up(D.w, kScTw) * div_up(D.h, kScTh), batch);
         PLP_LAUNCH(ctx, lsd_scale_kernel, grid, 256, 0, D);
     }
-    {
-        dim3 grid(div_up(D.npx, 256), batch);
-        PLP_LAUNCH(ctx, lsd_gradient_kernel, grid, 256, 0, D);
-    }
     PLP_LAUNCH(ctx, lsd_sort_kernel, batch, kSortWarps * 32, h->sort_smem, D);
-    PLP_LAUNCH(ctx, lsd_grow_kernel, batch, 32, 0, D);
+    PLP_LAUNCH(ctx, lsd_grow_kernel, batch, 32, h->grow_smem, D);
     PLP_LAUNCH(ctx, keyline_kernel, batch, 32, 0, D, d_kl, d_fn, d_n);
     {
         dim3 grid(div_up(D.w, kGrTw) * div_up(D.h, kGrTh), batch);
@@ -939,6 +1042,11 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
     D.min_reg_size = (int)(size_t)(-log_nt / std::log10(D.p));
     D.min_length = 0.125 * std::min(cols, rows);
     D.seg_cap = D.npx / std::max(D.min_reg_size, 2) + 1;
+    {  // largest squared norm with sqrt(k / 4.0) <= rho (lsd.cpp: `norm <= threshold` -> NOTDEF)
+        int k = (int)std::floor(4.0 * D.rho * D.rho) + 2;
+        while (k > 0 && !(std::sqrt((double)k / 4.0) <= D.rho)) --k;
+        D.kthr = k;
+    }
     D.kl_cap = 1024;
     {  // LBD weights, binary_descriptor_custom.cpp:229-257 (integer divisions kept)
         double u = (kBandWidth * 3 - 1) / 2;
@@ -960,13 +1068,9 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
     plp_status st = PLP_OK;
 #define A(call) if (st == PLP_OK) st = (call)
     A(dev_alloc(h, &D.scaled, B * npx));
-    A(dev_alloc(h, &D.rec, B * npx));
-    A(dev_alloc(h, &D.kmax, B));
     A(dev_alloc(h, &D.order, B * npx));
     A(dev_alloc(h, &D.nseeds, B));
     A(dev_alloc(h, &D.reg_xy, B * npx));
-    A(dev_alloc(h, &D.reg_k, B * npx));
-    A(dev_alloc(h, &D.reg_a, B * npx));
     A(dev_alloc(h, &D.segs, B * D.seg_cap));
     A(dev_alloc(h, &D.nseg, B));
     A(dev_alloc(h, &D.grad, B * (size_t)rows * cols));
@@ -977,12 +1081,31 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
     A(dev_alloc(h, &h->d_lbd, B * D.kl_cap * 32));
     A(dev_alloc(h, &h->d_fn, B * D.kl_cap * 3));
     A(dev_alloc(h, &h->d_n, B));
-#undef A
     if (st != PLP_OK) {
         plp_line_destroy(h);
         return st;
     }
+    A(dev_alloc(h, &h->d_cstab, (size_t)kGDim * kGDim));
+    if (st != PLP_OK) {
+        plp_line_destroy(h);
+        return st;
+    }
+#undef A
+    D.cstab = h->d_cstab;
+    lsd_cs_table_kernel<<<div_up(kGDim * kGDim, 256), 256, 0, ctx->stream>>>(h->d_cstab);
+    ctx->launches++;
     h->sort_smem = ((size_t)kSortWarps * kBins + kBins) * sizeof(uint32_t);
+    h->grow_smem = (size_t)((D.npx + 15) & ~15) + (size_t)((((D.npx + 31) >> 5) + 3) & ~3) * 4 + (size_t)kRegCap * 4;
+    if (h->grow_smem > 227 * 1024) {
+        set_error("line: a %d x %d image needs %zu bytes of shared memory per frame (limit 232448)", cols, rows, h->grow_smem);
+        plp_line_destroy(h);
+        return PLP_ERR_CAPACITY;
+    }
+    if (cudaFuncSetAttribute(lsd_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grow_smem) != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(lsd_grow_kernel) failed");
+        plp_line_destroy(h);
+        return PLP_ERR_CUDA;
+    }
     cudaError_t e = cudaFuncSetAttribute(lsd_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sort_smem);
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute(lsd_sort_kernel) failed: %s", cudaGetErrorString(e));
