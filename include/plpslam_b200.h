@@ -276,6 +276,31 @@ PLP_API plp_status plp_orb_debug_candidates(plp_orb *orb, int b, int level, plp_
                                             int *n_out);
 
 /* ------------------------------------------------------------------------ */
+/* stereo matching  (match/stereo.{h,cc})                                    */
+/* ------------------------------------------------------------------------ */
+/* match::stereo::compute(stereo_x_right, depths) (match/stereo.cc:45-150): per left keypoint the Hamming-closest right
+ * keypoint in the row band (+-2 * scale), octave +-1 and disparity range [0, focal_x_baseline / true_baseline), best
+ * distance < (100 + 50) / 2; 11 x 11 L1 patch slide over +-5 px at the keypoint's octave with parabola refinement;
+ * matches whose patch correlation exceeds twice the median are dropped.  The image pyramids are the ones the two
+ * extractors hold from their most recent extraction (orb_extractor::image_pyramid_, passed by frame.cc:475).
+ * Outputs have one entry per left keypoint (-1 = no stereo match), like the vectors the reference resizes at :51-52.
+ * best_right_out (optional parity tap): index of the Hamming-closest right keypoint before the sub-pixel stage. */
+PLP_API plp_status plp_stereo_compute(plp_ctx *ctx, const plp_orb *left, const plp_orb *right,
+                                      const plp_keypoint *kp_left, const uint8_t *desc_left, int n_left,
+                                      const plp_keypoint *kp_right, const uint8_t *desc_right, int n_right,
+                                      float focal_x_baseline, float true_baseline, float *stereo_x_right_out,
+                                      float *depths_out, int32_t *best_right_out);
+/* Device-resident batched variant: the arrays are the outputs of plp_orb_extract_batch_dev of the two handles
+ * (batch x plp_orb_capacity() entries); no synchronisation. */
+PLP_API plp_status plp_stereo_compute_batch_dev(plp_ctx *ctx, const plp_orb *left, const plp_orb *right, int batch,
+                                                const plp_keypoint *d_kp_left, const uint8_t *d_desc_left,
+                                                const int32_t *d_n_left, const plp_keypoint *d_kp_right,
+                                                const uint8_t *d_desc_right, const int32_t *d_n_right,
+                                                float focal_x_baseline, float true_baseline,
+                                                float *d_stereo_x_right_out, float *d_depths_out,
+                                                int32_t *d_best_right_out);
+
+/* ------------------------------------------------------------------------ */
 /* LSD + LBD line extraction  (feature/line_extractor.{h,cc},                */
 /* feature/line_descriptor/{LSDDetector_custom,binary_descriptor_custom}.cpp) */
 /* ------------------------------------------------------------------------ */

@@ -28,6 +28,7 @@
 #include "pose_opt.h"
 #include "local_ba.h"
 #include "lines.h"
+#include "stereo.h"
 
 #ifdef __cplusplus
 extern "C" {

@@ -404,6 +404,22 @@ class OrbExtractor:
                                                          desc.ctypes.data_as(_P), n.ctypes.data_as(_P)))
         return [(kps[b, :n[b]].copy(), desc[b, :n[b]].copy()) for b in range(B)]
 
+    def stereo_compute(self, right: "OrbExtractor", kp_left, desc_left, kp_right, desc_right, focal_x_baseline,
+                       true_baseline):
+        """match::stereo::compute with this extractor as the left one -> (stereo_x_right, depths, best_right_idx)."""
+        kl = np.ascontiguousarray(kp_left, KP_DTYPE)
+        kr = np.ascontiguousarray(kp_right, KP_DTYPE)
+        dl = np.ascontiguousarray(desc_left, np.uint8)
+        dr = np.ascontiguousarray(desc_right, np.uint8)
+        xr = np.zeros(max(len(kl), 1), np.float32)
+        dp = np.zeros(max(len(kl), 1), np.float32)
+        br = np.zeros(max(len(kl), 1), np.int32)
+        self._ctx._check(self._lib.plp_stereo_compute(
+            self._ctx.handle, self._h, right._h, kl.ctypes.data_as(_P), dl.ctypes.data_as(_P), C.c_int(len(kl)),
+            kr.ctypes.data_as(_P), dr.ctypes.data_as(_P), C.c_int(len(kr)), C.c_float(focal_x_baseline),
+            C.c_float(true_baseline), xr.ctypes.data_as(_P), dp.ctypes.data_as(_P), br.ctypes.data_as(_P)))
+        return xr[:len(kl)].copy(), dp[:len(kl)].copy(), br[:len(kl)].copy()
+
     def pyramid_level(self, b: int, level: int) -> np.ndarray:
         """orb_extractor::image_pyramid_[level] of frame b of the last extraction (downloaded)."""
         v = ImageView()

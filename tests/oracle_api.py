@@ -487,3 +487,27 @@ Oracle.lsd_keylines = _lsd_keylines
 Oracle.lbd_gradients = _lbd_gradients
 Oracle.lbd_compute = _lbd_compute
 Oracle.line_extract = _line_extract
+
+
+# ======================================================================== stereo matcher (oracle/stereo.cc)
+def _stereo_compute(self, res_left, res_right, scale_factors, inv_scale_factors, focal_x_baseline, true_baseline):
+    """res_* = outputs of Oracle.orb_extract (pyramid, kps, desc) of the left / right image."""
+    pl = np.ascontiguousarray(np.concatenate([l.ravel() for l in res_left["pyramid"]]))
+    pr = np.ascontiguousarray(np.concatenate([l.ravel() for l in res_right["pyramid"]]))
+    w = np.array([l.shape[1] for l in res_left["pyramid"]], np.int32)
+    h = np.array([l.shape[0] for l in res_left["pyramid"]], np.int32)
+    kl, kr = np.ascontiguousarray(res_left["kps"]), np.ascontiguousarray(res_right["kps"])
+    dl, dr = np.ascontiguousarray(res_left["desc"]), np.ascontiguousarray(res_right["desc"])
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    isf = np.ascontiguousarray(inv_scale_factors, np.float32)
+    n = len(kl)
+    xr, dp, br = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.int32)
+    self.lib.orc_stereo_compute(pl.ctypes.data_as(_P), pr.ctypes.data_as(_P), w.ctypes.data_as(_P), h.ctypes.data_as(_P),
+                                C.c_int(len(w)), kl.ctypes.data_as(_P), dl.ctypes.data_as(_P), C.c_int(n),
+                                kr.ctypes.data_as(_P), dr.ctypes.data_as(_P), C.c_int(len(kr)), sf.ctypes.data_as(_P),
+                                isf.ctypes.data_as(_P), C.c_float(focal_x_baseline), C.c_float(true_baseline),
+                                xr.ctypes.data_as(_P), dp.ctypes.data_as(_P), br.ctypes.data_as(_P))
+    return xr[:n].copy(), dp[:n].copy(), br[:n].copy()
+
+
+Oracle.stereo_compute = _stereo_compute

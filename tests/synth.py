@@ -332,3 +332,23 @@ def make_line_image(seed, h=480, w=640, n_patch=44, noise=2.0):
     img = cv2.GaussianBlur(img, (0, 0), 0.8)
     img += rng.normal(0, noise, (h, w)).astype(np.float32)
     return np.clip(np.round(img), 0, 255).astype(np.uint8)
+
+
+def make_stereo_pair(seed, h=480, w=752, bf=47.906, n_bands=6):
+    """Rectified stereo pair: the right image is the left texture shifted by a per-row-band
+    disparity bf / depth (sub-pixel, bilinear) plus independent sensor noise."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    left = make_texture(seed, h, w)
+    depths = rng.uniform(1.5, 12.0, n_bands)
+    right = np.zeros_like(left)
+    edges = np.linspace(0, h, n_bands + 1).astype(int)
+    xx = np.arange(w, dtype=np.float32)[None, :].repeat(h, 0)
+    yy = np.arange(h, dtype=np.float32)[:, None].repeat(w, 1)
+    disp = np.zeros((h, w), np.float32)
+    for i in range(n_bands):
+        disp[edges[i]:edges[i + 1]] = bf / depths[i]
+    right = cv2.remap(left, xx + disp, yy, cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    noise = rng.normal(0, 1.5, (h, w))
+    right = np.clip(np.round(right.astype(np.float64) + noise), 0, 255).astype(np.uint8)
+    return left, right, disp
