@@ -204,6 +204,29 @@ PLP_API plp_status plp_match_current_and_last_frames_line(
     const plp_last_frame_lines *last, float margin, int32_t *matched_last_idx_out,
     uint32_t *num_matches_out);
 
+/* projection::match_frame_and_keyframe (match/projection.cc:529-645), the relocalisation matcher.  The adapter walks
+ * keyfrm->get_landmarks() exactly like the reference and flattens one query per keyframe keypoint index: `valid` =
+ * lm && !lm->will_be_erased() && !already_matched_lms.count(lm) && reprojected inside the image && inside
+ * [0.7 min_valid_dist, 1.3 max_valid_dist] (:543-582); reproj = camera_->reproject_to_image; scale_level =
+ * lm->predict_scale_level(cam_to_lm_dist, &curr_frm) (host libm logf, data/landmark.cc:319-340); q_angle =
+ * keyfrm->undist_keypts_[idx].angle.  frm->claimed[i] = (curr_frm.landmarks_[i] != nullptr) (:604).  The window is
+ * margin * scale_factors[level] over levels [level - 1, level + 1]; best Hamming <= hamm_dist_thr; keypoints are
+ * claimed in query order; then the orientation histogram.  matched_kf_idx_out[n]: query index assigned to each
+ * keypoint of the frame (curr_frm.landmarks_[i] = landmarks[idx]) or -1. */
+PLP_API plp_status plp_match_frame_and_keyframe(plp_ctx *ctx, const plp_frame_points *frm, const plp_grid *grid,
+                                                const float *scale_factors, int num_levels,
+                                                const plp_landmark_queries *q, const float *q_angle, float margin,
+                                                unsigned hamm_dist_thr, int check_orientation,
+                                                int32_t *matched_kf_idx_out, uint32_t *num_matches_out);
+
+/* projection::match_frame_and_keyframe_line (match/projection.cc:648-779): as above for line landmarks; `valid`
+ * additionally encodes the partial-occlusion rule (:699-718: at least one end point, or the mid point, inside the
+ * image); no orientation check. */
+PLP_API plp_status plp_match_frame_and_keyframe_line(plp_ctx *ctx, const plp_frame_lines *frm,
+                                                     const float *scale_factors_lsd, int num_levels_lsd,
+                                                     const plp_line_queries *q, float margin, unsigned hamm_dist_thr,
+                                                     int32_t *matched_kf_idx_out, uint32_t *num_matches_out);
+
 /* robust::brute_force_match (match/robust.cc:257-385).
  * frame = "1", keyframe = "2".  kf_valid[j] = lm_2 && !lm_2->will_be_erased().
  * matched_kf_idx_in_frm_out[n_frm] = matched_indices_2_in_1 after the orientation check. */

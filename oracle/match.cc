@@ -382,6 +382,154 @@ unsigned orc_match_current_and_last_frames(const orc_grid *g, int n, const float
     return num_matches;
 }
 
+// data/landmark.cc:319-340 / data/landmark_line.cc:366-387
+static unsigned predict_scale_level(float max_valid_dist, float cam_to_lm_dist, float log_scale_factor, unsigned num_levels) {
+    const float ratio = max_valid_dist / cam_to_lm_dist;
+    const int pred = static_cast<int>(std::ceil(std::log(ratio) / log_scale_factor));
+    if (pred < 0) return 0;
+    if (num_levels <= static_cast<unsigned>(pred)) return num_levels - 1;
+    return static_cast<unsigned>(pred);
+}
+
+static void cam_center_of(const Pose &cw, double c[3]) {
+    for (int r = 0; r < 3; ++r) c[r] = -(cw.R[0 * 3 + r] * cw.t[0] + cw.R[1 * 3 + r] * cw.t[1] + cw.R[2 * 3 + r] * cw.t[2]);
+}
+
+unsigned orc_match_frame_and_keyframe(const orc_grid *g, int n, const float *x, const float *y, const int32_t *octave,
+                                      const float *angle, const uint8_t *desc, const uint8_t *claimed_in,
+                                      const float *scale_factors, int num_levels, float log_scale_factor,
+                                      const orc_camera *cam, const double *pose_cw_curr, int n_kf, const double *pos_w,
+                                      const float *min_valid_dist, const float *max_valid_dist, const float *kf_angle,
+                                      const uint8_t *kf_desc, const uint8_t *kf_valid, float margin, unsigned hamm_dist_thr,
+                                      int check_orientation, int32_t *matched_kf_idx_out, float *q_reproj_x,
+                                      float *q_reproj_y, int32_t *q_level, uint8_t *q_valid) {
+    // match/projection.cc:529-645
+    Grid grid(g, x, y, n);
+    std::vector<uint8_t> claimed(n, 0);
+    if (claimed_in) claimed.assign(claimed_in, claimed_in + n);
+    for (int i = 0; i < n; ++i) matched_kf_idx_out[i] = -1;
+    const Pose cw(pose_cw_curr);
+    double cc[3];
+    cam_center_of(cw, cc);
+    AngleChecker angle_checker;
+    unsigned num_matches = 0;
+    for (int idx = 0; idx < n_kf; ++idx) {
+        if (q_valid) {
+            q_valid[idx] = 0;
+            q_reproj_x[idx] = q_reproj_y[idx] = 0.f;
+            q_level[idx] = 0;
+        }
+        if (kf_valid && !kf_valid[idx]) continue;  // !lm || will_be_erased || already_matched
+        double reproj[2];
+        float xr;
+        if (!orc_reproject_to_image(cam, cw.R, cw.t, pos_w + 3 * idx, reproj, &xr)) continue;
+        const double v[3] = {pos_w[3 * idx] - cc[0], pos_w[3 * idx + 1] - cc[1], pos_w[3 * idx + 2] - cc[2]};
+        const double dist = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        const float max_d = (float)(1.3 * max_valid_dist[idx]), min_d = (float)(0.7 * min_valid_dist[idx]);  // landmark.cc:297-307
+        if (dist < min_d || max_d < dist) continue;
+        const unsigned lvl = predict_scale_level(max_valid_dist[idx], (float)dist, log_scale_factor, (unsigned)num_levels);
+        if (q_valid) {
+            q_valid[idx] = 1;
+            q_reproj_x[idx] = (float)reproj[0];
+            q_reproj_y[idx] = (float)reproj[1];
+            q_level[idx] = (int)lvl;
+        }
+        const auto indices = grid.query(x, y, octave, (float)reproj[0], (float)reproj[1], margin * scale_factors[lvl],
+                                        (int)lvl - 1, (int)lvl + 1);
+        if (indices.empty()) continue;
+        unsigned best_hamm_dist = MAX_HAMMING_DIST;
+        int best_idx = -1;
+        for (const auto curr_idx : indices) {
+            if (claimed[curr_idx]) continue;
+            const auto hamm_dist = orc_hamming_32(kf_desc + 32 * idx, desc + 32 * curr_idx);
+            if (hamm_dist < best_hamm_dist) {
+                best_hamm_dist = hamm_dist;
+                best_idx = curr_idx;
+            }
+        }
+        if (hamm_dist_thr < best_hamm_dist) continue;
+        matched_kf_idx_out[best_idx] = idx;
+        claimed[best_idx] = 1;
+        ++num_matches;
+        if (check_orientation) angle_checker.append(kf_angle[idx] - angle[best_idx], best_idx);
+    }
+    if (check_orientation) {
+        for (const auto invalid_idx : angle_checker.collect(false)) {
+            matched_kf_idx_out[invalid_idx] = -1;
+            --num_matches;
+        }
+    }
+    return num_matches;
+}
+
+unsigned orc_match_frame_and_keyframe_line(int n, const float *sx, const float *sy, const float *ex, const float *ey,
+                                           const int32_t *octave, const uint8_t *desc, const uint8_t *claimed_in,
+                                           const float *scale_factors_lsd, int num_levels_lsd, float log_scale_factor_lsd,
+                                           const orc_camera *cam, const double *pose_cw_curr, int n_kf,
+                                           const double *pos_w /*n_kf x 6*/, const float *min_valid_dist,
+                                           const float *max_valid_dist, const uint8_t *kf_desc, const uint8_t *kf_valid,
+                                           float margin, unsigned hamm_dist_thr, int32_t *matched_kf_idx_out,
+                                           float *q_sp_x, float *q_sp_y, float *q_ep_x, float *q_ep_y, int32_t *q_level,
+                                           uint8_t *q_valid) {
+    // match/projection.cc:648-779
+    std::vector<uint8_t> claimed(n, 0);
+    if (claimed_in) claimed.assign(claimed_in, claimed_in + n);
+    for (int i = 0; i < n; ++i) matched_kf_idx_out[i] = -1;
+    const Pose cw(pose_cw_curr);
+    double cc[3];
+    cam_center_of(cw, cc);
+    unsigned num_matches = 0;
+    for (int idx = 0; idx < n_kf; ++idx) {
+        if (q_valid) {
+            q_valid[idx] = 0;
+            q_sp_x[idx] = q_sp_y[idx] = q_ep_x[idx] = q_ep_y[idx] = 0.f;
+            q_level[idx] = 0;
+        }
+        if (kf_valid && !kf_valid[idx]) continue;
+        const double *p = pos_w + 6 * idx;
+        double rsp[2], rep[2], rmp[2];
+        float xr;
+        const bool in_sp = orc_reproject_to_image(cam, cw.R, cw.t, p, rsp, &xr) != 0;
+        const bool in_ep = orc_reproject_to_image(cam, cw.R, cw.t, p + 3, rep, &xr) != 0;
+        if (!in_sp && !in_ep) continue;
+        const double mp[3] = {0.5 * (p[0] + p[3]), 0.5 * (p[1] + p[4]), 0.5 * (p[2] + p[5])};
+        if (!in_sp || !in_ep) {
+            if (!orc_reproject_to_image(cam, cw.R, cw.t, mp, rmp, &xr)) continue;
+        }
+        const double v[3] = {mp[0] - cc[0], mp[1] - cc[1], mp[2] - cc[2]};
+        const double dist = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        const float max_d = (float)(1.3 * max_valid_dist[idx]), min_d = (float)(0.7 * min_valid_dist[idx]);
+        if (dist < min_d || max_d < dist) continue;
+        const unsigned lvl = predict_scale_level(max_valid_dist[idx], (float)dist, log_scale_factor_lsd, (unsigned)num_levels_lsd);
+        if (q_valid) {
+            q_valid[idx] = 1;
+            q_sp_x[idx] = (float)rsp[0];
+            q_sp_y[idx] = (float)rsp[1];
+            q_ep_x[idx] = (float)rep[0];
+            q_ep_y[idx] = (float)rep[1];
+            q_level[idx] = (int)lvl;
+        }
+        const auto indices = keylines_in_cell(n, sx, sy, ex, ey, octave, (float)rsp[0], (float)rsp[1], (float)rep[0],
+                                              (float)rep[1], margin * scale_factors_lsd[lvl], (int)lvl - 1, (int)lvl + 1);
+        if (indices.empty()) continue;
+        unsigned best_hamm_dist = MAX_HAMMING_DIST;
+        int best_idx = -1;
+        for (const auto curr_idx : indices) {
+            if (claimed[curr_idx]) continue;
+            const auto hamm_dist = orc_hamming_32(kf_desc + 32 * idx, desc + 32 * curr_idx);
+            if (hamm_dist < best_hamm_dist) {
+                best_hamm_dist = hamm_dist;
+                best_idx = curr_idx;
+            }
+        }
+        if (hamm_dist_thr < best_hamm_dist) continue;
+        matched_kf_idx_out[best_idx] = idx;
+        claimed[best_idx] = 1;
+        ++num_matches;
+    }
+    return num_matches;
+}
+
 unsigned orc_match_frame_and_landmarks_line(int n, const float *sx, const float *sy, const float *ex,
                                             const float *ey, const int32_t *octave,
                                             const int32_t *ratio_level, const uint8_t *desc,

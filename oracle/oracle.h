@@ -111,6 +111,26 @@ unsigned orc_match_current_and_last_frames_line(
     const double *pos_w /*n_last x 6*/, const int32_t *last_octave, const uint8_t *last_desc,
     const uint8_t *last_valid, float margin, int32_t *matched_last_idx_out);
 
+/* ---- match/projection.cc:529-645 / 648-779 (relocalisation matchers).  kf_valid[idx] = lm && !will_be_erased &&
+ * !already_matched.  The optional q_* outputs are the flattened per-landmark queries the reference-side adapter would
+ * hand to the C ABI (reprojection, predicted scale level, survived the visibility / distance gates). */
+unsigned orc_match_frame_and_keyframe(const orc_grid *g, int n, const float *x, const float *y, const int32_t *octave,
+                                      const float *angle, const uint8_t *desc, const uint8_t *claimed,
+                                      const float *scale_factors, int num_levels, float log_scale_factor,
+                                      const orc_camera *cam, const double *pose_cw_curr, int n_kf, const double *pos_w,
+                                      const float *min_valid_dist, const float *max_valid_dist, const float *kf_angle,
+                                      const uint8_t *kf_desc, const uint8_t *kf_valid, float margin, unsigned hamm_dist_thr,
+                                      int check_orientation, int32_t *matched_kf_idx_out, float *q_reproj_x,
+                                      float *q_reproj_y, int32_t *q_level, uint8_t *q_valid);
+unsigned orc_match_frame_and_keyframe_line(int n, const float *sx, const float *sy, const float *ex, const float *ey,
+                                           const int32_t *octave, const uint8_t *desc, const uint8_t *claimed,
+                                           const float *scale_factors_lsd, int num_levels_lsd, float log_scale_factor_lsd,
+                                           const orc_camera *cam, const double *pose_cw_curr, int n_kf,
+                                           const double *pos_w, const float *min_valid_dist, const float *max_valid_dist,
+                                           const uint8_t *kf_desc, const uint8_t *kf_valid, float margin,
+                                           unsigned hamm_dist_thr, int32_t *matched_kf_idx_out, float *q_sp_x,
+                                           float *q_sp_y, float *q_ep_x, float *q_ep_y, int32_t *q_level, uint8_t *q_valid);
+
 /* ---- match/robust.cc:257-385 --------------------------------------------------------- */
 unsigned orc_brute_force_match(const uint8_t *frm_desc, const float *frm_angle, int n_frm,
                                const uint8_t *kf_desc, const float *kf_angle,

@@ -246,6 +246,39 @@ class Context:
             C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P), C.byref(num)))
         return matched, int(num.value)
 
+    def match_frame_and_keyframe(self, grid, scale_factors, frm, q, margin, hamm_dist_thr, check_orientation=True):
+        """projection::match_frame_and_keyframe; q = flattened queries (reproj_x/y, scale_level, desc, angle, valid)."""
+        k = _Keep()
+        fp = self._frame_points(k, frm["x"], frm["y"], frm["octave"], frm["desc"], frm.get("angle"), None,
+                                frm.get("claimed"))
+        m = len(q["scale_level"])
+        lq = LandmarkQueries(m, k.arr(q["reproj_x"], np.float32), k.arr(q["reproj_y"], np.float32), None,
+                             k.arr(q["scale_level"], np.int32), k.arr(q["desc"], np.uint8), k.arr(q.get("valid"), np.uint8))
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        matched = np.full(fp.n, -2, np.int32)
+        num = C.c_uint32(0)
+        self._check(self._lib.plp_match_frame_and_keyframe(
+            self._h, C.byref(fp), C.byref(grid), sf.ctypes.data_as(_P), C.c_int(len(sf)), C.byref(lq),
+            k.arr(q.get("angle"), np.float32), C.c_float(margin), C.c_uint(hamm_dist_thr),
+            C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P), C.byref(num)))
+        return matched, int(num.value)
+
+    def match_frame_and_keyframe_line(self, scale_factors_lsd, frm, q, margin, hamm_dist_thr):
+        """projection::match_frame_and_keyframe_line; q = flattened queries (sp/ep, scale_level, desc, valid)."""
+        k = _Keep()
+        fl = self._frame_lines(k, frm)
+        m = len(q["scale_level"])
+        lq = LineQueries(m, k.arr(q["sp_x"], np.float32), k.arr(q["sp_y"], np.float32), k.arr(q["ep_x"], np.float32),
+                         k.arr(q["ep_y"], np.float32), k.arr(q["scale_level"], np.int32), k.arr(q["desc"], np.uint8),
+                         k.arr(q.get("valid"), np.uint8))
+        sf = np.ascontiguousarray(scale_factors_lsd, np.float32)
+        matched = np.full(fl.n, -2, np.int32)
+        num = C.c_uint32(0)
+        self._check(self._lib.plp_match_frame_and_keyframe_line(
+            self._h, C.byref(fl), sf.ctypes.data_as(_P), C.c_int(len(sf)), C.byref(lq), C.c_float(margin),
+            C.c_uint(hamm_dist_thr), matched.ctypes.data_as(_P), C.byref(num)))
+        return matched, int(num.value)
+
     @staticmethod
     def _frame_lines(k, f):
         n = len(f["sx"])

@@ -407,12 +407,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         // proposes to its best candidate; a keypoint keeps its smallest proposer; only bumped queries re-propose
         // to their next candidate in (distance, order).
         int *owner = owner_prev;  // min proposer so far; never reset
+        const unsigned hamm_thr = J.hamm_thr_p1 ? J.hamm_thr_p1 - 1u : (unsigned)PLP_HAMMING_DIST_THR_HIGH;
         for (int q = warp; q < m; q += nwarps) {
             int choice = -1;
             if (J.qvalid ? (J.qvalid[q] != 0) : true) {
                 unsigned long long k1, k2;
                 scan(q, nullptr, false, 0ull, k1, k2);
-                if (k1 != ~0ull && (unsigned)(k1 >> 40) <= PLP_HAMMING_DIST_THR_HIGH) choice = (int)((k1 >> 8) & 0xffffffffull);
+                if (k1 != ~0ull && (unsigned)(k1 >> 40) <= hamm_thr) choice = (int)((k1 >> 8) & 0xffffffffull);
             }
             if (lane == 0) {
                 J.choice[q] = choice;
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 unsigned long long k1, k2;
                 scan(q, nullptr, true, floor, k1, k2);
                 int choice = -1;
-                if (k1 != ~0ull && (unsigned)(k1 >> 40) <= PLP_HAMMING_DIST_THR_HIGH) choice = (int)((k1 >> 8) & 0xffffffffull);
+                if (k1 != ~0ull && (unsigned)(k1 >> 40) <= hamm_thr) choice = (int)((k1 >> 8) & 0xffffffffull);
                 if (lane == 0) {
                     J.choice[q] = choice;
                     if (choice >= 0) atomicMin(&owner[choice], q);
@@ -622,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         second = d;
                     }
                 }
-                if (best_p >= 0 && best <= PLP_HAMMING_DIST_THR_HIGH) {
+                if (best_p >= 0 && best <= (J.hamm_thr_p1 ? J.hamm_thr_p1 - 1u : (unsigned)PLP_HAMMING_DIST_THR_HIGH)) {
                     bool ok = true;
                     if (ratio_test && best_lvl == second_lvl && (float)best > lowe_ratio * (float)second) ok = false;
                     if (ok) choice = best_p;
@@ -1225,6 +1226,133 @@ plp_status plp_match_current_and_last_frames_line(plp_ctx *ctx, const plp_frame_
     PLP_TRY(launch_line_match(ctx, Packer::at<LineMatchJob>(d, o_job), 1, 0, 0.0f, cam->setup_type == 2));
     uint32_t num = 0;
     PLP_CUDA_TRY(cudaMemcpyAsync(matched_last_idx_out, d + o_matched, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaMemcpyAsync(&num, d + o_num, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (num_matches_out) *num_matches_out = num;
+    return PLP_OK;
+}
+
+plp_status plp_match_frame_and_keyframe(plp_ctx *ctx, const plp_frame_points *frm, const plp_grid *grid,
+                                        const float *scale_factors, int num_levels, const plp_landmark_queries *q,
+                                        const float *q_angle, float margin, unsigned hamm_dist_thr, int check_orientation,
+                                        int32_t *matched_kf_idx_out, uint32_t *num_matches_out) {
+    PLP_REQUIRE(ctx && frm && grid && scale_factors && q && matched_kf_idx_out, "null pointer");
+    PLP_REQUIRE(frm->n >= 0 && q->m >= 0 && num_levels > 0, "sizes");
+    if (num_matches_out) *num_matches_out = 0;
+    for (int i = 0; i < frm->n; ++i) matched_kf_idx_out[i] = -1;
+    if (frm->n == 0 || q->m == 0) return PLP_OK;
+    PLP_REQUIRE(frm->x && frm->y && frm->octave && frm->desc, "frame arrays");
+    PLP_REQUIRE(q->reproj_x && q->reproj_y && q->scale_level && q->desc, "query arrays");
+    PLP_REQUIRE(!check_orientation || (frm->angle && q_angle), "angles required for the orientation check");
+    PLP_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int m = q->m, n = frm->n;
+    // projection.cc:586-588: window margin * scale_factors[pred], levels [pred - 1, pred + 1]
+    std::vector<float> radius(m);
+    std::vector<int32_t> qmin(m), qmax(m);
+    for (int i = 0; i < m; ++i) {
+        const int lvl = q->scale_level[i];
+        PLP_REQUIRE(lvl >= 0 && lvl < num_levels, "scale_level out of range");
+        radius[i] = margin * scale_factors[lvl];
+        qmin[i] = lvl - 1;
+        qmax[i] = lvl + 1;
+    }
+    Packer pk;
+    PointMatchJob J;
+    memset(&J, 0, sizeof(J));
+    size_t fo[7];
+    pack_frame_points(pk, frm, J, fo);
+    const size_t o_qx = pk.add(q->reproj_x, (size_t)m * 4), o_qy = pk.add(q->reproj_y, (size_t)m * 4);
+    const size_t o_r = pk.add(radius.data(), (size_t)m * 4);
+    const size_t o_mn = pk.add(qmin.data(), (size_t)m * 4), o_mx = pk.add(qmax.data(), (size_t)m * 4);
+    const size_t o_qa = pk.add(q_angle, (size_t)m * 4);
+    const size_t o_qd = pk.add(q->desc, (size_t)m * 32), o_qv = pk.add(q->valid, (size_t)m);
+    const size_t o_choice = pk.reserve((size_t)m * 4), o_matched = pk.reserve((size_t)n * 4), o_num = pk.reserve(4);
+    const size_t o_job = pk.reserve(sizeof(PointMatchJob));
+    uint8_t *d;
+    PLP_TRY(pk.upload(ctx, 0, &d));
+    bind_frame_points(d, fo, J);
+    J.x_right = nullptr;  // no stereo gate in match_frame_and_keyframe
+    J.m = m;
+    J.qx = Packer::at<float>(d, o_qx);
+    J.qy = Packer::at<float>(d, o_qy);
+    J.qxr = nullptr;
+    J.qradius = Packer::at<float>(d, o_r);
+    J.qmin = Packer::at<int32_t>(d, o_mn);
+    J.qmax = Packer::at<int32_t>(d, o_mx);
+    J.qangle = q_angle ? Packer::at<float>(d, o_qa) : nullptr;
+    J.qdesc = Packer::at<uint8_t>(d, o_qd);
+    J.qvalid = q->valid ? Packer::at<uint8_t>(d, o_qv) : nullptr;
+    J.choice = Packer::at<int32_t>(d, o_choice);
+    J.matched_out = Packer::at<int32_t>(d, o_matched);
+    J.num_matches = Packer::at<uint32_t>(d, o_num);
+    J.hamm_thr_p1 = hamm_dist_thr + 1u;
+    PLP_CUDA_TRY(cudaMemcpyAsync(d + o_job, &J, sizeof(J), cudaMemcpyHostToDevice, ctx->stream));
+    PLP_TRY(launch_point_match(ctx, Packer::at<PointMatchJob>(d, o_job), 1, n, *grid, 0, 0.0f, check_orientation));
+    uint32_t num = 0;
+    PLP_CUDA_TRY(cudaMemcpyAsync(matched_kf_idx_out, d + o_matched, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaMemcpyAsync(&num, d + o_num, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (num_matches_out) *num_matches_out = num;
+    return PLP_OK;
+}
+
+plp_status plp_match_frame_and_keyframe_line(plp_ctx *ctx, const plp_frame_lines *frm, const float *scale_factors_lsd,
+                                             int num_levels_lsd, const plp_line_queries *q, float margin,
+                                             unsigned hamm_dist_thr, int32_t *matched_kf_idx_out,
+                                             uint32_t *num_matches_out) {
+    PLP_REQUIRE(ctx && frm && scale_factors_lsd && q && matched_kf_idx_out, "null pointer");
+    PLP_REQUIRE(frm->n >= 0 && q->m >= 0 && num_levels_lsd > 0, "sizes");
+    PLP_REQUIRE(frm->n <= 16384, "keyline capacity 16384");
+    if (num_matches_out) *num_matches_out = 0;
+    for (int i = 0; i < frm->n; ++i) matched_kf_idx_out[i] = -1;
+    if (frm->n == 0 || q->m == 0) return PLP_OK;
+    PLP_REQUIRE(frm->sx && frm->sy && frm->ex && frm->ey && frm->octave && frm->desc, "frame arrays");
+    PLP_REQUIRE(q->sp_x && q->sp_y && q->ep_x && q->ep_y && q->scale_level && q->desc, "query arrays");
+    PLP_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int m = q->m, n = frm->n;
+    std::vector<float> radius(m);
+    std::vector<int32_t> qmin(m), qmax(m);
+    for (int i = 0; i < m; ++i) {
+        const int lvl = q->scale_level[i];
+        PLP_REQUIRE(lvl >= 0 && lvl < num_levels_lsd, "scale_level out of range");
+        radius[i] = margin * scale_factors_lsd[lvl];  // projection.cc:734-737
+        qmin[i] = lvl - 1;
+        qmax[i] = lvl + 1;
+    }
+    Packer pk;
+    LineMatchJob J;
+    memset(&J, 0, sizeof(J));
+    size_t fo[11];
+    pack_frame_lines(pk, frm, fo);
+    const size_t o1 = pk.add(q->sp_x, (size_t)m * 4), o2 = pk.add(q->sp_y, (size_t)m * 4);
+    const size_t o3 = pk.add(q->ep_x, (size_t)m * 4), o4 = pk.add(q->ep_y, (size_t)m * 4);
+    const size_t o_r = pk.add(radius.data(), (size_t)m * 4);
+    const size_t o_mn = pk.add(qmin.data(), (size_t)m * 4), o_mx = pk.add(qmax.data(), (size_t)m * 4);
+    const size_t o_qd = pk.add(q->desc, (size_t)m * 32), o_qv = pk.add(q->valid, (size_t)m);
+    const size_t o_choice = pk.reserve((size_t)m * 4), o_matched = pk.reserve((size_t)n * 4), o_num = pk.reserve(4);
+    const size_t o_job = pk.reserve(sizeof(LineMatchJob));
+    uint8_t *d;
+    PLP_TRY(pk.upload(ctx, 0, &d));
+    bind_frame_lines(d, fo, frm, J);
+    J.m = m;
+    J.q_spx = Packer::at<float>(d, o1);
+    J.q_spy = Packer::at<float>(d, o2);
+    J.q_epx = Packer::at<float>(d, o3);
+    J.q_epy = Packer::at<float>(d, o4);
+    J.qradius = Packer::at<float>(d, o_r);
+    J.qmin = Packer::at<int32_t>(d, o_mn);
+    J.qmax = Packer::at<int32_t>(d, o_mx);
+    J.qdesc = Packer::at<uint8_t>(d, o_qd);
+    J.qvalid = q->valid ? Packer::at<uint8_t>(d, o_qv) : nullptr;
+    J.choice = Packer::at<int32_t>(d, o_choice);
+    J.matched_out = Packer::at<int32_t>(d, o_matched);
+    J.num_matches = Packer::at<uint32_t>(d, o_num);
+    J.ratio_level = nullptr;
+    J.hamm_thr_p1 = hamm_dist_thr + 1u;
+    PLP_CUDA_TRY(cudaMemcpyAsync(d + o_job, &J, sizeof(J), cudaMemcpyHostToDevice, ctx->stream));
+    PLP_TRY(launch_line_match(ctx, Packer::at<LineMatchJob>(d, o_job), 1, 0, 0.0f, 0));
+    uint32_t num = 0;
+    PLP_CUDA_TRY(cudaMemcpyAsync(matched_kf_idx_out, d + o_matched, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PLP_CUDA_TRY(cudaMemcpyAsync(&num, d + o_num, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (num_matches_out) *num_matches_out = num;

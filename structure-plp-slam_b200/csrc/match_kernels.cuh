@@ -29,6 +29,8 @@ struct PointMatchJob {
     int32_t *best_idx_out;  // m entries (match_frame_and_landmarks) or null
     int32_t *matched_out;   // n entries (match_current_and_last_frames) or null
     uint32_t *num_matches;  // 1 entry
+    // acceptance threshold of the no-ratio path + 1; 0 = HAMMING_DIST_THR_HIGH (match_frame_and_keyframe passes its own)
+    unsigned hamm_thr_p1;
 };
 
 struct LineMatchJob {
@@ -50,6 +52,7 @@ struct LineMatchJob {
     int32_t *best_idx_out;
     int32_t *matched_out;
     uint32_t *num_matches;
+    unsigned hamm_thr_p1;  // acceptance threshold + 1; 0 = HAMMING_DIST_THR_HIGH
 };
 
 struct BruteJob {

@@ -98,6 +98,7 @@ __global__ void track_prep_kernel(TrackDev T, float margin, int check_orientatio
             J.x_right = nullptr;
             J.desc = T.desc + base * 32;
             J.claimed = nullptr;  // curr_frm.landmarks_ was just cleared (frame_tracker.cc:61)
+            J.hamm_thr_p1 = 0;
             J.m = m;
             J.qx = P.qx;
             J.qy = P.qy;

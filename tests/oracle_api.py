@@ -153,6 +153,60 @@ class Oracle:
             C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P))
         return matched, int(num)
 
+    def match_frame_and_keyframe(self, grid, scale_factors, cam, frm, Tc, kf, margin, hamm_dist_thr,
+                                 check_orientation=True):
+        """kf: pos_w, min_valid_dist, max_valid_dist, angle, desc, valid.  Returns (matched, num, queries)."""
+        keep = []
+
+        def A(v, dt):
+            arr, p = _a(v, dt)
+            keep.append(arr)
+            return p
+        n, m = len(frm["x"]), len(kf["pos_w"])
+        matched = np.full(n, -2, np.int32)
+        sf, psf = _a(scale_factors, np.float32)
+        qx, qy = np.zeros(m, np.float32), np.zeros(m, np.float32)
+        ql, qv = np.zeros(m, np.int32), np.zeros(m, np.uint8)
+        lsf = np.float32(np.log(np.float32(sf[1] / sf[0]))) if len(sf) > 1 else np.float32(1.0)
+        self.lib.orc_match_frame_and_keyframe.restype = C.c_uint
+        num = self.lib.orc_match_frame_and_keyframe(
+            C.byref(as_grid(grid)), C.c_int(n), A(frm["x"], np.float32), A(frm["y"], np.float32),
+            A(frm["octave"], np.int32), A(frm.get("angle"), np.float32), A(frm["desc"], np.uint8),
+            A(frm.get("claimed"), np.uint8), psf, C.c_int(len(sf)), C.c_float(lsf), C.byref(as_camera(cam)),
+            A(np.asarray(Tc).reshape(16), np.float64), C.c_int(m), A(kf["pos_w"], np.float64),
+            A(kf["min_valid_dist"], np.float32), A(kf["max_valid_dist"], np.float32), A(kf.get("angle"), np.float32),
+            A(kf["desc"], np.uint8), A(kf.get("valid"), np.uint8), C.c_float(margin), C.c_uint(hamm_dist_thr),
+            C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P), qx.ctypes.data_as(_P),
+            qy.ctypes.data_as(_P), ql.ctypes.data_as(_P), qv.ctypes.data_as(_P))
+        q = dict(reproj_x=qx, reproj_y=qy, scale_level=ql, valid=qv, desc=kf["desc"], angle=kf.get("angle"))
+        return matched, int(num), q
+
+    def match_frame_and_keyframe_line(self, scale_factors_lsd, log_scale_factor_lsd, cam, frm, Tc, kf, margin,
+                                      hamm_dist_thr):
+        keep = []
+
+        def A(v, dt):
+            arr, p = _a(v, dt)
+            keep.append(arr)
+            return p
+        n, m = len(frm["sx"]), len(kf["pos_w"])
+        matched = np.full(n, -2, np.int32)
+        sf, psf = _a(scale_factors_lsd, np.float32)
+        q4 = [np.zeros(m, np.float32) for _ in range(4)]
+        ql, qv = np.zeros(m, np.int32), np.zeros(m, np.uint8)
+        self.lib.orc_match_frame_and_keyframe_line.restype = C.c_uint
+        num = self.lib.orc_match_frame_and_keyframe_line(
+            C.c_int(n), A(frm["sx"], np.float32), A(frm["sy"], np.float32), A(frm["ex"], np.float32),
+            A(frm["ey"], np.float32), A(frm["octave"], np.int32), A(frm["desc"], np.uint8), A(frm.get("claimed"), np.uint8),
+            psf, C.c_int(len(sf)), C.c_float(log_scale_factor_lsd), C.byref(as_camera(cam)),
+            A(np.asarray(Tc).reshape(16), np.float64), C.c_int(m), A(kf["pos_w"], np.float64),
+            A(kf["min_valid_dist"], np.float32), A(kf["max_valid_dist"], np.float32), A(kf["desc"], np.uint8),
+            A(kf.get("valid"), np.uint8), C.c_float(margin), C.c_uint(hamm_dist_thr), matched.ctypes.data_as(_P),
+            q4[0].ctypes.data_as(_P), q4[1].ctypes.data_as(_P), q4[2].ctypes.data_as(_P), q4[3].ctypes.data_as(_P),
+            ql.ctypes.data_as(_P), qv.ctypes.data_as(_P))
+        q = dict(sp_x=q4[0], sp_y=q4[1], ep_x=q4[2], ep_y=q4[3], scale_level=ql, valid=qv, desc=kf["desc"])
+        return matched, int(num), q
+
     def match_frame_and_landmarks_line(self, scale_factors, frm, q, margin, lowe_ratio=0.6):
         keep = []
 
