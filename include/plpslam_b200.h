@@ -298,6 +298,39 @@ PLP_API plp_status plp_orb_get_pyramid(const plp_orb *orb, int b, int level, plp
 PLP_API plp_status plp_orb_debug_candidates(plp_orb *orb, int b, int level, plp_keypoint *out, int cap,
                                             int *n_out);
 
+/* robust::match_for_triangulation (match/robust.cc:43-216): for every landmark-free keypoint of keyframe 1 (visited in
+ * the order of its BoW feature vector: ascending node id, then the node's index list) the landmark-free, not yet taken
+ * keypoint of keyframe 2 in the SAME BoW node with the smallest Hamming distance <= 50 (ties: the later one in the
+ * node's list) that is not within 3 deg of the epipole (monocular pairs only, :150-161) and satisfies the epipolar
+ * constraint of E_12 within 0.2 deg x scale_factors_1[octave_1] (robust.cc:387-406); then the orientation histogram.
+ * The feature vectors are DBoW2::FeatureVector / fbow::BoWFeatVector flattened in iteration order (node ids ascending).
+ * epipole_bearing_in_2 = camera_->reproject_to_bearing(rot_2w, trans_2w, cam_center_1) (:54-57).
+ * matched_idx2_in_1_out[n1] = matched_indices_2_in_keyfrm_1 after the orientation check (-1: none); the adapter turns
+ * it into matched_idx_pairs in ascending idx_1 order (:201-213). */
+typedef struct plp_keyframe_points {
+    int32_t n;                   /* keyframe::num_keypts_                                            */
+    const uint8_t *desc;         /* descriptors_, n x 32                                             */
+    const float *angle;          /* undist_keypts_[i].angle (may be NULL without orientation check)  */
+    const int32_t *octave;       /* undist_keypts_[i].octave (used for keyframe 1 only)              */
+    const double *bearings;      /* bearings_, n x 3                                                 */
+    const uint8_t *has_landmark; /* get_landmarks()[i] != nullptr                                    */
+    const float *x_right;        /* stereo_x_right_ (NULL == monocular)                              */
+} plp_keyframe_points;
+
+typedef struct plp_bow_feature_vector {
+    int32_t num_nodes;
+    const uint32_t *node_ids; /* ascending                            */
+    const int32_t *offsets;   /* num_nodes + 1, into indices          */
+    const uint32_t *indices;  /* keypoint indices of each node        */
+} plp_bow_feature_vector;
+
+PLP_API plp_status plp_match_for_triangulation(plp_ctx *ctx, const plp_keyframe_points *kf1,
+                                               const plp_keyframe_points *kf2, const plp_bow_feature_vector *fv1,
+                                               const plp_bow_feature_vector *fv2, const double *E_12 /*3x3 row-major*/,
+                                               const double *epipole_bearing_in_2 /*3*/, const float *scale_factors_1,
+                                               int num_levels, int check_orientation,
+                                               int32_t *matched_idx2_in_1_out, uint32_t *num_matches_out);
+
 /* ------------------------------------------------------------------------ */
 /* stereo matching  (match/stereo.{h,cc})                                    */
 /* ------------------------------------------------------------------------ */

@@ -2,6 +2,7 @@
 // Follows /root/reference/src/PLPSLAM/match/{base.h,angle_checker.h,projection.cc,robust.cc},
 // data/common.{h,cc} and camera/perspective.cc; see oracle.h for the pinning status.
 #include "oracle.h"
+#include "detmath.h"
 
 #include <algorithm>
 #include <cmath>
@@ -526,6 +527,84 @@ unsigned orc_match_frame_and_keyframe_line(int n, const float *sx, const float *
         matched_kf_idx_out[best_idx] = idx;
         claimed[best_idx] = 1;
         ++num_matches;
+    }
+    return num_matches;
+}
+
+// match/robust.cc:387-406.  libm != 0: std::acos as the reference writes it; 0: acos(c) = atan2(sqrt((1-c)(1+c)), c) with
+// the deterministic kernel of detmath.h (what the CUDA path evaluates)
+static bool check_epipolar_constraint(const double *b1, const double *b2, const double *E, float sf1, int libm) {
+    const double e0 = E[0] * b2[0] + E[1] * b2[1] + E[2] * b2[2];
+    const double e1 = E[3] * b2[0] + E[4] * b2[1] + E[5] * b2[2];
+    const double e2 = E[6] * b2[0] + E[7] * b2[1] + E[8] * b2[2];
+    const double cos_residual = (e0 * b1[0] + e1 * b1[1] + e2 * b1[2]) / std::sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+    const double ac = libm ? std::acos(cos_residual)
+                           : det_atan2(std::sqrt((1.0 - cos_residual) * (1.0 + cos_residual)), cos_residual);
+    const double residual_rad = M_PI / 2.0 - std::abs(ac);
+    constexpr double residual_rad_thr = 0.2 * M_PI / 180.0;
+    return residual_rad < residual_rad_thr * sf1;
+}
+
+unsigned orc_match_for_triangulation(int n1, const uint8_t *desc1, const float *angle1, const int32_t *octave1,
+                                     const double *bearing1, const uint8_t *has_lm1, const float *x_right1, int n2,
+                                     const uint8_t *desc2, const float *angle2, const double *bearing2,
+                                     const uint8_t *has_lm2, const float *x_right2, int nodes1, const uint32_t *ids1,
+                                     const int32_t *off1, const uint32_t *idx1, int nodes2, const uint32_t *ids2,
+                                     const int32_t *off2, const uint32_t *idx2, const double *E_12, const double *epipole,
+                                     const float *scale_factors_1, int check_orientation, int libm,
+                                     int32_t *matched_idx2_in_1_out) {
+    // match/robust.cc:43-216
+    unsigned num_matches = 0;
+    AngleChecker angle_checker;
+    std::vector<bool> already2(n2, false);
+    for (int i = 0; i < n1; ++i) matched_idx2_in_1_out[i] = -1;
+    int a = 0, b = 0;
+    while (a < nodes1 && b < nodes2) {
+        if (ids1[a] == ids2[b]) {
+            for (int k1 = off1[a]; k1 < off1[a + 1]; ++k1) {
+                const unsigned i1 = idx1[k1];
+                if (has_lm1[i1]) continue;
+                const bool st1 = x_right1 ? 0 <= x_right1[i1] : false;
+                unsigned best_hamm_dist = HAMMING_DIST_THR_LOW;
+                int best_idx_2 = -1;
+                for (int k2 = off2[b]; k2 < off2[b + 1]; ++k2) {
+                    const unsigned i2 = idx2[k2];
+                    if (has_lm2[i2]) continue;
+                    if (already2[i2]) continue;
+                    const bool st2 = x_right2 ? 0 <= x_right2[i2] : false;
+                    const unsigned hamm_dist = orc_hamming_32(desc1 + 32 * i1, desc2 + 32 * i2);
+                    if (HAMMING_DIST_THR_LOW < hamm_dist || best_hamm_dist < hamm_dist) continue;
+                    if (!st1 && !st2) {
+                        const double *b2 = bearing2 + 3 * i2;
+                        const double cos_dist = epipole[0] * b2[0] + epipole[1] * b2[1] + epipole[2] * b2[2];
+                        constexpr double cos_dist_thr = 0.99862953475;
+                        if (cos_dist_thr < cos_dist) continue;
+                    }
+                    if (check_epipolar_constraint(bearing1 + 3 * i1, bearing2 + 3 * i2, E_12,
+                                                  scale_factors_1[octave1[i1]], libm)) {
+                        best_idx_2 = (int)i2;
+                        best_hamm_dist = hamm_dist;
+                    }
+                }
+                if (best_idx_2 < 0) continue;
+                already2[best_idx_2] = true;
+                matched_idx2_in_1_out[i1] = best_idx_2;
+                ++num_matches;
+                if (check_orientation) angle_checker.append(angle1[i1] - angle2[best_idx_2], (int)i1);
+            }
+            ++a;
+            ++b;
+        } else if (ids1[a] < ids2[b]) {
+            while (a < nodes1 && ids1[a] < ids2[b]) ++a;  // lower_bound(itr_2->first)
+        } else {
+            while (b < nodes2 && ids2[b] < ids1[a]) ++b;
+        }
+    }
+    if (check_orientation) {
+        for (const auto invalid_idx : angle_checker.collect(false)) {
+            matched_idx2_in_1_out[invalid_idx] = -1;
+            --num_matches;
+        }
     }
     return num_matches;
 }

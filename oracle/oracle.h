@@ -131,6 +131,16 @@ unsigned orc_match_frame_and_keyframe_line(int n, const float *sx, const float *
                                            unsigned hamm_dist_thr, int32_t *matched_kf_idx_out, float *q_sp_x,
                                            float *q_sp_y, float *q_ep_x, float *q_ep_y, int32_t *q_level, uint8_t *q_valid);
 
+/* ---- match/robust.cc:43-216 (+ 387-406).  Feature vectors flattened in iteration order (ascending node id). */
+unsigned orc_match_for_triangulation(int n1, const uint8_t *desc1, const float *angle1, const int32_t *octave1,
+                                     const double *bearing1, const uint8_t *has_lm1, const float *x_right1, int n2,
+                                     const uint8_t *desc2, const float *angle2, const double *bearing2,
+                                     const uint8_t *has_lm2, const float *x_right2, int nodes1, const uint32_t *ids1,
+                                     const int32_t *off1, const uint32_t *idx1, int nodes2, const uint32_t *ids2,
+                                     const int32_t *off2, const uint32_t *idx2, const double *E_12, const double *epipole,
+                                     const float *scale_factors_1, int check_orientation, int libm,
+                                     int32_t *matched_idx2_in_1_out);
+
 /* ---- match/robust.cc:257-385 --------------------------------------------------------- */
 unsigned orc_brute_force_match(const uint8_t *frm_desc, const float *frm_angle, int n_frm,
                                const uint8_t *kf_desc, const float *kf_angle,

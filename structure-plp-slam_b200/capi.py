@@ -90,6 +90,15 @@ class LastFrameLines(C.Structure):
     _fields_ = [("n", C.c_int32), ("pos_w", _P), ("octave", _P), ("desc", _P), ("valid", _P)]
 
 
+class KeyframePoints(C.Structure):
+    _fields_ = [("n", C.c_int32), ("desc", _P), ("angle", _P), ("octave", _P), ("bearings", _P), ("has_landmark", _P),
+                ("x_right", _P)]
+
+
+class BowFeatureVector(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("node_ids", _P), ("offsets", _P), ("indices", _P)]
+
+
 class OrbParams(C.Structure):
     _fields_ = [("max_num_keypts", C.c_uint32), ("scale_factor", C.c_float), ("num_levels", C.c_uint32),
                 ("ini_fast_thr", C.c_uint32), ("min_fast_thr", C.c_uint32)]
@@ -278,6 +287,30 @@ class Context:
             self._h, C.byref(fl), sf.ctypes.data_as(_P), C.c_int(len(sf)), C.byref(lq), C.c_float(margin),
             C.c_uint(hamm_dist_thr), matched.ctypes.data_as(_P), C.byref(num)))
         return matched, int(num.value)
+
+    def match_for_triangulation(self, kf1, kf2, fv1, fv2, E_12, epipole, scale_factors_1, check_orientation=True):
+        """robust::match_for_triangulation; kf = dict(desc, angle, octave, bearings, has_landmark[, x_right]);
+        fv = (node_ids, offsets, indices)."""
+        k = _Keep()
+
+        def kp(f):
+            return KeyframePoints(len(f["desc"]), k.arr(f["desc"], np.uint8), k.arr(f.get("angle"), np.float32),
+                                  k.arr(f.get("octave"), np.int32), k.arr(f["bearings"], np.float64),
+                                  k.arr(f["has_landmark"], np.uint8), k.arr(f.get("x_right"), np.float32))
+
+        def bv(f):
+            return BowFeatureVector(len(f[0]), k.arr(f[0], np.uint32), k.arr(f[1], np.int32), k.arr(f[2], np.uint32))
+        a, b, va, vb = kp(kf1), kp(kf2), bv(fv1), bv(fv2)
+        sf = np.ascontiguousarray(scale_factors_1, np.float32)
+        E = np.ascontiguousarray(E_12, np.float64).reshape(9)
+        ep = np.ascontiguousarray(epipole, np.float64).reshape(3)
+        matched = np.full(max(a.n, 1), -2, np.int32)
+        num = C.c_uint32(0)
+        self._check(self._lib.plp_match_for_triangulation(
+            self._h, C.byref(a), C.byref(b), C.byref(va), C.byref(vb), E.ctypes.data_as(_P), ep.ctypes.data_as(_P),
+            sf.ctypes.data_as(_P), C.c_int(len(sf)), C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P),
+            C.byref(num)))
+        return matched[:a.n].copy(), int(num.value)
 
     @staticmethod
     def _frame_lines(k, f):

@@ -16,6 +16,7 @@
 //
 // Compiled with -fmad=false: float/double expressions must round exactly like the oracle.
 #include "match_kernels.cuh"
+#include "detmath.h"
 #include "pack.cuh"
 
 namespace plp {
@@ -759,6 +760,137 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (tid == 0 && J.num_matches) *J.num_matches = (uint32_t)(flags[1] - flags[2]);
 }
 
+// ---------------------------------------------------------------------------------------
+// robust::match_for_triangulation (match/robust.cc:43-216)
+// ---------------------------------------------------------------------------------------
+struct TriJob {
+    int n1, n2, num_seq;
+    const uint8_t *desc1, *desc2;
+    const float *angle1, *angle2;
+    const int32_t *octave1;
+    const double *bearing1, *bearing2;   // n x 3
+    const uint8_t *has_lm2;
+    const uint8_t *stereo1, *stereo2;    // 0 <= stereo_x_right; may be null (monocular)
+    const int32_t *seq_idx1;             // processing order: keyframe-1 keypoint of step p (landmark-free ones only)
+    const int32_t *seq_cbeg, *seq_cend;  // candidate span of step p in cand2 (the keyframe-2 indices of the same BoW node)
+    const int32_t *cand2;
+    const float *scale_factors1;
+    double E[9], epipole[3];
+    int32_t *choice;       // num_seq
+    int32_t *matched_out;  // n1
+    uint32_t *num_matches;
+};
+
+// robust.cc:387-406; acos(c) is evaluated as atan2(sqrt((1 - c)(1 + c)), c) with the deterministic kernel of detmath.h
+__device__ __forceinline__ bool check_epipolar_constraint(const double *b1, const double *b2, const double *E, float sf1) {
+    const double e0 = E[0] * b2[0] + E[1] * b2[1] + E[2] * b2[2];
+    const double e1 = E[3] * b2[0] + E[4] * b2[1] + E[5] * b2[2];
+    const double e2 = E[6] * b2[0] + E[7] * b2[1] + E[8] * b2[2];
+    const double cos_residual = (e0 * b1[0] + e1 * b1[1] + e2 * b1[2]) / sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+    const double ac = det_atan2(sqrt((1.0 - cos_residual) * (1.0 + cos_residual)), cos_residual);
+    const double residual_rad = 3.14159265358979323846 / 2.0 - fabs(ac);
+    const double residual_rad_thr = 0.2 * 3.14159265358979323846 / 180.0;
+    return residual_rad < residual_rad_thr * (double)sf1;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) triangulation_match_kernel(const TriJob *__restrict__ jobs, int cap2,
+                                                                          int check_orientation) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const TriJob &J = jobs[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int n1 = J.n1, n2 = J.n2, P = J.num_seq;
+    int *owner_prev = reinterpret_cast<int *>(smem_raw);
+    int *owner_next = owner_prev + cap2;
+    int *hist = owner_next + cap2;
+    int *flags = hist + kHistLen;
+    uint8_t *bin_valid = reinterpret_cast<uint8_t *>(flags + 4);
+    for (int j = tid; j < n2; j += kThreads) {
+        owner_prev[j] = 0x7fffffff;
+        owner_next[j] = 0x7fffffff;
+    }
+    if (tid < 4) flags[tid] = 0;
+    for (int b = tid; b < kHistLen; b += kThreads) hist[b] = 0;
+    __syncthreads();
+    // Sequential semantics: step p takes the best candidate not taken by an earlier step.  Iterating
+    // "choice[p] = best candidate not owned by a step < p" reaches the unique fixed point (step p depends only on < p).
+    for (int round = 0; round <= P; ++round) {
+        for (int p = tid; p < P; p += kThreads) {
+            const int i1 = J.seq_idx1[p];
+            uint4 q0, q1;
+            load_desc(J.desc1 + 32 * (size_t)i1, q0, q1);
+            const double *b1 = J.bearing1 + 3 * (size_t)i1;
+            const bool st1 = J.stereo1 ? (J.stereo1[i1] != 0) : false;
+            const float sf1 = J.scale_factors1[J.octave1[i1]];
+            unsigned best = PLP_HAMMING_DIST_THR_LOW;
+            int best_j = -1;
+            for (int c = J.seq_cbeg[p]; c < J.seq_cend[p]; ++c) {
+                const int j = J.cand2[c];
+                if (J.has_lm2[j]) continue;
+                if (owner_prev[j] < p) continue;  // is_already_matched_in_keyfrm_2
+                uint4 d0, d1;
+                load_desc(J.desc2 + 32 * (size_t)j, d0, d1);
+                const unsigned d = (unsigned)hamming256(q0, q1, d0, d1);
+                if (PLP_HAMMING_DIST_THR_LOW < d || best < d) continue;
+                const double *b2 = J.bearing2 + 3 * (size_t)j;
+                const bool st2 = J.stereo2 ? (J.stereo2[j] != 0) : false;
+                if (!st1 && !st2) {
+                    const double cos_dist = J.epipole[0] * b2[0] + J.epipole[1] * b2[1] + J.epipole[2] * b2[2];
+                    if (0.99862953475 < cos_dist) continue;
+                }
+                if (check_epipolar_constraint(b1, b2, J.E, sf1)) {
+                    best_j = j;
+                    best = d;
+                }
+            }
+            J.choice[p] = best_j;
+            if (best_j >= 0) atomicMin(&owner_next[best_j], p);
+        }
+        __syncthreads();
+        for (int j = tid; j < n2; j += kThreads)
+            if (owner_next[j] != owner_prev[j]) flags[0] = 1;
+        __syncthreads();
+        const int changed = flags[0];
+        __syncthreads();
+        if (!changed) break;
+        if (tid == 0) flags[0] = 0;
+        int *t = owner_prev;
+        owner_prev = owner_next;
+        owner_next = t;
+        for (int j = tid; j < n2; j += kThreads) owner_next[j] = 0x7fffffff;
+        __syncthreads();
+    }
+    for (int i = tid; i < n1; i += kThreads) J.matched_out[i] = -1;
+    __syncthreads();
+    const bool do_angle = check_orientation && J.angle1 && J.angle2;
+    for (int p = tid; p < P; p += kThreads) {
+        const int j = J.choice[p];
+        if (j < 0) continue;
+        atomicAdd(&flags[1], 1);
+        if (do_angle) atomicAdd(&hist[angle_bin(J.angle1[J.seq_idx1[p]] - J.angle2[j])], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (do_angle)
+            rank_bins(hist, bin_valid);
+        else
+            for (int b = 0; b < kHistLen; ++b) bin_valid[b] = 1;
+    }
+    __syncthreads();
+    for (int p = tid; p < P; p += kThreads) {
+        const int j = J.choice[p];
+        if (j < 0) continue;
+        const int i1 = J.seq_idx1[p];
+        bool keep = true;
+        if (do_angle) keep = bin_valid[angle_bin(J.angle1[i1] - J.angle2[j])] != 0;
+        if (keep)
+            J.matched_out[i1] = j;
+        else
+            atomicAdd(&flags[2], 1);
+    }
+    __syncthreads();
+    if (tid == 0 && J.num_matches) *J.num_matches = (uint32_t)(flags[1] - flags[2]);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -1396,6 +1528,112 @@ plp_status plp_match_brute_force(plp_ctx *ctx, const uint8_t *frm_desc, const fl
     uint32_t num = 0;
     PLP_CUDA_TRY(cudaMemcpyAsync(matched_kf_idx_in_frm_out, d + o_matched, (size_t)n_frm * 4, cudaMemcpyDeviceToHost,
                                  ctx->stream));
+    PLP_CUDA_TRY(cudaMemcpyAsync(&num, d + o_num, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (num_matches_out) *num_matches_out = num;
+    return PLP_OK;
+}
+
+plp_status plp_match_for_triangulation(plp_ctx *ctx, const plp_keyframe_points *kf1, const plp_keyframe_points *kf2,
+                                       const plp_bow_feature_vector *fv1, const plp_bow_feature_vector *fv2,
+                                       const double *E_12, const double *epipole_bearing_in_2, const float *scale_factors_1,
+                                       int num_levels, int check_orientation, int32_t *matched_idx2_in_1_out,
+                                       uint32_t *num_matches_out) {
+    PLP_REQUIRE(ctx && kf1 && kf2 && fv1 && fv2 && E_12 && epipole_bearing_in_2 && scale_factors_1 && matched_idx2_in_1_out,
+                "null pointer");
+    PLP_REQUIRE(kf1->n >= 0 && kf2->n >= 0 && num_levels > 0 && fv1->num_nodes >= 0 && fv2->num_nodes >= 0, "sizes");
+    if (num_matches_out) *num_matches_out = 0;
+    for (int i = 0; i < kf1->n; ++i) matched_idx2_in_1_out[i] = -1;
+    if (kf1->n == 0 || kf2->n == 0 || fv1->num_nodes == 0 || fv2->num_nodes == 0) return PLP_OK;
+    PLP_REQUIRE(kf1->desc && kf1->octave && kf1->bearings && kf1->has_landmark, "keyframe 1 arrays");
+    PLP_REQUIRE(kf2->desc && kf2->bearings && kf2->has_landmark, "keyframe 2 arrays");
+    PLP_REQUIRE(!check_orientation || (kf1->angle && kf2->angle), "angles required for the orientation check");
+    PLP_REQUIRE(fv1->node_ids && fv1->offsets && fv1->indices && fv2->node_ids && fv2->offsets && fv2->indices,
+                "feature vectors");
+    PLP_REQUIRE(kf2->n <= 24000, "keyframe 2 keypoint capacity 24000");
+    // merge-join of the two (ascending) feature vectors, robust.cc:78-199: processing order and candidate spans
+    std::vector<int32_t> seq_idx1, seq_cbeg, seq_cend, cand2;
+    int a = 0, b = 0;
+    while (a < fv1->num_nodes && b < fv2->num_nodes) {
+        if (fv1->node_ids[a] == fv2->node_ids[b]) {
+            const int cb = (int)cand2.size();
+            for (int k = fv2->offsets[b]; k < fv2->offsets[b + 1]; ++k) {
+                PLP_REQUIRE(fv2->indices[k] < (uint32_t)kf2->n, "feature vector index out of range");
+                cand2.push_back((int32_t)fv2->indices[k]);
+            }
+            const int ce = (int)cand2.size();
+            for (int k = fv1->offsets[a]; k < fv1->offsets[a + 1]; ++k) {
+                const uint32_t i1 = fv1->indices[k];
+                PLP_REQUIRE(i1 < (uint32_t)kf1->n, "feature vector index out of range");
+                PLP_REQUIRE(kf1->octave[i1] >= 0 && kf1->octave[i1] < num_levels, "octave range");
+                if (kf1->has_landmark[i1]) continue;  // robust.cc:99-103
+                seq_idx1.push_back((int32_t)i1);
+                seq_cbeg.push_back(cb);
+                seq_cend.push_back(ce);
+            }
+            ++a;
+            ++b;
+        } else if (fv1->node_ids[a] < fv2->node_ids[b]) {
+            ++a;  // lower_bound(itr_2->first) on an ascending map == skip the smaller ids
+        } else {
+            ++b;
+        }
+    }
+    const int P = (int)seq_idx1.size();
+    if (P == 0) return PLP_OK;
+    PLP_CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t n1 = kf1->n, n2 = kf2->n;
+    std::vector<uint8_t> st1(n1, 0), st2(n2, 0);
+    if (kf1->x_right)
+        for (size_t i = 0; i < n1; ++i) st1[i] = 0 <= kf1->x_right[i];
+    if (kf2->x_right)
+        for (size_t i = 0; i < n2; ++i) st2[i] = 0 <= kf2->x_right[i];
+    Packer pk;
+    TriJob J;
+    memset(&J, 0, sizeof(J));
+    const size_t o_d1 = pk.add(kf1->desc, n1 * 32), o_d2 = pk.add(kf2->desc, n2 * 32);
+    const size_t o_a1 = pk.add(kf1->angle, n1 * 4), o_a2 = pk.add(kf2->angle, n2 * 4);
+    const size_t o_o1 = pk.add(kf1->octave, n1 * 4);
+    const size_t o_b1 = pk.add(kf1->bearings, n1 * 24), o_b2 = pk.add(kf2->bearings, n2 * 24);
+    const size_t o_l2 = pk.add(kf2->has_landmark, n2);
+    const size_t o_s1 = pk.add(st1.data(), n1), o_s2 = pk.add(st2.data(), n2);
+    const size_t o_q1 = pk.add(seq_idx1.data(), (size_t)P * 4), o_qb = pk.add(seq_cbeg.data(), (size_t)P * 4);
+    const size_t o_qe = pk.add(seq_cend.data(), (size_t)P * 4), o_c2 = pk.add(cand2.data(), cand2.size() * 4);
+    const size_t o_sf = pk.add(scale_factors_1, (size_t)num_levels * 4);
+    const size_t o_choice = pk.reserve((size_t)P * 4), o_matched = pk.reserve(n1 * 4), o_num = pk.reserve(4);
+    const size_t o_job = pk.reserve(sizeof(TriJob));
+    uint8_t *d;
+    PLP_TRY(pk.upload(ctx, 0, &d));
+    J.n1 = (int)n1;
+    J.n2 = (int)n2;
+    J.num_seq = P;
+    J.desc1 = Packer::at<uint8_t>(d, o_d1);
+    J.desc2 = Packer::at<uint8_t>(d, o_d2);
+    J.angle1 = kf1->angle ? Packer::at<float>(d, o_a1) : nullptr;
+    J.angle2 = kf2->angle ? Packer::at<float>(d, o_a2) : nullptr;
+    J.octave1 = Packer::at<int32_t>(d, o_o1);
+    J.bearing1 = Packer::at<double>(d, o_b1);
+    J.bearing2 = Packer::at<double>(d, o_b2);
+    J.has_lm2 = Packer::at<uint8_t>(d, o_l2);
+    J.stereo1 = Packer::at<uint8_t>(d, o_s1);
+    J.stereo2 = Packer::at<uint8_t>(d, o_s2);
+    J.seq_idx1 = Packer::at<int32_t>(d, o_q1);
+    J.seq_cbeg = Packer::at<int32_t>(d, o_qb);
+    J.seq_cend = Packer::at<int32_t>(d, o_qe);
+    J.cand2 = Packer::at<int32_t>(d, o_c2);
+    J.scale_factors1 = Packer::at<float>(d, o_sf);
+    for (int k = 0; k < 9; ++k) J.E[k] = E_12[k];
+    for (int k = 0; k < 3; ++k) J.epipole[k] = epipole_bearing_in_2[k];
+    J.choice = Packer::at<int32_t>(d, o_choice);
+    J.matched_out = Packer::at<int32_t>(d, o_matched);
+    J.num_matches = Packer::at<uint32_t>(d, o_num);
+    PLP_CUDA_TRY(cudaMemcpyAsync(d + o_job, &J, sizeof(J), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t smem = (size_t)n2 * 8 + (kHistLen + 4) * 4 + kHistLen + 16;
+    PLP_CUDA_TRY(cudaFuncSetAttribute(triangulation_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLP_LAUNCH(ctx, triangulation_match_kernel, 1, kThreads, smem, Packer::at<TriJob>(d, o_job), (int)n2, check_orientation);
+    PLP_CHECK_LAUNCH();
+    uint32_t num = 0;
+    PLP_CUDA_TRY(cudaMemcpyAsync(matched_idx2_in_1_out, d + o_matched, n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PLP_CUDA_TRY(cudaMemcpyAsync(&num, d + o_num, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (num_matches_out) *num_matches_out = num;

@@ -207,6 +207,29 @@ class Oracle:
         q = dict(sp_x=q4[0], sp_y=q4[1], ep_x=q4[2], ep_y=q4[3], scale_level=ql, valid=qv, desc=kf["desc"])
         return matched, int(num), q
 
+    def match_for_triangulation(self, kf1, kf2, fv1, fv2, E_12, epipole, scale_factors_1, check_orientation=True,
+                                libm=0):
+        keep = []
+
+        def A(v, dt):
+            arr, p = _a(v, dt)
+            keep.append(arr)
+            return p
+        n1, n2 = len(kf1["desc"]), len(kf2["desc"])
+        matched = np.full(max(n1, 1), -2, np.int32)
+        self.lib.orc_match_for_triangulation.restype = C.c_uint
+        num = self.lib.orc_match_for_triangulation(
+            C.c_int(n1), A(kf1["desc"], np.uint8), A(kf1.get("angle"), np.float32), A(kf1["octave"], np.int32),
+            A(kf1["bearings"], np.float64), A(kf1["has_landmark"], np.uint8), A(kf1.get("x_right"), np.float32),
+            C.c_int(n2), A(kf2["desc"], np.uint8), A(kf2.get("angle"), np.float32), A(kf2["bearings"], np.float64),
+            A(kf2["has_landmark"], np.uint8), A(kf2.get("x_right"), np.float32),
+            C.c_int(len(fv1[0])), A(fv1[0], np.uint32), A(fv1[1], np.int32), A(fv1[2], np.uint32),
+            C.c_int(len(fv2[0])), A(fv2[0], np.uint32), A(fv2[1], np.int32), A(fv2[2], np.uint32),
+            A(np.asarray(E_12).reshape(9), np.float64), A(np.asarray(epipole).reshape(3), np.float64),
+            A(scale_factors_1, np.float32), C.c_int(1 if check_orientation else 0), C.c_int(libm),
+            matched.ctypes.data_as(_P))
+        return matched[:n1].copy(), int(num)
+
     def match_frame_and_landmarks_line(self, scale_factors, frm, q, margin, lowe_ratio=0.6):
         keep = []
 

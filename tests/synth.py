@@ -352,3 +352,63 @@ def make_stereo_pair(seed, h=480, w=752, bf=47.906, n_bands=6):
     noise = rng.normal(0, 1.5, (h, w))
     right = np.clip(np.round(right.astype(np.float64) + noise), 0, 255).astype(np.uint8)
     return left, right, disp
+
+
+def make_triangulation_scene(seed, n=1200, stereo=False, num_levels=8, n_nodes=90):
+    """Two keyframes observing a common point cloud, their relative essential matrix, and synthetic BoW feature vectors
+    (points near each other in descriptor space share a node; a few nodes exist in only one keyframe)."""
+    rng = np.random.default_rng(seed)
+    T1 = np.eye(4)
+    T2 = make_pose(rng, 0.05, 0.4)
+    X = np.stack([rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.uniform(2, 12, n)], 1)
+    node_of_point = rng.integers(0, n_nodes, n)
+    desc = rand_desc(rng, n)
+
+    def view(T, keep_frac, noise_px):
+        uv, z = project(T, X)
+        keep = (rng.random(n) < keep_frac) & (z > 0.1)
+        idx = np.nonzero(keep)[0]
+        uv = uv[idx] + rng.normal(0, noise_px, (len(idx), 2))
+        b = np.stack([(uv[:, 0] - CX) / FX, (uv[:, 1] - CY) / FY, np.ones(len(idx))], 1)
+        b /= np.linalg.norm(b, axis=1, keepdims=True)
+        d = flip_bits(rng, desc[idx], rng.integers(0, 45, len(idx)))
+        nodes = node_of_point[idx].copy()
+        # clutter: unrelated keypoints
+        nc = len(idx) // 5
+        bc = rng.normal(0, 1, (nc, 3)); bc[:, 2] = np.abs(bc[:, 2]) + 1.0
+        bc /= np.linalg.norm(bc, axis=1, keepdims=True)
+        b = np.concatenate([b, bc]); d = np.concatenate([d, rand_desc(rng, nc)])
+        nodes = np.concatenate([nodes, rng.integers(0, n_nodes + 10, nc)])
+        m = len(b)
+        perm = rng.permutation(m)
+        b, d, nodes = b[perm], d[perm], nodes[perm]
+        f = dict(desc=d, bearings=b, angle=rng.uniform(0, 360, m).astype(np.float32),
+                 octave=rng.integers(0, num_levels, m).astype(np.int32),
+                 has_landmark=(rng.random(m) < 0.3).astype(np.uint8))
+        if stereo:
+            xr = np.full(m, -1.0, np.float32)
+            has = rng.random(m) < 0.5
+            xr[has] = rng.uniform(1, 600, has.sum()).astype(np.float32)
+            f["x_right"] = xr
+        # feature vector: ascending node ids, random order inside a node (DBoW2 appends in keypoint order; any order is legal)
+        ids = np.unique(nodes)
+        ids = ids[rng.random(len(ids)) < 0.9]
+        offsets, indices = [0], []
+        for nid in ids:
+            members = np.nonzero(nodes == nid)[0]
+            indices.extend(members.tolist())
+            offsets.append(len(indices))
+        fv = (ids.astype(np.uint32), np.array(offsets, np.int32), np.array(indices, np.uint32))
+        return f, fv, idx
+
+    kf1, fv1, _ = view(T1, 0.8, 0.4)
+    kf2, fv2, _ = view(T2, 0.8, 0.4)
+    # consistent angles for true pairs are irrelevant for parity; E_12 = [t_12]x R_12 with x1^T E x2 = 0
+    T12 = T1 @ np.linalg.inv(T2)
+    R12, t12 = T12[:3, :3], T12[:3, 3]
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    E12 = tx @ R12
+    c1 = -T1[:3, :3].T @ T1[:3, 3]
+    ep = T2[:3, :3] @ c1 + T2[:3, 3]
+    ep = ep / np.linalg.norm(ep)
+    return kf1, kf2, fv1, fv2, E12, ep
