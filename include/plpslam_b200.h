@@ -331,6 +331,15 @@ PLP_API plp_status plp_match_for_triangulation(plp_ctx *ctx, const plp_keyframe_
                                                int num_levels, int check_orientation,
                                                int32_t *matched_idx2_in_1_out, uint32_t *num_matches_out);
 
+/* landmark::compute_descriptor / Line::compute_descriptor (data/landmark.cc:181-247, data/landmark_line.cc:215-283) for
+ * a batch of landmarks (the mapping thread calls it for every landmark touched by a new keyframe or a fuse,
+ * mapping_module.cc:704,756): descs holds the observation descriptors of landmark l at rows offsets[l] .. offsets[l+1];
+ * best_idx_out[l] = local index of the observation whose median Hamming distance to all observations
+ * (element floor(0.5 (k - 1)) of the sorted row) is smallest, first one on ties; -1 for a landmark without observations
+ * (the reference returns without touching descriptor_). */
+PLP_API plp_status plp_landmark_compute_descriptor_batch(plp_ctx *ctx, const uint8_t *descs, const int32_t *offsets,
+                                                         int num_landmarks, int32_t *best_idx_out);
+
 /* ------------------------------------------------------------------------ */
 /* stereo matching  (match/stereo.{h,cc})                                    */
 /* ------------------------------------------------------------------------ */
@@ -539,6 +548,14 @@ typedef struct plp_ba_comm plp_ba_comm; /* NCCL communicator for landmark-sharde
  * force_stop may be NULL; it is polled between chunks of LM iterations (mapping_module.cc:159-164). */
 PLP_API plp_status plp_local_ba(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg *cfg,
                                 volatile const uint8_t *force_stop, plp_ba_result *r);
+/* optimize::global_bundle_adjuster::optimize (optimize/global_bundle_adjuster.cc:64-253) on the same problem layout:
+ * every keyframe / point / line landmark of the map, kf_fixed = (keyframe id == 0) only, ONE optimize(num_iter) with or
+ * without the Huber kernel (use_huber_kernel_), no outlier rounds (the outlier arrays of `r` come back zero).  This entry
+ * point shares the dense in-shared-memory reduced-camera solve of the local adjuster and therefore accepts at most 32
+ * non-fixed keyframes -- enough for the map-initialisation call (module/initializer.cc:306-307: 2 keyframes, 20
+ * iterations); larger maps (loop_bundle_adjuster.cc:81-82) return PLP_ERR_CAPACITY until the reduced system moves to HBM. */
+PLP_API plp_status plp_global_ba(plp_ctx *ctx, const plp_ba_problem *p, int num_iter, int use_huber_kernel,
+                                 volatile const uint8_t *force_stop, plp_ba_result *r);
 /* split form: upload once, solve (repeatable), destroy.  With `comm`, `p` holds THIS RANK's block of landmarks
  * (all keyframes, its points/lines and their edges); every rank calls the same functions. */
 PLP_API plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg *cfg, plp_ba_comm *comm,

@@ -637,3 +637,70 @@ extern "C" int orc_local_ba(const orc_ba_problem *p, int num_first_iter, int num
     r->final_chi2 = S.active_robust_chi2();
     return r->iters_first + r->iters_second;
 }
+
+extern "C" int orc_global_ba(const orc_ba_problem *p, int num_iter, int use_huber_kernel,
+                            const volatile uint8_t *force_stop, orc_ba_result *r) {
+    const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
+    Solver S;
+    S.cam = {p->fx, p->fy, p->cx, p->cy, p->focal_x_baseline};
+    S.n_kf = p->n_kf;
+    S.n_pts = p->n_pts;
+    S.n_lines = p->n_lines;
+    S.kf.resize(p->n_kf);
+    S.kf_fixed.assign(p->kf_fixed, p->kf_fixed + p->n_kf);
+    S.kf_hidx.assign(p->n_kf, -1);
+    for (int k = 0; k < p->n_kf; ++k) {
+        S.kf[k] = se3_from_matrix(p->kf_pose_cw + 16 * (size_t)k);
+        if (!p->kf_fixed[k]) S.kf_hidx[k] = S.n_free++;
+    }
+    S.pts.resize(p->n_pts);
+    for (int l = 0; l < p->n_pts; ++l) S.pts[l] = {{p->pt_pos_w[3 * l], p->pt_pos_w[3 * l + 1], p->pt_pos_w[3 * l + 2]}};
+    S.lines.resize(p->n_lines);
+    for (int l = 0; l < p->n_lines; ++l)
+        for (int k = 0; k < 6; ++k) S.lines[l].v[k] = p->line_plucker[6 * (size_t)l + k];
+    S.delta_pt = p->setup_type == 0 ? std::sqrt(chi_sq_2D) : std::sqrt(chi_sq_3D);
+    S.delta_line = std::sqrt(chi_sq_2D);
+    S.pe.resize(p->n_pt_edges);
+    for (int i = 0; i < p->n_pt_edges; ++i) {
+        auto &e = S.pe[i];
+        e.kf = p->pt_edge_kf[i];
+        e.lm = p->pt_edge_lm[i];
+        e.obs[0] = p->pt_edge_obs[3 * i];
+        e.obs[1] = p->pt_edge_obs[3 * i + 1];
+        e.obs[2] = p->pt_edge_obs[3 * i + 2];
+        e.stereo = !(p->pt_edge_obs[3 * i + 2] < 0);
+        e.info = p->pt_edge_inv_sigma_sq[i];
+    }
+    S.le.resize(p->n_line_edges);
+    for (int i = 0; i < p->n_line_edges; ++i) {
+        auto &e = S.le[i];
+        e.kf = p->line_edge_kf[i];
+        e.lm = p->line_edge_lm[i];
+        for (int k = 0; k < 4; ++k) e.obs[k] = p->line_edge_obs[4 * i + k];
+        e.info = p->line_edge_inv_sigma_sq[i];
+    }
+    S.ple.resize(p->n_plane_edges);
+    for (int i = 0; i < p->n_plane_edges; ++i) {
+        S.ple[i].lm = p->plane_edge_lm[i];
+        for (int k = 0; k < 4; ++k) S.ple[i].fn[k] = p->plane_edge_fn[4 * i + k];
+    }
+    // optimize/global_bundle_adjuster.cc:64-253: the same vertices / edges as the local adjusters over ALL keyframes and
+    // landmarks (only keyframe id 0 fixed), one optimize(num_iter) with or without the Huber kernel, no outlier rounds
+    r->iters_first = r->iters_second = 0;
+    r->lm_tries = 0;
+    for (int i = 0; i < p->n_pt_edges; ++i) r->pt_edge_outlier[i] = 0;
+    for (int i = 0; i < p->n_line_edges; ++i) r->line_edge_outlier[i] = 0;
+    if (!use_huber_kernel) {
+        for (auto &e : S.pe) e.robust = false;
+        for (auto &e : S.le) e.robust = false;
+    }
+    r->iters_first = S.optimize(num_iter, force_stop, &r->lm_tries);
+    for (int k = 0; k < p->n_kf; ++k) se3_to_matrix(S.kf[k], r->kf_pose_cw + 16 * (size_t)k);
+    for (int l = 0; l < p->n_pts; ++l)
+        for (int a = 0; a < 3; ++a) r->pt_pos_w[3 * l + a] = S.pts[l][a];
+    for (int l = 0; l < p->n_lines; ++l)
+        for (int k = 0; k < 6; ++k) r->line_plucker[6 * (size_t)l + k] = S.lines[l].v[k];
+    S.compute_active_errors();
+    r->final_chi2 = S.active_robust_chi2();
+    return r->iters_first;
+}

@@ -44,6 +44,10 @@ typedef struct orc_ba_result {
 int orc_local_ba(const orc_ba_problem *p, int num_first_iter, int num_second_iter, const volatile uint8_t *force_stop,
                  orc_ba_result *r);
 
+/* optimize/global_bundle_adjuster.cc:64-253 on the same problem layout (kf_fixed = keyframe id 0 only) */
+int orc_global_ba(const orc_ba_problem *p, int num_iter, int use_huber_kernel, const volatile uint8_t *force_stop,
+                  orc_ba_result *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -609,6 +609,38 @@ unsigned orc_match_for_triangulation(int n1, const uint8_t *desc1, const float *
     return num_matches;
 }
 
+void orc_landmark_compute_descriptor_batch(const uint8_t *descs, const int32_t *offsets, int num_landmarks,
+                                           int32_t *best_idx_out) {
+    // data/landmark.cc:181-247
+    for (int l = 0; l < num_landmarks; ++l) {
+        const int beg = offsets[l], num_descs = offsets[l + 1] - beg;
+        if (num_descs <= 0) {
+            best_idx_out[l] = -1;
+            continue;
+        }
+        std::vector<std::vector<unsigned>> hamm_dists(num_descs, std::vector<unsigned>(num_descs));
+        for (int i = 0; i < num_descs; ++i) {
+            hamm_dists[i][i] = 0;
+            for (int j = i + 1; j < num_descs; ++j) {
+                const auto dist = orc_hamming_32(descs + 32 * (size_t)(beg + i), descs + 32 * (size_t)(beg + j));
+                hamm_dists[i][j] = dist;
+                hamm_dists[j][i] = dist;
+            }
+        }
+        unsigned best_median_dist = MAX_HAMMING_DIST, best_idx = 0;
+        for (int idx = 0; idx < num_descs; ++idx) {
+            std::vector<unsigned> partial(hamm_dists[idx].begin(), hamm_dists[idx].begin() + num_descs);
+            std::sort(partial.begin(), partial.end());
+            const auto median_dist = partial.at(static_cast<unsigned>(0.5 * (num_descs - 1)));
+            if (median_dist < best_median_dist) {
+                best_median_dist = median_dist;
+                best_idx = idx;
+            }
+        }
+        best_idx_out[l] = (int)best_idx;
+    }
+}
+
 unsigned orc_match_frame_and_landmarks_line(int n, const float *sx, const float *sy, const float *ex,
                                             const float *ey, const int32_t *octave,
                                             const int32_t *ratio_level, const uint8_t *desc,

@@ -141,6 +141,10 @@ unsigned orc_match_for_triangulation(int n1, const uint8_t *desc1, const float *
                                      const float *scale_factors_1, int check_orientation, int libm,
                                      int32_t *matched_idx2_in_1_out);
 
+/* ---- data/landmark.cc:181-247 (and data/landmark_line.cc:215-283) */
+void orc_landmark_compute_descriptor_batch(const uint8_t *descs, const int32_t *offsets, int num_landmarks,
+                                           int32_t *best_idx_out);
+
 /* ---- match/robust.cc:257-385 --------------------------------------------------------- */
 unsigned orc_brute_force_match(const uint8_t *frm_desc, const float *frm_angle, int n_frm,
                                const uint8_t *kf_desc, const float *kf_angle,

@@ -113,3 +113,20 @@ def shard_edges(edge_lm, lm_begin: int, lm_end: int):
     edge_lm = np.asarray(edge_lm)
     sel = np.nonzero((edge_lm >= lm_begin) & (edge_lm < lm_end))[0]
     return sel, (edge_lm[sel] - lm_begin).astype(np.int32)
+
+
+def global_ba(ctx: Context, problem_struct, n_sizes, num_iter=20, use_huber_kernel=True, force_stop=None):
+    """optimize::global_bundle_adjuster::optimize (global_bundle_adjuster.cc:64-253) through plp_global_ba."""
+    n_kf, n_pts, n_lines, n_pe, n_le = n_sizes
+    out = dict(kf_pose_cw=np.zeros((n_kf, 4, 4)), pt_pos_w=np.zeros((max(n_pts, 1), 3)),
+               line_plucker=np.zeros((max(n_lines, 1), 6)), pt_edge_outlier=np.zeros(max(n_pe, 1), np.uint8),
+               line_edge_outlier=np.zeros(max(n_le, 1), np.uint8))
+    r = BaResult(*[out[k].ctypes.data_as(_P) for k in ("kf_pose_cw", "pt_pos_w", "line_plucker", "pt_edge_outlier",
+                                                       "line_edge_outlier")], 0, 0, 0, 0.0)
+    fs = None if force_stop is None else force_stop.ctypes.data_as(_P)
+    ctx._check(ctx._lib.plp_global_ba(ctx.handle, C.byref(problem_struct), C.c_int(num_iter),
+                                      C.c_int(1 if use_huber_kernel else 0), fs, C.byref(r)))
+    out["pt_pos_w"] = out["pt_pos_w"][:n_pts]
+    out["line_plucker"] = out["line_plucker"][:n_lines]
+    out.update(iters_first=r.iters_first, lm_tries=r.lm_tries, final_chi2=r.final_chi2)
+    return out

@@ -288,6 +288,15 @@ class Context:
             C.c_uint(hamm_dist_thr), matched.ctypes.data_as(_P), C.byref(num)))
         return matched, int(num.value)
 
+    def landmark_compute_descriptor_batch(self, descs, offsets):
+        """landmark::compute_descriptor for a batch: index of the median-distance observation per landmark."""
+        d = np.ascontiguousarray(descs, np.uint8).reshape(-1, 32)
+        o = np.ascontiguousarray(offsets, np.int32)
+        out = np.full(max(len(o) - 1, 1), -2, np.int32)
+        self._check(self._lib.plp_landmark_compute_descriptor_batch(self._h, d.ctypes.data_as(_P), o.ctypes.data_as(_P),
+                                                                   C.c_int(len(o) - 1), out.ctypes.data_as(_P)))
+        return out[:len(o) - 1].copy()
+
     def match_for_triangulation(self, kf1, kf2, fv1, fv2, E_12, epipole, scale_factors_1, check_orientation=True):
         """robust::match_for_triangulation; kf = dict(desc, angle, octave, bearings, has_landmark[, x_right]);
         fv = (node_ids, offsets, indices)."""

@@ -347,7 +347,15 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
     return PLP_OK;
 }
 
+// mode 0: local BA (optimize(first) with Huber, outlier classification, optimize(second) without);
+// mode 1 / 2: global BA = one optimize(first) with (1) / without (2) the Huber kernel, no outlier rounds
+static plp_status ba_solve_impl(plp_ba *b, volatile const uint8_t *force_stop, plp_ba_result *r, int mode);
+
 plp_status plp_ba_solve(plp_ba *b, volatile const uint8_t *force_stop, plp_ba_result *r) {
+    return ba_solve_impl(b, force_stop, r, 0);
+}
+
+static plp_status ba_solve_impl(plp_ba *b, volatile const uint8_t *force_stop, plp_ba_result *r, int mode) {
     PLP_REQUIRE(b && r, "null pointer");
     plp_ctx *ctx = b->ctx;
     PLP_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -366,14 +374,16 @@ plp_status plp_ba_solve(plp_ba *b, volatile const uint8_t *force_stop, plp_ba_re
     const bool stop0 = force_stop && *force_stop;  // local_bundle_adjuster.cc:276-282
     if (!stop0) {
         int it1 = 0, it2 = 0;
-        PLP_TRY(run_optimize(b, b->cfg.num_first_iter, 1, true, force_stop, &it1));
+        PLP_TRY(run_optimize(b, b->cfg.num_first_iter, mode == 2 ? 0 : 1, true, force_stop, &it1));
         r->iters_first = it1;
-        if (!(force_stop && *force_stop)) {  // :289-337
+        if (mode != 0) {
+            // global_bundle_adjuster.cc:247-253: a single optimize(num_iter); edges keep level 0
+        } else if (!(force_stop && *force_stop)) {  // :289-337
             PLP_TRY(ba_launch_classify(ctx, D, 1));
             PLP_TRY(run_optimize(b, b->cfg.num_second_iter, 0, false, force_stop, &it2));
             r->iters_second = it2;
         }
-        PLP_TRY(ba_launch_classify(ctx, D, 0));
+        if (mode == 0) PLP_TRY(ba_launch_classify(ctx, D, 0));
         r->lm_tries = b->h_state->tries;
         r->final_chi2 = b->h_state->current_chi;
     } else {
@@ -416,6 +426,17 @@ plp_status plp_ba_bench_tries(plp_ba *b, int tries, int32_t *iters_done, int32_t
     if (iters_done) *iters_done = b->h_state->it;
     if (tries_done) *tries_done = b->h_state->tries;
     return PLP_OK;
+}
+
+plp_status plp_global_ba(plp_ctx *ctx, const plp_ba_problem *p, int num_iter, int use_huber_kernel,
+                         volatile const uint8_t *force_stop, plp_ba_result *r) {
+    PLP_REQUIRE(num_iter >= 0, "num_iter");
+    const plp_ba_cfg cfg{num_iter, 0, 0};
+    plp_ba *b = nullptr;
+    PLP_TRY(plp_ba_create(ctx, p, &cfg, nullptr, &b));
+    const plp_status s = ba_solve_impl(b, force_stop, r, use_huber_kernel ? 1 : 2);
+    plp_ba_destroy(b);
+    return s;
 }
 
 plp_status plp_local_ba(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg *cfg, volatile const uint8_t *force_stop,

@@ -891,6 +891,69 @@ __global__ void __launch_bounds__(kThreads, 1) triangulation_match_kernel(const 
     if (tid == 0 && J.num_matches) *J.num_matches = (uint32_t)(flags[1] - flags[2]);
 }
 
+// ---------------------------------------------------------------------------------------
+// landmark::compute_descriptor / Line::compute_descriptor (data/landmark.cc:181-247, data/landmark_line.cc:215-283):
+// the observation whose median Hamming distance to all observations is smallest (first such observation wins).
+// One warp per landmark; per row a 257-bin histogram of the distances gives the element of rank floor(0.5 (k - 1)).
+// ---------------------------------------------------------------------------------------
+constexpr int kMedWarps = 4;
+__global__ void __launch_bounds__(kMedWarps * 32) median_descriptor_kernel(const uint8_t *__restrict__ descs,
+                                                                             const int32_t *__restrict__ offsets,
+                                                                             int num_landmarks,
+                                                                             int32_t *__restrict__ best_out) {
+    __shared__ int s_hist[kMedWarps][264];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lm = blockIdx.x * kMedWarps + warp;
+    if (lm >= num_landmarks) return;
+    const int beg = offsets[lm], k = offsets[lm + 1] - beg;
+    if (k <= 0) {
+        if (lane == 0) best_out[lm] = -1;
+        return;
+    }
+    int *hist = s_hist[warp];
+    const int rank = (int)(0.5 * (double)(k - 1));
+    unsigned best_median = PLP_MAX_HAMMING_DIST;
+    int best_idx = 0;
+    for (int i = 0; i < k; ++i) {
+        for (int b = lane; b < 264; b += 32) hist[b] = 0;
+        __syncwarp();
+        uint4 a0, a1;
+        load_desc(descs + 32 * (size_t)(beg + i), a0, a1);
+        for (int j = lane; j < k; j += 32) {
+            uint4 b0, b1;
+            load_desc(descs + 32 * (size_t)(beg + j), b0, b1);
+            atomicAdd(&hist[hamming256(a0, a1, b0, b1)], 1);
+        }
+        __syncwarp();
+        // element of rank `rank` in ascending order: first bin whose inclusive prefix exceeds rank
+        int cnt[9], local = 0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const int b = lane * 9 + q;
+            cnt[q] = b < 257 ? hist[b] : 0;
+            local += cnt[q];
+        }
+        int incl = local;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += nb;
+        }
+        int run = incl - local, med = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            if (med == 0x7fffffff && run <= rank && rank < run + cnt[q]) med = lane * 9 + q;
+            run += cnt[q];
+        }
+        for (int off = 16; off >= 1; off >>= 1) med = min(med, __shfl_xor_sync(0xffffffffu, med, off));
+        if ((unsigned)med < best_median) {
+            best_median = (unsigned)med;
+            best_idx = i;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) best_out[lm] = best_idx;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -1637,6 +1700,28 @@ plp_status plp_match_for_triangulation(plp_ctx *ctx, const plp_keyframe_points *
     PLP_CUDA_TRY(cudaMemcpyAsync(&num, d + o_num, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (num_matches_out) *num_matches_out = num;
+    return PLP_OK;
+}
+
+plp_status plp_landmark_compute_descriptor_batch(plp_ctx *ctx, const uint8_t *descs, const int32_t *offsets,
+                                                 int num_landmarks, int32_t *best_idx_out) {
+    PLP_REQUIRE(ctx && offsets && best_idx_out, "null pointer");
+    PLP_REQUIRE(num_landmarks >= 0, "sizes");
+    if (num_landmarks == 0) return PLP_OK;
+    const int total = offsets[num_landmarks];
+    PLP_REQUIRE(offsets[0] == 0 && total >= 0 && (total == 0 || descs), "offsets");
+    for (int i = 0; i < num_landmarks; ++i) PLP_REQUIRE(offsets[i] <= offsets[i + 1], "offsets must ascend");
+    PLP_CUDA_TRY(cudaSetDevice(ctx->device));
+    Packer pk;
+    const size_t o_d = pk.add(descs, (size_t)total * 32), o_o = pk.add(offsets, (size_t)(num_landmarks + 1) * 4);
+    const size_t o_b = pk.reserve((size_t)num_landmarks * 4);
+    uint8_t *d;
+    PLP_TRY(pk.upload(ctx, 0, &d));
+    PLP_LAUNCH(ctx, median_descriptor_kernel, div_up(num_landmarks, kMedWarps), kMedWarps * 32, 0, Packer::at<uint8_t>(d, o_d),
+               Packer::at<int32_t>(d, o_o), num_landmarks, Packer::at<int32_t>(d, o_b));
+    PLP_CHECK_LAUNCH();
+    PLP_CUDA_TRY(cudaMemcpyAsync(best_idx_out, d + o_b, (size_t)num_landmarks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return PLP_OK;
 }
 

@@ -7,11 +7,16 @@
 //   src/PLPSLAM/match/projection.cc             (match_frame_and_landmarks, match_current_and_last_frames, *_line)
 //   src/PLPSLAM/match/robust.cc                 (brute_force_match)
 //   src/PLPSLAM/optimize/pose_optimizer*.cc     (optimize)
+//   src/PLPSLAM/feature/line_extractor.cc       (LineFeatureTracker::extract_LSD_LBD)
+//   src/PLPSLAM/data/frame.cc                   (match::stereo::compute call site)
+//   src/PLPSLAM/match/projection.cc / robust.cc (match_frame_and_keyframe, match_for_triangulation)
 // call.  Public signatures, PLPSLAM::system, the YAML configs and the map database stay unchanged.
 // See INTEGRATION.md for the patch of each call site.
 #pragma once
 #ifdef PLPSLAM_B200_WITH_REFERENCE_TYPES
 
+#include <cstring>
+#include <set>
 #include <stdexcept>
 #include <vector>
 
@@ -19,6 +24,8 @@
 
 #include "PLPSLAM/camera/perspective.h"
 #include "PLPSLAM/data/frame.h"
+#include "PLPSLAM/data/keyframe.h"
+#include "PLPSLAM/feature/line_descriptor/descriptor_custom.hpp"
 #include "PLPSLAM/data/landmark.h"
 #include "PLPSLAM/data/landmark_line.h"
 #include "plpslam_b200.h"
@@ -159,6 +166,153 @@ inline unsigned pose_optimize(PLPSLAM::data::frame &frm, bool with_lines, int nu
         for (int c = 0; c < 4; ++c) T(r, c) = T_out[r * 4 + c];
     frm.set_cam_pose(T);
     return (unsigned)n_inliers;
+}
+
+// ---- feature::LineFeatureTracker::extract_LSD_LBD (feature/line_extractor.cc:88-160) -------------------------
+struct line_backend {
+    plp_line *h = nullptr;
+    int rows = 0, cols = 0;
+    std::vector<plp_keyline> kl;
+    std::vector<double> fn;
+    void ensure(int r, int c) {
+        if (h && r == rows && c == cols) return;
+        if (h) plp_line_destroy(h);
+        check(plp_line_create(thread_ctx(), r, c, 1, &h));
+        rows = r;
+        cols = c;
+        kl.resize(plp_line_capacity(h));
+        fn.resize((size_t)plp_line_capacity(h) * 3);
+    }
+    void extract(const cv::Mat &img, std::vector<cv::line_descriptor::KeyLine> &frame_keylsd, cv::Mat &frame_lbd_descr,
+                 std::vector<PLPSLAM::Vec3_t> &keyline_functions) {
+        static_assert(sizeof(plp_keyline) == sizeof(cv::line_descriptor::KeyLine), "plp_keyline mirrors KeyLine");
+        cv::Mat lbd(plp_line_capacity(h), 32, CV_8U);
+        int n = 0;
+        check(plp_line_extract(h, img.data, img.rows, img.cols, img.step, kl.data(), lbd.data, fn.data(), &n));
+        auto *k = reinterpret_cast<cv::line_descriptor::KeyLine *>(kl.data());
+        frame_keylsd.assign(k, k + n);                                  // line_extractor.cc:143
+        frame_lbd_descr = n ? lbd.rowRange(0, n).clone() : cv::Mat();   // :144
+        for (int i = 0; i < n; ++i)                                      // :147-159 (appended, like the reference)
+            keyline_functions.emplace_back(fn[3 * i], fn[3 * i + 1], fn[3 * i + 2]);
+    }
+};
+
+// ---- match::stereo::compute (match/stereo.cc:45-150), called from data::frame (frame.cc:470-480) -------------
+// `left` / `right` are the backends of the two extractors that just produced keypts_ / keypts_right_.
+inline void stereo_compute(const orb_backend &left, const orb_backend &right, const std::vector<cv::KeyPoint> &keypts_left,
+                           const std::vector<cv::KeyPoint> &keypts_right, const cv::Mat &descs_left,
+                           const cv::Mat &descs_right, float focal_x_baseline, float true_baseline,
+                           std::vector<float> &stereo_x_right, std::vector<float> &depths) {
+    stereo_x_right.assign(keypts_left.size(), -1.0f);
+    depths.assign(keypts_left.size(), -1.0f);
+    check(plp_stereo_compute(thread_ctx(), left.h, right.h, reinterpret_cast<const plp_keypoint *>(keypts_left.data()),
+                             descs_left.data, (int)keypts_left.size(),
+                             reinterpret_cast<const plp_keypoint *>(keypts_right.data()), descs_right.data,
+                             (int)keypts_right.size(), focal_x_baseline, true_baseline, stereo_x_right.data(),
+                             depths.data(), nullptr));
+}
+
+// ---- match::projection::match_frame_and_keyframe (match/projection.cc:529-645) --------------------------------
+inline unsigned match_frame_and_keyframe(PLPSLAM::data::frame &curr_frm, PLPSLAM::data::keyframe *keyfrm,
+                                         const std::set<PLPSLAM::data::landmark *> &already_matched_lms, float margin,
+                                         unsigned hamm_dist_thr, bool check_orientation) {
+    const PLPSLAM::Mat33_t rot_cw = curr_frm.cam_pose_cw_.block<3, 3>(0, 0);
+    const PLPSLAM::Vec3_t trans_cw = curr_frm.cam_pose_cw_.block<3, 1>(0, 3);
+    const PLPSLAM::Vec3_t cam_center = -rot_cw.transpose() * trans_cw;
+    const auto landmarks = keyfrm->get_landmarks();
+    const int n = curr_frm.num_keypts_, m = (int)landmarks.size();
+    std::vector<float> x(n), y(n), ang(n), qx(m), qy(m), qang(m);
+    std::vector<int32_t> oct(n), lvl(m, 0), matched(n);
+    std::vector<uint8_t> claimed(n), valid(m, 0), qdesc((size_t)m * 32, 0);
+    for (int i = 0; i < n; ++i) {
+        x[i] = curr_frm.undist_keypts_[i].pt.x;
+        y[i] = curr_frm.undist_keypts_[i].pt.y;
+        oct[i] = curr_frm.undist_keypts_[i].octave;
+        ang[i] = curr_frm.undist_keypts_[i].angle;
+        claimed[i] = curr_frm.landmarks_[i] != nullptr;  // :604
+    }
+    for (int idx = 0; idx < m; ++idx) {  // the gates of :543-582 stay on the host (they read landmark state)
+        auto *lm = landmarks[idx];
+        if (!lm || lm->will_be_erased() || already_matched_lms.count(lm)) continue;
+        const PLPSLAM::Vec3_t pos_w = lm->get_pos_in_world();
+        PLPSLAM::Vec2_t reproj;
+        float x_right;
+        if (!curr_frm.camera_->reproject_to_image(rot_cw, trans_cw, pos_w, reproj, x_right)) continue;
+        const auto dist = (pos_w - cam_center).norm();
+        if (dist < lm->get_min_valid_distance() || lm->get_max_valid_distance() < dist) continue;
+        valid[idx] = 1;
+        qx[idx] = reproj(0);
+        qy[idx] = reproj(1);
+        lvl[idx] = lm->predict_scale_level(dist, &curr_frm);
+        qang[idx] = keyfrm->undist_keypts_[idx].angle;
+        std::memcpy(&qdesc[(size_t)idx * 32], lm->get_descriptor().data, 32);
+    }
+    const plp_frame_points fp{n, x.data(), y.data(), oct.data(), ang.data(), nullptr, curr_frm.descriptors_.data,
+                              claimed.data()};
+    const plp_landmark_queries q{m, qx.data(), qy.data(), nullptr, lvl.data(), qdesc.data(), valid.data()};
+    const plp_grid grid = grid_of(curr_frm.camera_);
+    uint32_t num = 0;
+    check(plp_match_frame_and_keyframe(thread_ctx(), &fp, &grid, curr_frm.scale_factors_.data(),
+                                       (int)curr_frm.scale_factors_.size(), &q, qang.data(), margin, hamm_dist_thr,
+                                       check_orientation, matched.data(), &num));
+    for (int i = 0; i < n; ++i)
+        if (matched[i] >= 0) curr_frm.landmarks_[i] = landmarks[matched[i]];
+    return num;
+}
+
+// ---- match::robust::match_for_triangulation (match/robust.cc:43-216) ------------------------------------------
+template <class FeatureVector>  // DBoW2::FeatureVector or fbow::BoWFeatVector: ordered map node id -> index list
+inline unsigned match_for_triangulation(PLPSLAM::data::keyframe *kf1, PLPSLAM::data::keyframe *kf2,
+                                        const FeatureVector &fv1, const FeatureVector &fv2, const PLPSLAM::Mat33_t &E_12,
+                                        bool check_orientation,
+                                        std::vector<std::pair<unsigned, unsigned>> &matched_idx_pairs) {
+    auto flatten_fv = [](const FeatureVector &fv, std::vector<uint32_t> &ids, std::vector<int32_t> &off,
+                         std::vector<uint32_t> &idx) {
+        off.push_back(0);
+        for (const auto &node : fv) {
+            ids.push_back(node.first);
+            idx.insert(idx.end(), node.second.begin(), node.second.end());
+            off.push_back((int32_t)idx.size());
+        }
+    };
+    auto flatten_kf = [](PLPSLAM::data::keyframe *kf, std::vector<float> &ang, std::vector<int32_t> &oct,
+                         std::vector<double> &bear, std::vector<uint8_t> &has) {
+        const auto lms = kf->get_landmarks();
+        for (unsigned i = 0; i < kf->num_keypts_; ++i) {
+            ang.push_back(kf->undist_keypts_[i].angle);
+            oct.push_back(kf->undist_keypts_[i].octave);
+            for (int k = 0; k < 3; ++k) bear.push_back(kf->bearings_[i](k));
+            has.push_back(lms[i] != nullptr);
+        }
+    };
+    std::vector<uint32_t> ids1, ids2, idx1, idx2;
+    std::vector<int32_t> off1, off2, oct1, oct2;
+    std::vector<float> ang1, ang2;
+    std::vector<double> b1, b2;
+    std::vector<uint8_t> has1, has2;
+    flatten_fv(fv1, ids1, off1, idx1);
+    flatten_fv(fv2, ids2, off2, idx2);
+    flatten_kf(kf1, ang1, oct1, b1, has1);
+    flatten_kf(kf2, ang2, oct2, b2, has2);
+    PLPSLAM::Vec3_t epi;
+    kf2->camera_->reproject_to_bearing(kf2->get_rotation(), kf2->get_translation(), kf1->get_cam_center(), epi);  // :54-57
+    double E[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) E[r * 3 + c] = E_12(r, c);
+    const plp_keyframe_points p1{(int32_t)kf1->num_keypts_, kf1->descriptors_.data, ang1.data(), oct1.data(), b1.data(),
+                                 has1.data(), kf1->stereo_x_right_.data()};
+    const plp_keyframe_points p2{(int32_t)kf2->num_keypts_, kf2->descriptors_.data, ang2.data(), oct2.data(), b2.data(),
+                                 has2.data(), kf2->stereo_x_right_.data()};
+    const plp_bow_feature_vector v1{(int32_t)ids1.size(), ids1.data(), off1.data(), idx1.data()};
+    const plp_bow_feature_vector v2{(int32_t)ids2.size(), ids2.data(), off2.data(), idx2.data()};
+    std::vector<int32_t> m21(kf1->num_keypts_);
+    uint32_t num = 0;
+    check(plp_match_for_triangulation(thread_ctx(), &p1, &p2, &v1, &v2, E, epi.data(), kf1->scale_factors_.data(),
+                                      (int)kf1->scale_factors_.size(), check_orientation, m21.data(), &num));
+    matched_idx_pairs.clear();
+    for (unsigned i = 0; i < m21.size(); ++i)   // :201-213
+        if (m21[i] >= 0) matched_idx_pairs.emplace_back(i, (unsigned)m21[i]);
+    return num;
 }
 
 }  // namespace plpslam_b200

@@ -117,6 +117,13 @@ def oracle_local_ba(orc, prob: BAProblem, num_first=5, num_second=10, force_stop
     return res.finish()
 
 
+def oracle_global_ba(orc, prob: BAProblem, num_iter=20, use_huber_kernel=True) -> BAResult:
+    res = BAResult(prob)
+    st = prob.struct()
+    orc.lib.orc_global_ba(C.byref(st), C.c_int(num_iter), C.c_int(1 if use_huber_kernel else 0), None, C.byref(res.st))
+    return res.finish()
+
+
 def make_ba_problem(seed, n_local=20, n_fixed=10, n_points=4000, n_lines=800, n_plane_pts=200, stereo=False,
                     outlier_frac=0.05, pose_sigma=(0.01, 0.03), point_sigma=0.05):
     """Config 4: local keyframes on a 4 m arc looking at a landmark cloud, fixed keyframes further along the arc,

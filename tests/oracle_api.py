@@ -207,6 +207,13 @@ class Oracle:
         q = dict(sp_x=q4[0], sp_y=q4[1], ep_x=q4[2], ep_y=q4[3], scale_level=ql, valid=qv, desc=kf["desc"])
         return matched, int(num), q
 
+    def landmark_compute_descriptor_batch(self, descs, offsets):
+        d, pd = _a(np.asarray(descs).reshape(-1, 32), np.uint8)
+        o, po = _a(offsets, np.int32)
+        out = np.full(max(len(o) - 1, 1), -2, np.int32)
+        self.lib.orc_landmark_compute_descriptor_batch(pd, po, C.c_int(len(o) - 1), out.ctypes.data_as(_P))
+        return out[:len(o) - 1].copy()
+
     def match_for_triangulation(self, kf1, kf2, fv1, fv2, E_12, epipole, scale_factors_1, check_orientation=True,
                                 libm=0):
         keep = []

@@ -79,3 +79,24 @@ def test_force_stop_before_start_returns_input(ctx, plp):
     ba.close()
     assert np.allclose(out["kf_pose_cw"], prob.kf_pose_cw.reshape(-1, 4, 4), atol=1e-12)
     assert np.array_equal(out["pt_pos_w"], prob.pt_pos_w) and out["iters_first"] == 0
+
+
+@pytest.mark.parametrize("n_kf,huber", [(2, True), (12, True), (12, False)])
+def test_global_ba(ctx, orc, plp, n_kf, huber):
+    # optimize::global_bundle_adjuster: only keyframe 0 is fixed, one optimize(20) with / without the Huber kernel.
+    # n_kf = 2 is the map-initialisation call (module/initializer.cc:306-307).
+    from plpslam_b200.ba import global_ba
+    prob = ba_data.make_ba_problem(60 + n_kf, n_local=n_kf, n_fixed=0, n_points=500, n_lines=80 if n_kf > 2 else 0,
+                                   n_plane_pts=0, outlier_frac=0.02)
+    prob.kf_fixed[:] = 0
+    prob.kf_fixed[0] = 1
+    o = ba_data.oracle_global_ba(orc, prob, 20, huber)
+    g = global_ba(ctx, prob.struct(), (len(prob.kf_fixed), len(prob.pt_pos_w), len(prob.line_plucker),
+                                       len(prob.pt_edge_kf), len(prob.line_edge_kf)), 20, huber)
+    rel_pose = np.linalg.norm(g["kf_pose_cw"] - o.kf_pose_cw) / np.linalg.norm(o.kf_pose_cw)
+    assert rel_pose < 1e-4, rel_pose
+    rel_pts = np.linalg.norm(g["pt_pos_w"] - o.pt_pos_w, axis=1) / np.linalg.norm(o.pt_pos_w, axis=1)
+    assert np.quantile(rel_pts, 0.999) < 1e-4
+    assert g["iters_first"] == o.iters_first and g["lm_tries"] == o.lm_tries
+    assert abs(g["final_chi2"] - o.final_chi2) <= 1e-6 * abs(o.final_chi2)
+    assert o.iters_first > 2

@@ -17,3 +17,12 @@ ncu --set full --clock-control none --import-source on \
     -s 53 -c 14 -o gpurun_out/prof_${TAG} -f \
     python bench.py --steps 2 --warmup 3 --batch ${BATCH} --no-cpu-baseline --no-ba --no-lines > gpurun_out/bench_under_ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out/
+# (3) line front end (LSD + LBD): launch list and one full capture of one step at the same batch
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
+    --log-file gpurun_out/launches_lines_${TAG}.csv \
+    python bench.py --only-lines --steps 2 --warmup 3 --line-batch ${BATCH} --no-cpu-baseline > gpurun_out/bench_lines_under_ncu_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on \
+    -k regex:"lsd_scale_kernel|lsd_sort_kernel|lsd_grow_kernel|keyline_kernel|lbd_gradient_kernel|lbd_kernel" \
+    -s 18 -c 6 -o gpurun_out/prof_lines_${TAG} -f \
+    python bench.py --only-lines --steps 2 --warmup 3 --line-batch ${BATCH} --no-cpu-baseline > gpurun_out/bench_lines_under_ncu_full_${TAG}.log 2>&1
+ls -la gpurun_out/
