@@ -330,6 +330,101 @@ def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_b
     return res
 
 
+def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
+    """BASELINE configs[4]: EuRoC-like rectified stereo 752x480, full point + line front end per stereo frame, frames
+    sharded over ranks with no collective: ORB left + ORB right (frame.cc:456-457), match::stereo::compute
+    (frame.cc:470-480), LSD + LBD left + right (frame.cc:458-463)."""
+    import torch
+    import torch.distributed as dist
+    import synth
+    from plpslam_b200.tracking import DeviceBuffer
+    lib = pkg.lib()
+    H, W = 480, 752
+    n_base = min(batch, 6)
+    pairs = [synth.make_stereo_pair(seed + 31 * i + 1000 * rank, H, W) for i in range(n_base)]
+    rng = np.random.default_rng(seed)
+    left = np.empty((batch, H, W), np.uint8)
+    right = np.empty((batch, H, W), np.uint8)
+    for b in range(batch):
+        sh = (0, 0) if b < n_base else (int(rng.integers(-40, 41)), int(rng.integers(-60, 61)))
+        left[b] = np.roll(pairs[b % n_base][0], sh, axis=(0, 1))
+        right[b] = np.roll(pairs[b % n_base][1], sh, axis=(0, 1))
+    el = pkg.OrbExtractor(ctx, H, W, max_batch=batch)
+    er = pkg.OrbExtractor(ctx, H, W, max_batch=batch)
+    ll = pkg.LineFeatureTracker(ctx, H, W, max_batch=batch)
+    lr = pkg.LineFeatureTracker(ctx, H, W, max_batch=batch)
+    cap, lcap = el.capacity, ll.capacity
+    d_l, d_r = DeviceBuffer.from_array(ctx, left), DeviceBuffer.from_array(ctx, right)
+    kp = [DeviceBuffer(ctx, batch * cap * pkg.KP_DTYPE.itemsize) for _ in range(2)]
+    ds = [DeviceBuffer(ctx, batch * cap * 32) for _ in range(2)]
+    nk = [DeviceBuffer(ctx, batch * 4) for _ in range(2)]
+    st = [DeviceBuffer(ctx, batch * 4) for _ in range(4)]
+    d_xr, d_dp = DeviceBuffer(ctx, batch * cap * 4), DeviceBuffer(ctx, batch * cap * 4)
+    kl = [DeviceBuffer(ctx, batch * lcap * pkg.KEYLINE_DTYPE.itemsize) for _ in range(2)]
+    lb = [DeviceBuffer(ctx, batch * lcap * 32) for _ in range(2)]
+    fn = [DeviceBuffer(ctx, batch * lcap * 24) for _ in range(2)]
+    nl = [DeviceBuffer(ctx, batch * 4) for _ in range(2)]
+    bf, baseline = 47.906, 0.11
+
+    def step():
+        for k, (ext, img) in enumerate(((el, d_l), (er, d_r))):
+            ctx._check(lib.plp_orb_extract_batch_dev(ext.handle, img.ptr, C.c_int(batch), C.c_size_t(W), kp[k].ptr,
+                                                     ds[k].ptr, nk[k].ptr, st[k].ptr))
+        ctx._check(lib.plp_stereo_compute_batch_dev(ctx.handle, el.handle, er.handle, C.c_int(batch), kp[0].ptr, ds[0].ptr,
+                                                    nk[0].ptr, kp[1].ptr, ds[1].ptr, nk[1].ptr, C.c_float(bf),
+                                                    C.c_float(baseline), d_xr.ptr, d_dp.ptr, None))
+        for k, (trk, img) in enumerate(((ll, d_l), (lr, d_r))):
+            ctx._check(lib.plp_line_extract_batch_dev(trk.handle, img.ptr, C.c_int(batch), C.c_size_t(W), kl[k].ptr,
+                                                      lb[k].ptr, fn[k].ptr, nl[k].ptr, st[2 + k].ptr))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=torch.cuda.current_device())
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    xr = d_xr.download(np.float32, (batch, cap))
+    n_left = nk[0].download(np.int32, (batch,))
+    n_lines = nl[0].download(np.int32, (batch,))
+    stereo_ok = float(np.mean([(xr[b, :n_left[b]] >= 0).sum() for b in range(batch)]))
+    ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 1))
+    for _ in range(min(steps, 2)):
+        step()
+    buf = C.create_string_buffer(1 << 16)
+    ctx._check(lib.plp_ctx_kernel_timing_report(ctx.handle, buf, C.c_size_t(len(buf))))
+    ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 0))
+    kt = json.loads(buf.value.decode())
+    tot = sum(v["total_ms"] for v in kt.values())
+    shares = {k: round(v["total_ms"] / tot, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["total_ms"])}
+    for o in (el, er, ll, lr):
+        o.close()
+    for d in [d_l, d_r, d_xr, d_dp] + kp + ds + nk + st + kl + lb + fn + nl:
+        d.free()
+    return {"metric": "stereo_frames_per_sec_point_line_frontend", "value": world * batch * steps / (ms * 1e-3),
+            "unit": "stereo frames/s", "ms_per_step": ms / steps, "scaling": "weak",
+            "config": {"workload": "rectified stereo 752x480: ORB L+R, match::stereo::compute, LSD+LBD L+R (BASELINE configs[4])",
+                       "stereo_frames_per_step_per_gpu": batch, "mean_left_keypoints": float(n_left.mean()),
+                       "mean_stereo_matches": stereo_ok, "mean_left_keylines": float(n_lines.mean()),
+                       "parallelism": f"stereo frames sharded over {world} GPU(s), no data-path collective"},
+            "gpu_launches": int(launches), "kernel_time_shares": shares}
+
+
 def bench_ba(pkg, ctx, stream, rank, world, steps, warmup):
     """Second BASELINE metric: local-BA LM iterations/s on config 4 (20 local + 10 fixed KF, 4000 points + 800 lines
     + 200 plane-owned points, ~29 k edges), landmark-sharded over `world` GPUs with one NCCL all-reduce of the packed
@@ -449,10 +544,14 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 307 KB > 126 MB L2)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--streams", type=int, default=2, help="sub-batches in flight per GPU (one context/stream each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true", help="skip the local-BA metric")
     ap.add_argument("--no-lines", action="store_true", help="skip the LSD+LBD line front-end metric")
     ap.add_argument("--only-lines", action="store_true", help="development: run only the line front-end leg")
+    ap.add_argument("--no-stereo", action="store_true", help="skip the stereo point+line front-end leg (configs[4])")
+    ap.add_argument("--only-stereo", action="store_true", help="development: run only the stereo leg")
+    ap.add_argument("--stereo-batch", type=int, default=128, help="stereo frames per step per GPU")
     ap.add_argument("--line-batch", type=int, default=512, help="frames per step per GPU of the line front-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -481,30 +580,59 @@ def main():
         if rank == 0:
             print(json.dumps(r))
         return
-    fe, frames, aux = setup_front_end(pkg, ctx, B, args.seed + 1000 * rank)
+    if args.only_stereo:
+        r = bench_stereo(pkg, ctx, stream, rank, world, args.steps, args.warmup, args.stereo_batch, args.seed)
+        if rank == 0:
+            print(json.dumps(r))
+        return
+    # The batch of a step is split into `--streams` sub-batches, each owned by its own context (= CUDA stream) with its
+    # own extractor / tracker handles: the H2D copy, the one-CTA-per-frame matcher / pose optimiser and the D2H copy of
+    # one sub-batch overlap the extraction kernels of the other (plain stream concurrency, no graph capture).
+    S = max(1, min(args.streams, B))
+    Bs = B // S
+    B = Bs * S
+    ctxs = [ctx] + [pkg.Context(local_rank) for _ in range(S - 1)]
+    fes, frames_l, auxs = [], [], []
+    for c in range(S):
+        fe_c, fr_c, aux_c = setup_front_end(pkg, ctxs[c], Bs, args.seed + 1000 * rank + 37 * c)
+        fes.append(fe_c)
+        frames_l.append(fr_c)
+        auxs.append(aux_c)
+    fe, frames, aux = fes[0], np.concatenate(frames_l), auxs[0]
 
     def barrier():
-        ctx.sync()
+        for cx in ctxs:
+            cx.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
+    def join_streams():  # stream 0 waits for the work enqueued on the other streams
+        for cx in ctxs[1:]:
+            ctx._check(lib.plp_ctx_wait_ctx(ctx.handle, cx.handle))
+
+    def step_all():
+        for c in range(S):
+            fes[c].step(Bs)
+
     # ---------------- value: device-resident ------------------------------------------------------------
     for _ in range(args.warmup):
-        fe.step(B)
+        step_all()
     barrier()
-    launches0 = ctx.launch_count()
+    launches0 = sum(cx.launch_count() for cx in ctxs)
     with ClockSampler(local_rank) as clk:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            fe.step(B)
+            step_all()
+        join_streams()
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - launches0
-    res = fe.download_tracking(B)
-    ok = int((res["num_valid"] >= 20).sum())
+    launches = sum(cx.launch_count() for cx in ctxs) - launches0
+    ok = 0
+    for c in range(S):
+        ok += int((fes[c].download_tracking(Bs)["num_valid"] >= 20).sum())
     t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -512,29 +640,43 @@ def main():
     value = world * B * args.steps / (ms_max * 1e-3)
 
     # ---------------- e2e: host buffers, copies inside the timed region ----------------------------------
-    pinned = C.c_void_p()
-    ctx._check(lib.plp_host_alloc_pinned(C.c_size_t(frames.nbytes), C.byref(pinned)))
-    C.memmove(pinned, frames.ctypes.data, frames.nbytes)
-    d2h_bytes = B * (128 + 4 + 4)
+    pinned_in, pinned_out = [], []
+    out_bytes = Bs * (128 + 4 + 4)
+    for c in range(S):
+        pi, po = C.c_void_p(), C.c_void_p()
+        ctx._check(lib.plp_host_alloc_pinned(C.c_size_t(frames_l[c].nbytes), C.byref(pi)))
+        ctx._check(lib.plp_host_alloc_pinned(C.c_size_t(out_bytes), C.byref(po)))
+        C.memmove(pi, frames_l[c].ctypes.data, frames_l[c].nbytes)
+        pinned_in.append(pi)
+        pinned_out.append(po)
+    d2h_bytes = S * out_bytes
 
     def e2e_step():
-        ctx._check(lib.plp_dev_upload(ctx.handle, fe.d_imgs.ptr, pinned, C.c_size_t(frames.nbytes)))
-        fe.step(B)
-        fe.d_pose.download(np.float64, (B, 4, 4))
-        fe.d_num_valid.download(np.int32, (B,))
-        fe.d_n_inl.download(np.int32, (B,))
+        for c in range(S):
+            cx, f = ctxs[c], fes[c]
+            cx._check(lib.plp_dev_upload_async(cx.handle, f.d_imgs.ptr, pinned_in[c], C.c_size_t(frames_l[c].nbytes)))
+            f.step(Bs)
+            po = pinned_out[c].value
+            cx._check(lib.plp_dev_download_async(cx.handle, C.c_void_p(po), f.d_pose.ptr, C.c_size_t(Bs * 128)))
+            cx._check(lib.plp_dev_download_async(cx.handle, C.c_void_p(po + Bs * 128), f.d_num_valid.ptr, C.c_size_t(Bs * 4)))
+            cx._check(lib.plp_dev_download_async(cx.handle, C.c_void_p(po + Bs * 132), f.d_n_inl.ptr, C.c_size_t(Bs * 4)))
 
     for _ in range(2):
         e2e_step()
     barrier()
-    t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
     for _ in range(args.steps):
         e2e_step()
+    join_streams()
     f1.record(stream)
     barrier()
     e2e_ms = f0.elapsed_time(f1)
+    # the results of the last step are in host memory now: read them (the "loss or metric" of the contract)
+    e2e_ok = 0
+    for c in range(S):
+        nv = np.frombuffer((C.c_char * (Bs * 4)).from_address(pinned_out[c].value + Bs * 128), np.int32)
+        e2e_ok += int((nv >= 20).sum())
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -543,7 +685,7 @@ def main():
     # ---------------- roofline: per-kernel event timing over the same steps ------------------------------
     ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 1))
     for _ in range(args.steps):
-        fe.step(B)
+        fe.step(Bs)
     buf = C.create_string_buffer(1 << 16)
     ctx._check(lib.plp_ctx_kernel_timing_report(ctx.handle, buf, C.c_size_t(len(buf))))
     ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 0))
@@ -557,13 +699,15 @@ def main():
     alg = ALG_BYTES.get(dom_name)
     if alg is None:
         alg = PYR_PX
-    alg_bytes_launch = alg * B
+    alg_bytes_launch = alg * Bs
     achieved = alg_bytes_launch / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": per_launch_ms,
                 "kernel_time_shares": shares,
-                "how": "CUDA events around every launch on the launching stream over a repeat of the timed steps"}
+                "frames_per_launch": Bs,
+                "how": "CUDA events around every launch on the launching stream over a repeat of the timed steps "
+                       "(one sub-batch, kernels serialised)"}
 
     ba_res = None
     if not args.no_ba:
@@ -574,6 +718,11 @@ def main():
         lines_res = bench_lines(pkg, ctx, stream, rank, world, args.steps, args.warmup, args.line_batch, args.seed,
                                 world == 1 and not args.no_cpu_baseline)
 
+    stereo_res = None
+    if not args.no_stereo:
+        stereo_res = bench_stereo(pkg, ctx, stream, rank, world, max(3, args.steps // 2), args.warmup, args.stereo_batch,
+                                  args.seed)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -582,8 +731,9 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "image": f"{COLS}x{ROWS}",
                        "orb": {"max_num_keypts": 1000, "scale_factor": 1.2, "num_levels": 8, "ini_fast_thr": 20, "min_fast_thr": 7},
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                       "streams_per_gpu": S, "frames_per_stream_per_step": Bs,
                        "l2": "inputs larger than L2 (batch x 307 KB images)",
-                       "tracked_ok_frames": ok},
+                       "tracked_ok_frames": ok, "tracked_ok_frames_e2e": e2e_ok},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes), "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches),
@@ -591,9 +741,9 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_sample = int(min(B, max(32, 2 * cores)))
-            fps_mt, dt_mt, _ = cpu_port_frames(frames, aux, list(range(n_sample)), cores)
-            fps_1, dt_1, _ = cpu_port_frames(frames, aux, list(range(min(8, n_sample))), 1)
+            n_sample = int(min(Bs, max(32, 2 * cores)))
+            fps_mt, dt_mt, _ = cpu_port_frames(frames_l[0], aux, list(range(n_sample)), cores)
+            fps_1, dt_1, _ = cpu_port_frames(frames_l[0], aux, list(range(min(8, n_sample))), 1)
             line["cpu_baseline"] = {"value": fps_mt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_sample} frames of the same workload over {cores} host threads ({dt_mt:.1f} s)",
                                     "single_thread_value": fps_1}
@@ -603,6 +753,8 @@ def main():
             line["local_ba"] = ba_res
         if lines_res is not None:
             line["line_frontend"] = lines_res
+        if stereo_res is not None:
+            line["stereo_frontend"] = stereo_res
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -59,6 +59,12 @@ PLP_API plp_status plp_dev_alloc(plp_ctx *ctx, size_t bytes, void **out);
 PLP_API plp_status plp_dev_free(plp_ctx *ctx, void *ptr);
 PLP_API plp_status plp_dev_upload(plp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 PLP_API plp_status plp_dev_download(plp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+/* asynchronous variants (no synchronisation; the host buffer should be pinned) and a cross-context dependency: the
+ * waiter's stream waits for everything enqueued so far on the other context's stream.  Two contexts on one device give
+ * two streams: the copies and the low-occupancy kernels of one sub-batch overlap the compute of the other. */
+PLP_API plp_status plp_dev_upload_async(plp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+PLP_API plp_status plp_dev_download_async(plp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+PLP_API plp_status plp_ctx_wait_ctx(plp_ctx *waiter, plp_ctx *other);
 PLP_API plp_status plp_host_alloc_pinned(size_t bytes, void **out);
 PLP_API plp_status plp_host_free_pinned(void *ptr);
 /* number of kernels this library has launched since the context was created */

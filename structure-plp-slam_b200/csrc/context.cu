@@ -189,6 +189,31 @@ plp_status plp_dev_download(plp_ctx *ctx, void *dst_host, const void *src_dev, s
     return PLP_OK;
 }
 
+plp_status plp_dev_upload_async(plp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    PLP_REQUIRE(ctx != nullptr, "ctx");
+    if (bytes == 0) return PLP_OK;
+    PLP_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return PLP_OK;
+}
+
+plp_status plp_dev_download_async(plp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    PLP_REQUIRE(ctx != nullptr, "ctx");
+    if (bytes == 0) return PLP_OK;
+    PLP_CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return PLP_OK;
+}
+
+plp_status plp_ctx_wait_ctx(plp_ctx *waiter, plp_ctx *other) {
+    PLP_REQUIRE(waiter != nullptr && other != nullptr, "ctx");
+    if (waiter == other) return PLP_OK;
+    cudaEvent_t ev;
+    PLP_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    PLP_CUDA_TRY(cudaEventRecord(ev, other->stream));
+    PLP_CUDA_TRY(cudaStreamWaitEvent(waiter->stream, ev, 0));
+    PLP_CUDA_TRY(cudaEventDestroy(ev));  // released once the recorded work has completed
+    return PLP_OK;
+}
+
 plp_status plp_host_alloc_pinned(size_t bytes, void **out) {
     PLP_REQUIRE(out != nullptr, "out");
     PLP_CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
