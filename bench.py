@@ -349,10 +349,13 @@ def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
         sh = (0, 0) if b < n_base else (int(rng.integers(-40, 41)), int(rng.integers(-60, 61)))
         left[b] = np.roll(pairs[b % n_base][0], sh, axis=(0, 1))
         right[b] = np.roll(pairs[b % n_base][1], sh, axis=(0, 1))
+    # two contexts = two streams, like the reference's left / right extraction threads (frame.cc:456-463): the right
+    # image's ORB + line extraction runs on the second stream; match::stereo::compute waits for both ORB passes
+    ctx_r = pkg.Context(ctx.device)
     el = pkg.OrbExtractor(ctx, H, W, max_batch=batch)
-    er = pkg.OrbExtractor(ctx, H, W, max_batch=batch)
+    er = pkg.OrbExtractor(ctx_r, H, W, max_batch=batch)
     ll = pkg.LineFeatureTracker(ctx, H, W, max_batch=batch)
-    lr = pkg.LineFeatureTracker(ctx, H, W, max_batch=batch)
+    lr = pkg.LineFeatureTracker(ctx_r, H, W, max_batch=batch)
     cap, lcap = el.capacity, ll.capacity
     d_l, d_r = DeviceBuffer.from_array(ctx, left), DeviceBuffer.from_array(ctx, right)
     kp = [DeviceBuffer(ctx, batch * cap * pkg.KP_DTYPE.itemsize) for _ in range(2)]
@@ -367,18 +370,24 @@ def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
     bf, baseline = 47.906, 0.11
 
     def step():
-        for k, (ext, img) in enumerate(((el, d_l), (er, d_r))):
-            ctx._check(lib.plp_orb_extract_batch_dev(ext.handle, img.ptr, C.c_int(batch), C.c_size_t(W), kp[k].ptr,
-                                                     ds[k].ptr, nk[k].ptr, st[k].ptr))
+        ctx._check(lib.plp_orb_extract_batch_dev(er.handle, d_r.ptr, C.c_int(batch), C.c_size_t(W), kp[1].ptr, ds[1].ptr,
+                                                 nk[1].ptr, st[1].ptr))
+        ctx._check(lib.plp_orb_extract_batch_dev(el.handle, d_l.ptr, C.c_int(batch), C.c_size_t(W), kp[0].ptr, ds[0].ptr,
+                                                 nk[0].ptr, st[0].ptr))
+        ctx._check(lib.plp_ctx_wait_ctx(ctx.handle, ctx_r.handle))   # the right keypoints / pyramid are ready
+        ctx._check(lib.plp_line_extract_batch_dev(lr.handle, d_r.ptr, C.c_int(batch), C.c_size_t(W), kl[1].ptr, lb[1].ptr,
+                                                  fn[1].ptr, nl[1].ptr, st[3].ptr))
         ctx._check(lib.plp_stereo_compute_batch_dev(ctx.handle, el.handle, er.handle, C.c_int(batch), kp[0].ptr, ds[0].ptr,
                                                     nk[0].ptr, kp[1].ptr, ds[1].ptr, nk[1].ptr, C.c_float(bf),
                                                     C.c_float(baseline), d_xr.ptr, d_dp.ptr, None))
-        for k, (trk, img) in enumerate(((ll, d_l), (lr, d_r))):
-            ctx._check(lib.plp_line_extract_batch_dev(trk.handle, img.ptr, C.c_int(batch), C.c_size_t(W), kl[k].ptr,
-                                                      lb[k].ptr, fn[k].ptr, nl[k].ptr, st[2 + k].ptr))
+        ctx._check(lib.plp_line_extract_batch_dev(ll.handle, d_l.ptr, C.c_int(batch), C.c_size_t(W), kl[0].ptr, lb[0].ptr,
+                                                  fn[0].ptr, nl[0].ptr, st[2].ptr))
+        # the next step's right-image ORB pass overwrites the right pyramid: it must wait for this stereo match
+        ctx._check(lib.plp_ctx_wait_ctx(ctx_r.handle, ctx.handle))
 
     def barrier():
         ctx.sync()
+        ctx_r.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -386,14 +395,15 @@ def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
     for _ in range(max(warmup, 3)):
         step()
     barrier()
-    l0 = ctx.launch_count()
+    l0 = ctx.launch_count() + ctx_r.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
         step()
+    ctx._check(lib.plp_ctx_wait_ctx(ctx.handle, ctx_r.handle))
     e1.record(stream)
     barrier()
-    launches = ctx.launch_count() - l0
+    launches = ctx.launch_count() + ctx_r.launch_count() - l0
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=torch.cuda.current_device())
     if world > 1:
@@ -414,6 +424,7 @@ def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
     shares = {k: round(v["total_ms"] / tot, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["total_ms"])}
     for o in (el, er, ll, lr):
         o.close()
+    ctx_r.close()
     for d in [d_l, d_r, d_xr, d_dp] + kp + ds + nk + st + kl + lb + fn + nl:
         d.free()
     return {"metric": "stereo_frames_per_sec_point_line_frontend", "value": world * batch * steps / (ms * 1e-3),

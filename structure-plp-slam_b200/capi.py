@@ -160,6 +160,7 @@ class Context:
 
     def __init__(self, device: int = 0):
         self._lib = lib()
+        self.device = int(device)
         h = C.c_void_p()
         self._h = None
         self._check(self._lib.plp_ctx_create(C.c_int(device), C.byref(h)))
