@@ -132,12 +132,12 @@ def build_inputs(batch: int, seed: int):
     return seqs, np.stack(frames), t_idx
 
 
-def setup_front_end(pkg, ctx, batch, seed):
+def setup_front_end(pkg, ctx, batch, seed, track_ctx=None):
     """Render frames, extract the 'last' frames once (untimed) to obtain landmark sets, upload everything."""
     import synth
     from plpslam_b200.tracking import FrontEnd
     cam = pkg.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, COLS, ROWS)
-    fe = FrontEnd(ctx, ROWS, COLS, cam, max_batch=batch)
+    fe = FrontEnd(ctx, ROWS, COLS, cam, max_batch=batch, track_ctx=track_ctx)
     seqs, frames, t_idx = build_inputs(batch, seed)
     # last-frame landmarks: extract frame t-1 of every problem on the GPU (setup, untimed)
     last_imgs = np.stack([seqs[s].frames[t - 1] for (s, t) in t_idx])
@@ -556,6 +556,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--streams", type=int, default=2, help="sub-batches in flight per GPU (one context/stream each)")
+    ap.add_argument("--track-streams", type=int, default=1,
+                    help="1: matcher / pose optimiser of every sub-batch on a high-priority stream of its own")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true", help="skip the local-BA metric")
     ap.add_argument("--no-lines", action="store_true", help="skip the LSD+LBD line front-end metric")
@@ -563,7 +565,7 @@ def main():
     ap.add_argument("--no-stereo", action="store_true", help="skip the stereo point+line front-end leg (configs[4])")
     ap.add_argument("--only-stereo", action="store_true", help="development: run only the stereo leg")
     ap.add_argument("--stereo-batch", type=int, default=128, help="stereo frames per step per GPU")
-    ap.add_argument("--line-batch", type=int, default=512, help="frames per step per GPU of the line front-end leg")
+    ap.add_argument("--line-batch", type=int, default=888, help="frames per step per GPU of the line front-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -603,23 +605,27 @@ def main():
     Bs = B // S
     B = Bs * S
     ctxs = [ctx] + [pkg.Context(local_rank) for _ in range(S - 1)]
+    # tracking (one CTA per frame: matcher, pose optimiser) on high-priority streams of its own
+    tctxs = [pkg.Context(local_rank, high_priority=True) for _ in range(S)] if args.track_streams else [None] * S
     fes, frames_l, auxs = [], [], []
     for c in range(S):
-        fe_c, fr_c, aux_c = setup_front_end(pkg, ctxs[c], Bs, args.seed + 1000 * rank + 37 * c)
+        fe_c, fr_c, aux_c = setup_front_end(pkg, ctxs[c], Bs, args.seed + 1000 * rank + 37 * c, tctxs[c])
         fes.append(fe_c)
         frames_l.append(fr_c)
         auxs.append(aux_c)
     fe, frames, aux = fes[0], np.concatenate(frames_l), auxs[0]
 
+    all_ctxs = ctxs + [t for t in tctxs if t is not None]
+
     def barrier():
-        for cx in ctxs:
+        for cx in all_ctxs:
             cx.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
     def join_streams():  # stream 0 waits for the work enqueued on the other streams
-        for cx in ctxs[1:]:
+        for cx in all_ctxs[1:]:
             ctx._check(lib.plp_ctx_wait_ctx(ctx.handle, cx.handle))
 
     def step_all():
@@ -630,7 +636,7 @@ def main():
     for _ in range(args.warmup):
         step_all()
     barrier()
-    launches0 = sum(cx.launch_count() for cx in ctxs)
+    launches0 = sum(cx.launch_count() for cx in all_ctxs)
     with ClockSampler(local_rank) as clk:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -640,7 +646,7 @@ def main():
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
-    launches = sum(cx.launch_count() for cx in ctxs) - launches0
+    launches = sum(cx.launch_count() for cx in all_ctxs) - launches0
     ok = 0
     for c in range(S):
         ok += int((fes[c].download_tracking(Bs)["num_valid"] >= 20).sum())
@@ -668,6 +674,7 @@ def main():
             cx._check(lib.plp_dev_upload_async(cx.handle, f.d_imgs.ptr, pinned_in[c], C.c_size_t(frames_l[c].nbytes)))
             f.step(Bs)
             po = pinned_out[c].value
+            cx = f.track_ctx  # the results are produced on the tracking stream
             cx._check(lib.plp_dev_download_async(cx.handle, C.c_void_p(po), f.d_pose.ptr, C.c_size_t(Bs * 128)))
             cx._check(lib.plp_dev_download_async(cx.handle, C.c_void_p(po + Bs * 128), f.d_num_valid.ptr, C.c_size_t(Bs * 4)))
             cx._check(lib.plp_dev_download_async(cx.handle, C.c_void_p(po + Bs * 132), f.d_n_inl.ptr, C.c_size_t(Bs * 4)))
@@ -694,13 +701,17 @@ def main():
     e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
 
     # ---------------- roofline: per-kernel event timing over the same steps ------------------------------
-    ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 1))
+    tim_ctxs = [fe.ctx] + ([fe.track_ctx] if fe.track_ctx is not fe.ctx else [])
+    for cx in tim_ctxs:
+        cx._check(lib.plp_ctx_kernel_timing(cx.handle, 1))
     for _ in range(args.steps):
         fe.step(Bs)
-    buf = C.create_string_buffer(1 << 16)
-    ctx._check(lib.plp_ctx_kernel_timing_report(ctx.handle, buf, C.c_size_t(len(buf))))
-    ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 0))
-    kt = json.loads(buf.value.decode())
+    kt = {}
+    for cx in tim_ctxs:
+        buf = C.create_string_buffer(1 << 16)
+        cx._check(lib.plp_ctx_kernel_timing_report(cx.handle, buf, C.c_size_t(len(buf))))
+        cx._check(lib.plp_ctx_kernel_timing(cx.handle, 0))
+        kt.update(json.loads(buf.value.decode()))
     total_ms = sum(v["total_ms"] for v in kt.values())
     shares = {k: round(v["total_ms"] / total_ms, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["total_ms"])}
     dom = max(kt.items(), key=lambda kv: kv[1]["total_ms"])
@@ -742,7 +753,9 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "image": f"{COLS}x{ROWS}",
                        "orb": {"max_num_keypts": 1000, "scale_factor": 1.2, "num_levels": 8, "ini_fast_thr": 20, "min_fast_thr": 7},
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                       "streams_per_gpu": S, "frames_per_stream_per_step": Bs,
+                       "streams_per_gpu": S * (2 if args.track_streams else 1), "frames_per_stream_per_step": Bs,
+                       "stream_layout": ("per sub-batch: extraction stream + high-priority tracking stream"
+                                         if args.track_streams else "per sub-batch: one stream"),
                        "l2": "inputs larger than L2 (batch x 307 KB images)",
                        "tracked_ok_frames": ok, "tracked_ok_frames_e2e": e2e_ok},
             "clocks": clk.summary(),

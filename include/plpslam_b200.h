@@ -50,6 +50,10 @@ PLP_API const char *plp_last_error(void);
 PLP_API int plp_version(void);
 PLP_API int plp_device_count(void);
 PLP_API plp_status plp_ctx_create(int device, plp_ctx **out);
+/* high_priority != 0: the context's stream gets the device's highest stream priority, so that its (small, latency-bound)
+ * kernels are placed on the SMs ahead of the pending CTAs of normal-priority streams -- used to run the one-CTA-per-frame
+ * matcher / pose optimiser of one sub-batch underneath the extraction kernels of the next. */
+PLP_API plp_status plp_ctx_create_ex(int device, int high_priority, plp_ctx **out);
 PLP_API void plp_ctx_destroy(plp_ctx *ctx);
 PLP_API plp_status plp_ctx_sync(plp_ctx *ctx);
 /* cudaStream_t of the context as an opaque pointer (for event timing by the harness) */
@@ -414,6 +418,10 @@ PLP_API plp_status plp_line_extract_batch_dev(plp_line *h, const uint8_t *d_imgs
 /* parity taps of the most recent extraction (host copies): the raw cv::LineSegmentDetector segments of frame b
  * (x1, y1, x2, y2 in detection order), the half-resolution image LSD works on, and the 72-float LBD vectors. */
 PLP_API plp_status plp_line_debug_segments(plp_line *h, int b, float *segs_out, int cap, int *n_out);
+/* the region-growing kernel keeps the half-resolution image in shared memory for batches that fit the resident frames
+ * (2 per SM at VGA) and reads it through L2 for larger batches (6 frames per SM); this forces the second variant so that
+ * the parity tests cover both */
+PLP_API plp_status plp_line_debug_force_global_image(plp_line *h, int on);
 PLP_API plp_status plp_line_debug_scaled(plp_line *h, int b, uint8_t *out /* (rows/2) x (cols/2) */);
 PLP_API plp_status plp_line_debug_lbd_float(plp_line *h, int b, float *out /* n x 72 */, int cap);
 

@@ -158,12 +158,12 @@ def make_camera(fx, fy, cx, cy, cols, rows, bf=-1.0, setup_type=0) -> Camera:
 class Context:
     """One plp_ctx (device + stream).  Methods are named after the reference methods they replace."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, high_priority: bool = False):
         self._lib = lib()
         self.device = int(device)
         h = C.c_void_p()
         self._h = None
-        self._check(self._lib.plp_ctx_create(C.c_int(device), C.byref(h)))
+        self._check(self._lib.plp_ctx_create_ex(C.c_int(device), C.c_int(1 if high_priority else 0), C.byref(h)))
         self._h = h
 
     def close(self):
@@ -184,6 +184,10 @@ class Context:
     @property
     def handle(self):
         return self._h
+
+    def wait(self, other: "Context"):
+        """This context's stream waits for everything enqueued so far on `other`."""
+        self._check(self._lib.plp_ctx_wait_ctx(self._h, other._h))
 
     def sync(self):
         self._check(self._lib.plp_ctx_sync(self._h))
@@ -574,6 +578,9 @@ class LineFeatureTracker:
             self._h, imgs.ctypes.data_as(_P), C.c_int(B), C.c_size_t(imgs.strides[1]), kl.ctypes.data_as(_P),
             lbd.ctypes.data_as(_P), fn.ctypes.data_as(_P), n.ctypes.data_as(_P)))
         return [(kl[b, :n[b]].copy(), lbd[b, :n[b]].copy(), fn[b, :n[b]].copy()) for b in range(B)]
+
+    def force_global_image(self, on: bool):
+        self._ctx._check(self._lib.plp_line_debug_force_global_image(self._h, C.c_int(1 if on else 0)))
 
     def debug_segments(self, b: int) -> np.ndarray:
         cap = 20000

@@ -73,7 +73,9 @@ int plp_device_count(void) {
     return n;
 }
 
-plp_status plp_ctx_create(int device, plp_ctx **out) {
+plp_status plp_ctx_create(int device, plp_ctx **out) { return plp_ctx_create_ex(device, 0, out); }
+
+plp_status plp_ctx_create_ex(int device, int high_priority, plp_ctx **out) {
     PLP_REQUIRE(out != nullptr, "out");
     *out = nullptr;
     int n = plp_device_count();
@@ -88,7 +90,9 @@ plp_status plp_ctx_create(int device, plp_ctx **out) {
     cudaDeviceProp prop;
     PLP_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    PLP_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    PLP_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // numerically lower = higher priority
+    PLP_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, high_priority ? prio_hi : prio_lo));
     *out = c;
     return PLP_OK;
 }

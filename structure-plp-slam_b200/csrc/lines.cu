@@ -588,6 +588,10 @@ __device__ bool refine(const Grow &G, int &n, float seed_deg, double reg_angle, 
 #define PROF_ADD(slot, t0)
 #endif
 
+// kImgSmem: the half-resolution image is staged in shared memory (lowest latency, 2 frames per SM at VGA) or read from
+// global memory through L1 / L2 (34 KB of shared memory per frame -> 6 frames per SM: more frames in flight for big
+// batches; the images of a batch, 77 KB each, stay L2 resident)
+template <bool kImgSmem>
 __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
     extern __shared__ uint4 s_grow[];
 #ifdef PLP_LSD_PROF
@@ -598,14 +602,16 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
     const long long t_start = clock64();
 #endif
     uint8_t *s_img = reinterpret_cast<uint8_t *>(s_grow);
-    const int img_bytes = (D.npx + 15) & ~15;
+    const int img_bytes = kImgSmem ? ((D.npx + 15) & ~15) : 0;
     uint32_t *s_used = reinterpret_cast<uint32_t *>(s_img + img_bytes);
     const int used_words = (D.npx + 31) >> 5;
     uint32_t *s_reg = s_used + ((used_words + 3) & ~3);
     const int b = blockIdx.x, lane = threadIdx.x;
-    {  // stage the frame: the allocation is padded to 16 bytes per frame? no: copy bytes with 4-byte words where aligned
+    {  // stage the frame
         const uint8_t *src = D.scaled + (size_t)b * D.npx;
-        if (((size_t)src & 15) == 0) {
+        if (!kImgSmem) {
+            // nothing to stage
+        } else if (((size_t)src & 15) == 0) {
             const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
             for (int i = lane; i < D.npx / 16; i += 32) s_grow[i] = s4[i];
             for (int i = (D.npx / 16) * 16 + lane; i < D.npx; i += 32) s_img[i] = src[i];
@@ -620,7 +626,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
     G.sh = D.sh;
     G.kthr = D.kthr;
     G.density_th = D.density_th;
-    G.img = s_img;
+    G.img = kImgSmem ? s_img : D.scaled + (size_t)b * D.npx;
     G.used = s_used;
     G.reg = s_reg;
     G.reg_ovf = D.reg_xy + (size_t)b * D.npx;
@@ -644,7 +650,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
             const uint32_t seed_xy = __shfl_sync(kFull, oxy, l);
             const int sidx = __shfl_sync(kFull, oidx, l);
             int gx, gy;
-            grad_at(s_img, sw, sidx, gx, gy);
+            grad_at(G.img, sw, sidx, gx, gy);
             const float seed_deg = fast_atan2_deg((float)gx, (float)-gy);
             double reg_angle;
             PROF_T(t0);
@@ -958,7 +964,10 @@ struct plp_line {
     uint8_t *d_lbd = nullptr;
     double *d_fn = nullptr;
     int32_t *d_n = nullptr;
-    size_t sort_smem = 0, grow_smem = 0;
+    size_t sort_smem = 0, grow_smem = 0, grow_smem_noimg = 0;
+    bool img_smem_ok = true;
+    int resident_smem_frames = 0;
+    bool force_global_image = false;
     float4 *d_cstab = nullptr;
     std::vector<void *> owned;
 };
@@ -991,7 +1000,13 @@ static plp_status line_run(plp_line *h, const uint8_t *d_imgs, int batch, size_t
         PLP_LAUNCH(ctx, lsd_scale_kernel, grid, 256, 0, D);
     }
     PLP_LAUNCH(ctx, lsd_sort_kernel, batch, kSortWarps * 32, h->sort_smem, D);
-    PLP_LAUNCH(ctx, lsd_grow_kernel, batch, 32, h->grow_smem, D);
+    // small batches (at most half of what stays resident, so that a second handle -- the right image of a stereo pair --
+    // fits beside it): image in shared memory (latency); larger batches: image through L2, 3x the frames per SM
+    if (h->img_smem_ok && 2 * batch <= h->resident_smem_frames && !h->force_global_image) {
+        PLP_LAUNCH(ctx, lsd_grow_kernel<true>, batch, 32, h->grow_smem, D);
+    } else {
+        PLP_LAUNCH(ctx, lsd_grow_kernel<false>, batch, 32, h->grow_smem_noimg, D);
+    }
     PLP_LAUNCH(ctx, keyline_kernel, batch, 32, 0, D, d_kl, d_fn, d_n);
     {
         dim3 grid(div_up(D.w, kGrTw) * div_up(D.h, kGrTh), batch);
@@ -1095,20 +1110,26 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
     lsd_cs_table_kernel<<<div_up(kGDim * kGDim, 256), 256, 0, ctx->stream>>>(h->d_cstab);
     ctx->launches++;
     h->sort_smem = ((size_t)kSortWarps * kBins + kBins) * sizeof(uint32_t);
-    h->grow_smem = (size_t)((D.npx + 15) & ~15) + (size_t)((((D.npx + 31) >> 5) + 3) & ~3) * 4 + (size_t)kRegCap * 4;
-    if (h->grow_smem > 227 * 1024) {
-        set_error("line: a %d x %d image needs %zu bytes of shared memory per frame (limit 232448)", cols, rows, h->grow_smem);
+    h->grow_smem_noimg = (size_t)((((D.npx + 31) >> 5) + 3) & ~3) * 4 + (size_t)kRegCap * 4;
+    h->grow_smem = (size_t)((D.npx + 15) & ~15) + h->grow_smem_noimg;
+    h->img_smem_ok = h->grow_smem <= 227 * 1024;
+    if (h->grow_smem_noimg > 227 * 1024) {
+        set_error("line: a %d x %d image needs %zu bytes of shared memory per frame (limit 232448)", cols, rows,
+                  h->grow_smem_noimg);
         plp_line_destroy(h);
         return PLP_ERR_CAPACITY;
     }
-    if (cudaFuncSetAttribute(lsd_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grow_smem) != cudaSuccess) {
+    h->resident_smem_frames = h->img_smem_ok ? ctx->sm_count * (int)std::max<size_t>(1, (227 * 1024) / (h->grow_smem + 1024)) : 0;
+    if ((h->img_smem_ok && cudaFuncSetAttribute(lsd_grow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)h->grow_smem) != cudaSuccess) ||
+        cudaFuncSetAttribute(lsd_grow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grow_smem_noimg) !=
+            cudaSuccess) {
         set_error("cudaFuncSetAttribute(lsd_grow_kernel) failed");
         plp_line_destroy(h);
         return PLP_ERR_CUDA;
     }
-    cudaError_t e = cudaFuncSetAttribute(lsd_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sort_smem);
-    if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(lsd_sort_kernel) failed: %s", cudaGetErrorString(e));
+    if (cudaFuncSetAttribute(lsd_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sort_smem) != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(lsd_sort_kernel) failed");
         plp_line_destroy(h);
         return PLP_ERR_CUDA;
     }
@@ -1169,6 +1190,12 @@ plp_status plp_line_extract_batch(plp_line *h, const uint8_t *imgs, int batch, s
     PLP_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch exceeds the handle's max_batch");
     PLP_REQUIRE(step >= (size_t)h->cols, "step < cols");
     return line_extract_host(h, imgs, batch, step, kl_out, lbd_out, fn_out, n_out);
+}
+
+plp_status plp_line_debug_force_global_image(plp_line *h, int on) {
+    PLP_REQUIRE(h, "null pointer");
+    h->force_global_image = on != 0;
+    return PLP_OK;
 }
 
 plp_status plp_line_debug_segments(plp_line *h, int b, float *segs_out, int cap, int *n_out) {

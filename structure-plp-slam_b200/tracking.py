@@ -57,8 +57,12 @@ class FrontEnd:
     """extract (orb_extractor::extract) -> motion_based_track for a batch of frames, all on the device."""
 
     def __init__(self, ctx: Context, rows: int, cols: int, cam, max_batch: int, max_last_points: int = 4096,
-                 max_num_keypts=1000, scale_factor=1.2, num_levels=8, ini_fast_thr=20, min_fast_thr=7):
+                 max_num_keypts=1000, scale_factor=1.2, num_levels=8, ini_fast_thr=20, min_fast_thr=7,
+                 track_ctx: Context | None = None):
+        """track_ctx: optional second context (stream) for the tracking kernels; extraction stays on `ctx`.  The two
+        streams are chained by plp_ctx_wait_ctx, so extract(k + 1) of ANOTHER FrontEnd can run under track(k)."""
         self.ctx = ctx
+        self.track_ctx = track_ctx if track_ctx is not None else ctx
         self.lib = ctx._lib
         self.rows, self.cols, self.max_batch = rows, cols, max_batch
         self.cam = cam
@@ -70,7 +74,7 @@ class FrontEnd:
         h = C.c_void_p()
         sf = np.ascontiguousarray(self.orb.scale_factors, np.float32)
         isig = np.ascontiguousarray(self.orb.inv_level_sigma_sq, np.float32)
-        ctx._check(self.lib.plp_tracker_create(ctx.handle, C.byref(cam), C.byref(self.grid), sf.ctypes.data_as(_P),
+        ctx._check(self.lib.plp_tracker_create(self.track_ctx.handle, C.byref(cam), C.byref(self.grid), sf.ctypes.data_as(_P),
                                                isig.ctypes.data_as(_P), C.c_int(num_levels), C.c_int(max_batch),
                                                C.c_int(self.cap), C.c_int(max_last_points), C.byref(h)))
         self._trk = h
@@ -116,11 +120,15 @@ class FrontEnd:
 
     # -- the hot path (no host synchronisation) ---------------------------------------------------------
     def extract(self, batch: int):
+        if self.track_ctx is not self.ctx:
+            self.ctx.wait(self.track_ctx)  # the previous track() still reads the keypoint / descriptor arrays
         self.ctx._check(self.lib.plp_orb_extract_batch_dev(self.orb.handle, self.d_imgs.ptr, C.c_int(batch),
                                                           C.c_size_t(self.cols), self.d_kp.ptr, self.d_desc.ptr,
                                                           self.d_n.ptr, self.d_status.ptr))
 
     def track(self, batch: int, margin: float = 20.0):
+        if self.track_ctx is not self.ctx:
+            self.track_ctx.wait(self.ctx)  # the extraction of this batch
         self.ctx._check(self.lib.plp_tracker_motion_track_batch_dev(
             self._trk, C.c_int(batch), self.d_kp.ptr, self.d_desc.ptr, self.d_n.ptr, C.byref(self._last),
             C.c_float(margin), self.d_matched.ptr, self.d_pose.ptr, self.d_num_valid.ptr, self.d_n_inl.ptr,

@@ -70,9 +70,12 @@ def test_edge_cases(ctx, orc, plp):
 def test_batch_equals_single(ctx, orc, plp):
     imgs = np.stack([synth.make_line_image(20 + i) for i in range(5)] + [synth.make_texture(3)])
     trk = plp.LineFeatureTracker(ctx, 480, 640, max_batch=6)
-    res = trk.extract_batch(imgs)
-    for b in range(len(imgs)):
-        _compare(trk, orc, imgs[b], b=b, got=res[b])
+    for global_image in (False, True):  # both placements of the half-resolution image in the region-growing kernel
+        trk.force_global_image(global_image)
+        res = trk.extract_batch(imgs)
+        for b in range(len(imgs)):
+            _compare(trk, orc, imgs[b], b=b, got=res[b])
+    trk.force_global_image(False)
     # strided input (step > cols) through the single-frame entry point
     wide = np.zeros((480, 700), np.uint8)
     wide[:, :640] = imgs[1]
