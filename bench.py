@@ -565,7 +565,7 @@ def main():
     ap.add_argument("--no-stereo", action="store_true", help="skip the stereo point+line front-end leg (configs[4])")
     ap.add_argument("--only-stereo", action="store_true", help="development: run only the stereo leg")
     ap.add_argument("--stereo-batch", type=int, default=128, help="stereo frames per step per GPU")
-    ap.add_argument("--line-batch", type=int, default=888, help="frames per step per GPU of the line front-end leg")
+    ap.add_argument("--line-batch", type=int, default=1776, help="frames per step per GPU of the line front-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

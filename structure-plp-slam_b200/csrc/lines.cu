@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(kSortWarps * 32) lsd_sort_kernel(LineDev D) {
 // K4: region growing + rectangle + refinement: one warp per frame; half-resolution image, `used` bitmap and the region
 //     list (= BFS queue) in shared memory.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kRegCap = 6144;  // region entries kept in shared memory; longer regions spill to global memory
+constexpr int kRegCap = 6144;       // region entries kept in shared memory; longer regions spill to global memory
+constexpr int kRegCapSmall = 2048;  // ... in the many-frames-per-SM variant
 
 struct Rect {
     double x1, y1, x2, y2, width;
@@ -291,13 +292,13 @@ struct Grow {  // per-warp state
     uint32_t *reg;         // shared: first kRegCap region entries (packed y<<16|x)
     uint32_t *reg_ovf;     // global: all entries beyond kRegCap (indexed by absolute position)
     const float4 *tab;     // global: {deg, cos, sin} by (gx, gy)
-    int lane;
+    int lane, reg_cap;
 #ifdef PLP_LSD_PROF
     long long *pc;         // [0] iterations [1] rounds [2] cycles load phase [3] cycles resolve phase [4] on-demand loads
 #endif
-    __device__ __forceinline__ uint32_t get(int e) const { return e < kRegCap ? reg[e] : reg_ovf[e]; }
+    __device__ __forceinline__ uint32_t get(int e) const { return e < reg_cap ? reg[e] : reg_ovf[e]; }
     __device__ __forceinline__ void put(int e, uint32_t v) const {
-        if (e < kRegCap) reg[e] = v;
+        if (e < reg_cap) reg[e] = v;
         else reg_ovf[e] = v;
     }
     __device__ __forceinline__ bool is_used(int idx) const { return (used[idx >> 5] >> (idx & 31)) & 1u; }
@@ -627,6 +628,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
     G.kthr = D.kthr;
     G.density_th = D.density_th;
     G.img = kImgSmem ? s_img : D.scaled + (size_t)b * D.npx;
+    G.reg_cap = kImgSmem ? kRegCap : kRegCapSmall;
     G.used = s_used;
     G.reg = s_reg;
     G.reg_ovf = D.reg_xy + (size_t)b * D.npx;
@@ -1110,8 +1112,9 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
     lsd_cs_table_kernel<<<div_up(kGDim * kGDim, 256), 256, 0, ctx->stream>>>(h->d_cstab);
     ctx->launches++;
     h->sort_smem = ((size_t)kSortWarps * kBins + kBins) * sizeof(uint32_t);
-    h->grow_smem_noimg = (size_t)((((D.npx + 31) >> 5) + 3) & ~3) * 4 + (size_t)kRegCap * 4;
-    h->grow_smem = (size_t)((D.npx + 15) & ~15) + h->grow_smem_noimg;
+    const size_t used_bytes = (size_t)((((D.npx + 31) >> 5) + 3) & ~3) * 4;
+    h->grow_smem_noimg = used_bytes + (size_t)kRegCapSmall * 4;
+    h->grow_smem = (size_t)((D.npx + 15) & ~15) + used_bytes + (size_t)kRegCap * 4;
     h->img_smem_ok = h->grow_smem <= 227 * 1024;
     if (h->grow_smem_noimg > 227 * 1024) {
         set_error("line: a %d x %d image needs %zu bytes of shared memory per frame (limit 232448)", cols, rows,
