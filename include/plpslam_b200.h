@@ -351,6 +351,77 @@ PLP_API plp_status plp_landmark_compute_descriptor_batch(plp_ctx *ctx, const uin
                                                          int num_landmarks, int32_t *best_idx_out);
 
 /* ------------------------------------------------------------------------ */
+/* fuse matchers  (match/fuse.{h,cc})                                        */
+/* ------------------------------------------------------------------------ */
+/* match::fuse::replace_duplication / detect_duplication / replace_duplication_line (match/fuse.cc:40-151, 153-300,
+ * 304-503), the step after triangulation in mapping_module::fuse_landmark_duplication[_line] (mapping_module.cc:701-812)
+ * and in the loop corrector (global_optimization_module.cc:632, detect_duplication with the corrected Sim3).
+ *
+ * In the reference every landmark's search -- reprojection into the target keyframe, visibility / distance / viewing-
+ * angle gates, predict_scale_level, the window query, the level and chi-square gates and the best Hamming distance
+ * <= HAMMING_DIST_THR_LOW (ties: first in get_keypoints_in_cell order) -- reads only the landmark and the keyframe's
+ * features, never the state written by earlier landmarks (there is no "claimed" skip in fuse.cc).  Only the EFFECT
+ * (add_observation / replace, :265-296) is sequential.  The entry points therefore return best_idx for every
+ * (target keyframe, landmark) pair of a batch -- mapping_module.cc:711-714 is `num_targets` keyframes x one landmark
+ * list, :749 is one keyframe x the united landmark list -- and the adapter applies the effects in the reference's order,
+ * re-checking will_be_erased() / is_observed_in_keyframe() at apply time and re-issuing the search for landmarks whose
+ * descriptor was recomputed by landmark::replace (data/landmark.cc:429) before the remaining targets.
+ *
+ * predict_scale_level (data/landmark.cc:341-362) = clamp(ceil(logf(max_valid_dist_ / dist) / log_scale_factor)) is
+ * evaluated on the device as a comparison of the float ratio against num_levels - 1 thresholds that the library derives
+ * on the host from the caller's libm logf (smallest float r with logf(r) / log_scale_factor > k), so the level is the
+ * host's, bit for bit, for every ratio. */
+typedef struct plp_fuse_landmarks { /* landmarks_to_check in the caller's iteration order */
+    int32_t m;
+    const double *pos_w;             /* get_pos_in_world(): m x 3 (points) or m x 6 (lines: sp, ep)             */
+    const double *obs_mean_normal;   /* get_obs_mean_normal(), m x 3 (points only; NULL for lines)               */
+    const float *min_valid_dist;     /* get_min_valid_distance() (0.7 / 0.8 x min_valid_dist_)                   */
+    const float *max_valid_dist;     /* get_max_valid_distance() (1.3 / 1.2 x max_valid_dist_)                   */
+    const float *max_valid_dist_raw; /* max_valid_dist_, the numerator of predict_scale_level                    */
+    const uint8_t *desc;             /* get_descriptor(), m x 32                                                  */
+    const uint8_t *valid;            /* lm && !lm->will_be_erased(); NULL == all                                  */
+} plp_fuse_landmarks;
+
+typedef struct plp_fuse_target_points {
+    plp_frame_points pts; /* keyfrm->undist_keypts_ (x, y, octave), stereo_x_right_, descriptors_; angle/claimed unused */
+    double rot_cw[9];     /* keyfrm->get_rotation() (or the Sim3 rotation / s, fuse.cc:46-49), row-major            */
+    double trans_cw[3];   /* keyfrm->get_translation() (or Sim3 translation / s)                                    */
+    double cam_center[3]; /* keyfrm->get_cam_center() (or -rot_cw^T trans_cw)                                        */
+    const uint8_t *skip;  /* m entries: lm->is_observed_in_keyframe(keyfrm) / valid_lms_in_keyfrm.count(lm); NULL == none */
+} plp_fuse_target_points;
+
+typedef struct plp_fuse_target_lines {
+    plp_frame_lines lines; /* keyfrm->_keylsd (sx, sy, ex, ey, octave), _lbd_descr; the other members unused */
+    double rot_cw[9], trans_cw[3], cam_center[3];
+    const uint8_t *skip;
+} plp_fuse_target_lines;
+
+#define PLP_FUSE_DETECT 0  /* detect_duplication: signed level gate [pred - 1, pred], no chi-square gate (fuse.cc:113-121) */
+#define PLP_FUSE_REPLACE 1 /* replace_duplication: unsigned level gate (pred == 0 rejects every candidate, :228-236),
+                              chi-square gate 5.99146 / 7.81473 on the reprojection error (:238-266)                 */
+
+/* best_idx_out[t * lms->m + i] = keypoint index of target t matched to landmark i, or -1 (any `continue` of the
+ * reference loop body).  best_dist_out (optional, same shape) = its Hamming distance, 0xFFFF when unmatched. */
+PLP_API plp_status plp_fuse_search_points(plp_ctx *ctx, const plp_fuse_target_points *targets, int num_targets,
+                                          const plp_grid *grid, const plp_camera *cam, const float *scale_factors,
+                                          const float *inv_level_sigma_sq, int num_levels, float log_scale_factor,
+                                          const plp_fuse_landmarks *lms, float margin, int mode, int32_t *best_idx_out,
+                                          uint16_t *best_dist_out);
+/* replace_duplication_line (fuse.cc:304-503): candidates = get_keylines_in_cell over all keylines (both end points
+ * within margin x _scale_factors_lsd[pred] of the reprojected line), chi-square gate 5.99146 on the two point-to-line
+ * errors, best LBD Hamming distance <= 50 (ties: smallest keyline index). */
+PLP_API plp_status plp_fuse_search_lines(plp_ctx *ctx, const plp_fuse_target_lines *targets, int num_targets,
+                                         const plp_camera *cam, const float *scale_factors_lsd,
+                                         const float *inv_level_sigma_sq_lsd, int num_levels_lsd,
+                                         float log_scale_factor_lsd, const plp_fuse_landmarks *lms, float margin,
+                                         int32_t *best_idx_out, uint16_t *best_dist_out);
+
+/* Parity tap (host only, no device work): thr_out[k], 1 <= k < num_levels, is the smallest float ratio whose
+ * predict_scale_level is >= k under the calling process's libm logf; thr_out[0] is unused (set to 0).  The kernels
+ * evaluate predict_scale_level as count(ratio >= thr[k]). */
+PLP_API plp_status plp_fuse_level_thresholds(float log_scale_factor, int num_levels, float *thr_out);
+
+/* ------------------------------------------------------------------------ */
 /* stereo matching  (match/stereo.{h,cc})                                    */
 /* ------------------------------------------------------------------------ */
 /* match::stereo::compute(stereo_x_right, depths) (match/stereo.cc:45-150): per left keypoint the Hamming-closest right

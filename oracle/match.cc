@@ -764,6 +764,155 @@ unsigned orc_match_current_and_last_frames_line(int n, const float *sx, const fl
     return num_matches;
 }
 
+// =========================================================================================
+// match/fuse.cc -- per-landmark search of the fuse matchers (the effects stay with the caller)
+// =========================================================================================
+unsigned orc_predict_scale_level(float max_valid_dist, float cam_to_lm_dist, float log_scale_factor, unsigned num_levels) {
+    return predict_scale_level(max_valid_dist, cam_to_lm_dist, log_scale_factor, num_levels);
+}
+
+void orc_fuse_search_points(const orc_grid *g, const orc_camera *cam, int n, const float *x, const float *y,
+                            const int32_t *octave, const float *x_right, const uint8_t *desc, const double *rot_cw,
+                            const double *trans_cw, const double *cam_center, const float *scale_factors,
+                            const float *inv_level_sigma_sq, int num_levels, float log_scale_factor, int m,
+                            const double *pos_w, const double *obs_mean_normal, const float *min_valid_dist,
+                            const float *max_valid_dist, const float *max_valid_dist_raw, const uint8_t *lm_desc,
+                            const uint8_t *lm_valid, const uint8_t *lm_skip, float margin, int mode,
+                            int32_t *best_idx_out, uint16_t *best_dist_out, int32_t *level_out) {
+    Grid grid(g, x, y, n);
+    for (int i = 0; i < m; ++i) {
+        best_idx_out[i] = -1;
+        if (best_dist_out) best_dist_out[i] = 0xFFFF;
+        if (level_out) level_out[i] = -1;
+        if (lm_valid && !lm_valid[i]) continue;  // fuse.cc:163-170 / 58-61: !lm || will_be_erased
+        if (lm_skip && lm_skip[i]) continue;     // :171-174 is_observed_in_keyframe / :63-66 valid_lms_in_keyfrm.count
+        const double *pw = pos_w + 3 * i;
+        // :180-188 / 72-80
+        double reproj[2];
+        float xr;
+        if (!orc_reproject_to_image(cam, rot_cw, trans_cw, pw, reproj, &xr)) continue;
+        // :190-199 / 82-91
+        const double v[3] = {pw[0] - cam_center[0], pw[1] - cam_center[1], pw[2] - cam_center[2]};
+        const double cam_to_lm_dist = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        const float max_d = max_valid_dist[i], min_d = min_valid_dist[i];
+        if (cam_to_lm_dist < min_d || max_d < cam_to_lm_dist) continue;
+        // :201-208 / 93-100: angle to the mean observation direction below 60 deg
+        const double *nm = obs_mean_normal + 3 * i;
+        if (v[0] * nm[0] + v[1] * nm[1] + v[2] * nm[2] < 0.5 * cam_to_lm_dist) continue;
+        // :210-218 / 102-110
+        const unsigned pred = predict_scale_level(max_valid_dist_raw[i], (float)cam_to_lm_dist, log_scale_factor, (unsigned)num_levels);
+        if (level_out) level_out[i] = (int)pred;
+        const auto indices = grid.query(x, y, octave, (float)reproj[0], (float)reproj[1], margin * scale_factors[pred], -1, -1);
+        if (indices.empty()) continue;
+        unsigned best_dist = MAX_HAMMING_DIST;
+        int best_idx = -1;
+        for (const auto idx : indices) {
+            if (mode == 0) {
+                // detect_duplication :113-121 -- int arithmetic
+                const int scale_level = octave[idx];
+                const int pred_i = (int)pred;
+                if (scale_level < pred_i - 1 || pred_i < scale_level) continue;
+            } else {
+                // replace_duplication :228-236 -- UNSIGNED arithmetic: pred == 0 makes pred - 1 wrap and rejects everything
+                const unsigned scale_level = (unsigned)octave[idx];
+                if (scale_level < pred - 1u || pred < scale_level) continue;
+                const float kxr = x_right ? x_right[idx] : -1.0f;
+                if (kxr >= 0) {
+                    // :238-251
+                    const double e_x = reproj[0] - x[idx];
+                    const double e_y = reproj[1] - y[idx];
+                    const float e_x_right = xr - kxr;
+                    const double reproj_error_sq = e_x * e_x + e_y * e_y + e_x_right * e_x_right;
+                    constexpr float chi_sq_3D = 7.81473;
+                    if (chi_sq_3D < reproj_error_sq * inv_level_sigma_sq[scale_level]) continue;
+                } else {
+                    // :252-265
+                    const double e_x = reproj[0] - x[idx];
+                    const double e_y = reproj[1] - y[idx];
+                    const double reproj_error_sq = e_x * e_x + e_y * e_y;
+                    constexpr float chi_sq_2D = 5.99146;
+                    if (chi_sq_2D < reproj_error_sq * inv_level_sigma_sq[scale_level]) continue;
+                }
+            }
+            const auto hamm_dist = orc_hamming_32(lm_desc + 32 * i, desc + 32 * idx);
+            if (hamm_dist < best_dist) {
+                best_dist = hamm_dist;
+                best_idx = idx;
+            }
+        }
+        if (HAMMING_DIST_THR_LOW < best_dist) continue;  // :279-282 / 135-138
+        best_idx_out[i] = best_idx;
+        if (best_dist_out) best_dist_out[i] = (uint16_t)best_dist;
+    }
+}
+
+void orc_fuse_search_lines(const orc_camera *cam, int n, const float *sx, const float *sy, const float *ex, const float *ey,
+                           const int32_t *octave, const uint8_t *desc, const double *rot_cw, const double *trans_cw,
+                           const double *cam_center, const float *scale_factors_lsd, const float *inv_level_sigma_sq_lsd,
+                           int num_levels_lsd, float log_scale_factor_lsd, int m, const double *pos_w,
+                           const float *min_valid_dist, const float *max_valid_dist, const float *max_valid_dist_raw,
+                           const uint8_t *lm_desc, const uint8_t *lm_valid, const uint8_t *lm_skip, float margin,
+                           int32_t *best_idx_out, uint16_t *best_dist_out, int32_t *level_out) {
+    for (int i = 0; i < m; ++i) {
+        best_idx_out[i] = -1;
+        if (best_dist_out) best_dist_out[i] = 0xFFFF;
+        if (level_out) level_out[i] = -1;
+        if (lm_valid && !lm_valid[i]) continue;  // fuse.cc:314-321
+        if (lm_skip && lm_skip[i]) continue;     // :322-325
+        const double *sp = pos_w + 6 * i, *ep = sp + 3;
+        // :332-339
+        // a point behind the camera leaves its reprojection unset in the reference (camera/perspective.cc:197-200 returns
+        // before writing); the oracle and the CUDA path define it as (0, 0)
+        double rsp[2] = {0.0, 0.0}, rep[2] = {0.0, 0.0}, rmp[2];
+        float xr;
+        const bool in_sp = orc_reproject_to_image(cam, rot_cw, trans_cw, sp, rsp, &xr) != 0;
+        const bool in_ep = orc_reproject_to_image(cam, rot_cw, trans_cw, ep, rep, &xr) != 0;
+        if (!in_sp && !in_ep) continue;
+        // :347-366 partial occlusion: the mid point must be visible
+        const double mp[3] = {0.5 * (sp[0] + ep[0]), 0.5 * (sp[1] + ep[1]), 0.5 * (sp[2] + ep[2])};
+        if (!in_sp || !in_ep) {
+            if (!orc_reproject_to_image(cam, rot_cw, trans_cw, mp, rmp, &xr)) continue;
+        }
+        // :368-383
+        const double vs[3] = {sp[0] - cam_center[0], sp[1] - cam_center[1], sp[2] - cam_center[2]};
+        const double ve[3] = {ep[0] - cam_center[0], ep[1] - cam_center[1], ep[2] - cam_center[2]};
+        const double dist_sp = std::sqrt(vs[0] * vs[0] + vs[1] * vs[1] + vs[2] * vs[2]);
+        const double dist_ep = std::sqrt(ve[0] * ve[0] + ve[1] * ve[1] + ve[2] * ve[2]);
+        const float max_d = max_valid_dist[i], min_d = min_valid_dist[i];
+        if (dist_sp < min_d || max_d < dist_sp || dist_ep < min_d || max_d < dist_ep) continue;
+        // :385-392
+        const double vm[3] = {mp[0] - cam_center[0], mp[1] - cam_center[1], mp[2] - cam_center[2]};
+        const double dist_mp = std::sqrt(vm[0] * vm[0] + vm[1] * vm[1] + vm[2] * vm[2]);
+        const unsigned pred = predict_scale_level(max_valid_dist_raw[i], (float)dist_mp, log_scale_factor_lsd, (unsigned)num_levels_lsd);
+        if (level_out) level_out[i] = (int)pred;
+        const auto indices = keylines_in_cell(n, sx, sy, ex, ey, octave, (float)rsp[0], (float)rsp[1], (float)rep[0],
+                                              (float)rep[1], margin * scale_factors_lsd[pred], -1, -1);
+        if (indices.empty()) continue;
+        // :405-445
+        const double l0 = rsp[1] * 1.0 - 1.0 * rep[1];
+        const double l1 = 1.0 * rep[0] - rsp[0] * 1.0;
+        const double l2 = rsp[0] * rep[1] - rsp[1] * rep[0];
+        unsigned best_dist = MAX_HAMMING_DIST;
+        int best_idx = -1;
+        for (const auto idx : indices) {
+            const unsigned scale_level = (unsigned)octave[idx];
+            const double den = std::sqrt(l0 * l0 + l1 * l1);
+            const double e_sp = (sx[idx] * l0 + sy[idx] * l1 + l2) / den;
+            const double e_ep = (ex[idx] * l0 + ey[idx] * l1 + l2) / den;
+            constexpr float chi_sq_2D = 5.99146;
+            if (chi_sq_2D < (e_sp * e_sp + e_ep * e_ep) * inv_level_sigma_sq_lsd[scale_level]) continue;
+            const auto hamm_dist = orc_hamming_32(lm_desc + 32 * i, desc + 32 * idx);
+            if (hamm_dist < best_dist) {
+                best_dist = hamm_dist;
+                best_idx = idx;
+            }
+        }
+        if (HAMMING_DIST_THR_LOW < best_dist) continue;  // :447-450
+        best_idx_out[i] = best_idx;
+        if (best_dist_out) best_dist_out[i] = (uint16_t)best_dist;
+    }
+}
+
 unsigned orc_brute_force_match(const uint8_t *frm_desc, const float *frm_angle, int n_frm,
                                const uint8_t *kf_desc, const float *kf_angle, const uint8_t *kf_valid, int n_kf,
                                float lowe_ratio, int check_orientation, int32_t *matched) {

@@ -145,6 +145,29 @@ unsigned orc_match_for_triangulation(int n1, const uint8_t *desc1, const float *
 void orc_landmark_compute_descriptor_batch(const uint8_t *descs, const int32_t *offsets, int num_landmarks,
                                            int32_t *best_idx_out);
 
+/* ---- match/fuse.cc:40-151 (mode 0, detect_duplication) / :153-300 (mode 1, replace_duplication): the per-landmark search
+ * of ONE target keyframe (everything up to "auto *lm_in_keyfrm = keyfrm->get_landmark(best_idx)"); best_idx_out[i] = -1
+ * wherever the reference loop body `continue`s.  The sequential effects (add_observation / replace) belong to the caller.
+ * level_out (optional): predicted scale level of the landmarks that reached predict_scale_level, else -1. */
+void orc_fuse_search_points(const orc_grid *g, const orc_camera *cam, int n, const float *x, const float *y,
+                            const int32_t *octave, const float *x_right, const uint8_t *desc, const double *rot_cw,
+                            const double *trans_cw, const double *cam_center, const float *scale_factors,
+                            const float *inv_level_sigma_sq, int num_levels, float log_scale_factor, int m,
+                            const double *pos_w, const double *obs_mean_normal, const float *min_valid_dist,
+                            const float *max_valid_dist, const float *max_valid_dist_raw, const uint8_t *lm_desc,
+                            const uint8_t *lm_valid, const uint8_t *lm_skip, float margin, int mode,
+                            int32_t *best_idx_out, uint16_t *best_dist_out, int32_t *level_out);
+/* ---- match/fuse.cc:304-503 (replace_duplication_line), same contract */
+void orc_fuse_search_lines(const orc_camera *cam, int n, const float *sx, const float *sy, const float *ex, const float *ey,
+                           const int32_t *octave, const uint8_t *desc, const double *rot_cw, const double *trans_cw,
+                           const double *cam_center, const float *scale_factors_lsd, const float *inv_level_sigma_sq_lsd,
+                           int num_levels_lsd, float log_scale_factor_lsd, int m, const double *pos_w /*m x 6*/,
+                           const float *min_valid_dist, const float *max_valid_dist, const float *max_valid_dist_raw,
+                           const uint8_t *lm_desc, const uint8_t *lm_valid, const uint8_t *lm_skip, float margin,
+                           int32_t *best_idx_out, uint16_t *best_dist_out, int32_t *level_out);
+/* data/landmark.cc:319-362 predict_scale_level (host libm logf) -- exposed for the threshold-table test */
+unsigned orc_predict_scale_level(float max_valid_dist, float cam_to_lm_dist, float log_scale_factor, unsigned num_levels);
+
 /* ---- match/robust.cc:257-385 --------------------------------------------------------- */
 unsigned orc_brute_force_match(const uint8_t *frm_desc, const float *frm_angle, int n_frm,
                                const uint8_t *kf_desc, const float *kf_angle,

@@ -31,6 +31,7 @@ FILE_FLAGS = {
     "orb.cu": NO_FMA,
     "lines.cu": NO_FMA,
     "stereo.cu": NO_FMA,
+    "fuse.cu": NO_FMA,
 }
 
 

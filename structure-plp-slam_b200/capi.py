@@ -99,6 +99,33 @@ class BowFeatureVector(C.Structure):
     _fields_ = [("num_nodes", C.c_int32), ("node_ids", _P), ("offsets", _P), ("indices", _P)]
 
 
+class FuseLandmarks(C.Structure):
+    _fields_ = [("m", C.c_int32), ("pos_w", _P), ("obs_mean_normal", _P), ("min_valid_dist", _P),
+                ("max_valid_dist", _P), ("max_valid_dist_raw", _P), ("desc", _P), ("valid", _P)]
+
+
+class FuseTargetPoints(C.Structure):
+    _fields_ = [("pts", FramePoints), ("rot_cw", C.c_double * 9), ("trans_cw", C.c_double * 3),
+                ("cam_center", C.c_double * 3), ("skip", _P)]
+
+
+class FuseTargetLines(C.Structure):
+    _fields_ = [("lines", FrameLines), ("rot_cw", C.c_double * 9), ("trans_cw", C.c_double * 3),
+                ("cam_center", C.c_double * 3), ("skip", _P)]
+
+
+FUSE_DETECT, FUSE_REPLACE = 0, 1
+
+
+def fuse_level_thresholds(log_scale_factor: float, num_levels: int) -> np.ndarray:
+    """Host-side table behind the device predict_scale_level (no GPU needed)."""
+    out = np.zeros(max(num_levels, 1), np.float32)
+    st = lib().plp_fuse_level_thresholds(C.c_float(log_scale_factor), C.c_int(num_levels), out.ctypes.data_as(_P))
+    if st != 0:
+        raise PlpError(f"plp status {st}: {lib().plp_last_error().decode()}")
+    return out
+
+
 class OrbParams(C.Structure):
     _fields_ = [("max_num_keypts", C.c_uint32), ("scale_factor", C.c_float), ("num_levels", C.c_uint32),
                 ("ini_fast_thr", C.c_uint32), ("min_fast_thr", C.c_uint32)]
@@ -292,6 +319,69 @@ class Context:
             self._h, C.byref(fl), sf.ctypes.data_as(_P), C.c_int(len(sf)), C.byref(lq), C.c_float(margin),
             C.c_uint(hamm_dist_thr), matched.ctypes.data_as(_P), C.byref(num)))
         return matched, int(num.value)
+
+    # ------------------------------------------------------------------ match::fuse
+    @staticmethod
+    def _fuse_landmarks(k, lms, width):
+        m = len(lms["min_valid_dist"])
+        pos = np.ascontiguousarray(lms["pos_w"], np.float64).reshape(m, width)
+        return FuseLandmarks(m, k.arr(pos, np.float64), k.arr(lms.get("obs_mean_normal"), np.float64),
+                             k.arr(lms["min_valid_dist"], np.float32), k.arr(lms["max_valid_dist"], np.float32),
+                             k.arr(lms["max_valid_dist_raw"], np.float32), k.arr(lms["desc"], np.uint8),
+                             k.arr(lms.get("valid"), np.uint8))
+
+    @staticmethod
+    def _fuse_pose(t, tgt):
+        R = np.ascontiguousarray(tgt["rot_cw"], np.float64).reshape(9)
+        tr = np.ascontiguousarray(tgt["trans_cw"], np.float64).reshape(3)
+        cc = np.ascontiguousarray(tgt["cam_center"], np.float64).reshape(3)
+        t.rot_cw = (C.c_double * 9)(*R)
+        t.trans_cw = (C.c_double * 3)(*tr)
+        t.cam_center = (C.c_double * 3)(*cc)
+
+    def fuse_search_points(self, grid, cam, scale_factors, inv_level_sigma_sq, log_scale_factor, targets, lms, margin,
+                           mode=FUSE_REPLACE):
+        """match::fuse::replace_duplication / detect_duplication search for a (target keyframe x landmark) batch.
+        targets: list of dict(x, y, octave, desc[, x_right], rot_cw, trans_cw, cam_center[, skip]);
+        lms: dict(pos_w, obs_mean_normal, min_valid_dist, max_valid_dist, max_valid_dist_raw, desc[, valid]).
+        Returns (best_idx[num_targets, m], best_dist[num_targets, m])."""
+        k = _Keep()
+        L = self._fuse_landmarks(k, lms, 3)
+        arr = (FuseTargetPoints * max(len(targets), 1))()
+        for i, tgt in enumerate(targets):
+            arr[i].pts = self._frame_points(k, tgt["x"], tgt["y"], tgt["octave"], tgt["desc"], None, tgt.get("x_right"))
+            self._fuse_pose(arr[i], tgt)
+            arr[i].skip = k.arr(tgt.get("skip"), np.uint8)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        isg = np.ascontiguousarray(inv_level_sigma_sq, np.float32)
+        best = np.full((len(targets), L.m), -2, np.int32)
+        dist = np.full((len(targets), L.m), 0xFFFE, np.uint16)
+        self._check(self._lib.plp_fuse_search_points(
+            self._h, arr, C.c_int(len(targets)), C.byref(grid), C.byref(cam), sf.ctypes.data_as(_P),
+            isg.ctypes.data_as(_P), C.c_int(len(sf)), C.c_float(log_scale_factor), C.byref(L), C.c_float(margin),
+            C.c_int(mode), best.ctypes.data_as(_P), dist.ctypes.data_as(_P)))
+        return best, dist
+
+    def fuse_search_lines(self, cam, scale_factors_lsd, inv_level_sigma_sq_lsd, log_scale_factor_lsd, targets, lms,
+                          margin):
+        """match::fuse::replace_duplication_line search; targets: list of dict(sx, sy, ex, ey, octave, desc, rot_cw,
+        trans_cw, cam_center[, skip]); lms: dict(pos_w (m x 6), min/max_valid_dist, max_valid_dist_raw, desc[, valid])."""
+        k = _Keep()
+        L = self._fuse_landmarks(k, lms, 6)
+        arr = (FuseTargetLines * max(len(targets), 1))()
+        for i, tgt in enumerate(targets):
+            arr[i].lines = self._frame_lines(k, tgt)
+            self._fuse_pose(arr[i], tgt)
+            arr[i].skip = k.arr(tgt.get("skip"), np.uint8)
+        sf = np.ascontiguousarray(scale_factors_lsd, np.float32)
+        isg = np.ascontiguousarray(inv_level_sigma_sq_lsd, np.float32)
+        best = np.full((len(targets), L.m), -2, np.int32)
+        dist = np.full((len(targets), L.m), 0xFFFE, np.uint16)
+        self._check(self._lib.plp_fuse_search_lines(
+            self._h, arr, C.c_int(len(targets)), C.byref(cam), sf.ctypes.data_as(_P), isg.ctypes.data_as(_P),
+            C.c_int(len(sf)), C.c_float(log_scale_factor_lsd), C.byref(L), C.c_float(margin), best.ctypes.data_as(_P),
+            dist.ctypes.data_as(_P)))
+        return best, dist
 
     def landmark_compute_descriptor_batch(self, descs, offsets):
         """landmark::compute_descriptor for a batch: index of the median-distance observation per landmark."""

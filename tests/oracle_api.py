@@ -207,6 +207,68 @@ class Oracle:
         q = dict(sp_x=q4[0], sp_y=q4[1], ep_x=q4[2], ep_y=q4[3], scale_level=ql, valid=qv, desc=kf["desc"])
         return matched, int(num), q
 
+    def fuse_search_points(self, grid, cam, scale_factors, inv_level_sigma_sq, log_scale_factor, tgt, lms, margin, mode=1):
+        """match::fuse::{detect,replace}_duplication search against ONE target keyframe -> (best_idx, best_dist, level)."""
+        keep = []
+
+        def A(v, dt):
+            arr, ptr = _a(v, dt)
+            keep.append(arr)
+            return ptr
+        g, c = as_grid(grid), as_camera(cam)
+        n, m = len(tgt["x"]), len(lms["min_valid_dist"])
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        isg = np.ascontiguousarray(inv_level_sigma_sq, np.float32)
+        best = np.full(m, -2, np.int32)
+        dist = np.full(m, 0xFFFE, np.uint16)
+        lvl = np.full(m, -2, np.int32)
+        self.lib.orc_fuse_search_points(
+            C.byref(g), C.byref(c), C.c_int(n), A(tgt["x"], np.float32), A(tgt["y"], np.float32),
+            A(tgt["octave"], np.int32), A(tgt.get("x_right"), np.float32), A(tgt["desc"], np.uint8),
+            A(np.asarray(tgt["rot_cw"], np.float64).reshape(9), np.float64),
+            A(np.asarray(tgt["trans_cw"], np.float64).reshape(3), np.float64),
+            A(np.asarray(tgt["cam_center"], np.float64).reshape(3), np.float64), sf.ctypes.data_as(C.c_void_p),
+            isg.ctypes.data_as(C.c_void_p), C.c_int(len(sf)), C.c_float(log_scale_factor), C.c_int(m),
+            A(np.asarray(lms["pos_w"], np.float64).reshape(m, 3), np.float64), A(lms["obs_mean_normal"], np.float64),
+            A(lms["min_valid_dist"], np.float32), A(lms["max_valid_dist"], np.float32),
+            A(lms["max_valid_dist_raw"], np.float32), A(lms["desc"], np.uint8), A(lms.get("valid"), np.uint8),
+            A(tgt.get("skip"), np.uint8), C.c_float(margin), C.c_int(mode), best.ctypes.data_as(C.c_void_p),
+            dist.ctypes.data_as(C.c_void_p), lvl.ctypes.data_as(C.c_void_p))
+        return best, dist, lvl
+
+    def fuse_search_lines(self, cam, scale_factors_lsd, inv_level_sigma_sq_lsd, log_scale_factor_lsd, tgt, lms, margin):
+        """match::fuse::replace_duplication_line search against ONE target keyframe -> (best_idx, best_dist, level)."""
+        keep = []
+
+        def A(v, dt):
+            arr, ptr = _a(v, dt)
+            keep.append(arr)
+            return ptr
+        c = as_camera(cam)
+        n, m = len(tgt["sx"]), len(lms["min_valid_dist"])
+        sf = np.ascontiguousarray(scale_factors_lsd, np.float32)
+        isg = np.ascontiguousarray(inv_level_sigma_sq_lsd, np.float32)
+        best = np.full(m, -2, np.int32)
+        dist = np.full(m, 0xFFFE, np.uint16)
+        lvl = np.full(m, -2, np.int32)
+        self.lib.orc_fuse_search_lines(
+            C.byref(c), C.c_int(n), A(tgt["sx"], np.float32), A(tgt["sy"], np.float32), A(tgt["ex"], np.float32),
+            A(tgt["ey"], np.float32), A(tgt["octave"], np.int32), A(tgt["desc"], np.uint8),
+            A(np.asarray(tgt["rot_cw"], np.float64).reshape(9), np.float64),
+            A(np.asarray(tgt["trans_cw"], np.float64).reshape(3), np.float64),
+            A(np.asarray(tgt["cam_center"], np.float64).reshape(3), np.float64), sf.ctypes.data_as(C.c_void_p),
+            isg.ctypes.data_as(C.c_void_p), C.c_int(len(sf)), C.c_float(log_scale_factor_lsd), C.c_int(m),
+            A(np.asarray(lms["pos_w"], np.float64).reshape(m, 6), np.float64), A(lms["min_valid_dist"], np.float32),
+            A(lms["max_valid_dist"], np.float32), A(lms["max_valid_dist_raw"], np.float32), A(lms["desc"], np.uint8),
+            A(lms.get("valid"), np.uint8), A(tgt.get("skip"), np.uint8), C.c_float(margin),
+            best.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p), lvl.ctypes.data_as(C.c_void_p))
+        return best, dist, lvl
+
+    def predict_scale_level(self, max_valid_dist, cam_to_lm_dist, log_scale_factor, num_levels):
+        self.lib.orc_predict_scale_level.restype = C.c_uint
+        return int(self.lib.orc_predict_scale_level(C.c_float(max_valid_dist), C.c_float(cam_to_lm_dist),
+                                                    C.c_float(log_scale_factor), C.c_uint(num_levels)))
+
     def landmark_compute_descriptor_batch(self, descs, offsets):
         d, pd = _a(np.asarray(descs).reshape(-1, 32), np.uint8)
         o, po = _a(offsets, np.int32)
