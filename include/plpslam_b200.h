@@ -422,6 +422,62 @@ PLP_API plp_status plp_fuse_search_lines(plp_ctx *ctx, const plp_fuse_target_lin
 PLP_API plp_status plp_fuse_level_thresholds(float log_scale_factor, int num_levels, float *thr_out);
 
 /* ------------------------------------------------------------------------ */
+/* BoW: vocabulary tree transform and match::bow_tree  (data/frame.cc:785-795, */
+/* match/bow_tree.{h,cc})                                                     */
+/* ------------------------------------------------------------------------ */
+/* The DBoW2 vocabulary (data/bow_vocabulary.h:40) on the device.  plp_bow_vocab_load reads the binary file the reference
+ * loads with bow_vocab_->loadFromBinaryFile (system.cc:82; orb_vocab/orb_vocab.dbow2: header {u32 n_nodes, u32 node_size
+ * = 41, i32 k, i32 L, i32 scoring, i32 weighting}, then n_nodes - 1 records {i32 parent, u8 descriptor[32], f32 weight,
+ * u8 is_leaf}; node 0 is the root, children are ordered by node id, words are numbered in file order).
+ * plp_bow_vocab_create takes the same records as arrays (entry i describes node i + 1). */
+typedef struct plp_bow_vocab plp_bow_vocab;
+PLP_API plp_status plp_bow_vocab_create(plp_ctx *ctx, int k, int L, int num_nodes, const int32_t *parent,
+                                        const uint8_t *desc, const float *weight, const uint8_t *is_leaf,
+                                        plp_bow_vocab **out);
+PLP_API plp_status plp_bow_vocab_load(plp_ctx *ctx, const char *path, plp_bow_vocab **out);
+PLP_API void plp_bow_vocab_destroy(plp_bow_vocab *v);
+PLP_API plp_status plp_bow_vocab_info(const plp_bow_vocab *v, int32_t *k, int32_t *L, int32_t *num_nodes,
+                                      int32_t *num_words);
+/* frame::compute_bow / keyframe::compute_bow (data/frame.cc:785-795): TemplatedVocabulary::transform(features, bow_vec,
+ * bow_feat_vec, levelsup = 4).  Per descriptor row: the word reached by descending the tree along the child with the
+ * smallest Hamming distance (first child on ties), its weight, and the id of the node passed at level L - levelsup.
+ * The adapter folds the rows into the two std::maps exactly like DBoW2: rows with weight > 0 only,
+ * bow_vec[word_id] += weight in row order then L1-normalised over ascending word ids, bow_feat_vec[node_id].push_back(row). */
+PLP_API plp_status plp_bow_transform(plp_bow_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *word_id_out,
+                                     int32_t *node_id_out, float *weight_out);
+/* Device-resident variant for the batched front end (rows = batch x plp_orb_capacity(), rows past a frame's keypoint
+ * count are computed and ignored by the caller); runs on the vocabulary context's stream, no synchronisation. */
+PLP_API plp_status plp_bow_transform_dev(plp_bow_vocab *v, const uint8_t *d_desc, int n, int levelsup,
+                                         int32_t *d_word_id_out, int32_t *d_node_id_out, float *d_weight_out);
+
+/* match::bow_tree::match_frame_and_keyframe (match/bow_tree.cc:41-165): side 1 = the keyframe (valid = lm &&
+ * !lm->will_be_erased()), side 2 = the frame (valid = NULL); match::bow_tree::match_keyframes (:167-305): side 1 =
+ * keyfrm_1, side 2 = keyfrm_2, both with valid flags.  For every node id present in both feature vectors, every valid
+ * side-1 keypoint of the node (in list order) takes the not-yet-taken valid side-2 keypoint OF THE SAME NODE with the
+ * smallest Hamming distance (first on ties) if it is <= 50 and passes lowe_ratio against the second smallest; then the
+ * orientation histogram.  A keypoint index may appear in at most one node of a feature vector (true for DBoW2's
+ * transform), which makes the nodes independent: one warp per node, sequential inside the node.  A call takes a batch
+ * of pairs (module/relocalizer.cc:79: one frame x every relocalisation candidate; module/loop_detector.cc:356: the current
+ * keyframe x every loop candidate; module/frame_tracker.cc:130-139: one pair). */
+typedef struct plp_bow_side {
+    int32_t n;            /* num_keypts_                                       */
+    const uint8_t *desc;  /* descriptors_, n x 32                              */
+    const float *angle;   /* keypts_[i].angle; NULL without orientation check  */
+    const uint8_t *valid; /* see above; NULL == all                            */
+    plp_bow_feature_vector fv; /* bow_feat_vec_ flattened in iteration order   */
+} plp_bow_side;
+
+typedef struct plp_bow_pair {
+    const plp_bow_side *side1, *side2;
+    int32_t *matched_2_of_1_out; /* side1->n entries or NULL: index on side 2 matched to each side-1 keypoint, -1 none */
+    int32_t *matched_1_of_2_out; /* side2->n entries or NULL (matched_lms_in_frm[i] = keyfrm_lms[matched_1_of_2[i]])   */
+    uint32_t num_matches;        /* out */
+} plp_bow_pair;
+
+PLP_API plp_status plp_match_bow_tree(plp_ctx *ctx, plp_bow_pair *pairs, int num_pairs, float lowe_ratio,
+                                      int check_orientation);
+
+/* ------------------------------------------------------------------------ */
 /* stereo matching  (match/stereo.{h,cc})                                    */
 /* ------------------------------------------------------------------------ */
 /* match::stereo::compute(stereo_x_right, depths) (match/stereo.cc:45-150): per left keypoint the Hamming-closest right

@@ -913,6 +913,66 @@ void orc_fuse_search_lines(const orc_camera *cam, int n, const float *sx, const 
     }
 }
 
+// =========================================================================================
+// match/bow_tree.cc:41-165 / :167-305
+// =========================================================================================
+unsigned orc_bow_tree_match(int n1, const uint8_t *desc1, const float *angle1, const uint8_t *valid1, int n2,
+                            const uint8_t *desc2, const float *angle2, const uint8_t *valid2, int nodes1,
+                            const uint32_t *ids1, const int32_t *off1, const uint32_t *idx1, int nodes2,
+                            const uint32_t *ids2, const int32_t *off2, const uint32_t *idx2, float lowe_ratio,
+                            int check_orientation, int32_t *matched_2_of_1, int32_t *matched_1_of_2) {
+    unsigned num_matches = 0;
+    AngleChecker angle_checker;
+    for (int i = 0; i < n1; ++i) matched_2_of_1[i] = -1;
+    std::vector<int32_t> m1of2(n2, -1);  // matched_lms_in_frm / is_already_matched_in_keyfrm_2
+    int a = 0, b = 0;
+    while (a < nodes1 && b < nodes2) {
+        if (ids1[a] == ids2[b]) {
+            for (int ka = off1[a]; ka < off1[a + 1]; ++ka) {
+                const int i1 = (int)idx1[ka];
+                if (valid1 && !valid1[i1]) continue;  // :70-78 / :219-227
+                unsigned best_hamm_dist = MAX_HAMMING_DIST, second_best_hamm_dist = MAX_HAMMING_DIST;
+                int best_idx_2 = -1;
+                for (int kb = off2[b]; kb < off2[b + 1]; ++kb) {
+                    const int i2 = (int)idx2[kb];
+                    if (valid2 && !valid2[i2]) continue;  // :238-247 (match_keyframes only)
+                    if (m1of2[i2] >= 0) continue;         // :89-92 / :249-252
+                    const auto hamm_dist = orc_hamming_32(desc1 + 32 * (size_t)i1, desc2 + 32 * (size_t)i2);
+                    if (hamm_dist < best_hamm_dist) {
+                        second_best_hamm_dist = best_hamm_dist;
+                        best_hamm_dist = hamm_dist;
+                        best_idx_2 = i2;
+                    } else if (hamm_dist < second_best_hamm_dist) {
+                        second_best_hamm_dist = hamm_dist;
+                    }
+                }
+                if (HAMMING_DIST_THR_LOW < best_hamm_dist) continue;                                  // :110-113
+                if (lowe_ratio * second_best_hamm_dist < static_cast<float>(best_hamm_dist)) continue;  // :115-119
+                matched_2_of_1[i1] = best_idx_2;
+                m1of2[best_idx_2] = i1;
+                if (check_orientation) angle_checker.append(angle1[i1] - angle2[best_idx_2], i1);  // :123-127
+                ++num_matches;
+            }
+            ++a;
+            ++b;
+        } else if (ids1[a] < ids2[b]) {
+            ++a;  // lower_bound on an ascending map
+        } else {
+            ++b;
+        }
+    }
+    if (check_orientation) {
+        for (const auto invalid_i1 : angle_checker.collect(false)) {  // :152-160
+            m1of2[matched_2_of_1[invalid_i1]] = -1;
+            matched_2_of_1[invalid_i1] = -1;
+            --num_matches;
+        }
+    }
+    if (matched_1_of_2)
+        for (int j = 0; j < n2; ++j) matched_1_of_2[j] = m1of2[j];
+    return num_matches;
+}
+
 unsigned orc_brute_force_match(const uint8_t *frm_desc, const float *frm_angle, int n_frm,
                                const uint8_t *kf_desc, const float *kf_angle, const uint8_t *kf_valid, int n_kf,
                                float lowe_ratio, int check_orientation, int32_t *matched) {

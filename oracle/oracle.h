@@ -29,6 +29,7 @@
 #include "local_ba.h"
 #include "lines.h"
 #include "stereo.h"
+#include "bow.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -167,6 +168,16 @@ void orc_fuse_search_lines(const orc_camera *cam, int n, const float *sx, const 
                            int32_t *best_idx_out, uint16_t *best_dist_out, int32_t *level_out);
 /* data/landmark.cc:319-362 predict_scale_level (host libm logf) -- exposed for the threshold-table test */
 unsigned orc_predict_scale_level(float max_valid_dist, float cam_to_lm_dist, float log_scale_factor, unsigned num_levels);
+
+/* ---- match/bow_tree.cc:41-165 (match_frame_and_keyframe: side 1 = keyframe, side 2 = frame, valid2 = NULL) and
+ * :167-305 (match_keyframes: side 1 = keyfrm_1, side 2 = keyfrm_2, valid2 = lm_2 && !will_be_erased).  valid1[i] =
+ * lm_1 && !will_be_erased.  Feature vectors flattened in iteration order (ascending node id).  Outputs after the
+ * orientation check: matched_2_of_1[n1] (index on side 2 matched to each side-1 keypoint) and matched_1_of_2[n2]. */
+unsigned orc_bow_tree_match(int n1, const uint8_t *desc1, const float *angle1, const uint8_t *valid1, int n2,
+                            const uint8_t *desc2, const float *angle2, const uint8_t *valid2, int nodes1,
+                            const uint32_t *ids1, const int32_t *off1, const uint32_t *idx1, int nodes2,
+                            const uint32_t *ids2, const int32_t *off2, const uint32_t *idx2, float lowe_ratio,
+                            int check_orientation, int32_t *matched_2_of_1, int32_t *matched_1_of_2);
 
 /* ---- match/robust.cc:257-385 --------------------------------------------------------- */
 unsigned orc_brute_force_match(const uint8_t *frm_desc, const float *frm_angle, int n_frm,

@@ -11,6 +11,7 @@ from .capi import (  # noqa: F401
     Context,
     OrbExtractor,
     LineFeatureTracker,
+    BowVocabulary,
     KP_DTYPE,
     KEYLINE_DTYPE,
     PT_OBS_DTYPE,

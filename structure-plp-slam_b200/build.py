@@ -32,6 +32,7 @@ FILE_FLAGS = {
     "lines.cu": NO_FMA,
     "stereo.cu": NO_FMA,
     "fuse.cu": NO_FMA,
+    "bow.cu": NO_FMA,
 }
 
 

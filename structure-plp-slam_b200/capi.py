@@ -126,6 +126,15 @@ def fuse_level_thresholds(log_scale_factor: float, num_levels: int) -> np.ndarra
     return out
 
 
+class BowSide(C.Structure):
+    _fields_ = [("n", C.c_int32), ("desc", _P), ("angle", _P), ("valid", _P), ("fv", BowFeatureVector)]
+
+
+class BowPair(C.Structure):
+    _fields_ = [("side1", C.POINTER(BowSide)), ("side2", C.POINTER(BowSide)), ("matched_2_of_1_out", _P),
+                ("matched_1_of_2_out", _P), ("num_matches", C.c_uint32)]
+
+
 class OrbParams(C.Structure):
     _fields_ = [("max_num_keypts", C.c_uint32), ("scale_factor", C.c_float), ("num_levels", C.c_uint32),
                 ("ini_fast_thr", C.c_uint32), ("min_fast_thr", C.c_uint32)]
@@ -383,6 +392,38 @@ class Context:
             dist.ctypes.data_as(_P)))
         return best, dist
 
+    # ------------------------------------------------------------------ match::bow_tree
+    def match_bow_tree(self, pairs, lowe_ratio, check_orientation=True):
+        """match::bow_tree::match_frame_and_keyframe / match_keyframes for a batch of (side1, side2) pairs.
+        A side is a dict(desc, angle[, valid], fv=(node_ids, offsets, indices)); dict objects may be shared between pairs.
+        Returns a list of (matched_2_of_1, matched_1_of_2, num_matches)."""
+        k = _Keep()
+        sides = {}
+
+        def side(f):
+            if id(f) not in sides:
+                fv = f["fv"]
+                s = BowSide(len(f["desc"]), k.arr(f["desc"], np.uint8), k.arr(f.get("angle"), np.float32),
+                            k.arr(f.get("valid"), np.uint8),
+                            BowFeatureVector(len(fv[0]), k.arr(fv[0], np.uint32), k.arr(fv[1], np.int32),
+                                             k.arr(fv[2], np.uint32)))
+                sides[id(f)] = s
+            return sides[id(f)]
+        arr = (BowPair * max(len(pairs), 1))()
+        outs = []
+        for i, (a, b) in enumerate(pairs):
+            sa, sb = side(a), side(b)
+            m21 = np.full(max(sa.n, 1), -2, np.int32)
+            m12 = np.full(max(sb.n, 1), -2, np.int32)
+            arr[i].side1 = C.pointer(sa)
+            arr[i].side2 = C.pointer(sb)
+            arr[i].matched_2_of_1_out = m21.ctypes.data_as(_P)
+            arr[i].matched_1_of_2_out = m12.ctypes.data_as(_P)
+            outs.append((m21, m12, sa.n, sb.n))
+        self._check(self._lib.plp_match_bow_tree(self._h, arr, C.c_int(len(pairs)), C.c_float(lowe_ratio),
+                                                 C.c_int(1 if check_orientation else 0)))
+        return [(m21[:n1].copy(), m12[:n2].copy(), int(arr[i].num_matches)) for i, (m21, m12, n1, n2) in enumerate(outs)]
+
     def landmark_compute_descriptor_batch(self, descs, offsets):
         """landmark::compute_descriptor for a batch: index of the median-distance observation per landmark."""
         d = np.ascontiguousarray(descs, np.uint8).reshape(-1, 32)
@@ -503,6 +544,81 @@ class Context:
             k.arr(kf_angle, np.float32), k.arr(kf_valid, np.uint8), C.c_int(kd.shape[0]), C.c_float(lowe_ratio),
             C.c_int(1 if check_orientation else 0), matched.ctypes.data_as(_P), C.byref(num)))
         return matched, int(num.value)
+
+
+class BowVocabulary:
+    """data::bow_vocabulary (DBoW2 tree) resident on the device; transform() = the per-row part of frame::compute_bow."""
+
+    def __init__(self, ctx: Context, path=None, k=None, L=None, parent=None, desc=None, weight=None, is_leaf=None):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        self._h = None
+        h = C.c_void_p()
+        if path is not None:
+            ctx._check(self._lib.plp_bow_vocab_load(ctx.handle, str(path).encode(), C.byref(h)))
+        else:
+            kk = _Keep()
+            parent = np.ascontiguousarray(parent, np.int32)
+            ctx._check(self._lib.plp_bow_vocab_create(
+                ctx.handle, C.c_int(k), C.c_int(L), C.c_int(len(parent) + 1), kk.arr(parent, np.int32),
+                kk.arr(np.ascontiguousarray(desc, np.uint8).reshape(-1, 32), np.uint8), kk.arr(weight, np.float32),
+                kk.arr(is_leaf, np.uint8), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h is not None:
+            self._lib.plp_bow_vocab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        v = [C.c_int32() for _ in range(4)]
+        self._ctx._check(self._lib.plp_bow_vocab_info(self._h, *[C.byref(x) for x in v]))
+        return dict(k=v[0].value, L=v[1].value, num_nodes=v[2].value, num_words=v[3].value)
+
+    def transform(self, desc, levelsup=4):
+        """-> (word_id, node_id, weight) per descriptor row."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = d.shape[0]
+        word = np.full(max(n, 1), -2, np.int32)
+        node = np.full(max(n, 1), -2, np.int32)
+        w = np.full(max(n, 1), -1, np.float32)
+        self._ctx._check(self._lib.plp_bow_transform(self._h, d.ctypes.data_as(_P), C.c_int(n), C.c_int(levelsup),
+                                                     word.ctypes.data_as(_P), node.ctypes.data_as(_P),
+                                                     w.ctypes.data_as(_P)))
+        return word[:n].copy(), node[:n].copy(), w[:n].copy()
+
+
+def fold_bow(word_id, node_id, weight):
+    """The adapter's fold of transform() rows into DBoW2's two maps (TemplatedVocabulary::transform(features, v, fv,
+    levelsup) with TF_IDF weighting and L1 scoring): rows with weight > 0 only; bow_vec[word] += weight in row order,
+    then L1-normalised over ascending word ids; bow_feat_vec[node].push_back(row).  Returns (words, values, fv) with
+    fv = (node_ids, offsets, indices) flattened in map order."""
+    word_id, node_id = np.asarray(word_id), np.asarray(node_id)
+    weight = np.asarray(weight, np.float32)
+    keep = np.nonzero(weight > 0)[0]
+    vec, feat = {}, {}
+    for i in keep:
+        vec[int(word_id[i])] = vec.get(int(word_id[i]), 0.0) + float(weight[i])
+        feat.setdefault(int(node_id[i]), []).append(int(i))
+    words = np.array(sorted(vec), np.int64)
+    vals = np.array([vec[int(w)] for w in words], np.float64)
+    norm = 0.0
+    for v in vals:
+        norm += abs(v)
+    if norm > 0.0:
+        vals = vals / norm
+    nodes = sorted(feat)
+    offsets = np.zeros(len(nodes) + 1, np.int32)
+    for i, nd in enumerate(nodes):
+        offsets[i + 1] = offsets[i] + len(feat[nd])
+    indices = np.array([i for nd in nodes for i in feat[nd]], np.uint32)
+    return words, vals, (np.array(nodes, np.uint32), offsets, indices)
 
 
 class OrbExtractor:

@@ -269,6 +269,60 @@ class Oracle:
         return int(self.lib.orc_predict_scale_level(C.c_float(max_valid_dist), C.c_float(cam_to_lm_dist),
                                                     C.c_float(log_scale_factor), C.c_uint(num_levels)))
 
+    # ---- DBoW2 vocabulary + match::bow_tree
+    def bow_vocab_create(self, k, L, parent, desc, weight, is_leaf):
+        self.lib.orc_bow_vocab_create.restype = C.c_void_p
+        parent = np.ascontiguousarray(parent, np.int32)
+        h = self.lib.orc_bow_vocab_create(C.c_int(k), C.c_int(L), C.c_int(len(parent) + 1), _a(parent, np.int32)[1],
+                                          _a(np.ascontiguousarray(desc, np.uint8).reshape(-1, 32), np.uint8)[1],
+                                          _a(np.ascontiguousarray(weight, np.float32), np.float32)[1],
+                                          _a(np.ascontiguousarray(is_leaf, np.uint8), np.uint8)[1])
+        if not h:
+            raise RuntimeError("orc_bow_vocab_create failed")
+        return C.c_void_p(h)
+
+    def bow_vocab_load(self, path):
+        self.lib.orc_bow_vocab_load.restype = C.c_void_p
+        h = self.lib.orc_bow_vocab_load(str(path).encode())
+        if not h:
+            raise RuntimeError(f"orc_bow_vocab_load({path}) failed")
+        return C.c_void_p(h)
+
+    def bow_vocab_destroy(self, v):
+        self.lib.orc_bow_vocab_destroy(v)
+
+    def bow_vocab_info(self, v):
+        o = [C.c_int32() for _ in range(4)]
+        self.lib.orc_bow_vocab_info(v, *[C.byref(x) for x in o])
+        return dict(k=o[0].value, L=o[1].value, num_nodes=o[2].value, num_words=o[3].value)
+
+    def bow_transform(self, v, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = d.shape[0]
+        word, node, w = np.full(n, -2, np.int32), np.full(n, -2, np.int32), np.full(n, -1, np.float32)
+        self.lib.orc_bow_transform(v, d.ctypes.data_as(_P), C.c_int(n), C.c_int(levelsup), word.ctypes.data_as(_P),
+                                   node.ctypes.data_as(_P), w.ctypes.data_as(_P))
+        return word, node, w
+
+    def bow_tree_match(self, side1, side2, lowe_ratio, check_orientation=True):
+        keep = []
+
+        def A(v, dt):
+            arr, ptr = _a(v, dt)
+            keep.append(arr)
+            return ptr
+        n1, n2 = len(side1["desc"]), len(side2["desc"])
+        m21, m12 = np.full(max(n1, 1), -2, np.int32), np.full(max(n2, 1), -2, np.int32)
+        f1, f2 = side1["fv"], side2["fv"]
+        self.lib.orc_bow_tree_match.restype = C.c_uint
+        num = self.lib.orc_bow_tree_match(
+            C.c_int(n1), A(side1["desc"], np.uint8), A(side1.get("angle"), np.float32), A(side1.get("valid"), np.uint8),
+            C.c_int(n2), A(side2["desc"], np.uint8), A(side2.get("angle"), np.float32), A(side2.get("valid"), np.uint8),
+            C.c_int(len(f1[0])), A(f1[0], np.uint32), A(f1[1], np.int32), A(f1[2], np.uint32),
+            C.c_int(len(f2[0])), A(f2[0], np.uint32), A(f2[1], np.int32), A(f2[2], np.uint32),
+            C.c_float(lowe_ratio), C.c_int(1 if check_orientation else 0), m21.ctypes.data_as(_P), m12.ctypes.data_as(_P))
+        return m21[:n1].copy(), m12[:n2].copy(), int(num)
+
     def landmark_compute_descriptor_batch(self, descs, offsets):
         d, pd = _a(np.asarray(descs).reshape(-1, 32), np.uint8)
         o, po = _a(offsets, np.int32)
