@@ -493,6 +493,88 @@ def bench_ba(pkg, ctx, stream, rank, world, steps, warmup):
             "hbm_roofline_frac": (alg_bytes / (ms * 1e-3 / max(done, 1))) / 1e9 / _peaks()[0]}
 
 
+def bench_mapping(pkg, ctx, cpu_baseline, reps=10):
+    """SURVEY 8(f) rows measured through the C ABI with HOST buffers (the calls the mapping / relocalisation threads make;
+    every call includes its H2D/D2H copies): match::fuse search (20 target keyframes x 1000 landmarks,
+    mapping_module.cc:711-714), DBoW2 transform on a full-size synthetic vocabulary (k = 10, L = 6, 1 111 110 nodes like the
+    shipped orb_vocab.dbow2) and match::bow_tree (one frame x 20 candidate keyframes, relocalizer.cc:79).  Wall clock
+    around synchronous calls, median of `reps`; the CPU oracle port (one thread) of the same call beside it."""
+    import bow_data
+    import fuse_data
+    import oracle_api
+    import synth
+    out = {}
+
+    def med(fn):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return 1e3 * float(np.median(ts))
+
+    orc = oracle_api.Oracle() if cpu_baseline else None
+    # ---- fuse
+    grid = pkg.capi.make_grid(COLS, ROWS)
+    cam = pkg.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, COLS, ROWS)
+    sf, isg = synth.scale_factors(), fuse_data.inv_level_sigma_sq()
+    lms, targets = fuse_data.make_point_fuse_scene(77, m=1000, num_targets=20)
+    l0 = ctx.launch_count()
+    ms = med(lambda: ctx.fuse_search_points(grid, cam, sf, isg, fuse_data.LOG_SF, targets, lms, 3.0, 1))
+    pairs = 20 * 1000
+    out["fuse_replace_duplication"] = {"ms_per_call": ms, "pairs_per_s": pairs / (ms * 1e-3), "config": "20 target keyframes x 1000 landmarks, ~1200 keypoints each",
+                                       "gpu_launches": int(ctx.launch_count() - l0)}
+    if orc:
+        t0 = time.perf_counter()
+        for t in targets:
+            orc.fuse_search_points(grid, cam, sf, isg, fuse_data.LOG_SF, t, lms, 3.0, 1)
+        out["fuse_replace_duplication"]["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+    # ---- DBoW2 transform: full-size complete tree (breadth-first ids: parent(i) = (i - 1) // k)
+    k, L = 10, 6
+    n_nodes = (k ** (L + 1) - 1) // (k - 1)
+    rng = np.random.default_rng(5)
+    parent = ((np.arange(1, n_nodes, dtype=np.int64) - 1) // k).astype(np.int32)
+    vdesc = rng.integers(0, 256, size=(n_nodes - 1, 32), dtype=np.uint8)
+    leaf = (np.arange(1, n_nodes) >= (k ** L - 1) // (k - 1)).astype(np.uint8)
+    weight = (rng.uniform(0.1, 9.7, n_nodes - 1) * leaf).astype(np.float32)
+    vocab = pkg.BowVocabulary(ctx, k=k, L=L, parent=parent, desc=vdesc, weight=weight, is_leaf=leaf)
+    rows = 64 * 1000
+    desc = rng.integers(0, 256, size=(rows, 32), dtype=np.uint8)
+    l0 = ctx.launch_count()
+    ms = med(lambda: vocab.transform(desc, 4))
+    alg = rows * (32 + 12 + L * k * 32)   # descriptor in, 3 outputs, k child descriptors per level (L2-resident tree)
+    out["bow_transform"] = {"ms_per_call": ms, "descriptors_per_s": rows / (ms * 1e-3), "rows": rows,
+                            "config": f"k={k} L={L} {n_nodes} nodes ({(n_nodes * 32) >> 20} MB of descriptors), levelsup 4",
+                            "algorithmic_bytes": alg, "gathered_GBps": alg / (ms * 1e-3) / 1e9,
+                            "gpu_launches": int(ctx.launch_count() - l0)}
+    if orc:
+        ov = orc.bow_vocab_create(k, L, parent, vdesc, weight, leaf)
+        t0 = time.perf_counter()
+        orc.bow_transform(ov, desc[:8000], 4)
+        out["bow_transform"]["cpu_port_descriptors_per_s"] = 8000 / (time.perf_counter() - t0)
+        orc.bow_vocab_destroy(ov)
+    vocab.close()
+    # ---- match::bow_tree: one frame x 20 candidate keyframes
+    frame, bp = None, []
+    for sd in range(20):
+        s1, s2, _ = bow_data.make_bow_sides(100 + sd, n1=1000, n2=1000, num_nodes=90)
+        if frame is None:
+            frame = dict(s2)
+            frame.pop("valid")
+        bp.append((s1, frame))
+    l0 = ctx.launch_count()
+    ms = med(lambda: ctx.match_bow_tree(bp, 0.75, True))
+    out["bow_tree_match"] = {"ms_per_call": ms, "pairs_per_s": 20 / (ms * 1e-3), "config": "1 frame x 20 keyframes, 1000 keypoints, ~110 nodes",
+                             "gpu_launches": int(ctx.launch_count() - l0)}
+    if orc:
+        t0 = time.perf_counter()
+        for a, b in bp:
+            orc.bow_tree_match(a, b, 0.75, True)
+        out["bow_tree_match"]["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+    return out
+
+
 def bench_ba_cpu(n_solves=3):
     """CPU oracle port of the same local BA (single thread)."""
     import ba_data
@@ -552,7 +634,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 307 KB > 126 MB L2)")
+    ap.add_argument("--batch", type=int, default=592,
+                    help="frames per step per GPU: 2 sub-batches of 296 = 2 x 148 SMs, so the one-CTA-per-frame kernels "
+                         "(matcher, pose optimiser: 1 CTA/SM) run in whole waves; 592 x 307 KB = 182 MB > 126 MB L2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--streams", type=int, default=2, help="sub-batches in flight per GPU (one context/stream each)")
@@ -562,9 +646,10 @@ def main():
     ap.add_argument("--no-ba", action="store_true", help="skip the local-BA metric")
     ap.add_argument("--no-lines", action="store_true", help="skip the LSD+LBD line front-end metric")
     ap.add_argument("--only-lines", action="store_true", help="development: run only the line front-end leg")
+    ap.add_argument("--no-mapping", action="store_true", help="skip the fuse / BoW legs (SURVEY 8(f) rows)")
     ap.add_argument("--no-stereo", action="store_true", help="skip the stereo point+line front-end leg (configs[4])")
     ap.add_argument("--only-stereo", action="store_true", help="development: run only the stereo leg")
-    ap.add_argument("--stereo-batch", type=int, default=128, help="stereo frames per step per GPU")
+    ap.add_argument("--stereo-batch", type=int, default=148, help="stereo frames per step per GPU")
     ap.add_argument("--line-batch", type=int, default=1776, help="frames per step per GPU of the line front-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -723,8 +808,16 @@ def main():
         alg = PYR_PX
     alg_bytes_launch = alg * Bs
     achieved = alg_bytes_launch / (per_launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tf = sorted((ROOT / "profiles").glob("traffic_*.json"))
+    if tf:  # dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture, scaled to this launch
+        tj = json.loads(tf[-1].read_text())
+        kk = tj["kernels"].get(dom_name)
+        if kk:
+            traffic = (kk["dram_bytes_read"] + kk["dram_bytes_write"]) / tj["frames_per_launch"] * Bs
+            traffic_src = f"{tf[-1].name}: {tj['source']}; per-frame bytes x {Bs} frames"
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": per_launch_ms,
                 "kernel_time_shares": shares,
                 "frames_per_launch": Bs,
@@ -744,6 +837,13 @@ def main():
     if not args.no_stereo:
         stereo_res = bench_stereo(pkg, ctx, stream, rank, world, max(3, args.steps // 2), args.warmup, args.stereo_batch,
                                   args.seed)
+
+    mapping_res = None
+    if rank == 0 and world == 1 and not args.no_mapping:
+        try:
+            mapping_res = bench_mapping(pkg, ctx, not args.no_cpu_baseline)
+        except Exception as e:  # an auxiliary leg must not take the headline line down with it; say so loudly
+            mapping_res = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
@@ -779,6 +879,8 @@ def main():
             line["line_frontend"] = lines_res
         if stereo_res is not None:
             line["stereo_frontend"] = stereo_res
+        if mapping_res is not None:
+            line["mapping_matchers"] = mapping_res
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

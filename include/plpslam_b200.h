@@ -478,6 +478,25 @@ PLP_API plp_status plp_match_bow_tree(plp_ctx *ctx, plp_bow_pair *pairs, int num
                                       int check_orientation);
 
 /* ------------------------------------------------------------------------ */
+/* essential-matrix RANSAC  (solve/essential_solver.{h,cc})                  */
+/* ------------------------------------------------------------------------ */
+/* solve::essential_solver::find_via_ransac(max_num_iter, recompute) (solve/essential_solver.cc:37-121), the inlier filter
+ * of robust::match_frame_and_keyframe (match/robust.cc:218-255: brute_force_match, then find_via_ransac(50, false)).
+ * matches_12[i] = {index into bearings_1, index into bearings_2}.  `samples` holds the num_iter x 8 match indices the
+ * reference draws with util::create_random_array(8, 0, num_matches - 1) per iteration (the reference seeds a fresh
+ * mt19937 from std::random_device each time, util/random_array.cc:37-44, so its result is not reproducible; with the
+ * samples as an input the result is a deterministic function of them).  All num_iter hypotheses are evaluated
+ * concurrently (one CTA each: eight-point solve, inlier test over all matches, score summed in match order); the first
+ * hypothesis with the largest score wins exactly like the reference's sequential `best_score_ < score_in_sac` scan.
+ * Outputs: is_inlier_out[num_matches], best_E_21_out[9] (row-major), *best_score_out, *solution_is_valid_out
+ * (best_score > 0 and >= 8 inliers; with fewer than 8 matches: 0 and nothing else is touched, :45-49).
+ * The two Eigen::JacobiSVD calls of compute_E_21 are restated with cyclic Jacobi rotations (csrc/essmath.h). */
+PLP_API plp_status plp_essential_ransac(plp_ctx *ctx, const double *bearings_1, int n1, const double *bearings_2, int n2,
+                                        const int32_t *matches_12, int num_matches, const int32_t *samples,
+                                        int num_iter, int recompute, uint8_t *is_inlier_out, double *best_E_21_out,
+                                        double *best_score_out, int32_t *solution_is_valid_out);
+
+/* ------------------------------------------------------------------------ */
 /* stereo matching  (match/stereo.{h,cc})                                    */
 /* ------------------------------------------------------------------------ */
 /* match::stereo::compute(stereo_x_right, depths) (match/stereo.cc:45-150): per left keypoint the Hamming-closest right

@@ -30,6 +30,7 @@
 #include "lines.h"
 #include "stereo.h"
 #include "bow.h"
+#include "essential.h"
 
 #ifdef __cplusplus
 extern "C" {

@@ -33,6 +33,7 @@ FILE_FLAGS = {
     "stereo.cu": NO_FMA,
     "fuse.cu": NO_FMA,
     "bow.cu": NO_FMA,
+    "essential.cu": NO_FMA,
 }
 
 
@@ -44,7 +45,7 @@ def _stamp(src: Path, flags) -> str:
     h = hashlib.sha1()
     h.update(" ".join(flags).encode())
     h.update(src.read_bytes())
-    for hdr in sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + list((HERE.parent / "include").glob("*.h"))):
+    for hdr in sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + list(CSRC.glob("*.h")) + list((HERE.parent / "include").glob("*.h"))):
         h.update(hdr.read_bytes())
     return h.hexdigest()
 

@@ -424,6 +424,23 @@ class Context:
                                                  C.c_int(1 if check_orientation else 0)))
         return [(m21[:n1].copy(), m12[:n2].copy(), int(arr[i].num_matches)) for i, (m21, m12, n1, n2) in enumerate(outs)]
 
+    # ------------------------------------------------------------------ solve::essential_solver
+    def essential_ransac(self, bearings_1, bearings_2, matches_12, samples, recompute=False):
+        """solve::essential_solver::find_via_ransac with caller-drawn sample sets (num_iter x 8 match indices).
+        Returns (solution_is_valid, is_inlier, E_21, best_score)."""
+        b1 = np.ascontiguousarray(bearings_1, np.float64).reshape(-1, 3)
+        b2 = np.ascontiguousarray(bearings_2, np.float64).reshape(-1, 3)
+        m = np.ascontiguousarray(matches_12, np.int32).reshape(-1, 2)
+        sm = np.ascontiguousarray(samples, np.int32).reshape(-1, 8)
+        inl = np.zeros(max(len(m), 1), np.uint8)
+        E = np.zeros(9, np.float64)
+        score, valid = C.c_double(0.0), C.c_int32(0)
+        self._check(self._lib.plp_essential_ransac(
+            self._h, b1.ctypes.data_as(_P), C.c_int(len(b1)), b2.ctypes.data_as(_P), C.c_int(len(b2)),
+            m.ctypes.data_as(_P), C.c_int(len(m)), sm.ctypes.data_as(_P), C.c_int(len(sm)), C.c_int(1 if recompute else 0),
+            inl.ctypes.data_as(_P), E.ctypes.data_as(_P), C.byref(score), C.byref(valid)))
+        return int(valid.value), inl[:len(m)].copy(), E.reshape(3, 3), float(score.value)
+
     def landmark_compute_descriptor_batch(self, descs, offsets):
         """landmark::compute_descriptor for a batch: index of the median-distance observation per landmark."""
         d = np.ascontiguousarray(descs, np.uint8).reshape(-1, 32)

@@ -515,10 +515,16 @@ plp_status plp_match_bow_tree(plp_ctx *ctx, plp_bow_pair *pairs, int num_pairs, 
         po[p].o_ne2 = pk.add(nn ? po[p].ne2.data() : nullptr, nn * 4);
         po[p].o_claimed = pk.reserve(n2 + 1);
         po[p].o_choice = pk.reserve(n1 * 4 + 4);
+    }
+    // all results in ONE contiguous region -> one D2H copy (a copy per pair and array costs more than the kernel)
+    const size_t o_out0 = pk.total;
+    for (int p = 0; p < num_pairs; ++p) {
+        const size_t n1 = (size_t)pairs[p].side1->n, n2 = (size_t)pairs[p].side2->n;
         po[p].o_m21 = pk.reserve(n1 * 4 + 4);
         po[p].o_m12 = pk.reserve(n2 * 4 + 4);
         po[p].o_num = pk.reserve(4);
     }
+    const size_t o_out1 = pk.total;
     std::vector<BowJob> jobs(num_pairs);
     const size_t o_jobs = pk.add(jobs.data(), sizeof(BowJob) * (size_t)num_pairs);
     PLP_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -559,16 +565,18 @@ plp_status plp_match_bow_tree(plp_ctx *ctx, plp_bow_pair *pairs, int num_pairs, 
     PLP_LAUNCH(ctx, bow_match_kernel, num_pairs, kMatchThreads, 0, Packer::at<BowJob>(d, o_jobs), lowe_ratio,
                check_orientation);
     PLP_CHECK_LAUNCH();
+    void *hp = nullptr;
+    PLP_TRY(ctx_pinned(ctx, pk.total ? pk.total : 256, &hp));  // the staging buffer upload() just used
+    uint8_t *h = (uint8_t *)hp;
+    PLP_CUDA_TRY(cudaMemcpyAsync(h + o_out0, d + o_out0, o_out1 - o_out0, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     std::vector<uint32_t> nums(num_pairs, 0);
     for (int p = 0; p < num_pairs; ++p) {
         const size_t n1 = (size_t)pairs[p].side1->n, n2 = (size_t)pairs[p].side2->n;
-        if (pairs[p].matched_2_of_1_out && n1)
-            PLP_CUDA_TRY(cudaMemcpyAsync(pairs[p].matched_2_of_1_out, d + po[p].o_m21, n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (pairs[p].matched_1_of_2_out && n2)
-            PLP_CUDA_TRY(cudaMemcpyAsync(pairs[p].matched_1_of_2_out, d + po[p].o_m12, n2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        PLP_CUDA_TRY(cudaMemcpyAsync(&nums[p], d + po[p].o_num, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (pairs[p].matched_2_of_1_out && n1) memcpy(pairs[p].matched_2_of_1_out, h + po[p].o_m21, n1 * 4);
+        if (pairs[p].matched_1_of_2_out && n2) memcpy(pairs[p].matched_1_of_2_out, h + po[p].o_m12, n2 * 4);
+        memcpy(&nums[p], h + po[p].o_num, 4);
     }
-    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     for (int p = 0; p < num_pairs; ++p) pairs[p].num_matches = nums[p];
     return PLP_OK;
 }

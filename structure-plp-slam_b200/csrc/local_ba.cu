@@ -535,7 +535,7 @@ __global__ void ba_reduce_kernel(BaDev B) {
 }
 
 // =========================================================================================================
-// ba_solve_kernel: 6N x 6N LDL^T in shared memory (packed lower triangle)
+// ba_solve_kernel: 6N x 6N blocked Cholesky in shared memory (packed lower triangle)
 // =========================================================================================================
 constexpr int kSolveThreads = 1024;
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
@@ -583,42 +583,82 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
     for (int i = tid; i < n; i += kSolveThreads) rhs[i] = packed[nS + i];
     if (tid == 0) s_ok = 1;
     __syncthreads();
-    // LDL^T, right-looking, ONE barrier per column: at step j the (unscaled) column c_i = A[i][j] and the pivot d_j
-    // are only read while the trailing triangle (k > j) is only written.  One warp per row, lanes over the columns
-    // (contiguous in the packed lower triangle).
+    // Blocked Cholesky (L L^T) on the packed lower triangle, block = one keyframe (6 x 6), right-looking, with the
+    // right-hand side carried along as an extra row "n" so that the forward substitution z = L^-1 b falls out of the
+    // factorisation.  Per block column three short phases / three barriers (N block columns instead of 6N scalar
+    // columns): (1) thread 0 factors the 6 x 6 diagonal block, (2) one thread per row below solves its 6-vector
+    // against it, (3) one warp per trailing row applies the rank-6 update, lanes over the (contiguous) columns.
+    __shared__ double s_lkk[21], s_inv[6];
     {
         const int lane = tid & 31, warp = tid >> 5, nwarps = kSolveThreads / 32;
-        for (int j = 0; j < n; ++j) {
-            const double dj = L[tri(j, j)];
-            if (!(dj > 0.0) || !isfinite(dj)) {  // not positive definite (uniform branch)
-                if (tid == 0) s_ok = 0;
-                break;
+        for (int K = 0; K < n; K += 6) {
+            if (tid == 0) {
+                double l[6][6];
+                bool pd = true;
+                for (int r = 0; r < 6; ++r)
+                    for (int c = 0; c <= r; ++c) l[r][c] = L[tri(K + r, K + c)];
+                for (int c = 0; c < 6 && pd; ++c) {
+                    double d = l[c][c];
+                    for (int m = 0; m < c; ++m) d -= l[c][m] * l[c][m];
+                    if (!(d > 0.0) || !isfinite(d)) {  // not positive definite
+                        pd = false;
+                        break;
+                    }
+                    const double lcc = sqrt(d), inv = 1.0 / lcc;
+                    l[c][c] = lcc;
+                    s_inv[c] = inv;
+                    for (int r = c + 1; r < 6; ++r) {
+                        double v = l[r][c];
+                        for (int m = 0; m < c; ++m) v -= l[r][m] * l[c][m];
+                        l[r][c] = v * inv;
+                    }
+                }
+                if (!pd) s_ok = 0;
+                int q = 0;
+                for (int r = 0; r < 6; ++r)
+                    for (int c = 0; c <= r; ++c) {
+                        L[tri(K + r, K + c)] = l[r][c];
+                        s_lkk[q++] = l[r][c];
+                    }
             }
-            const double inv = 1.0 / dj;
-            for (int i = j + 1 + warp; i < n; i += nwarps) {
-                const double ci = L[tri(i, j)] * inv;
-                const int base = tri(i, 0);
-                for (int k = j + 1 + lane; k <= i; k += 32) L[base + k] -= ci * L[tri(k, j)];
+            __syncthreads();
+            if (!s_ok) break;  // uniform
+            for (int row = K + 6 + tid; row <= n; row += kSolveThreads) {
+                double *a = row < n ? &L[tri(row, K)] : &rhs[K];
+                double xv[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    double v = a[c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) v -= xv[m] * s_lkk[c * (c + 1) / 2 + m];
+                    xv[c] = v * s_inv[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 6; ++c) a[c] = xv[c];
+            }
+            __syncthreads();
+            for (int i = K + 6 + warp; i <= n; i += nwarps) {
+                const double *li = i < n ? &L[tri(i, K)] : &rhs[K];
+                const double l0 = li[0], l1 = li[1], l2 = li[2], l3 = li[3], l4 = li[4], l5 = li[5];
+                double *rowp = i < n ? &L[tri(i, 0)] : rhs;
+                const int kmax = i < n ? i : n - 1;
+                for (int k = K + 6 + lane; k <= kmax; k += 32) {
+                    const double *lk = &L[tri(k, K)];
+                    rowp[k] -= l0 * lk[0] + l1 * lk[1] + l2 * lk[2] + l3 * lk[3] + l4 * lk[4] + l5 * lk[5];
+                }
             }
             __syncthreads();
         }
     }
     __syncthreads();
     const int ok = s_ok;
-    // substitutions by one warp: L z = b, y = D^-1 z, L^T x = y   (l_ij = L[i][j] / d_j)
+    // rhs now holds z = L^-1 b; back substitution L^T x = z by one warp (row j of L is contiguous: lanes over i < j)
     if (tid < 32 && ok) {
-        for (int j = 0; j < n; ++j) {
-            const double zj = rhs[j];
-            const double f = zj / L[tri(j, j)];
-            for (int i = j + 1 + tid; i < n; i += 32) rhs[i] -= L[tri(i, j)] * f;
-            __syncwarp();
-        }
-        for (int j = tid; j < n; j += 32) rhs[j] /= L[tri(j, j)];
-        __syncwarp();
         for (int j = n - 1; j >= 0; --j) {
-            const double xj = rhs[j];
+            const double xj = rhs[j] / L[tri(j, j)];
             if (tid == 0) x[j] = xj;
-            for (int i = tid; i < j; i += 32) rhs[i] -= (L[tri(j, i)] / L[tri(i, i)]) * xj;
+            const double *lj = &L[tri(j, 0)];
+            for (int i = tid; i < j; i += 32) rhs[i] -= lj[i] * xj;
             __syncwarp();
         }
     }

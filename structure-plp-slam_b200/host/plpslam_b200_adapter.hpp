@@ -10,6 +10,8 @@
 //   src/PLPSLAM/feature/line_extractor.cc       (LineFeatureTracker::extract_LSD_LBD)
 //   src/PLPSLAM/data/frame.cc                   (match::stereo::compute call site)
 //   src/PLPSLAM/match/projection.cc / robust.cc (match_frame_and_keyframe, match_for_triangulation)
+//   src/PLPSLAM/mapping_module.cc               (fuse_landmark_duplication -> match::fuse::replace_duplication)
+//   src/PLPSLAM/data/frame.cc / keyframe.cc     (compute_bow), src/PLPSLAM/module/relocalizer.cc (bow_tree matcher)
 // call.  Public signatures, PLPSLAM::system, the YAML configs and the map database stay unchanged.
 // See INTEGRATION.md for the patch of each call site.
 #pragma once
@@ -314,6 +316,200 @@ inline unsigned match_for_triangulation(PLPSLAM::data::keyframe *kf1, PLPSLAM::d
         if (m21[i] >= 0) matched_idx_pairs.emplace_back(i, (unsigned)m21[i]);
     return num;
 }
+
+// ---- match::fuse::replace_duplication (match/fuse.cc:153-300) over the loop of mapping_module.cc:711-714 / :749 ---
+// One batched search for (targets x landmarks); the effects are applied in the reference's order.  landmark::replace
+// recomputes the surviving landmark's descriptor (data/landmark.cc:429), so a landmark whose descriptor changed is
+// searched again against the remaining targets before its next use -- results are identical to the sequential loop
+// (tests/test_fuse_oracle.py::test_adapter_protocol_equals_sequential_reference checks the protocol on a map model).
+// NOTE: needs read access to landmark::max_valid_dist_ (predict_scale_level's numerator, landmark.cc:346); add
+// `friend struct plpslam_b200::landmark_access;` to data/landmark.h (no public signature changes).
+struct landmark_access {
+    static float max_valid_dist_raw(const PLPSLAM::data::landmark *lm) { return lm->max_valid_dist_; }
+};
+
+struct fuse_batch {
+    std::vector<double> pos, normal;
+    std::vector<float> min_d, max_d, max_raw;
+    std::vector<uint8_t> desc, valid;
+    void gather(const std::vector<PLPSLAM::data::landmark *> &lms, const std::vector<size_t> &which) {
+        const size_t m = which.size();
+        pos.resize(3 * m), normal.resize(3 * m), min_d.resize(m), max_d.resize(m), max_raw.resize(m);
+        desc.resize(32 * m), valid.resize(m);
+        for (size_t q = 0; q < m; ++q) {
+            auto *lm = lms[which[q]];
+            valid[q] = lm && !lm->will_be_erased();
+            if (!valid[q]) continue;
+            const PLPSLAM::Vec3_t p = lm->get_pos_in_world(), nrm = lm->get_obs_mean_normal();
+            for (int k = 0; k < 3; ++k) pos[3 * q + k] = p(k), normal[3 * q + k] = nrm(k);
+            min_d[q] = lm->get_min_valid_distance();
+            max_d[q] = lm->get_max_valid_distance();
+            max_raw[q] = landmark_access::max_valid_dist_raw(lm);
+            const cv::Mat d = lm->get_descriptor();
+            std::copy(d.data, d.data + 32, desc.begin() + 32 * q);
+        }
+    }
+    plp_fuse_landmarks view() const {
+        return plp_fuse_landmarks{(int32_t)valid.size(), pos.data(), normal.data(), min_d.data(), max_d.data(),
+                                  max_raw.data(), desc.data(), valid.data()};
+    }
+};
+
+struct fuse_target {
+    std::vector<float> x, y;
+    std::vector<int32_t> oct;
+    plp_fuse_target_points t;
+    explicit fuse_target(PLPSLAM::data::keyframe *kf) {
+        const int n = kf->num_keypts_;
+        x.resize(n), y.resize(n), oct.resize(n);
+        for (int i = 0; i < n; ++i) x[i] = kf->undist_keypts_[i].pt.x, y[i] = kf->undist_keypts_[i].pt.y, oct[i] = kf->undist_keypts_[i].octave;
+        t.pts = plp_frame_points{n, x.data(), y.data(), oct.data(), nullptr, kf->stereo_x_right_.data(), kf->descriptors_.data, nullptr};
+        const PLPSLAM::Mat33_t R = kf->get_rotation();
+        const PLPSLAM::Vec3_t tr = kf->get_translation(), c = kf->get_cam_center();
+        for (int r = 0; r < 3; ++r) {
+            for (int k = 0; k < 3; ++k) t.rot_cw[3 * r + k] = R(r, k);
+            t.trans_cw[r] = tr(r), t.cam_center[r] = c(r);
+        }
+        t.skip = nullptr;  // is_observed_in_keyframe is re-checked when the effect is applied
+    }
+};
+
+// fuse.cc:284-318 for one landmark with a search hit
+inline void fuse_apply(PLPSLAM::data::keyframe *keyfrm, PLPSLAM::data::landmark *lm, int best_idx) {
+    auto *lm_in_keyfrm = keyfrm->get_landmark(best_idx);
+    if (lm_in_keyfrm) {
+        if (!lm_in_keyfrm->will_be_erased()) {
+            if (lm->num_observations() < lm_in_keyfrm->num_observations())
+                lm->replace(lm_in_keyfrm);
+            else
+                lm_in_keyfrm->replace(lm);
+        }
+    } else {
+        lm->add_observation(keyfrm, best_idx);
+        keyfrm->add_landmark(lm, best_idx);
+    }
+}
+
+// body of `for (fuse_tgt_keyfrm : fuse_tgt_keyfrms) matcher.replace_duplication(fuse_tgt_keyfrm, cur_landmarks)` and of
+// the single-target call at mapping_module.cc:749 (targets.size() == 1); returns num_fused per target
+inline std::vector<unsigned> replace_duplication(const std::vector<PLPSLAM::data::keyframe *> &targets,
+                                                 const std::vector<PLPSLAM::data::landmark *> &lms, float margin = 3.0f) {
+    const size_t K = targets.size(), M = lms.size();
+    std::vector<unsigned> num_fused(K, 0);
+    if (!K || !M) return num_fused;
+    auto *kf0 = targets[0];
+    const plp_grid g = grid_of(kf0->camera_);
+    const plp_camera cam = camera_of(kf0->camera_);
+    std::vector<fuse_target> tg;
+    tg.reserve(K);
+    for (auto *kf : targets) tg.emplace_back(kf);
+    auto search = [&](size_t first_target, const std::vector<size_t> &which, std::vector<int32_t> &best) {
+        fuse_batch fb;
+        fb.gather(lms, which);
+        std::vector<plp_fuse_target_points> tv;
+        for (size_t k = first_target; k < K; ++k) tv.push_back(tg[k].t);
+        const plp_fuse_landmarks lv = fb.view();
+        best.resize(tv.size() * which.size());
+        check(plp_fuse_search_points(thread_ctx(), tv.data(), (int)tv.size(), &g, &cam, kf0->scale_factors_.data(),
+                                     kf0->inv_level_sigma_sq_.data(), (int)kf0->num_scale_levels_, kf0->log_scale_factor_,
+                                     &lv, margin, PLP_FUSE_REPLACE, best.data(), nullptr));
+    };
+    std::vector<size_t> all(M);
+    for (size_t i = 0; i < M; ++i) all[i] = i;
+    std::vector<int32_t> best;
+    search(0, all, best);  // best[k * M + i]
+    std::vector<std::vector<uint8_t>> desc_seen(M);
+    for (size_t i = 0; i < M; ++i)
+        if (lms[i]) { const cv::Mat d = lms[i]->get_descriptor(); desc_seen[i].assign(d.data, d.data + 32); }
+    for (size_t k = 0; k < K; ++k) {
+        for (size_t i = 0; i < M; ++i) {
+            auto *lm = lms[i];
+            if (!lm || lm->will_be_erased() || lm->is_observed_in_keyframe(targets[k])) continue;  // fuse.cc:163-174
+            const cv::Mat d = lm->get_descriptor();
+            if (!std::equal(d.data, d.data + 32, desc_seen[i].begin())) {  // recomputed by an earlier replace()
+                std::vector<int32_t> again;
+                search(k, {i}, again);
+                for (size_t kk = k; kk < K; ++kk) best[kk * M + i] = again[kk - k];
+                desc_seen[i].assign(d.data, d.data + 32);
+            }
+            const int b = best[k * M + i];
+            if (b < 0) continue;
+            fuse_apply(targets[k], lm, b);
+            ++num_fused[k];
+        }
+    }
+    return num_fused;
+}
+
+// ---- frame::compute_bow / keyframe::compute_bow (data/frame.cc:785-795) ----------------------------------------
+// One device vocabulary per process (loaded from the same file as bow_vocab_->loadFromBinaryFile, system.cc:82).
+#ifdef USE_DBOW2
+inline void compute_bow(plp_bow_vocab *vocab, const cv::Mat &descriptors, DBoW2::BowVector &bow_vec,
+                        DBoW2::FeatureVector &bow_feat_vec, int levelsup = 4) {
+    const int n = descriptors.rows;
+    std::vector<int32_t> word(n), node(n);
+    std::vector<float> weight(n);
+    check(plp_bow_transform(vocab, descriptors.data, n, levelsup, word.data(), node.data(), weight.data()));
+    bow_vec.clear();
+    bow_feat_vec.clear();
+    for (int i = 0; i < n; ++i) {  // TemplatedVocabulary::transform(features, v, fv, levelsup), TF_IDF branch
+        if (!(weight[i] > 0)) continue;
+        bow_vec.addWeight((DBoW2::WordId)word[i], (DBoW2::WordValue)weight[i]);
+        bow_feat_vec.addFeature((DBoW2::NodeId)node[i], (unsigned)i);
+    }
+    bow_vec.normalize(DBoW2::L1);  // L1_NORM scoring: mustNormalize
+}
+
+// ---- match::bow_tree::match_frame_and_keyframe (match/bow_tree.cc:41-165) for a batch of candidate keyframes -----
+struct bow_side_view {
+    std::vector<uint32_t> ids, idx;
+    std::vector<int32_t> off;
+    std::vector<float> angle;
+    std::vector<uint8_t> valid;
+    plp_bow_side s;
+    template <class KP>
+    void fill(const DBoW2::FeatureVector &fv, const KP &keypts, const cv::Mat &desc, bool with_valid) {
+        off.push_back(0);
+        for (const auto &kv : fv) {
+            ids.push_back(kv.first);
+            idx.insert(idx.end(), kv.second.begin(), kv.second.end());
+            off.push_back((int32_t)idx.size());
+        }
+        angle.resize(keypts.size());
+        for (size_t i = 0; i < keypts.size(); ++i) angle[i] = keypts[i].angle;
+        s = plp_bow_side{(int32_t)keypts.size(), desc.data, angle.data(), with_valid ? valid.data() : nullptr,
+                         plp_bow_feature_vector{(int32_t)ids.size(), ids.data(), off.data(), idx.data()}};
+    }
+};
+
+inline std::vector<unsigned> match_frame_and_keyframes(const std::vector<PLPSLAM::data::keyframe *> &keyfrms,
+                                                       PLPSLAM::data::frame &frm, float lowe_ratio, bool check_orientation,
+                                                       std::vector<std::vector<PLPSLAM::data::landmark *>> &matched_lms_in_frm) {
+    const size_t K = keyfrms.size();
+    bow_side_view fs;
+    fs.fill(frm.bow_feat_vec_, frm.keypts_, frm.descriptors_, false);
+    std::vector<bow_side_view> ks(K);
+    std::vector<std::vector<PLPSLAM::data::landmark *>> kf_lms(K);
+    std::vector<std::vector<int32_t>> m12(K, std::vector<int32_t>(frm.num_keypts_));
+    std::vector<plp_bow_pair> pairs(K);
+    for (size_t k = 0; k < K; ++k) {
+        kf_lms[k] = keyfrms[k]->get_landmarks();
+        ks[k].valid.resize(kf_lms[k].size());
+        for (size_t i = 0; i < kf_lms[k].size(); ++i) ks[k].valid[i] = kf_lms[k][i] && !kf_lms[k][i]->will_be_erased();
+        ks[k].fill(keyfrms[k]->bow_feat_vec_, keyfrms[k]->keypts_, keyfrms[k]->descriptors_, true);
+        pairs[k] = plp_bow_pair{&ks[k].s, &fs.s, nullptr, m12[k].data(), 0};
+    }
+    check(plp_match_bow_tree(thread_ctx(), pairs.data(), (int)K, lowe_ratio, check_orientation));
+    std::vector<unsigned> num(K);
+    matched_lms_in_frm.assign(K, std::vector<PLPSLAM::data::landmark *>(frm.num_keypts_, nullptr));
+    for (size_t k = 0; k < K; ++k) {
+        for (unsigned i = 0; i < frm.num_keypts_; ++i)
+            if (m12[k][i] >= 0) matched_lms_in_frm[k][i] = kf_lms[k][m12[k][i]];
+        num[k] = pairs[k].num_matches;
+    }
+    return num;
+}
+#endif  // USE_DBOW2
 
 }  // namespace plpslam_b200
 

@@ -22,7 +22,7 @@ def _pose_parts(T):
     return R, t, -R.T @ t
 
 
-def make_point_fuse_scene(seed, m=800, num_targets=4, n_extra=250, stereo=False, num_levels=8):
+def make_point_fuse_scene(seed, m=800, num_targets=4, n_extra=250, stereo=False, num_levels=8, obs_frac=0.8):
     """Landmarks + `num_targets` target keyframes that re-observe most of them (noisy, on the level grid)."""
     rng = np.random.default_rng(seed)
     sf = synth.scale_factors(num_levels)
@@ -57,7 +57,7 @@ def make_point_fuse_scene(seed, m=800, num_targets=4, n_extra=250, stereo=False,
         s = sf[octv][:, None].astype(np.float32)
         pts = (np.round((uv + noise) / s) * s).astype(np.float32)
         kdesc = synth.flip_bits(rng, desc, rng.integers(3, 75, m))
-        keep = (rng.random(m) > 0.2) & (z > 0.1)
+        keep = (rng.random(m) > 1.0 - obs_frac) & (z > 0.1)
         xs, ys, octs, descs = [pts[keep, 0]], [pts[keep, 1]], [octv[keep]], [kdesc[keep]]
         zs = [z[keep]]
         nd = int(0.15 * keep.sum())

@@ -323,6 +323,28 @@ class Oracle:
             C.c_float(lowe_ratio), C.c_int(1 if check_orientation else 0), m21.ctypes.data_as(_P), m12.ctypes.data_as(_P))
         return m21[:n1].copy(), m12[:n2].copy(), int(num)
 
+    # ---- solve::essential_solver
+    def essential_compute_E21(self, b1, b2):
+        b1 = np.ascontiguousarray(b1, np.float64).reshape(-1, 3)
+        b2 = np.ascontiguousarray(b2, np.float64).reshape(-1, 3)
+        E = np.zeros(9, np.float64)
+        self.lib.orc_essential_compute_E21(b1.ctypes.data_as(_P), b2.ctypes.data_as(_P), C.c_int(len(b1)), E.ctypes.data_as(_P))
+        return E.reshape(3, 3)
+
+    def essential_ransac(self, b1, b2, matches, samples, recompute=False):
+        """-> (valid, is_inlier, E_21, best_score, scores)"""
+        b1 = np.ascontiguousarray(b1, np.float64).reshape(-1, 3)
+        b2 = np.ascontiguousarray(b2, np.float64).reshape(-1, 3)
+        m = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+        sm = np.ascontiguousarray(samples, np.int32).reshape(-1, 8)
+        inl = np.zeros(max(len(m), 1), np.uint8)
+        E, score, scores = np.zeros(9), C.c_double(0), np.zeros(max(len(sm), 1), np.float32)
+        valid = self.lib.orc_essential_ransac(b1.ctypes.data_as(_P), b2.ctypes.data_as(_P), m.ctypes.data_as(_P),
+                                              C.c_int(len(m)), sm.ctypes.data_as(_P), C.c_int(len(sm)),
+                                              C.c_int(1 if recompute else 0), inl.ctypes.data_as(_P), E.ctypes.data_as(_P),
+                                              C.byref(score), scores.ctypes.data_as(_P))
+        return int(valid), inl[:len(m)].copy(), E.reshape(3, 3), float(score.value), scores[:len(sm)].copy()
+
     def landmark_compute_descriptor_batch(self, descs, offsets):
         d, pd = _a(np.asarray(descs).reshape(-1, 32), np.uint8)
         o, po = _a(offsets, np.int32)

@@ -31,7 +31,7 @@ def test_fuse_search_points(ctx, orc, plp, seed):
             assert np.array_equal(g_idx[t], o_idx)
             assert np.array_equal(g_dist[t], o_dist)
             matched += (o_idx >= 0).sum()
-    assert matched > 200
+    assert matched > 100
 
 
 @pytest.mark.parametrize("seed", range(4))
@@ -63,7 +63,7 @@ def test_fuse_full_size_batch(ctx, orc, plp):
     for t in (0, 7, 19):
         o_idx, o_dist, _ = orc.fuse_search_points(grid, cam, sf, isg, fuse_data.LOG_SF, targets[t], lms, 3.0, 1)
         assert np.array_equal(g_idx[t], o_idx) and np.array_equal(g_dist[t], o_dist)
-    lms, targets = fuse_data.make_point_fuse_scene(78, m=6000, num_targets=1, n_extra=400)
+    lms, targets = fuse_data.make_point_fuse_scene(78, m=6000, num_targets=1, n_extra=400, obs_frac=0.2)
     g_idx, g_dist = ctx.fuse_search_points(grid, cam, sf, isg, fuse_data.LOG_SF, targets, lms, 3.0, 1)
     o_idx, o_dist, _ = orc.fuse_search_points(grid, cam, sf, isg, fuse_data.LOG_SF, targets[0], lms, 3.0, 1)
     assert np.array_equal(g_idx[0], o_idx) and np.array_equal(g_dist[0], o_dist)
