@@ -174,7 +174,8 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
         deg_e[n_pts + l + 1] = deg_e[n_pts + l] + 4 * (ln_off[l + 1] - ln_off[l]) + 1;  // numeric Jacobians: ~4x cost
     }
     PLP_REQUIRE(max_deg <= kBaMaxFree, "a landmark is observed twice by the same keyframe");
-    const int LB = std::max(1, std::min(16, 96 / max_deg));
+    const int pool_cap = ba_pool_capacity(n_free, n_free * (n_free + 1) / 2, max_deg);
+    const int LB = std::max(1, std::min(16, pool_cap / max_deg));
     int G = cfg->num_ctas > 0 ? cfg->num_ctas : std::max(1, std::min(ctx->sm_count, (n_lm + 2 * LB - 1) / (2 * LB)));
     G = std::max(1, std::min(G, std::max(1, n_lm)));
     std::vector<int> ranges(G + 1, n_lm);
@@ -204,7 +205,7 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
     const int packed_sum_len = n_pairs * 36 + 12 * n_free + 1;
     const int packed_len = (packed_sum_len + 1 + 31) & ~31;
     PLP_CUDA_TRY(cudaSetDevice(ctx->device));
-    PLP_TRY(ba_prepare_kernels(n_free, n_pairs));
+    PLP_TRY(ba_prepare_kernels(n_free, n_pairs, pool_cap));
     plp_ba *b = new plp_ba();
     b->ctx = ctx;
     b->cfg = *cfg;
@@ -289,6 +290,7 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
     D.n_pl_edges = p->n_plane_edges;
     D.num_ctas = G;
     D.batch_landmarks = LB;
+    D.pool_cap = pool_cap;
     D.packed_len = packed_len;
     D.packed_sum_len = packed_sum_len;
     D.rank = rank;

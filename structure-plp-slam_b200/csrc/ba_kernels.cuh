@@ -23,7 +23,7 @@ struct BaDev {
     double delta_pt, delta_ln;  // Huber deltas (sqrt(5.991) | sqrt(7.815), sqrt(5.991))
     // sizes
     int n_kf, n_free, n_pairs, n_pts, n_lines, n_pt_edges, n_ln_edges, n_pl_edges;
-    int num_ctas, batch_landmarks, packed_len, packed_sum_len;
+    int num_ctas, batch_landmarks, pool_cap, packed_len, packed_sum_len;
     int rank, world;
     // keyframes
     const int *kf_hidx;             // index among the free keyframes or -1
@@ -65,9 +65,10 @@ struct BaCollective {
     virtual ~BaCollective() {}
 };
 
-size_t ba_linearize_smem(int n_free, int n_pairs);
+size_t ba_linearize_smem(int n_free, int n_pairs, int pool_cap);
+int ba_pool_capacity(int n_free, int n_pairs, int max_free_degree);
 size_t ba_solve_smem(int n_free);
-plp_status ba_prepare_kernels(int n_free, int n_pairs);
+plp_status ba_prepare_kernels(int n_free, int n_pairs, int pool_cap);
 plp_status ba_launch_try(plp_ctx *ctx, const BaDev &B, BaCollective *coll);
 plp_status ba_launch_decide(plp_ctx *ctx, const BaDev &B);
 plp_status ba_launch_set_state(plp_ctx *ctx, const BaDev &B, int max_it, int robust, int reset_cur);

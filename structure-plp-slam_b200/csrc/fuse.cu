@@ -17,6 +17,7 @@
 #include <math.h>
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 
 namespace plp {
 
@@ -113,7 +114,7 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
 }
 
 static size_t fuse_point_smem_bytes(int cap, int cells) {
-    return (size_t)cap * (32 + 6 * 4) + (size_t)(cells + 2) * 4 + 16;
+    return (size_t)cap * (32 + 6 * 4) + (size_t)(cells + 2) * 8 + 32 * 4;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -150,31 +151,81 @@ __global__ void __launch_bounds__(kThreads, 1)
     base += (size_t)cap * 4;
     int *s_cell_start = reinterpret_cast<int *>(base);
     base += (size_t)(cells + 2) * 4;
-    int *s_flags = reinterpret_cast<int *>(base);
+    int *s_cursor = reinterpret_cast<int *>(base);
+    base += (size_t)(cells + 2) * 4;
+    int *s_warp = reinterpret_cast<int *>(base);
 
-    // ---- 1. cell key of every keypoint (data/common.h:104-109)
+    // ---- 1. cell key of every keypoint (data/common.h:104-109) and the cell histogram
+    for (int k = tid; k < cells + 2; k += kThreads) s_cell_start[k] = 0;
+    __syncthreads();
     for (int i = tid; i < n; i += kThreads) {
         const float px = T.x[i], py = T.y[i];
         const int cx = cv_floor((double)(px - grid.min_x) * grid.inv_cell_width);
         const int cy = cv_floor((double)(py - grid.min_y) * grid.inv_cell_height);
         const bool in = (0 <= cx && cx < grid.num_cols && 0 <= cy && cy < grid.num_rows);
-        s_key[i] = in ? cx * grid.num_rows + cy : cells;  // out-of-grid keypoints sort last and are never visited
+        const int key = in ? cx * grid.num_rows + cy : cells;  // out-of-grid keypoints sort last and are never visited
+        s_key[i] = key;
+        atomicAdd(&s_cell_start[key], 1);
     }
-    if (tid == 0) s_flags[0] = 0;
     __syncthreads();
-    // ---- 2. stable rank sort by (cell key, index) = traversal order of get_keypoints_in_cell (data/common.cc:275-309)
-    for (int i = tid; i < n; i += kThreads) {
-        const int ki = s_key[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            const int kj = s_key[j];
-            rank += (kj < ki) || (kj == ki && j < i);
+    // ---- 2. stable counting sort by (cell key, index) = traversal order of get_keypoints_in_cell
+    //         (data/common.cc:275-309).  (a) exclusive scan of the histogram: cell_start[k] = first sorted position
+    //         whose key >= k; (b) one warp walks the keypoints in index order, __match_any groups equal keys and gives
+    //         every lane its rank inside the group, the group leader advances the cell cursor.
+    {
+        const int total = cells + 1;  // keys 0 .. cells
+        const int per = (total + kThreads - 1) / kThreads;
+        const int b0 = min(total, tid * per), b1 = min(total, b0 + per);
+        int sum = 0;
+        for (int k = b0; k < b1; ++k) sum += s_cell_start[k];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        s_orig[rank] = i;
-        if (ki < cells) atomicAdd(&s_flags[0], 1);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = lane < nwarps ? s_warp[lane] : 0;
+            int sc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, sc, o);
+                if (lane >= o) sc += u;
+            }
+            if (lane < nwarps) s_warp[lane] = sc - v;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        int run = s_warp[warp] + incl - sum;
+        for (int k = b0; k < b1; ++k) {
+            const int v = s_cell_start[k];
+            s_cell_start[k] = run;
+            s_cursor[k] = run;
+            run += v;
+        }
+        if (tid == 0) s_cell_start[cells + 1] = n;
+        __syncthreads();
+        if (warp == 0) {
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                const int key = i < n ? s_key[i] : (0x40000000 | lane);  // idle lanes get unique keys
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                const int leader = __ffs(peers) - 1;
+                const int rank = __popc(peers & ((1u << lane) - 1));
+                int b = 0;
+                if (lane == leader && i < n) {
+                    b = s_cursor[key];
+                    s_cursor[key] = b + __popc(peers);
+                }
+                b = __shfl_sync(0xffffffffu, b, leader);
+                if (i < n) s_orig[b + rank] = i;
+                __syncwarp();
+            }
+        }
     }
     __syncthreads();
-    const int n_in = s_flags[0];
+    const int n_in = s_cell_start[cells];
     // ---- 3. gather in sorted order; s_oct keeps the octave, the cell key is re-read from s_key through s_orig
     for (int p = tid; p < n_in; p += kThreads) {
         const int i = s_orig[p];
@@ -186,12 +237,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         load_desc(T.desc + 32 * (size_t)i, d0, d1);
         s_desc[2 * p] = d0;
         s_desc[2 * p + 1] = d1;
-    }
-    // cell start table: cell_start[k] = first sorted position whose key >= k
-    for (int p = tid; p <= n_in; p += kThreads) {
-        const int kp = p < n_in ? s_key[s_orig[p]] : cells;
-        const int kprev = p > 0 ? s_key[s_orig[p - 1]] : -1;
-        for (int k = kprev + 1; k <= kp; ++k) s_cell_start[k] = p;
     }
     __syncthreads();
 
@@ -405,8 +450,35 @@ static int host_pred(float ratio, float lsf) {
 
 // level_thr[k] (1 <= k < num_levels) = smallest positive float r with host_pred(r) >= k.  logf is monotone in every
 // libm we know of; the neighbourhood of each threshold is checked and a violation is reported, never papered over.
+struct ThresholdCacheEntry {
+    float lsf;
+    int num_levels;
+    float thr[kMaxLevels];
+};
+static std::mutex g_thr_mutex;
+static std::vector<ThresholdCacheEntry> g_thr_cache;  // a process sees a handful of (scale factor, levels) pairs
+
+static plp_status build_level_thresholds_uncached(float lsf, int num_levels, float *thr);
+
+// the table costs ~60 k logf evaluations (bisection + the monotonicity check): computed once per (lsf, num_levels)
 static plp_status build_level_thresholds(float lsf, int num_levels, float *thr) {
     PLP_REQUIRE(lsf > 0.0f && num_levels >= 1 && num_levels <= kMaxLevels, "log_scale_factor / num_levels");
+    std::lock_guard<std::mutex> lock(g_thr_mutex);
+    for (const ThresholdCacheEntry &e : g_thr_cache)
+        if (memcmp(&e.lsf, &lsf, 4) == 0 && e.num_levels == num_levels) {
+            memcpy(thr, e.thr, sizeof(e.thr));
+            return PLP_OK;
+        }
+    ThresholdCacheEntry e;
+    e.lsf = lsf;
+    e.num_levels = num_levels;
+    PLP_TRY(build_level_thresholds_uncached(lsf, num_levels, e.thr));
+    if (g_thr_cache.size() < 64) g_thr_cache.push_back(e);
+    memcpy(thr, e.thr, sizeof(e.thr));
+    return PLP_OK;
+}
+
+static plp_status build_level_thresholds_uncached(float lsf, int num_levels, float *thr) {
     for (int k = 0; k < kMaxLevels; ++k) thr[k] = INFINITY;
     for (int k = 1; k < num_levels; ++k) {
         uint32_t lo = 0x00000001u, hi = 0x7f7fffffu;  // predicate false at lo, true at hi

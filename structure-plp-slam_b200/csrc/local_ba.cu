@@ -38,7 +38,7 @@ using se3::Pose;
 
 constexpr int kBaThreads = 512;
 constexpr int kBaWarps = kBaThreads / 32;
-constexpr int kPool = 96;        // per-batch pool of (free keyframe, landmark) blocks
+constexpr int kPoolMax = kBaWarps * kBaMaxFree;  // upper bound of the per-batch pool of (free keyframe, landmark) blocks
 constexpr double kDelta = 1e-9;  // g2o numeric Jacobian step
 
 // ---------------------------------------------------------------------------------------------------------
@@ -188,8 +188,8 @@ struct BaPoolEntry {
     double gpe[6];  // bpe - W * (Dinv bl)
 };
 
-struct BaSmem {
-    BaPoolEntry pool[kPool];
+struct BaSmem {  // the pool (B.pool_cap entries) and the partial system follow in dynamic shared memory
+    unsigned kfmask[kBaMaxFree];  // per free keyframe: which landmarks of the batch observe it (bit = landmark in batch)
     double pert_line[kBaWarps][8][6];  // per warp: the 8 perturbed lines of its landmark
     double hll[kBaWarps][16], bl[kBaWarps][4], dinv[kBaWarps][16], dl[kBaWarps][4];
     short slot[kBaWarps][kBaMaxFree];  // landmark-in-batch x free keyframe -> pool index (-1: none)
@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
     if (ST.phase == kBaDone) return;
     BaSmem &S = *reinterpret_cast<BaSmem *>(ba_smem_raw);
     const int nS = B.n_pairs * 36, n6 = 6 * B.n_free;
-    double *Ssm = reinterpret_cast<double *>(ba_smem_raw + ((sizeof(BaSmem) + 15) & ~(size_t)15));
+    BaPoolEntry *pool = reinterpret_cast<BaPoolEntry *>(ba_smem_raw + ((sizeof(BaSmem) + 15) & ~(size_t)15));
+    double *Ssm = reinterpret_cast<double *>(pool + B.pool_cap);
     double *gsm = Ssm + nS, *bpsm = gsm + n6;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool init_mode = ST.phase == kBaNeedInit;  // only max diag(H) is wanted
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
     for (int i = tid; i < nS + 2 * n6; i += kBaThreads) Ssm[i] = 0.0;
     double chi_acc = 0.0, maxdiag = 0.0;
     const int lm_begin = B.cta_ranges[blockIdx.x], lm_end = B.cta_ranges[blockIdx.x + 1];
-    const int LB = B.batch_landmarks;  // landmarks per batch (<= kBaWarps), LB * max_free_degree <= kPool
+    const int LB = B.batch_landmarks;  // landmarks per batch (<= kBaWarps), LB * max_free_degree <= B.pool_cap
     __syncthreads();
 
     for (int batch0 = lm_begin; batch0 < lm_end; batch0 += LB) {
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
         const bool has_lm = lmb < LB && lm < lm_end;
         // ---- slot table reset, count free active edges per landmark for the pool layout
         for (int i = tid; i < kBaWarps * kBaMaxFree; i += kBaThreads) (&S.slot[0][0])[i] = -1;
+        for (int i = tid; i < kBaMaxFree; i += kBaThreads) S.kfmask[i] = 0u;
         int e0 = 0, e1 = 0, D = 3;
         bool is_line = false;
         if (has_lm) {
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
                 const unsigned bal = __ballot_sync(0xffffffffu, freee);
                 if (freee) {
                     const int pi = pool_cursor + __popc(bal & ((1u << lane) - 1));
-                    BaPoolEntry &pe = S.pool[pi];
+                    BaPoolEntry &pe = pool[pi];
                     for (int a = 0; a < 6; ++a) {
                         for (int c = 0; c < D; ++c) {
                             double s = 0;
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
                             pe.A[q++] = s;
                         }
                     S.slot[lmb][h] = (short)pi;
+                    atomicOr(&S.kfmask[h], 1u << lmb);
                     // W is needed again by the back-substitution
                     double *Wg = (is_line ? B.ln_W : B.pt_W) + 24 * (size_t)e;
                     for (int q2 = 0; q2 < 6 * D; ++q2) Wg[q2] = pe.W[q2];
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
             // Y = W Dinv, gpe = bpe - W dl for this landmark's pool entries
             const int pb = S.pool_base[warp], pn = S.warp_cnt[warp];
             for (int pi = pb + lane; pi < pb + pn; pi += 32) {
-                BaPoolEntry &pe = S.pool[pi];
+                BaPoolEntry &pe = pool[pi];
                 for (int a = 0; a < 6; ++a) {
                     double gs = pe.bpe[a];
                     for (int c = 0; c < D; ++c) {
@@ -457,20 +460,22 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
         }
         __syncthreads();
         // ---- phase 2: every thread owns fixed entries of S / g / bp (no atomics, fixed summation order)
-        const int nb = min(LB, lm_end - batch0);
+        // only the landmarks that observe BOTH keyframes of a block contribute: walk the set bits of the two masks
+        // (ascending landmark = the summation order of a dense scan)
         for (int ent = tid; ent < nS; ent += kBaThreads) {
             const int p = ent / 36, rc = ent - p * 36, r = rc / 6, c = rc - r * 6;
             const int bi = B.pair_bi[p], bj = B.pair_bj[p];
+            unsigned m = S.kfmask[bi] & S.kfmask[bj];
+            if (!m) continue;
             double acc = 0.0;
-            for (int lb = 0; lb < nb; ++lb) {
-                const int si = S.slot[lb][bi];
-                if (si < 0) continue;
-                const int sj = S.slot[lb][bj];
-                if (sj < 0) continue;
+            while (m) {
+                const int lb = __ffs(m) - 1;
+                m &= m - 1;
+                const int si = S.slot[lb][bi], sj = S.slot[lb][bj];
                 const int Dl = (batch0 + lb) >= B.n_pts ? 4 : 3;
-                const BaPoolEntry &pi = S.pool[si], &pj = S.pool[sj];
+                const BaPoolEntry &pi = pool[si], &pj = pool[sj];
                 double s = 0;
-                for (int m = 0; m < Dl; ++m) s += pi.Y[r * Dl + m] * pj.W[c * Dl + m];
+                for (int q = 0; q < Dl; ++q) s += pi.Y[r * Dl + q] * pj.W[c * Dl + q];
                 acc -= s;
                 if (bi == bj) {
                     const int a = r < c ? r : c, b2 = r < c ? c : r;
@@ -481,12 +486,15 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
         }
         for (int ent = tid; ent < n6; ent += kBaThreads) {
             const int bi = ent / 6, r = ent - bi * 6;
+            unsigned m = S.kfmask[bi];
+            if (!m) continue;
             double ga = 0.0, ba = 0.0;
-            for (int lb = 0; lb < nb; ++lb) {
+            while (m) {
+                const int lb = __ffs(m) - 1;
+                m &= m - 1;
                 const int si = S.slot[lb][bi];
-                if (si < 0) continue;
-                ga += S.pool[si].gpe[r];
-                ba += S.pool[si].bpe[r];
+                ga += pool[si].gpe[r];
+                ba += pool[si].bpe[r];
             }
             gsm[ent] += ga;
             bpsm[ent] += ba;
@@ -604,9 +612,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
                         pd = false;
                         break;
                     }
-                    const double lcc = sqrt(d), inv = 1.0 / lcc;
+                    const double inv = rsqrt(d), lcc = d * inv;  // one reciprocal square root instead of sqrt + division
                     l[c][c] = lcc;
                     s_inv[c] = inv;
+                    x[K + c] = inv;  // x[] is free until the back substitution: keep 1 / l_cc for it
                     for (int r = c + 1; r < 6; ++r) {
                         double v = l[r][c];
                         for (int m = 0; m < c; ++m) v -= l[r][m] * l[c][m];
@@ -655,7 +664,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
     // rhs now holds z = L^-1 b; back substitution L^T x = z by one warp (row j of L is contiguous: lanes over i < j)
     if (tid < 32 && ok) {
         for (int j = n - 1; j >= 0; --j) {
-            const double xj = rhs[j] / L[tri(j, j)];
+            const double xj = rhs[j] * x[j];  // x[j] holds 1 / l_jj until it is overwritten by the solution
+            __syncwarp();
             if (tid == 0) x[j] = xj;
             const double *lj = &L[tri(j, 0)];
             for (int i = tid; i < j; i += 32) rhs[i] -= lj[i] * xj;
@@ -955,17 +965,25 @@ __global__ void ba_set_state_kernel(BaDev B, int max_it, int robust, int reset_c
 
 }  // namespace
 
-size_t ba_linearize_smem(int n_free, int n_pairs) {
-    return ((sizeof(BaSmem) + 15) & ~(size_t)15) + (size_t)(n_pairs * 36 + 12 * n_free) * 8 + 64;
+size_t ba_linearize_smem(int n_free, int n_pairs, int pool_cap) {
+    return ((sizeof(BaSmem) + 15) & ~(size_t)15) + (size_t)pool_cap * sizeof(BaPoolEntry) +
+           (size_t)(n_pairs * 36 + 12 * n_free) * 8 + 64;
+}
+// pool entries per batch: enough for kBaWarps landmarks of the maximum free degree if the 227 KB of shared memory allow
+int ba_pool_capacity(int n_free, int n_pairs, int max_free_degree) {
+    const size_t budget = 227 * 1024;
+    const size_t fixed = ba_linearize_smem(n_free, n_pairs, 0);
+    const int fit = fixed < budget ? (int)((budget - fixed) / sizeof(BaPoolEntry)) : 0;
+    return std::max(max_free_degree, std::min(std::min(kBaWarps * max_free_degree, kPoolMax), fit));
 }
 size_t ba_solve_smem(int n_free) {
     const size_t n = 6 * (size_t)n_free;
     return (n * (n + 1) / 2 + 2 * n) * 8 + 64;
 }
 
-plp_status ba_prepare_kernels(int n_free, int n_pairs) {
+plp_status ba_prepare_kernels(int n_free, int n_pairs, int pool_cap) {
     PLP_CUDA_TRY(cudaFuncSetAttribute(ba_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)ba_linearize_smem(n_free, n_pairs)));
+                                      (int)ba_linearize_smem(n_free, n_pairs, pool_cap)));
     PLP_CUDA_TRY(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_solve_smem(n_free)));
     return PLP_OK;
 }
@@ -973,7 +991,7 @@ plp_status ba_prepare_kernels(int n_free, int n_pairs) {
 // one LM try on the context stream; `between` (may be null) is called where the multi-GPU path all-reduces
 plp_status ba_launch_try(plp_ctx *ctx, const BaDev &B, BaCollective *coll) {
     PLP_LAUNCH(ctx, ba_decide_kernel, 1, 256, 0, B);
-    PLP_LAUNCH(ctx, ba_linearize_kernel, B.num_ctas, kBaThreads, ba_linearize_smem(B.n_free, B.n_pairs), B);
+    PLP_LAUNCH(ctx, ba_linearize_kernel, B.num_ctas, kBaThreads, ba_linearize_smem(B.n_free, B.n_pairs, B.pool_cap), B);
     PLP_LAUNCH(ctx, ba_reduce_kernel, div_up(B.packed_sum_len + 1, 256), 256, 0, B);
     if (coll) PLP_TRY(coll->all_reduce(B.packed, B.packed_sum_len + B.world));
     PLP_LAUNCH(ctx, ba_solve_kernel, 1, kSolveThreads, ba_solve_smem(B.n_free), B);

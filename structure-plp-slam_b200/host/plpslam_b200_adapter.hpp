@@ -317,6 +317,66 @@ inline unsigned match_for_triangulation(PLPSLAM::data::keyframe *kf1, PLPSLAM::d
     return num;
 }
 
+// ---- match::robust::brute_force_match + match_frame_and_keyframe (match/robust.cc:218-385) -------------------------
+inline unsigned brute_force_match(PLPSLAM::data::frame &frm, PLPSLAM::data::keyframe *keyfrm, float lowe_ratio,
+                                  bool check_orientation, std::vector<std::pair<int, int>> &matches) {
+    const auto keyfrm_lms = keyfrm->get_landmarks();
+    const int n_frm = frm.num_keypts_, n_kf = (int)keyfrm->num_keypts_;
+    std::vector<float> a_frm(n_frm), a_kf(n_kf);
+    std::vector<uint8_t> kf_valid(n_kf);
+    for (int i = 0; i < n_frm; ++i) a_frm[i] = frm.keypts_[i].angle;
+    for (int j = 0; j < n_kf; ++j) {
+        a_kf[j] = keyfrm->keypts_[j].angle;
+        kf_valid[j] = keyfrm_lms[j] && !keyfrm_lms[j]->will_be_erased();  // robust.cc:283-291
+    }
+    std::vector<int32_t> matched(n_frm);
+    uint32_t num = 0;
+    check(plp_match_brute_force(thread_ctx(), frm.descriptors_.data, a_frm.data(), n_frm, keyfrm->descriptors_.data,
+                                a_kf.data(), kf_valid.data(), n_kf, lowe_ratio, check_orientation, matched.data(), &num));
+    matches.clear();
+    for (int i = 0; i < n_frm; ++i)  // robust.cc:372-382: pairs (idx_1 in frame, idx_2 in keyframe), ascending idx_1
+        if (matched[i] >= 0) matches.emplace_back(i, matched[i]);
+    return num;
+}
+
+// robust::match_frame_and_keyframe (:218-255): brute force, then the eight-point RANSAC keeps the inliers.  The sample
+// sets are drawn here with the reference's own util::create_random_array, so the random stream is the reference's.
+inline unsigned robust_match_frame_and_keyframe(PLPSLAM::data::frame &frm, PLPSLAM::data::keyframe *keyfrm, float lowe_ratio,
+                                                bool check_orientation,
+                                                std::vector<PLPSLAM::data::landmark *> &matched_lms_in_frm) {
+    const auto keyfrm_lms = keyfrm->get_landmarks();
+    matched_lms_in_frm.assign(frm.num_keypts_, nullptr);
+    std::vector<std::pair<int, int>> matches;
+    brute_force_match(frm, keyfrm, lowe_ratio, check_orientation, matches);
+    const int M = (int)matches.size();
+    if (M < 8) return 0;  // essential_solver.cc:45-49 -> solution invalid -> robust.cc:233-236
+    constexpr int num_iter = 50;
+    std::vector<int32_t> samples((size_t)num_iter * 8), m12((size_t)M * 2);
+    for (int it = 0; it < num_iter; ++it) {
+        const auto idx = PLPSLAM::util::create_random_array(8, 0U, (unsigned)(M - 1));
+        for (int k = 0; k < 8; ++k) samples[(size_t)it * 8 + k] = (int32_t)idx[k];
+    }
+    for (int i = 0; i < M; ++i) m12[2 * i] = matches[i].first, m12[2 * i + 1] = matches[i].second;
+    std::vector<double> b1((size_t)frm.num_keypts_ * 3), b2((size_t)keyfrm->num_keypts_ * 3);
+    for (unsigned i = 0; i < frm.num_keypts_; ++i)
+        for (int k = 0; k < 3; ++k) b1[3 * i + k] = frm.bearings_[i](k);
+    for (unsigned i = 0; i < keyfrm->num_keypts_; ++i)
+        for (int k = 0; k < 3; ++k) b2[3 * i + k] = keyfrm->bearings_[i](k);
+    std::vector<uint8_t> inlier(M);
+    double E[9], score = 0;
+    int32_t valid = 0;
+    check(plp_essential_ransac(thread_ctx(), b1.data(), (int)frm.num_keypts_, b2.data(), (int)keyfrm->num_keypts_, m12.data(),
+                               M, samples.data(), num_iter, /*recompute=*/0, inlier.data(), E, &score, &valid));
+    if (!valid) return 0;
+    unsigned num_inlier_matches = 0;
+    for (int i = 0; i < M; ++i) {  // :240-252
+        if (!inlier[i]) continue;
+        matched_lms_in_frm[matches[i].first] = keyfrm_lms[matches[i].second];
+        ++num_inlier_matches;
+    }
+    return num_inlier_matches;
+}
+
 // ---- match::fuse::replace_duplication (match/fuse.cc:153-300) over the loop of mapping_module.cc:711-714 / :749 ---
 // One batched search for (targets x landmarks); the effects are applied in the reference's order.  landmark::replace
 // recomputes the surviving landmark's descriptor (data/landmark.cc:429), so a landmark whose descriptor changed is
