@@ -62,6 +62,22 @@ __device__ __forceinline__ void block_reduce(PoShared &S, double *v /*kRed per t
     __syncthreads();
 }
 
+// block sum of one value into S.sum[27] with exactly the summation tree of block_reduce (shuffle tree, then warps in order)
+__device__ __forceinline__ void block_reduce_chi(PoShared &S, double a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) S.red[warp][27] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+#pragma unroll
+        for (int w = 0; w < kPoWarps; ++w) t += S.red[w][27];
+        S.sum[27] = t;
+    }
+    __syncthreads();
+}
+
 // 6x6 SPD solve (Cholesky); H given as upper triangle packed row-wise (21 values); returns false if not SPD
 __device__ bool solve6(const double *Hu, double lambda, const double *b, double *x) {
     double A[36];
@@ -129,7 +145,7 @@ __device__ __forceinline__ EdgeEval eval_line(const se3::Cam &cam, const se3::Po
 }
 
 __global__ void __launch_bounds__(kPoThreads, 1)
-    pose_opt_kernel(const PoseJob *__restrict__ jobs, plp_camera pcam, plp_pose_opt_cfg cfg) {
+    pose_opt_kernel(const PoseJob *__restrict__ jobs, plp_camera pcam, plp_pose_opt_cfg cfg, int stage_cap) {
     extern __shared__ __align__(16) uint8_t po_smem[];
     PoShared &S = *reinterpret_cast<PoShared *>(po_smem);
     const PoseJob J = jobs[blockIdx.x];
@@ -137,6 +153,24 @@ __global__ void __launch_bounds__(kPoThreads, 1)
     double *chi2_last = reinterpret_cast<double *>(po_smem + ((sizeof(PoShared) + 15) & ~(size_t)15));
     uint8_t *level = reinterpret_cast<uint8_t *>(chi2_last + n_edges);  // 1 = outlier (g2o level 1)
     const int tid = threadIdx.x;
+    // The observations are read twice per LM iteration (system build + trial evaluation), ~80 times per call: stage
+    // them in shared memory once when they fit (they do at the config sizes), else read them through L2.
+    const plp_pt_obs *pts = J.pts;
+    const plp_line_obs *lines = J.lines;
+    {
+        uint8_t *stage = po_smem + ((((sizeof(PoShared) + 15) & ~(size_t)15) + (size_t)n_edges * 9 + 15) & ~(size_t)15);
+        const size_t pt_bytes = (size_t)n_pts * sizeof(plp_pt_obs), ln_bytes = (size_t)n_lines * sizeof(plp_line_obs);
+        if (pt_bytes + ln_bytes <= (size_t)stage_cap) {
+            static_assert(sizeof(plp_pt_obs) % 8 == 0 && sizeof(plp_line_obs) % 8 == 0, "observation PODs are 8-byte multiples");
+            double *dst = reinterpret_cast<double *>(stage);
+            const double *src_p = reinterpret_cast<const double *>(J.pts), *src_l = reinterpret_cast<const double *>(J.lines);
+            const int wp = (int)(pt_bytes / 8), wl = (int)(ln_bytes / 8);
+            for (int i = tid; i < wp; i += kPoThreads) dst[i] = src_p[i];
+            for (int i = tid; i < wl; i += kPoThreads) dst[wp + i] = src_l[i];
+            pts = reinterpret_cast<const plp_pt_obs *>(stage);
+            lines = reinterpret_cast<const plp_line_obs *>(stage + pt_bytes);
+        }
+    }
     const se3::Cam cam{pcam.fx, pcam.fy, pcam.cx, pcam.cy, pcam.focal_x_baseline};
     // pose_optimizer.cc:120-123: chi-square thresholds (float literals promoted to double)
     const double chi_sq_2D = (double)5.99146f, chi_sq_3D = (double)7.81473f;
@@ -184,14 +218,14 @@ __global__ void __launch_bounds__(kPoThreads, 1)
                 EdgeEval ev;
                 double w, delta;
                 if (i < n_pts) {
-                    const plp_pt_obs o = J.pts[i];
+                    const plp_pt_obs o = pts[i];
                     double pc[3];
                     ev = eval_point(cam, S.est, o, pc);
                     se3::point_jac_pose(cam, pc, ev.dim == 3, Jm);
                     w = (double)o.inv_sigma_sq;
                     delta = delta_pt;
                 } else {
-                    const plp_line_obs o = J.lines[i - n_pts];
+                    const plp_line_obs o = lines[i - n_pts];
                     ev = eval_line(cam, S.est, o);
                     const double scalar = 1.0 / (2 * 1e-9);
 #pragma unroll
@@ -255,10 +289,10 @@ __global__ void __launch_bounds__(kPoThreads, 1)
                     double delta;
                     if (i < n_pts) {
                         double pc[3];
-                        ev = eval_point(cam, S.trial, J.pts[i], pc);
+                        ev = eval_point(cam, S.trial, pts[i], pc);
                         delta = delta_pt;
                     } else {
-                        ev = eval_line(cam, S.trial, J.lines[i - n_pts]);
+                        ev = eval_line(cam, S.trial, lines[i - n_pts]);
                         delta = delta_line;
                     }
                     chi2_last[i] = ev.chi2;  // stays even if the step is rejected (g2o pop() does not recompute)
@@ -266,11 +300,7 @@ __global__ void __launch_bounds__(kPoThreads, 1)
                     if (robust) se3::huber(ev.chi2, delta, rho0, rho1);
                     chi += rho0;
                 }
-                double acc2[kRed];
-#pragma unroll
-                for (int k = 0; k < kRed; ++k) acc2[k] = 0;
-                acc2[27] = chi;
-                block_reduce(S, acc2);
+                block_reduce_chi(S, chi);
                 if (tid == 0) {
                     double temp_chi = S.sum[27];
                     if (!S.ok2) temp_chi = 1.7976931348623157e308;
@@ -309,7 +339,7 @@ __global__ void __launch_bounds__(kPoThreads, 1)
         // ---------------- re-classification (pose_optimizer.cc:171-216)
         int bad = 0;
         for (int i = tid; i < n_pts; i += kPoThreads) {
-            const plp_pt_obs o = J.pts[i];
+            const plp_pt_obs o = pts[i];
             double chi2 = chi2_last[i];
             if (level[i]) {  // outlier edges are recomputed at the current estimate
                 double pc[3];
@@ -343,7 +373,7 @@ __global__ void __launch_bounds__(kPoThreads, 1)
             const int e = n_pts + i;
             double chi2 = chi2_last[e];
             if (level[e]) {
-                chi2 = eval_line(cam, S.est, J.lines[i]).chi2;
+                chi2 = eval_line(cam, S.est, lines[i]).chi2;
                 chi2_last[e] = chi2;
             }
             const bool out = chi_sq_2D < chi2;
@@ -385,8 +415,12 @@ __global__ void build_pose_jobs_kernel(PoseJob *jobs, int batch, const double *T
 
 }  // namespace
 
+// staging area for the observations: every edge could be a line (72 B), capped so that the CTA stays within 200 KB
+static size_t pose_stage_bytes(int max_edges) {
+    return std::min((size_t)max_edges * sizeof(plp_line_obs), (size_t)144 * 1024);
+}
 size_t pose_smem_bytes(int max_edges) {
-    return ((sizeof(PoShared) + 15) & ~(size_t)15) + (size_t)max_edges * 9 + 64;
+    return ((sizeof(PoShared) + 15) & ~(size_t)15) + (size_t)max_edges * 9 + 64 + pose_stage_bytes(max_edges);
 }
 
 plp_status launch_pose_opt(plp_ctx *ctx, const PoseJob *d_jobs, int batch, int max_edges, const plp_camera &cam,
@@ -398,7 +432,8 @@ plp_status launch_pose_opt(plp_ctx *ctx, const PoseJob *d_jobs, int batch, int m
     }
     const size_t smem = pose_smem_bytes(max_edges < 64 ? 64 : max_edges);
     PLP_CUDA_TRY(cudaFuncSetAttribute(pose_opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PLP_LAUNCH(ctx, pose_opt_kernel, batch, kPoThreads, smem, d_jobs, cam, cfg);
+    PLP_LAUNCH(ctx, pose_opt_kernel, batch, kPoThreads, smem, d_jobs, cam, cfg,
+               (int)pose_stage_bytes(max_edges < 64 ? 64 : max_edges));
     PLP_CHECK_LAUNCH();
     return PLP_OK;
 }
