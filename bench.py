@@ -44,6 +44,7 @@ WORKLOAD = "ORB extract + Hamming match + pose-opt, 640x480, 8-level pyramid, 10
 PYR_PX = 950532
 ALG_BYTES = {
     "fast_cells_kernel": PYR_PX,  # every pyramid level read once for FAST (+ candidates out, negligible)
+    "fast_cells_kernel_v2": PYR_PX,
     "pyr_resize_kernel": None,    # per level, filled below
     "describe_kernel": PYR_PX + 60 * 1200,
     "quadtree_kernel": 8 * 11000 + 8 * 1200,
@@ -80,6 +81,24 @@ class ClockSampler:
         self._t = None
 
     def _run(self):
+        # NVML in-process (a sample every 10 ms, so even a 100 ms timed region yields several samples under load);
+        # nvidia-smi as the fallback (one sample per ~150 ms)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+            while not self._stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b, _ in bits])
+                self._stop.wait(0.01)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
@@ -812,7 +831,7 @@ def main():
     tf = sorted((ROOT / "profiles").glob("traffic_*.json"))
     if tf:  # dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture, scaled to this launch
         tj = json.loads(tf[-1].read_text())
-        kk = tj["kernels"].get(dom_name)
+        kk = tj["kernels"].get(dom_name) or tj["kernels"].get(dom_name.replace("_v2", ""))
         if kk:
             traffic = (kk["dram_bytes_read"] + kk["dram_bytes_write"]) / tj["frames_per_launch"] * Bs
             traffic_src = f"{tf[-1].name}: {tj['source']}; per-frame bytes x {Bs} frames"

@@ -15,6 +15,7 @@
 //                             Gaussian in smem -> 256 steered comparisons, one descriptor byte per lane
 // Compiled with -fmad=false: the f32 steering must round exactly like the oracle (no FMA).
 #include "common.cuh"
+#include <stdlib.h>
 #include "brief_pattern.inc"
 
 namespace plp {
@@ -360,6 +361,201 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(OrbDev P) {
             const int sc = score[y * kTilePitch + x];
             const int lx = x + cell.j * kCellSize, ly = y + cell.i * kCellSize;  // relative to the 19-px border
             if (pos < kCellCap) buf[pos] = (uint32_t)lx | ((uint32_t)ly << 11) | ((uint32_t)sc << 21);
+        }
+    }
+    if (tid == 0) *cnt_out = min(s_total[0], kCellCap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fast_cells_kernel_v2: same cell semantics, fewer instructions per pixel.
+//   phase A  four pixels per lane on aligned 32-bit shared-memory words; the pretest is the sign-agnostic compass
+//            condition "two ADJACENT compass pixels differ from the centre by more than t" evaluated with the native
+//            VABSDIFF4 byte SIMD -- a necessary condition for a FAST-9 corner (a 9-arc covers two adjacent compass
+//            pixels, all darker or all brighter), slightly weaker than fast_compass; phase B decides exactly;
+//   NMS      only over the corners found (they set bits in the per-(row, half) masks with atomicOr -- a bit mask is
+//            order independent, so the row-major output order is unchanged);
+//   output   one thread per mask word walks its set bits.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t compass4(const uint32_t *T32, int y, int g, uint32_t t4) {
+    constexpr int kPitchW = kTilePitch / 4;
+    const uint32_t *row = T32 + y * kPitchW;
+    const uint32_t c = row[g], up = row[g - 3 * kPitchW], dn = row[g + 3 * kPitchW];
+    const uint32_t wl = g > 0 ? row[g - 1] : 0u, wr = row[g + 1];
+    const uint32_t lf = __funnelshift_r(wl, c, 8);   // bytes x-3 .. x   of the four pixels x = 4g .. 4g+3
+    const uint32_t rt = __funnelshift_r(c, wr, 24);  // bytes x+3 .. x+6
+    const uint32_t a0 = __vcmpgtu4(__vabsdiffu4(c, dn), t4), a4 = __vcmpgtu4(__vabsdiffu4(c, rt), t4);
+    const uint32_t a8 = __vcmpgtu4(__vabsdiffu4(c, up), t4), a12 = __vcmpgtu4(__vabsdiffu4(c, lf), t4);
+    const uint32_t sv = (a4 | a12) & (a0 | a8);  // the four adjacent pairs (0,4) (4,8) (8,12) (12,0)
+    const uint32_t m = sv & 0x01010101u;
+    return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xfu;
+}
+
+__global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
+    __shared__ __align__(16) uint8_t tile[kTileRows * kTilePitch];
+    __shared__ __align__(16) uint8_t score[kTileRows * kTilePitch];
+    __shared__ int s_total[2];
+    __shared__ unsigned short s_list[4096 + 8];  // tile offsets of the pixels that survive the pretest
+    __shared__ int s_nsurv;
+    __shared__ unsigned s_rowbits[128];  // NMS survivors: one 32-bit mask per (tested row, 32-column half)
+    __shared__ int s_rowbase[128];
+    const int b = blockIdx.y, ci = blockIdx.x, tid = threadIdx.x;
+    const CellDesc cell = P.cells[ci];
+    const int l = cell.level;
+    const int w = cell.max_x - cell.min_x, h = cell.max_y - cell.min_y;
+    int *cnt_out = P.cell_cnt + (size_t)b * P.num_cells + ci;
+    uint32_t *buf = P.cell_buf + ((size_t)b * P.num_cells + ci) * kCellCap;
+    const float scale = P.lv[l].scale_factor;
+    bool skip = (w < 7 || h < 7);
+    if (!skip && P.mask) {  // orb_extractor.cc:395-401
+        skip = masked(P, cell.min_y, cell.min_x, scale) || masked(P, cell.max_y, cell.min_x, scale) ||
+               masked(P, cell.min_y, cell.max_x, scale) || masked(P, cell.max_y, cell.max_x, scale);
+    }
+    if (skip) {
+        if (tid == 0) *cnt_out = 0;
+        return;
+    }
+    const uint8_t *img = level_ptr(P, b, l);
+    const int pitch = level_pitch(P, l);
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int y = warp; y < h; y += 8) {
+        const uint8_t *src = img + (size_t)(cell.min_y + y) * pitch + cell.min_x;
+        for (int x = lane; x < w; x += 32) tile[y * kTilePitch + x] = src[x];
+    }
+    for (int idx = tid; idx < kTileRows * kTilePitch / 4; idx += 256) reinterpret_cast<uint32_t *>(score)[idx] = 0;
+    const int tw = w - 6, th = h - 6;  // tested area: rows 3 .. h-4, columns 3 .. w-4 (<= 64 x 64)
+    const int halves = tw > 32 ? 2 : 1;
+    const int x_lo = 3, x_hi = 3 + tw;
+    const uint32_t *T32 = reinterpret_cast<const uint32_t *>(tile);
+    // append the pixels of `nib` (bits = pixels 4g .. 4g+3 of row y) to the survivor list; called by whole warps
+    auto append = [&](uint32_t nib, int y, int g) {
+        const int cnt = __popc(nib);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int wbase = 0;
+        if (lane == 31 && total) wbase = atomicAdd(&s_nsurv, total);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        int pos = wbase + incl - cnt;
+        while (nib) {
+            const int bit = __ffs(nib) - 1;
+            nib &= nib - 1;
+            s_list[pos++] = (unsigned short)(y * kTilePitch + 4 * g + bit);
+        }
+    };
+    auto valid_nibble = [&](int g) -> uint32_t {
+        const int lo = max(0, x_lo - 4 * g), hi = min(4, x_hi - 4 * g);
+        return hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+        const int thr = pass == 0 ? P.ini_thr : P.min_thr;
+        const uint32_t t4 = (uint32_t)min(thr, 255) * 0x01010101u;
+        if (tid < 128) s_rowbits[tid] = 0u;
+        if (tid == 0) s_nsurv = 0;
+        if (pass == 1)  // scores of the first pass must not leak into the second (cv::FAST runs from scratch)
+            for (int idx = tid; idx < kTileRows * kTilePitch / 4; idx += 256) reinterpret_cast<uint32_t *>(score)[idx] = 0;
+        __syncthreads();
+        // phase A: a warp takes two rows, a lane four pixels (word groups 0 .. 15 = columns 0 .. 63)
+        for (int rp = warp; rp < (th + 1) / 2; rp += 8) {
+            const int ry = 2 * rp + (lane >> 4), g = lane & 15;
+            uint32_t nib = 0;
+            if (ry < th) nib = compass4(T32, 3 + ry, g, t4) & valid_nibble(g);
+            append(nib, 3 + ry, g);
+        }
+        if (x_hi > 64) {  // word group 16 (columns 64 .. 66)
+            for (int base = 0; base < th; base += 256) {
+                const int ry = base + tid;
+                uint32_t nib = 0;
+                if (ry < th) nib = compass4(T32, 3 + ry, 16, t4) & valid_nibble(16);
+                append(nib, 3 + ry, 16);
+            }
+        }
+        __syncthreads();
+        // phase B: exact arc test / score for the survivors
+        const int nsurv = s_nsurv;
+        for (int i = tid; i < nsurv; i += 256) {
+            const int off = s_list[i];
+            const int m = fast_m(tile + off, thr);
+            if (m > thr) score[off] = (uint8_t)(m - 1);
+        }
+        __syncthreads();
+        // 3x3 non-maximum suppression over the corners only
+        bool any_local = false;
+        for (int i = tid; i < nsurv; i += 256) {
+            const int off = s_list[i];
+            const uint8_t *sp = score + off;
+            const int sc = sp[0];
+            if (sc == 0) continue;
+            bool keep = true;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (dx == 0 && dy == 0) continue;
+                    keep = keep && (sc > (int)sp[dy * kTilePitch + dx]);
+                }
+            if (keep) {
+                const int y = off / kTilePitch, xx = off - y * kTilePitch - 3;
+                atomicOr(&s_rowbits[(y - 3) * 2 + (xx >> 5)], 1u << (xx & 31));
+                any_local = true;
+            }
+        }
+        const int any = __syncthreads_or(any_local);
+        if (any || P.min_thr == P.ini_thr) break;
+    }
+    const int njobs = th * halves;
+    // per-keypoint mask test (orb_extractor.cc:429): one thread per mask word
+    if (P.mask) {
+        for (int jdx = tid; jdx < njobs; jdx += 256) {
+            const int ry = jdx / halves, hx = jdx - ry * halves;
+            unsigned bits = s_rowbits[ry * 2 + hx], keepbits = bits;
+            while (bits) {
+                const int bit = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int x = 3 + hx * 32 + bit, y = 3 + ry;
+                const float kx = (float)x + (float)(cell.j * kCellSize), ky = (float)y + (float)(cell.i * kCellSize);
+                if (masked(P, (unsigned)((float)kPatchRadius + ky), (unsigned)((float)kPatchRadius + kx), scale))
+                    keepbits &= ~(1u << bit);
+            }
+            s_rowbits[ry * 2 + hx] = keepbits;
+        }
+        __syncthreads();
+    }
+    // exclusive prefix of the per-(row, half) counts (<= 128 entries) by warp 0
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < njobs; base += 32) {
+            const int jdx = base + lane;
+            const int ry = jdx / halves, hx = jdx - ry * halves;
+            const int c = jdx < njobs ? __popc(s_rowbits[ry * 2 + hx]) : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (jdx < njobs) s_rowbase[jdx] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_total[0] = run;
+    }
+    __syncthreads();
+    // ordered (row-major) output: one thread per mask word walks its bits
+    for (int jdx = tid; jdx < njobs; jdx += 256) {
+        const int ry = jdx / halves, hx = jdx - ry * halves;
+        unsigned bits = s_rowbits[ry * 2 + hx];
+        int pos = s_rowbase[jdx];
+        while (bits) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int x = 3 + hx * 32 + bit, y = 3 + ry;
+            const int sc = score[y * kTilePitch + x];
+            const int lx = x + cell.j * kCellSize, ly = y + cell.i * kCellSize;  // relative to the 19-px border
+            if (pos < kCellCap) buf[pos] = (uint32_t)lx | ((uint32_t)ly << 11) | ((uint32_t)sc << 21);
+            ++pos;
         }
     }
     if (tid == 0) *cnt_out = min(s_total[0], kCellCap);
@@ -1162,6 +1358,7 @@ struct plp_orb {
     uint8_t *d_desc = nullptr;
     int32_t *d_n = nullptr;
     size_t qt_smem = 0;
+    bool fast_v1 = false;  // PLP_FAST_V1=1 selects the first-generation FAST kernel (kept for A/B measurements)
     int last_batch = 0;
     const uint8_t *last_img0 = nullptr;
     size_t last_step = 0;
@@ -1237,6 +1434,10 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
                 "FAST thresholds: 1 <= min <= ini < 255");
     PLP_CUDA_TRY(cudaSetDevice(ctx->device));
     plp_orb *o = new plp_orb();
+    {
+        const char *v1 = getenv("PLP_FAST_V1");
+        o->fast_v1 = v1 && v1[0] == '1';
+    }
     o->ctx = ctx;
     o->params = *params;
     o->rows = rows;
@@ -1474,7 +1675,10 @@ static plp_status orb_run(plp_orb *o, const uint8_t *d_imgs, int batch, size_t s
     }
     if (D.num_cells > 0) {
         dim3 grid(D.num_cells, batch);
-        PLP_LAUNCH(ctx, fast_cells_kernel, grid, 256, 0, D);
+        if (o->fast_v1)
+            PLP_LAUNCH(ctx, fast_cells_kernel, grid, 256, 0, D);
+        else
+            PLP_LAUNCH(ctx, fast_cells_kernel_v2, grid, 256, 0, D);
     }
     if (D.num_blur_tiles > 0) {
         dim3 grid(D.num_blur_tiles, batch);
