@@ -417,14 +417,29 @@ __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
     const uint8_t *img = level_ptr(P, b, l);
     const int pitch = level_pitch(P, l);
     const int lane = tid & 31, warp = tid >> 5;
-    for (int y = warp; y < h; y += 8) {
-        const uint8_t *src = img + (size_t)(cell.min_y + y) * pitch + cell.min_x;
-        for (int x = lane; x < w; x += 32) tile[y * kTilePitch + x] = src[x];
+    // tile load.  Level pitches are 64-byte multiples and cells start at x = 19 + 64 j, so a tile row is fetched as
+    // aligned 16-byte chunks starting xo = min_x & 15 (= 3) bytes to the left of the cell; the tile keeps that offset
+    // (tile column = cell column + xo).  The chunks read [min_x - xo, min_x + w + 15) at most: left of it lie >= 16 border
+    // pixels, and max_x + 15 <= cols - 4, so no read leaves the image row.  Unaligned caller buffers take the byte path.
+    const bool vec = (((uintptr_t)img | (uintptr_t)pitch) & 15) == 0 && (cell.min_x & 15) + w <= kTilePitch;
+    const int xo = vec ? (cell.min_x & 15) : 0;
+    if (vec) {
+        const int nchunks = (xo + w + 15) >> 4;  // <= 5 (xo + w <= 73 <= kTilePitch)
+        for (int idx = tid; idx < h * nchunks; idx += 256) {
+            const int y = idx / nchunks, c = idx - y * nchunks;
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)(cell.min_y + y) * pitch + (cell.min_x - xo)) + c);
+            *reinterpret_cast<uint4 *>(tile + y * kTilePitch + 16 * c) = v;
+        }
+    } else {
+        for (int y = warp; y < h; y += 8) {
+            const uint8_t *src = img + (size_t)(cell.min_y + y) * pitch + cell.min_x;
+            for (int x = lane; x < w; x += 32) tile[y * kTilePitch + x] = src[x];
+        }
     }
     for (int idx = tid; idx < kTileRows * kTilePitch / 4; idx += 256) reinterpret_cast<uint32_t *>(score)[idx] = 0;
     const int tw = w - 6, th = h - 6;  // tested area: rows 3 .. h-4, columns 3 .. w-4 (<= 64 x 64)
     const int halves = tw > 32 ? 2 : 1;
-    const int x_lo = 3, x_hi = 3 + tw;
+    const int x_lo = 3 + xo, x_hi = 3 + xo + tw;  // tested tile columns
     const uint32_t *T32 = reinterpret_cast<const uint32_t *>(tile);
     // append the pixels of `nib` (bits = pixels 4g .. 4g+3 of row y) to the survivor list; called by whole warps
     auto append = [&](uint32_t nib, int y, int g) {
@@ -465,12 +480,12 @@ __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
             if (ry < th) nib = compass4(T32, 3 + ry, g, t4) & valid_nibble(g);
             append(nib, 3 + ry, g);
         }
-        if (x_hi > 64) {  // word group 16 (columns 64 .. 66)
+        for (int g = 16; 4 * g < x_hi; ++g) {  // word groups 16, 17 (tile columns 64 .. 71), one thread per row
             for (int base = 0; base < th; base += 256) {
                 const int ry = base + tid;
                 uint32_t nib = 0;
-                if (ry < th) nib = compass4(T32, 3 + ry, 16, t4) & valid_nibble(16);
-                append(nib, 3 + ry, 16);
+                if (ry < th) nib = compass4(T32, 3 + ry, g, t4) & valid_nibble(g);
+                append(nib, 3 + ry, g);
             }
         }
         __syncthreads();
@@ -498,7 +513,7 @@ __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
                     keep = keep && (sc > (int)sp[dy * kTilePitch + dx]);
                 }
             if (keep) {
-                const int y = off / kTilePitch, xx = off - y * kTilePitch - 3;
+                const int y = off / kTilePitch, xx = off - y * kTilePitch - 3 - xo;
                 atomicOr(&s_rowbits[(y - 3) * 2 + (xx >> 5)], 1u << (xx & 31));
                 any_local = true;
             }
@@ -552,7 +567,7 @@ __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
             const int bit = __ffs(bits) - 1;
             bits &= bits - 1;
             const int x = 3 + hx * 32 + bit, y = 3 + ry;
-            const int sc = score[y * kTilePitch + x];
+            const int sc = score[y * kTilePitch + x + xo];
             const int lx = x + cell.j * kCellSize, ly = y + cell.i * kCellSize;  // relative to the 19-px border
             if (pos < kCellCap) buf[pos] = (uint32_t)lx | ((uint32_t)ly << 11) | ((uint32_t)sc << 21);
             ++pos;

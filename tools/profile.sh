@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 71 -c 40 --csv \
     python bench.py --steps 2 --warmup 3 --batch ${BATCH} --no-cpu-baseline --no-ba --no-lines --no-stereo > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 # (2) full capture of the hot kernels of one step (one launch each)
 ncu --set full --clock-control none --import-source on \
-    -k regex:"fast_cells_kernel|blur_tiles_kernel|quadtree_kernel|describe_kernel|point_match_kernel|pose_opt_kernel|pyr_resize_kernel" \
+    -k regex:"fast_cells_kernel_v2|blur_tiles_kernel|quadtree_kernel|describe_kernel|point_match_kernel|pose_opt_kernel|pyr_resize_kernel" \
     -s 53 -c 14 -o gpurun_out/prof_${TAG} -f \
     python bench.py --steps 2 --warmup 3 --batch ${BATCH} --no-cpu-baseline --no-ba --no-lines --no-stereo > gpurun_out/bench_under_ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out/
