@@ -46,8 +46,14 @@ ALG_BYTES = {
     "fast_cells_kernel": PYR_PX,  # every pyramid level read once for FAST (+ candidates out, negligible)
     "fast_cells_kernel_v2": PYR_PX,
     "pyr_resize_kernel": None,    # per level, filled below
+    "blur_tiles_kernel": 2 * PYR_PX,          # pyramid read + blurred pyramid written
     "describe_kernel": PYR_PX + 60 * 1200,
     "quadtree_kernel": 8 * 11000 + 8 * 1200,
+    # match (per frame) = (M + N) x 48 B: 32 B descriptor + 16 B geometry on each side, N ~ 1200 keypoints, M ~ 1000 queries
+    "point_match_kernel": 48 * (1200 + 1000),
+    # pose-opt = 41 B per point edge and LM iteration (24 B position + 12 B observation + 4 B weight + 1 B flag), <= 40
+    # iterations + 4 re-classification passes per call; ~1000 edges per frame
+    "pose_opt_kernel": 41 * 1000 * 44,
 }
 
 
@@ -822,11 +828,15 @@ def main():
     peak, peak_src = _peaks()
     dom_name = dom[0]
     per_launch_ms = dom[1]["total_ms"] / dom[1]["count"]
+    launches_per_step = dom[1]["count"] / max(args.steps, 1)
     alg = ALG_BYTES.get(dom_name)
     if alg is None:
         alg = PYR_PX
+    # algorithmic bytes of ONE step of this kernel (all of its launches in a step together process the sub-batch once:
+    # the matcher's second launch only revisits the few frames that need the wider margin) over its time per step
     alg_bytes_launch = alg * Bs
-    achieved = alg_bytes_launch / (per_launch_ms * 1e-3) / 1e9
+    per_step_ms = dom[1]["total_ms"] / max(args.steps, 1)
+    achieved = alg_bytes_launch / (per_step_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tf = sorted((ROOT / "profiles").glob("traffic_*.json"))
     if tf:  # dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture, scaled to this launch
@@ -838,6 +848,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": per_launch_ms,
+                "launches_per_step": launches_per_step, "ms_per_step_of_this_kernel": per_step_ms,
                 "kernel_time_shares": shares,
                 "frames_per_launch": Bs,
                 "how": "CUDA events around every launch on the launching stream over a repeat of the timed steps "
