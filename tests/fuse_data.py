@@ -247,3 +247,188 @@ def fuse_batched(model, lm_ids, kf_order, search_batch):
             model.apply(kf, lm, b)
             num_fused += 1
     return num_fused, researches
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# independent pure-Python restatement of the fuse search (pins the C++ oracle with a second implementation)
+# ------------------------------------------------------------------------------------------------------------------
+def _logf(x):
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.logf.restype = ctypes.c_float
+    libm.logf.argtypes = [ctypes.c_float]
+    return np.float32(libm.logf(float(x)))
+
+
+def _cv_floor(v):
+    i = int(v)
+    return i - (i > v)
+
+
+def _cv_ceil(v):
+    i = int(v)
+    return i + (i < v)
+
+
+def fuse_search_points_python(grid, cam, scale_factors, inv_level_sigma_sq, log_scale_factor, tgt, lms, margin, mode):
+    """match/fuse.cc:40-151 (mode 0) / :153-300 (mode 1), written from the reference text with numpy scalars carrying the
+    reference's types (double reprojection, float window, unsigned / int level gates, float-double chi-square mix)."""
+    f32, f64 = np.float32, np.float64
+    x, y, octv = tgt["x"].astype(f32), tgt["y"].astype(f32), tgt["octave"]
+    xr_all = tgt.get("x_right")
+    n, m = len(x), len(lms["min_valid_dist"])
+    # assign_keypoints_to_grid (data/common.cc:205-231)
+    cells = {}
+    for i in range(n):
+        cx = _cv_floor(f64(f32(x[i] - f32(grid.min_x))) * grid.inv_cell_width)
+        cy = _cv_floor(f64(f32(y[i] - f32(grid.min_y))) * grid.inv_cell_height)
+        if 0 <= cx < grid.num_cols and 0 <= cy < grid.num_rows:
+            cells.setdefault((cx, cy), []).append(i)
+    R = np.asarray(tgt["rot_cw"], f64).reshape(3, 3)
+    t = np.asarray(tgt["trans_cw"], f64).reshape(3)
+    c = np.asarray(tgt["cam_center"], f64).reshape(3)
+    bits_k = np.unpackbits(tgt["desc"], axis=1)
+    bits_l = np.unpackbits(lms["desc"], axis=1)
+    best_out = np.full(m, -1, np.int32)
+    dist_out = np.full(m, 0xFFFF, np.uint16)
+    num_levels = len(scale_factors)
+    for i in range(m):
+        if lms.get("valid") is not None and not lms["valid"][i]:
+            continue
+        if tgt.get("skip") is not None and tgt["skip"][i]:
+            continue
+        X = np.asarray(lms["pos_w"][i], f64)
+        pc = [R[r, 0] * X[0] + R[r, 1] * X[1] + R[r, 2] * X[2] + t[r] for r in range(3)]
+        if pc[2] <= 0.0:
+            continue
+        z_inv = f64(1.0) / pc[2]
+        u = cam.fx * pc[0] * z_inv + cam.cx
+        v = cam.fy * pc[1] * z_inv + cam.cy
+        q_xr = f32(u - cam.focal_x_baseline * z_inv)
+        if not (cam.min_x < u < cam.max_x and cam.min_y < v < cam.max_y):
+            continue
+        d = X - c
+        dist = np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+        if dist < f64(lms["min_valid_dist"][i]) or f64(lms["max_valid_dist"][i]) < dist:
+            continue
+        nm = np.asarray(lms["obs_mean_normal"][i], f64)
+        if d[0] * nm[0] + d[1] * nm[1] + d[2] * nm[2] < 0.5 * dist:
+            continue
+        ratio = f32(f32(lms["max_valid_dist_raw"][i]) / f32(dist))
+        pred = int(np.ceil(f32(_logf(ratio) / f32(log_scale_factor))))
+        pred = 0 if pred < 0 else (num_levels - 1 if pred >= num_levels else pred)
+        ref_x, ref_y, r = f32(u), f32(v), f32(f32(margin) * f32(scale_factors[pred]))
+        min_cx = max(0, _cv_floor(f64(f32(f32(ref_x - f32(grid.min_x)) - r)) * grid.inv_cell_width))
+        max_cx = min(grid.num_cols - 1, _cv_ceil(f64(f32(f32(ref_x - f32(grid.min_x)) + r)) * grid.inv_cell_width))
+        min_cy = max(0, _cv_floor(f64(f32(f32(ref_y - f32(grid.min_y)) - r)) * grid.inv_cell_height))
+        max_cy = min(grid.num_rows - 1, _cv_ceil(f64(f32(f32(ref_y - f32(grid.min_y)) + r)) * grid.inv_cell_height))
+        if grid.num_cols <= min_cx or max_cx < 0 or grid.num_rows <= min_cy or max_cy < 0:
+            continue
+        best_d, best_i = 256, -1
+        for cx in range(min_cx, max_cx + 1):
+            for cy in range(min_cy, max_cy + 1):
+                for k in cells.get((cx, cy), []):
+                    if not (abs(f32(x[k] - ref_x)) < r and abs(f32(y[k] - ref_y)) < r):
+                        continue
+                    lvl = int(octv[k])
+                    if mode == 0:
+                        if lvl < pred - 1 or pred < lvl:
+                            continue
+                    else:
+                        if pred == 0:          # unsigned pred - 1 wraps: every candidate is rejected
+                            continue
+                        if lvl < pred - 1 or pred < lvl:
+                            continue
+                        e_x, e_y = u - f64(x[k]), v - f64(y[k])
+                        kxr = f32(xr_all[k]) if xr_all is not None else f32(-1)
+                        if kxr >= 0:
+                            e_r = f32(q_xr - kxr)
+                            err = e_x * e_x + e_y * e_y + f64(f32(e_r * e_r))
+                            if f64(f32(7.81473)) < err * f64(f32(inv_level_sigma_sq[lvl])):
+                                continue
+                        else:
+                            err = e_x * e_x + e_y * e_y
+                            if f64(f32(5.99146)) < err * f64(f32(inv_level_sigma_sq[lvl])):
+                                continue
+                    hd = int((bits_l[i] != bits_k[k]).sum())
+                    if hd < best_d:
+                        best_d, best_i = hd, k
+        if 50 < best_d:
+            continue
+        best_out[i], dist_out[i] = best_i, best_d
+    return best_out, dist_out
+
+
+def fuse_search_lines_python(cam, scale_factors_lsd, inv_level_sigma_sq_lsd, log_scale_factor_lsd, tgt, lms, margin):
+    """match/fuse.cc:304-503 written from the reference text (second implementation beside the C++ oracle)."""
+    f32, f64 = np.float32, np.float64
+    sx, sy, ex, ey = (tgt[k].astype(f32) for k in ("sx", "sy", "ex", "ey"))
+    octv = tgt["octave"]
+    n, m = len(sx), len(lms["min_valid_dist"])
+    R = np.asarray(tgt["rot_cw"], f64).reshape(3, 3)
+    t = np.asarray(tgt["trans_cw"], f64).reshape(3)
+    c = np.asarray(tgt["cam_center"], f64).reshape(3)
+    bits_k = np.unpackbits(tgt["desc"], axis=1)
+    bits_l = np.unpackbits(lms["desc"], axis=1)
+    num_levels = len(scale_factors_lsd)
+    best_out = np.full(m, -1, np.int32)
+    dist_out = np.full(m, 0xFFFF, np.uint16)
+
+    def reproject(X):
+        pc = [R[r, 0] * X[0] + R[r, 1] * X[1] + R[r, 2] * X[2] + t[r] for r in range(3)]
+        if pc[2] <= 0.0:
+            return False, f64(0.0), f64(0.0)       # the reference leaves the reprojection unset; oracle rule: (0, 0)
+        z_inv = f64(1.0) / pc[2]
+        u = cam.fx * pc[0] * z_inv + cam.cx
+        v = cam.fy * pc[1] * z_inv + cam.cy
+        return bool(cam.min_x < u < cam.max_x and cam.min_y < v < cam.max_y), u, v
+
+    def norm3(d):
+        return np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+    for i in range(m):
+        if lms.get("valid") is not None and not lms["valid"][i]:
+            continue
+        if tgt.get("skip") is not None and tgt["skip"][i]:
+            continue
+        P = np.asarray(lms["pos_w"][i], f64).reshape(6)
+        S, E = P[:3], P[3:]
+        in_s, su, sv = reproject(S)
+        in_e, eu, ev = reproject(E)
+        if not in_s and not in_e:
+            continue
+        M = np.array([0.5 * (S[k] + E[k]) for k in range(3)], f64)
+        if not in_s or not in_e:
+            if not reproject(M)[0]:
+                continue
+        ds, de = norm3(S - c), norm3(E - c)
+        mn, mx = f64(lms["min_valid_dist"][i]), f64(lms["max_valid_dist"][i])
+        if ds < mn or mx < ds or de < mn or mx < de:
+            continue
+        dm = norm3(M - c)
+        ratio = f32(f32(lms["max_valid_dist_raw"][i]) / f32(dm))
+        pred = int(np.ceil(f32(_logf(ratio) / f32(log_scale_factor_lsd))))
+        pred = 0 if pred < 0 else (num_levels - 1 if pred >= num_levels else pred)
+        r = f32(f32(margin) * f32(scale_factors_lsd[pred]))
+        # get_keylines_in_cell: the line through the FLOAT reprojections (data/common.cc:324-327)
+        ax, ay, bx, by = (f64(f32(w)) for w in (su, sv, eu, ev))
+        f0, f1, f2 = ay * 1.0 - 1.0 * by, 1.0 * bx - ax * 1.0, ax * by - ay * bx
+        l0, l1, l2 = sv * 1.0 - 1.0 * ev, 1.0 * eu - su * 1.0, su * ev - sv * eu
+        best_d, best_i = 256, -1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            fden, lden = np.sqrt(f0 * f0 + f1 * f1), np.sqrt(l0 * l0 + l1 * l1)
+            for k in range(n):
+                dsp = f32((f64(sx[k]) * f0 + f64(sy[k]) * f1 + f2) / fden)
+                dep = f32((f64(ex[k]) * f0 + f64(ey[k]) * f1 + f2) / fden)
+                if abs(dsp) > r or abs(dep) > r:
+                    continue
+                e_sp = (f64(sx[k]) * l0 + f64(sy[k]) * l1 + l2) / lden
+                e_ep = (f64(ex[k]) * l0 + f64(ey[k]) * l1 + l2) / lden
+                if f64(f32(5.99146)) < (e_sp * e_sp + e_ep * e_ep) * f64(f32(inv_level_sigma_sq_lsd[int(octv[k])])):
+                    continue
+                hd = int((bits_l[i] != bits_k[k]).sum())
+                if hd < best_d:
+                    best_d, best_i = hd, k
+        if 50 < best_d:
+            continue
+        best_out[i], dist_out[i] = best_i, best_d
+    return best_out, dist_out

@@ -158,3 +158,41 @@ def test_adapter_protocol_equals_sequential_reference(plp, orc, seed):
     assert np.array_equal(sa[2], sb_[2]) and np.array_equal(sa[3], sb_[3])
     assert a.erased.sum() > 5          # replace() fired
     assert js_of and researches >= 0
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_fuse_points_oracle_matches_python_restatement(plp, orc, seed):
+    """The C++ oracle against a second, independent restatement of fuse.cc (pure Python, libm logf via ctypes)."""
+    stereo = bool(seed & 1)
+    lms, targets = fuse_data.make_point_fuse_scene(seed + 50, m=260, num_targets=2, n_extra=60, stereo=stereo)
+    grid = plp.capi.make_grid(synth.COLS, synth.ROWS)
+    cam = _cam(plp, stereo)
+    sf, isg = synth.scale_factors(), fuse_data.inv_level_sigma_sq()
+    matched = 0
+    for tgt in targets:
+        for margin, mode in [(3.0, 1), (4.0, 0), (8.0, 1)]:
+            o_idx, o_dist, _ = orc.fuse_search_points(grid, cam, sf, isg, fuse_data.LOG_SF, tgt, lms, margin, mode)
+            p_idx, p_dist = fuse_data.fuse_search_points_python(grid, cam, sf, isg, fuse_data.LOG_SF, tgt, lms, margin, mode)
+            assert np.array_equal(o_idx, p_idx)
+            assert np.array_equal(o_dist, p_dist)
+            matched += (o_idx >= 0).sum()
+    assert matched > 60
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_fuse_lines_oracle_matches_python_restatement(plp, orc, seed):
+    levels = 1 + 2 * (seed & 1)
+    lms, targets = fuse_data.make_line_fuse_scene(seed + 30, m=160, num_targets=2, n_extra=30, num_levels=levels)
+    cam = _cam(plp)
+    sf = np.float32([1.0, 2.0, 4.0])[:levels]
+    isg = (1.0 / (sf * sf)).astype(np.float32)
+    lsf = float(np.log(np.float32(2.0)).astype(np.float32))
+    matched = 0
+    for tgt in targets:
+        for margin in (10.0, 4.0):
+            o_idx, o_dist, _ = orc.fuse_search_lines(cam, sf, isg, lsf, tgt, lms, margin)
+            p_idx, p_dist = fuse_data.fuse_search_lines_python(cam, sf, isg, lsf, tgt, lms, margin)
+            assert np.array_equal(o_idx, p_idx)
+            assert np.array_equal(o_dist, p_dist)
+            matched += (o_idx >= 0).sum()
+    assert matched > 20
