@@ -497,6 +497,33 @@ PLP_API plp_status plp_essential_ransac(plp_ctx *ctx, const double *bearings_1, 
                                         double *best_score_out, int32_t *solution_is_valid_out);
 
 /* ------------------------------------------------------------------------ */
+/* plane RANSAC  (planar_mapping_module.{h,cc})                              */
+/* ------------------------------------------------------------------------ */
+/* Planar_Mapping_module::estimate_plane_sequential_RANSAC (planar_mapping_module.cc:412-591, mode 0) and
+ * update_plane_via_RANSAC (:593-733, mode 1) with estimate_plane_SVD (:735-771): the landmarks linked to one plane
+ * instance, `num_iter` hypotheses.  The random index draws are an input (num_iter x sample_size indices, drawn by the
+ * adapter exactly like :447-457 / :620-632; the reference seeds its mt19937 from std::random_device).  Every hypothesis
+ * (sample fit, inlier test of all landmarks, refit on the inliers) is evaluated by its own CTA; the reference's
+ * sequential bookkeeping -- best_error also drops to a SAMPLE residual (:461-464), the Plane object takes the sample fit
+ * of every iteration (:465-467), early exit of mode 0 (:526-534) -- is replayed over the results in iteration order, and
+ * step [4] filters the best inlier list with the equation the Plane holds at the end.
+ * valid[j] = !lms[j]->will_be_erased() (NULL == all).  eq_inout / plane_error_inout: the Plane's equation and
+ * best_error_ before and after the call (they are mutated every iteration, also when the call fails).
+ * inlier_out[j] = 1 for the landmarks the plane keeps.  *status_out: 1 = true, 0 = false, 2 = false + set_invalid().
+ * Eigen::JacobiSVD is restated with cyclic Jacobi rotations on the 3 x 3 scatter matrix (csrc/planemath.h); the sign of
+ * the plane normal is arbitrary in both. */
+typedef struct plp_plane_ransac_cfg {
+    int32_t mode;              /* 0 estimate_plane_sequential_RANSAC, 1 update_plane_via_RANSAC */
+    int32_t points_per_ransac; /* POINTS_PER_RANSAC */
+    double planar_distance_thresh, final_error_thresh, inliers_ratio_thr;
+    double initial_best_error; /* mode 1: plane->get_best_error() (:609) */
+} plp_plane_ransac_cfg;
+PLP_API plp_status plp_plane_ransac(plp_ctx *ctx, const double *pos_w, const uint8_t *valid, int n,
+                                    const int32_t *samples, int num_iter, int sample_size,
+                                    const plp_plane_ransac_cfg *cfg, double *eq_inout /*4*/, double *plane_error_inout,
+                                    uint8_t *inlier_out, int32_t *status_out);
+
+/* ------------------------------------------------------------------------ */
 /* stereo matching  (match/stereo.{h,cc})                                    */
 /* ------------------------------------------------------------------------ */
 /* match::stereo::compute(stereo_x_right, depths) (match/stereo.cc:45-150): per left keypoint the Hamming-closest right

@@ -31,6 +31,7 @@
 #include "stereo.h"
 #include "bow.h"
 #include "essential.h"
+#include "plane.h"
 
 #ifdef __cplusplus
 extern "C" {

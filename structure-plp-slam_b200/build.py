@@ -34,6 +34,7 @@ FILE_FLAGS = {
     "fuse.cu": NO_FMA,
     "bow.cu": NO_FMA,
     "essential.cu": NO_FMA,
+    "plane.cu": NO_FMA,
 }
 
 

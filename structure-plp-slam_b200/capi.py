@@ -135,6 +135,11 @@ class BowPair(C.Structure):
                 ("matched_1_of_2_out", _P), ("num_matches", C.c_uint32)]
 
 
+class PlaneRansacCfg(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("points_per_ransac", C.c_int32), ("planar_distance_thresh", C.c_double),
+                ("final_error_thresh", C.c_double), ("inliers_ratio_thr", C.c_double), ("initial_best_error", C.c_double)]
+
+
 class OrbParams(C.Structure):
     _fields_ = [("max_num_keypts", C.c_uint32), ("scale_factor", C.c_float), ("num_levels", C.c_uint32),
                 ("ini_fast_thr", C.c_uint32), ("min_fast_thr", C.c_uint32)]
@@ -440,6 +445,26 @@ class Context:
             m.ctypes.data_as(_P), C.c_int(len(m)), sm.ctypes.data_as(_P), C.c_int(len(sm)), C.c_int(1 if recompute else 0),
             inl.ctypes.data_as(_P), E.ctypes.data_as(_P), C.byref(score), C.byref(valid)))
         return int(valid.value), inl[:len(m)].copy(), E.reshape(3, 3), float(score.value)
+
+    # ------------------------------------------------------------------ Planar_Mapping_module
+    def plane_ransac(self, pos_w, valid, samples, cfg, eq0=(0, 0, 0, 0), err0=0.0):
+        """estimate_plane_sequential_RANSAC (cfg['mode'] = 0) / update_plane_via_RANSAC (1) with caller-drawn index samples
+        (num_iter x sample_size).  Returns (status, eq, plane_error, inlier flags)."""
+        P = np.ascontiguousarray(pos_w, np.float64).reshape(-1, 3)
+        sm = np.ascontiguousarray(samples, np.int32)
+        sm = sm.reshape(len(sm), -1) if sm.size else sm.reshape(0, 1)
+        v = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+        c = PlaneRansacCfg(cfg["mode"], cfg["points_per_ransac"], cfg["planar_distance_thresh"], cfg["final_error_thresh"],
+                           cfg["inliers_ratio_thr"], cfg.get("initial_best_error", 0.0))
+        eq = np.array(eq0, np.float64)
+        err = C.c_double(err0)
+        inl = np.zeros(max(len(P), 1), np.uint8)
+        st = C.c_int32(0)
+        self._check(self._lib.plp_plane_ransac(
+            self._h, P.ctypes.data_as(_P), None if v is None else v.ctypes.data_as(_P), C.c_int(len(P)),
+            sm.ctypes.data_as(_P), C.c_int(sm.shape[0]), C.c_int(sm.shape[1]), C.byref(c), eq.ctypes.data_as(_P),
+            C.byref(err), inl.ctypes.data_as(_P), C.byref(st)))
+        return int(st.value), eq, float(err.value), inl[:len(P)].copy()
 
     def landmark_compute_descriptor_batch(self, descs, offsets):
         """landmark::compute_descriptor for a batch: index of the median-distance observation per landmark."""

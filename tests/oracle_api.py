@@ -345,6 +345,36 @@ class Oracle:
                                               C.byref(score), scores.ctypes.data_as(_P))
         return int(valid), inl[:len(m)].copy(), E.reshape(3, 3), float(score.value), scores[:len(sm)].copy()
 
+    # ---- Planar_Mapping_module plane RANSAC
+    def plane_fit(self, pos_w, idx):
+        P = np.ascontiguousarray(pos_w, np.float64).reshape(-1, 3)
+        ix = np.ascontiguousarray(idx, np.int32)
+        eq = np.zeros(4, np.float64)
+        self.lib.orc_plane_fit.restype = C.c_double
+        r = self.lib.orc_plane_fit(P.ctypes.data_as(_P), ix.ctypes.data_as(_P), C.c_int(len(ix)), eq.ctypes.data_as(_P))
+        return eq, float(r)
+
+    def plane_ransac(self, pos_w, valid, samples, cfg, eq0=(0, 0, 0, 0), err0=0.0):
+        """cfg = dict(mode, points_per_ransac, planar_distance_thresh, final_error_thresh, inliers_ratio_thr,
+        initial_best_error) -> (status, eq, plane_error, inlier flags)."""
+        class Cfg(C.Structure):
+            _fields_ = [("mode", C.c_int32), ("points_per_ransac", C.c_int32), ("planar_distance_thresh", C.c_double),
+                        ("final_error_thresh", C.c_double), ("inliers_ratio_thr", C.c_double),
+                        ("initial_best_error", C.c_double)]
+        P = np.ascontiguousarray(pos_w, np.float64).reshape(-1, 3)
+        sm = np.ascontiguousarray(samples, np.int32)
+        sm = sm.reshape(len(sm), -1) if sm.size else sm.reshape(0, 1)
+        v = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+        c = Cfg(cfg["mode"], cfg["points_per_ransac"], cfg["planar_distance_thresh"], cfg["final_error_thresh"],
+                cfg["inliers_ratio_thr"], cfg.get("initial_best_error", 0.0))
+        eq = np.array(eq0, np.float64)
+        err = C.c_double(err0)
+        inl = np.zeros(max(len(P), 1), np.uint8)
+        st = self.lib.orc_plane_ransac(P.ctypes.data_as(_P), None if v is None else v.ctypes.data_as(_P), C.c_int(len(P)),
+                                       sm.ctypes.data_as(_P), C.c_int(sm.shape[0]), C.c_int(sm.shape[1]), C.byref(c),
+                                       eq.ctypes.data_as(_P), C.byref(err), inl.ctypes.data_as(_P))
+        return int(st), eq, float(err.value), inl[:len(P)].copy()
+
     def landmark_compute_descriptor_batch(self, descs, offsets):
         d, pd = _a(np.asarray(descs).reshape(-1, 32), np.uint8)
         o, po = _a(offsets, np.int32)
