@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/gpu_round4.sh TAG -- run ON THE GPU BOX: whole GPU suite, BA breakdown, default bench
+# tools/gpu_check_full.sh TAG -- run ON THE GPU BOX: whole GPU suite, BA breakdown, default bench
 set -u
 TAG=${1:-r01h}
 mkdir -p gpurun_out
