@@ -12,11 +12,13 @@
 //   src/PLPSLAM/match/projection.cc / robust.cc (match_frame_and_keyframe, match_for_triangulation)
 //   src/PLPSLAM/mapping_module.cc               (fuse_landmark_duplication -> match::fuse::replace_duplication)
 //   src/PLPSLAM/data/frame.cc / keyframe.cc     (compute_bow), src/PLPSLAM/module/relocalizer.cc (bow_tree matcher)
+//   src/PLPSLAM/planar_mapping_module.cc        (estimate_plane_sequential_RANSAC, update_plane_via_RANSAC)
 // call.  Public signatures, PLPSLAM::system, the YAML configs and the map database stay unchanged.
 // See INTEGRATION.md for the patch of each call site.
 #pragma once
 #ifdef PLPSLAM_B200_WITH_REFERENCE_TYPES
 
+#include <cmath>
 #include <cstring>
 #include <set>
 #include <stdexcept>
@@ -30,6 +32,9 @@
 #include "PLPSLAM/feature/line_descriptor/descriptor_custom.hpp"
 #include "PLPSLAM/data/landmark.h"
 #include "PLPSLAM/data/landmark_line.h"
+#include "PLPSLAM/data/landmark_plane.h"
+#include <functional>
+#include <random>
 #include "plpslam_b200.h"
 
 namespace plpslam_b200 {
@@ -499,6 +504,54 @@ inline std::vector<unsigned> replace_duplication(const std::vector<PLPSLAM::data
         }
     }
     return num_fused;
+}
+
+// ---- Planar_Mapping_module::estimate_plane_sequential_RANSAC / update_plane_via_RANSAC (planar_mapping_module.cc:412-733)
+// `update` = false: estimate (POINTS_PER_RANSAC samples, ratio gate, early exit); true: update (0.8 n samples).
+inline bool plane_ransac(PLPSLAM::data::Plane *plane, bool update, unsigned iterations_count, unsigned points_per_ransac,
+                         double planar_distance_thresh, double final_error_thresh, double inliers_ratio_thr) {
+    std::vector<PLPSLAM::data::landmark *> lms = plane->get_landmarks();
+    const int n = (int)lms.size();
+    if (n == 0) return false;                                   // :423-426 / :597-600
+    if (n < (int)points_per_ransac) {                           // :428-436 / :602-606
+        if (update) plane->set_invalid();
+        return false;
+    }
+    std::vector<double> pos((size_t)n * 3);
+    std::vector<uint8_t> valid(n), inlier(n);
+    for (int j = 0; j < n; ++j) {
+        valid[j] = !lms[j]->will_be_erased();
+        const PLPSLAM::Vec3_t p = lms[j]->get_pos_in_world();
+        for (int k = 0; k < 3; ++k) pos[3 * (size_t)j + k] = p(k);
+    }
+    // the reference's own index draws (:444-457 / :613-632): uniform indices, erased landmarks rejected
+    const int sample_size = update ? (int)std::ceil(n * 0.8) : (int)points_per_ransac;
+    std::function<int()> rnd = std::bind(std::uniform_int_distribution<>(0, n - 1), std::mt19937(std::random_device()()));
+    std::vector<int32_t> samples((size_t)iterations_count * sample_size);
+    for (auto &s : samples) {
+        int index = rnd();
+        while (!valid[index] || (update && !lms[index]->get_Owning_Plane())) index = rnd();  // :623-631
+        s = index;
+    }
+    double eq[4], best_error = plane->get_best_error();
+    plane->get_equation(eq[0], eq[1], eq[2], eq[3]);
+    const plp_plane_ransac_cfg cfg{update ? 1 : 0, (int32_t)points_per_ransac, planar_distance_thresh, final_error_thresh,
+                                   inliers_ratio_thr, best_error};
+    int32_t status = 0;
+    check(plp_plane_ransac(thread_ctx(), pos.data(), valid.data(), n, samples.data(), (int)iterations_count, sample_size, &cfg,
+                           eq, &best_error, inlier.data(), &status));
+    plane->set_equation(eq[0], eq[1], eq[2], eq[3]);  // the Plane is mutated every iteration, also on failure (:465-467)
+    plane->set_best_error(best_error);
+    if (status == 2) plane->set_invalid();                      // :713-717
+    if (status == 0 && update) plane->set_need_refinement();    // :691-695
+    if (status != 1) return false;
+    std::vector<PLPSLAM::data::landmark *> kept;
+    for (int j = 0; j < n; ++j)
+        if (inlier[j]) kept.push_back(lms[j]);
+    plane->remove_landmarks_ownership();                        // :586-588 / :719-721
+    plane->set_landmarks(kept);
+    plane->set_landmarks_ownership();
+    return true;
 }
 
 // ---- frame::compute_bow / keyframe::compute_bow (data/frame.cc:785-795) ----------------------------------------
