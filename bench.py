@@ -597,6 +597,40 @@ def bench_mapping(pkg, ctx, cpu_baseline, reps=10):
         for a, b in bp:
             orc.bow_tree_match(a, b, 0.75, True)
         out["bow_tree_match"]["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+    # ---- solve::essential_solver RANSAC (robust.cc:232: 50 hypotheses over ~500 brute-force matches)
+    try:
+        import ess_data
+        b1, b2, matches, _ = ess_data.make_two_view(10, n=500, outlier_frac=0.3)
+        smp = ess_data.draw_samples(1, len(matches), 50)
+        l0 = ctx.launch_count()
+        ms = med(lambda: ctx.essential_ransac(b1, b2, matches, smp, False))
+        out["essential_ransac"] = {"ms_per_call": ms, "config": "500 matches, 50 eight-point hypotheses",
+                                   "gpu_launches": int(ctx.launch_count() - l0)}
+        if orc:
+            t0 = time.perf_counter()
+            orc.essential_ransac(b1, b2, matches, smp, False)
+            out["essential_ransac"]["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+    except Exception as e:
+        out["essential_ransac"] = {"error": f"{type(e).__name__}: {e}"}
+    # ---- Planar_Mapping_module plane RANSAC (first GPU execution of this path happens at round end)
+    try:
+        import plane_data
+        pts, valid, _, _ = plane_data.make_plane_cloud(10, n=400)
+        psmp = plane_data.draw_plane_samples(0, valid, 50, 18)
+        l0 = ctx.launch_count()
+        ms = med(lambda: ctx.plane_ransac(pts, valid, psmp, plane_data.CFG_ESTIMATE))
+        out["plane_ransac"] = {"ms_per_call": ms, "config": "400 landmarks, 50 hypotheses of 18 points",
+                               "gpu_launches": int(ctx.launch_count() - l0)}
+        if orc:
+            want = orc.plane_ransac(pts, valid, psmp, plane_data.CFG_ESTIMATE)
+            got = ctx.plane_ransac(pts, valid, psmp, plane_data.CFG_ESTIMATE)
+            out["plane_ransac"]["matches_oracle"] = bool(got[0] == want[0] and np.array_equal(got[1], want[1]) and
+                                                         np.array_equal(got[3], want[3]))
+            t0 = time.perf_counter()
+            orc.plane_ransac(pts, valid, psmp, plane_data.CFG_ESTIMATE)
+            out["plane_ransac"]["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+    except Exception as e:
+        out["plane_ransac"] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 
