@@ -69,3 +69,20 @@ def test_plane_ransac_failure_paths(orc):
     cloud = rng.uniform(-1, 1, (80, 3))
     st, eq, err, inl = orc.plane_ransac(cloud, None, plane_data.draw_plane_samples(2, np.ones(80), 15, 18), plane_data.CFG_ESTIMATE)
     assert st == 0 and inl.sum() == 0 and abs(np.linalg.norm(eq[:3]) - 1) < 1e-12 and err > 0.002
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_plane_ransac_oracle_matches_python_restatement(orc, seed):
+    """The C++ oracle's loop bookkeeping (best_error also fed by sample residuals, the Plane taking every sample fit, the
+    final filter with the LAST equation) against a second implementation written from the reference text."""
+    n = [300, 150, 500, 90, 260, 40][seed]
+    pts, valid, _, _ = plane_data.make_plane_cloud(seed + 40, n=n, outlier_frac=[0.25, 0.1, 0.35, 0.2, 0.5, 0.1][seed])
+    for cfg, size, e0 in ((plane_data.CFG_ESTIMATE, 18, 0.0), (plane_data.CFG_UPDATE, int(np.ceil(0.8 * n)), 0.01)):
+        smp = plane_data.draw_plane_samples(seed, valid, 30, size)
+        st, eq, err, inl = orc.plane_ransac(pts, valid, smp, cfg, (0, 0, 1, 0), e0)
+        ps, peq, perr, pinl = plane_data.plane_ransac_python(pts, valid, smp, cfg, (0, 0, 1, 0), e0)
+        assert st == ps
+        assert np.array_equal(inl, pinl)
+        if eq[:3] @ peq[:3] < 0:
+            peq = -peq
+        assert np.abs(eq - peq).max() < 1e-8 and abs(err - perr) < 1e-10
