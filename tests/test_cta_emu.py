@@ -71,3 +71,39 @@ def test_plane_kernels_on_cpu_failure_paths(emu, orc):
     want = orc.plane_ransac(cloud, None, smp, plane_data.CFG_ESTIMATE)
     got = _run(emu, cloud, None, smp, plane_data.CFG_ESTIMATE)
     assert got[0] == want[0] == 0 and np.array_equal(got[1], want[1]) and got[2] == want[2] and got[3].sum() == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the essential-matrix RANSAC kernels are GPU-verified (tests/test_essential_gpu.py): running them through the emulator as
+# well validates the emulator itself
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ess_emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = tmp_path_factory.mktemp("emu") / "libess_emu.so"
+    cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-shared", "-fPIC", "-ffp-contract=off",
+           f"-I{ROOT / 'structure-plp-slam_b200' / 'csrc'}", f"-I{ROOT / 'tests' / 'cta_emu'}",
+           str(ROOT / "tests" / "cta_emu" / "essential_emu.cc"), "-o", str(so)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[:3000]
+    return C.CDLL(str(so))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_essential_kernels_on_cpu_match_oracle(ess_emu, orc, seed):
+    import ess_data
+    n = [200, 60, 33][seed]
+    b1, b2, matches, _ = ess_data.make_two_view(seed + 10, n=n)
+    smp = ess_data.draw_samples(seed, len(matches), 12)
+    for recompute in (False, True):
+        want = orc.essential_ransac(b1, b2, matches, smp, recompute)
+        B1, B2 = np.ascontiguousarray(b1, np.float64), np.ascontiguousarray(b2, np.float64)
+        m, sm = np.ascontiguousarray(matches, np.int32), np.ascontiguousarray(smp, np.int32)
+        inl, E, score = np.zeros(len(m), np.uint8), np.zeros(9), C.c_double(0)
+        valid = ess_emu.emu_essential_ransac(B1.ctypes.data_as(_P), B2.ctypes.data_as(_P), m.ctypes.data_as(_P),
+                                             C.c_int(len(m)), sm.ctypes.data_as(_P), C.c_int(len(sm)),
+                                             C.c_int(1 if recompute else 0), inl.ctypes.data_as(_P), E.ctypes.data_as(_P),
+                                             C.byref(score))
+        assert valid == want[0] and np.array_equal(inl, want[1]) and np.array_equal(E.reshape(3, 3), want[2])
+        assert score.value == want[3]
