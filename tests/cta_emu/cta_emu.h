@@ -29,24 +29,95 @@ static pthread_barrier_t g_cta_barrier;
 #define __launch_bounds__(...)
 #define __shared__ static
 
+#define __align__(n) __attribute__((aligned(n)))
+
 static inline void __syncthreads() { pthread_barrier_wait(&g_cta_barrier); }
 static inline int atomicAdd(int *a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicOr(unsigned *a, unsigned v) { return __atomic_fetch_or(a, v, __ATOMIC_SEQ_CST); }
+
+// ---- vector types / scalar built-ins the kernels use
+struct uint4 {
+    unsigned x, y, z, w;
+};
+template <class T>
+static inline T __ldg(const T *p) { return *p; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __float2int_rn(float v) { return (int)lrintf(v); }   // round-half-even (default rounding mode)
+static inline int __double2int_rn(double v) { return (int)lrint(v); }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+
+// ---- warp intrinsics: 32 consecutive host threads form a warp with its own barrier and exchange buffer.  Only
+// full-mask, convergent use is supported (what the kernels do); a divergent shuffle deadlocks here -- it would be a bug
+// on the GPU as well.
+struct emu_warp_ctx {
+    pthread_barrier_t bar;
+    unsigned long long buf[32];
+    unsigned lanes;
+};
+static thread_local emu_warp_ctx *emu_warp = nullptr;
+static thread_local unsigned emu_lane = 0;
+
+static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&emu_warp->bar); }
+template <class T>
+static inline T emu_exchange(T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    unsigned long long raw = 0;
+    __builtin_memcpy(&raw, &v, sizeof(T));
+    emu_warp->buf[emu_lane] = raw;
+    pthread_barrier_wait(&emu_warp->bar);
+    T out = v;
+    if (src >= 0 && src < (int)emu_warp->lanes) {
+        raw = emu_warp->buf[src];
+        __builtin_memcpy(&out, &raw, sizeof(T));
+    }
+    pthread_barrier_wait(&emu_warp->bar);
+    return out;
+}
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src & 31); }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int o) { return emu_exchange(v, (int)(emu_lane ^ (unsigned)o)); }
+template <class T>
+static inline T __shfl_down_sync(unsigned, T v, int o) { return emu_exchange(v, (int)emu_lane + o < 32 ? (int)emu_lane + o : -1); }
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int o) { return emu_exchange(v, (int)emu_lane - o); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    emu_warp->buf[emu_lane] = pred ? 1ull : 0ull;
+    pthread_barrier_wait(&emu_warp->bar);
+    unsigned m = 0;
+    for (unsigned l = 0; l < emu_warp->lanes; ++l) m |= (emu_warp->buf[l] ? 1u : 0u) << l;
+    pthread_barrier_wait(&emu_warp->bar);
+    return m;
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 
 template <class Kernel, class... Args>
 static void emu_launch(Kernel kernel, unsigned grid, unsigned block, Args... args) {
     gridDim.x = grid;
     blockDim.x = block;
+    const unsigned nwarps = (block + 31) / 32;
+    std::vector<emu_warp_ctx> warps(nwarps);
     for (unsigned b = 0; b < grid; ++b) {
         pthread_barrier_init(&g_cta_barrier, nullptr, block);
+        for (unsigned w = 0; w < nwarps; ++w) {
+            warps[w].lanes = (w + 1) * 32 <= block ? 32 : block - w * 32;
+            pthread_barrier_init(&warps[w].bar, nullptr, warps[w].lanes);
+        }
         std::vector<std::thread> threads;
         threads.reserve(block);
+        emu_warp_ctx *wp = warps.data();
         for (unsigned t = 0; t < block; ++t)
             threads.emplace_back([=]() {
                 threadIdx.x = t;
                 blockIdx.x = b;
+                emu_warp = wp + t / 32;
+                emu_lane = t % 32;
                 kernel(args...);
             });
         for (auto &th : threads) th.join();
+        for (unsigned w = 0; w < nwarps; ++w) pthread_barrier_destroy(&warps[w].bar);
         pthread_barrier_destroy(&g_cta_barrier);
     }
 }

@@ -107,3 +107,103 @@ def test_essential_kernels_on_cpu_match_oracle(ess_emu, orc, seed):
                                              C.byref(score))
         assert valid == want[0] and np.array_equal(inl, want[1]) and np.array_equal(E.reshape(3, 3), want[2])
         assert score.value == want[3]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DBoW2 transform and match::bow_tree kernels (GPU-verified, tests/test_bow_gpu.py): warp shuffles / ballots / match on the
+# emulator's per-warp exchange
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def bow_emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = tmp_path_factory.mktemp("emu") / "libbow_emu.so"
+    cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-shared", "-fPIC", "-ffp-contract=off",
+           f"-I{ROOT / 'structure-plp-slam_b200' / 'csrc'}", f"-I{ROOT / 'tests' / 'cta_emu'}",
+           str(ROOT / "tests" / "cta_emu" / "bow_emu.cc"), "-o", str(so)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[:3000]
+    lib = C.CDLL(str(so))
+    lib.emu_bow_match.restype = C.c_uint
+    return lib
+
+
+def _csr_vocab(vocab):
+    """The device layout plp_bow_vocab_create builds (csrc/bow.cu): node 0 = root, children grouped by parent."""
+    parent = vocab["parent"]
+    N = len(parent) + 1
+    cnt = np.bincount(parent, minlength=N)
+    child_begin = np.zeros(N + 1, np.uint32)
+    child_begin[1:] = np.cumsum(cnt)
+    fill = child_begin[:-1].astype(np.int64).copy()
+    children = np.zeros(max(N - 1, 1), np.uint32)
+    for i, p in enumerate(parent):
+        children[fill[p]] = i + 1
+        fill[p] += 1
+    desc = np.zeros((N, 32), np.uint8)
+    desc[1:] = vocab["desc"]
+    weight = np.zeros(N, np.float32)
+    weight[1:] = vocab["weight"]
+    word = np.full(N, -1, np.int32)
+    word[1:][vocab["is_leaf"] > 0] = np.arange(int(vocab["is_leaf"].sum()))
+    return child_begin, children, desc, weight, word, int(cnt.max())
+
+
+@pytest.mark.parametrize("k,L,levelsup", [(10, 3, 1), (4, 4, 4), (20, 2, 1)])
+def test_bow_transform_kernel_on_cpu_matches_oracle(bow_emu, orc, k, L, levelsup):
+    import bow_data
+    import synth
+    vocab = bow_data.make_vocab(k * 100 + L, k=k, L=L)
+    child_begin, children, ndesc, weight, word, maxc = _csr_vocab(vocab)
+    rng = np.random.default_rng(L)
+    n = 70
+    desc = synth.rand_desc(rng, n)
+    ov = orc.bow_vocab_create(k, L, vocab["parent"], vocab["desc"], vocab["weight"], vocab["is_leaf"])
+    want = orc.bow_transform(ov, desc, levelsup)
+    orc.bow_vocab_destroy(ov)
+    G = 4 if maxc <= 4 else 8 if maxc <= 8 else 16 if maxc <= 16 else 32
+    w_out, n_out, f_out = np.full(n, -2, np.int32), np.full(n, -2, np.int32), np.full(n, -1, np.float32)
+    bow_emu.emu_bow_transform(C.c_int(G), ndesc.ctypes.data_as(_P), child_begin.ctypes.data_as(_P),
+                              children.ctypes.data_as(_P), weight.ctypes.data_as(_P), word.ctypes.data_as(_P),
+                              desc.ctypes.data_as(_P), C.c_int(n), C.c_int(L - levelsup), w_out.ctypes.data_as(_P),
+                              n_out.ctypes.data_as(_P), f_out.ctypes.data_as(_P))
+    assert np.array_equal(w_out, want[0]) and np.array_equal(n_out, want[1]) and np.array_equal(f_out, want[2])
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_bow_match_kernel_on_cpu_matches_oracle(bow_emu, orc, seed):
+    import bow_data
+    s1, s2, _ = bow_data.make_bow_sides(seed, n1=160, n2=180, num_nodes=14)
+    for ratio, check, use_valid2 in [(0.75, True, True), (0.9, False, False)]:
+        b = dict(s2)
+        if not use_valid2:
+            b.pop("valid")
+        want = orc.bow_tree_match(s1, b, ratio, check)
+        f1, f2 = s1["fv"], b["fv"]
+        nb1, ne1, nb2, ne2 = [], [], [], []
+        i = j = 0
+        while i < len(f1[0]) and j < len(f2[0]):      # the host's merge-join (csrc/bow.cu)
+            if f1[0][i] == f2[0][j]:
+                nb1.append(f1[1][i]); ne1.append(f1[1][i + 1]); nb2.append(f2[1][j]); ne2.append(f2[1][j + 1])
+                i += 1
+                j += 1
+            elif f1[0][i] < f2[0][j]:
+                i += 1
+            else:
+                j += 1
+        A = lambda v, dt: np.ascontiguousarray(v, dt)  # noqa: E731
+        d1, d2 = A(s1["desc"], np.uint8), A(b["desc"], np.uint8)
+        a1, a2 = A(s1["angle"], np.float32), A(b["angle"], np.float32)
+        v1 = A(s1["valid"], np.uint8)
+        v2 = A(b["valid"], np.uint8) if "valid" in b else None
+        i1, i2 = A(f1[2], np.uint32), A(f2[2], np.uint32)
+        nb1, ne1, nb2, ne2 = (A(x, np.int32) for x in (nb1, ne1, nb2, ne2))
+        m21, m12 = np.full(len(d1), -2, np.int32), np.full(len(d2), -2, np.int32)
+        num = bow_emu.emu_bow_match(C.c_int(len(d1)), d1.ctypes.data_as(_P), a1.ctypes.data_as(_P), v1.ctypes.data_as(_P),
+                                    C.c_int(len(d2)), d2.ctypes.data_as(_P), a2.ctypes.data_as(_P),
+                                    None if v2 is None else v2.ctypes.data_as(_P), i1.ctypes.data_as(_P),
+                                    i2.ctypes.data_as(_P), C.c_int(len(nb1)), nb1.ctypes.data_as(_P), ne1.ctypes.data_as(_P),
+                                    nb2.ctypes.data_as(_P), ne2.ctypes.data_as(_P), C.c_float(ratio),
+                                    C.c_int(1 if check else 0), m21.ctypes.data_as(_P), m12.ctypes.data_as(_P))
+        assert np.array_equal(m21, want[0]) and np.array_equal(m12, want[1]) and num == want[2]
+        assert want[2] > 20
