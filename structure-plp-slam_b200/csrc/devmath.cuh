@@ -3,6 +3,13 @@
 #pragma once
 #include <stdint.h>
 
+// dynamic shared memory of a kernel: `extern __shared__` on the device; tests/cta_emu hands out a host buffer instead
+#ifdef PLP_CTA_EMU
+#define PLP_DYNAMIC_SMEM(name) uint8_t *name = emu_dynamic_smem
+#else
+#define PLP_DYNAMIC_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
+
 namespace plp {
 
 // ---- device helpers -------------------------------------------------------

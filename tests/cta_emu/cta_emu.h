@@ -92,14 +92,39 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     return m;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline unsigned __match_any_sync(unsigned, int key) {
+    emu_warp->buf[emu_lane] = (unsigned long long)(unsigned)key;
+    pthread_barrier_wait(&emu_warp->bar);
+    unsigned m = 0;
+    for (unsigned l = 0; l < emu_warp->lanes; ++l) m |= (emu_warp->buf[l] == (unsigned long long)(unsigned)key ? 1u : 0u) << l;
+    pthread_barrier_wait(&emu_warp->bar);
+    return m;
+}
+
+// ---- dynamic shared memory (kernels declare it with PLP_DYNAMIC_SMEM, csrc/devmath.cuh)
+#define PLP_CTA_EMU 1
+static uint8_t *emu_dynamic_smem = nullptr;
+
+template <class Kernel, class... Args>
+static void emu_launch2(Kernel kernel, unsigned grid_x, unsigned grid_y, unsigned block, size_t smem_bytes, Args... args);
 
 template <class Kernel, class... Args>
 static void emu_launch(Kernel kernel, unsigned grid, unsigned block, Args... args) {
-    gridDim.x = grid;
+    emu_launch2(kernel, grid, 1u, block, (size_t)0, args...);
+}
+
+// <<<(grid_x, grid_y), block, smem_bytes>>>
+template <class Kernel, class... Args>
+static void emu_launch2(Kernel kernel, unsigned grid_x, unsigned grid_y, unsigned block, size_t smem_bytes, Args... args) {
+    gridDim.x = grid_x;
+    gridDim.y = grid_y;
     blockDim.x = block;
     const unsigned nwarps = (block + 31) / 32;
     std::vector<emu_warp_ctx> warps(nwarps);
-    for (unsigned b = 0; b < grid; ++b) {
+    std::vector<unsigned long long> smem(smem_bytes / 8 + 4);
+    emu_dynamic_smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    for (unsigned bb = 0; bb < grid_x * grid_y; ++bb) {
+        const unsigned b = bb % grid_x, by = bb / grid_x;
         pthread_barrier_init(&g_cta_barrier, nullptr, block);
         for (unsigned w = 0; w < nwarps; ++w) {
             warps[w].lanes = (w + 1) * 32 <= block ? 32 : block - w * 32;
@@ -112,6 +137,7 @@ static void emu_launch(Kernel kernel, unsigned grid, unsigned block, Args... arg
             threads.emplace_back([=]() {
                 threadIdx.x = t;
                 blockIdx.x = b;
+                blockIdx.y = by;
                 emu_warp = wp + t / 32;
                 emu_lane = t % 32;
                 kernel(args...);

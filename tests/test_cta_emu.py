@@ -207,3 +207,69 @@ def test_bow_match_kernel_on_cpu_matches_oracle(bow_emu, orc, seed):
                                     C.c_int(1 if check else 0), m21.ctypes.data_as(_P), m12.ctypes.data_as(_P))
         assert np.array_equal(m21, want[0]) and np.array_equal(m12, want[1]) and num == want[2]
         assert want[2] > 20
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# match::fuse search kernel (GPU-verified, tests/test_fuse_gpu.py): dynamic shared memory, counting sort with __match_any
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def fuse_emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = tmp_path_factory.mktemp("emu") / "libfuse_emu.so"
+    cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-shared", "-fPIC", "-ffp-contract=off",
+           f"-I{ROOT / 'structure-plp-slam_b200' / 'csrc'}", f"-I{ROOT / 'tests' / 'cta_emu'}",
+           str(ROOT / "tests" / "cta_emu" / "fuse_emu.cc"), "-o", str(so)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[:3000]
+    return C.CDLL(str(so))
+
+
+@pytest.mark.parametrize("seed,mode,stereo", [(0, 1, False), (1, 0, False), (2, 1, True)])
+def test_fuse_points_kernel_on_cpu_matches_oracle(fuse_emu, orc, plp, seed, mode, stereo):
+    import fuse_data
+    import synth
+    lms, targets = fuse_data.make_point_fuse_scene(seed + 60, m=90, num_targets=2, n_extra=40, stereo=stereo)
+    grid = plp.capi.make_grid(synth.COLS, synth.ROWS)
+    cam = plp.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, synth.COLS, synth.ROWS,
+                               bf=synth.BF if stereo else -1.0, setup_type=1 if stereo else 0)
+    sf, isg = synth.scale_factors(), fuse_data.inv_level_sigma_sq()
+    thr = plp.capi.fuse_level_thresholds(fuse_data.LOG_SF, len(sf))       # the product's host-side table
+    thr[0] = np.inf
+    keep = []
+
+    def A(v, dt):
+        a = np.ascontiguousarray(v, dt)
+        keep.append(a)
+        return a
+    K = len(targets)
+    n_arr = A([len(t["x"]) for t in targets], np.int32)
+    ptrs = {k: (C.c_void_p * K)() for k in ("x", "y", "xr", "oct", "desc", "skip")}
+    pose = np.zeros((K, 15), np.float64)
+    for i, t in enumerate(targets):
+        ptrs["x"][i] = A(t["x"], np.float32).ctypes.data
+        ptrs["y"][i] = A(t["y"], np.float32).ctypes.data
+        ptrs["xr"][i] = A(t["x_right"], np.float32).ctypes.data if "x_right" in t else None
+        ptrs["oct"][i] = A(t["octave"], np.int32).ctypes.data
+        ptrs["desc"][i] = A(t["desc"], np.uint8).ctypes.data
+        ptrs["skip"][i] = A(t["skip"], np.uint8).ctypes.data
+        pose[i, :9] = np.asarray(t["rot_cw"]).reshape(9)
+        pose[i, 9:12] = t["trans_cw"]
+        pose[i, 12:] = t["cam_center"]
+    m = len(lms["desc"])
+    best = np.full((K, m), -2, np.int32)
+    dist = np.full((K, m), 0xFFFE, np.uint16)
+    fuse_emu.emu_fuse_points(
+        C.c_int(K), n_arr.ctypes.data_as(_P), ptrs["x"], ptrs["y"], ptrs["xr"], ptrs["oct"], ptrs["desc"], ptrs["skip"],
+        pose.ctypes.data_as(_P), C.byref(grid), C.byref(cam), sf.ctypes.data_as(_P), isg.ctypes.data_as(_P),
+        thr.ctypes.data_as(_P), C.c_int(len(sf)), C.c_float(3.0), C.c_int(mode), C.c_int(m),
+        A(lms["pos_w"], np.float64).ctypes.data_as(_P), A(lms["obs_mean_normal"], np.float64).ctypes.data_as(_P),
+        A(lms["min_valid_dist"], np.float32).ctypes.data_as(_P), A(lms["max_valid_dist"], np.float32).ctypes.data_as(_P),
+        A(lms["max_valid_dist_raw"], np.float32).ctypes.data_as(_P), A(lms["desc"], np.uint8).ctypes.data_as(_P),
+        A(lms["valid"], np.uint8).ctypes.data_as(_P), C.c_int(48), best.ctypes.data_as(_P), dist.ctypes.data_as(_P))
+    total = 0
+    for i, t in enumerate(targets):
+        o_idx, o_dist, _ = orc.fuse_search_points(grid, cam, sf, isg, fuse_data.LOG_SF, t, lms, 3.0, mode)
+        assert np.array_equal(best[i], o_idx) and np.array_equal(dist[i], o_dist)
+        total += (o_idx >= 0).sum()
+    assert total > 10
