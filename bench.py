@@ -180,8 +180,37 @@ def setup_front_end(pkg, ctx, batch, seed, track_ctx=None):
     return fe, frames, dict(seqs=seqs, t_idx=t_idx, lasts=lasts, preds=preds, gt=gt)
 
 
+def host_cpu_info():
+    """Logical CPUs this process may use, physical cores and the CPU model (for the cpu_baseline / reference lines)."""
+    import oracle_api
+    info = {"logical": oracle_api.Oracle().host_cpus(), "physical": None, "model": None}
+    try:
+        cores, model = set(), None
+        phys, core = None, None
+        for ln in open("/proc/cpuinfo"):
+            k, _, v = ln.partition(":")
+            k, v = k.strip(), v.strip()
+            if k == "model name" and model is None:
+                model = v
+            elif k == "physical id":
+                phys = v
+            elif k == "core id":
+                core = v
+            elif not ln.strip():
+                if phys is not None and core is not None:
+                    cores.add((phys, core))
+                phys, core = None, None
+        info["physical"] = len(cores) or None
+        info["model"] = model
+    except OSError:
+        pass
+    return info
+
+
 def cpu_port_frames(frames, aux, idxs, threads):
-    """The oracle port of the same path (extract -> match -> pose-opt) on `threads` host threads."""
+    """The oracle port of the same path (extract -> match [+ widened retry] -> pose-opt -> discard_outliers) on `threads`
+    NATIVE host threads (oracle/frontend_mt.cc: a std::thread pool inside liboracle.so, one pinned thread per CPU,
+    frames handed out by an atomic counter; the wall time is taken inside the library around the parallel region)."""
     import oracle_api
     import synth
     pkg = _load_pkg()
@@ -189,58 +218,37 @@ def cpu_port_frames(frames, aux, idxs, threads):
     p = oracle_api.orb_params()
     grid = pkg.capi.make_grid(COLS, ROWS)
     cam = pkg.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, COLS, ROWS)
-    sf, isig = synth.scale_factors(), synth.inv_level_sigma_sq()
-
-    def one(b):
-        r = orc.orb_extract(p, frames[b])
-        k = r["kps"]
-        last = aux["lasts"][b]
-        s, t = aux["t_idx"][b]
-        curr = dict(x=k["x"], y=k["y"], octave=k["octave"], angle=k["angle"], desc=r["desc"])
-        Tp = aux["preds"][b]
-        Tl = aux["seqs"][s].poses[t - 1]
-        m, nm = orc.match_current_and_last_frames(grid, sf, cam, curr, Tp, Tl, last, 20.0, True)
-        if nm < 20:
-            m, nm = orc.match_current_and_last_frames(grid, sf, cam, curr, Tp, Tl, last, 40.0, True)
-        idx = np.nonzero(m >= 0)[0]
-        pts = np.zeros(len(idx), oracle_api.PT_OBS_DTYPE)
-        pts["pos_w"] = last["pos_w"][m[idx]]
-        pts["obs_x"], pts["obs_y"] = k["x"][idx], k["y"][idx]
-        pts["x_right"] = -1.0
-        pts["inv_sigma_sq"] = isig[k["octave"][idx]]
-        T, pout, _, n_inl, _ = orc.pose_optimize(cam, Tp, pts)
-        return n_inl
-
-    t0 = time.perf_counter()
-    if threads <= 1:
-        out = [one(b) for b in idxs]
-    else:
-        with ThreadPoolExecutor(max_workers=threads) as ex:
-            out = list(ex.map(one, idxs))
-    dt = time.perf_counter() - t0
-    return len(idxs) / dt, dt, out
+    idxs = list(idxs)
+    imgs = np.ascontiguousarray(frames[idxs])
+    lasts = [aux["lasts"][b] for b in idxs]
+    preds = np.stack([aux["preds"][b] for b in idxs])
+    plast = np.stack([aux["seqs"][aux["t_idx"][b][0]].poses[aux["t_idx"][b][1] - 1] for b in idxs])
+    r = orc.frontend_track_batch(p, grid, cam, imgs, lasts, preds, plast, 20.0, max(1, threads), pin=True)
+    return len(idxs) / r["seconds"], r["seconds"], r["n_inliers"]
 
 
-def build_line_frames(batch: int, seed: int):
-    """`batch` distinct 640x480 line-rich frames: a few rendered scenes (tests/synth.make_line_image), each shifted by a
-    different offset so that no two frames of a batch are equal."""
+def build_line_frames(batch: int, seed: int, rows=ROWS, cols=COLS):
+    """`batch` distinct point-and-line-rich frames (tests/synth.make_plp_texture: ~1000 ORB keypoints and ~180 keylines
+    >= 60 px per 640x480 frame, BASELINE north_star "~1000 ORB + 200 line features/frame"): a few rendered scenes, each
+    shifted by a different offset so that no two frames of a batch are equal."""
     import synth
     n_base = min(batch, 12)
-    base = [synth.make_line_image(seed + i, ROWS, COLS) for i in range(n_base)]
+    base = [synth.make_plp_texture(seed + i, rows, cols) for i in range(n_base)]
     rng = np.random.default_rng(seed)
-    out = np.empty((batch, ROWS, COLS), np.uint8)
+    out = np.empty((batch, rows, cols), np.uint8)
     for b in range(batch):
         dx, dy = (0, 0) if b < n_base else (int(rng.integers(-60, 61)), int(rng.integers(-40, 41)))
         out[b] = np.roll(base[b % n_base], (dy, dx), axis=(0, 1))
     return out
 
 
-# SURVEY 8(d): remap is skipped (identity); per frame the line front end must read the image twice (LSD scale pass and
-# LBD blur+Sobel pass), write + read the half-resolution image, write the per-pixel level-line record once (16 B at
-# quarter resolution) and the int16 gradient pair once (4 B per pixel), and read both back at least once.
+# SURVEY 8(d) line figure with the remap skipped (identity, verified bit-exact): image read by the LSD scale pass (W H) +
+# half-resolution image written and read (2 W H / 4) + the LBD blur+Sobel pass (W H read, 2 x int16 per pixel written and
+# read back by the descriptor: 2 x 4 W H).  The level-line field is never materialised (DESIGN 3.6), so it is not counted:
+# 10.5 W H = 3.2 MB at 640x480 (SURVEY's 3.8 MB includes the remap's read + write).
 def line_alg_bytes(rows, cols):
     px, spx = rows * cols, (rows // 2) * (cols // 2)
-    return 2 * px + 2 * spx + 2 * 16 * spx + 2 * 4 * px
+    return 2 * px + 2 * spx + 2 * 4 * px
 
 
 def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_baseline):
@@ -328,7 +336,7 @@ def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_b
            "ms_per_step": ms / steps, "scaling": "weak",
            "config": {"workload": "LSD (refine 1, scale 0.5) + LBD line extraction, 640x480, lines >= 60 px kept",
                       "frames_per_step_per_gpu": batch, "mean_keylines_per_frame": float(n.mean()),
-                      "l2": "per-step working set (3.8 MB/frame of intermediates) larger than L2"},
+                      "l2": "per-step working set (3.2 MB/frame of intermediates) larger than L2"},
            "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
                    "d2h_bytes_per_step": int(kl.nbytes + lbd.nbytes + fn.nbytes + nn.nbytes)},
            "gpu_launches": int(launches), "kernel_time_shares": shares, "ms_per_launch": per_launch,
@@ -336,18 +344,12 @@ def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_b
     if cpu_baseline and rank == 0:
         import oracle_api
         orc = oracle_api.Oracle()
-        cores = os.cpu_count() or 1
-        ns = int(min(batch, max(32, 2 * cores)))
-        t0 = time.perf_counter()
-        with ThreadPoolExecutor(max_workers=cores) as ex:
-            list(ex.map(lambda b: orc.line_extract(frames[b]), range(ns)))
-        dt = time.perf_counter() - t0
-        t1 = time.perf_counter()
-        for b in range(8):
-            orc.line_extract(frames[b])
-        d1 = time.perf_counter() - t1
+        cores = orc.host_cpus()
+        ns = int(min(batch, max(32, 4 * cores)))
+        _, dt = orc.line_extract_batch_mt(frames[:ns], cores)
+        _, d1 = orc.line_extract_batch_mt(frames[:8], 1)
         res["cpu_baseline"] = {"value": ns / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-                               "sample": f"{ns} frames over {cores} host threads ({dt:.2f} s)",
+                               "sample": f"{ns} frames over {cores} native host threads ({dt:.2f} s)",
                                "single_thread_value": 8 / d1}
     trk.close()
     for d in (d_imgs, d_kl, d_lbd, d_fn, d_n, d_st):
@@ -366,7 +368,7 @@ def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
     lib = pkg.lib()
     H, W = 480, 752
     n_base = min(batch, 6)
-    pairs = [synth.make_stereo_pair(seed + 31 * i + 1000 * rank, H, W) for i in range(n_base)]
+    pairs = [synth.make_stereo_pair(seed + 31 * i + 1000 * rank, H, W, plp=True) for i in range(n_base)]
     rng = np.random.default_rng(seed)
     left = np.empty((batch, H, W), np.uint8)
     right = np.empty((batch, H, W), np.uint8)
@@ -461,15 +463,23 @@ def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
             "gpu_launches": int(launches), "kernel_time_shares": shares}
 
 
-def bench_ba(pkg, ctx, stream, rank, world, steps, warmup):
-    """Second BASELINE metric: local-BA LM iterations/s on config 4 (20 local + 10 fixed KF, 4000 points + 800 lines
-    + 200 plane-owned points, ~29 k edges), landmark-sharded over `world` GPUs with one NCCL all-reduce of the packed
-    reduced camera system per LM try (strong scaling: the problem size is fixed)."""
+BA_CONFIGS = {
+    # BASELINE configs[3]: 20 local + 10 fixed KF, 4000 points + 800 lines + 200 plane-owned points (~29 k edges)
+    "config4": dict(seed=42, n_local=20, n_fixed=10, n_points=4000, n_lines=800, n_plane_pts=200),
+    # SURVEY 8(e) scaled-up variant where landmark sharding has work to split: 60 KF x 200 k landmarks (~1.2 M edges)
+    "large": dict(seed=43, n_local=30, n_fixed=30, n_points=160000, n_lines=40000, n_plane_pts=2000, fast=True),
+}
+
+
+def bench_ba(pkg, ctx, stream, rank, world, steps, warmup, which="config4"):
+    """Second BASELINE metric: local-BA LM iterations/s, landmark-sharded over `world` GPUs with the packed reduced
+    camera system all-reduced over NCCL (strong scaling: the problem size is fixed)."""
     import torch
     import torch.distributed as dist
     import ba_data
     from plpslam_b200.ba import BaComm, LocalBA, shard_boundaries, shard_edges
-    prob = ba_data.make_ba_problem(42)
+    kw = BA_CONFIGS[which]
+    prob = ba_data.make_ba_problem(**kw)
     comm = None
     if world > 1:
         uid = [BaComm.unique_id(ctx) if rank == 0 else None]
@@ -487,6 +497,7 @@ def bench_ba(pkg, ctx, stream, rank, world, steps, warmup):
     ctx.sync()
     if world > 1:
         dist.barrier()
+    ar0 = comm.allreduce_count() if comm else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     done = 0
@@ -495,6 +506,7 @@ def bench_ba(pkg, ctx, stream, rank, world, steps, warmup):
         done += tr
     e1.record(stream)
     ctx.sync()
+    ar = (comm.allreduce_count() - ar0) if comm else 0
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=torch.cuda.current_device())
     if world > 1:
@@ -509,13 +521,82 @@ def bench_ba(pkg, ctx, stream, rank, world, steps, warmup):
         comm.close()
     edges = len(prob.pt_edge_kf) + len(prob.line_edge_kf) + len(prob.plane_edge_lm)
     alg_bytes = edges * 32 + len(prob.pt_pos_w) * 48 + len(prob.line_plucker) * 96 + len(prob.kf_fixed) * 112
+    launches_per_try = steps * (tries_per_step + 1)  # bench_tries runs tries + the lambda-init pass
     return {"metric": "local_ba_lm_iterations_per_sec", "value": done / (ms * 1e-3), "unit": "LM iterations/s",
             "scaling": "strong", "lm_tries_timed": done, "ms_per_lm_iteration": ms / max(done, 1),
             "full_solve_ms": solve_ms, "solve_iters": [out["iters_first"], out["iters_second"], out["lm_tries"]],
-            "config": {"workload": "local_bundle_adjuster 20 local + 10 fixed KF, 4000 points + 800 lines + 200 plane edges",
-                       "edges": edges, "parallelism": f"landmark-sharded over {world} GPU(s), 1 packed all-reduce per LM try"},
+            "allreduces_per_try": (ar / launches_per_try) if comm else 0.0, "ranks": world,
+            "config": {"workload": f"local_bundle_adjuster {kw['n_local']} local + {kw['n_fixed']} fixed KF, {kw['n_points']} points + "
+                                   f"{kw['n_lines']} lines + {kw['n_plane_pts']} plane edges",
+                       "edges": edges, "parallelism": f"landmark-sharded over {world} GPU(s), packed all-reduce of the reduced camera system"},
             "algorithmic_bytes_per_iteration": alg_bytes,
             "hbm_roofline_frac": (alg_bytes / (ms * 1e-3 / max(done, 1))) / 1e9 / _peaks()[0]}
+
+
+def ba_summary(r):
+    """The part of a local-BA leg that rides in `config` of the headline line (the driver keeps `config` verbatim)."""
+    return {"workload": r["config"]["workload"], "edges": r["config"]["edges"], "lm_iters_per_s": round(r["value"], 1),
+            "ms_per_try": round(r["ms_per_lm_iteration"], 4), "ranks": r["ranks"],
+            "allreduces_per_try": round(r["allreduces_per_try"], 3), "full_solve_ms": round(r["full_solve_ms"], 3),
+            "hbm_roofline_frac": float(f"{r['hbm_roofline_frac']:.3g}"), "scaling": "strong"}
+
+
+def bench_pose_opt_config3(pkg, ctx, stream, rank, world, steps, warmup, batch=296):
+    """BASELINE configs[2]: pose_optimizer_extended_line::optimize (pose_optimizer_extended_line.cc:62-305) on 1000 point +
+    200 line reprojection edges per frame (SURVEY 8(d) config-3 inputs: 15 % gross outliers, N(0, 1 px x scale) noise,
+    initial pose = GT o exp(N(0, diag(0.02 rad, 0.05 m))), seeds 0..batch-1), device-resident, one launch per step;
+    frames shard over ranks with no collective."""
+    import torch
+    import torch.distributed as dist
+    import synth
+    from plpslam_b200.tracking import DeviceBuffer
+    lib = pkg.lib()
+    cam = pkg.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, COLS, ROWS)
+    n_base = min(batch, 37)
+    scenes = [synth.make_pose_opt_scene(1000 * rank + s, n_pts=1000, n_lines=200) for s in range(n_base)]
+    T_in = np.stack([scenes[b % n_base][1] for b in range(batch)]).astype(np.float64)
+    pts = np.concatenate([np.ascontiguousarray(scenes[b % n_base][2], pkg.PT_OBS_DTYPE) for b in range(batch)])
+    lines = np.concatenate([np.ascontiguousarray(scenes[b % n_base][3], pkg.LINE_OBS_DTYPE) for b in range(batch)])
+    pt_off = (1000 * np.arange(batch + 1)).astype(np.int32)
+    ln_off = (200 * np.arange(batch + 1)).astype(np.int32)
+    d_T, d_pts, d_lines = DeviceBuffer.from_array(ctx, T_in), DeviceBuffer.from_array(ctx, pts), DeviceBuffer.from_array(ctx, lines)
+    d_po, d_lo = DeviceBuffer.from_array(ctx, pt_off), DeviceBuffer.from_array(ctx, ln_off)
+    d_To, d_pout, d_lout = DeviceBuffer(ctx, batch * 128), DeviceBuffer(ctx, batch * 1000), DeviceBuffer(ctx, batch * 200)
+    d_ninl, d_it = DeviceBuffer(ctx, batch * 4), DeviceBuffer(ctx, batch * 4)
+    cfg = pkg.capi.PoseOptCfg(4, 10)
+
+    def step():
+        ctx._check(lib.plp_pose_optimize_batch_dev(ctx.handle, C.byref(cam), C.c_int(batch), d_T.ptr, d_pts.ptr, d_po.ptr,
+                                                   d_lines.ptr, d_lo.ptr, C.c_int(1200), C.byref(cfg), d_To.ptr, d_pout.ptr,
+                                                   d_lout.ptr, d_ninl.ptr, d_it.ptr))
+
+    for _ in range(max(warmup, 3)):
+        step()
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    ctx.sync()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=torch.cuda.current_device())
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    iters = d_it.download(np.int32, (batch,))
+    ninl = d_ninl.download(np.int32, (batch,))
+    lm_its = int(iters.sum())
+    alg = 54800 * lm_its  # SURVEY 8(d): 1000 x 41 + 200 x 69 bytes per LM iteration
+    for d in (d_T, d_pts, d_lines, d_po, d_lo, d_To, d_pout, d_lout, d_ninl, d_it):
+        d.free()
+    return {"workload": "pose_optimizer_extended_line, 1000 point + 200 line edges/frame (BASELINE configs[2])",
+            "frames_per_step_per_gpu": batch, "frames_per_s": round(world * batch / (ms * 1e-3), 1), "ms_per_step": round(ms, 4),
+            "us_per_frame_latency_bound": round(1e3 * ms, 1), "lm_iterations_per_frame": round(lm_its / batch, 2),
+            "lm_iterations_per_s": round(world * lm_its / (ms * 1e-3), 1), "mean_inliers": round(float(ninl.mean()), 1),
+            "algorithmic_bytes_per_step": alg, "hbm_roofline_frac": float(f"{alg / (ms * 1e-3) / 1e9 / _peaks()[0]:.3g}")}
 
 
 def bench_mapping(pkg, ctx, cpu_baseline, reps=10):
@@ -635,57 +716,109 @@ def bench_mapping(pkg, ctx, cpu_baseline, reps=10):
 
 
 def bench_ba_cpu(n_solves=3):
-    """CPU oracle port of the same local BA (single thread)."""
+    """CPU oracle port of the same local BA (single thread, like the reference's g2o solve)."""
     import ba_data
     import oracle_api
     orc = oracle_api.Oracle()
-    prob = ba_data.make_ba_problem(42)
+    prob = ba_data.make_ba_problem(**BA_CONFIGS["config4"])
     t0 = time.perf_counter()
     tries = 0
     for _ in range(n_solves):
         r = ba_data.oracle_local_ba(orc, prob)
         tries += r.lm_tries
     dt = time.perf_counter() - t0
-    return {"value": tries / dt, "unit": "LM iterations/s", "cores": 1, "kind": "port",
+    return {"value": round(tries / dt, 2), "unit": "LM iterations/s", "cores": 1, "kind": "port",
             "sample": f"{n_solves} full local-BA solves ({tries} LM tries, {dt:.1f} s)"}
 
 
+def bench_latency(pkg, ctx, n_frames=24, seed=4321, with_lines=False):
+    """BASELINE configs[0] (the live-sequence plumbing loop) and SURVEY 8(d)'s batch-1 latency: ONE sequence through the
+    host entry points in the order of tracking_module::track (tracking_module.cc:424-570): extract -> motion-based track
+    (match_current_and_last_frames + pose_optimizer) -> search_local_landmarks (match_frame_and_landmarks,
+    tracking_module.cc:908-984) -> second pose_optimizer (:749-759); frame t uses the pose estimated for frame t-1.  Every
+    call takes HOST buffers and synchronises, like the reference's blocking calls.  Wall clock per frame."""
+    import scene
+    import synth
+    from plpslam_b200.sequence import SequentialTracker
+    seq = scene.PlanarSequence(seed=seed, n_frames=n_frames, plp=with_lines)
+    cam = pkg.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, COLS, ROWS)
+    trk = SequentialTracker.for_gpu(pkg, ctx, ROWS, COLS, cam, with_lines=with_lines)
+    l0 = ctx.launch_count()
+    res = trk.run(seq)
+    launches = ctx.launch_count() - l0
+    trk.close()
+    st = res["stage_ms"]   # per frame, per stage
+    tot = np.array([sum(f.values()) for f in st[2:]])  # the first tracked frames include lazy allocations
+    med = {k: round(float(np.median([f[k] for f in st[2:]])), 3) for k in st[2]}
+    err = [float(np.linalg.norm(res["poses"][t] - seq.poses[t]) / np.linalg.norm(seq.poses[t])) for t in range(1, n_frames)]
+    return {"workload": "one live 640x480 sequence through the host entry points, tracking_module::track order "
+                        "(extract, motion track, local-map track" + (", points + lines)" if with_lines else ", points)"),
+            "frames": n_frames - 1, "ms_per_frame_median": round(float(np.median(tot)), 3),
+            "ms_per_frame_p90": round(float(np.percentile(tot, 90)), 3), "frames_per_s": round(1e3 / float(np.median(tot)), 1),
+            "stage_ms_median": med, "tracked_frames": int(res["tracked"]), "max_rel_pose_err_vs_gt": float(f"{max(err):.3g}"),
+            "gpu_launches_per_frame": round(launches / max(n_frames - 1, 1), 1)}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the path (oracle port; the reference binary cannot be built here)."""
+    """--impl reference: the CPU implementation of the path (oracle port; the reference binary cannot be built here) on
+    every host CPU this process may use, through the NATIVE thread pool of liboracle.so (oracle/frontend_mt.cc)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    # bounded sample per step: 2 frames per host thread (capped), same workload/config as the GPU arm
-    per_step = int(min(256, max(16, 2 * cores)))
-    seqs, frames, t_idx = build_inputs(per_step, args.seed)
     import oracle_api
-    import synth
     orc = oracle_api.Oracle()
+    hw = host_cpu_info()
+    cores = hw["logical"]
+    # bounded sample per step: a few frames per host thread (capped), same workload/config as the GPU arm
+    per_step = int(min(512, max(16, 4 * cores)))
+    seqs, frames, t_idx = build_inputs(per_step, args.seed)
     p = oracle_api.orb_params()
     rng = np.random.default_rng(args.seed)
-    with ThreadPoolExecutor(max_workers=cores) as ex:
+    pkg = _load_pkg()
+    import synth
+    grid = pkg.capi.make_grid(COLS, ROWS)
+    cam = pkg.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, COLS, ROWS)
+    # last-frame landmarks: extract frame t-1 of every problem (setup, untimed, threaded through ctypes)
+    with ThreadPoolExecutor(max_workers=min(cores, 64)) as ex:
         kps = list(ex.map(lambda st: orc.orb_extract(p, seqs[st[0]].frames[st[1] - 1]), t_idx))
     lasts = [seqs[s].last_frame_landmarks(t - 1, kps[b]["kps"], kps[b]["desc"]) for b, (s, t) in enumerate(t_idx)]
     preds = np.stack([seqs[s].predicted_pose(t, rng) for (s, t) in t_idx])
     aux = dict(seqs=seqs, t_idx=t_idx, lasts=lasts, preds=preds)
     for _ in range(max(args.warmup, 1)):
-        cpu_port_frames(frames, aux, list(range(min(per_step, cores))), cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
         cpu_port_frames(frames, aux, list(range(per_step)), cores)
-    dt = time.perf_counter() - t0
+    per = []
+    ok = 0
+    for _ in range(args.steps):
+        fps_s, dt_s, ninl = cpu_port_frames(frames, aux, list(range(per_step)), cores)
+        per.append(dt_s)
+        ok = int((ninl >= 20).sum())
+    dt = float(sum(per))
     fps = args.steps * per_step / dt
+    fps_1, dt_1, _ = cpu_port_frames(frames, aux, list(range(min(8, per_step))), 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": per_step,
-                   "note": "reference binary unbuildable here (no C++ OpenCV/Eigen/g2o); CPU oracle port, frames spread over host threads"},
+        "config": {"workload": WORKLOAD, "frames_per_step": per_step, "tracked_ok_frames": ok,
+                   "note": "reference binary unbuildable here (no C++ OpenCV/Eigen/g2o); CPU oracle port, frames spread over "
+                           "a native pinned thread pool inside liboracle.so",
+                   "cpu_model": hw["model"], "physical_cores": hw["physical"], "logical_cpus": cores,
+                   "frames_per_s_per_logical_cpu": round(fps / cores, 3), "single_thread_frames_per_s": round(fps_1, 3),
+                   "step_seconds_min_max": [round(min(per), 4), round(max(per), 4)]},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{per_step} frames/step x {args.steps} steps"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def _round_floats(o, nd=6):
+    if isinstance(o, float):
+        return float(f"{o:.{nd}g}")
+    if isinstance(o, dict):
+        return {k: _round_floats(v, nd) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_round_floats(v, nd) for v in o]
+    return o
 
 
 def main():
@@ -703,13 +836,18 @@ def main():
                     help="1: matcher / pose optimiser of every sub-batch on a high-priority stream of its own")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true", help="skip the local-BA metric")
+    ap.add_argument("--no-ba-large", action="store_true", help="skip the scaled-up local-BA problem (60 KF x 200 k landmarks)")
+    ap.add_argument("--no-pose3", action="store_true", help="skip the config-3 pose-opt leg (1000 point + 200 line edges)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the sequential batch-1 latency leg (config 1)")
     ap.add_argument("--no-lines", action="store_true", help="skip the LSD+LBD line front-end metric")
     ap.add_argument("--only-lines", action="store_true", help="development: run only the line front-end leg")
     ap.add_argument("--no-mapping", action="store_true", help="skip the fuse / BoW legs (SURVEY 8(f) rows)")
     ap.add_argument("--no-stereo", action="store_true", help="skip the stereo point+line front-end leg (configs[4])")
     ap.add_argument("--only-stereo", action="store_true", help="development: run only the stereo leg")
+    ap.add_argument("--only-ba", action="store_true", help="development: run only the local-BA legs")
     ap.add_argument("--stereo-batch", type=int, default=148, help="stereo frames per step per GPU")
     ap.add_argument("--line-batch", type=int, default=1776, help="frames per step per GPU of the line front-end leg")
+    ap.add_argument("--detail", default=None, help="file for the full per-leg JSON (default gpurun_out/bench_detail_n<N>.json)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -741,6 +879,15 @@ def main():
         r = bench_stereo(pkg, ctx, stream, rank, world, args.steps, args.warmup, args.stereo_batch, args.seed)
         if rank == 0:
             print(json.dumps(r))
+        return
+    if args.only_ba:
+        out = {"local_ba": bench_ba(pkg, ctx, stream, rank, world, max(args.steps, 5), args.warmup, "config4")}
+        if not args.no_ba_large:
+            out["local_ba_large"] = bench_ba(pkg, ctx, stream, rank, world, 3, 1, "large")
+        if rank == 0:
+            print(json.dumps(out))
+        if world > 1:
+            dist.destroy_process_group()
         return
     # The batch of a step is split into `--streams` sub-batches, each owned by its own context (= CUDA stream) with its
     # own extractor / tracker handles: the H2D copy, the one-CTA-per-frame matcher / pose optimiser and the D2H copy of
@@ -800,28 +947,22 @@ def main():
     ms_max = float(t.item())
     value = world * B * args.steps / (ms_max * 1e-3)
 
-    # ---------------- e2e: host buffers, copies inside the timed region ----------------------------------
-    pinned_in, pinned_out = [], []
-    out_bytes = Bs * (128 + 4 + 4)
+    # ---------------- e2e: host buffers, every copy of a step inside the timed region -------------------
+    # per step and sub-batch, from / to PINNED host memory: H2D of the images AND of that step's last-frame landmarks
+    # (positions, octaves, angles, descriptors, validity, offsets) and predicted / last poses; D2H of everything the
+    # host-side data::frame needs: keypoints, descriptors, counts, the landmark index kept on every keypoint, poses,
+    # valid / inlier counts, LM iterations, status (full-capacity arrays: the API's fixed per-frame stride).
     for c in range(S):
-        pi, po = C.c_void_p(), C.c_void_p()
-        ctx._check(lib.plp_host_alloc_pinned(C.c_size_t(frames_l[c].nbytes), C.byref(pi)))
-        ctx._check(lib.plp_host_alloc_pinned(C.c_size_t(out_bytes), C.byref(po)))
-        C.memmove(pi, frames_l[c].ctypes.data, frames_l[c].nbytes)
-        pinned_in.append(pi)
-        pinned_out.append(po)
-    d2h_bytes = S * out_bytes
+        fes[c].stage_host_io(frames_l[c])
+    h2d_bytes = sum(f.h2d_bytes_per_step for f in fes)
+    d2h_bytes = sum(f.d2h_bytes_per_step for f in fes)
 
     def e2e_step():
         for c in range(S):
-            cx, f = ctxs[c], fes[c]
-            cx._check(lib.plp_dev_upload_async(cx.handle, f.d_imgs.ptr, pinned_in[c], C.c_size_t(frames_l[c].nbytes)))
+            f = fes[c]
+            f.upload_inputs_async()
             f.step(Bs)
-            po = pinned_out[c].value
-            cx = f.track_ctx  # the results are produced on the tracking stream
-            cx._check(lib.plp_dev_download_async(cx.handle, C.c_void_p(po), f.d_pose.ptr, C.c_size_t(Bs * 128)))
-            cx._check(lib.plp_dev_download_async(cx.handle, C.c_void_p(po + Bs * 128), f.d_num_valid.ptr, C.c_size_t(Bs * 4)))
-            cx._check(lib.plp_dev_download_async(cx.handle, C.c_void_p(po + Bs * 132), f.d_n_inl.ptr, C.c_size_t(Bs * 4)))
+            f.download_outputs_async()
 
     for _ in range(2):
         e2e_step()
@@ -835,10 +976,11 @@ def main():
     barrier()
     e2e_ms = f0.elapsed_time(f1)
     # the results of the last step are in host memory now: read them (the "loss or metric" of the contract)
-    e2e_ok = 0
+    e2e_ok, e2e_kp = 0, 0
     for c in range(S):
-        nv = np.frombuffer((C.c_char * (Bs * 4)).from_address(pinned_out[c].value + Bs * 128), np.int32)
-        e2e_ok += int((nv >= 20).sum())
+        hr = fes[c].host_results()
+        e2e_ok += int((hr["num_valid"] >= 20).sum())
+        e2e_kp += int(hr["n_kp"].sum())
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -879,35 +1021,69 @@ def main():
         if kk:
             traffic = (kk["dram_bytes_read"] + kk["dram_bytes_write"]) / tj["frames_per_launch"] * Bs
             traffic_src = f"{tf[-1].name}: {tj['source']}; per-frame bytes x {Bs} frames"
+    # whole-step figure beside the dominant kernel's: all algorithmic bytes of a frame over the step time
+    step_alg = (2604396 + 48 * 2200 + 41 * 1000 * 44) * B
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": per_launch_ms,
                 "launches_per_step": launches_per_step, "ms_per_step_of_this_kernel": per_step_ms,
-                "kernel_time_shares": shares,
+                "kernel_time_shares": shares, "kernel_ms_per_step": {k: round(v["total_ms"] / max(args.steps, 1), 4) for k, v in kt.items()},
                 "frames_per_launch": Bs,
+                "whole_step": {"algorithmic_bytes": step_alg, "achieved": step_alg / (ms_max / args.steps * 1e-3) / 1e9,
+                               "frac": step_alg / (ms_max / args.steps * 1e-3) / 1e9 / peak},
                 "how": "CUDA events around every launch on the launching stream over a repeat of the timed steps "
                        "(one sub-batch, kernels serialised)"}
 
-    ba_res = None
+    detail = {}
+    cfg_extra = {}
     if not args.no_ba:
-        ba_res = bench_ba(pkg, ctx, stream, rank, world, steps=max(args.steps, 5), warmup=args.warmup)
-
-    lines_res = None
+        r = bench_ba(pkg, ctx, stream, rank, world, steps=max(args.steps, 5), warmup=args.warmup, which="config4")
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            r["cpu_baseline"] = bench_ba_cpu()
+        detail["local_ba"] = r
+        cfg_extra["local_ba"] = ba_summary(r)
+        if "cpu_baseline" in r:
+            cfg_extra["local_ba"]["cpu_port_lm_iters_per_s"] = r["cpu_baseline"]["value"]
+        if not args.no_ba_large:
+            r = bench_ba(pkg, ctx, stream, rank, world, steps=3, warmup=1, which="large")
+            detail["local_ba_large"] = r
+            cfg_extra["local_ba_large"] = ba_summary(r)
+    if not args.no_pose3:
+        r = bench_pose_opt_config3(pkg, ctx, stream, rank, world, max(3, args.steps // 2), args.warmup)
+        detail["pose_opt_config3"] = r
+        cfg_extra["pose_opt_config3"] = r
+    if not args.no_latency and rank == 0:
+        try:
+            r = bench_latency(pkg, ctx)
+        except Exception as e:  # an auxiliary leg must not take the headline line down with it; say so loudly
+            r = {"error": f"{type(e).__name__}: {e}"}
+        detail["latency_batch1"] = r
+        cfg_extra["latency_batch1"] = r
+    if world > 1:
+        dist.barrier()
     if not args.no_lines:
-        lines_res = bench_lines(pkg, ctx, stream, rank, world, args.steps, args.warmup, args.line_batch, args.seed,
-                                world == 1 and not args.no_cpu_baseline)
-
-    stereo_res = None
+        r = bench_lines(pkg, ctx, stream, rank, world, args.steps, args.warmup, args.line_batch, args.seed,
+                        world == 1 and not args.no_cpu_baseline)
+        detail["line_frontend"] = r
+        cfg_extra["line_frontend"] = {"frames_per_s": round(r["value"], 1), "e2e_frames_per_s": round(r["e2e"]["value"], 1),
+                                      "mean_keylines_per_frame": round(r["config"]["mean_keylines_per_frame"], 1),
+                                      "hbm_roofline_frac": float(f"{r['hbm_roofline_frac']:.3g}"),
+                                      "frames_per_step_per_gpu": args.line_batch}
+        if "cpu_baseline" in r:
+            cfg_extra["line_frontend"]["cpu_port_frames_per_s"] = round(r["cpu_baseline"]["value"], 1)
     if not args.no_stereo:
-        stereo_res = bench_stereo(pkg, ctx, stream, rank, world, max(3, args.steps // 2), args.warmup, args.stereo_batch,
-                                  args.seed)
-
-    mapping_res = None
+        r = bench_stereo(pkg, ctx, stream, rank, world, max(3, args.steps // 2), args.warmup, args.stereo_batch, args.seed)
+        detail["stereo_frontend"] = r
+        cfg_extra["stereo_frontend"] = {"stereo_frames_per_s": round(r["value"], 1),
+                                        "mean_left_keylines": round(r["config"]["mean_left_keylines"], 1),
+                                        "mean_left_keypoints": round(r["config"]["mean_left_keypoints"], 1),
+                                        "mean_stereo_matches": round(r["config"]["mean_stereo_matches"], 1),
+                                        "stereo_frames_per_step_per_gpu": args.stereo_batch}
     if rank == 0 and world == 1 and not args.no_mapping:
         try:
-            mapping_res = bench_mapping(pkg, ctx, not args.no_cpu_baseline)
-        except Exception as e:  # an auxiliary leg must not take the headline line down with it; say so loudly
-            mapping_res = {"error": f"{type(e).__name__}: {e}"}
+            detail["mapping_matchers"] = bench_mapping(pkg, ctx, not args.no_cpu_baseline)
+        except Exception as e:
+            detail["mapping_matchers"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
@@ -918,34 +1094,38 @@ def main():
                        "orb": {"max_num_keypts": 1000, "scale_factor": 1.2, "num_levels": 8, "ini_fast_thr": 20, "min_fast_thr": 7},
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                        "streams_per_gpu": S * (2 if args.track_streams else 1), "frames_per_stream_per_step": Bs,
-                       "stream_layout": ("per sub-batch: extraction stream + high-priority tracking stream"
-                                         if args.track_streams else "per sub-batch: one stream"),
                        "l2": "inputs larger than L2 (batch x 307 KB images)",
-                       "tracked_ok_frames": ok, "tracked_ok_frames_e2e": e2e_ok},
+                       "tracked_ok_frames": ok, "tracked_ok_frames_e2e": e2e_ok, "mean_keypoints_e2e": round(e2e_kp / max(B, 1), 1),
+                       **cfg_extra},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes), "d2h_bytes_per_step": d2h_bytes},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "what": "pinned H2D of images + last-frame landmarks/descriptors/poses; D2H of keypoints, descriptors, "
+                            "match indices, poses, counts (full-capacity arrays), every step"},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            n_sample = int(min(Bs, max(32, 2 * cores)))
+            hw = host_cpu_info()
+            cores = hw["logical"]
+            n_sample = int(min(Bs, max(32, 4 * cores)))
             fps_mt, dt_mt, _ = cpu_port_frames(frames_l[0], aux, list(range(n_sample)), cores)
+            fps_mt2, dt_mt2, _ = cpu_port_frames(frames_l[0], aux, list(range(n_sample)), cores)
             fps_1, dt_1, _ = cpu_port_frames(frames_l[0], aux, list(range(min(8, n_sample))), 1)
-            line["cpu_baseline"] = {"value": fps_mt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n_sample} frames of the same workload over {cores} host threads ({dt_mt:.1f} s)",
-                                    "single_thread_value": fps_1}
-        if ba_res is not None:
-            if world == 1 and not args.no_cpu_baseline:
-                ba_res["cpu_baseline"] = bench_ba_cpu()
-            line["local_ba"] = ba_res
-        if lines_res is not None:
-            line["line_frontend"] = lines_res
-        if stereo_res is not None:
-            line["stereo_frontend"] = stereo_res
-        if mapping_res is not None:
-            line["mapping_matchers"] = mapping_res
-        print(json.dumps(line))
+            line["cpu_baseline"] = {"value": max(fps_mt, fps_mt2), "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_sample} frames of the same workload over {cores} native pinned host threads, "
+                                              f"best of two runs ({dt_mt:.2f} s, {dt_mt2:.2f} s)",
+                                    "single_thread_value": fps_1, "cpu_model": hw["model"], "physical_cores": hw["physical"],
+                                    "repeat_values": [round(fps_mt, 1), round(fps_mt2, 1)]}
+        detail["headline"] = dict(line)
+        dpath = Path(args.detail) if args.detail else ROOT / "gpurun_out" / f"bench_detail_n{world}.json"
+        try:
+            dpath.parent.mkdir(parents=True, exist_ok=True)
+            dpath.write_text(json.dumps(detail, indent=1))
+            line["detail_file"] = str(dpath.relative_to(ROOT)) if dpath.is_relative_to(ROOT) else str(dpath)
+        except OSError as e:
+            line["detail_file"] = f"unwritable: {e}"
+        sys.stderr.write("[bench detail] " + json.dumps(_round_floats(detail, 5)) + "\n")
+        print(json.dumps(_round_floats(line, 7)))
     if world > 1:
         dist.destroy_process_group()
 

@@ -756,6 +756,8 @@ PLP_API plp_status plp_ba_bench_tries(plp_ba *ba, int tries, int32_t *iters_done
 PLP_API plp_status plp_ba_comm_unique_id(uint8_t id_out[128]);
 PLP_API plp_status plp_ba_comm_init(plp_ctx *ctx, const uint8_t id[128], int world, int rank, plp_ba_comm **out);
 PLP_API void plp_ba_comm_destroy(plp_ba_comm *comm);
+/* number of ncclAllReduce calls issued through the communicator so far (measurement: all-reduces per LM try) */
+PLP_API uint64_t plp_ba_comm_allreduce_count(const plp_ba_comm *comm);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,10 @@ class BaComm:
         ctx._check(ctx._lib.plp_ba_comm_unique_id(buf))
         return bytes(buf)
 
+    def allreduce_count(self) -> int:
+        self._lib.plp_ba_comm_allreduce_count.restype = C.c_uint64
+        return int(self._lib.plp_ba_comm_allreduce_count(self.handle))
+
     def close(self):
         if self.handle is not None:
             self._lib.plp_ba_comm_destroy(self.handle)

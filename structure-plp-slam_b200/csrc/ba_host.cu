@@ -28,6 +28,8 @@ struct plp_ba {
     double *d_T_in = nullptr, *d_pts_in = nullptr, *d_lines_in = nullptr;
     double *d_T_out = nullptr, *d_pts_out = nullptr, *d_lines_out = nullptr;
     BaState *h_state = nullptr;  // pinned
+    double *d_stop = nullptr;    // multi-GPU: the force-stop word every rank agrees on (sum over ranks)
+    double *h_stop = nullptr;    // pinned, 2 doubles: [0] upload, [1] reduced value
     plp_ba_comm *comm = nullptr;
     int n_kf = 0, n_pts = 0, n_lines = 0, n_pe = 0, n_le = 0;
     cudaGraphExec_t try_graph = nullptr;  // one LM try captured as a CUDA graph
@@ -78,10 +80,31 @@ plp_status read_state(plp_ba *b) {
     return PLP_OK;
 }
 
-// SparseOptimizer::optimize(n): enqueue tries in chunks until the device state machine reports completion
-plp_status run_optimize(plp_ba *b, int n, int robust, bool first, volatile const uint8_t *force_stop, int *iters_done) {
-    plp_ctx *ctx = b->ctx;
+// The force-stop flag is written asynchronously by another host thread (mapping_module.cc:159-164), so two ranks may
+// read different values at the "same" point.  With a communicator every rank issues the same sequence of collectives
+// only if the stop decision itself is collective: the local flag is summed over the ranks (one 8-byte all-reduce per
+// chunk of LM tries, outside the per-try path) and every rank acts on the reduced value.
+plp_status stop_requested(plp_ba *b, volatile const uint8_t *force_stop, bool *stop) {
+    const bool local = force_stop && *force_stop;
     BaCollective *coll = b->comm ? ba_comm_collective(b->comm) : nullptr;
+    if (!coll) {
+        *stop = local;
+        return PLP_OK;
+    }
+    plp_ctx *ctx = b->ctx;
+    b->h_stop[0] = local ? 1.0 : 0.0;
+    PLP_CUDA_TRY(cudaMemcpyAsync(b->d_stop, b->h_stop, 8, cudaMemcpyHostToDevice, ctx->stream));
+    PLP_TRY(coll->all_reduce(b->d_stop, 1));
+    PLP_CUDA_TRY(cudaMemcpyAsync(b->h_stop + 1, b->d_stop, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *stop = b->h_stop[1] != 0.0;
+    return PLP_OK;
+}
+
+// SparseOptimizer::optimize(n): enqueue tries in chunks until the device state machine reports completion
+plp_status run_optimize(plp_ba *b, int n, int robust, bool first, volatile const uint8_t *force_stop, int *iters_done,
+                        bool *stopped) {
+    plp_ctx *ctx = b->ctx;
     PLP_TRY(ba_launch_set_state(ctx, b->dev, n, robust, first ? 1 : 0));
     int launched = 0;
     const int hard_cap = n * 10 + 4;
@@ -91,8 +114,11 @@ plp_status run_optimize(plp_ba *b, int n, int robust, bool first, volatile const
         PLP_TRY(ba_launch_decide(ctx, b->dev));
         launched += chunk;
         PLP_TRY(read_state(b));
-        if (b->h_state->phase == kBaDone || launched >= hard_cap) break;
-        if (force_stop && *force_stop) break;  // g2o polls the force-stop flag between iterations
+        if (b->h_state->phase == kBaDone || launched >= hard_cap) break;  // identical on every rank (replicated state)
+        if (force_stop || b->comm) {  // g2o polls the force-stop flag between iterations
+            PLP_TRY(stop_requested(b, force_stop, stopped));
+            if (*stopped) break;
+        }
         chunk = 2;
     }
     *iters_done = b->h_state->it;
@@ -109,6 +135,7 @@ void plp_ba_destroy(plp_ba *b) {
     cudaStreamSynchronize(b->ctx->stream);
     if (b->d_block) cudaFree(b->d_block);
     if (b->h_state) cudaFreeHost(b->h_state);
+    if (b->h_stop) cudaFreeHost(b->h_stop);
     if (b->try_graph) cudaGraphExecDestroy(b->try_graph);
     delete b;
 }
@@ -116,7 +143,7 @@ void plp_ba_destroy(plp_ba *b) {
 plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg *cfg, plp_ba_comm *comm, plp_ba **out) {
     PLP_REQUIRE(ctx && p && cfg && out, "null pointer");
     *out = nullptr;
-    PLP_REQUIRE(p->n_kf >= 1 && p->n_kf <= kBaMaxKf, "1 <= n_kf <= 128");
+    PLP_REQUIRE(p->n_kf >= 1, "n_kf >= 1");  // fixed keyframes are unbounded: every array is sized by n_kf
     PLP_REQUIRE(p->n_pts >= 0 && p->n_lines >= 0 && p->n_pt_edges >= 0 && p->n_line_edges >= 0 && p->n_plane_edges >= 0, "sizes");
     PLP_REQUIRE(p->kf_pose_cw && p->kf_fixed, "keyframe arrays");
     PLP_REQUIRE(p->n_pts == 0 || p->pt_pos_w, "pt_pos_w");
@@ -234,22 +261,23 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
     const size_t o_packed = cv.take((size_t)(packed_sum_len + world + 8) * 8), o_dp = cv.take(6 * kBaMaxFree * 8);
     const size_t o_tp = cv.take((size_t)G * 16), o_ts = cv.take(64), o_state = cv.take(sizeof(BaState));
     const size_t o_Tin = cv.take(n_kf * 128), o_ptsin = cv.take(P1 * 24), o_lnin = cv.take(L1 * 48), o_Tout = cv.take(n_kf * 128);
-    const size_t o_ptsout = cv.take(P1 * 24), o_lnout2 = cv.take(L1 * 48);
+    const size_t o_ptsout = cv.take(P1 * 24), o_lnout2 = cv.take(L1 * 48), o_stop = cv.take(64);
     if (cudaMalloc((void **)&b->d_block, cv.off) != cudaSuccess) {
         set_error("local BA: cudaMalloc(%zu) failed", cv.off);
         delete b;
         return PLP_ERR_CUDA;
     }
     b->block_bytes = cv.off;
-    if (cudaMallocHost((void **)&b->h_state, sizeof(BaState)) != cudaSuccess) {
+    if (cudaMallocHost((void **)&b->h_state, sizeof(BaState)) != cudaSuccess ||
+        cudaMallocHost((void **)&b->h_stop, 16) != cudaSuccess) {
         set_error("local BA: cudaMallocHost failed");
         plp_ba_destroy(b);
         return PLP_ERR_CUDA;
     }
     uint8_t *d = b->d_block;
-    cudaMemsetAsync(d, 0, cv.off, ctx->stream);
+    cudaError_t up_err = cudaMemsetAsync(d, 0, cv.off, ctx->stream);
     auto up = [&](size_t off, const void *src, size_t bytes) {
-        if (bytes) cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (bytes && up_err == cudaSuccess) up_err = cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
     up(o_hidx, hidx.data(), n_kf * 4);
     up(o_pbi, pair_bi.data(), n_pairs * 4);
@@ -270,7 +298,13 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
     up(o_Tin, p->kf_pose_cw, (size_t)n_kf * 128);
     up(o_ptsin, p->pt_pos_w, (size_t)n_pts * 24);
     up(o_lnin, p->line_plucker, (size_t)n_lines * 48);
-    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (up_err == cudaSuccess) up_err = cudaStreamSynchronize(ctx->stream);
+    if (up_err != cudaSuccess) {
+        set_error("local BA: upload failed: %s", cudaGetErrorString(up_err));
+        plp_ba_destroy(b);
+        return PLP_ERR_CUDA;
+    }
+    b->d_stop = (double *)(d + o_stop);
     BaDev &D = b->dev;
     memset(&D, 0, sizeof(D));
     D.fx = p->fx;
@@ -373,16 +407,19 @@ static plp_status ba_solve_impl(plp_ba *b, volatile const uint8_t *force_stop, p
     if (b->n_le) PLP_CUDA_TRY(cudaMemsetAsync(D.ln_outlier, 0, b->n_le, ctx->stream));
     r->iters_first = r->iters_second = r->lm_tries = 0;
     r->final_chi2 = 0;
-    const bool stop0 = force_stop && *force_stop;  // local_bundle_adjuster.cc:276-282
+    bool stop0 = false;  // local_bundle_adjuster.cc:276-282
+    if (force_stop || b->comm) PLP_TRY(stop_requested(b, force_stop, &stop0));
     if (!stop0) {
         int it1 = 0, it2 = 0;
-        PLP_TRY(run_optimize(b, b->cfg.num_first_iter, mode == 2 ? 0 : 1, true, force_stop, &it1));
+        bool stopped = false;
+        PLP_TRY(run_optimize(b, b->cfg.num_first_iter, mode == 2 ? 0 : 1, true, force_stop, &it1, &stopped));
         r->iters_first = it1;
+        if (!stopped && mode == 0 && (force_stop || b->comm)) PLP_TRY(stop_requested(b, force_stop, &stopped));
         if (mode != 0) {
             // global_bundle_adjuster.cc:247-253: a single optimize(num_iter); edges keep level 0
-        } else if (!(force_stop && *force_stop)) {  // :289-337
+        } else if (!stopped) {  // :289-337
             PLP_TRY(ba_launch_classify(ctx, D, 1));
-            PLP_TRY(run_optimize(b, b->cfg.num_second_iter, 0, false, force_stop, &it2));
+            PLP_TRY(run_optimize(b, b->cfg.num_second_iter, 0, false, force_stop, &it2, &stopped));
             r->iters_second = it2;
         }
         if (mode == 0) PLP_TRY(ba_launch_classify(ctx, D, 0));

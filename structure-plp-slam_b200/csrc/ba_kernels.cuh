@@ -7,7 +7,6 @@
 namespace plp {
 
 constexpr int kBaMaxFree = 32;  // non-fixed keyframes per problem (reduced system <= 192 x 192)
-constexpr int kBaMaxKf = 128;   // keyframes (free + fixed)
 enum { kBaNeedInit = 0, kBaRunning = 1, kBaDone = 2 };
 
 struct BaState {  // LM state machine, lives in device memory (single writer: the 1-CTA kernels)

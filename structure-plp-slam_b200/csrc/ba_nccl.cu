@@ -13,6 +13,7 @@ struct plp_ba_comm : public BaCollective {
     plp_ctx *ctx = nullptr;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
+    uint64_t calls = 0;  // ncclAllReduce calls issued through this communicator (bench.py: all-reduces per LM try)
     plp_status all_reduce(double *d_buf, int n) override {
         const ncclResult_t r = ncclAllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, comm, ctx->stream);
         if (r != ncclSuccess) {
@@ -20,6 +21,7 @@ struct plp_ba_comm : public BaCollective {
             return PLP_ERR_NCCL;
         }
         ctx->launches++;  // the NCCL kernel
+        calls++;
         return PLP_OK;
     }
 };
@@ -64,6 +66,8 @@ plp_status plp_ba_comm_init(plp_ctx *ctx, const uint8_t id[128], int world, int 
     *out = c;
     return PLP_OK;
 }
+
+uint64_t plp_ba_comm_allreduce_count(const plp_ba_comm *c) { return c ? c->calls : 0; }
 
 void plp_ba_comm_destroy(plp_ba_comm *c) {
     if (!c) return;

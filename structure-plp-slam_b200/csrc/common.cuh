@@ -47,6 +47,11 @@ void timing_begin(plp_ctx *ctx, const char *name);
 void timing_end(plp_ctx *ctx);
 plp_status ctx_scratch(plp_ctx *ctx, int slot, size_t bytes, void **out);
 plp_status ctx_pinned(plp_ctx *ctx, size_t bytes, void **out);
+// Opt a kernel in to the DEVICE MAXIMUM of dynamic shared memory, once per (kernel, device), and check that `need`
+// fits.  cudaFuncAttributeMaxDynamicSharedMemorySize is global per kernel: setting it to the size of the current
+// problem would lower it under a concurrent larger launch of another handle / thread, so it is only ever raised.
+plp_status ensure_smem_optin(const void *kernel, size_t need, const char *name);
+#define PLP_SMEM_OPTIN(kernel, need) PLP_TRY(plp::ensure_smem_optin((const void *)(kernel), (need), #kernel))
 
 #define PLP_CUDA_TRY(expr)                                                                   \
     do {                                                                                     \

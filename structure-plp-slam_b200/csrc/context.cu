@@ -1,6 +1,10 @@
 // context.cu -- plp_ctx lifetime, error string, device-memory helpers of the C ABI.
 #include "common.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace plp {
 
 static thread_local char g_err[512] = "";
@@ -53,6 +57,29 @@ plp_status ctx_pinned(plp_ctx *ctx, size_t bytes, void **out) {
         ctx->pinned_bytes = want;
     }
     *out = ctx->pinned;
+    return PLP_OK;
+}
+
+plp_status ensure_smem_optin(const void *kernel, size_t need, const char *name) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> done;  // (kernel, device) -> opted-in bytes
+    int dev = 0;
+    PLP_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find({kernel, dev});
+    if (it == done.end()) {
+        int optin = 0;
+        PLP_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cudaFuncAttributes fa;
+        PLP_CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+        const int dyn_max = optin - (int)fa.sharedSizeBytes;  // static shared memory counts against the same limit
+        PLP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+        it = done.emplace(std::make_pair(kernel, dev), (size_t)dyn_max).first;
+    }
+    if (need > it->second) {
+        set_error("%s needs %zu bytes of dynamic shared memory, the device offers %zu", name, need, it->second);
+        return PLP_ERR_CAPACITY;
+    }
     return PLP_OK;
 }
 

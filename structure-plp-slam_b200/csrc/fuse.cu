@@ -243,7 +243,7 @@ plp_status plp_fuse_search_points(plp_ctx *ctx, const plp_fuse_target_points *ta
     const FuseLandmarks L = bind_landmarks(d, lo, m);
     const int cap = max_n < 64 ? 64 : ((max_n + 63) / 64) * 64;
     const size_t smem = fuse_point_smem_bytes(cap, grid->num_cols * grid->num_rows);
-    PLP_CUDA_TRY(cudaFuncSetAttribute(fuse_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLP_SMEM_OPTIN(fuse_points_kernel, smem);
     const int chunk = chunk_size(ctx, m, num_targets);
     dim3 g(div_up(m, chunk), num_targets);
     PLP_LAUNCH(ctx, fuse_points_kernel, g, kThreads, smem, Packer::at<FusePointTarget>(d, o_targets), L, P, cap, chunk,
@@ -334,7 +334,7 @@ plp_status plp_fuse_search_lines(plp_ctx *ctx, const plp_fuse_target_lines *targ
     const FuseLandmarks L = bind_landmarks(d, lo, m);
     const int cap = max_n < 64 ? 64 : ((max_n + 63) / 64) * 64;
     const size_t smem = (size_t)cap * (32 + 5 * 4);
-    PLP_CUDA_TRY(cudaFuncSetAttribute(fuse_lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLP_SMEM_OPTIN(fuse_lines_kernel, smem);
     const int chunk = chunk_size(ctx, m, num_targets);
     dim3 g(div_up(m, chunk), num_targets);
     PLP_LAUNCH(ctx, fuse_lines_kernel, g, kThreads, smem, Packer::at<FuseLineTarget>(d, o_targets), L, P, cap, chunk,

@@ -1123,18 +1123,13 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
         return PLP_ERR_CAPACITY;
     }
     h->resident_smem_frames = h->img_smem_ok ? ctx->sm_count * (int)std::max<size_t>(1, (227 * 1024) / (h->grow_smem + 1024)) : 0;
-    if ((h->img_smem_ok && cudaFuncSetAttribute(lsd_grow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)h->grow_smem) != cudaSuccess) ||
-        cudaFuncSetAttribute(lsd_grow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grow_smem_noimg) !=
-            cudaSuccess) {
-        set_error("cudaFuncSetAttribute(lsd_grow_kernel) failed");
+    plp_status so = PLP_OK;
+    if (h->img_smem_ok) so = ensure_smem_optin((const void *)lsd_grow_kernel<true>, h->grow_smem, "lsd_grow_kernel<true>");
+    if (so == PLP_OK) so = ensure_smem_optin((const void *)lsd_grow_kernel<false>, h->grow_smem_noimg, "lsd_grow_kernel<false>");
+    if (so == PLP_OK) so = ensure_smem_optin((const void *)lsd_sort_kernel, h->sort_smem, "lsd_sort_kernel");
+    if (so != PLP_OK) {
         plp_line_destroy(h);
-        return PLP_ERR_CUDA;
-    }
-    if (cudaFuncSetAttribute(lsd_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sort_smem) != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(lsd_sort_kernel) failed");
-        plp_line_destroy(h);
-        return PLP_ERR_CUDA;
+        return so;
     }
     *out = h;
     return PLP_OK;

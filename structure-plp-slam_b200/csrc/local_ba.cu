@@ -982,9 +982,8 @@ size_t ba_solve_smem(int n_free) {
 }
 
 plp_status ba_prepare_kernels(int n_free, int n_pairs, int pool_cap) {
-    PLP_CUDA_TRY(cudaFuncSetAttribute(ba_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)ba_linearize_smem(n_free, n_pairs, pool_cap)));
-    PLP_CUDA_TRY(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_solve_smem(n_free)));
+    PLP_SMEM_OPTIN(ba_linearize_kernel, ba_linearize_smem(n_free, n_pairs, pool_cap));
+    PLP_SMEM_OPTIN(ba_solve_kernel, ba_solve_smem(n_free));
     return PLP_OK;
 }
 

@@ -972,7 +972,7 @@ plp_status launch_point_match(plp_ctx *ctx, const PointMatchJob *d_jobs, int num
     }
     const int cap = max_n < 64 ? 64 : ((max_n + 63) / 64) * 64;
     const size_t smem = point_smem_bytes(cap, grid.num_cols, grid.num_rows);
-    PLP_CUDA_TRY(cudaFuncSetAttribute(point_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLP_SMEM_OPTIN(point_match_kernel, smem);
     PLP_LAUNCH(ctx, point_match_kernel, num_jobs, kThreads, smem, d_jobs, grid, cap, ratio_test, lowe_ratio,
                check_orientation);
     PLP_CHECK_LAUNCH();
@@ -984,7 +984,7 @@ plp_status launch_line_match(plp_ctx *ctx, const LineMatchJob *d_jobs, int num_j
     if (num_jobs <= 0) return PLP_OK;
     // shared memory: 2 owner arrays; capacity fixed at 16384 keylines per frame
     const size_t smem = (size_t)2 * 16384 * 4 + 32;
-    PLP_CUDA_TRY(cudaFuncSetAttribute(line_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLP_SMEM_OPTIN(line_match_kernel, smem);
     PLP_LAUNCH(ctx, line_match_kernel, num_jobs, kThreads, smem, d_jobs, ratio_test, lowe_ratio, rgbd_gate);
     PLP_CHECK_LAUNCH();
     return PLP_OK;
@@ -999,7 +999,7 @@ plp_status launch_brute_match(plp_ctx *ctx, const BruteJob *d_jobs, int num_jobs
     }
     const int cap = max_n_frm < 64 ? 64 : ((max_n_frm + 63) / 64) * 64;
     const size_t smem = (size_t)cap * 32 + (size_t)cap * 8 + kHistLen * 4 + 16 + 32;
-    PLP_CUDA_TRY(cudaFuncSetAttribute(brute_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLP_SMEM_OPTIN(brute_match_kernel, smem);
     PLP_LAUNCH(ctx, brute_match_kernel, num_jobs, kThreads, smem, d_jobs, cap, lowe_ratio, check_orientation);
     PLP_CHECK_LAUNCH();
     return PLP_OK;
@@ -1692,7 +1692,7 @@ plp_status plp_match_for_triangulation(plp_ctx *ctx, const plp_keyframe_points *
     J.num_matches = Packer::at<uint32_t>(d, o_num);
     PLP_CUDA_TRY(cudaMemcpyAsync(d + o_job, &J, sizeof(J), cudaMemcpyHostToDevice, ctx->stream));
     const size_t smem = (size_t)n2 * 8 + (kHistLen + 4) * 4 + kHistLen + 16;
-    PLP_CUDA_TRY(cudaFuncSetAttribute(triangulation_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLP_SMEM_OPTIN(triangulation_match_kernel, smem);
     PLP_LAUNCH(ctx, triangulation_match_kernel, 1, kThreads, smem, Packer::at<TriJob>(d, o_job), (int)n2, check_orientation);
     PLP_CHECK_LAUNCH();
     uint32_t num = 0;

@@ -1644,11 +1644,10 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
     D.qt_scratch = o->d_qt_scratch;
     D.status = o->d_status;
     o->qt_smem = ((sizeof(QtShared) + 15) & ~(size_t)15) + (size_t)kQtSmemCands * (4 + 2 * 5 + 1) + 64;
-    cudaError_t e = cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->qt_smem);
-    if (e != cudaSuccess) {
-        set_error("orb: quadtree kernel needs %zu bytes of shared memory: %s", o->qt_smem, cudaGetErrorString(e));
+    const plp_status so = ensure_smem_optin((const void *)quadtree_kernel, o->qt_smem, "quadtree_kernel");
+    if (so != PLP_OK) {
         plp_orb_destroy(o);
-        return PLP_ERR_CUDA;
+        return so;
     }
     *out = o;
     return PLP_OK;

@@ -431,7 +431,7 @@ plp_status launch_pose_opt(plp_ctx *ctx, const PoseJob *d_jobs, int batch, int m
         return PLP_ERR_CAPACITY;
     }
     const size_t smem = pose_smem_bytes(max_edges < 64 ? 64 : max_edges);
-    PLP_CUDA_TRY(cudaFuncSetAttribute(pose_opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLP_SMEM_OPTIN(pose_opt_kernel, smem);
     PLP_LAUNCH(ctx, pose_opt_kernel, batch, kPoThreads, smem, d_jobs, cam, cfg,
                (int)pose_stage_bytes(max_edges < 64 ? 64 : max_edges));
     PLP_CHECK_LAUNCH();

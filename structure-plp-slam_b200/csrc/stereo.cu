@@ -251,7 +251,7 @@ plp_status plp_stereo_compute_batch_dev(plp_ctx *ctx, const plp_orb *left, const
     D.depth = d_depth_out;
     D.best_right = d_best_right_out;
     const size_t smem = stereo_smem(D.cap);
-    PLP_CUDA_TRY(cudaFuncSetAttribute(stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLP_SMEM_OPTIN(stereo_kernel, smem);
     PLP_LAUNCH(ctx, stereo_kernel, batch, kThreads, smem, D);
     PLP_CHECK_LAUNCH();
     return PLP_OK;

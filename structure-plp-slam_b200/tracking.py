@@ -53,6 +53,36 @@ class DeviceBuffer:
             self.ptr = None
 
 
+class PinnedBuffer:
+    """Page-locked host memory owned through the C ABI (plp_host_alloc_pinned): the source / destination of the
+    asynchronous copies of the end-to-end path."""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self._lib = ctx._lib
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        ctx._check(self._lib.plp_host_alloc_pinned(C.c_size_t(max(self.nbytes, 1)), C.byref(p)))
+        self.ptr = p
+
+    @classmethod
+    def from_array(cls, ctx: Context, arr: np.ndarray) -> "PinnedBuffer":
+        arr = np.ascontiguousarray(arr)
+        buf = cls(ctx, arr.nbytes)
+        C.memmove(buf.ptr, arr.ctypes.data, arr.nbytes)
+        return buf
+
+    def view(self, dtype, shape, offset: int = 0) -> np.ndarray:
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        assert offset + n <= self.nbytes
+        raw = (C.c_char * n).from_address(self.ptr.value + offset)
+        return np.frombuffer(raw, dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr is not None:
+            self._lib.plp_host_free_pinned(self.ptr)
+            self.ptr = None
+
+
 class FrontEnd:
     """extract (orb_extractor::extract) -> motion_based_track for a batch of frames, all on the device."""
 
@@ -91,6 +121,10 @@ class FrontEnd:
         self.d_lm = DeviceBuffer(ctx, B * 4)
         self._last_bufs = []
         self._last = None
+        self._last_pinned = []   # host copies of the last-frame arrays (end-to-end path: uploaded every step)
+        self._pin_imgs = None
+        self._pin_out = None
+        self._out_layout = None
 
     def close(self):
         if self._trk is not None:
@@ -117,6 +151,68 @@ class FrontEnd:
                   offs, np.ascontiguousarray(pose_pred, np.float64), np.ascontiguousarray(pose_last, np.float64)]
         self._last_bufs = [DeviceBuffer.from_array(self.ctx, a) for a in arrays]
         self._last = TrackLast(*[b.ptr for b in self._last_bufs])
+        for b in self._last_pinned:
+            b.free()
+        self._last_pinned = [PinnedBuffer.from_array(self.ctx, a) for a in arrays]
+
+    # -- end-to-end path: every input of a step comes from pinned host memory, every result goes back ----
+    def stage_host_io(self, imgs: np.ndarray):
+        """Pinned host staging of one step: the images (input) and one block for all results."""
+        batch = imgs.shape[0]
+        if self._pin_imgs is not None:
+            self._pin_imgs.free()
+            self._pin_out.free()
+        self._pin_imgs = PinnedBuffer.from_array(self.ctx, np.ascontiguousarray(imgs, np.uint8))
+        items = [("kp", self.d_kp, batch * self.cap * KP_DTYPE.itemsize), ("desc", self.d_desc, batch * self.cap * 32),
+                 ("n_kp", self.d_n, batch * 4), ("status", self.d_status, batch * 4),
+                 ("matched", self.d_matched, batch * self.cap * 4), ("pose", self.d_pose, batch * 128),
+                 ("num_valid", self.d_num_valid, batch * 4), ("n_inliers", self.d_n_inl, batch * 4),
+                 ("lm_iters", self.d_lm, batch * 4)]
+        off, layout = 0, []
+        for name, dbuf, nbytes in items:
+            layout.append((name, dbuf, off, nbytes))
+            off += (nbytes + 255) & ~255
+        self._pin_out = PinnedBuffer(self.ctx, off)
+        self._out_layout = layout
+        self._io_batch = batch
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return self._pin_imgs.nbytes + sum(b.nbytes for b in self._last_pinned)
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return sum(nb for _, _, _, nb in self._out_layout)
+
+    def upload_inputs_async(self):
+        """H2D of this step's images AND of its last-frame landmarks / descriptors / predicted poses (extraction stream).
+        The previous step's tracking kernels and result downloads (tracking stream) must have drained first."""
+        lib = self.lib
+        if self.track_ctx is not self.ctx:
+            self.ctx.wait(self.track_ctx)
+        self.ctx._check(lib.plp_dev_upload_async(self.ctx.handle, self.d_imgs.ptr, self._pin_imgs.ptr,
+                                                 C.c_size_t(self._pin_imgs.nbytes)))
+        for dbuf, pbuf in zip(self._last_bufs, self._last_pinned):
+            self.ctx._check(lib.plp_dev_upload_async(self.ctx.handle, dbuf.ptr, pbuf.ptr, C.c_size_t(pbuf.nbytes)))
+
+    def download_outputs_async(self):
+        """D2H of everything the host-side data::frame needs from this step: keypoints, descriptors, counts, the
+        landmark index kept on every keypoint, pose, valid / inlier counts (tracking stream, after track())."""
+        cx = self.track_ctx
+        for _, dbuf, off, nbytes in self._out_layout:
+            cx._check(self.lib.plp_dev_download_async(cx.handle, C.c_void_p(self._pin_out.ptr.value + off), dbuf.ptr,
+                                                      C.c_size_t(nbytes)))
+
+    def host_results(self):
+        """Views into the pinned result block (valid after the tracking stream has been synchronised)."""
+        b, out = self._io_batch, {}
+        shapes = {"kp": (KP_DTYPE, (b, self.cap)), "desc": (np.uint8, (b, self.cap, 32)), "n_kp": (np.int32, (b,)),
+                  "status": (np.int32, (b,)), "matched": (np.int32, (b, self.cap)), "pose": (np.float64, (b, 4, 4)),
+                  "num_valid": (np.int32, (b,)), "n_inliers": (np.int32, (b,)), "lm_iters": (np.int32, (b,))}
+        for name, _, off, _ in self._out_layout:
+            dt, shp = shapes[name]
+            out[name] = self._pin_out.view(dt, shp, off)
+        return out
 
     # -- the hot path (no host synchronisation) ---------------------------------------------------------
     def extract(self, batch: int):

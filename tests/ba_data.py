@@ -125,7 +125,7 @@ def oracle_global_ba(orc, prob: BAProblem, num_iter=20, use_huber_kernel=True) -
 
 
 def make_ba_problem(seed, n_local=20, n_fixed=10, n_points=4000, n_lines=800, n_plane_pts=200, stereo=False,
-                    outlier_frac=0.05, pose_sigma=(0.01, 0.03), point_sigma=0.05):
+                    outlier_frac=0.05, pose_sigma=(0.01, 0.03), point_sigma=0.05, fast=False):
     """Config 4: local keyframes on a 4 m arc looking at a landmark cloud, fixed keyframes further along the arc,
     k ~ U{3..9} observations per landmark, octave-scaled pixel noise, 5 % outlier observations, perturbed poses
     and points; 3 planes own `n_plane_pts` of the points."""
@@ -164,6 +164,13 @@ def make_ba_problem(seed, n_local=20, n_fixed=10, n_points=4000, n_lines=800, n_
             X[sel, ax] = -planes[pi, 3]
 
     def observe(Xw_list_fn, n_lm):
+        if fast:  # vectorised draw for the scaled-up problems (another random stream than the loop below)
+            k = np.minimum(rng.integers(3, 10, n_lm), n_kf)
+            pick = np.argsort(rng.random((n_lm, n_kf)), axis=1)[:, :9]
+            pick = np.where(np.arange(pick.shape[1])[None, :] < k[:, None], pick, n_kf + 1)
+            pick.sort(axis=1)
+            sel = pick < n_kf
+            return pick[sel].astype(np.int32), np.repeat(np.arange(n_lm), sel.sum(1)).astype(np.int32)
         kfs, lms = [], []
         for l in range(n_lm):
             k = int(rng.integers(3, 10))

@@ -763,3 +763,49 @@ def _stereo_compute(self, res_left, res_right, scale_factors, inv_scale_factors,
 
 
 Oracle.stereo_compute = _stereo_compute
+
+
+# ======================================================================== native thread pool (oracle/frontend_mt.cc)
+def _host_cpus(self):
+    return int(self.lib.orc_host_cpus())
+
+
+def _frontend_track_batch(self, p, grid, cam, imgs, lasts, pose_pred, pose_last, margin=20.0, threads=1, pin=True):
+    """extract -> match_current_and_last_frames (+ widened retry) -> pose_optimizer -> discard_outliers for a batch of
+    independent frames on `threads` native threads.  lasts[b]: dict(pos_w, octave, angle, desc, valid|None)."""
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    B, rows, cols = imgs.shape
+    offs = np.zeros(B + 1, np.int32)
+    offs[1:] = np.cumsum([len(l["octave"]) for l in lasts])
+    cat = lambda k, dt: np.ascontiguousarray(np.concatenate([np.asarray(l[k], dt) for l in lasts]))
+    pos, octv, ang, desc = cat("pos_w", np.float64), cat("octave", np.int32), cat("angle", np.float32), cat("desc", np.uint8)
+    valid = np.ascontiguousarray(np.concatenate([np.asarray(l["valid"] if l.get("valid") is not None else
+                                                            np.ones(len(l["octave"]), np.uint8), np.uint8) for l in lasts]))
+    pp = np.ascontiguousarray(np.asarray(pose_pred, np.float64).reshape(B, 16))
+    pl = np.ascontiguousarray(np.asarray(pose_last, np.float64).reshape(B, 16))
+    pose = np.zeros((B, 16), np.float64)
+    n_inl, n_valid, n_kp = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    sec = C.c_double(0)
+    g, c = as_grid(grid), as_camera(cam)
+    P = lambda a: a.ctypes.data_as(_P)
+    self.lib.orc_frontend_track_batch(C.byref(p), C.byref(g), C.byref(c), P(imgs), C.c_int(B), C.c_int(rows), C.c_int(cols),
+                                      P(pos), P(octv), P(ang), P(desc), P(valid), P(offs), P(pp), P(pl), C.c_float(margin),
+                                      C.c_int(threads), C.c_int(1 if pin else 0), P(pose), P(n_inl), P(n_valid), P(n_kp),
+                                      C.byref(sec))
+    return dict(pose=pose.reshape(B, 4, 4), n_inliers=n_inl, num_valid=n_valid, n_kp=n_kp, seconds=sec.value)
+
+
+def _line_extract_batch_mt(self, imgs, threads=1, pin=True, mode=LSD_DET):
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    B, rows, cols = imgs.shape
+    n = np.zeros(B, np.int32)
+    sec = C.c_double(0)
+    cfg = OLsdCfg(*mode)
+    self.lib.orc_line_extract_batch_mt(imgs.ctypes.data_as(_P), C.c_int(B), C.c_int(rows), C.c_int(cols), C.byref(cfg),
+                                       C.c_int(threads), C.c_int(1 if pin else 0), n.ctypes.data_as(_P), C.byref(sec))
+    return n, sec.value
+
+
+Oracle.host_cpus = _host_cpus
+Oracle.frontend_track_batch = _frontend_track_batch
+Oracle.line_extract_batch_mt = _line_extract_batch_mt

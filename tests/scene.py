@@ -12,12 +12,15 @@ Z0 = 4.0  # plane depth [m]
 
 class PlanarSequence:
     def __init__(self, seed=1234, n_frames=9, rows=synth.ROWS, cols=synth.COLS, fx=synth.FX, fy=synth.FY,
-                 cx=synth.CX, cy=synth.CY, tex_scale=1.6):
+                 cx=synth.CX, cy=synth.CY, tex_scale=1.6, plp=False):
         import cv2
         self.rows, self.cols = rows, cols
         self.K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
         th, tw = int(rows * tex_scale), int(cols * tex_scale)
-        self.tex = synth.make_texture(seed, th, tw, n_rect=int(400 * tex_scale ** 2), n_blob=int(2000 * tex_scale ** 2))
+        if plp:  # point- and line-rich texture (~1000 ORB + ~200 keylines per frame)
+            self.tex = synth.make_plp_texture(seed, th, tw)
+        else:
+            self.tex = synth.make_texture(seed, th, tw, n_rect=int(400 * tex_scale ** 2), n_blob=int(2000 * tex_scale ** 2))
         s = fx / Z0  # texture pixels per metre: ~1 texture px per image px at depth Z0
         self.A = np.array([[s, 0, tw / 2.0], [0, s, th / 2.0], [0, 0, 1.0]])
         rng = np.random.default_rng(seed + 1)

@@ -334,12 +334,12 @@ def make_line_image(seed, h=480, w=640, n_patch=44, noise=2.0):
     return np.clip(np.round(img), 0, 255).astype(np.uint8)
 
 
-def make_stereo_pair(seed, h=480, w=752, bf=47.906, n_bands=6):
+def make_stereo_pair(seed, h=480, w=752, bf=47.906, n_bands=6, plp=False):
     """Rectified stereo pair: the right image is the left texture shifted by a per-row-band
     disparity bf / depth (sub-pixel, bilinear) plus independent sensor noise."""
     import cv2
     rng = np.random.default_rng(seed)
-    left = make_texture(seed, h, w)
+    left = make_plp_texture(seed, h, w) if plp else make_texture(seed, h, w)
     depths = rng.uniform(1.5, 12.0, n_bands)
     right = np.zeros_like(left)
     edges = np.linspace(0, h, n_bands + 1).astype(int)
@@ -412,3 +412,39 @@ def make_triangulation_scene(seed, n=1200, stereo=False, num_levels=8, n_nodes=9
     ep = T2[:3, :3] @ c1 + T2[:3, 3]
     ep = ep / np.linalg.norm(ep)
     return kf1, kf2, fv1, fv2, E12, ep
+
+
+def make_plp_texture(seed, h=480, w=640, tile=(80, 106), cover=0.95, noise=2.0):
+    """Point-AND-line-rich scene for the full PLP front end (BASELINE north_star: ~1000 ORB + ~200 line features per
+    640x480 frame): the corner-rich texture of make_texture with non-overlapping tiles of parallel stripes (facades,
+    shelves, floor boards) painted over `cover` of the tile grid.  LSD works at half resolution and keeps segments
+    >= 60 px, so ~200 of them need about two thirds of the image as edges ~100 px long and >= 12 px apart: the stripes run
+    along the long side of their tile (+- 0.1 rad), which makes every edge a full tile long."""
+    import cv2
+    rng = np.random.default_rng(seed + 7919)
+    img = make_texture(seed, h, w).astype(np.float32)
+    th, tw = tile
+    ny, nx = max(1, h // th), max(1, w // tw)
+    cells = [(j, i) for j in range(ny) for i in range(nx)]
+    rng.shuffle(cells)
+    for (j, i) in cells[:int(round(cover * len(cells)))]:
+        y0, x0 = j * h // ny, i * w // nx
+        y1, x1 = (j + 1) * h // ny, (i + 1) * w // nx
+        hh, ww = y1 - y0, x1 - x0
+        pad = 6
+        yy, xx = np.mgrid[0:hh, 0:ww].astype(np.float32)
+        ang = (np.pi / 2 if ww >= hh else 0.0) + rng.uniform(-0.1, 0.1)
+        period = rng.uniform(12, 15)
+        phase = rng.uniform(0, period)
+        u = (xx - ww / 2) * np.cos(ang) + (yy - hh / 2) * np.sin(ang) + phase
+        k = np.floor(u / period).astype(np.int64)
+        levels = rng.uniform(15, 240, 64)
+        levels[1::2] = np.clip(levels[::2] + rng.choice([-1, 1], 32) * rng.uniform(45, 110, 32), 5, 250)
+        patch = levels[np.mod(k, 64)].astype(np.float32)
+        m = np.zeros((hh, ww), np.float32)
+        m[pad:hh - pad, pad:ww - pad] = 1.0
+        m = cv2.GaussianBlur(m, (0, 0), 1.0)
+        img[y0:y1, x0:x1] = img[y0:y1, x0:x1] * (1 - m) + patch * m
+    img = cv2.GaussianBlur(img, (0, 0), 0.7)
+    img += rng.normal(0, noise, (h, w)).astype(np.float32)
+    return np.clip(np.round(img), 0, 255).astype(np.uint8)
