@@ -10,12 +10,14 @@
 // Query q only depends on queries < q, so after round r the first r queries are final and any
 // fixed point equals the sequential result; conflicts are rare so 2-4 rounds suffice in practice.
 // Candidate traversal order (cell-x, cell-y, insertion -- data/common.cc:275-309) decides '<' ties:
-// keypoints are rank-sorted by (cell_x, cell_y, index) into shared memory once per frame, so a
-// query scans one contiguous span [col_start[min_cx], col_start[max_cx+1]) in exactly the
-// reference's order.  Descriptors live in shared memory as 2 x uint4; distances are 8 x __popc.
+// keypoints are counting-sorted by (cell_x, cell_y, index) into shared memory once per frame, so a
+// query scans one contiguous span per grid column of its window in exactly the reference's order
+// (the window matcher lives in point_match_kernels.cuh).  Descriptors live in shared memory as
+// 2 x uint4; distances are 8 x __popc.
 //
 // Compiled with -fmad=false: float/double expressions must round exactly like the oracle.
 #include "match_kernels.cuh"
+#include "point_match_kernels.cuh"
 #include "detmath.h"
 #include "pack.cuh"
 
@@ -204,355 +206,6 @@ __global__ void project_lines_kernel(const ProjectJob *__restrict__ jobs, plp_ca
     J.qmin[i] = mn;
     J.qmax[i] = mx;
     J.qvalid[i] = valid ? 1 : 0;
-}
-
-// ---------------------------------------------------------------------------------------
-// window matcher over the 64x48 keypoint grid
-// ---------------------------------------------------------------------------------------
-struct PointSmem {
-    uint4 *desc;    // 2 per keypoint, sorted order
-    float *x, *y, *xr;
-    int *meta;      // octave (bits 0-7, signed) | cell_y (8-15) | claimed (16)
-    int *orig;      // original index of the keypoint at each sorted position
-    int *owner_a, *owner_b;
-    int *col_start;  // cell start table: num_cols * num_rows + 2
-    int *hist;       // kHistLen
-    uint8_t *bin_valid;
-    uint8_t *colchg;  // per grid column: did an owner change there in the last round?
-    int *flags;  // [0] changed, [1] num accepted, [2] num invalid, [3] num in grid
-};
-
-__device__ __forceinline__ PointSmem carve_point_smem(uint8_t *base, int cap, int num_cols, int num_rows) {
-    PointSmem s;
-    s.desc = reinterpret_cast<uint4 *>(base);
-    base += (size_t)cap * 32;
-    s.x = reinterpret_cast<float *>(base);
-    base += (size_t)cap * 4;
-    s.y = reinterpret_cast<float *>(base);
-    base += (size_t)cap * 4;
-    s.xr = reinterpret_cast<float *>(base);
-    base += (size_t)cap * 4;
-    s.meta = reinterpret_cast<int *>(base);
-    base += (size_t)cap * 4;
-    s.orig = reinterpret_cast<int *>(base);
-    base += (size_t)cap * 4;
-    s.owner_a = reinterpret_cast<int *>(base);
-    base += (size_t)cap * 4;
-    s.owner_b = reinterpret_cast<int *>(base);
-    base += (size_t)cap * 4;
-    s.col_start = reinterpret_cast<int *>(base);
-    base += (size_t)(num_cols * num_rows + 2) * 4;
-    s.hist = reinterpret_cast<int *>(base);
-    base += kHistLen * 4;
-    s.flags = reinterpret_cast<int *>(base);
-    base += 4 * 4;
-    s.bin_valid = base;
-    s.colchg = base + 32;
-    return s;
-}
-
-static size_t point_smem_bytes(int cap, int num_cols, int num_rows) {
-    return (size_t)cap * (32 + 7 * 4) + (size_t)(num_cols * num_rows + 2) * 4 + kHistLen * 4 + 16 + 32 + (size_t)(num_cols + 16);
-}
-
-__global__ void __launch_bounds__(kThreads, 1)
-    point_match_kernel(const PointMatchJob *__restrict__ jobs, plp_grid grid, int cap, int ratio_test,
-                       float lowe_ratio, int check_orientation) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    const PointMatchJob &J = jobs[blockIdx.x];
-    if (J.m < 0) return;  // job disabled (e.g. the widened-margin retry is not needed for this frame)
-    PointSmem S = carve_point_smem(smem_raw, cap, grid.num_cols, grid.num_rows);
-    const int tid = threadIdx.x;
-    if (J.n > cap) {  // more keypoints than the shared-memory tables hold: report "no matches" loudly (0xffffffff)
-        if (J.matched_out)
-            for (int i = tid; i < J.n; i += kThreads) J.matched_out[i] = -1;
-        if (J.best_idx_out)
-            for (int q = tid; q < J.m; q += kThreads) J.best_idx_out[q] = -1;
-        if (tid == 0 && J.num_matches) *J.num_matches = 0xffffffffu;
-        return;
-    }
-    const int n = J.n, m = J.m;
-    const int cells = grid.num_cols * grid.num_rows;
-
-    // ---- 1. cell key of every keypoint (data/common.h:104-109); owner_a doubles as key buffer
-    int *key = S.owner_a;
-    for (int i = tid; i < n; i += kThreads) {
-        const float px = J.x[i], py = J.y[i];
-        const int cx = cv_floor((double)(px - grid.min_x) * grid.inv_cell_width);
-        const int cy = cv_floor((double)(py - grid.min_y) * grid.inv_cell_height);
-        const bool in = (0 <= cx && cx < grid.num_cols && 0 <= cy && cy < grid.num_rows);
-        key[i] = in ? cx * grid.num_rows + cy : cells;  // out-of-grid keypoints sort last and are never visited
-    }
-    if (tid < 4) S.flags[tid] = 0;
-    __syncthreads();
-
-    // ---- 2. stable rank sort by (key, index): reproduces the traversal order of
-    //         get_keypoints_in_cell (data/common.cc:275-309)
-    for (int i = tid; i < n; i += kThreads) {
-        const int ki = key[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            const int kj = key[j];
-            rank += (kj < ki) || (kj == ki && j < i);
-        }
-        S.orig[rank] = i;
-        if (ki < cells) atomicAdd(&S.flags[3], 1);
-    }
-    __syncthreads();
-    const int n_in = S.flags[3];
-
-    // ---- 3. gather sorted keypoint data into shared memory
-    for (int p = tid; p < n_in; p += kThreads) {
-        const int i = S.orig[p];
-        const int k = key[i];
-        const int cy = k % grid.num_rows;
-        S.x[p] = J.x[i];
-        S.y[p] = J.y[i];
-        S.xr[p] = J.x_right ? J.x_right[i] : -1.0f;
-        const int cl = J.claimed ? (J.claimed[i] != 0) : 0;
-        S.meta[p] = (J.octave[i] & 0xff) | (cy << 8) | (cl << 16) | ((k / grid.num_rows) << 17);
-        uint4 d0, d1;
-        load_desc(J.desc + 32 * (size_t)i, d0, d1);
-        S.desc[2 * p] = d0;
-        S.desc[2 * p + 1] = d1;
-    }
-    __syncthreads();  // key[] (owner_a) no longer needed after this point
-    // cell start table over the sorted keypoints: cell_start[k] = first sorted position whose cell key >= k
-    // (k = cell_x * num_rows + cell_y), so the cells [min_cy, max_cy] of one grid column are ONE contiguous span
-    for (int p = tid; p <= n_in; p += kThreads) {
-        const int kp = p < n_in ? ((S.meta[p] >> 17) & 0x3fff) * grid.num_rows + ((S.meta[p] >> 8) & 0xff) : cells;
-        const int kprev = p > 0 ? ((S.meta[p - 1] >> 17) & 0x3fff) * grid.num_rows + ((S.meta[p - 1] >> 8) & 0xff) : -1;
-        for (int k = kprev + 1; k <= kp; ++k) S.col_start[k] = p;
-    }
-    __syncthreads();
-
-    int *owner_prev = S.owner_a, *owner_next = S.owner_b;
-    for (int p = tid; p < n_in; p += kThreads) {
-        owner_prev[p] = 0x7fffffff;
-        owner_next[p] = 0x7fffffff;
-    }
-    __syncthreads();
-
-    // ---- 4. the sequential greedy assignment, in parallel
-    // One WARP per query: lanes stride the candidates of the window's cells (per grid column the cells
-    // [min_cy, max_cy] are one contiguous span of the sorted arrays), each lane keeps its two smallest keys
-    // key = (distance << 40 | sorted position << 8 | octave), i.e. top-2 by (distance, traversal order) -- exactly
-    // the reference's strict-'<' scan -- and the 32 partial top-2 lists are merged with shuffles.
-    const int lane = tid & 31, warp = tid >> 5, nwarps = kThreads / 32;
-    // scan(q, owner, has_floor, floor): top-2 keys among q's window candidates that are not pre-claimed, not owned
-    // by a smaller query (when `owner` is given) and strictly after `floor` in (distance, order) (when has_floor)
-    auto scan = [&](int q, const int *owner, bool has_floor, unsigned long long floor, unsigned long long &k1,
-                    unsigned long long &k2) {
-        k1 = ~0ull;
-        k2 = ~0ull;
-        const float ref_x = J.qx[q], ref_y = J.qy[q], r = J.qradius[q];
-        const int min_level = J.qmin[q], max_level = J.qmax[q];
-        // data/common.cc:249-272
-        const int min_cx = max(0, cv_floor((double)(ref_x - grid.min_x - r) * grid.inv_cell_width));
-        const int max_cx = min(grid.num_cols - 1, cv_ceil((double)(ref_x - grid.min_x + r) * grid.inv_cell_width));
-        const int min_cy = max(0, cv_floor((double)(ref_y - grid.min_y - r) * grid.inv_cell_height));
-        const int max_cy = min(grid.num_rows - 1, cv_ceil((double)(ref_y - grid.min_y + r) * grid.inv_cell_height));
-        if (min_cx < grid.num_cols && max_cx >= 0 && min_cy < grid.num_rows && max_cy >= 0) {
-            const bool check_level = (0 < min_level) || (0 <= max_level);
-            const float qxr = J.qxr ? J.qxr[q] : 0.0f;
-            uint4 q0, q1;
-            load_desc(J.qdesc + 32 * (size_t)q, q0, q1);
-            for (int c = min_cx; c <= max_cx; ++c) {
-                const int p_begin = S.col_start[c * grid.num_rows + min_cy];
-                const int p_end = S.col_start[c * grid.num_rows + max_cy + 1];
-                for (int p = p_begin + lane; p < p_end; p += 32) {
-                    const int meta = S.meta[p];
-                    const int oct = (int)(signed char)(meta & 0xff);
-                    if (check_level) {
-                        if (oct < min_level) continue;
-                        if (0 <= max_level && max_level < oct) continue;
-                    }
-                    const float dx = S.x[p] - ref_x, dy = S.y[p] - ref_y;
-                    if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
-                    if ((meta >> 16) & 1) continue;          // already has a landmark with observations
-                    if (owner && owner[p] < q) continue;     // claimed by an earlier query
-                    const float xr = S.xr[p];
-                    if (0 < xr) {  // projection.cc:76-83 / 310-317
-                        const float err = fabsf(qxr - xr);
-                        if (r < err) continue;
-                    }
-                    const unsigned d = (unsigned)hamming256(q0, q1, S.desc[2 * p], S.desc[2 * p + 1]);
-                    if (d >= PLP_MAX_HAMMING_DIST) continue;  // can never replace the initial best / second
-                    const unsigned long long key =
-                        ((unsigned long long)d << 40) | ((unsigned long long)(unsigned)p << 8) | (unsigned)(oct & 0xff);
-                    if (has_floor && key <= floor) continue;
-                    if (key < k1) {
-                        k2 = k1;
-                        k1 = key;
-                    } else if (key < k2) {
-                        k2 = key;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o);
-            const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, k2, o);
-            const unsigned long long lo = k1 < o1 ? k1 : o1, hi = k1 < o1 ? o1 : k1;
-            const unsigned long long s2 = k2 < o2 ? k2 : o2;
-            k1 = lo;
-            k2 = hi < s2 ? hi : s2;
-        }
-    };
-
-    if (!ratio_test) {
-        // No ratio test (match_current_and_last_frames): "best unclaimed candidate, queries served in index order"
-        // is a serial dictatorship = the unique stable matching when every keypoint prefers the smallest query
-        // index.  Deferred acceptance reaches it with work proportional to the number of conflicts: every query
-        // proposes to its best candidate; a keypoint keeps its smallest proposer; only bumped queries re-propose
-        // to their next candidate in (distance, order).
-        int *owner = owner_prev;  // min proposer so far; never reset
-        const unsigned hamm_thr = J.hamm_thr_p1 ? J.hamm_thr_p1 - 1u : (unsigned)PLP_HAMMING_DIST_THR_HIGH;
-        for (int q = warp; q < m; q += nwarps) {
-            int choice = -1;
-            if (J.qvalid ? (J.qvalid[q] != 0) : true) {
-                unsigned long long k1, k2;
-                scan(q, nullptr, false, 0ull, k1, k2);
-                if (k1 != ~0ull && (unsigned)(k1 >> 40) <= hamm_thr) choice = (int)((k1 >> 8) & 0xffffffffull);
-            }
-            if (lane == 0) {
-                J.choice[q] = choice;
-                if (choice >= 0) atomicMin(&owner[choice], q);
-            }
-        }
-        __syncthreads();
-        for (int round = 0; round <= m; ++round) {
-            for (int q = warp; q < m; q += nwarps) {
-                const int c = J.choice[q];
-                if (c < 0 || owner[c] == q) continue;  // still holding its proposal (or exhausted)
-                // bumped by a smaller query: next candidate after the lost one
-                uint4 q0, q1;
-                load_desc(J.qdesc + 32 * (size_t)q, q0, q1);
-                const unsigned dc = (unsigned)hamming256(q0, q1, S.desc[2 * c], S.desc[2 * c + 1]);
-                const unsigned long long floor =
-                    ((unsigned long long)dc << 40) | ((unsigned long long)(unsigned)c << 8) | (unsigned)(S.meta[c] & 0xff);
-                unsigned long long k1, k2;
-                scan(q, nullptr, true, floor, k1, k2);
-                int choice = -1;
-                if (k1 != ~0ull && (unsigned)(k1 >> 40) <= hamm_thr) choice = (int)((k1 >> 8) & 0xffffffffull);
-                if (lane == 0) {
-                    J.choice[q] = choice;
-                    if (choice >= 0) atomicMin(&owner[choice], q);
-                    S.flags[0] = 1;
-                }
-            }
-            __syncthreads();
-            const int changed = S.flags[0];
-            __syncthreads();
-            if (!changed) break;
-            if (tid == 0) S.flags[0] = 0;
-            __syncthreads();
-        }
-    } else {
-        // Ratio test (match_frame_and_landmarks): acceptance depends on the second-best AVAILABLE candidate, so we
-        // iterate choice[q] = f(claims of queries < q) to its (unique) fixed point.
-        for (int round = 0; round <= m; ++round) {
-            for (int q = warp; q < m; q += nwarps) {
-                int choice = -1;
-                const bool valid = J.qvalid ? (J.qvalid[q] != 0) : true;
-                if (valid) {
-                    if (round > 0) {
-                        // a query's result depends only on the owners inside its column span: if none of them changed
-                        // in the previous round the previous choice stands (it only re-issues its claim)
-                        const float ref_x = J.qx[q], r = J.qradius[q];
-                        const int min_cx = max(0, cv_floor((double)(ref_x - grid.min_x - r) * grid.inv_cell_width));
-                        const int max_cx = min(grid.num_cols - 1, cv_ceil((double)(ref_x - grid.min_x + r) * grid.inv_cell_width));
-                        bool dirty = false;
-                        for (int c = min_cx + lane; c <= max_cx; c += 32) dirty = dirty || S.colchg[c];
-                        if (!__any_sync(0xffffffffu, dirty)) {
-                            if (lane == 0) {
-                                choice = J.choice[q];
-                                if (choice >= 0) atomicMin(&owner_next[choice], q);
-                            }
-                            continue;
-                        }
-                    }
-                    unsigned long long k1, k2;
-                    scan(q, owner_prev, false, 0ull, k1, k2);
-                    if (k1 != ~0ull) {
-                        const unsigned best = (unsigned)(k1 >> 40);
-                        const int best_p = (int)((k1 >> 8) & 0xffffffffull);
-                        const int best_lvl = (int)(signed char)(k1 & 0xff);
-                        const unsigned second = k2 != ~0ull ? (unsigned)(k2 >> 40) : (unsigned)PLP_MAX_HAMMING_DIST;
-                        const int second_lvl = k2 != ~0ull ? (int)(signed char)(k2 & 0xff) : -1;
-                        if (best <= PLP_HAMMING_DIST_THR_HIGH) {
-                            bool ok = true;
-                            if (best_lvl == second_lvl && (float)best > lowe_ratio * (float)second) ok = false;
-                            if (ok) choice = best_p;
-                        }
-                    }
-                }
-                if (lane == 0) {
-                    J.choice[q] = choice;
-                    if (choice >= 0) atomicMin(&owner_next[choice], q);
-                }
-            }
-            __syncthreads();
-            for (int c = tid; c < grid.num_cols; c += kThreads) S.colchg[c] = 0;
-            __syncthreads();
-            for (int p = tid; p < n_in; p += kThreads)
-                if (owner_next[p] != owner_prev[p]) {
-                    S.flags[0] = 1;
-                    S.colchg[(S.meta[p] >> 17) & 0x3fff] = 1;
-                }
-            __syncthreads();
-            const int changed = S.flags[0];
-            __syncthreads();
-            if (!changed) break;
-            if (tid == 0) S.flags[0] = 0;
-            int *t = owner_prev;
-            owner_prev = owner_next;
-            owner_next = t;
-            for (int p = tid; p < n_in; p += kThreads) owner_next[p] = 0x7fffffff;
-            __syncthreads();
-        }
-    }
-    // choice[] now holds the sequential result
-
-    // ---- 5. orientation histogram (projection.cc:337-354) and outputs
-    for (int b = tid; b < kHistLen; b += kThreads) S.hist[b] = 0;
-    if (J.matched_out)
-        for (int i = tid; i < n; i += kThreads) J.matched_out[i] = -1;
-    __syncthreads();
-    const bool do_angle = check_orientation && J.qangle != nullptr && J.angle != nullptr;
-    for (int q = tid; q < m; q += kThreads) {
-        const int p = J.choice[q];
-        if (p < 0) continue;
-        atomicAdd(&S.flags[1], 1);
-        if (do_angle) atomicAdd(&S.hist[angle_bin(J.qangle[q] - J.angle[S.orig[p]])], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (do_angle)
-            rank_bins(S.hist, S.bin_valid);
-        else
-            for (int b = 0; b < kHistLen; ++b) S.bin_valid[b] = 1;
-    }
-    __syncthreads();
-    for (int q = tid; q < m; q += kThreads) {
-        const int p = J.choice[q];
-        int out = -1;
-        if (p >= 0) {
-            const int i = S.orig[p];
-            bool keep = true;
-            if (do_angle) keep = S.bin_valid[angle_bin(J.qangle[q] - J.angle[i])] != 0;
-            if (keep) {
-                out = i;
-                if (J.matched_out) J.matched_out[i] = q;
-            } else {
-                atomicAdd(&S.flags[2], 1);
-            }
-        }
-        if (J.best_idx_out) J.best_idx_out[q] = out;
-    }
-    __syncthreads();
-    if (tid == 0 && J.num_matches) *J.num_matches = (uint32_t)(S.flags[1] - S.flags[2]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -971,9 +624,10 @@ plp_status launch_point_match(plp_ctx *ctx, const PointMatchJob *d_jobs, int num
         return PLP_ERR_INVALID;
     }
     const int cap = max_n < 64 ? 64 : ((max_n + 63) / 64) * 64;
-    const size_t smem = point_smem_bytes(cap, grid.num_cols, grid.num_rows);
+    const size_t smem = pm::point_smem_bytes(cap, grid.num_cols, grid.num_rows);
+    using pm::point_match_kernel;
     PLP_SMEM_OPTIN(point_match_kernel, smem);
-    PLP_LAUNCH(ctx, point_match_kernel, num_jobs, kThreads, smem, d_jobs, grid, cap, ratio_test, lowe_ratio,
+    PLP_LAUNCH(ctx, point_match_kernel, num_jobs, pm::kThreads, smem, d_jobs, grid, cap, ratio_test, lowe_ratio,
                check_orientation);
     PLP_CHECK_LAUNCH();
     return PLP_OK;

@@ -7,7 +7,10 @@
 //   - SE3Quat::exp: Rodrigues for R, V matrix for the translation, small-angle branch at theta < 1e-5
 //   - error = obs - projection                                   (perspective_pose_opt_edge.h:55-60)
 #pragma once
+#ifndef PLP_CTA_EMU
 #include <cuda_runtime.h>
+#endif
+#include <math.h>
 
 namespace plp {
 namespace se3 {

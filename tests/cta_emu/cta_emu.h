@@ -34,6 +34,12 @@ static pthread_barrier_t g_cta_barrier;
 static inline void __syncthreads() { pthread_barrier_wait(&g_cta_barrier); }
 static inline int atomicAdd(int *a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicOr(unsigned *a, unsigned v) { return __atomic_fetch_or(a, v, __ATOMIC_SEQ_CST); }
+static inline int atomicMin(int *a, int v) {
+    int old = __atomic_load_n(a, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+    }
+    return old;
+}
 
 // ---- vector types / scalar built-ins the kernels use
 struct uint4 {
