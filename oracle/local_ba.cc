@@ -14,6 +14,9 @@ using namespace g2o_lite;
 
 namespace {
 
+// per-try trace of the most recent solve on this thread: (lambda used, rho, accepted) -- read by tests/test_ba_oracle.py
+thread_local std::vector<double> g_lm_trace;
+
 // ---- optimize/g2o/line3d.h:57-207 -------------------------------------------------------------------------
 struct Line3D {
     double v[6];  // (w = moment, d = direction)
@@ -519,6 +522,9 @@ struct Solver {
                 scale += 1e-3;
                 rho /= scale;
                 if (lm_tries) ++*lm_tries;
+                g_lm_trace.push_back(lambda);
+                g_lm_trace.push_back(rho);
+                g_lm_trace.push_back((rho > 0 && std::isfinite(temp_chi)) ? 1.0 : 0.0);
                 if (rho > 0 && std::isfinite(temp_chi)) {
                     double alpha = 1. - std::pow((2 * rho - 1), 3);
                     alpha = std::min(alpha, 2. / 3.);
@@ -547,9 +553,16 @@ struct Solver {
 
 }  // namespace
 
+extern "C" int orc_debug_lm_trace(double *out, int cap) {
+    const int n = (int)g_lm_trace.size() / 3;
+    for (int i = 0; i < 3 * std::min(n, cap); ++i) out[i] = g_lm_trace[i];
+    return n;
+}
+
 extern "C" int orc_local_ba(const orc_ba_problem *p, int num_first_iter, int num_second_iter,
                             const volatile uint8_t *force_stop, orc_ba_result *r) {
     const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
+    g_lm_trace.clear();
     Solver S;
     S.cam = {p->fx, p->fy, p->cx, p->cy, p->focal_x_baseline};
     S.n_kf = p->n_kf;
@@ -641,6 +654,7 @@ extern "C" int orc_local_ba(const orc_ba_problem *p, int num_first_iter, int num
 extern "C" int orc_global_ba(const orc_ba_problem *p, int num_iter, int use_huber_kernel,
                             const volatile uint8_t *force_stop, orc_ba_result *r) {
     const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
+    g_lm_trace.clear();
     Solver S;
     S.cam = {p->fx, p->fy, p->cx, p->cy, p->focal_x_baseline};
     S.n_kf = p->n_kf;
@@ -703,4 +717,39 @@ extern "C" int orc_global_ba(const orc_ba_problem *p, int num_iter, int use_hube
     S.compute_active_errors();
     r->final_chi2 = S.active_robust_chi2();
     return r->iters_first;
+}
+
+// ---- parity taps for tests/test_ba_oracle.py: the edge algebra this file and pose_opt.cc build on --------------------
+extern "C" void orc_debug_point_edge(const double *cam5 /*fx fy cx cy bf*/, const double *T_cw, const double *X,
+                                     const double *obs3, double *e3, double *Jpose18, double *Jlm9) {
+    const Cam c{cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+    const SE3 P = se3_from_matrix(T_cw);
+    const bool stereo = !(obs3[2] < 0);
+    Vec3 pc;
+    e3[2] = 0;
+    point_error(c, P.R(), P.t, Vec3{{X[0], X[1], X[2]}}, obs3, stereo, e3, &pc);
+    for (int i = 0; i < 18; ++i) Jpose18[i] = 0;
+    for (int i = 0; i < 9; ++i) Jlm9[i] = 0;
+    point_jac_pose(c, pc, stereo, Jpose18);
+    point_jac_landmark(c, P.R(), pc, stereo, Jlm9);
+}
+extern "C" void orc_debug_se3_oplus(const double *T_cw, const double *u6, double *T_out) {
+    se3_to_matrix(se3_oplus(se3_from_matrix(T_cw), u6), T_out);
+}
+extern "C" void orc_debug_line_oplus(const double *L6, const double *v4, double *out6) {
+    Line3D l;
+    for (int k = 0; k < 6; ++k) l.v[k] = L6[k];
+    const Line3D r = line_oplus(l, v4);
+    for (int k = 0; k < 6; ++k) out6[k] = r.v[k];
+}
+extern "C" void orc_debug_line_error(const double *cam5, const double *T_cw, const double *L6, const double *obs4, double *e2) {
+    const Cam c{cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+    const SE3 P = se3_from_matrix(T_cw);
+    line_error(c, P.R(), P.t, L6, obs4, e2);
+}
+extern "C" int orc_debug_line_depth_positive(const double *cam5, const double *T_cw, const double *L6, const double *obs4) {
+    const Cam c{cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+    Line3D l;
+    for (int k = 0; k < 6; ++k) l.v[k] = L6[k];
+    return line_depth_positive(c, se3_from_matrix(T_cw), l, obs4) ? 1 : 0;
 }

@@ -15,6 +15,7 @@
 //                             Gaussian in smem -> 256 steered comparisons, one descriptor byte per lane
 // Compiled with -fmad=false: the f32 steering must round exactly like the oracle (no FMA).
 #include "common.cuh"
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #include <stdlib.h>
 #include "brief_pattern.inc"
 
@@ -220,151 +221,6 @@ __device__ __forceinline__ bool masked(const OrbDev &P, unsigned y, unsigned x, 
     return P.mask[(size_t)(int)(y * scale) * P.mask_step + (int)(x * scale)] == 0;
 }
 
-__global__ void __launch_bounds__(256) fast_cells_kernel(OrbDev P) {
-    __shared__ __align__(16) uint8_t tile[kTileRows * kTilePitch];
-    __shared__ __align__(16) uint8_t score[kTileRows * kTilePitch];
-    __shared__ int s_total[2];
-    __shared__ unsigned short s_list[4096];  // tile offsets of the pixels that survive the compass pretest
-    __shared__ int s_nsurv;
-    __shared__ unsigned s_rowbits[128];  // NMS survivors: one 32-bit mask per (tested row, 32-column half)
-    __shared__ int s_rowbase[128];
-    const int b = blockIdx.y, ci = blockIdx.x, tid = threadIdx.x;
-    const CellDesc cell = P.cells[ci];
-    const int l = cell.level;
-    const int w = cell.max_x - cell.min_x, h = cell.max_y - cell.min_y;
-    int *cnt_out = P.cell_cnt + (size_t)b * P.num_cells + ci;
-    uint32_t *buf = P.cell_buf + ((size_t)b * P.num_cells + ci) * kCellCap;
-    const float scale = P.lv[l].scale_factor;
-    bool skip = (w < 7 || h < 7);
-    if (!skip && P.mask) {  // orb_extractor.cc:395-401
-        skip = masked(P, cell.min_y, cell.min_x, scale) || masked(P, cell.max_y, cell.min_x, scale) ||
-               masked(P, cell.min_y, cell.max_x, scale) || masked(P, cell.max_y, cell.max_x, scale);
-    }
-    if (skip) {
-        if (tid == 0) *cnt_out = 0;
-        return;
-    }
-    const uint8_t *img = level_ptr(P, b, l);
-    const int pitch = level_pitch(P, l);
-    const int lane = tid & 31, warp = tid >> 5;
-    // tile load: one warp per row, lanes stride the <= 70 columns (coalesced)
-    for (int y = warp; y < h; y += 8) {
-        const uint8_t *src = img + (size_t)(cell.min_y + y) * pitch + cell.min_x;
-        for (int x = lane; x < w; x += 32) tile[y * kTilePitch + x] = src[x];
-    }
-    for (int idx = tid; idx < kTileRows * kTilePitch / 4; idx += 256) reinterpret_cast<uint32_t *>(score)[idx] = 0;
-    __syncthreads();
-    // tested area: rows 3 .. h-4, columns 3 .. w-4 (<= 64 x 64).  Work mapping everywhere below: one warp per
-    // (row, 32-column half), so no integer division is needed and ballots give row-major ordered bit masks.
-    const int tw = w - 6, th = h - 6;
-    const int halves = tw > 32 ? 2 : 1;
-    // cv::FAST(cell, ini_thr) first; only if the cell yields nothing, again with min_thr (orb_extractor.cc:404-412).
-    // The score of a corner (m - 1) does not depend on the threshold, non-corners score 0 in the NMS buffer.
-    for (int pass = 0; pass < 2; ++pass) {
-        const int thr = pass == 0 ? P.ini_thr : P.min_thr;
-        // phase A (uniform, cheap): compass pretest on every tested pixel, survivors are compacted so that the
-        // expensive arc test below runs on full warps instead of diverging inside them
-        if (tid == 0) s_nsurv = 0;
-        __syncthreads();
-        for (int job = warp; job < th * halves; job += 8) {
-            const int ry = job / halves, hx = job - ry * halves;  // halves is 1 or 2: cheap
-            const int y = 3 + ry, x = 3 + hx * 32 + lane;
-            bool surv = false;
-            if (x < 3 + tw) {
-                score[y * kTilePitch + x] = 0;
-                surv = fast_compass(tile + y * kTilePitch + x, thr);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, surv);
-            int wbase = 0;
-            if (lane == 0 && bal) wbase = atomicAdd(&s_nsurv, __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (surv) s_list[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)(y * kTilePitch + x);
-        }
-        __syncthreads();
-        // phase B: exact arc test / score for the survivors
-        const int nsurv = s_nsurv;
-        for (int i = tid; i < nsurv; i += 256) {
-            const int off = s_list[i];
-            const int m = fast_m(tile + off, thr);
-            if (m > thr) score[off] = (uint8_t)(m - 1);
-        }
-        __syncthreads();
-        // 3x3 non-maximum suppression -> one 32-bit mask per (row, half)
-        bool any_local = false;
-        for (int job = warp; job < th * halves; job += 8) {
-            const int ry = job / halves, hx = job - ry * halves;
-            const int y = 3 + ry, x = 3 + hx * 32 + lane;
-            bool keep = false;
-            if (x < 3 + tw) {
-                const uint8_t *sp = score + y * kTilePitch + x;
-                const int sc = sp[0];
-                if (sc != 0) {
-                    keep = true;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            if (dx == 0 && dy == 0) continue;
-                            keep = keep && (sc > (int)sp[dy * kTilePitch + dx]);
-                        }
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_rowbits[ry * 2 + hx] = bal;
-            any_local = any_local || bal != 0;
-        }
-        const int any = __syncthreads_or(any_local);  // also orders the score-map reads before the next pass
-        if (any || P.min_thr == P.ini_thr) break;
-    }
-    // per-keypoint mask test (orb_extractor.cc:429), then ordered (row-major) compaction
-    if (P.mask) {
-        for (int job = warp; job < th * halves; job += 8) {
-            const int ry = job / halves, hx = job - ry * halves;
-            const int y = 3 + ry, x = 3 + hx * 32 + lane;
-            unsigned bits = s_rowbits[ry * 2 + hx];
-            bool drop = false;
-            if ((bits >> lane) & 1) {
-                const float kx = (float)x + (float)(cell.j * kCellSize), ky = (float)y + (float)(cell.i * kCellSize);
-                drop = masked(P, (unsigned)((float)kPatchRadius + ky), (unsigned)((float)kPatchRadius + kx), scale);
-            }
-            const unsigned dropbal = __ballot_sync(0xffffffffu, drop);
-            if (lane == 0) s_rowbits[ry * 2 + hx] = bits & ~dropbal;
-        }
-        __syncthreads();
-    }
-    // exclusive prefix of the per-(row, half) counts (<= 128 entries) by warp 0
-    if (warp == 0) {
-        int run = 0;
-        const int njobs = th * halves;
-        for (int base = 0; base < njobs; base += 32) {
-            const int jdx = base + lane;
-            const int ry = jdx / halves, hx = jdx - ry * halves;
-            const int c = jdx < njobs ? __popc(s_rowbits[ry * 2 + hx]) : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (jdx < njobs) s_rowbase[jdx] = run + incl - c;
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) s_total[0] = run;
-    }
-    __syncthreads();
-    for (int job = warp; job < th * halves; job += 8) {
-        const int ry = job / halves, hx = job - ry * halves;
-        const int y = 3 + ry, x = 3 + hx * 32 + lane;
-        const unsigned bits = s_rowbits[ry * 2 + hx];
-        if ((bits >> lane) & 1) {
-            const int pos = s_rowbase[job] + __popc(bits & ((1u << lane) - 1));
-            const int sc = score[y * kTilePitch + x];
-            const int lx = x + cell.j * kCellSize, ly = y + cell.i * kCellSize;  // relative to the 19-px border
-            if (pos < kCellCap) buf[pos] = (uint32_t)lx | ((uint32_t)ly << 11) | ((uint32_t)sc << 21);
-        }
-    }
-    if (tid == 0) *cnt_out = min(s_total[0], kCellCap);
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // fast_cells_kernel_v2: same cell semantics, fewer instructions per pixel.
@@ -1220,6 +1076,105 @@ __global__ void __launch_bounds__(256) blur_tiles_kernel(OrbDev P) {
     }
 }
 
+// ---- the same blur with the source tile staged by TMA and the passes on byte / half-word SIMD ---------------------
+// One CTA per 64 x 32 output tile.  (1) ONE bulk tensor copy (cp.async.bulk.tensor.3d, box 80 x 38 x 1 of the
+// (x, y, frame) tensor of the level; the box starts at (x0 - 3, y0 - 3): coordinates need no alignment, out-of-image
+// elements arrive as zeros) completes on an mbarrier -- no per-byte address arithmetic, no loads issued by the SMs.
+// (2) tiles that touch the image border rebuild BORDER_REFLECT_101 inside shared memory (the mirrored pixels are part of
+// the same box).  (3) horizontal pass: a thread makes 4 outputs from 3 words with funnel shifts and DP4A
+// ([18 34 48 56] . bytes + [48 34 18 0] . bytes); (4) vertical pass on the u16 rows; OpenCV's rounding (v + 32768) >> 16.
+struct BlurMaps {
+    CUtensorMap m[kMaxLevels];
+};
+constexpr int kBoxW = 80, kBoxH = kBtH + 6;
+static_assert(kBoxW >= kBtW + 6 && kBoxW % 16 == 0, "TMA box: inner extent a multiple of 16 bytes covering the halo");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) blur_tiles_tma_kernel(const __grid_constant__ BlurMaps M, OrbDev P) {
+    __shared__ __align__(128) uint8_t s_src[kBoxH * kBoxW];
+    __shared__ __align__(16) unsigned short s_h[kBoxH * kBtW];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const BlurTile t = P.blur_tiles[blockIdx.x];
+    const int l = t.level, W = P.lv[l].w, H = P.lv[l].h;
+    const int bx0 = t.x0 - 3, by0 = t.y0 - 3;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBoxH * kBoxW) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(s_src)), "l"(&M.m[l]), "r"(bx0), "r"(by0), "r"(b), "r"(bar)
+            : "memory");
+    }
+    {
+        uint32_t done = 0;
+        for (int spin = 0; spin < (1 << 14) && !done; ++spin)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        if (!done && tid == 0) P.status[b] = 3;  // the copy never completed: report it instead of hanging the device
+    }
+    if (bx0 < 0 || by0 < 0 || bx0 + kBoxW > W || by0 + kBoxH > H) {  // BORDER_REFLECT_101 from inside the box
+        for (int i = tid; i < kBoxH * kBoxW; i += 256) {
+            const int py = i / kBoxW, px = i - py * kBoxW;
+            const int gx = bx0 + px, gy = by0 + py;
+            if (gy < 0 || gy >= H) continue;
+            if (gx < 0 || (gx >= W && gx <= W + 2)) s_src[i] = s_src[py * kBoxW + (reflect101(gx, W) - bx0)];
+        }
+        __syncthreads();
+        for (int i = tid; i < kBoxH * kBoxW; i += 256) {
+            const int py = i / kBoxW, px = i - py * kBoxW;
+            const int gy = by0 + py;
+            if (gy < 0 || (gy >= H && gy <= H + 2)) s_src[i] = s_src[(reflect101(gy, H) - by0) * kBoxW + px];
+        }
+        __syncthreads();
+    }
+    // horizontal pass: output x of box row py uses box bytes x .. x + 6
+    const uint32_t *src32 = reinterpret_cast<const uint32_t *>(s_src);
+    for (int i = tid; i < kBoxH * (kBtW / 4); i += 256) {
+        const int py = i >> 4, j = i & 15;
+        const uint32_t A = src32[py * (kBoxW / 4) + j], B = src32[py * (kBoxW / 4) + j + 1], C = src32[py * (kBoxW / 4) + j + 2];
+        const uint32_t kW1 = 0x38302212u, kW2 = 0x00122230u;  // bytes (18, 34, 48, 56) and (48, 34, 18, 0)
+        const uint32_t h0 = __dp4a(A, kW1, __dp4a(B, kW2, 0u));
+        const uint32_t h1 = __dp4a(__funnelshift_r(A, B, 8), kW1, __dp4a(__funnelshift_r(B, C, 8), kW2, 0u));
+        const uint32_t h2 = __dp4a(__funnelshift_r(A, B, 16), kW1, __dp4a(__funnelshift_r(B, C, 16), kW2, 0u));
+        const uint32_t h3 = __dp4a(__funnelshift_r(A, B, 24), kW1, __dp4a(__funnelshift_r(B, C, 24), kW2, 0u));
+        *reinterpret_cast<uint2 *>(s_h + py * kBtW + 4 * j) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+    }
+    __syncthreads();
+    uint8_t *dst = P.blur + (size_t)b * P.blur_frame_bytes + P.lv[l].blur_offset;
+    const int dpitch = P.lv[l].pitch;
+    for (int i = tid; i < kBtH * (kBtW / 4); i += 256) {
+        const int py = i >> 4, px = (i & 15) * 4;
+        if (t.y0 + py >= H || t.x0 + px >= W) continue;
+        uint2 r[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) r[k] = *reinterpret_cast<const uint2 *>(s_h + (py + k) * kBtW + px);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t h[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const uint32_t w = (c < 2) ? r[k].x : r[k].y;
+                h[k] = (c & 1) ? (w >> 16) : (w & 0xffffu);
+            }
+            const uint32_t acc = 18u * (h[0] + h[6]) + 34u * (h[1] + h[5]) + 48u * (h[2] + h[4]) + 56u * h[3];
+            packed |= ((acc + 32768u) >> 16) << (8 * c);
+        }
+        // pitch is a multiple of 64: aligned 4-byte store; bytes past the image width are padding
+        *reinterpret_cast<uint32_t *>(dst + (size_t)(t.y0 + py) * dpitch + t.x0 + px) = packed;
+    }
+}
+
 __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp_keypoint *__restrict__ kp_out,
                                                                     uint8_t *__restrict__ desc_out,
                                                                     int32_t *__restrict__ n_out) {
@@ -1373,11 +1328,45 @@ struct plp_orb {
     uint8_t *d_desc = nullptr;
     int32_t *d_n = nullptr;
     size_t qt_smem = 0;
-    bool fast_v1 = false;  // PLP_FAST_V1=1 selects the first-generation FAST kernel (kept for A/B measurements)
+    // TMA descriptors of the pyramid levels as (x, y, frame) uint8 tensors; levels >= 1 live in d_pyr (encoded once),
+    // level 0 is the caller's buffer (re-encoded when its address / pitch / batch changes)
+    BlurMaps maps;
+    bool maps_ok = false;       // levels >= 1 encoded
+    bool no_tma = false;        // PLP_BLUR_NO_TMA=1
+    const uint8_t *map0_img = nullptr;
+    size_t map0_step = 0;
+    int map0_batch = 0;
     int last_batch = 0;
     const uint8_t *last_img0 = nullptr;
     size_t last_step = 0;
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// (x, y, frame) uint8 tensor of one pyramid level; box = the blur kernel's source tile.  false when the buffer does not
+// meet TMA's alignment rules (16-byte base and strides) -- the caller then uses the plain-load kernel for this batch.
+static bool encode_level_map(CUtensorMap *m, const uint8_t *base, int w, int h, int frames, size_t pitch, size_t frame_stride) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || ((uintptr_t)base & 15) || (pitch & 15) || (frame_stride & 15) || w < 1 || h < 1 || frames < 1) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)kBoxW, (cuuint32_t)kBoxH, 1u}, estr[3] = {1u, 1u, 1u};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 static int cv_round_host(double v) { return (int)lrint(v); }
 
@@ -1450,8 +1439,8 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
     PLP_CUDA_TRY(cudaSetDevice(ctx->device));
     plp_orb *o = new plp_orb();
     {
-        const char *v1 = getenv("PLP_FAST_V1");
-        o->fast_v1 = v1 && v1[0] == '1';
+        const char *nt = getenv("PLP_BLUR_NO_TMA");
+        o->no_tma = nt && nt[0] == '1';
     }
     o->ctx = ctx;
     o->params = *params;
@@ -1643,6 +1632,12 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
     D.lvl_cnt = o->d_lvl_cnt;
     D.qt_scratch = o->d_qt_scratch;
     D.status = o->d_status;
+    // TMA descriptors of the levels that live in the handle's own pyramid block (level 0 follows the caller's buffer)
+    o->maps_ok = true;
+    memset(&o->maps, 0, sizeof(o->maps));
+    for (unsigned l = 1; l < L && o->maps_ok; ++l)
+        o->maps_ok = encode_level_map(&o->maps.m[l], o->d_pyr + D.lv[l].offset, D.lv[l].w, D.lv[l].h, max_batch, D.lv[l].pitch,
+                                      D.pyr_frame_bytes);
     o->qt_smem = ((sizeof(QtShared) + 15) & ~(size_t)15) + (size_t)kQtSmemCands * (4 + 2 * 5 + 1) + 64;
     const plp_status so = ensure_smem_optin((const void *)quadtree_kernel, o->qt_smem, "quadtree_kernel");
     if (so != PLP_OK) {
@@ -1689,14 +1684,21 @@ static plp_status orb_run(plp_orb *o, const uint8_t *d_imgs, int batch, size_t s
     }
     if (D.num_cells > 0) {
         dim3 grid(D.num_cells, batch);
-        if (o->fast_v1)
-            PLP_LAUNCH(ctx, fast_cells_kernel, grid, 256, 0, D);
-        else
-            PLP_LAUNCH(ctx, fast_cells_kernel_v2, grid, 256, 0, D);
+        PLP_LAUNCH(ctx, fast_cells_kernel_v2, grid, 256, 0, D);
     }
     if (D.num_blur_tiles > 0) {
         dim3 grid(D.num_blur_tiles, batch);
-        PLP_LAUNCH(ctx, blur_tiles_kernel, grid, 256, 0, D);
+        bool tma = o->maps_ok && !o->no_tma;
+        if (tma && (o->map0_img != d_imgs || o->map0_step != step || o->map0_batch != batch)) {
+            tma = encode_level_map(&o->maps.m[0], d_imgs, D.lv[0].w, D.lv[0].h, batch, step, D.img0_frame_stride);
+            o->map0_img = tma ? d_imgs : nullptr;
+            o->map0_step = step;
+            o->map0_batch = batch;
+        }
+        if (tma)
+            PLP_LAUNCH(ctx, blur_tiles_tma_kernel, grid, 256, 0, o->maps, D);
+        else  // caller buffer not 16-byte aligned / pitched (or PLP_BLUR_NO_TMA=1 for A/B runs): plain loads
+            PLP_LAUNCH(ctx, blur_tiles_kernel, grid, 256, 0, D);
     }
     {
         dim3 grid(D.num_levels, batch);

@@ -6,7 +6,7 @@
 // OptimizationAlgorithmLevenberg: 4 trials x <= 10 LM iterations with chi-square re-classification of ALL
 // edges after each trial and removal of the Huber kernels at trial 2.
 //
-// One WARP per frame runs the whole optimisation in a single launch (40 LM iterations x launch latency would
+// One 128-thread CTA per frame runs the whole optimisation in a single launch (40 LM iterations x launch latency would
 // otherwise dominate); device code and the work decomposition are in pose_opt_kernels.cuh.  The batch dimension is
 // the grid.
 //
@@ -55,7 +55,7 @@ plp_status launch_pose_opt(plp_ctx *ctx, const PoseJob *d_jobs, int batch, int m
     (void)max_edges;  // no per-frame shared-memory tables any more: the edge count is unbounded
     if (batch <= 0) return PLP_OK;
     using po::pose_opt_kernel;
-    PLP_LAUNCH(ctx, pose_opt_kernel, div_up(batch, po::kWarpsPerCta), po::kThreads, 0, d_jobs, batch, cam, cfg);
+    PLP_LAUNCH(ctx, pose_opt_kernel, batch, po::kThreads, 0, d_jobs, batch, cam, cfg);
     PLP_CHECK_LAUNCH();
     return PLP_OK;
 }

@@ -1,4 +1,4 @@
-// poseopt_emu.cc -- csrc/pose_opt_kernels.cuh (motion-only BA, one warp per frame, no block barrier) executed on the host.
+// poseopt_emu.cc -- csrc/pose_opt_kernels.cuh (motion-only BA, one 128-thread CTA per frame) executed on the host.
 #include "cta_emu.h"
 
 #include <string.h>
@@ -31,6 +31,6 @@ extern "C" void emu_pose_optimize_batch(const plp_camera *cam, int batch, const 
     }
     const PoseJob *d_jobs = jobs.data();
     plp_pose_opt_cfg cfg{num_trials, num_each_iter};
-    emu_launch(po::pose_opt_kernel, (unsigned)((batch + po::kWarpsPerCta - 1) / po::kWarpsPerCta), (unsigned)po::kThreads,
+    emu_launch(po::pose_opt_kernel, (unsigned)batch, (unsigned)po::kThreads,
                d_jobs, batch, *cam, cfg);
 }

@@ -442,3 +442,42 @@ def test_pose_opt_kernel_on_cpu_stereo(poseopt_emu, orc, plp):
         To, po, lo, no, it_o = orc.pose_optimize(cam, T_init, pts, lines)
         assert np.linalg.norm(T[b] - To) / np.linalg.norm(To) < 1e-8
         assert np.array_equal(pf[b], po) and np.array_equal(lf[b], lo) and ninl[b] == no
+
+
+def test_point_match_kernel_on_cpu_worklist_overflow(pmatch_emu, orc, plp):
+    """Far more queries than keypoints: every keypoint is contested by ~10 queries, the bumped-query work list (cap / 2
+    entries) overflows and the kernel finishes with full-scan rounds -- same sequential result."""
+    import synth
+    grid = plp.capi.make_grid(synth.COLS, synth.ROWS)
+    cam = plp.capi.make_camera(synth.FX, synth.FY, synth.CX, synth.CY, synth.COLS, synth.ROWS)
+    sf = synth.scale_factors()
+    rng = np.random.default_rng(5)
+    n, m = 48, 500
+    curr = dict(x=rng.uniform(200, 440, n).astype(np.float32), y=rng.uniform(150, 330, n).astype(np.float32),
+                octave=rng.integers(0, 3, n).astype(np.int32), angle=rng.uniform(0, 360, n).astype(np.float32),
+                desc=synth.rand_desc(rng, n))
+    src = rng.integers(0, n, m)
+    lvl = np.clip(curr["octave"][src] + rng.integers(-1, 2, m), 0, 7).astype(np.int32)
+    qq = dict(qx=(curr["x"][src] + rng.normal(0, 3, m)).astype(np.float32), qy=(curr["y"][src] + rng.normal(0, 3, m)).astype(np.float32),
+              qxr=np.zeros(m, np.float32), qradius=(np.float32(20.0) * sf[lvl].astype(np.float32)).astype(np.float32),
+              qmin=lvl - 1, qmax=lvl + 1, qangle=rng.uniform(0, 360, m).astype(np.float32),
+              qdesc=synth.flip_bits(rng, curr["desc"][src], rng.integers(0, 40, m)), qvalid=np.ones(m, np.uint8))
+    # sequential reference of the no-ratio path: best unclaimed candidate per query in index order (projection.cc:294-335)
+    claimed = np.zeros(n, bool)
+    want = np.full(n, -1, np.int32)
+    order = np.lexsort((np.arange(n), np.floor(curr["y"] * grid.inv_cell_height).astype(int), np.floor(curr["x"] * grid.inv_cell_width).astype(int)))
+    for q in range(m):
+        best, best_i = 256, -1
+        for i in order:
+            if claimed[i] or not (qq["qmin"][q] <= curr["octave"][i] <= qq["qmax"][q]):
+                continue
+            if not (abs(curr["x"][i] - qq["qx"][q]) < qq["qradius"][q] and abs(curr["y"][i] - qq["qy"][q]) < qq["qradius"][q]):
+                continue
+            d = int(np.unpackbits(curr["desc"][i] ^ qq["qdesc"][q]).sum())
+            if d < best:
+                best, best_i = d, i
+        if best_i >= 0 and best <= 100:
+            claimed[best_i] = True
+            want[best_i] = q
+    _, matched, num = _emu_point_match(pmatch_emu, grid, curr, qq, 0, 0.0, 0)
+    assert np.array_equal(matched, want) and num == int((want >= 0).sum()) and num >= 40
