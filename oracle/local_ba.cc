@@ -16,6 +16,9 @@ namespace {
 
 // per-try trace of the most recent solve on this thread: (lambda used, rho, accepted) -- read by tests/test_ba_oracle.py
 thread_local std::vector<double> g_lm_trace;
+// step of g2o's central-difference Jacobians (BaseBinaryEdge::linearizeOplus: delta = 1e-9).  tests/ may move it by a relative
+// 1e-7 to find the landmarks whose optimum the reference's own numeric differentiation does not determine reproducibly.
+double g_numeric_delta = 1e-9;
 
 // ---- optimize/g2o/line3d.h:57-207 -------------------------------------------------------------------------
 struct Line3D {
@@ -271,7 +274,7 @@ struct Solver {
         for (auto &e : le) {  // numeric Jacobians for both vertices (BaseBinaryEdge::linearizeOplus, delta 1e-9)
             if (e.level) continue;
             act_l[e.lm] = 1;
-            const double delta = 1e-9, scalar = 1 / (2 * delta);
+            const double delta = g_numeric_delta, scalar = 1 / (2 * delta);
             double Jp[12], Jl[8];
             const double before[2] = {e.err[0], e.err[1]};
             for (int d = 0; d < 6; ++d) {
@@ -325,7 +328,7 @@ struct Solver {
         }
         for (auto &e : ple) {  // unary on the landmark, numeric Jacobian (additive landmark update)
             act_p[e.lm] = 1;
-            const double delta = 1e-9, scalar = 1 / (2 * delta);
+            const double delta = g_numeric_delta, scalar = 1 / (2 * delta);
             double J[3];
             const double before = e.err;
             for (int d = 0; d < 3; ++d) {
@@ -553,6 +556,8 @@ struct Solver {
 
 }  // namespace
 
+extern "C" void orc_debug_set_numeric_delta(double d) { g_numeric_delta = d; }
+
 extern "C" int orc_debug_lm_trace(double *out, int cap) {
     const int n = (int)g_lm_trace.size() / 3;
     for (int i = 0; i < 3 * std::min(n, cap); ++i) out[i] = g_lm_trace[i];
@@ -752,4 +757,45 @@ extern "C" int orc_debug_line_depth_positive(const double *cam5, const double *T
     Line3D l;
     for (int k = 0; k < 6; ++k) l.v[k] = L6[k];
     return line_depth_positive(c, se3_from_matrix(T_cw), l, obs4) ? 1 : 0;
+}
+
+// ---- local_bundle_adjuster_extended_line::endpoint_trimming (optimize/local_bundle_adjuster_extended_line.cc:676-787) ----
+// Restated with the matrix helpers of g2o_lite.hpp (the product's host function in structure-plp-slam_b200/host/
+// plpslam_b200_line_trimming.h is written out in scalars).  cam4 = fx fy cx cy.  Returns 1 = keep, 0 = erase.
+extern "C" int orc_endpoint_trimming(const double *cam4, const double *pose_cw, const double *plucker, const float *sp,
+                                     const float *ep, const double *old_endpoints, double median_depth, double *updated) {
+    const Cam c{cam4[0], cam4[1], cam4[2], cam4[3], 0.0};
+    Mat3 R;
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) R(r, k) = pose_cw[r * 4 + k];
+    const Vec3 t{{pose_cw[3], pose_cw[7], pose_cw[11]}};
+    const Vec3 proj = line_project(c, R, t, plucker);
+    const double l1 = proj[0], l2 = proj[1], l3 = proj[2];
+    double P[12];
+    const double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1};
+    for (int r = 0; r < 3; ++r)
+        for (int col = 0; col < 4; ++col) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += K[r * 3 + k] * (col < 3 ? R(k, col) : t[k]);
+            P[r * 4 + col] = s;
+        }
+    const Vec3 m{{plucker[0], plucker[1], plucker[2]}}, d{{plucker[3], plucker[4], plucker[5]}};
+    const Mat3 Sm = skew(m);
+    const float *pts[2] = {sp, ep};
+    for (int e = 0; e < 2; ++e) {
+        const double x = pts[e][0], y = pts[e][1];
+        const double xc = -(y - (l2 / l1) * x + (l3 / l2)) * ((l1 * l2) / (l1 * l1 + l2 * l2));
+        const double yc = -(l1 / l2) * xc - (l3 / l2);
+        const double y0 = y - (l2 / l1) * x;
+        const Vec3 lt = cross(Vec3{{xc, yc, 1.0}}, Vec3{{0.0, y0, 1.0}});
+        double pl[4];
+        for (int col = 0; col < 4; ++col) pl[col] = P[col] * lt[0] + P[4 + col] * lt[1] + P[8 + col] * lt[2];
+        double X[4];
+        for (int r = 0; r < 3; ++r) X[r] = Sm(r, 0) * pl[0] + Sm(r, 1) * pl[1] + Sm(r, 2) * pl[2] + d[r] * pl[3];
+        X[3] = -(d[0] * pl[0] + d[1] * pl[1] + d[2] * pl[2]);
+        for (int r = 0; r < 3; ++r) updated[3 * e + r] = X[r] / X[3];
+    }
+    const Vec3 ds{{updated[0] - old_endpoints[0], updated[1] - old_endpoints[1], updated[2] - old_endpoints[2]}};
+    const Vec3 de{{updated[3] - old_endpoints[3], updated[4] - old_endpoints[4], updated[5] - old_endpoints[5]}};
+    return (norm(ds) / median_depth > 0.1 || norm(de) / median_depth > 0.1) ? 0 : 1;
 }

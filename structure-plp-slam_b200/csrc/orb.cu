@@ -1091,7 +1091,8 @@ static_assert(kBoxW >= kBtW + 6 && kBoxW % 16 == 0, "TMA box: inner extent a mul
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256) blur_tiles_tma_kernel(const __grid_constant__ BlurMaps M, OrbDev P) {
+template <bool kMapsInGlobal>
+__global__ void __launch_bounds__(256) blur_tiles_tma_kernel(const __grid_constant__ BlurMaps M, const CUtensorMap *gmaps, OrbDev P) {
     __shared__ __align__(128) uint8_t s_src[kBoxH * kBoxW];
     __shared__ __align__(16) unsigned short s_h[kBoxH * kBtW];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -1106,10 +1107,14 @@ __global__ void __launch_bounds__(256) blur_tiles_tma_kernel(const __grid_consta
     }
     __syncthreads();
     if (tid == 0) {
+        // the descriptor: a kernel parameter (__grid_constant__) or, with PLP_TMA_MAPS=global, an array in device memory
+        // (acquired through the tensormap proxy, since the level-0 entry is rewritten when the caller's buffer changes)
+        const CUtensorMap *tm = kMapsInGlobal ? gmaps + l : &M.m[l];
+        if (kMapsInGlobal) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBoxH * kBoxW) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(smem_u32(s_src)), "l"(&M.m[l]), "r"(bx0), "r"(by0), "r"(b), "r"(bar)
+            ::"r"(smem_u32(s_src)), "l"(tm), "r"(bx0), "r"(by0), "r"(b), "r"(bar)
             : "memory");
     }
     {
@@ -1333,6 +1338,9 @@ struct plp_orb {
     BlurMaps maps;
     bool maps_ok = false;       // levels >= 1 encoded
     bool no_tma = false;        // PLP_BLUR_NO_TMA=1
+    bool maps_global = false;   // PLP_TMA_MAPS=global: descriptors read from device memory instead of kernel parameters
+    CUtensorMap *d_maps = nullptr;
+    bool d_maps_dirty = true;
     const uint8_t *map0_img = nullptr;
     size_t map0_step = 0;
     int map0_batch = 0;
@@ -1419,7 +1427,7 @@ void plp_orb_destroy(plp_orb *o) {
         if (o->d_ytab[l]) cudaFree(o->d_ytab[l]);
     }
     void *ptrs[] = {o->d_blur, o->d_blur_tiles, o->d_cells, o->d_pyr, o->d_img, o->d_mask, o->d_cell_buf, o->d_cell_cnt, o->d_lvl_kp,
-                    o->d_lvl_cnt, o->d_qt_scratch, o->d_status, o->d_kp, o->d_desc, o->d_n};
+                    o->d_lvl_cnt, o->d_qt_scratch, o->d_status, o->d_kp, o->d_desc, o->d_n, o->d_maps};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete o;
@@ -1441,6 +1449,8 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
     {
         const char *nt = getenv("PLP_BLUR_NO_TMA");
         o->no_tma = nt && nt[0] == '1';
+        const char *mg = getenv("PLP_TMA_MAPS");
+        o->maps_global = mg && mg[0] == 'g';
     }
     o->ctx = ctx;
     o->params = *params;
@@ -1618,6 +1628,7 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
     D.qt_scratch_per_job = (size_t)65536 * (4 + 2 * 5 + 1) + 256;
     ORB_ALLOC(o->d_qt_scratch, B * L * D.qt_scratch_per_job);
     ORB_ALLOC(o->d_status, B * sizeof(int));
+    ORB_ALLOC(o->d_maps, sizeof(BlurMaps));
     ORB_ALLOC(o->d_kp, B * (size_t)D.out_cap * sizeof(plp_keypoint));
     ORB_ALLOC(o->d_desc, B * (size_t)D.out_cap * 32);
     ORB_ALLOC(o->d_n, B * sizeof(int32_t));
@@ -1692,11 +1703,18 @@ static plp_status orb_run(plp_orb *o, const uint8_t *d_imgs, int batch, size_t s
         if (tma && (o->map0_img != d_imgs || o->map0_step != step || o->map0_batch != batch)) {
             tma = encode_level_map(&o->maps.m[0], d_imgs, D.lv[0].w, D.lv[0].h, batch, step, D.img0_frame_stride);
             o->map0_img = tma ? d_imgs : nullptr;
+            o->d_maps_dirty = true;
             o->map0_step = step;
             o->map0_batch = batch;
         }
-        if (tma)
-            PLP_LAUNCH(ctx, blur_tiles_tma_kernel, grid, 256, 0, o->maps, D);
+        if (tma && o->maps_global) {
+            if (o->d_maps_dirty) {
+                PLP_CUDA_TRY(cudaMemcpyAsync(o->d_maps, &o->maps, sizeof(BlurMaps), cudaMemcpyHostToDevice, ctx->stream));
+                o->d_maps_dirty = false;
+            }
+            PLP_LAUNCH(ctx, blur_tiles_tma_kernel<true>, grid, 256, 0, o->maps, o->d_maps, D);
+        } else if (tma)
+            PLP_LAUNCH(ctx, blur_tiles_tma_kernel<false>, grid, 256, 0, o->maps, (const CUtensorMap *)nullptr, D);
         else  // caller buffer not 16-byte aligned / pitched (or PLP_BLUR_NO_TMA=1 for A/B runs): plain loads
             PLP_LAUNCH(ctx, blur_tiles_kernel, grid, 256, 0, D);
     }

@@ -13,6 +13,7 @@
 //   src/PLPSLAM/mapping_module.cc               (fuse_landmark_duplication -> match::fuse::replace_duplication)
 //   src/PLPSLAM/data/frame.cc / keyframe.cc     (compute_bow), src/PLPSLAM/module/relocalizer.cc (bow_tree matcher)
 //   src/PLPSLAM/planar_mapping_module.cc        (estimate_plane_sequential_RANSAC, update_plane_via_RANSAC)
+//   src/PLPSLAM/optimize/local_bundle_adjuster*.cc (optimize: gather, plp_local_ba, outlier erase + write-back, trimming)
 // call.  Public signatures, PLPSLAM::system, the YAML configs and the map database stay unchanged.
 // See INTEGRATION.md for the patch of each call site.
 #pragma once
@@ -34,8 +35,13 @@
 #include "PLPSLAM/data/landmark_line.h"
 #include "PLPSLAM/data/landmark_plane.h"
 #include <functional>
+#include <map>
+#include <mutex>
 #include <random>
+#include "PLPSLAM/data/map_database.h"
+#include "PLPSLAM/data/graph_node.h"
 #include "plpslam_b200.h"
+#include "plpslam_b200_line_trimming.h"
 
 namespace plpslam_b200 {
 
@@ -623,6 +629,332 @@ inline std::vector<unsigned> match_frame_and_keyframes(const std::vector<PLPSLAM
     return num;
 }
 #endif  // USE_DBOW2
+
+
+// ---- match::projection::match_current_and_last_frames (match/projection.cc:214-358) ----------------------------------
+// The per-frame call of frame_tracker::motion_based_track (module/frame_tracker.cc:63-71).  The reprojection of the last
+// frame's landmarks, the window query, the claimed-keypoint rule and the orientation histogram all run on the device;
+// the adapter flattens the last frame's (landmark, keypoint) pairs and re-applies the pointer writes.
+inline unsigned match_current_and_last_frames(PLPSLAM::data::frame &curr_frm, const PLPSLAM::data::frame &last_frm, float margin,
+                                              bool check_orientation = true) {
+    const int n = curr_frm.num_keypts_;
+    std::vector<float> x(n), y(n), ang(n);
+    std::vector<int32_t> oct(n), matched(n);
+    std::vector<uint8_t> claimed(n);
+    for (int i = 0; i < n; ++i) {
+        x[i] = curr_frm.undist_keypts_[i].pt.x;
+        y[i] = curr_frm.undist_keypts_[i].pt.y;
+        oct[i] = curr_frm.undist_keypts_[i].octave;
+        ang[i] = curr_frm.undist_keypts_[i].angle;
+        claimed[i] = curr_frm.landmarks_[i] && curr_frm.landmarks_[i]->has_observation();  // :303-306
+    }
+    std::vector<PLPSLAM::data::landmark *> lms;
+    std::vector<double> pos;
+    std::vector<int32_t> l_oct;
+    std::vector<float> l_ang;
+    std::vector<uint8_t> l_desc;
+    for (unsigned idx = 0; idx < last_frm.num_keypts_; ++idx) {  // :240-253
+        auto *lm = last_frm.landmarks_[idx];
+        if (!lm || last_frm.outlier_flags_[idx]) continue;
+        const PLPSLAM::Vec3_t X = lm->get_pos_in_world();
+        lms.push_back(lm);
+        pos.insert(pos.end(), {X(0), X(1), X(2)});
+        l_oct.push_back(last_frm.keypts_[idx].octave);           // :268
+        l_ang.push_back(last_frm.undist_keypts_[idx].angle);     // :329
+        const cv::Mat d = lm->get_descriptor();
+        l_desc.insert(l_desc.end(), d.data, d.data + 32);
+    }
+    double Tc[16], Tl[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            Tc[r * 4 + c] = curr_frm.cam_pose_cw_(r, c);
+            Tl[r * 4 + c] = last_frm.cam_pose_cw_(r, c);
+        }
+    const plp_frame_points fp{n, x.data(), y.data(), oct.data(), ang.data(), curr_frm.stereo_x_right_.data(),
+                              curr_frm.descriptors_.data, claimed.data()};
+    const plp_last_frame_points lp{(int32_t)lms.size(), pos.data(), l_oct.data(), l_ang.data(), l_desc.data(), nullptr};
+    const plp_grid grid = grid_of(curr_frm.camera_);
+    const plp_camera cam = camera_of(curr_frm.camera_);
+    uint32_t num = 0;
+    check(plp_match_current_and_last_frames(thread_ctx(), &fp, &grid, curr_frm.scale_factors_.data(),
+                                            (int)curr_frm.scale_factors_.size(), &cam, Tc, Tl, &lp, margin, check_orientation,
+                                            matched.data(), &num));
+    for (int i = 0; i < n; ++i)  // curr_frm.landmarks_.at(best_idx) = lm (:325), minus the orientation rejects (:337-354)
+        if (matched[i] >= 0) curr_frm.landmarks_[i] = lms[matched[i]];
+    return num;
+}
+
+// keylines of a frame as the C ABI sees them; ratio_level reproduces the reference reading a POINT octave at a line index
+// (match/projection.cc:170,175) so that the behaviour is unchanged
+struct frame_lines_view {
+    std::vector<float> sx, sy, ex, ey;
+    std::vector<int32_t> oct, ratio_level;
+    std::vector<uint8_t> claimed;
+    plp_frame_lines v;
+    explicit frame_lines_view(PLPSLAM::data::frame &frm) {
+        const int n = frm._num_keylines;
+        sx.resize(n), sy.resize(n), ex.resize(n), ey.resize(n), oct.resize(n), ratio_level.resize(n), claimed.resize(n);
+        for (int i = 0; i < n; ++i) {
+            const auto &kl = frm._keylsd[i];
+            sx[i] = kl.getStartPoint().x;
+            sy[i] = kl.getStartPoint().y;
+            ex[i] = kl.getEndPoint().x;
+            ey[i] = kl.getEndPoint().y;
+            oct[i] = kl.octave;
+            ratio_level[i] = i < (int)frm.undist_keypts_.size() ? frm.undist_keypts_[i].octave : kl.octave;
+            claimed[i] = frm._landmarks_line[i] && frm._landmarks_line[i]->has_observation();
+        }
+        v = plp_frame_lines{n, sx.data(), sy.data(), ex.data(), ey.data(), oct.data(), ratio_level.data(), nullptr, nullptr,
+                            frm._lbd_descr.data, claimed.data()};
+    }
+};
+
+// ---- match::projection::match_current_and_last_frames_line (match/projection.cc:361-527) --------------------------------
+inline unsigned match_current_and_last_frames_line(PLPSLAM::data::frame &curr_frm, const PLPSLAM::data::frame &last_frm,
+                                                   float margin) {
+    frame_lines_view cv_(curr_frm);
+    std::vector<PLPSLAM::data::Line *> lms;
+    std::vector<double> pos;
+    std::vector<int32_t> l_oct;
+    std::vector<uint8_t> l_desc;
+    for (unsigned idx = 0; idx < last_frm._num_keylines; ++idx) {  // :392-405
+        auto *ll = last_frm._landmarks_line[idx];
+        if (!ll || last_frm._outlier_flags_line[idx]) continue;
+        const PLPSLAM::Vec6_t X = ll->get_pos_in_world();
+        lms.push_back(ll);
+        for (int k = 0; k < 6; ++k) pos.push_back(X(k));
+        l_oct.push_back(last_frm._keylsd[idx].octave);
+        const cv::Mat d = ll->get_descriptor();
+        l_desc.insert(l_desc.end(), d.data, d.data + 32);
+    }
+    double Tc[16], Tl[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            Tc[r * 4 + c] = curr_frm.cam_pose_cw_(r, c);
+            Tl[r * 4 + c] = last_frm.cam_pose_cw_(r, c);
+        }
+    const plp_last_frame_lines lp{(int32_t)lms.size(), pos.data(), l_oct.data(), l_desc.data(), nullptr};
+    const plp_camera cam = camera_of(curr_frm.camera_);
+    std::vector<int32_t> matched(curr_frm._num_keylines);
+    uint32_t num = 0;
+    check(plp_match_current_and_last_frames_line(thread_ctx(), &cv_.v, curr_frm._scale_factors_lsd.data(),
+                                                 (int)curr_frm._scale_factors_lsd.size(), &cam, Tc, Tl, &lp, margin,
+                                                 matched.data(), &num));
+    for (unsigned i = 0; i < curr_frm._num_keylines; ++i)
+        if (matched[i] >= 0) curr_frm._landmarks_line[i] = lms[matched[i]];
+    return num;
+}
+
+// ---- match::projection::match_frame_and_landmarks_line (match/projection.cc:124-212) -------------------------------------
+// called beside the point matcher in tracking_module::search_local_landmarks_line (tracking_module.cc:986-1060)
+inline unsigned match_frame_and_landmarks_line(PLPSLAM::data::frame &frm, const std::vector<PLPSLAM::data::Line *> &local_lines,
+                                               float margin, float lowe_ratio) {
+    const int m = (int)local_lines.size();
+    if (m == 0) return 0;  // :130-133
+    frame_lines_view fv(frm);
+    std::vector<float> spx(m), spy(m), epx(m), epy(m);
+    std::vector<int32_t> lvl(m), best(m);
+    std::vector<uint8_t> valid(m), qdesc((size_t)m * 32);
+    for (int q = 0; q < m; ++q) {
+        auto *ll = local_lines[q];
+        valid[q] = ll->_is_observable_in_tracking && !ll->will_be_erased();
+        spx[q] = ll->_reproj_in_tracking_sp(0);
+        spy[q] = ll->_reproj_in_tracking_sp(1);
+        epx[q] = ll->_reproj_in_tracking_ep(0);
+        epy[q] = ll->_reproj_in_tracking_ep(1);
+        lvl[q] = ll->_scale_level_in_tracking;
+        const cv::Mat d = ll->get_descriptor();
+        std::copy(d.data, d.data + 32, qdesc.begin() + (size_t)q * 32);
+    }
+    const plp_line_queries lq{m, spx.data(), spy.data(), epx.data(), epy.data(), lvl.data(), qdesc.data(), valid.data()};
+    uint32_t num = 0;
+    check(plp_match_frame_and_landmarks_line(thread_ctx(), &fv.v, frm._scale_factors_lsd.data(), (int)frm._scale_factors_lsd.size(),
+                                             &lq, margin, lowe_ratio, best.data(), &num));
+    for (int q = 0; q < m; ++q)
+        if (best[q] >= 0) frm._landmarks_line[best[q]] = local_lines[q];
+    return num;
+}
+
+// ---- optimize::local_bundle_adjuster[_extended_line|_extended_plane]::optimize ------------------------------------------
+// (optimize/local_bundle_adjuster.cc:62-410, local_bundle_adjuster_extended_line.cc:69-674,
+//  local_bundle_adjuster_extended_plane.cc:70-487): the WHOLE method body.  [1] gather local / fixed keyframes and local
+// landmarks by walking the covisibility graph and the observation tables (:72-158) -- ordered maps by id instead of the
+// reference's unordered_map, which only fixes the summation order; [2-6] the solve on the GPU (plp_local_ba: two LM runs
+// with the outlier round in between, force-stop polled between chunks of LM tries); [7-8] outlier observations erased
+// and the estimates written back under the map mutex (:342-409), lines re-trimmed on their reference keyframe
+// (local_bundle_adjuster_extended_line.cc:642-672, 676-787).  plp_local_ba holds the reduced camera system in shared
+// memory and therefore takes at most 32 NON-FIXED keyframes: a larger local window returns PLP_ERR_CAPACITY, which
+// check() turns into an exception -- never a silent CPU path.
+struct local_ba_options {
+    bool with_lines = false;   // local_bundle_adjuster_extended_line
+    bool with_planes = false;  // local_bundle_adjuster_extended_plane: unary point-to-plane edges (:309-345)
+    int num_first_iter = 5, num_second_iter = 10;
+};
+
+inline void local_bundle_adjust(PLPSLAM::data::keyframe *curr_keyfrm, bool *const force_stop_flag, const local_ba_options &opt) {
+    using namespace PLPSLAM;
+    // ---- [1] aggregate (local_bundle_adjuster.cc:72-158)
+    std::map<unsigned, data::keyframe *> local_keyfrms, fixed_keyfrms;
+    local_keyfrms[curr_keyfrm->id_] = curr_keyfrm;
+    for (auto *kf : curr_keyfrm->graph_node_->get_covisibilities())
+        if (kf && !kf->will_be_erased()) local_keyfrms[kf->id_] = kf;
+    std::map<unsigned, data::landmark *> local_lms;
+    std::map<unsigned, data::Line *> local_lines;
+    for (auto &ikf : local_keyfrms) {
+        for (auto *lm : ikf.second->get_landmarks())
+            if (lm && !lm->will_be_erased()) local_lms.emplace(lm->id_, lm);
+        if (opt.with_lines)
+            for (auto *ll : ikf.second->get_landmarks_line())
+                if (ll && !ll->will_be_erased()) local_lines.emplace(ll->_id, ll);
+    }
+    auto add_fixed = [&](data::keyframe *kf) {
+        if (kf && !kf->will_be_erased() && !local_keyfrms.count(kf->id_)) fixed_keyfrms.emplace(kf->id_, kf);
+    };
+    for (auto &ilm : local_lms)
+        for (auto &obs : ilm.second->get_observations()) add_fixed(obs.first);
+    for (auto &ill : local_lines)
+        for (auto &obs : ill.second->get_observations()) add_fixed(obs.first);
+    // ---- [3-4] flatten: keyframes (local first, then fixed), landmarks, one edge per observation grouped by landmark
+    std::vector<data::keyframe *> kfs;
+    std::map<data::keyframe *, int> kf_index;
+    std::vector<double> kf_pose;
+    std::vector<uint8_t> kf_fixed;
+    auto push_kf = [&](data::keyframe *kf, bool fixed) {
+        kf_index[kf] = (int)kfs.size();
+        kfs.push_back(kf);
+        const Mat44_t T = kf->get_cam_pose();
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) kf_pose.push_back(T(r, c));
+        kf_fixed.push_back(fixed ? 1 : 0);
+    };
+    for (auto &ikf : local_keyfrms) push_kf(ikf.second, ikf.second->id_ == 0);  // :197-202
+    for (auto &ikf : fixed_keyfrms) push_kf(ikf.second, true);                  // :205-213
+    std::vector<data::landmark *> lms;
+    std::vector<double> pt_pos, plane_fn;
+    std::vector<int32_t> pe_kf, pe_lm, plane_lm;
+    std::vector<float> pe_obs, pe_info;
+    std::vector<std::pair<data::keyframe *, data::landmark *>> pe_owner;
+    for (auto &ilm : local_lms) {  // :226-272
+        auto *lm = ilm.second;
+        const int li = (int)lms.size();
+        lms.push_back(lm);
+        const Vec3_t X = lm->get_pos_in_world();
+        pt_pos.insert(pt_pos.end(), {X(0), X(1), X(2)});
+        for (auto &obs : lm->get_observations()) {
+            auto *kf = obs.first;
+            if (!kf || kf->will_be_erased()) continue;
+            const auto &kp = kf->undist_keypts_.at(obs.second);
+            pe_kf.push_back(kf_index.at(kf));
+            pe_lm.push_back(li);
+            pe_obs.insert(pe_obs.end(), {kp.pt.x, kp.pt.y, kf->stereo_x_right_.at(obs.second)});
+            pe_info.push_back(kf->inv_level_sigma_sq_.at(kp.octave));
+            pe_owner.emplace_back(kf, lm);
+        }
+        if (opt.with_planes) {  // local_bundle_adjuster_extended_plane.cc:309-345: constants, not vertices
+            auto *pl = lm->get_Owning_Plane();
+            if (pl && pl->is_valid() && !pl->need_refinement()) {
+                const Vec3_t nrm = pl->get_normal();
+                plane_lm.push_back(li);
+                plane_fn.insert(plane_fn.end(), {nrm(0), nrm(1), nrm(2), pl->get_offset()});
+            }
+        }
+    }
+    std::vector<data::Line *> lines;
+    std::vector<double> ln_plucker;
+    std::vector<int32_t> le_kf, le_lm;
+    std::vector<float> le_obs, le_info;
+    std::vector<std::pair<data::keyframe *, data::Line *>> le_owner;
+    for (auto &ill : local_lines) {  // local_bundle_adjuster_extended_line.cc:365-417
+        auto *ll = ill.second;
+        const int li = (int)lines.size();
+        lines.push_back(ll);
+        const Vec6_t L = ll->get_PlueckerCoord();
+        for (int k = 0; k < 6; ++k) ln_plucker.push_back(L(k));
+        for (auto &obs : ll->get_observations()) {
+            auto *kf = obs.first;
+            if (!kf || kf->will_be_erased()) continue;
+            const auto &kl = kf->_keylsd.at(obs.second);
+            le_kf.push_back(kf_index.at(kf));
+            le_lm.push_back(li);
+            le_obs.insert(le_obs.end(), {kl.getStartPoint().x, kl.getStartPoint().y, kl.getEndPoint().x, kl.getEndPoint().y});
+            le_info.push_back(kf->_inv_level_sigma_sq_lsd.at(kl.octave));
+            le_owner.emplace_back(kf, ll);
+        }
+    }
+    if (force_stop_flag && *force_stop_flag) return;  // :276-282
+    const auto *pc = static_cast<const camera::perspective *>(curr_keyfrm->camera_);
+    plp_ba_problem P{};
+    P.fx = pc->fx_, P.fy = pc->fy_, P.cx = pc->cx_, P.cy = pc->cy_;
+    P.focal_x_baseline = curr_keyfrm->camera_->focal_x_baseline_;
+    P.setup_type = (int32_t)curr_keyfrm->camera_->setup_type_;
+    P.n_kf = (int32_t)kfs.size(), P.kf_pose_cw = kf_pose.data(), P.kf_fixed = kf_fixed.data();
+    P.n_pts = (int32_t)lms.size(), P.pt_pos_w = pt_pos.data();
+    P.n_pt_edges = (int32_t)pe_kf.size(), P.pt_edge_kf = pe_kf.data(), P.pt_edge_lm = pe_lm.data();
+    P.pt_edge_obs = pe_obs.data(), P.pt_edge_inv_sigma_sq = pe_info.data();
+    P.n_lines = (int32_t)lines.size(), P.line_plucker = ln_plucker.data();
+    P.n_line_edges = (int32_t)le_kf.size(), P.line_edge_kf = le_kf.data(), P.line_edge_lm = le_lm.data();
+    P.line_edge_obs = le_obs.data(), P.line_edge_inv_sigma_sq = le_info.data();
+    P.n_plane_edges = (int32_t)plane_lm.size(), P.plane_edge_lm = plane_lm.data(), P.plane_edge_fn = plane_fn.data();
+    std::vector<double> out_pose(kf_pose.size()), out_pts(pt_pos.size() + 3), out_lines(ln_plucker.size() + 6);
+    std::vector<uint8_t> pt_out(pe_kf.size() + 1), ln_out(le_kf.size() + 1);
+    plp_ba_result R{out_pose.data(), out_pts.data(), out_lines.data(), pt_out.data(), ln_out.data(), 0, 0, 0, 0.0};
+    const plp_ba_cfg cfg{opt.num_first_iter, opt.num_second_iter, 0};
+    // the reference hands g2o a plain bool that the tracking thread writes (mapping_module.cc:159-164)
+    check(plp_local_ba(thread_ctx(), &P, &cfg, reinterpret_cast<volatile const uint8_t *>(force_stop_flag), &R));
+    // ---- [7-8] write-back under the map mutex (:375-409)
+    std::lock_guard<std::mutex> lock(data::map_database::mtx_database_);
+    for (size_t e = 0; e < pe_owner.size(); ++e) {
+        if (!pt_out[e] || pe_owner[e].second->will_be_erased()) continue;  // :346-372
+        pe_owner[e].first->erase_landmark(pe_owner[e].second);
+        pe_owner[e].second->erase_observation(pe_owner[e].first);
+    }
+    for (size_t e = 0; e < le_owner.size(); ++e) {
+        if (!ln_out[e] || le_owner[e].second->will_be_erased()) continue;
+        le_owner[e].first->erase_landmark_line(le_owner[e].second);
+        le_owner[e].second->erase_observation(le_owner[e].first);
+    }
+    for (auto &ikf : local_keyfrms) {
+        const int k = kf_index.at(ikf.second);
+        Mat44_t T;
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) T(r, c) = out_pose[16 * (size_t)k + r * 4 + c];
+        ikf.second->set_cam_pose(T);
+    }
+    for (size_t l = 0; l < lms.size(); ++l) {
+        lms[l]->set_pos_in_world(Vec3_t(out_pts[3 * l], out_pts[3 * l + 1], out_pts[3 * l + 2]));
+        lms[l]->update_normal_and_depth();
+    }
+    for (size_t l = 0; l < lines.size(); ++l) {  // local_bundle_adjuster_extended_line.cc:642-672
+        auto *ll = lines[l];
+        Vec6_t L;
+        for (int k = 0; k < 6; ++k) L(k) = out_lines[6 * l + k];
+        ll->set_PlueckerCoord_without_update_endpoints(L);
+        auto *ref_kf = ll->get_ref_keyframe();
+        const int idx = ll->get_index_in_keyframe(ref_kf);
+        bool keep = idx != -1;  // :688-691
+        Vec6_t updated;
+        if (keep) {
+            const auto &kl = ref_kf->_keylsd.at(idx);
+            const auto *rc = static_cast<const camera::perspective *>(ref_kf->camera_);
+            const Mat44_t T = ref_kf->get_cam_pose();
+            double Tm[16], old_ep[6], new_ep[6];
+            for (int r = 0; r < 4; ++r)
+                for (int c = 0; c < 4; ++c) Tm[r * 4 + c] = T(r, c);
+            const Vec6_t old = ll->get_pos_in_world();
+            for (int k = 0; k < 6; ++k) old_ep[k] = old(k);
+            keep = endpoint_trimming(trimming_camera{rc->fx_, rc->fy_, rc->cx_, rc->cy_}, Tm, &out_lines[6 * l],
+                                     kl.getStartPoint().x, kl.getStartPoint().y, kl.getEndPoint().x, kl.getEndPoint().y, old_ep,
+                                     ref_kf->compute_median_depth(true), new_ep);
+            for (int k = 0; k < 6; ++k) updated(k) = new_ep[k];
+        }
+        if (keep) {
+            ll->set_pos_in_world_without_update_pluecker(updated);
+            ll->update_information();
+        } else {
+            ll->prepare_for_erasing();  // outlier found by trimming
+        }
+    }
+}
 
 }  // namespace plpslam_b200
 

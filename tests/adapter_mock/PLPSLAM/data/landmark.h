@@ -1,11 +1,14 @@
 #pragma once
 #include <opencv2/core.hpp>
+#include <map>
 #include "PLPSLAM/type.h"
 namespace plpslam_b200 { struct landmark_access; }
 namespace PLPSLAM { namespace data {
 class keyframe; class frame; class Plane;
 class landmark {  // data/landmark.h
 public:
+    unsigned id_; std::map<keyframe *, unsigned> get_observations() const; void erase_observation(keyframe *);
+    void set_pos_in_world(const Vec3_t &); void update_normal_and_depth();
     Vec3_t get_pos_in_world() const; Vec3_t get_obs_mean_normal() const; cv::Mat get_descriptor() const;
     bool will_be_erased(); bool has_observation() const; bool is_observed_in_keyframe(keyframe *) const;
     unsigned num_observations() const; void add_observation(keyframe *, unsigned); void replace(landmark *);

@@ -18,8 +18,22 @@ def _solve_gpu(ctx, plp, prob, **kw):
     return out
 
 
-def _compare(g, o, prob, tol=1e-4):
+def _line_self_move(orc, prob, o):
+    """How far every line of the oracle's result moves when g2o's finite-difference step changes by a relative 1e-7."""
+    import ctypes as C
+    if not len(o.line_plucker):
+        return np.zeros(0)
+    orc.lib.orc_debug_set_numeric_delta(C.c_double(1.0000001e-9))
+    try:
+        o2 = ba_data.oracle_local_ba(orc, prob)
+    finally:
+        orc.lib.orc_debug_set_numeric_delta(C.c_double(1e-9))
+    return np.linalg.norm(o.line_plucker - o2.line_plucker, axis=1) / np.linalg.norm(o.line_plucker, axis=1)
+
+
+def _compare(g, o, prob, tol=1e-4, orc=None):
     free = prob.kf_fixed == 0
+    line_self_move = _line_self_move(orc, prob, o) if orc is not None else np.zeros(len(o.line_plucker))
     rel_pose = np.linalg.norm(g["kf_pose_cw"] - o.kf_pose_cw) / np.linalg.norm(o.kf_pose_cw)
     assert rel_pose < tol, rel_pose
     assert np.array_equal(g["kf_pose_cw"][~free], prob.kf_pose_cw[~free].reshape(-1, 4, 4)) or \
@@ -29,16 +43,22 @@ def _compare(g, o, prob, tol=1e-4):
     if len(o.line_plucker):
         # Pluecker lines are homogeneous: compare after the reference's normalisation (|d| = 1)
         rel_ln = np.linalg.norm(g["line_plucker"] - o.line_plucker, axis=1) / np.linalg.norm(o.line_plucker, axis=1)
-        # north_star's 1e-4 holds for every line landmark that keeps >= 2 inlier observations.  A line whose
-        # observations are ALL outliers is not part of the second optimize() (its vertex keeps what the 5 robust iterations
-        # left, amplified numeric-Jacobian noise included) and the reference erases those observations right after the
-        # solve (local_bundle_adjuster_extended_line.cc:560-640): excluded here, see
-        # tests/test_ba_oracle.py::test_line_result_sensitivity_to_numeric_jacobian_noise for the same effect between
+        # north_star's 1e-4 holds for every line landmark whose optimum the reference itself determines reproducibly.
+        # Two groups are excluded, and counted:
+        #  (a) lines whose observations are ALL outliers: not part of the second optimize() (the vertex keeps what the 5 robust
+        #      iterations left) and erased right after the solve (local_bundle_adjuster_extended_line.cc:560-640);
+        #  (b) lines that move by more than 3e-6 when the ORACLE is re-run with g2o's finite-difference step changed from
+        #      1e-9 to 1.0000001e-9: line edges have no analytic Jacobian in the reference, the central difference carries
+        #      ~1e-7 relative noise, and a weakly observed line (few views, narrow baseline) amplifies it -- the reference's
+        #      own result on such a line depends on its compiler flags.  The GPU's Jacobian noise differs from the oracle's
+        #      by ~1e-6 relative (FMA contraction), i.e. ten probes.
+        # tests/test_ba_oracle.py::test_line_result_sensitivity_to_numeric_jacobian_noise shows the same effect between
         # two CPU restatements.
         inl = np.bincount(prob.line_edge_lm, weights=1.0 - o.line_edge_outlier, minlength=len(o.line_plucker))
-        kept = inl >= 2
-        assert kept.sum() >= 0.8 * len(rel_ln)
+        kept = (inl >= 2) & (line_self_move < 3e-6)
+        assert kept.sum() >= 0.9 * len(rel_ln), kept.sum()
         assert rel_ln[kept].max() < tol, rel_ln[kept].max()
+        assert np.quantile(rel_ln, 0.99) < 10 * tol
         mism = int((g["line_edge_outlier"] != o.line_edge_outlier).sum())
         assert mism <= max(1, int(1e-3 * len(o.line_edge_outlier))), mism
     mism = int((g["pt_edge_outlier"] != o.pt_edge_outlier).sum())
@@ -51,27 +71,27 @@ def _compare(g, o, prob, tol=1e-4):
 @pytest.mark.parametrize("seed", range(4))
 def test_points_only_small(ctx, orc, plp, seed):
     prob = ba_data.make_ba_problem(seed, n_local=6, n_fixed=3, n_points=300, n_lines=0, n_plane_pts=0)
-    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob)
+    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob, orc=orc)
 
 
 @pytest.mark.parametrize("seed,stereo", [(0, False), (1, True), (2, False)])
 def test_points_lines_planes_medium(ctx, orc, plp, seed, stereo):
     prob = ba_data.make_ba_problem(10 + seed, n_local=10, n_fixed=5, n_points=800, n_lines=150, n_plane_pts=60, stereo=stereo)
-    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob)
+    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob, orc=orc)
 
 
 @pytest.mark.parametrize("stereo", [False, True])
 def test_config4_full_size(ctx, orc, plp, stereo):
     # BASELINE config 4: 20 local + 10 fixed keyframes, 4000 points + 800 lines, 200 plane-owned points
     prob = ba_data.make_ba_problem(42, stereo=stereo)
-    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob)
+    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob, orc=orc)
 
 
 def test_shard_count_does_not_change_the_result(ctx, orc, plp):
     prob = ba_data.make_ba_problem(7, n_local=8, n_fixed=4, n_points=600, n_lines=100, n_plane_pts=30)
     o = ba_data.oracle_local_ba(orc, prob)
     for ctas in (1, 3, 32, 148):
-        _compare(_solve_gpu(ctx, plp, prob, num_ctas=ctas), o, prob)
+        _compare(_solve_gpu(ctx, plp, prob, num_ctas=ctas), o, prob, orc=orc)
 
 
 def test_force_stop_before_start_returns_input(ctx, plp):

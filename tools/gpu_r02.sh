@@ -6,7 +6,20 @@ TAG=${1:-r02a}
 WHAT=${2:-"tests bench ref prof"}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi_${TAG}.txt 2>&1
+if [[ " $WHAT " == *" tmadbg "* ]]; then
+  T="tests/test_orb_gpu.py -x -q -m gpu"
+  PLP_BLUR_NO_TMA=1 timeout 200 python -m pytest $T > gpurun_out/tma_none_${TAG}.log 2>&1; echo "no-tma exit $?"; tail -2 gpurun_out/tma_none_${TAG}.log
+  PLP_TMA_MAPS=global timeout 200 python -m pytest $T > gpurun_out/tma_global_${TAG}.log 2>&1; echo "tma global exit $?"; tail -2 gpurun_out/tma_global_${TAG}.log
+  timeout 200 python -m pytest $T > gpurun_out/tma_param_${TAG}.log 2>&1; echo "tma param exit $?"; tail -2 gpurun_out/tma_param_${TAG}.log
+  timeout 300 compute-sanitizer --tool memcheck python -m pytest $T -k "1234" > gpurun_out/tma_san_param_${TAG}.log 2>&1; echo "sanitizer param exit $?"
+  grep -m 12 -A12 "=========" gpurun_out/tma_san_param_${TAG}.log | head -60
+  PLP_TMA_MAPS=global timeout 300 compute-sanitizer --tool memcheck python -m pytest $T -k "1234" > gpurun_out/tma_san_global_${TAG}.log 2>&1; echo "sanitizer global exit $?"
+  grep -m 12 -A12 "=========" gpurun_out/tma_san_global_${TAG}.log | head -40
+fi
 if [[ " $WHAT " == *" tests "* ]]; then
+  # the kernels changed most recently first, under a short timeout (a hung copy engine must not eat the box)
+  timeout 300 python -m pytest tests/test_orb_gpu.py tests/test_golden.py tests/test_pose_opt_gpu.py tests/test_match_gpu.py tests/test_pipeline_gpu.py -q -m gpu -x > gpurun_out/test_first_${TAG}.log 2>&1
+  echo "first tests exit $?"; tail -4 gpurun_out/test_first_${TAG}.log
   timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/test_all_${TAG}.log 2>&1
   echo "gpu tests exit $?"; tail -6 gpurun_out/test_all_${TAG}.log
 fi
