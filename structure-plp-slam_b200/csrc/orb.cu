@@ -1077,17 +1077,20 @@ __global__ void __launch_bounds__(256) blur_tiles_kernel(OrbDev P) {
 }
 
 // ---- the same blur with the source tile staged by TMA and the passes on byte / half-word SIMD ---------------------
-// One CTA per 64 x 32 output tile.  (1) ONE bulk tensor copy (cp.async.bulk.tensor.3d, box 80 x 38 x 1 of the
-// (x, y, frame) tensor of the level; the box starts at (x0 - 3, y0 - 3): coordinates need no alignment, out-of-image
-// elements arrive as zeros) completes on an mbarrier -- no per-byte address arithmetic, no loads issued by the SMs.
+// One CTA per 64 x 32 output tile.  (1) ONE bulk tensor copy (cp.async.bulk.tensor.3d, box 96 x 38 x 1 of the
+// (x, y, frame) tensor of the level) completes on an mbarrier -- no per-byte address arithmetic, no loads issued by the
+// SMs.  The innermost coordinate of a tiled copy must be a multiple of 16 BYTES (measured with tools/probe/tma_probe.cu: an
+// unaligned x raises "illegal instruction", any y -- negative included -- is accepted, out-of-image elements arrive as
+// zeros), so the box is the 16-byte aligned superset [x0 - 16, x0 + 80) of the 70 columns the tile needs.
 // (2) tiles that touch the image border rebuild BORDER_REFLECT_101 inside shared memory (the mirrored pixels are part of
 // the same box).  (3) horizontal pass: a thread makes 4 outputs from 3 words with funnel shifts and DP4A
 // ([18 34 48 56] . bytes + [48 34 18 0] . bytes); (4) vertical pass on the u16 rows; OpenCV's rounding (v + 32768) >> 16.
 struct BlurMaps {
     CUtensorMap m[kMaxLevels];
 };
-constexpr int kBoxW = 80, kBoxH = kBtH + 6;
-static_assert(kBoxW >= kBtW + 6 && kBoxW % 16 == 0, "TMA box: inner extent a multiple of 16 bytes covering the halo");
+constexpr int kBoxW = 96, kBoxH = kBtH + 6, kBoxX = 16;  // the box starts kBoxX columns left of the tile
+static_assert(kBoxW >= kBoxX + kBtW + 3 && kBoxW % 16 == 0 && kBoxX % 16 == 0 && kBtW % 16 == 0,
+              "TMA box: 16-byte aligned start and extent covering the 3-pixel halo");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -1099,7 +1102,7 @@ __global__ void __launch_bounds__(256) blur_tiles_tma_kernel(const __grid_consta
     const int b = blockIdx.y, tid = threadIdx.x;
     const BlurTile t = P.blur_tiles[blockIdx.x];
     const int l = t.level, W = P.lv[l].w, H = P.lv[l].h;
-    const int bx0 = t.x0 - 3, by0 = t.y0 - 3;
+    const int bx0 = t.x0 - kBoxX, by0 = t.y0 - 3;  // image coordinates of box element (0, 0)
     const uint32_t bar = smem_u32(&s_bar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -1127,7 +1130,7 @@ __global__ void __launch_bounds__(256) blur_tiles_tma_kernel(const __grid_consta
                 : "memory");
         if (!done && tid == 0) P.status[b] = 3;  // the copy never completed: report it instead of hanging the device
     }
-    if (bx0 < 0 || by0 < 0 || bx0 + kBoxW > W || by0 + kBoxH > H) {  // BORDER_REFLECT_101 from inside the box
+    if (t.x0 < 3 || by0 < 0 || t.x0 + kBtW + 3 > W || by0 + kBoxH > H) {  // BORDER_REFLECT_101 from inside the box
         for (int i = tid; i < kBoxH * kBoxW; i += 256) {
             const int py = i / kBoxW, px = i - py * kBoxW;
             const int gx = bx0 + px, gy = by0 + py;
@@ -1142,16 +1145,18 @@ __global__ void __launch_bounds__(256) blur_tiles_tma_kernel(const __grid_consta
         }
         __syncthreads();
     }
-    // horizontal pass: output x of box row py uses box bytes x .. x + 6
+    // horizontal pass: output x of box row py uses box bytes x + 13 .. x + 19 (image columns x0 + x - 3 .. + 3); for the
+    // outputs 4j .. 4j + 3 that is byte 1 of word j + 3 up to byte 2 of word j + 5
     const uint32_t *src32 = reinterpret_cast<const uint32_t *>(s_src);
     for (int i = tid; i < kBoxH * (kBtW / 4); i += 256) {
         const int py = i >> 4, j = i & 15;
-        const uint32_t A = src32[py * (kBoxW / 4) + j], B = src32[py * (kBoxW / 4) + j + 1], C = src32[py * (kBoxW / 4) + j + 2];
+        const uint32_t *w = src32 + py * (kBoxW / 4) + j + (kBoxX - 4) / 4;
+        const uint32_t A = w[0], B = w[1], C = w[2];
         const uint32_t kW1 = 0x38302212u, kW2 = 0x00122230u;  // bytes (18, 34, 48, 56) and (48, 34, 18, 0)
-        const uint32_t h0 = __dp4a(A, kW1, __dp4a(B, kW2, 0u));
-        const uint32_t h1 = __dp4a(__funnelshift_r(A, B, 8), kW1, __dp4a(__funnelshift_r(B, C, 8), kW2, 0u));
-        const uint32_t h2 = __dp4a(__funnelshift_r(A, B, 16), kW1, __dp4a(__funnelshift_r(B, C, 16), kW2, 0u));
-        const uint32_t h3 = __dp4a(__funnelshift_r(A, B, 24), kW1, __dp4a(__funnelshift_r(B, C, 24), kW2, 0u));
+        const uint32_t h0 = __dp4a(__funnelshift_r(A, B, 8), kW1, __dp4a(__funnelshift_r(B, C, 8), kW2, 0u));
+        const uint32_t h1 = __dp4a(__funnelshift_r(A, B, 16), kW1, __dp4a(__funnelshift_r(B, C, 16), kW2, 0u));
+        const uint32_t h2 = __dp4a(__funnelshift_r(A, B, 24), kW1, __dp4a(__funnelshift_r(B, C, 24), kW2, 0u));
+        const uint32_t h3 = __dp4a(B, kW1, __dp4a(C, kW2, 0u));
         *reinterpret_cast<uint2 *>(s_h + py * kBtW + 4 * j) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
     }
     __syncthreads();

@@ -216,10 +216,11 @@ def make_ba_problem(seed, n_local=20, n_fixed=10, n_points=4000, n_lines=800, n_
         Pn = P + rng.normal(0, point_sigma, P.shape)
         Qn = Q + rng.normal(0, point_sigma, Q.shape)
         plucker = synth.plucker_from_endpoints(Pn, Qn)
+        line_endpoints = np.concatenate([Pn, Qn], 1)
         line_kw = dict(line_plucker=plucker, line_edge_kf=lkf, line_edge_lm=llm, line_edge_obs=lobs.astype(np.float32),
                        line_edge_inv_sigma_sq=np.ones(len(lkf), np.float32))
     else:
-        line_kw = {}
+        line_kw, line_endpoints = {}, np.zeros((0, 6))
     # perturb the free poses and all points
     poses = poses_gt.copy()
     for k in range(n_kf):
@@ -235,4 +236,4 @@ def make_ba_problem(seed, n_local=20, n_fixed=10, n_points=4000, n_lines=800, n_
     return BAProblem(stereo=stereo, kf_pose_cw=poses, kf_fixed=fixed, pt_pos_w=Xn, pt_edge_kf=ekf, pt_edge_lm=elm,
                      pt_edge_obs=obs, pt_edge_inv_sigma_sq=isig[octv], plane_edge_lm=pl_lm,
                      plane_edge_fn=planes[plane_of[pl_lm]] if len(pl_lm) else np.zeros((0, 4)),
-                     gt=dict(poses=poses_gt, points=X), **line_kw)
+                     gt=dict(poses=poses_gt, points=X, line_endpoints=line_endpoints), **line_kw)
