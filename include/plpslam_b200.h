@@ -737,10 +737,12 @@ PLP_API plp_status plp_local_ba(plp_ctx *ctx, const plp_ba_problem *p, const plp
                                 volatile const uint8_t *force_stop, plp_ba_result *r);
 /* optimize::global_bundle_adjuster::optimize (optimize/global_bundle_adjuster.cc:64-253) on the same problem layout:
  * every keyframe / point / line landmark of the map, kf_fixed = (keyframe id == 0) only, ONE optimize(num_iter) with or
- * without the Huber kernel (use_huber_kernel_), no outlier rounds (the outlier arrays of `r` come back zero).  This entry
- * point shares the dense in-shared-memory reduced-camera solve of the local adjuster and therefore accepts at most 32
- * non-fixed keyframes -- enough for the map-initialisation call (module/initializer.cc:306-307: 2 keyframes, 20
- * iterations); larger maps (loop_bundle_adjuster.cc:81-82) return PLP_ERR_CAPACITY until the reduced system moves to HBM. */
+ * without the Huber kernel (use_huber_kernel_), no outlier rounds (the outlier arrays of `r` come back zero).  Up to 32
+ * non-fixed keyframes (the map-initialisation call, module/initializer.cc:306-307: 2 keyframes, 20 iterations) share the
+ * in-shared-memory reduced-camera solve of the local adjuster; larger maps (after a loop closure,
+ * module/loop_bundle_adjuster.cc:81-82) keep the reduced system dense in HBM: FP64 atomics per landmark, right-looking
+ * blocked Cholesky with FP64 tensor-core (DMMA) trailing updates.  plp_local_ba / plp_ba_create take the same path for a
+ * local window of more than 32 non-fixed keyframes (fixed keyframes are never bounded). */
 PLP_API plp_status plp_global_ba(plp_ctx *ctx, const plp_ba_problem *p, int num_iter, int use_huber_kernel,
                                  volatile const uint8_t *force_stop, plp_ba_result *r);
 /* split form: upload once, solve (repeatable), destroy.  With `comm`, `p` holds THIS RANK's block of landmarks

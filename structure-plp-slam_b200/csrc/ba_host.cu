@@ -156,10 +156,7 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
     int n_free = 0;
     for (int k = 0; k < n_kf; ++k)
         if (!p->kf_fixed[k]) hidx[k] = n_free++;
-    if (n_free > kBaMaxFree) {
-        set_error("local BA: %d non-fixed keyframes exceed the capacity %d", n_free, kBaMaxFree);
-        return PLP_ERR_CAPACITY;
-    }
+    const bool large = n_free > kBaMaxFree;  // reduced camera system dense in HBM + blocked Cholesky (ba_chol.cu)
     PLP_REQUIRE(n_free >= 1, "at least one non-fixed keyframe");
     // CSR offsets (edges must be grouped by ascending landmark index, as the reference creates them)
     std::vector<int> pt_off(n_pts + 1, 0), ln_off(n_lines + 1, 0);
@@ -200,7 +197,7 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
         max_deg = std::max(max_deg, d);
         deg_e[n_pts + l + 1] = deg_e[n_pts + l] + 4 * (ln_off[l + 1] - ln_off[l]) + 1;  // numeric Jacobians: ~4x cost
     }
-    PLP_REQUIRE(max_deg <= kBaMaxFree, "a landmark is observed twice by the same keyframe");
+    PLP_REQUIRE(max_deg <= n_free, "a landmark is observed twice by the same keyframe");
     const int pool_cap = ba_pool_capacity(n_free, n_free * (n_free + 1) / 2, max_deg);
     const int LB = std::max(1, std::min(16, pool_cap / max_deg));
     int G = cfg->num_ctas > 0 ? cfg->num_ctas : std::max(1, std::min(ctx->sm_count, (n_lm + 2 * LB - 1) / (2 * LB)));
@@ -257,8 +254,9 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
     const size_t o_lnoff = cv.take((L1 + 1) * 4), o_lnkf = cv.take(F1 * 4), o_lnlm = cv.take(F1 * 4), o_lnobs = cv.take(F1 * 16);
     const size_t o_lninfo = cv.take(F1 * 4), o_lnlvl = cv.take(F1), o_lnout = cv.take(F1), o_lnchi = cv.take(F1 * 8);
     const size_t o_lnW = cv.take(F1 * 24 * 8), o_lnD = cv.take(L1 * 16 * 8), o_lnbl = cv.take(L1 * 4 * 8), o_lnact = cv.take(L1);
-    const size_t o_ranges = cv.take((G + 1) * 4), o_partial = cv.take((size_t)G * packed_len * 8);
-    const size_t o_packed = cv.take((size_t)(packed_sum_len + world + 8) * 8), o_dp = cv.take(6 * kBaMaxFree * 8);
+    const size_t o_ranges = cv.take((G + 1) * 4), o_partial = cv.take(large ? 64 : (size_t)G * packed_len * 8);
+    const size_t o_dense = cv.take(large ? ba_dense_bytes(n_free) : 64);
+    const size_t o_packed = cv.take((size_t)(packed_sum_len + world + 8) * 8), o_dp = cv.take((size_t)6 * std::max(n_free, kBaMaxFree) * 8);
     const size_t o_tp = cv.take((size_t)G * 16), o_ts = cv.take(64), o_state = cv.take(sizeof(BaState));
     const size_t o_Tin = cv.take(n_kf * 128), o_ptsin = cv.take(P1 * 24), o_lnin = cv.take(L1 * 48), o_Tout = cv.take(n_kf * 128);
     const size_t o_ptsout = cv.take(P1 * 24), o_lnout2 = cv.take(L1 * 48), o_stop = cv.take(64);
@@ -329,6 +327,9 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
     D.packed_sum_len = packed_sum_len;
     D.rank = rank;
     D.world = world;
+    D.large = large ? 1 : 0;
+    D.phase_init_grid = 64;
+    D.dense = (double *)(d + o_dense);
     D.kf_hidx = (int *)(d + o_hidx);
     D.poses[0] = (se3::Pose *)(d + o_pose0);
     D.poses[1] = (se3::Pose *)(d + o_pose1);

@@ -6,13 +6,14 @@
 
 namespace plp {
 
-constexpr int kBaMaxFree = 32;  // non-fixed keyframes per problem (reduced system <= 192 x 192)
+constexpr int kBaMaxFree = 32;  // non-fixed keyframes whose reduced system (<= 192 x 192) is solved in shared memory; more
+                                // keyframes take the dense-in-HBM path (ba_chol.cu)
 enum { kBaNeedInit = 0, kBaRunning = 1, kBaDone = 2 };
 
 struct BaState {  // LM state machine, lives in device memory (single writer: the 1-CTA kernels)
     int phase, it, max_it, qmax;
     int iter_start, have_trial, ok2, robust;
-    int cur, tries, accepted, pad;
+    int cur, tries, accepted, solve_active;  // solve_active: the HBM Cholesky kernels of this try have work (large path)
     double lambda, ni, rho, current_chi, scale_pose;
 };
 
@@ -24,6 +25,9 @@ struct BaDev {
     int n_kf, n_free, n_pairs, n_pts, n_lines, n_pt_edges, n_ln_edges, n_pl_edges;
     int num_ctas, batch_landmarks, pool_cap, packed_len, packed_sum_len;
     int rank, world;
+    int large;            // > kBaMaxFree non-fixed keyframes: reduced system dense in HBM (ba_chol.cu), FP64 atomics
+    int phase_init_grid;  // grid of ba_chol_prepare_kernel
+    double *dense;        // (6 n_free + 1) x 6 n_free, row-major lower triangle + right-hand side row (large path)
     // keyframes
     const int *kf_hidx;             // index among the free keyframes or -1
     se3::Pose *poses[2];            // current / trial, toggled by BaState::cur
@@ -69,6 +73,8 @@ int ba_pool_capacity(int n_free, int n_pairs, int max_free_degree);
 size_t ba_solve_smem(int n_free);
 plp_status ba_prepare_kernels(int n_free, int n_pairs, int pool_cap);
 plp_status ba_launch_try(plp_ctx *ctx, const BaDev &B, BaCollective *coll);
+size_t ba_dense_bytes(int n_free);
+plp_status ba_launch_solve_large(plp_ctx *ctx, const BaDev &B);
 plp_status ba_launch_decide(plp_ctx *ctx, const BaDev &B);
 plp_status ba_launch_set_state(plp_ctx *ctx, const BaDev &B, int max_it, int robust, int reset_cur);
 plp_status ba_launch_classify(plp_ctx *ctx, const BaDev &B, int set_levels);

@@ -186,6 +186,7 @@ struct BaPoolEntry {
     double A[21];   // Jp^T w Jp, upper triangle row-wise
     double bpe[6];  // -Jp^T w e
     double gpe[6];  // bpe - W * (Dinv bl)
+    int h, pad;     // free-keyframe index of the edge (large path: the accumulation walks the pool, not the slot table)
 };
 
 struct BaSmem {  // the pool (B.pool_cap entries) and the partial system follow in dynamic shared memory
@@ -207,6 +208,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 // =========================================================================================================
 // ba_linearize_kernel
 // =========================================================================================================
+// kLarge = false: <= kBaMaxFree non-fixed keyframes, the CTA's share of the reduced camera system lives in shared memory
+// (no atomics, fixed summation order).  kLarge = true (global BA / large local windows): the reduced system is the dense
+// block-upper-triangular `packed` vector in HBM (L2-resident: 5.8 MB for 200 keyframes) and every landmark adds its
+// -Y_i W_j^T / A blocks with FP64 atomics; nothing in the kernel is sized by the number of keyframes any more.
+template <bool kLarge>
 __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
     extern __shared__ __align__(16) uint8_t ba_smem_raw[];
     const BaState &ST = *B.state;
@@ -224,7 +230,8 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
     const Pose *poses = B.poses[cur];
     const double *pts = B.pts[cur], *lines = B.lines[cur];
     const se3::Cam cam{B.fx, B.fy, B.cx, B.cy, B.bf};
-    for (int i = tid; i < nS + 2 * n6; i += kBaThreads) Ssm[i] = 0.0;
+    if (!kLarge)
+        for (int i = tid; i < nS + 2 * n6; i += kBaThreads) Ssm[i] = 0.0;
     double chi_acc = 0.0, maxdiag = 0.0;
     const int lm_begin = B.cta_ranges[blockIdx.x], lm_end = B.cta_ranges[blockIdx.x + 1];
     const int LB = B.batch_landmarks;  // landmarks per batch (<= kBaWarps), LB * max_free_degree <= B.pool_cap
@@ -235,8 +242,10 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
         const int lm = batch0 + lmb;
         const bool has_lm = lmb < LB && lm < lm_end;
         // ---- slot table reset, count free active edges per landmark for the pool layout
-        for (int i = tid; i < kBaWarps * kBaMaxFree; i += kBaThreads) (&S.slot[0][0])[i] = -1;
-        for (int i = tid; i < kBaMaxFree; i += kBaThreads) S.kfmask[i] = 0u;
+        if (!kLarge) {
+            for (int i = tid; i < kBaWarps * kBaMaxFree; i += kBaThreads) (&S.slot[0][0])[i] = -1;
+            for (int i = tid; i < kBaMaxFree; i += kBaThreads) S.kfmask[i] = 0u;
+        }
         int e0 = 0, e1 = 0, D = 3;
         bool is_line = false;
         if (has_lm) {
@@ -372,8 +381,11 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
                             for (int rr = 0; rr < Rr; ++rr) s += Jp[rr * 6 + a] * w * Jp[rr * 6 + c];
                             pe.A[q++] = s;
                         }
-                    S.slot[lmb][h] = (short)pi;
-                    atomicOr(&S.kfmask[h], 1u << lmb);
+                    pe.h = h;
+                    if (!kLarge) {
+                        S.slot[lmb][h] = (short)pi;
+                        atomicOr(&S.kfmask[h], 1u << lmb);
+                    }
                     // W is needed again by the back-substitution
                     double *Wg = (is_line ? B.ln_W : B.pt_W) + 24 * (size_t)e;
                     for (int q2 = 0; q2 < 6 * D; ++q2) Wg[q2] = pe.W[q2];
@@ -459,6 +471,38 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
             }
         }
         __syncthreads();
+        if (kLarge) {
+            // ---- phase 2 (large): the warp of a landmark adds the blocks of every pair of its free observers to the dense
+            // reduced system in HBM: S(hi, hj) -= Y_i W_j^T for hi <= hj, S(h, h) += A, g(h) += gpe, bp(h) += bpe
+            if (has_lm) {
+                const int pb = S.pool_base[warp], pn = S.warp_cnt[warp];
+                const int Dl = is_line ? 4 : 3;
+                const int N = B.n_free;
+                for (int w = lane; w < pn * pn * 36; w += 32) {
+                    const int rc = w % 36, ij = w / 36, i = ij / pn, j = ij - i * pn;
+                    const BaPoolEntry &pi = pool[pb + i], &pj = pool[pb + j];
+                    if (pi.h > pj.h) continue;  // upper block triangle only (a keyframe observes a landmark once: pi.h == pj.h <=> i == j)
+                    const int r = rc / 6, c = rc - r * 6;
+                    double sacc = 0;
+                    for (int q = 0; q < Dl; ++q) sacc += pi.Y[r * Dl + q] * pj.W[c * Dl + q];
+                    sacc = -sacc;
+                    if (i == j) {
+                        const int a2 = r < c ? r : c, b2 = r < c ? c : r;
+                        sacc += pi.A[a2 * 6 - a2 * (a2 - 1) / 2 + (b2 - a2)];
+                    }
+                    const size_t p = (size_t)pi.h * N - (size_t)pi.h * (pi.h - 1) / 2 + (pj.h - pi.h);
+                    atomicAdd(&B.packed[p * 36 + rc], sacc);
+                }
+                for (int w = lane; w < pn * 6; w += 32) {
+                    const int i = w / 6, r = w - i * 6;
+                    const BaPoolEntry &pi = pool[pb + i];
+                    atomicAdd(&B.packed[nS + 6 * pi.h + r], pi.gpe[r]);
+                    atomicAdd(&B.packed[nS + n6 + 6 * pi.h + r], pi.bpe[r]);
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         // ---- phase 2: every thread owns fixed entries of S / g / bp (no atomics, fixed summation order)
         // only the landmarks that observe BOTH keyframes of a block contribute: walk the set bits of the two masks
         // (ascending landmark = the summation order of a dense scan)
@@ -503,7 +547,8 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
     }
     // ---- per-CTA partial system + chi2 / max-diag
     double *out = B.partial + (size_t)blockIdx.x * B.packed_len;
-    for (int i = tid; i < nS + 2 * n6; i += kBaThreads) out[i] = Ssm[i];
+    if (!kLarge)
+        for (int i = tid; i < nS + 2 * n6; i += kBaThreads) out[i] = Ssm[i];
     chi_acc = warp_sum(chi_acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxdiag = fmax(maxdiag, __shfl_xor_sync(0xffffffffu, maxdiag, o));
@@ -518,8 +563,14 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
             c += S.red[w][0];
             m = fmax(m, S.red[w][1]);
         }
-        out[nS + 2 * n6] = c;
-        out[nS + 2 * n6 + 1] = m;
+        if (kLarge) {  // chi2 sums, max diag(H) of the landmark blocks is a maximum: both straight into the packed vector
+            atomicAdd(&B.packed[nS + 2 * n6], c);
+            atomicMax(reinterpret_cast<unsigned long long *>(&B.packed[nS + 2 * n6 + 1 + B.rank]),
+                      (unsigned long long)__double_as_longlong(m));  // non-negative doubles order like their bit patterns
+        } else {
+            out[nS + 2 * n6] = c;
+            out[nS + 2 * n6 + 1] = m;
+        }
     }
 }
 
@@ -706,7 +757,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
 __global__ void __launch_bounds__(kBaThreads, 1) ba_update_kernel(BaDev B) {
     const BaState &ST = *B.state;
     if (ST.phase == kBaDone || !ST.have_trial) return;
-    __shared__ double s_dp[6 * kBaMaxFree];
+    extern __shared__ __align__(16) double s_dp[];  // 6 x n_free
     __shared__ double s_red[kBaWarps][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cur = ST.cur, nxt = cur ^ 1;
@@ -956,6 +1007,7 @@ __global__ void ba_set_state_kernel(BaDev B, int max_it, int robust, int reset_c
     ST.ni = 2;
     ST.rho = 0;
     ST.accepted = 0;
+    ST.solve_active = 0;
     if (reset_cur) {
         ST.cur = 0;
         ST.tries = 0;
@@ -966,15 +1018,17 @@ __global__ void ba_set_state_kernel(BaDev B, int max_it, int robust, int reset_c
 }  // namespace
 
 size_t ba_linearize_smem(int n_free, int n_pairs, int pool_cap) {
+    const bool large = n_free > kBaMaxFree;  // large path: the reduced system is in HBM, not in the CTA
     return ((sizeof(BaSmem) + 15) & ~(size_t)15) + (size_t)pool_cap * sizeof(BaPoolEntry) +
-           (size_t)(n_pairs * 36 + 12 * n_free) * 8 + 64;
+           (large ? 0 : (size_t)(n_pairs * 36 + 12 * n_free) * 8) + 64;
 }
 // pool entries per batch: enough for kBaWarps landmarks of the maximum free degree if the 227 KB of shared memory allow
 int ba_pool_capacity(int n_free, int n_pairs, int max_free_degree) {
     const size_t budget = 227 * 1024;
     const size_t fixed = ba_linearize_smem(n_free, n_pairs, 0);
     const int fit = fixed < budget ? (int)((budget - fixed) / sizeof(BaPoolEntry)) : 0;
-    return std::max(max_free_degree, std::min(std::min(kBaWarps * max_free_degree, kPoolMax), fit));
+    const int want = n_free > kBaMaxFree ? kBaWarps * max_free_degree : std::min(kBaWarps * max_free_degree, kPoolMax);
+    return std::max(max_free_degree, std::min(want, fit));
 }
 size_t ba_solve_smem(int n_free) {
     const size_t n = 6 * (size_t)n_free;
@@ -982,7 +1036,12 @@ size_t ba_solve_smem(int n_free) {
 }
 
 plp_status ba_prepare_kernels(int n_free, int n_pairs, int pool_cap) {
-    PLP_SMEM_OPTIN(ba_linearize_kernel, ba_linearize_smem(n_free, n_pairs, pool_cap));
+    if (n_free > kBaMaxFree) {
+        PLP_SMEM_OPTIN(ba_linearize_kernel<true>, ba_linearize_smem(n_free, n_pairs, pool_cap));
+        PLP_SMEM_OPTIN(ba_update_kernel, (size_t)6 * n_free * 8);
+        return PLP_OK;
+    }
+    PLP_SMEM_OPTIN(ba_linearize_kernel<false>, ba_linearize_smem(n_free, n_pairs, pool_cap));
     PLP_SMEM_OPTIN(ba_solve_kernel, ba_solve_smem(n_free));
     return PLP_OK;
 }
@@ -990,11 +1049,20 @@ plp_status ba_prepare_kernels(int n_free, int n_pairs, int pool_cap) {
 // one LM try on the context stream; `between` (may be null) is called where the multi-GPU path all-reduces
 plp_status ba_launch_try(plp_ctx *ctx, const BaDev &B, BaCollective *coll) {
     PLP_LAUNCH(ctx, ba_decide_kernel, 1, 256, 0, B);
-    PLP_LAUNCH(ctx, ba_linearize_kernel, B.num_ctas, kBaThreads, ba_linearize_smem(B.n_free, B.n_pairs, B.pool_cap), B);
-    PLP_LAUNCH(ctx, ba_reduce_kernel, div_up(B.packed_sum_len + 1, 256), 256, 0, B);
+    if (B.large) {
+        // every landmark adds its blocks to the packed system in HBM with FP64 atomics: start from zero
+        PLP_CUDA_TRY(cudaMemsetAsync(B.packed, 0, (size_t)(B.packed_sum_len + B.world) * sizeof(double), ctx->stream));
+        PLP_LAUNCH(ctx, ba_linearize_kernel<true>, B.num_ctas, kBaThreads, ba_linearize_smem(B.n_free, B.n_pairs, B.pool_cap), B);
+    } else {
+        PLP_LAUNCH(ctx, ba_linearize_kernel<false>, B.num_ctas, kBaThreads, ba_linearize_smem(B.n_free, B.n_pairs, B.pool_cap), B);
+        PLP_LAUNCH(ctx, ba_reduce_kernel, div_up(B.packed_sum_len + 1, 256), 256, 0, B);
+    }
     if (coll) PLP_TRY(coll->all_reduce(B.packed, B.packed_sum_len + B.world));
-    PLP_LAUNCH(ctx, ba_solve_kernel, 1, kSolveThreads, ba_solve_smem(B.n_free), B);
-    PLP_LAUNCH(ctx, ba_update_kernel, B.num_ctas, kBaThreads, 0, B);
+    if (B.large)
+        PLP_TRY(ba_launch_solve_large(ctx, B));
+    else
+        PLP_LAUNCH(ctx, ba_solve_kernel, 1, kSolveThreads, ba_solve_smem(B.n_free), B);
+    PLP_LAUNCH(ctx, ba_update_kernel, B.num_ctas, kBaThreads, (size_t)6 * B.n_free * sizeof(double), B);
     PLP_LAUNCH(ctx, ba_trial_reduce_kernel, 1, 32, 0, B);
     if (coll) PLP_TRY(coll->all_reduce(B.trial_sum, 2));
     PLP_CHECK_LAUNCH();

@@ -246,6 +246,35 @@ __device__ __forceinline__ uint32_t compass4(const uint32_t *T32, int y, int g, 
     return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xfu;
 }
 
+// Stronger byte-SIMD pretest (thresholds < 128): a 9-arc covers at least FOUR CONSECUTIVE of the eight even ring pixels
+// (0, 2, .., 14), which must then all differ from the centre by more than t -- a necessary condition for a FAST-9 corner
+// that rejects about three times as many pixels as the compass pair, so that the scalar arc test (250 instructions)
+// runs on few of them.  |ring - c| with the native VABSDIFF4; "byte > t" as ((x & 0x7f) + (0x7f - t) | x) & 0x80.
+__device__ __forceinline__ uint32_t even8_4(const uint32_t *T32, int y, int g, uint32_t k7) {
+    constexpr int kPitchW = kTilePitch / 4;
+    const uint32_t *row = T32 + y * kPitchW + g;
+    const uint32_t c = row[0];
+    const uint32_t wl = g > 0 ? row[-1] : 0u, wr = row[1];
+    const uint32_t *rp2 = row + 2 * kPitchW, *rm2 = row - 2 * kPitchW;
+    const uint32_t p2l = g > 0 ? rp2[-1] : 0u, m2l = g > 0 ? rm2[-1] : 0u;
+    auto gt = [&](uint32_t ring) -> uint32_t {
+        const uint32_t d = __vabsdiffu4(c, ring);
+        return (((d & 0x7f7f7f7fu) + k7) | d) & 0x80808080u;
+    };
+    const uint32_t e0 = gt(row[3 * kPitchW]);                      // ( 0, +3)
+    const uint32_t e2 = gt(__funnelshift_r(rp2[0], rp2[1], 16));   // (+2, +2)
+    const uint32_t e4 = gt(__funnelshift_r(c, wr, 24));            // (+3,  0)
+    const uint32_t e6 = gt(__funnelshift_r(rm2[0], rm2[1], 16));   // (+2, -2)
+    const uint32_t e8 = gt(row[-3 * kPitchW]);                     // ( 0, -3)
+    const uint32_t e10 = gt(__funnelshift_r(m2l, rm2[0], 16));     // (-2, -2)
+    const uint32_t e12 = gt(__funnelshift_r(wl, c, 8));            // (-3,  0)
+    const uint32_t e14 = gt(__funnelshift_r(p2l, rp2[0], 16));     // (-2, +2)
+    const uint32_t p0 = e0 & e2, p2 = e2 & e4, p4 = e4 & e6, p6 = e6 & e8, p8 = e8 & e10, p10 = e10 & e12, p12 = e12 & e14,
+                   p14 = e14 & e0;
+    const uint32_t r = (p0 & p4) | (p2 & p6) | (p4 & p8) | (p6 & p10) | (p8 & p12) | (p10 & p14) | (p12 & p0) | (p14 & p2);
+    return ((r >> 7) | (r >> 14) | (r >> 21) | (r >> 28)) & 0xfu;
+}
+
 __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
     __shared__ __align__(16) uint8_t tile[kTileRows * kTilePitch];
     __shared__ __align__(16) uint8_t score[kTileRows * kTilePitch];
@@ -297,20 +326,12 @@ __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
     const int halves = tw > 32 ? 2 : 1;
     const int x_lo = 3 + xo, x_hi = 3 + xo + tw;  // tested tile columns
     const uint32_t *T32 = reinterpret_cast<const uint32_t *>(tile);
-    // append the pixels of `nib` (bits = pixels 4g .. 4g+3 of row y) to the survivor list; called by whole warps
+    // append the pixels of `nib` (bits = pixels 4g .. 4g+3 of row y) to the survivor list.  The order of the list is
+    // irrelevant (scores and NMS bits are per pixel, the output order comes from the row masks), so a lane with survivors
+    // simply reserves its slots with one shared-memory atomic
     auto append = [&](uint32_t nib, int y, int g) {
-        const int cnt = __popc(nib);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        int wbase = 0;
-        if (lane == 31 && total) wbase = atomicAdd(&s_nsurv, total);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        int pos = wbase + incl - cnt;
+        if (!nib) return;
+        int pos = atomicAdd(&s_nsurv, __popc(nib));
         while (nib) {
             const int bit = __ffs(nib) - 1;
             nib &= nib - 1;
@@ -324,6 +345,8 @@ __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
     for (int pass = 0; pass < 2; ++pass) {
         const int thr = pass == 0 ? P.ini_thr : P.min_thr;
         const uint32_t t4 = (uint32_t)min(thr, 255) * 0x01010101u;
+        const bool strong = thr < 128;  // the SWAR "byte > t" of even8_4 needs t < 128
+        const uint32_t k7 = (uint32_t)(0x7f - min(thr, 127)) * 0x01010101u;
         if (tid < 128) s_rowbits[tid] = 0u;
         if (tid == 0) s_nsurv = 0;
         if (pass == 1)  // scores of the first pass must not leak into the second (cv::FAST runs from scratch)
@@ -333,14 +356,14 @@ __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
         for (int rp = warp; rp < (th + 1) / 2; rp += 8) {
             const int ry = 2 * rp + (lane >> 4), g = lane & 15;
             uint32_t nib = 0;
-            if (ry < th) nib = compass4(T32, 3 + ry, g, t4) & valid_nibble(g);
+            if (ry < th) nib = (strong ? even8_4(T32, 3 + ry, g, k7) : compass4(T32, 3 + ry, g, t4)) & valid_nibble(g);
             append(nib, 3 + ry, g);
         }
         for (int g = 16; 4 * g < x_hi; ++g) {  // word groups 16, 17 (tile columns 64 .. 71), one thread per row
             for (int base = 0; base < th; base += 256) {
                 const int ry = base + tid;
                 uint32_t nib = 0;
-                if (ry < th) nib = compass4(T32, 3 + ry, g, t4) & valid_nibble(g);
+                if (ry < th) nib = (strong ? even8_4(T32, 3 + ry, g, k7) : compass4(T32, 3 + ry, g, t4)) & valid_nibble(g);
                 append(nib, 3 + ry, g);
             }
         }
@@ -1131,17 +1154,21 @@ __global__ void __launch_bounds__(256) blur_tiles_tma_kernel(const __grid_consta
         if (!done && tid == 0) P.status[b] = 3;  // the copy never completed: report it instead of hanging the device
     }
     if (t.x0 < 3 || by0 < 0 || t.x0 + kBtW + 3 > W || by0 + kBoxH > H) {  // BORDER_REFLECT_101 from inside the box
-        for (int i = tid; i < kBoxH * kBoxW; i += 256) {
-            const int py = i / kBoxW, px = i - py * kBoxW;
-            const int gx = bx0 + px, gy = by0 + py;
-            if (gy < 0 || gy >= H) continue;
-            if (gx < 0 || (gx >= W && gx <= W + 2)) s_src[i] = s_src[py * kBoxW + (reflect101(gx, W) - bx0)];
+        // only the (at most) 3 + 3 halo columns and 3 + 3 halo rows the stored outputs read are rebuilt
+        for (int i = tid; i < kBoxH * 6; i += 256) {
+            const int py = i / 6, k = i - py * 6;
+            const int gx = k < 3 ? k - 3 : W + (k - 3), gy = by0 + py;   // image columns -3 .. -1 and W .. W + 2
+            const int px = gx - bx0;
+            if (gy < 0 || gy >= H || px < 0 || px >= kBoxW) continue;
+            s_src[py * kBoxW + px] = s_src[py * kBoxW + (reflect101(gx, W) - bx0)];
         }
         __syncthreads();
-        for (int i = tid; i < kBoxH * kBoxW; i += 256) {
-            const int py = i / kBoxW, px = i - py * kBoxW;
-            const int gy = by0 + py;
-            if (gy < 0 || (gy >= H && gy <= H + 2)) s_src[i] = s_src[(reflect101(gy, H) - by0) * kBoxW + px];
+        for (int i = tid; i < 6 * kBoxW; i += 256) {
+            const int k = i / kBoxW, px = i - k * kBoxW;
+            const int gy = k < 3 ? k - 3 : H + (k - 3);                  // image rows -3 .. -1 and H .. H + 2
+            const int py = gy - by0;
+            if (py < 0 || py >= kBoxH) continue;
+            s_src[py * kBoxW + px] = s_src[(reflect101(gy, H) - by0) * kBoxW + px];
         }
         __syncthreads();
     }

@@ -329,104 +329,45 @@ __global__ void __launch_bounds__(kThreads, 1)
         // to their next candidate in (distance, order).
         int *owner = owner_prev;  // min proposer so far; never reset
         const int hamm_thr = J.hamm_thr_p1 ? (int)J.hamm_thr_p1 - 1 : PLP_HAMMING_DIST_THR_HIGH;
-        // Work lists of bumped queries (owner_b is free on this path): a proposal returns the previous owner from its
-        // atomicMin -- smaller: the proposer lost at once; larger: that owner has just been bumped -- so who must
-        // re-propose is known at proposal time and a round only touches those queries (a query enters a list once per
-        // lost proposal: owner[c] moves away from it exactly once).  flags: [0] / [1] list sizes, [3] overflow.
-        const int half = cap / 2;
-        int *wl[2] = {S.owner_b, S.owner_b + half};
-        auto propose = [&](int q, int k1, int next) {  // one lane per query
-            int choice = -1;
-            if (k1 != kNoKey && (k1 >> 12) <= hamm_thr) choice = k1 & 0xfff;
-            J.choice[q] = choice;
-            if (choice < 0) return;
-            const int old = atomicMin(&owner[choice], q);
-            const int loser = old < q ? q : (old != kNoOwner ? old : -1);
-            if (loser >= 0) {
-                const int i = atomicAdd(&S.flags[next], 1);
-                if (i < half)
-                    wl[next][i] = loser;
-                else
-                    S.flags[3] = 1;
-            }
-        };
+        // A proposal returns the previous owner from its atomicMin: smaller -> the proposer lost at once and moves to its
+        // next candidate; larger -> that owner has just been bumped, and the SAME group re-proposes for it right away
+        // (it knows the lost keypoint, hence the floor).  A query is in the hands of at most one group at any time (it
+        // holds one proposal; only the group that displaces it takes it over), every step lowers an owner or exhausts a
+        // candidate list, so the chains end -- without a single block barrier or work list.  The first generation re-ran
+        // whole rounds separated by barriers: 46-68 % of the kernel's stall samples were 1000 threads waiting for the few
+        // bumped queries of a round (profiles/source_hotspots_r02*.md).
         for (int q0 = 0; q0 < m_pad; q0 += kGroups) {
             const int q = q0 + grp;
-            const bool active = q < m && (J.qvalid ? (J.qvalid[q] != 0) : true);
-            int k1, k2;
-            group_scan(S, J, grid, active, q, gl, nullptr, -1, k1, k2);
-            if (gl == 0 && q < m) {
-                if (active)
-                    propose(q, k1, 0);
-                else
-                    J.choice[q] = -1;
-            }
-        }
-        __syncthreads();
-        for (int round = 0; round <= m && !S.flags[3]; ++round) {
-            const int cur = round & 1, nxt = cur ^ 1;
-            const int n_w = min(S.flags[cur], half);
-            if (n_w == 0) break;  // uniform: read after the barrier, rewritten only after the next one
-            __syncthreads();
-            if (tid == 0) S.flags[nxt] = 0;
-            __syncthreads();
-            const int w_pad = ((n_w + kGroups - 1) / kGroups) * kGroups;
-            for (int e0 = 0; e0 < w_pad; e0 += kGroups) {
-                const int e = e0 + grp;
-                const bool act = e < n_w;
-                if (!__any_sync(0xffffffffu, act)) continue;
-                int q = 0, floor = -1;
-                if (act) {  // next candidate after the lost one
-                    q = wl[cur][e];
-                    const int c = J.choice[q];
-                    uint4 q0d, q1d;
-                    load_desc(J.qdesc + 32 * (size_t)q, q0d, q1d);
-                    floor = (hamming256(q0d, q1d, S.desc[2 * c], S.desc[2 * c + 1]) << 12) | c;
-                }
+            int cur = (q < m && (J.qvalid ? (J.qvalid[q] != 0) : true)) ? q : -1;
+            int floor = -1;
+            if (gl == 0 && q < m && cur < 0) J.choice[q] = -1;
+            while (__any_sync(0xffffffffu, cur >= 0)) {
                 int k1, k2;
-                group_scan(S, J, grid, act, q, gl, nullptr, floor, k1, k2);
-                if (gl == 0 && act) propose(q, k1, nxt);
-            }
-            __syncthreads();
-        }
-        if (S.flags[3]) {
-            // a work list overflowed (more than cap / 2 bumped queries in one round): finish with full scans -- every round
-            // looks at every query and re-proposes the bumped ones; correct from any intermediate state
-            __syncthreads();
-            if (tid == 0) S.flags[0] = 0;
-            __syncthreads();
-            for (int round = 0; round <= m; ++round) {
-                for (int q0 = 0; q0 < m_pad; q0 += kGroups) {
-                    const int q = q0 + grp;
-                    int c = -1;
-                    if (q < m) c = J.choice[q];
-                    const bool bumped = c >= 0 && owner[c] != q;  // lost its proposal to a smaller query
-                    if (!__any_sync(0xffffffffu, bumped)) continue;
-                    int floor = -1;
-                    if (bumped) {
-                        uint4 q0d, q1d;
-                        load_desc(J.qdesc + 32 * (size_t)q, q0d, q1d);
-                        floor = (hamming256(q0d, q1d, S.desc[2 * c], S.desc[2 * c + 1]) << 12) | c;
-                    }
-                    int k1, k2;
-                    group_scan(S, J, grid, bumped, q, gl, nullptr, floor, k1, k2);
-                    if (gl == 0 && bumped) {
-                        int choice = -1;
-                        if (k1 != kNoKey && (k1 >> 12) <= hamm_thr) choice = k1 & 0xfff;
-                        J.choice[q] = choice;
-                        if (choice >= 0) atomicMin(&owner[choice], q);
-                        S.flags[0] = 1;
+                group_scan(S, J, grid, cur >= 0, cur, gl, nullptr, floor, k1, k2);
+                int next = -1, nfloor = -1;
+                if (gl == 0 && cur >= 0) {
+                    int choice = -1;
+                    if (k1 != kNoKey && (k1 >> 12) <= hamm_thr) choice = k1 & 0xfff;
+                    J.choice[cur] = choice;
+                    if (choice >= 0) {
+                        __threadfence_block();  // the choice is visible before another group can take the query over
+                        const int old = atomicMin(&owner[choice], cur);
+                        if (old < cur) {  // lost at once: continue behind this candidate
+                            next = cur;
+                            nfloor = k1;
+                        } else if (old != kNoOwner) {  // bumped `old` off this keypoint: find its next candidate
+                            uint4 o0, o1;
+                            load_desc(J.qdesc + 32 * (size_t)old, o0, o1);
+                            next = old;
+                            nfloor = (hamming256(o0, o1, S.desc[2 * choice], S.desc[2 * choice + 1]) << 12) | choice;
+                        }
                     }
                 }
-                __syncthreads();
-                const int changed = S.flags[0];
-                __syncthreads();
-                if (!changed) break;
-                if (tid == 0) S.flags[0] = 0;
-                __syncthreads();
+                const int leader = lane & ~(kGroup - 1);
+                cur = __shfl_sync(0xffffffffu, next, leader);
+                floor = __shfl_sync(0xffffffffu, nfloor, leader);
             }
         }
-        if (tid < 4) S.flags[tid] = 0;  // the output stage counts in flags[1], flags[2]
         __syncthreads();
     } else {
         // Ratio test (match_frame_and_landmarks): acceptance depends on the second-best AVAILABLE candidate, so we

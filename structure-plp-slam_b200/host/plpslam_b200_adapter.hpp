@@ -782,9 +782,8 @@ inline unsigned match_frame_and_landmarks_line(PLPSLAM::data::frame &frm, const 
 // reference's unordered_map, which only fixes the summation order; [2-6] the solve on the GPU (plp_local_ba: two LM runs
 // with the outlier round in between, force-stop polled between chunks of LM tries); [7-8] outlier observations erased
 // and the estimates written back under the map mutex (:342-409), lines re-trimmed on their reference keyframe
-// (local_bundle_adjuster_extended_line.cc:642-672, 676-787).  plp_local_ba holds the reduced camera system in shared
-// memory and therefore takes at most 32 NON-FIXED keyframes: a larger local window returns PLP_ERR_CAPACITY, which
-// check() turns into an exception -- never a silent CPU path.
+// (local_bundle_adjuster_extended_line.cc:642-672, 676-787).  Neither the number of local nor of fixed keyframes is
+// bounded: up to 32 NON-FIXED keyframes the reduced camera system is solved in shared memory, beyond that dense in HBM.
 struct local_ba_options {
     bool with_lines = false;   // local_bundle_adjuster_extended_line
     bool with_planes = false;  // local_bundle_adjuster_extended_plane: unary point-to-plane edges (:309-345)

@@ -32,6 +32,7 @@ static pthread_barrier_t g_cta_barrier;
 #define __align__(n) __attribute__((aligned(n)))
 
 static inline void __syncthreads() { pthread_barrier_wait(&g_cta_barrier); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int *a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicOr(unsigned *a, unsigned v) { return __atomic_fetch_or(a, v, __ATOMIC_SEQ_CST); }
 static inline int atomicMin(int *a, int v) {

@@ -105,7 +105,14 @@ def test_force_stop_before_start_returns_input(ctx, plp):
     assert np.array_equal(out["pt_pos_w"], prob.pt_pos_w) and out["iters_first"] == 0
 
 
-@pytest.mark.parametrize("n_kf,huber", [(2, True), (12, True), (12, False)])
+def test_local_window_larger_than_shared_memory_path(ctx, orc, plp):
+    """40 non-fixed keyframes (> 32): the reduced camera system is dense in HBM (FP64 atomics, blocked Cholesky with DMMA
+    trailing updates, ba_chol.cu) instead of in shared memory -- same LM path and result as the oracle."""
+    prob = ba_data.make_ba_problem(71, n_local=40, n_fixed=8, n_points=1500, n_lines=200, n_plane_pts=50)
+    _compare(_solve_gpu(ctx, plp, prob), ba_data.oracle_local_ba(orc, prob), prob, orc=orc)
+
+
+@pytest.mark.parametrize("n_kf,huber", [(2, True), (12, True), (12, False), (72, True)])
 def test_global_ba(ctx, orc, plp, n_kf, huber):
     # optimize::global_bundle_adjuster: only keyframe 0 is fixed, one optimize(20) with / without the Huber kernel.
     # n_kf = 2 is the map-initialisation call (module/initializer.cc:306-307).

@@ -1,7 +1,7 @@
 """The plane RANSAC DEVICE code (structure-plp-slam_b200/csrc/plane_kernels.cuh) executed on the CPU: tests/cta_emu compiles
 the same kernel text for the host (one host thread per CUDA thread, a pthread barrier for __syncthreads, blocks one
 after the other) and this test compares it with the oracle bit for bit.  It checks the kernels' logic -- indexing, phase
-structure, replay bookkeeping -- in a container without a GPU; the GPU parity run is tests/test_zz_plane_gpu.py."""
+structure, replay bookkeeping -- in a container without a GPU; the GPU parity run is tests/test_plane_gpu.py."""
 import ctypes as C
 import shutil
 import subprocess

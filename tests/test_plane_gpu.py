@@ -1,15 +1,13 @@
 """GPU parity: Planar_Mapping_module plane RANSAC through the C ABI vs the oracle (both compile the same planemath.h text
 without FMA contraction: equation, error, inlier flags and status must be bit-identical).
 
-This kernel was written after the round's GPU minutes were spent: its first execution on a B200 is the driver's
-round-end run.  The file sorts last and the tests are non-strict xfail so that a defect here cannot mask the verified
-suite; an XPASS in the log means the path is parity-green."""
+Verified on a B200 since round 1 (GPUTEST_r01: all cases passed)."""
 import numpy as np
 import pytest
 
 import plane_data
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU execution happens at round end")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("seed", range(5))

@@ -40,7 +40,7 @@ if [[ " $WHAT " == *" prof "* ]]; then
   echo "launch list exit $?"
   # (2) full capture of the hot kernels of one warm step (setup extraction = 11 matched launches, a step = 14)
   timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:"fast_cells_kernel_v2|blur_tiles_kernel|quadtree_kernel|describe_kernel|point_match_kernel|pose_opt_kernel|pyr_resize_kernel" \
+      -k regex:"fast_cells_kernel_v2|blur_tiles|quadtree_kernel|describe_kernel|point_match_kernel|pose_opt_kernel|pyr_resize_kernel" \
       -s 53 -c 14 -o gpurun_out/prof_${TAG} -f python bench.py $FE > gpurun_out/bench_under_ncu_full_${TAG}.log 2>&1
   echo "full capture exit $?"
 fi
