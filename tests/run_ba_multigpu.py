@@ -30,7 +30,9 @@ def main():
     dist.broadcast_object_list(uid, src=0)
     comm = BaComm(ctx, uid[0], world, rank)
     ok = True
-    for seed, kw in [(5, dict(n_local=8, n_fixed=4, n_points=600, n_lines=100, n_plane_pts=30)), (42, dict())]:
+    for seed, kw in [(5, dict(n_local=8, n_fixed=4, n_points=600, n_lines=100, n_plane_pts=30)), (42, dict()),
+                     # > 32 non-fixed keyframes: reduced system dense in HBM, 1 all-reduce of 0.5 MB per try
+                     (71, dict(n_local=40, n_fixed=8, n_points=1500, n_lines=200, n_plane_pts=50))]:
         prob = ba_data.make_ba_problem(seed, **kw)
         sub = prob.shard(world, rank, shard_boundaries, shard_edges)
         st = sub.struct()
