@@ -357,7 +357,7 @@ def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_b
     return res
 
 
-def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
+def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_baseline=False):
     """BASELINE configs[4]: EuRoC-like rectified stereo 752x480, full point + line front end per stereo frame, frames
     sharded over ranks with no collective: ORB left + ORB right (frame.cc:456-457), match::stereo::compute
     (frame.cc:470-480), LSD + LBD left + right (frame.cc:458-463)."""
@@ -440,6 +440,47 @@ def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
     n_left = nk[0].download(np.int32, (batch,))
     n_lines = nl[0].download(np.int32, (batch,))
     stereo_ok = float(np.mean([(xr[b, :n_left[b]] >= 0).sum() for b in range(batch)]))
+    # e2e: pinned host stereo pairs in (left on the first stream, right on the second), everything frame::frame keeps
+    # out (keypoints, descriptors, counts, stereo_x_right, depths, keylines, LBD rows, line functions of both images)
+    from plpslam_b200.tracking import PinnedBuffer
+    pin_l, pin_r = PinnedBuffer.from_array(ctx, left), PinnedBuffer.from_array(ctx, right)
+    outs = [(ctx, d) for d in (kp[0], ds[0], nk[0], d_xr, d_dp, kl[0], lb[0], fn[0], nl[0])] + \
+           [(ctx_r, d) for d in (kp[1], ds[1], nk[1], kl[1], lb[1], fn[1], nl[1])]
+    pin_out = [PinnedBuffer(ctx, d.nbytes) for _, d in outs]
+
+    def e2e_step():
+        ctx._check(lib.plp_dev_upload_async(ctx_r.handle, d_r.ptr, pin_r.ptr, C.c_size_t(pin_r.nbytes)))
+        ctx._check(lib.plp_dev_upload_async(ctx.handle, d_l.ptr, pin_l.ptr, C.c_size_t(pin_l.nbytes)))
+        step()
+        for (cx, d), pb in zip(outs, pin_out):
+            cx._check(lib.plp_dev_download_async(cx.handle, pb.ptr, d.ptr, C.c_size_t(d.nbytes)))
+        ctx.sync()
+        ctx_r.sync()
+
+    e2e_step()
+    barrier()
+    n_e2e = max(2, steps // 3)
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / n_e2e
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=torch.cuda.current_device())
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d, d2h = int(pin_l.nbytes + pin_r.nbytes), int(sum(pb.nbytes for pb in pin_out))
+    for pb in [pin_l, pin_r] + pin_out:
+        pb.free()
+    cpu = None
+    if cpu_baseline and rank == 0:
+        import oracle_api
+        orc = oracle_api.Oracle()
+        cores = orc.host_cpus()
+        ns = int(min(batch, max(16, 2 * cores)))
+        r = orc.stereo_frontend_batch_mt(oracle_api.orb_params(), left[:ns], right[:ns], bf, baseline, cores)
+        cpu = {"value": ns / r["seconds"], "unit": "stereo frames/s", "cores": cores, "kind": "port",
+               "sample": f"{ns} stereo frames over {cores} native host threads ({r['seconds']:.2f} s)"}
     ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 1))
     for _ in range(min(steps, 2)):
         step()
@@ -460,7 +501,9 @@ def bench_stereo(pkg, ctx, stream, rank, world, steps, warmup, batch, seed):
                        "stereo_frames_per_step_per_gpu": batch, "mean_left_keypoints": float(n_left.mean()),
                        "mean_stereo_matches": stereo_ok, "mean_left_keylines": float(n_lines.mean()),
                        "parallelism": f"stereo frames sharded over {world} GPU(s), no data-path collective"},
-            "gpu_launches": int(launches), "kernel_time_shares": shares}
+            "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "stereo frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "cpu_baseline": cpu, "gpu_launches": int(launches), "kernel_time_shares": shares}
 
 
 BA_CONFIGS = {
@@ -876,7 +919,8 @@ def main():
             print(json.dumps(r))
         return
     if args.only_stereo:
-        r = bench_stereo(pkg, ctx, stream, rank, world, args.steps, args.warmup, args.stereo_batch, args.seed)
+        r = bench_stereo(pkg, ctx, stream, rank, world, args.steps, args.warmup, args.stereo_batch, args.seed,
+                         world == 1 and not args.no_cpu_baseline)
         if rank == 0:
             print(json.dumps(r))
         return
@@ -1072,13 +1116,17 @@ def main():
         if "cpu_baseline" in r:
             cfg_extra["line_frontend"]["cpu_port_frames_per_s"] = round(r["cpu_baseline"]["value"], 1)
     if not args.no_stereo:
-        r = bench_stereo(pkg, ctx, stream, rank, world, max(3, args.steps // 2), args.warmup, args.stereo_batch, args.seed)
+        r = bench_stereo(pkg, ctx, stream, rank, world, max(3, args.steps // 2), args.warmup, args.stereo_batch, args.seed,
+                         world == 1 and not args.no_cpu_baseline)
         detail["stereo_frontend"] = r
         cfg_extra["stereo_frontend"] = {"stereo_frames_per_s": round(r["value"], 1),
                                         "mean_left_keylines": round(r["config"]["mean_left_keylines"], 1),
                                         "mean_left_keypoints": round(r["config"]["mean_left_keypoints"], 1),
                                         "mean_stereo_matches": round(r["config"]["mean_stereo_matches"], 1),
-                                        "stereo_frames_per_step_per_gpu": args.stereo_batch}
+                                        "stereo_frames_per_step_per_gpu": args.stereo_batch,
+                                        "e2e_stereo_frames_per_s": round(r["e2e"]["value"], 1)}
+        if r.get("cpu_baseline"):
+            cfg_extra["stereo_frontend"]["cpu_port_stereo_frames_per_s"] = round(r["cpu_baseline"]["value"], 1)
     if rank == 0 and world == 1 and not args.no_mapping:
         try:
             detail["mapping_matchers"] = bench_mapping(pkg, ctx, not args.no_cpu_baseline)

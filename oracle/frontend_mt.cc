@@ -162,4 +162,64 @@ int orc_line_extract_batch_mt(const uint8_t *imgs, int batch, int rows, int cols
     return batch;
 }
 
+/* one rectified stereo frame of frame::frame (data/frame.cc:456-480): ORB left + right, match::stereo::compute, LSD + LBD
+ * left + right; frames spread over `threads` native threads */
+int orc_stereo_frontend_batch_mt(const orc_orb_params *p, const orc_lsd_config *cfg, const uint8_t *left, const uint8_t *right,
+                                 int batch, int rows, int cols, float focal_x_baseline, float true_baseline, int threads,
+                                 int pin, int32_t *n_kp_out, int32_t *n_stereo_out, int32_t *n_lines_out, double *seconds_out) {
+    if (threads < 1) threads = 1;
+    const int L = (int)p->num_levels;
+    std::vector<float> sf(L), isf(L), ls(L), ils(L);
+    std::vector<uint32_t> nk(L);
+    int32_t umax[16];
+    orc_orb_tables(p, sf.data(), isf.data(), ls.data(), ils.data(), nk.data(), umax);
+    std::vector<int32_t> lw(L), lh(L);
+    orc_orb_level_sizes(p, rows, cols, lw.data(), lh.data());
+    size_t pyr_bytes = 0;
+    for (int l = 0; l < L; ++l) pyr_bytes += (size_t)lw[l] * lh[l];
+    const int cap = 4 * (int)p->max_num_keypts + 64 * L, lcap = 8192;
+    std::atomic<int> next(0);
+    const std::vector<int> cpus = allowed_cpus();
+    auto worker = [&](int tix) {
+        if (pin && threads > 1) pin_thread(cpus, tix);
+        std::vector<orc_keypoint> kl_(cap), kr_(cap);
+        std::vector<uint8_t> dl((size_t)cap * 32), dr((size_t)cap * 32), pl(pyr_bytes), pr(pyr_bytes);
+        std::vector<float> xr(cap), dp(cap);
+        std::vector<orc_keyline> kl(lcap);
+        std::vector<uint8_t> lbd((size_t)lcap * 32);
+        std::vector<double> fn((size_t)lcap * 3);
+        for (;;) {
+            const int b = next.fetch_add(1);
+            if (b >= batch) break;
+            const uint8_t *il = left + (size_t)b * rows * cols, *ir = right + (size_t)b * rows * cols;
+            const int nl = orc_orb_extract(p, il, rows, cols, cols, nullptr, 0, kl_.data(), dl.data(), cap, pl.data(), nullptr,
+                                           0, nullptr, nullptr);
+            const int nr = orc_orb_extract(p, ir, rows, cols, cols, nullptr, 0, kr_.data(), dr.data(), cap, pr.data(), nullptr,
+                                           0, nullptr, nullptr);
+            n_kp_out[2 * b] = nl;
+            n_kp_out[2 * b + 1] = nr;
+            int ns = 0;
+            if (nl > 0 && nr > 0) {
+                orc_stereo_compute(pl.data(), pr.data(), lw.data(), lh.data(), L, kl_.data(), dl.data(), nl, kr_.data(),
+                                   dr.data(), nr, sf.data(), isf.data(), focal_x_baseline, true_baseline, xr.data(), dp.data(),
+                                   nullptr);
+                for (int i = 0; i < nl; ++i) ns += dp[i] > 0.0f ? 1 : 0;
+            }
+            n_stereo_out[b] = ns;
+            n_lines_out[2 * b] = orc_line_extract(il, cols, rows, cols, cfg, kl.data(), lbd.data(), fn.data(), lcap);
+            n_lines_out[2 * b + 1] = orc_line_extract(ir, cols, rows, cols, cfg, kl.data(), lbd.data(), fn.data(), lcap);
+        }
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    if (threads == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(worker, t);
+        for (auto &t : pool) t.join();
+    }
+    if (seconds_out) *seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return batch;
+}
+
 }  // extern "C"

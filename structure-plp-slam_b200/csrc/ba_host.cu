@@ -181,21 +181,25 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
         PLP_REQUIRE(pt_plane[l] < 0, "at most one plane edge per landmark (landmark::get_Owning_Plane)");
         pt_plane[l] = i;
     }
-    // free degree per landmark -> landmarks per batch; edge-balanced CTA ranges
+    // free degree per landmark -> landmarks per batch; CTA ranges balanced by the cost model of ba_linearize_kernel: a
+    // warp owns a landmark, a point landmark costs one round over its (<= 32) edges, a line landmark one round per edge
+    // (numeric Jacobians: 21 evaluations spread over the lanes) plus the same per-landmark tail
     const int n_lm = n_pts + n_lines;
+    int w_point = 4, w_line0 = 2;
+    if (const char *wenv = getenv("PLP_BA_COST_WEIGHTS")) sscanf(wenv, "%d,%d", &w_point, &w_line0);  // tuning aid
     int max_deg = 1;
     std::vector<int> deg_e(n_lm + 1, 0);
     for (int l = 0; l < n_pts; ++l) {
         int d = 0;
         for (int e = pt_off[l]; e < pt_off[l + 1]; ++e) d += hidx[p->pt_edge_kf[e]] >= 0;
         max_deg = std::max(max_deg, d);
-        deg_e[l + 1] = deg_e[l] + (pt_off[l + 1] - pt_off[l]) + 1;
+        deg_e[l + 1] = deg_e[l] + w_point * (1 + (pt_off[l + 1] - pt_off[l] - 1) / 32);  // lane = edge: one round per 32 edges
     }
     for (int l = 0; l < n_lines; ++l) {
         int d = 0;
         for (int e = ln_off[l]; e < ln_off[l + 1]; ++e) d += hidx[p->line_edge_kf[e]] >= 0;
         max_deg = std::max(max_deg, d);
-        deg_e[n_pts + l + 1] = deg_e[n_pts + l] + 4 * (ln_off[l + 1] - ln_off[l]) + 1;  // numeric Jacobians: ~4x cost
+        deg_e[n_pts + l + 1] = deg_e[n_pts + l] + w_line0 + (ln_off[l + 1] - ln_off[l]);  // one warp round per line edge
     }
     PLP_REQUIRE(max_deg <= n_free, "a landmark is observed twice by the same keyframe");
     const int pool_cap = ba_pool_capacity(n_free, n_free * (n_free + 1) / 2, max_deg);

@@ -8,7 +8,7 @@
 // (Huber in the first optimize(5), none in the second optimize(10), outliers = chi2 > 5.991|7.815 or depth <= 0),
 // optional unary point-to-plane edges.  g2o's BlockSolver + OptimizationAlgorithmLevenberg are restated.
 //
-// Work decomposition (one LM "try" = 5 small kernels, no host synchronisation inside an optimize() chunk):
+// Work decomposition (one LM "try" = 5 kernels, no host synchronisation inside an optimize() chunk):
 //   ba_decide_kernel   1 CTA    accept/reject of the previous try (rho test), lambda / nu update, iteration count
 //   ba_linearize_kernel G CTAs  landmark-sharded: one warp per landmark evaluates its edges (residual, Jacobians,
 //                               Huber weight), forms Hll, bl, (Hll+lambda I)^-1 and the per-edge blocks
@@ -21,7 +21,8 @@
 //                               exchanges: one ncclAllReduce(sum) of this vector per try (ba_nccl.cu)
 //   ba_solve_kernel    1 CTA    dense Cholesky of the 6N x 6N reduced system in shared memory, dp, trial poses
 //   ba_update_kernel   G CTAs   back-substitution dl = Dinv (bl - W^T dp), trial landmarks, errors at the trial
-//                               state (kept even if the step is rejected, like g2o), chi2 / scale partial sums
+//                               state (kept even if the step is rejected, like g2o), chi2 / scale partial sums; the CTA
+//                               that finishes last adds the partials up (fixed order)
 // Linearisation is recomputed on every try (also after a rejection) instead of being cached: the numbers are
 // identical and it removes all bookkeeping.  Numeric Jacobians (delta = 1e-9 central differences) are used where
 // the reference has no linearizeOplus (line edges, plane edges), see g2o BaseBinaryEdge::linearizeOplus.
@@ -159,6 +160,8 @@ __device__ bool inv_small(const double *A, int D, double *Ai) {
     return true;
 }
 
+__device__ __noinline__ bool inv_small_cold(const double *A, int D, double *Ai) { return inv_small(A, D, Ai); }
+
 // ---------------------------------------------------------------------------------------------------------
 // edge evaluation shared by linearize / update / classify
 // ---------------------------------------------------------------------------------------------------------
@@ -189,12 +192,16 @@ struct BaPoolEntry {
     int h, pad;     // free-keyframe index of the edge (large path: the accumulation walks the pool, not the slot table)
 };
 
+struct BaLineScratch {  // one line edge at a time: its numeric Jacobians, residual and weight, written by the evaluating lanes
+    double jp[12], jl[8], r[2], w, pad;
+};
+
 struct BaSmem {  // the pool (B.pool_cap entries) and the partial system follow in dynamic shared memory
     unsigned kfmask[kBaMaxFree];  // per free keyframe: which landmarks of the batch observe it (bit = landmark in batch)
     double pert_line[kBaWarps][8][6];  // per warp: the 8 perturbed lines of its landmark
+    BaLineScratch scr[kBaWarps];
     double hll[kBaWarps][16], bl[kBaWarps][4], dinv[kBaWarps][16], dl[kBaWarps][4];
     short slot[kBaWarps][kBaMaxFree];  // landmark-in-batch x free keyframe -> pool index (-1: none)
-    int pool_base[kBaWarps + 1];
     int warp_cnt[kBaWarps];
     double red[kBaWarps][2];
 };
@@ -205,6 +212,135 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// inverse of the symmetric positive definite D x D landmark block (Hll + lambda I) by an unrolled Cholesky factorisation:
+// everything stays in registers.  Returns false when a pivot is not positive (the caller falls back to inv_small).
+template <int D>
+__device__ __forceinline__ bool inv_spd(const double *H /*D x D, full*/, double *Hi) {
+    double l[D][D], li[D][D];  // L (lower) and L^-1 (lower)
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        double d = H[c * D + c];
+#pragma unroll
+        for (int m = 0; m < c; ++m) d -= l[c][m] * l[c][m];
+        ok = ok && (d > 0.0) && isfinite(d);
+        const double inv = 1.0 / sqrt(d);
+        l[c][c] = inv;  // the diagonal keeps 1 / l_cc
+#pragma unroll
+        for (int r = c + 1; r < D; ++r) {
+            double v = H[r * D + c];
+#pragma unroll
+            for (int m = 0; m < c; ++m) v -= l[r][m] * l[c][m];
+            l[r][c] = v * inv;
+        }
+    }
+    // L^-1 by forward substitution on the identity
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        li[c][c] = l[c][c];
+#pragma unroll
+        for (int r = c + 1; r < D; ++r) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = c; m < r; ++m) v -= l[r][m] * li[m][c];
+            li[r][c] = v * l[r][r];
+        }
+    }
+    // H^-1 = L^-T L^-1
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = a; c < D; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int m = c; m < D; ++m) s += li[m][a] * li[m][c];
+            Hi[a * D + c] = s;
+            Hi[c * D + a] = s;
+        }
+    return ok;
+}
+
+// lane 0 of a landmark's warp: damped block inverse, Dinv bl, the per-landmark outputs the back-substitution reads
+template <int D>
+__device__ __forceinline__ void finish_landmark(const BaDev &B, BaSmem &S, int warp, bool is_line, int li, const double *hll,
+                                                const double *bl, bool any_active, bool init_mode, double lambda,
+                                                double &maxdiag) {
+    double H[D * D];
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = a; c < D; ++c) {
+            H[a * D + c] = hll[q];
+            H[c * D + a] = hll[q];
+            ++q;
+        }
+    if (any_active) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) maxdiag = fmax(maxdiag, fabs(H[a * D + a]));
+    }
+#pragma unroll
+    for (int a = 0; a < D; ++a) H[a * D + a] += lambda;
+    double Di[D * D];
+    bool ok = false;
+    if (any_active && !init_mode) {
+        ok = inv_spd<D>(H, Di);
+        if (!ok) {  // numerically indefinite block: pivoted Gauss-Jordan (cold; its operands live in local memory)
+            double Hc[D * D], Dc[D * D];
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) Hc[i] = H[i];
+            ok = inv_small_cold(Hc, D, Dc);
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) Di[i] = Dc[i];
+        }
+    }
+    if (!ok) {
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) Di[i] = 0.0;
+    }
+    double *Dg = (is_line ? B.ln_Dinv + 16 * (size_t)li : B.pt_Dinv + 16 * (size_t)li);
+    double *bg = (is_line ? B.ln_bl + 4 * (size_t)li : B.pt_bl + 4 * (size_t)li);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) {
+        S.dinv[warp][i] = Di[i];
+        Dg[i] = Di[i];
+    }
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        double s = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) s += Di[a * D + c] * bl[c];
+        S.dl[warp][a] = s;
+        S.bl[warp][a] = bl[a];
+        bg[a] = bl[a];
+    }
+    (is_line ? B.ln_active : B.pt_active)[li] = (any_active && (ok || init_mode)) ? 1 : 0;
+}
+
+// Y = W Dinv and gpe = bpe - W (Dinv bl) of a landmark's pool entries, one output per lane and round
+template <int D>
+__device__ __forceinline__ void pool_products(BaSmem &S, BaPoolEntry *pool, int warp, int lane, int pb, int pn) {
+    constexpr int kPer = 6 * D + 6;
+    const double *Di = S.dinv[warp], *dl = S.dl[warp];
+    for (int idx = lane; idx < pn * kPer; idx += 32) {
+        const int i = idx / kPer, o = idx - i * kPer;
+        BaPoolEntry &pe = pool[pb + i];
+        if (o < 6 * D) {
+            const int a = o / D, c = o - a * D;
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) s += pe.W[a * D + k] * Di[k * D + c];
+            pe.Y[o] = s;
+        } else {
+            const int a = o - 6 * D;
+            double gs = pe.bpe[a];
+#pragma unroll
+            for (int c = 0; c < D; ++c) gs -= pe.W[a * D + c] * dl[c];
+            pe.gpe[a] = gs;
+        }
+    }
+}
+
 // =========================================================================================================
 // ba_linearize_kernel
 // =========================================================================================================
@@ -212,6 +348,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 // (no atomics, fixed summation order).  kLarge = true (global BA / large local windows): the reduced system is the dense
 // block-upper-triangular `packed` vector in HBM (L2-resident: 5.8 MB for 200 keyframes) and every landmark adds its
 // -Y_i W_j^T / A blocks with FP64 atomics; nothing in the kernel is sized by the number of keyframes any more.
+//
+// Phase 1, one warp per landmark.  Point landmarks (analytic Jacobians): lane = edge.  Line landmarks (numeric Jacobians:
+// 21 evaluations of the error function per edge -- the estimate, 6 x 2 perturbed poses, 4 x 2 perturbed lines): one edge
+// at a time, lane = evaluation, the central differences by one shuffle, then lane = output entry of Hll / bl / W / A / b.
 template <bool kLarge>
 __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
     extern __shared__ __align__(16) uint8_t ba_smem_raw[];
@@ -235,6 +375,10 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
     double chi_acc = 0.0, maxdiag = 0.0;
     const int lm_begin = B.cta_ranges[blockIdx.x], lm_end = B.cta_ranges[blockIdx.x + 1];
     const int LB = B.batch_landmarks;  // landmarks per batch (<= kBaWarps), LB * max_free_degree <= B.pool_cap
+    // phase 2 ownership: thread t < 504 owns entry (r, c) = (t % 36) of the blocks p = t / 36, t / 36 + 14, ...
+    const int own_rc = tid % 36, own_r = own_rc / 6, own_c = own_rc - own_r * 6, own_p0 = tid / 36;
+    const int own_a = own_r < own_c ? own_r : own_c, own_b = own_r < own_c ? own_c : own_r;
+    const int own_tri = own_a * 6 - own_a * (own_a - 1) / 2 + (own_b - own_a);
     __syncthreads();
 
     for (int batch0 = lm_begin; batch0 < lm_end; batch0 += LB) {
@@ -246,11 +390,10 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
             for (int i = tid; i < kBaWarps * kBaMaxFree; i += kBaThreads) (&S.slot[0][0])[i] = -1;
             for (int i = tid; i < kBaMaxFree; i += kBaThreads) S.kfmask[i] = 0u;
         }
-        int e0 = 0, e1 = 0, D = 3;
+        int e0 = 0, e1 = 0;
         bool is_line = false;
         if (has_lm) {
             is_line = lm >= B.n_pts;
-            D = is_line ? 4 : 3;
             const int *off = is_line ? B.ln_off : B.pt_off;
             const int li = is_line ? lm - B.n_pts : lm;
             e0 = off[li];
@@ -264,96 +407,62 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
         for (int o = 16; o > 0; o >>= 1) nfree += __shfl_xor_sync(0xffffffffu, nfree, o);
         if (lane == 0) S.warp_cnt[warp] = has_lm ? nfree : 0;
         __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int w = 0; w < kBaWarps; ++w) {
-                S.pool_base[w] = acc;
-                acc += S.warp_cnt[w];
+        // pool base of this warp = exclusive prefix of the per-warp counts (every warp scans the 16 counts itself)
+        int pb;
+        {
+            const int cnt = lane < kBaWarps ? S.warp_cnt[lane] : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < kBaWarps; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
-            S.pool_base[kBaWarps] = acc;
+            pb = __shfl_sync(0xffffffffu, incl - cnt, warp);
         }
-        __syncthreads();
+        const int pn = has_lm ? nfree : 0;
         // ---- phase 1: one warp per landmark
-        if (has_lm) {
-            const int li = is_line ? lm - B.n_pts : lm;
-            const double *Lm = is_line ? lines + 6 * (size_t)li : nullptr;
-            const double *X = is_line ? nullptr : pts + 3 * (size_t)li;
-            if (is_line && lane < 8) {  // perturbed lines for the numeric Jacobian w.r.t. the line vertex
-                double v[4] = {0, 0, 0, 0};
-                v[lane >> 1] = (lane & 1) ? -kDelta : kDelta;
-                line_oplus(Lm, v, S.pert_line[warp][lane]);
-            }
-            __syncwarp();
-            double hll[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, bl[4] = {0, 0, 0, 0};  // upper triangle of Hll (D<=4)
+        if (has_lm && !is_line) {
+            const int li = lm;
+            const double *X = pts + 3 * (size_t)li;
+            double hll[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};  // upper triangle of Hll
             bool any_active = false;
-            int pool_cursor = S.pool_base[warp];
+            int pool_cursor = pb;
             for (int ebase = e0; ebase < e1; ebase += 32) {
                 const int e = ebase + lane;
-                const bool in = e < e1;
-                const bool active = in && elevel[e] == 0;
-                double Jp[18], Jl[12], r[3] = {0, 0, 0}, w = 0;
-                int Rr = 2, h = -1;
+                const bool active = e < e1 && elevel[e] == 0;
+                double Jp[18], Jl[9], r[3] = {0, 0, 0}, w = 0;
+                int h = -1;
                 if (active) {
                     const int k = ekf[e];
                     h = B.kf_hidx[k];
                     const Pose &P = poses[k];
-                    double chi2;
-                    if (!is_line) {
-                        const float *obs = B.pt_obs + 3 * (size_t)e;
-                        const double info = B.pt_info[e];
-                        double pc[3];
-                        chi2 = eval_pt(cam, P, X, obs, info, r, pc);
-                        const bool stereo = !(obs[2] < 0);
-                        Rr = stereo ? 3 : 2;
-                        se3::point_jac_pose(cam, pc, stereo, Jp);
-                        double Jl9[9];
-                        se3::point_jac_landmark(cam, P.R, pc, stereo, Jl9);
-                        for (int q = 0; q < 9; ++q) Jl[q] = Jl9[q];
-                        w = info;
-                        B.pt_chi2[e] = chi2;
-                        double rho0 = chi2, rho1 = 1.0;
-                        if (robust) se3::huber(chi2, B.delta_pt, rho0, rho1);
-                        chi_acc += rho0;
-                        w *= rho1;
-                    } else {
-                        const float *obs = B.ln_obs + 4 * (size_t)e;
-                        const double info = B.ln_info[e];
-                        chi2 = eval_ln(cam, P, Lm, obs, info, r);
-                        const double scalar = 1.0 / (2 * kDelta);
-                        const Pose *pp = B.pert_pose + 12 * (size_t)k;
-#pragma unroll
-                        for (int d = 0; d < 6; ++d) {
-                            double ep[2], em[2];
-                            eval_ln(cam, pp[2 * d], Lm, obs, info, ep);
-                            eval_ln(cam, pp[2 * d + 1], Lm, obs, info, em);
-                            Jp[d] = scalar * (ep[0] - em[0]);
-                            Jp[6 + d] = scalar * (ep[1] - em[1]);
-                        }
-#pragma unroll
-                        for (int d = 0; d < 4; ++d) {
-                            double ep[2], em[2];
-                            eval_ln(cam, P, S.pert_line[warp][2 * d], obs, info, ep);
-                            eval_ln(cam, P, S.pert_line[warp][2 * d + 1], obs, info, em);
-                            Jl[d] = scalar * (ep[0] - em[0]);
-                            Jl[4 + d] = scalar * (ep[1] - em[1]);
-                        }
-                        w = info;
-                        B.ln_chi2[e] = chi2;
-                        double rho0 = chi2, rho1 = 1.0;
-                        if (robust) se3::huber(chi2, B.delta_ln, rho0, rho1);
-                        chi_acc += rho0;
-                        w *= rho1;
-                    }
-                    // landmark block contributions
+                    const float *obs = B.pt_obs + 3 * (size_t)e;
+                    const double info = B.pt_info[e];
+                    double pc[3];
+                    const double chi2 = eval_pt(cam, P, X, obs, info, r, pc);
+                    const bool stereo = !(obs[2] < 0);
+                    // the third row of both Jacobians and r[2] are zero for a monocular observation: always 3 rows
+                    se3::point_jac_pose(cam, pc, stereo, Jp);
+                    se3::point_jac_landmark(cam, P.R, pc, stereo, Jl);
+                    w = info;
+                    B.pt_chi2[e] = chi2;
+                    double rho0 = chi2, rho1 = 1.0;
+                    if (robust) se3::huber(chi2, B.delta_pt, rho0, rho1);
+                    chi_acc += rho0;
+                    w *= rho1;
                     int q = 0;
-                    for (int a = 0; a < D; ++a) {
-                        for (int c = a; c < D; ++c) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                        for (int c = a; c < 3; ++c) {
                             double s = 0;
-                            for (int rr = 0; rr < Rr; ++rr) s += Jl[rr * D + a] * w * Jl[rr * D + c];
+#pragma unroll
+                            for (int rr = 0; rr < 3; ++rr) s += Jl[rr * 3 + a] * w * Jl[rr * 3 + c];
                             hll[q++] += s;
                         }
                         double s = 0;
-                        for (int rr = 0; rr < Rr; ++rr) s += Jl[rr * D + a] * (-w * r[rr]);
+#pragma unroll
+                        for (int rr = 0; rr < 3; ++rr) s += Jl[rr * 3 + a] * (-w * r[rr]);
                         bl[a] += s;
                     }
                 }
@@ -364,21 +473,30 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
                 if (freee) {
                     const int pi = pool_cursor + __popc(bal & ((1u << lane) - 1));
                     BaPoolEntry &pe = pool[pi];
+                    double *Wg = B.pt_W + 24 * (size_t)e;  // W is needed again by the back-substitution
+#pragma unroll
                     for (int a = 0; a < 6; ++a) {
-                        for (int c = 0; c < D; ++c) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
                             double s = 0;
-                            for (int rr = 0; rr < Rr; ++rr) s += Jp[rr * 6 + a] * w * Jl[rr * D + c];
-                            pe.W[a * D + c] = s;
+#pragma unroll
+                            for (int rr = 0; rr < 3; ++rr) s += Jp[rr * 6 + a] * w * Jl[rr * 3 + c];
+                            pe.W[a * 3 + c] = s;
+                            Wg[a * 3 + c] = s;
                         }
                         double s = 0;
-                        for (int rr = 0; rr < Rr; ++rr) s += Jp[rr * 6 + a] * (-w * r[rr]);
+#pragma unroll
+                        for (int rr = 0; rr < 3; ++rr) s += Jp[rr * 6 + a] * (-w * r[rr]);
                         pe.bpe[a] = s;
                     }
                     int q = 0;
+#pragma unroll
                     for (int a = 0; a < 6; ++a)
+#pragma unroll
                         for (int c = a; c < 6; ++c) {
                             double s = 0;
-                            for (int rr = 0; rr < Rr; ++rr) s += Jp[rr * 6 + a] * w * Jp[rr * 6 + c];
+#pragma unroll
+                            for (int rr = 0; rr < 3; ++rr) s += Jp[rr * 6 + a] * w * Jp[rr * 6 + c];
                             pe.A[q++] = s;
                         }
                     pe.h = h;
@@ -386,19 +504,17 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
                         S.slot[lmb][h] = (short)pi;
                         atomicOr(&S.kfmask[h], 1u << lmb);
                     }
-                    // W is needed again by the back-substitution
-                    double *Wg = (is_line ? B.ln_W : B.pt_W) + 24 * (size_t)e;
-                    for (int q2 = 0; q2 < 6 * D; ++q2) Wg[q2] = pe.W[q2];
                 }
                 pool_cursor += __popc(bal);
             }
             // plane edge (unary, numeric Jacobian; Huber delta = 1 in both phases)
-            if (!is_line && lane == 0) {
+            if (lane == 0) {
                 const int pe_i = B.pt_plane ? B.pt_plane[li] : -1;
                 if (pe_i >= 0) {
                     const double *fn = B.pl_fn + 4 * (size_t)pe_i;
                     const double err = eval_plane(X, fn);
                     double Jn[3];
+#pragma unroll
                     for (int d = 0; d < 3; ++d) {
                         double Xp[3] = {X[0], X[1], X[2]}, Xm[3] = {X[0], X[1], X[2]};
                         Xp[d] += kDelta;
@@ -410,7 +526,9 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
                     chi_acc += rho0;
                     B.pl_err[pe_i] = err;
                     int q = 0;
+#pragma unroll
                     for (int a = 0; a < 3; ++a) {
+#pragma unroll
                         for (int c = a; c < 3; ++c) hll[q++] += Jn[a] * rho1 * Jn[c];
                         bl[a] += Jn[a] * (-rho1 * err);
                     }
@@ -418,64 +536,134 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
                 }
             }
             any_active = __any_sync(0xffffffffu, any_active);
-            // reduce Hll / bl over the lanes
-            const int nh = D * (D + 1) / 2;
-            for (int q = 0; q < nh; ++q) hll[q] = warp_sum(hll[q]);
-            for (int a = 0; a < D; ++a) bl[a] = warp_sum(bl[a]);
-            if (lane == 0) {
-                double H[16];
-                int q = 0;
-                for (int a = 0; a < D; ++a)
-                    for (int c = a; c < D; ++c) {
-                        H[a * D + c] = hll[q];
-                        H[c * D + a] = hll[q];
-                        ++q;
-                    }
-                if (any_active)
-                    for (int a = 0; a < D; ++a) maxdiag = fmax(maxdiag, fabs(H[a * D + a]));
-                for (int a = 0; a < D; ++a) H[a * D + a] += lambda;
-                double Di[16];
-                bool ok = any_active && !init_mode && inv_small(H, D, Di);
-                if (!ok)
-                    for (int i = 0; i < 16; ++i) Di[i] = 0.0;
-                double *Dg = (is_line ? B.ln_Dinv + 16 * (size_t)li : B.pt_Dinv + 16 * (size_t)li);
-                double *bg = (is_line ? B.ln_bl + 4 * (size_t)li : B.pt_bl + 4 * (size_t)li);
-                for (int i = 0; i < D * D; ++i) {
-                    S.dinv[warp][i] = Di[i];
-                    Dg[i] = Di[i];
-                }
-                for (int a = 0; a < D; ++a) {
-                    double s = 0;
-                    for (int c = 0; c < D; ++c) s += Di[a * D + c] * bl[c];
-                    S.dl[warp][a] = s;
-                    S.bl[warp][a] = bl[a];
-                    bg[a] = bl[a];
-                }
-                (is_line ? B.ln_active : B.pt_active)[li] = (any_active && (ok || init_mode)) ? 1 : 0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) hll[q] = warp_sum(hll[q]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) bl[a] = warp_sum(bl[a]);
+            if (lane == 0) finish_landmark<3>(B, S, warp, false, li, hll, bl, any_active, init_mode, lambda, maxdiag);
+            __syncwarp();
+            pool_products<3>(S, pool, warp, lane, pb, pn);
+        } else if (has_lm) {
+            const int li = lm - B.n_pts;
+            const double *Lm = lines + 6 * (size_t)li;
+            if (lane < 8) {  // perturbed lines for the numeric Jacobian w.r.t. the line vertex
+                double v[4] = {0, 0, 0, 0};
+                v[lane >> 1] = (lane & 1) ? -kDelta : kDelta;
+                line_oplus(Lm, v, S.pert_line[warp][lane]);
             }
             __syncwarp();
-            // Y = W Dinv, gpe = bpe - W dl for this landmark's pool entries
-            const int pb = S.pool_base[warp], pn = S.warp_cnt[warp];
-            for (int pi = pb + lane; pi < pb + pn; pi += 32) {
-                BaPoolEntry &pe = pool[pi];
-                for (int a = 0; a < 6; ++a) {
-                    double gs = pe.bpe[a];
-                    for (int c = 0; c < D; ++c) {
-                        double s = 0;
-                        for (int k = 0; k < D; ++k) s += pe.W[a * D + k] * S.dinv[warp][k * D + c];
-                        pe.Y[a * D + c] = s;
-                        gs -= pe.W[a * D + c] * S.dl[warp][c];
-                    }
-                    pe.gpe[a] = gs;
+            BaLineScratch &sc = S.scr[warp];
+            // lanes 0..9 own the upper triangle of Hll, lanes 10..13 own bl; (oa, oc) = this lane's entry
+            int oa = 0, oc = 0;
+            if (lane < 10) {
+                int q = lane;
+                while (q >= 4 - oa) {
+                    q -= 4 - oa;
+                    ++oa;
                 }
+                oc = oa + q;
+            } else if (lane < 14) {
+                oa = lane - 10;
             }
+            // second-round ownership of A (upper triangle of the 6 x 6 pose block), lanes 0..20
+            int aa = 0, ac = 0;
+            {
+                int q = lane < 21 ? lane : 0;
+                while (q >= 6 - aa) {
+                    q -= 6 - aa;
+                    ++aa;
+                }
+                ac = aa + q;
+            }
+            double hacc = 0.0;
+            bool any_active = false;
+            int pool_cursor = pb;
+            const double scalar = 1.0 / (2 * kDelta);
+            const double *Lv = lane >= 13 && lane < 21 ? S.pert_line[warp][lane - 13] : Lm;
+            for (int e = e0; e < e1; ++e) {
+                if (elevel[e] != 0) continue;  // warp-uniform
+                any_active = true;
+                const int k = ekf[e];
+                const int h = B.kf_hidx[k];
+                const float *obs = B.ln_obs + 4 * (size_t)e;
+                const double info = B.ln_info[e];
+                double ev[2] = {0, 0};
+                if (lane < 21) {
+                    const Pose &P = (lane >= 1 && lane < 13) ? B.pert_pose[12 * (size_t)k + (lane - 1)] : poses[k];
+                    eval_ln(cam, P, Lv, obs, info, ev);
+                }
+                // central differences: lane 1 + 2d (pose direction d) and lane 13 + 2d (line direction d) pair with the next lane
+                const double em0 = __shfl_down_sync(0xffffffffu, ev[0], 1), em1 = __shfl_down_sync(0xffffffffu, ev[1], 1);
+                if (lane == 0) {
+                    const double chi2 = ev[0] * (info * ev[0]) + ev[1] * (info * ev[1]);
+                    B.ln_chi2[e] = chi2;
+                    double rho0 = chi2, rho1 = 1.0;
+                    if (robust) se3::huber(chi2, B.delta_ln, rho0, rho1);
+                    chi_acc += rho0;
+                    sc.r[0] = ev[0];
+                    sc.r[1] = ev[1];
+                    sc.w = info * rho1;
+                } else if (lane < 13) {
+                    if (lane & 1) {
+                        const int d = (lane - 1) >> 1;
+                        sc.jp[d] = scalar * (ev[0] - em0);
+                        sc.jp[6 + d] = scalar * (ev[1] - em1);
+                    }
+                } else if (lane < 21) {
+                    if (lane & 1) {
+                        const int d = (lane - 13) >> 1;
+                        sc.jl[d] = scalar * (ev[0] - em0);
+                        sc.jl[4 + d] = scalar * (ev[1] - em1);
+                    }
+                }
+                __syncwarp();
+                const double w = sc.w, r0 = sc.r[0], r1 = sc.r[1];
+                if (lane < 10) {
+                    hacc += sc.jl[oa] * w * sc.jl[oc] + sc.jl[4 + oa] * w * sc.jl[4 + oc];
+                } else if (lane < 14) {
+                    hacc += sc.jl[oa] * (-w * r0) + sc.jl[4 + oa] * (-w * r1);
+                }
+                if (h >= 0) {  // warp-uniform: pool entry of a free-keyframe edge
+                    BaPoolEntry &pe = pool[pool_cursor];
+                    if (lane < 24) {
+                        const int a = lane >> 2, c = lane & 3;
+                        const double s = sc.jp[a] * w * sc.jl[c] + sc.jp[6 + a] * w * sc.jl[4 + c];
+                        pe.W[lane] = s;
+                        B.ln_W[24 * (size_t)e + lane] = s;  // W is needed again by the back-substitution
+                    } else if (lane < 30) {
+                        const int a = lane - 24;
+                        pe.bpe[a] = sc.jp[a] * (-w * r0) + sc.jp[6 + a] * (-w * r1);
+                    } else if (lane == 30) {
+                        pe.h = h;
+                        if (!kLarge) {
+                            S.slot[lmb][h] = (short)pool_cursor;
+                            atomicOr(&S.kfmask[h], 1u << lmb);
+                        }
+                    }
+                    if (lane < 21) pe.A[lane] = sc.jp[aa] * w * sc.jp[ac] + sc.jp[6 + aa] * w * sc.jp[6 + ac];
+                    ++pool_cursor;
+                }
+                __syncwarp();  // the scratch is rewritten by the next edge
+            }
+            if (lane < 10) S.hll[warp][lane] = hacc;
+            else if (lane < 14) S.bl[warp][lane - 10] = hacc;
+            __syncwarp();
+            if (lane == 0) {
+                double hll[10], bl[4];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) hll[q] = S.hll[warp][q];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) bl[a] = S.bl[warp][a];
+                finish_landmark<4>(B, S, warp, true, li, hll, bl, any_active, init_mode, lambda, maxdiag);
+            }
+            __syncwarp();
+            pool_products<4>(S, pool, warp, lane, pb, pn);
         }
         __syncthreads();
         if (kLarge) {
             // ---- phase 2 (large): the warp of a landmark adds the blocks of every pair of its free observers to the dense
             // reduced system in HBM: S(hi, hj) -= Y_i W_j^T for hi <= hj, S(h, h) += A, g(h) += gpe, bp(h) += bpe
             if (has_lm) {
-                const int pb = S.pool_base[warp], pn = S.warp_cnt[warp];
                 const int Dl = is_line ? 4 : 3;
                 const int N = B.n_free;
                 for (int w = lane; w < pn * pn * 36; w += 32) {
@@ -506,27 +694,30 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
         // ---- phase 2: every thread owns fixed entries of S / g / bp (no atomics, fixed summation order)
         // only the landmarks that observe BOTH keyframes of a block contribute: walk the set bits of the two masks
         // (ascending landmark = the summation order of a dense scan)
-        for (int ent = tid; ent < nS; ent += kBaThreads) {
-            const int p = ent / 36, rc = ent - p * 36, r = rc / 6, c = rc - r * 6;
-            const int bi = B.pair_bi[p], bj = B.pair_bj[p];
-            unsigned m = S.kfmask[bi] & S.kfmask[bj];
-            if (!m) continue;
-            double acc = 0.0;
-            while (m) {
-                const int lb = __ffs(m) - 1;
-                m &= m - 1;
-                const int si = S.slot[lb][bi], sj = S.slot[lb][bj];
-                const int Dl = (batch0 + lb) >= B.n_pts ? 4 : 3;
-                const BaPoolEntry &pi = pool[si], &pj = pool[sj];
-                double s = 0;
-                for (int q = 0; q < Dl; ++q) s += pi.Y[r * Dl + q] * pj.W[c * Dl + q];
-                acc -= s;
-                if (bi == bj) {
-                    const int a = r < c ? r : c, b2 = r < c ? c : r;
-                    acc += pi.A[a * 6 - a * (a - 1) / 2 + (b2 - a)];
+        if (tid < 504) {
+            const int n_line0 = B.n_pts - batch0;  // landmarks lb >= n_line0 of this batch are lines
+            for (int p = own_p0; p < B.n_pairs; p += 14) {
+                const int bi = B.pair_bi[p], bj = B.pair_bj[p];
+                unsigned m = S.kfmask[bi] & S.kfmask[bj];
+                if (!m) continue;
+                double acc = 0.0;
+                while (m) {
+                    const int lb = __ffs(m) - 1;
+                    m &= m - 1;
+                    const BaPoolEntry &pi = pool[S.slot[lb][bi]], &pj = pool[S.slot[lb][bj]];
+                    double s;
+                    if (lb >= n_line0) {
+                        const double *y = pi.Y + own_r * 4, *wv = pj.W + own_c * 4;
+                        s = y[0] * wv[0] + y[1] * wv[1] + y[2] * wv[2] + y[3] * wv[3];
+                    } else {
+                        const double *y = pi.Y + own_r * 3, *wv = pj.W + own_c * 3;
+                        s = y[0] * wv[0] + y[1] * wv[1] + y[2] * wv[2];
+                    }
+                    acc -= s;
+                    if (bi == bj) acc += pi.A[own_tri];
                 }
+                Ssm[p * 36 + own_rc] += acc;
             }
-            Ssm[ent] += acc;
         }
         for (int ent = tid; ent < n6; ent += kBaThreads) {
             const int bi = ent / 6, r = ent - bi * 6;
@@ -582,8 +773,20 @@ __global__ void ba_reduce_kernel(BaDev B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_sum = B.n_pairs * 36 + 12 * B.n_free + 1;
     if (i < n_sum) {
+        // fixed summation order (CTA 0, 1, ...); the loads of 8 partials are issued together
+        const double *src = B.partial + i;
+        const size_t len = (size_t)B.packed_len;
+        const int G = B.num_ctas;
         double s = 0;
-        for (int g = 0; g < B.num_ctas; ++g) s += B.partial[(size_t)g * B.packed_len + i];
+        int g = 0;
+        for (; g + 8 <= G; g += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(g + u) * len);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; g < G; ++g) s += __ldcg(src + (size_t)g * len);
         B.packed[i] = s;
     } else if (i == n_sum) {
         double m = 0;
@@ -596,7 +799,7 @@ __global__ void ba_reduce_kernel(BaDev B) {
 // =========================================================================================================
 // ba_solve_kernel: 6N x 6N blocked Cholesky in shared memory (packed lower triangle)
 // =========================================================================================================
-constexpr int kSolveThreads = 1024;
+constexpr int kSolveThreads = 512;
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
 
 __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
@@ -624,6 +827,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
     double *L = solve_smem;               // n(n+1)/2
     double *rhs = L + (size_t)n * (n + 1) / 2;  // n
     double *x = rhs + n;                  // n
+    double *Ld = x + n;                   // N x 21: the factored diagonal blocks (lower triangle row-wise, 1 / l_cc on the diagonal)
     __shared__ int s_ok;
     const double lambda = ST.lambda;
     for (int p = tid; p < B.n_pairs * 36; p += kSolveThreads) {
@@ -644,82 +848,94 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
     __syncthreads();
     // Blocked Cholesky (L L^T) on the packed lower triangle, block = one keyframe (6 x 6), right-looking, with the
     // right-hand side carried along as an extra row "n" so that the forward substitution z = L^-1 b falls out of the
-    // factorisation.  Per block column three short phases / three barriers (N block columns instead of 6N scalar
-    // columns): (1) thread 0 factors the 6 x 6 diagonal block, (2) one thread per row below solves its 6-vector
-    // against it, (3) one warp per trailing row applies the rank-6 update, lanes over the (contiguous) columns.
-    __shared__ double s_lkk[21], s_inv[6];
-    {
-        const int lane = tid & 31, warp = tid >> 5, nwarps = kSolveThreads / 32;
-        for (int K = 0; K < n; K += 6) {
+    // factorisation.  Per block column two phases / two barriers: (1) every thread that owns a row below the diagonal
+    // block factors that 6 x 6 block ITSELF, in registers (the same 21 shared-memory words for everybody: broadcast
+    // reads, no serial section, no barrier between factor and use) and solves its row against it; (2) one warp per
+    // trailing row applies the rank-6 update, lanes over the (contiguous) columns.  The factored diagonal blocks go to
+    // Ld (the unfactored ones stay in L: other threads may still be reading them).
+    const int lane = tid & 31, warp = tid >> 5, nwarps = kSolveThreads / 32;
+    for (int K = 0; K < n; K += 6) {
+        const int row = K + 6 + tid;
+        if (row <= n) {
+            double l[21];  // lower triangle row-wise: (r, c) -> r (r + 1) / 2 + c
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) l[r * (r + 1) / 2 + c] = L[tri(K + r, K + c)];
+            bool pd = true;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                double d = l[c * (c + 1) / 2 + c];
+#pragma unroll
+                for (int m = 0; m < c; ++m) d -= l[c * (c + 1) / 2 + m] * l[c * (c + 1) / 2 + m];
+                pd = pd && (d > 0.0) && isfinite(d);  // not positive definite otherwise
+                const double inv = rsqrt(d);          // the diagonal keeps 1 / l_cc
+                l[c * (c + 1) / 2 + c] = inv;
+#pragma unroll
+                for (int r = c + 1; r < 6; ++r) {
+                    double v = l[r * (r + 1) / 2 + c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) v -= l[r * (r + 1) / 2 + m] * l[c * (c + 1) / 2 + m];
+                    l[r * (r + 1) / 2 + c] = v * inv;
+                }
+            }
             if (tid == 0) {
-                double l[6][6];
-                bool pd = true;
-                for (int r = 0; r < 6; ++r)
-                    for (int c = 0; c <= r; ++c) l[r][c] = L[tri(K + r, K + c)];
-                for (int c = 0; c < 6 && pd; ++c) {
-                    double d = l[c][c];
-                    for (int m = 0; m < c; ++m) d -= l[c][m] * l[c][m];
-                    if (!(d > 0.0) || !isfinite(d)) {  // not positive definite
-                        pd = false;
-                        break;
-                    }
-                    const double inv = rsqrt(d), lcc = d * inv;  // one reciprocal square root instead of sqrt + division
-                    l[c][c] = lcc;
-                    s_inv[c] = inv;
-                    x[K + c] = inv;  // x[] is free until the back substitution: keep 1 / l_cc for it
-                    for (int r = c + 1; r < 6; ++r) {
-                        double v = l[r][c];
-                        for (int m = 0; m < c; ++m) v -= l[r][m] * l[c][m];
-                        l[r][c] = v * inv;
-                    }
-                }
+#pragma unroll
+                for (int q = 0; q < 21; ++q) Ld[(K / 6) * 21 + q] = l[q];
                 if (!pd) s_ok = 0;
-                int q = 0;
-                for (int r = 0; r < 6; ++r)
-                    for (int c = 0; c <= r; ++c) {
-                        L[tri(K + r, K + c)] = l[r][c];
-                        s_lkk[q++] = l[r][c];
-                    }
             }
-            __syncthreads();
-            if (!s_ok) break;  // uniform
-            for (int row = K + 6 + tid; row <= n; row += kSolveThreads) {
-                double *a = row < n ? &L[tri(row, K)] : &rhs[K];
-                double xv[6];
+            double *a = row < n ? &L[tri(row, K)] : &rhs[K];
+            double xv[6];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) {
-                    double v = a[c];
+            for (int c = 0; c < 6; ++c) {
+                double v = a[c];
 #pragma unroll
-                    for (int m = 0; m < c; ++m) v -= xv[m] * s_lkk[c * (c + 1) / 2 + m];
-                    xv[c] = v * s_inv[c];
-                }
-#pragma unroll
-                for (int c = 0; c < 6; ++c) a[c] = xv[c];
+                for (int m = 0; m < c; ++m) v -= xv[m] * l[c * (c + 1) / 2 + m];
+                xv[c] = v * l[c * (c + 1) / 2 + c];
             }
-            __syncthreads();
-            for (int i = K + 6 + warp; i <= n; i += nwarps) {
-                const double *li = i < n ? &L[tri(i, K)] : &rhs[K];
-                const double l0 = li[0], l1 = li[1], l2 = li[2], l3 = li[3], l4 = li[4], l5 = li[5];
-                double *rowp = i < n ? &L[tri(i, 0)] : rhs;
-                const int kmax = i < n ? i : n - 1;
-                for (int k = K + 6 + lane; k <= kmax; k += 32) {
-                    const double *lk = &L[tri(k, K)];
-                    rowp[k] -= l0 * lk[0] + l1 * lk[1] + l2 * lk[2] + l3 * lk[3] + l4 * lk[4] + l5 * lk[5];
-                }
-            }
-            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 6; ++c) a[c] = xv[c];
         }
+        __syncthreads();
+        if (!s_ok) break;  // uniform
+        for (int i = K + 6 + warp; i <= n; i += nwarps) {
+            const double *li = i < n ? &L[tri(i, K)] : &rhs[K];
+            const double l0 = li[0], l1 = li[1], l2 = li[2], l3 = li[3], l4 = li[4], l5 = li[5];
+            double *rowp = i < n ? &L[tri(i, 0)] : rhs;
+            const int kmax = i < n ? i : n - 1;
+            for (int k = K + 6 + lane; k <= kmax; k += 32) {
+                const double *lk = &L[tri(k, K)];
+                rowp[k] -= l0 * lk[0] + l1 * lk[1] + l2 * lk[2] + l3 * lk[3] + l4 * lk[4] + l5 * lk[5];
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const int ok = s_ok;
-    // rhs now holds z = L^-1 b; back substitution L^T x = z by one warp (row j of L is contiguous: lanes over i < j)
+    // rhs now holds z = L^-1 b; back substitution L^T x = z by one warp, one keyframe block per step: every lane solves
+    // the 6 x 6 transposed triangle itself (registers), then the lanes subtract the block's columns from the rows above
     if (tid < 32 && ok) {
-        for (int j = n - 1; j >= 0; --j) {
-            const double xj = rhs[j] * x[j];  // x[j] holds 1 / l_jj until it is overwritten by the solution
+        for (int J = N - 1; J >= 0; --J) {
+            double l[21], xb[6];
+#pragma unroll
+            for (int q = 0; q < 21; ++q) l[q] = Ld[J * 21 + q];
+#pragma unroll
+            for (int c = 5; c >= 0; --c) {
+                double v = rhs[6 * J + c];
+#pragma unroll
+                for (int m = c + 1; m < 6; ++m) v -= l[m * (m + 1) / 2 + c] * xb[m];
+                xb[c] = v * l[c * (c + 1) / 2 + c];
+            }
             __syncwarp();
-            if (tid == 0) x[j] = xj;
-            const double *lj = &L[tri(j, 0)];
-            for (int i = tid; i < j; i += 32) rhs[i] -= lj[i] * xj;
+            if (tid == 0) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) x[6 * J + c] = xb[c];
+            }
+            for (int i = tid; i < 6 * J; i += 32) {
+                double v = rhs[i];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) v -= L[tri(6 * J + c, i)] * xb[c];
+                rhs[i] = v;
+            }
             __syncwarp();
         }
     }
@@ -743,11 +959,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
             ST.qmax = 0;
             ST.iter_start = 0;
         }
-        double sc = 0;
-        for (int i = 0; i < n; ++i) sc += x[i] * (lambda * x[i] + packed[nS + n + i]);
-        ST.scale_pose = sc;
         ST.ok2 = ok;
         ST.have_trial = 1;
+    }
+    if (warp == 0) {  // computeScale: dp . (lambda dp + b), lane-strided then the shuffle tree
+        double sc = 0;
+        for (int i = lane; i < n; i += 32) sc += x[i] * (lambda * x[i] + packed[nS + n + i]);
+        sc = warp_sum(sc);
+        if (lane == 0) ST.scale_pose = sc;
     }
 }
 
@@ -860,6 +1079,8 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_update_kernel(BaDev B) {
         s_red[warp][1] = scale_acc;
     }
     __syncthreads();
+    __shared__ int s_last;
+    unsigned *done = reinterpret_cast<unsigned *>(B.trial_sum + 4);  // zero between kernels (reset by the last CTA)
     if (tid == 0) {
         double c = 0, s = 0;
         for (int w = 0; w < kBaWarps; ++w) {
@@ -868,28 +1089,33 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_update_kernel(BaDev B) {
         }
         B.trial_partial[2 * blockIdx.x] = c;
         B.trial_partial[2 * blockIdx.x + 1] = s;
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1 ? 1 : 0;
     }
-}
-
-// local reduction of the trial partials (then all-reduced over ranks in multi-GPU runs)
-__global__ void ba_trial_reduce_kernel(BaDev B) {
-    const BaState &ST = *B.state;
-    if (ST.phase == kBaDone || !ST.have_trial) return;
-    if (threadIdx.x == 0) {
+    __syncthreads();
+    // the CTA that finishes last sums the per-CTA partials in a fixed order (lane-strided, then the shuffle tree);
+    // multi-GPU runs all-reduce trial_sum[0..1] over the ranks afterwards
+    if (s_last && warp == 0) {
+        __threadfence();
         double c = 0, s = 0;
-        for (int g = 0; g < B.num_ctas; ++g) {
-            c += B.trial_partial[2 * g];
-            s += B.trial_partial[2 * g + 1];
+        for (int g = lane; g < (int)gridDim.x; g += 32) {
+            c += __ldcg(B.trial_partial + 2 * g);
+            s += __ldcg(B.trial_partial + 2 * g + 1);
         }
-        B.trial_sum[0] = c;
-        B.trial_sum[1] = s;
+        c = warp_sum(c);
+        s = warp_sum(s);
+        if (lane == 0) {
+            B.trial_sum[0] = c;
+            B.trial_sum[1] = s;
+            *done = 0u;
+        }
     }
 }
 
 // =========================================================================================================
 // ba_decide_kernel: OptimizationAlgorithmLevenberg accept / reject + SparseOptimizer::optimize loop control
 // =========================================================================================================
-__global__ void ba_decide_kernel(BaDev B) {
+__global__ void __launch_bounds__(512) ba_decide_kernel(BaDev B) {
     BaState &ST = *B.state;
     if (ST.phase == kBaDone) return;
     if (ST.have_trial) {
@@ -1032,7 +1258,7 @@ int ba_pool_capacity(int n_free, int n_pairs, int max_free_degree) {
 }
 size_t ba_solve_smem(int n_free) {
     const size_t n = 6 * (size_t)n_free;
-    return (n * (n + 1) / 2 + 2 * n) * 8 + 64;
+    return (n * (n + 1) / 2 + 2 * n + 21 * (size_t)n_free) * 8 + 64;
 }
 
 plp_status ba_prepare_kernels(int n_free, int n_pairs, int pool_cap) {
@@ -1047,8 +1273,11 @@ plp_status ba_prepare_kernels(int n_free, int n_pairs, int pool_cap) {
 }
 
 // one LM try on the context stream; `between` (may be null) is called where the multi-GPU path all-reduces
+// ba_decide_kernel also refreshes the 12 perturbed poses per keyframe (one se3::oplus each): one thread per pose
+static int ba_decide_threads(const BaDev &B) { return std::max(64, std::min(512, (B.n_kf * 12 + 31) / 32 * 32)); }
+
 plp_status ba_launch_try(plp_ctx *ctx, const BaDev &B, BaCollective *coll) {
-    PLP_LAUNCH(ctx, ba_decide_kernel, 1, 256, 0, B);
+    PLP_LAUNCH(ctx, ba_decide_kernel, 1, ba_decide_threads(B), 0, B);
     if (B.large) {
         // every landmark adds its blocks to the packed system in HBM with FP64 atomics: start from zero
         PLP_CUDA_TRY(cudaMemsetAsync(B.packed, 0, (size_t)(B.packed_sum_len + B.world) * sizeof(double), ctx->stream));
@@ -1063,14 +1292,13 @@ plp_status ba_launch_try(plp_ctx *ctx, const BaDev &B, BaCollective *coll) {
     else
         PLP_LAUNCH(ctx, ba_solve_kernel, 1, kSolveThreads, ba_solve_smem(B.n_free), B);
     PLP_LAUNCH(ctx, ba_update_kernel, B.num_ctas, kBaThreads, (size_t)6 * B.n_free * sizeof(double), B);
-    PLP_LAUNCH(ctx, ba_trial_reduce_kernel, 1, 32, 0, B);
     if (coll) PLP_TRY(coll->all_reduce(B.trial_sum, 2));
     PLP_CHECK_LAUNCH();
     return PLP_OK;
 }
 
 plp_status ba_launch_decide(plp_ctx *ctx, const BaDev &B) {
-    PLP_LAUNCH(ctx, ba_decide_kernel, 1, 256, 0, B);
+    PLP_LAUNCH(ctx, ba_decide_kernel, 1, ba_decide_threads(B), 0, B);
     PLP_CHECK_LAUNCH();
     return PLP_OK;
 }

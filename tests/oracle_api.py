@@ -806,6 +806,22 @@ def _line_extract_batch_mt(self, imgs, threads=1, pin=True, mode=LSD_DET):
     return n, sec.value
 
 
+def _stereo_frontend_batch_mt(self, p, left, right, focal_x_baseline, true_baseline, threads=1, pin=True, mode=LSD_DET):
+    """ORB left + right, match::stereo::compute, LSD + LBD left + right (data/frame.cc:456-480) per stereo frame."""
+    left, right = np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(right, np.uint8)
+    B, rows, cols = left.shape
+    n_kp, n_st, n_ln = np.zeros((B, 2), np.int32), np.zeros(B, np.int32), np.zeros((B, 2), np.int32)
+    sec = C.c_double(0)
+    cfg = OLsdCfg(*mode)
+    self.lib.orc_stereo_frontend_batch_mt(C.byref(p), C.byref(cfg), left.ctypes.data_as(_P), right.ctypes.data_as(_P),
+                                          C.c_int(B), C.c_int(rows), C.c_int(cols), C.c_float(focal_x_baseline),
+                                          C.c_float(true_baseline), C.c_int(threads), C.c_int(1 if pin else 0),
+                                          n_kp.ctypes.data_as(_P), n_st.ctypes.data_as(_P), n_ln.ctypes.data_as(_P),
+                                          C.byref(sec))
+    return dict(n_kp=n_kp, n_stereo=n_st, n_lines=n_ln, seconds=sec.value)
+
+
 Oracle.host_cpus = _host_cpus
 Oracle.frontend_track_batch = _frontend_track_batch
 Oracle.line_extract_batch_mt = _line_extract_batch_mt
+Oracle.stereo_frontend_batch_mt = _stereo_frontend_batch_mt

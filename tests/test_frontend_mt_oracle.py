@@ -58,3 +58,21 @@ def test_native_chain_equals_composed_chain():
             assert got["n_inliers"][b] == want[b][1] and got["num_valid"][b] == want[b][2] and got["n_kp"][b] == want[b][3]
         assert got["n_inliers"].min() >= 20
     assert orc.host_cpus() >= 1
+
+
+def test_native_stereo_chain_equals_composed_chain():
+    """orc_stereo_frontend_batch_mt (bench.py's stereo CPU arm) = orb_extract x2 + stereo_compute + line_extract x2."""
+    orc = oracle_api.Oracle()
+    p = oracle_api.orb_params()
+    pairs = [synth.make_stereo_pair(11 + i, 240, 376, plp=True) for i in range(3)]
+    left, right = np.stack([pr[0] for pr in pairs]), np.stack([pr[1] for pr in pairs])
+    bf, baseline = 47.906, 0.11
+    for threads in (1, 3):
+        got = orc.stereo_frontend_batch_mt(p, left, right, bf, baseline, threads)
+        for b in range(3):
+            a, c = orc.orb_extract(p, left[b]), orc.orb_extract(p, right[b])
+            _, dp, _ = orc.stereo_compute(a, c, synth.scale_factors(), 1.0 / synth.scale_factors(), bf, baseline)
+            assert tuple(got["n_kp"][b]) == (len(a["kps"]), len(c["kps"]))
+            assert got["n_stereo"][b] == int((dp > 0).sum())
+            assert got["n_lines"][b, 0] == len(orc.line_extract(left[b])[0])
+            assert got["n_lines"][b, 1] == len(orc.line_extract(right[b])[0])

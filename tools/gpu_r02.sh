@@ -53,6 +53,13 @@ if [[ " $WHAT " == *" proflines "* ]]; then
       python bench.py --only-lines --steps 2 --warmup 3 --line-batch 64 --no-cpu-baseline > gpurun_out/bench_lines_under_ncu_full_${TAG}.log 2>&1
   echo "line profile exit $?"
 fi
+if [[ " $WHAT " == *" ba "* ]]; then
+  timeout 600 python -m pytest tests/test_ba_gpu.py tests/test_plane_gpu.py -q -m gpu -x > gpurun_out/test_ba_${TAG}.log 2>&1
+  echo "ba tests exit $?"; tail -5 gpurun_out/test_ba_${TAG}.log
+  timeout 300 python tools/ba_profile.py > gpurun_out/ba_profile_${TAG}.log 2>&1; echo "ba_profile exit $?"; cat gpurun_out/ba_profile_${TAG}.log
+  timeout 600 python bench.py --only-ba --steps 10 --warmup 3 > gpurun_out/bench_ba_${TAG}.json 2> gpurun_out/bench_ba_${TAG}.err
+  echo "bench ba exit $?"; cut -c1-1500 gpurun_out/bench_ba_${TAG}.json
+fi
 if [[ " $WHAT " == *" profba "* ]]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_ba_${TAG}.csv \
       python bench.py --only-ba --no-ba-large --steps 2 --warmup 1 > gpurun_out/bench_ba_under_ncu_${TAG}.log 2>&1
