@@ -768,31 +768,45 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
 // =========================================================================================================
 // ba_reduce_kernel: packed = sum over CTAs of the partial systems; max-diag goes to this rank's one-hot slot
 // =========================================================================================================
-__global__ void ba_reduce_kernel(BaDev B) {
+constexpr int kReduceLanes = 8;  // threads per packed entry: enough loads in flight to stream the partials out of L2
+__global__ void __launch_bounds__(256) ba_reduce_kernel(BaDev B) {
     if (B.state->phase == kBaDone) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / kReduceLanes, j = t % kReduceLanes;  // entry, slice of the CTA partials
     const int n_sum = B.n_pairs * 36 + 12 * B.n_free + 1;
-    if (i < n_sum) {
-        // fixed summation order (CTA 0, 1, ...); the loads of 8 partials are issued together
+    const int G = B.num_ctas;
+    const size_t len = (size_t)B.packed_len;
+    // fixed summation order: slice j adds the partials of CTA j, j + 8, ..., then the slices are combined by a shuffle tree
+    double s = 0;
+    if (i <= n_sum) {
         const double *src = B.partial + i;
-        const size_t len = (size_t)B.packed_len;
-        const int G = B.num_ctas;
-        double s = 0;
-        int g = 0;
-        for (; g + 8 <= G; g += 8) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(g + u) * len);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s += v[u];
+        int g = j;
+        if (i < n_sum) {
+            for (; g + 3 * kReduceLanes < G; g += 4 * kReduceLanes) {
+                const double v0 = __ldcg(src + (size_t)g * len), v1 = __ldcg(src + (size_t)(g + kReduceLanes) * len);
+                const double v2 = __ldcg(src + (size_t)(g + 2 * kReduceLanes) * len);
+                const double v3 = __ldcg(src + (size_t)(g + 3 * kReduceLanes) * len);
+                s += v0;
+                s += v1;
+                s += v2;
+                s += v3;
+            }
+            for (; g < G; g += kReduceLanes) s += __ldcg(src + (size_t)g * len);
+        } else {
+            for (; g < G; g += kReduceLanes) s = fmax(s, __ldcg(src + (size_t)g * len));
         }
-        for (; g < G; ++g) s += __ldcg(src + (size_t)g * len);
+    }
+#pragma unroll
+    for (int o = kReduceLanes / 2; o > 0; o >>= 1) {
+        const double v = __shfl_xor_sync(0xffffffffu, s, o);
+        s = i < n_sum ? s + v : fmax(s, v);
+    }
+    if (j != 0) return;
+    if (i < n_sum) {
         B.packed[i] = s;
     } else if (i == n_sum) {
-        double m = 0;
-        for (int g = 0; g < B.num_ctas; ++g) m = fmax(m, B.partial[(size_t)g * B.packed_len + n_sum]);
         // max diag of the pose blocks = diagonal of the diagonal S blocks in init mode (no Schur term yet)
-        for (int w = 0; w < B.world; ++w) B.packed[n_sum + w] = (w == B.rank) ? m : 0.0;
+        for (int w = 0; w < B.world; ++w) B.packed[n_sum + w] = (w == B.rank) ? s : 0.0;
     }
 }
 
@@ -830,17 +844,19 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
     double *Ld = x + n;                   // N x 21: the factored diagonal blocks (lower triangle row-wise, 1 / l_cc on the diagonal)
     __shared__ int s_ok;
     const double lambda = ST.lambda;
-    for (int p = tid; p < B.n_pairs * 36; p += kSolveThreads) {
-        const int pr = p / 36, rc = p - pr * 36, r = rc / 6, c = rc - r * 6;
-        const int bi = B.pair_bi[pr], bj = B.pair_bj[pr];
-        const int gi = bi * 6 + r, gj = bj * 6 + c;
-        double v = packed[p];
-        if (bi == bj) {
-            if (c > r) continue;  // lower part of the (symmetric) diagonal block
-            if (r == c) v += lambda;
-            L[tri(gi, gj)] = v;
-        } else {
-            L[tri(gj, gi)] = v;  // bi < bj: entry (gi, gj) of the upper part -> (gj, gi) of the lower part
+    if (tid < 504) {  // thread t owns entry (r, c) = t % 36 of the blocks t / 36, t / 36 + 14, ...
+        const int rc = tid % 36, r = rc / 6, c = rc - r * 6;
+        for (int pr = tid / 36; pr < B.n_pairs; pr += 14) {
+            const int bi = B.pair_bi[pr], bj = B.pair_bj[pr];
+            const int gi = bi * 6 + r, gj = bj * 6 + c;
+            double v = packed[pr * 36 + rc];
+            if (bi == bj) {
+                if (c > r) continue;  // lower part of the (symmetric) diagonal block
+                if (r == c) v += lambda;
+                L[tri(gi, gj)] = v;
+            } else {
+                L[tri(gj, gi)] = v;  // bi < bj: entry (gi, gj) of the upper part -> (gj, gi) of the lower part
+            }
         }
     }
     for (int i = tid; i < n; i += kSolveThreads) rhs[i] = packed[nS + i];
@@ -1284,7 +1300,7 @@ plp_status ba_launch_try(plp_ctx *ctx, const BaDev &B, BaCollective *coll) {
         PLP_LAUNCH(ctx, ba_linearize_kernel<true>, B.num_ctas, kBaThreads, ba_linearize_smem(B.n_free, B.n_pairs, B.pool_cap), B);
     } else {
         PLP_LAUNCH(ctx, ba_linearize_kernel<false>, B.num_ctas, kBaThreads, ba_linearize_smem(B.n_free, B.n_pairs, B.pool_cap), B);
-        PLP_LAUNCH(ctx, ba_reduce_kernel, div_up(B.packed_sum_len + 1, 256), 256, 0, B);
+        PLP_LAUNCH(ctx, ba_reduce_kernel, div_up((B.packed_sum_len + 1) * kReduceLanes, 256), 256, 0, B);
     }
     if (coll) PLP_TRY(coll->all_reduce(B.packed, B.packed_sum_len + B.world));
     if (B.large)

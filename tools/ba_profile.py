@@ -16,7 +16,7 @@ ctx = plp.Context(0)
 lib = plp.lib()
 import os  # noqa: E402
 
-for ctas, weights in ((0, None), (32, None), (0, "2,2"), (0, "8,2"), (0, "4,8"), (0, "1,0")):
+for ctas, weights in ((0, None), (0, "4,8"), (0, "4,16"), (0, "2,8"), (0, "4,32"), (0, "8,16")):
     if weights:
         os.environ["PLP_BA_COST_WEIGHTS"] = weights  # cost model of the CTA landmark ranges (ba_host.cu)
     else:
