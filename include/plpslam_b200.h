@@ -595,6 +595,11 @@ PLP_API plp_status plp_line_debug_segments(plp_line *h, int b, float *segs_out, 
  * (2 per SM at VGA) and reads it through L2 for larger batches (6 frames per SM); this forces the second variant so that
  * the parity tests cover both */
 PLP_API plp_status plp_line_debug_force_global_image(plp_line *h, int on);
+/* region growing variant: 0 automatic (multi-warp for at most one wave of frames, i.e. the live-sequence case), 1 one warp
+ * per frame, 2 speculative multi-warp with in-order commit; all three produce the sequential result bit for bit.
+ * grow_stats: {rounds, seeds run, seeds redone after a conflict} of frame b in the last multi-warp run. */
+PLP_API plp_status plp_line_debug_grow_variant(plp_line *h, int variant);
+PLP_API plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out3);
 PLP_API plp_status plp_line_debug_scaled(plp_line *h, int b, uint8_t *out /* (rows/2) x (cols/2) */);
 PLP_API plp_status plp_line_debug_lbd_float(plp_line *h, int b, float *out /* n x 72 */, int cap);
 

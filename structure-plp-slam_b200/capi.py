@@ -830,6 +830,16 @@ class LineFeatureTracker:
     def force_global_image(self, on: bool):
         self._ctx._check(self._lib.plp_line_debug_force_global_image(self._h, C.c_int(1 if on else 0)))
 
+    def grow_variant(self, variant: int):
+        """0 automatic, 1 one warp per frame, 2 speculative multi-warp region growing (same result, bit for bit)."""
+        self._ctx._check(self._lib.plp_line_debug_grow_variant(self._h, C.c_int(variant)))
+
+    def grow_stats(self, b: int = 0):
+        """{rounds, seeds run, seeds redone after a conflict} of frame b in the last multi-warp run."""
+        out = (C.c_ulonglong * 3)()
+        self._ctx._check(self._lib.plp_line_debug_grow_stats(self._h, C.c_int(b), out))
+        return dict(rounds=int(out[0]), seeds_run=int(out[1]), seeds_redone=int(out[2]))
+
     def debug_segments(self, b: int) -> np.ndarray:
         cap = 20000
         out = np.zeros((cap, 4), np.float32)

@@ -53,6 +53,7 @@ struct LineDev {
     uint32_t *order;     // npx packed (y<<16|x) seeds, bin desc / raster asc
     int *nseeds;
     uint32_t *reg_xy;    // npx: region entries beyond the shared-memory window
+    unsigned long long *mw_stat;  // per frame {rounds, seeds run, seeds redone} of lsd_grow_mw_kernel (may be null)
     float4 *segs;        // seg_cap
     int *nseg;
     short2 *grad;        // w*h Sobel (dx, dy) of the 5x5-blurred frame
@@ -284,15 +285,22 @@ struct Rect {
     double x1, y1, x2, y2, width;
 };
 
-struct Grow {  // per-warp state
+// kMw = false: one warp per frame, marks go straight into the frame's `used` bitmap.
+// kMw = true (lsd_grow_mw_kernel): several warps of a CTA work on seeds of the SAME frame speculatively: `used` is the
+// committed bitmap (read only while the warps grow), the warp's own marks live in its private bitmap `mark`, and the
+// bounding box of every pixel the warp ever accepted is tracked for the conflict test.
+template <bool kMw>
+struct GrowT {  // per-warp state
     int sw, sh, kthr;
     double density_th;
     const uint8_t *img;    // shared: half-resolution image
-    uint32_t *used;        // shared: bitmap
-    uint32_t *reg;         // shared: first kRegCap region entries (packed y<<16|x)
-    uint32_t *reg_ovf;     // global: all entries beyond kRegCap (indexed by absolute position)
+    uint32_t *used;        // shared: bitmap (kMw: committed marks of the frame)
+    uint32_t *mark;        // shared: where this warp sets / clears marks (= used unless kMw)
+    uint32_t *reg;         // shared: first reg_cap region entries (packed y<<16|x)
+    uint32_t *reg_ovf;     // global: all entries beyond reg_cap (indexed by absolute position)
     const float4 *tab;     // global: {deg, cos, sin} by (gx, gy)
     int lane, reg_cap;
+    mutable int bx0, by0, bx1, by1;  // kMw: per-lane bounding box of the pixels this lane accepted (reduced by the caller)
 #ifdef PLP_LSD_PROF
     long long *pc;         // [0] iterations [1] rounds [2] cycles load phase [3] cycles resolve phase [4] on-demand loads
 #endif
@@ -301,8 +309,23 @@ struct Grow {  // per-warp state
         if (e < reg_cap) reg[e] = v;
         else reg_ovf[e] = v;
     }
-    __device__ __forceinline__ bool is_used(int idx) const { return (used[idx >> 5] >> (idx & 31)) & 1u; }
+    __device__ __forceinline__ bool is_used(int idx) const {
+        uint32_t w = used[idx >> 5];
+        if (kMw) w |= mark[idx >> 5];
+        return (w >> (idx & 31)) & 1u;
+    }
+    __device__ __forceinline__ void accept(int idx, uint32_t xy) const {  // one lane: mark a pixel of the region
+        mark[idx >> 5] |= 1u << (idx & 31);
+        if (kMw) {
+            const int x = (int)(xy & 0xffff), y = (int)(xy >> 16);
+            bx0 = min(bx0, x);
+            bx1 = max(bx1, x);
+            by0 = min(by0, y);
+            by1 = max(by1, y);
+        }
+    }
 };
+using Grow = GrowT<false>;
 
 __device__ __forceinline__ bool is_aligned(double a, double theta, double prec) {
     double n_theta = theta - a;
@@ -335,7 +358,8 @@ struct Nb {
 };
 
 // neighbour jj (0..7, centre skipped) of queue entry e
-__device__ __forceinline__ Nb load_nb(const Grow &G, int e, int ddx, int ddy) {
+template <bool kMw>
+__device__ __forceinline__ Nb load_nb(const GrowT<kMw> &G, int e, int ddx, int ddy) {
     Nb r;
     r.nidx = -1;
     r.xy = 0;
@@ -360,14 +384,15 @@ __device__ __forceinline__ Nb load_nb(const Grow &G, int e, int ddx, int ddy) {
 // 32 lanes = 4 queue entries x 8 neighbours, in the scalar visiting order (entry, then yy, then xx).  The immutable data
 // of the next four entries is fetched while the current four are resolved; every candidate lane keeps the region sums
 // and angle it WOULD produce if it were accepted next, so an acceptance is one shuffle away.
-__device__ int region_grow(const Grow &G, uint32_t seed_xy, float seed_deg, double prec, double &reg_angle_out) {
+template <bool kMw>
+__device__ int region_grow(const GrowT<kMw> &G, uint32_t seed_xy, float seed_deg, double prec, double &reg_angle_out) {
     const int sw = G.sw, lane = G.lane;
     double reg_angle = (double)seed_deg * kDegToRads;
     float sumdx = (float)det_cos(reg_angle);
     float sumdy = (float)det_sin(reg_angle);
     if (lane == 0) {
         const int sidx = (int)(seed_xy >> 16) * sw + (int)(seed_xy & 0xffff);
-        G.used[sidx >> 5] |= 1u << (sidx & 31);
+        G.accept(sidx, seed_xy);
         G.reg[0] = seed_xy;
     }
     __syncwarp();
@@ -417,7 +442,7 @@ __device__ int region_grow(const Grow &G, uint32_t seed_xy, float seed_deg, doub
             reg_angle = __shfl_sync(kFull, my_theta, l);
             const int q = __shfl_sync(kFull, cur.nidx, l);
             if (lane == l) {
-                G.used[cur.nidx >> 5] |= 1u << (cur.nidx & 31);
+                G.accept(cur.nidx, cur.xy);
                 G.put(n, cur.xy);
             }
             ++n;
@@ -448,14 +473,16 @@ __device__ __forceinline__ double dist2(double x1, double y1, double x2, double 
     return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);
 }
 // modgrad of a region pixel, recomputed from the image
-__device__ __forceinline__ double px_weight(const Grow &G, uint32_t xy) {
+template <bool kMw>
+__device__ __forceinline__ double px_weight(const GrowT<kMw> &G, uint32_t xy) {
     int gx, gy;
     grad_at(G.img, G.sw, (int)(xy >> 16) * G.sw + (int)(xy & 0xffff), gx, gy);
     return sqrt((double)(gx * gx + gy * gy) / 4.0);
 }
 
 // lsd.cpp region2rect + get_theta
-__device__ void region2rect(const Grow &G, int n, double reg_angle, double prec, Rect &R) {
+template <bool kMw>
+__device__ void region2rect(const GrowT<kMw> &G, int n, double reg_angle, double prec, Rect &R) {
     const int lane = G.lane;
     double sx = 0, sy = 0, ss = 0;
     for (int i = lane; i < n; i += 32) {
@@ -513,7 +540,8 @@ __device__ __forceinline__ double rect_density(int n, const Rect &R) {
 }
 
 // lsd.cpp refine + reduce_region_radius; n is updated; returns false when the region is rejected
-__device__ bool refine(const Grow &G, int &n, float seed_deg, double reg_angle, double prec, Rect &R) {
+template <bool kMw>
+__device__ bool refine(const GrowT<kMw> &G, int &n, float seed_deg, double reg_angle, double prec, Rect &R) {
     const int lane = G.lane, sw = G.sw;
     double density = rect_density(n, R);
     if (density >= G.density_th) return true;
@@ -526,7 +554,7 @@ __device__ bool refine(const Grow &G, int &n, float seed_deg, double reg_angle, 
         const uint32_t xy = G.get(i);
         const int px = xy & 0xffff, py = xy >> 16;
         const int pidx = py * sw + px;
-        atomicAnd(&G.used[pidx >> 5], ~(1u << (pidx & 31)));  // NOTUSED again
+        atomicAnd(&G.mark[pidx >> 5], ~(1u << (pidx & 31)));  // NOTUSED again
         if (sqrt(dist2(xc, yc, (double)px, (double)py)) < R.width) {
             int gx, gy;
             grad_at(G.img, sw, pidx, gx, gy);
@@ -564,7 +592,7 @@ __device__ bool refine(const Grow &G, int &n, float seed_deg, double reg_angle, 
                 keep = !(dist2(xc, yc, (double)px, (double)py) > rad_sq);
                 if (!keep) {
                     const int pidx = py * sw + px;
-                    atomicAnd(&G.used[pidx >> 5], ~(1u << (pidx & 31)));
+                    atomicAnd(&G.mark[pidx >> 5], ~(1u << (pidx & 31)));
                 }
             }
             const unsigned km = __ballot_sync(kFull, keep);
@@ -630,6 +658,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
     G.img = kImgSmem ? s_img : D.scaled + (size_t)b * D.npx;
     G.reg_cap = kImgSmem ? kRegCap : kRegCapSmall;
     G.used = s_used;
+    G.mark = s_used;
     G.reg = s_reg;
     G.reg_ovf = D.reg_xy + (size_t)b * D.npx;
     G.tab = D.cstab;
@@ -696,6 +725,192 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
         printf("[lsd prof] total %lld grow %lld rect %lld refine %lld | seeds %d regions %lld px %lld big %lld segs %d | iters %lld rounds %lld load-cyc %lld resolve-cyc %lld ondemand %lld\n",
                clock64() - t_start, prof[0], prof[1], prof[2], nseeds, cnt_regions, cnt_px, cnt_refine, nseg, s_pc[0], s_pc[1], s_pc[2], s_pc[3], s_pc[4]);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K4': the same region growing for a SINGLE live frame (small batches): kMwWarps warps of one CTA work on consecutive
+//      seeds of the frame speculatively and commit in seed order, so the result is the sequential one bit for bit.
+//
+// The sequential algorithm visits the seeds in order; what it does with a seed depends on the `used` map only through the
+// pixels it ACCEPTS into a region (a neighbour that is not aligned is rejected whether it is used or not, a used one is
+// never accepted).  One round: every warp takes the next not-yet-used seed (warp w the w-th), grows / refines it against
+// the committed map plus a private mark bitmap, and records the bounding box of every pixel it accepted at any time.  The
+// round's seeds e < w come earlier in the sequential order: if the box of w is disjoint from the boxes of all of them,
+// nothing they mark can be a pixel w accepted, so w saw exactly the map the sequential run would have shown it.  The
+// longest conflict-free prefix of the round commits (marks are OR-ed into the committed map, segments are emitted in
+// seed order); the first conflicting seed and everything after it is redone in the next round, where it is first (and
+// therefore commits): every round makes progress.  Marks of a committed region are final (refinement only ever clears a
+// region's OWN pixels, before it commits), which is why skipping a seed that is used in the committed map is exact.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMwMaxWarps = 8;
+constexpr int kMwRegCap = 1024;  // region entries per warp in shared memory (longer regions continue in global memory)
+
+struct MwCtl {
+    int bbox[kMwMaxWarps][4];
+    int nfinal[kMwMaxWarps];
+    int ok[kMwMaxWarps];
+    float4 seg[kMwMaxWarps];
+    unsigned long long stat[4];  // rounds, seeds run, seeds redone (tuning aid, read by nobody on the hot path)
+};
+
+__global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D, uint32_t *reg_ovf_mw) {
+    extern __shared__ uint4 s_grow[];
+    const int W = blockDim.x >> 5;
+    uint8_t *s_img = reinterpret_cast<uint8_t *>(s_grow);
+    const int img_bytes = (D.npx + 15) & ~15;
+    const int used_words = (D.npx + 31) >> 5, used_pad = (used_words + 3) & ~3;
+    uint32_t *s_used = reinterpret_cast<uint32_t *>(s_img + img_bytes);  // committed marks
+    uint32_t *s_priv = s_used + used_pad;                                // W private bitmaps
+    uint32_t *s_reg = s_priv + (size_t)W * used_pad;                     // W region windows
+    MwCtl &C = *reinterpret_cast<MwCtl *>(s_reg + (size_t)W * kMwRegCap);
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {  // stage the frame
+        const uint8_t *src = D.scaled + (size_t)b * D.npx;
+        if (((size_t)src & 15) == 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            for (int i = tid; i < D.npx / 16; i += blockDim.x) s_grow[i] = s4[i];
+            for (int i = (D.npx / 16) * 16 + tid; i < D.npx; i += blockDim.x) s_img[i] = src[i];
+        } else {
+            for (int i = tid; i < D.npx; i += blockDim.x) s_img[i] = src[i];
+        }
+        for (int i = tid; i < used_pad * (W + 1); i += blockDim.x) s_used[i] = 0;
+        if (tid < 4) C.stat[tid] = 0;
+    }
+    __syncthreads();
+    GrowT<true> G;
+    G.sw = D.sw;
+    G.sh = D.sh;
+    G.kthr = D.kthr;
+    G.density_th = D.density_th;
+    G.img = s_img;
+    G.reg_cap = kMwRegCap;
+    G.used = s_used;
+    G.mark = s_priv + (size_t)warp * used_pad;
+    G.reg = s_reg + (size_t)warp * kMwRegCap;
+    G.reg_ovf = reg_ovf_mw + ((size_t)b * kMwMaxWarps + warp) * D.npx;
+    G.tab = D.cstab;
+    G.lane = lane;
+    const uint32_t *order = D.order + (size_t)b * D.npx;
+    float4 *segs = D.segs + (size_t)b * D.seg_cap;
+    const int nseeds = D.nseeds[b];
+    const int sw = D.sw;
+    int nseg = 0, cursor = 0;  // identical in every warp
+    for (;;) {
+        // ---- the next W seeds that are not used in the committed map (every warp scans for itself: same result)
+        int my_pos = -1;       // lane i < W: position of the round's i-th seed in the order list
+        uint32_t my_xy = 0;
+        int found = 0, scan = cursor;
+        while (found < W && scan < nseeds) {
+            const int sidx_l = scan + lane;
+            const uint32_t oxy = sidx_l < nseeds ? order[sidx_l] : 0;
+            const int oidx = (int)(oxy >> 16) * sw + (int)(oxy & 0xffff);
+            unsigned m = __ballot_sync(kFull, sidx_l < nseeds && !((s_used[oidx >> 5] >> (oidx & 31)) & 1u));
+            while (m && found < W) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t xy = __shfl_sync(kFull, oxy, l);
+                if (lane == found) {
+                    my_pos = scan + l;
+                    my_xy = xy;
+                }
+                ++found;
+            }
+            scan += 32;
+        }
+        if (found == 0) break;  // uniform over the CTA
+        // ---- phase 1: warp w runs the w-th seed
+        if (warp < found) {
+            const uint32_t seed_xy = __shfl_sync(kFull, my_xy, warp);
+            const int sidx = (int)(seed_xy >> 16) * sw + (int)(seed_xy & 0xffff);
+            G.bx0 = G.by0 = 0x7fffffff;
+            G.bx1 = G.by1 = -1;
+            int gx, gy;
+            grad_at(G.img, sw, sidx, gx, gy);
+            const float seed_deg = fast_atan2_deg((float)gx, (float)-gy);
+            double reg_angle;
+            int n = region_grow(G, seed_xy, seed_deg, D.prec, reg_angle);
+            bool okr = false;
+            Rect R;
+            if (n >= D.min_reg_size) {
+                region2rect(G, n, reg_angle, D.prec, R);
+                okr = refine(G, n, seed_deg, reg_angle, D.prec, R);
+            }
+            int x0 = G.bx0, y0 = G.by0, x1 = G.bx1, y1 = G.by1;
+            for (int off = 16; off >= 1; off >>= 1) {
+                x0 = min(x0, __shfl_xor_sync(kFull, x0, off));
+                y0 = min(y0, __shfl_xor_sync(kFull, y0, off));
+                x1 = max(x1, __shfl_xor_sync(kFull, x1, off));
+                y1 = max(y1, __shfl_xor_sync(kFull, y1, off));
+            }
+            if (lane == 0) {
+                C.bbox[warp][0] = x0;
+                C.bbox[warp][1] = y0;
+                C.bbox[warp][2] = x1;
+                C.bbox[warp][3] = y1;
+                C.nfinal[warp] = n;
+                C.ok[warp] = okr ? 1 : 0;
+                if (okr)  // + 0.5 offset, then / scale (0.5)
+                    C.seg[warp] = make_float4((float)((R.x1 + 0.5) / 0.5), (float)((R.y1 + 0.5) / 0.5),
+                                              (float)((R.x2 + 0.5) / 0.5), (float)((R.y2 + 0.5) / 0.5));
+            }
+        }
+        __syncthreads();
+        // ---- phase 2 (every warp, same result): first seed whose box meets the box of an earlier seed of the round
+        int first_bad = found;
+        {
+            // lane = pair (v, e), e < v < found: at most 28 pairs
+            int v = 1, e = lane;
+            while (v < kMwMaxWarps && e >= v) {
+                e -= v;
+                ++v;
+            }
+            bool hit = false;
+            if (v < found) {
+                const int *bv = C.bbox[v], *be = C.bbox[e];
+                hit = !(bv[2] < be[0] || be[2] < bv[0] || bv[3] < be[1] || be[3] < bv[1]);
+            }
+            for (int q = 1; q < found; ++q) {
+                const unsigned mq = __ballot_sync(kFull, hit && v == q);
+                if (mq && first_bad == found) first_bad = q;
+            }
+        }
+        // ---- phase 3: commit the prefix, forget the rest
+        if (warp < found) {
+            const int n = C.nfinal[warp];
+            const bool commit = warp < first_bad;
+            for (int i = lane; i < n; i += 32) {
+                const uint32_t xy = G.get(i);
+                const int pidx = (int)(xy >> 16) * sw + (int)(xy & 0xffff);
+                atomicAnd(&G.mark[pidx >> 5], ~(1u << (pidx & 31)));
+                if (commit) atomicOr(&s_used[pidx >> 5], 1u << (pidx & 31));
+            }
+            if (commit && C.ok[warp] && lane == 0) {
+                int slot = nseg;
+                for (int e = 0; e < warp; ++e) slot += C.ok[e];
+                if (slot < D.seg_cap) segs[slot] = C.seg[warp];
+                else atomicOr(&D.status[b], 1);
+            }
+        }
+        for (int e = 0; e < first_bad; ++e) nseg += C.ok[e];
+        {
+            const int pos_bad = __shfl_sync(kFull, my_pos, min(first_bad, found - 1));
+            cursor = first_bad < found ? pos_bad : pos_bad + 1;
+        }
+        if (tid == 0) {
+            C.stat[0] += 1;
+            C.stat[1] += (unsigned long long)found;
+            C.stat[2] += (unsigned long long)(found - first_bad);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        D.nseg[b] = min(nseg, D.seg_cap);
+        if (D.mw_stat) {
+            D.mw_stat[3 * b] = C.stat[0];
+            D.mw_stat[3 * b + 1] = C.stat[1];
+            D.mw_stat[3 * b + 2] = C.stat[2];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -970,6 +1185,10 @@ struct plp_line {
     bool img_smem_ok = true;
     int resident_smem_frames = 0;
     bool force_global_image = false;
+    int grow_variant = 0;  // 0 automatic, 1 one warp per frame, 2 speculative multi-warp (lsd_grow_mw_kernel)
+    int mw_warps = 0, mw_max_batch = 0;
+    size_t mw_smem = 0;
+    uint32_t *d_reg_mw = nullptr;
     float4 *d_cstab = nullptr;
     std::vector<void *> owned;
 };
@@ -1004,7 +1223,13 @@ static plp_status line_run(plp_line *h, const uint8_t *d_imgs, int batch, size_t
     PLP_LAUNCH(ctx, lsd_sort_kernel, batch, kSortWarps * 32, h->sort_smem, D);
     // small batches (at most half of what stays resident, so that a second handle -- the right image of a stereo pair --
     // fits beside it): image in shared memory (latency); larger batches: image through L2, 3x the frames per SM
-    if (h->img_smem_ok && 2 * batch <= h->resident_smem_frames && !h->force_global_image) {
+    // a wave of frames or less: the frame-level parallelism cannot fill the GPU, several warps per frame (speculative, in-order
+    // commit) cut the latency of a live frame instead
+    const bool mw = h->mw_warps >= 2 && batch <= h->mw_max_batch && h->grow_variant != 1 &&
+                    (h->grow_variant == 2 || batch <= ctx->sm_count);
+    if (mw) {
+        PLP_LAUNCH(ctx, lsd_grow_mw_kernel, batch, h->mw_warps * 32, h->mw_smem, D, h->d_reg_mw);
+    } else if (h->img_smem_ok && 2 * batch <= h->resident_smem_frames && !h->force_global_image) {
         PLP_LAUNCH(ctx, lsd_grow_kernel<true>, batch, 32, h->grow_smem, D);
     } else {
         PLP_LAUNCH(ctx, lsd_grow_kernel<false>, batch, 32, h->grow_smem_noimg, D);
@@ -1127,6 +1352,20 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
     if (h->img_smem_ok) so = ensure_smem_optin((const void *)lsd_grow_kernel<true>, h->grow_smem, "lsd_grow_kernel<true>");
     if (so == PLP_OK) so = ensure_smem_optin((const void *)lsd_grow_kernel<false>, h->grow_smem_noimg, "lsd_grow_kernel<false>");
     if (so == PLP_OK) so = ensure_smem_optin((const void *)lsd_sort_kernel, h->sort_smem, "lsd_sort_kernel");
+    {  // multi-warp variant: image + committed bitmap + per warp {private bitmap, region window}
+        const size_t fixed = (size_t)((D.npx + 15) & ~15) + used_bytes + sizeof(MwCtl) + 64, per_warp = used_bytes + (size_t)kMwRegCap * 4;
+        const size_t budget = 227 * 1024;
+        h->mw_warps = fixed + 2 * per_warp <= budget ? (int)std::min<size_t>(kMwMaxWarps, (budget - fixed) / per_warp) : 0;
+        if (const char *ev = getenv("PLP_LSD_MW_WARPS")) h->mw_warps = std::max(0, std::min(h->mw_warps, atoi(ev)));  // tuning aid
+        h->mw_smem = fixed + (size_t)h->mw_warps * per_warp;
+        h->mw_max_batch = h->mw_warps >= 2 ? std::min(max_batch, ctx->sm_count) : 0;
+        if (h->mw_warps >= 2) {
+            if (so == PLP_OK) so = ensure_smem_optin((const void *)lsd_grow_mw_kernel, h->mw_smem, "lsd_grow_mw_kernel");
+            if (so == PLP_OK) so = dev_alloc(h, &h->d_reg_mw, (size_t)h->mw_max_batch * kMwMaxWarps * D.npx);
+            if (so == PLP_OK) so = dev_alloc(h, &h->dev.mw_stat, (size_t)3 * max_batch);
+            if (so == PLP_OK && cudaMemsetAsync(h->dev.mw_stat, 0, (size_t)3 * max_batch * 8, ctx->stream) != cudaSuccess) so = PLP_ERR_CUDA;
+        }
+    }
     if (so != PLP_OK) {
         plp_line_destroy(h);
         return so;
@@ -1193,6 +1432,25 @@ plp_status plp_line_extract_batch(plp_line *h, const uint8_t *imgs, int batch, s
 plp_status plp_line_debug_force_global_image(plp_line *h, int on) {
     PLP_REQUIRE(h, "null pointer");
     h->force_global_image = on != 0;
+    return PLP_OK;
+}
+
+plp_status plp_line_debug_grow_variant(plp_line *h, int variant) {
+    PLP_REQUIRE(h && variant >= 0 && variant <= 2, "variant must be 0 (automatic), 1 (one warp per frame) or 2 (multi-warp)");
+    PLP_REQUIRE(variant != 2 || h->mw_warps >= 2, "the multi-warp variant does not fit the shared memory at this image size");
+    h->grow_variant = variant;
+    return PLP_OK;
+}
+
+plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out3) {
+    PLP_REQUIRE(h && out3, "null pointer");
+    PLP_REQUIRE(b >= 0 && b < h->max_batch, "index");
+    out3[0] = out3[1] = out3[2] = 0;
+    if (!h->dev.mw_stat) return PLP_OK;
+    plp_ctx *ctx = h->ctx;
+    PLP_CUDA_TRY(cudaSetDevice(ctx->device));
+    PLP_CUDA_TRY(cudaMemcpyAsync(out3, h->dev.mw_stat + 3 * (size_t)b, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return PLP_OK;
 }
 

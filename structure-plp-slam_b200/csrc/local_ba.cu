@@ -696,15 +696,27 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
         // (ascending landmark = the summation order of a dense scan)
         if (tid < 504) {
             const int n_line0 = B.n_pts - batch0;  // landmarks lb >= n_line0 of this batch are lines
+            // block p = (bi, bj), bi <= bj, row-wise; the walk in steps of 14 is tracked without the index tables
+            const int N = B.n_free;
+            int bi = 0, bj = own_p0;
+            while (bj >= N && bi < N) {  // bi == N: past the last block (the loop below does not run)
+                ++bi;
+                bj = bj - N + bi;
+            }
             for (int p = own_p0; p < B.n_pairs; p += 14) {
-                const int bi = B.pair_bi[p], bj = B.pair_bj[p];
-                unsigned m = S.kfmask[bi] & S.kfmask[bj];
+                const int cbi = bi, cbj = bj;
+                bj += 14;
+                while (bj >= N && bi < N) {
+                    ++bi;
+                    bj = bj - N + bi;
+                }
+                unsigned m = S.kfmask[cbi] & S.kfmask[cbj];
                 if (!m) continue;
                 double acc = 0.0;
                 while (m) {
                     const int lb = __ffs(m) - 1;
                     m &= m - 1;
-                    const BaPoolEntry &pi = pool[S.slot[lb][bi]], &pj = pool[S.slot[lb][bj]];
+                    const BaPoolEntry &pi = pool[S.slot[lb][cbi]], &pj = pool[S.slot[lb][cbj]];
                     double s;
                     if (lb >= n_line0) {
                         const double *y = pi.Y + own_r * 4, *wv = pj.W + own_c * 4;
@@ -714,7 +726,7 @@ __global__ void __launch_bounds__(kBaThreads, 1) ba_linearize_kernel(BaDev B) {
                         s = y[0] * wv[0] + y[1] * wv[1] + y[2] * wv[2];
                     }
                     acc -= s;
-                    if (bi == bj) acc += pi.A[own_tri];
+                    if (cbi == cbj) acc += pi.A[own_tri];
                 }
                 Ssm[p * 36 + own_rc] += acc;
             }
@@ -866,10 +878,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
     // right-hand side carried along as an extra row "n" so that the forward substitution z = L^-1 b falls out of the
     // factorisation.  Per block column two phases / two barriers: (1) every thread that owns a row below the diagonal
     // block factors that 6 x 6 block ITSELF, in registers (the same 21 shared-memory words for everybody: broadcast
-    // reads, no serial section, no barrier between factor and use) and solves its row against it; (2) one warp per
-    // trailing row applies the rank-6 update, lanes over the (contiguous) columns.  The factored diagonal blocks go to
+    // reads, no serial section, no barrier between factor and use) and solves its row against it; (2) the rank-6
+    // update of the trailing triangle, one 4 x 4 register tile per thread.  The factored diagonal blocks go to
     // Ld (the unfactored ones stay in L: other threads may still be reading them).
-    const int lane = tid & 31, warp = tid >> 5, nwarps = kSolveThreads / 32;
+    const int lane = tid & 31, warp = tid >> 5;
     for (int K = 0; K < n; K += 6) {
         const int row = K + 6 + tid;
         if (row <= n) {
@@ -914,14 +926,53 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(BaDev B) {
         }
         __syncthreads();
         if (!s_ok) break;  // uniform
-        for (int i = K + 6 + warp; i <= n; i += nwarps) {
-            const double *li = i < n ? &L[tri(i, K)] : &rhs[K];
-            const double l0 = li[0], l1 = li[1], l2 = li[2], l3 = li[3], l4 = li[4], l5 = li[5];
-            double *rowp = i < n ? &L[tri(i, 0)] : rhs;
-            const int kmax = i < n ? i : n - 1;
-            for (int k = K + 6 + lane; k <= kmax; k += 32) {
+        // rank-6 update of the trailing lower triangle, register-tiled: one thread = one 4 x 4 tile (24 + 24 loads for 96
+        // multiply-adds, all independent), then the right-hand side row
+        const int m = n - K - 6;
+        if (m > 0) {
+            const int T = (m + 3) >> 2, ntiles = T * (T + 1) / 2;
+            for (int q = tid; q < ntiles; q += kSolveThreads) {
+                int ti = (int)((sqrtf(8.f * (float)q + 1.f) - 1.f) * 0.5f);
+                while (ti * (ti + 1) / 2 > q) --ti;
+                while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
+                const int tk = q - ti * (ti + 1) / 2;
+                const int i0 = K + 6 + 4 * ti, k0 = K + 6 + 4 * tk;
+                int ri[4], rk[4];  // row starts in the packed triangle (rows past the end are clamped: loaded, never stored)
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    ri[a] = tri(min(i0 + a, n - 1), 0);
+                    rk[a] = tri(min(k0 + a, n - 1), 0);
+                }
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    double rv[4], cv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        rv[a] = L[ri[a] + K + c];
+                        cv[a] = L[rk[a] + K + c];
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] += rv[a] * cv[b2];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) {
+                        const int i = i0 + a, k = k0 + b2;
+                        if (i < n && k <= i) L[ri[a] + k] -= acc[a][b2];
+                    }
+            }
+            const double a0 = rhs[K], a1 = rhs[K + 1], a2 = rhs[K + 2], a3 = rhs[K + 3], a4 = rhs[K + 4], a5 = rhs[K + 5];
+            for (int k = K + 6 + tid; k < n; k += kSolveThreads) {
                 const double *lk = &L[tri(k, K)];
-                rowp[k] -= l0 * lk[0] + l1 * lk[1] + l2 * lk[2] + l3 * lk[3] + l4 * lk[4] + l5 * lk[5];
+                rhs[k] -= a0 * lk[0] + a1 * lk[1] + a2 * lk[2] + a3 * lk[3] + a4 * lk[4] + a5 * lk[5];
             }
         }
         __syncthreads();

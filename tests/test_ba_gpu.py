@@ -133,12 +133,12 @@ def test_global_ba(ctx, orc, plp, n_kf, huber, lines):
     assert rel_pose < 1e-4, rel_pose
     rel_pts = np.linalg.norm(g["pt_pos_w"] - o.pt_pos_w, axis=1) / np.linalg.norm(o.pt_pos_w, axis=1)
     assert np.quantile(rel_pts, 0.999) < 1e-4
-    assert g["iters_first"] == o.iters_first
-    if big and lines:
-        # 426 pose unknowns + numeric line Jacobians: once converged, the accept / reject decision of a try hangs on the
-        # sign of a chi2 difference at rounding level (measured: 33 vs 30 tries, same 20 iterations, same optimum)
-        assert abs(g["lm_tries"] - o.lm_tries) <= 5
+    if big:
+        # 426 pose unknowns: once converged, the accept / reject decision of a try (and the rho == 0 stop) hangs on the
+        # sign of a chi2 difference at rounding level (measured: 33 vs 30 tries with lines, 18 vs 20 iterations without;
+        # same optimum, same final chi2 to 1e-6)
+        assert abs(g["lm_tries"] - o.lm_tries) <= 5 and abs(g["iters_first"] - o.iters_first) <= 3
     else:
-        assert g["lm_tries"] == o.lm_tries
+        assert g["iters_first"] == o.iters_first and g["lm_tries"] == o.lm_tries
     assert abs(g["final_chi2"] - o.final_chi2) <= 1e-6 * abs(o.final_chi2)
     assert o.iters_first > 2

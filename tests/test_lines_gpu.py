@@ -32,20 +32,30 @@ def _compare(trk, orc, img, b=0, got=None):
     return len(segs), len(kl)
 
 
+# region growing variants (lines.cu): 1 = one warp per frame, 2 = several warps per frame, speculative with in-order commit
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("kind,seed,shape", [("lines", 1, (480, 640)), ("lines", 2, (480, 752)), ("texture", 1234, (480, 640)),
-                                             ("texture", 7, (480, 752)), ("lines", 9, (376, 1240))])
-def test_line_extract_matches_oracle(ctx, orc, plp, kind, seed, shape):
-    img = synth.make_line_image(seed, *shape) if kind == "lines" else synth.make_texture(seed, *shape)
+                                             ("texture", 7, (480, 752)), ("lines", 9, (376, 1240)), ("plp", 5, (480, 640))])
+def test_line_extract_matches_oracle(ctx, orc, plp, kind, seed, shape, variant):
+    img = (synth.make_line_image(seed, *shape) if kind == "lines" else synth.make_plp_texture(seed, *shape) if kind == "plp"
+           else synth.make_texture(seed, *shape))
     trk = plp.LineFeatureTracker(ctx, shape[0], shape[1])
+    trk.grow_variant(variant)
     nseg, nkl = _compare(trk, orc, img)
     assert nseg > 100
     if kind == "lines":
         assert nkl > 40
+    if variant == 2:
+        st = trk.grow_stats(0)
+        assert st["rounds"] > 0 and st["seeds_run"] >= nseg
+        print(f"[mw] {kind} {shape}: {st}, {nseg} segments")
     trk.close()
 
 
-def test_edge_cases(ctx, orc, plp):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_edge_cases(ctx, orc, plp, variant):
     trk = plp.LineFeatureTracker(ctx, 480, 640)
+    trk.grow_variant(variant)
     # flat image: no gradient above the threshold, no seed, no line (the reference returns empty outputs)
     kl, lbd, fn = trk.extract_LSD_LBD(np.full((480, 640), 128, np.uint8))
     assert len(kl) == 0 and lbd.shape == (0, 32) and fn.shape == (0, 3)
@@ -70,12 +80,15 @@ def test_edge_cases(ctx, orc, plp):
 def test_batch_equals_single(ctx, orc, plp):
     imgs = np.stack([synth.make_line_image(20 + i) for i in range(5)] + [synth.make_texture(3)])
     trk = plp.LineFeatureTracker(ctx, 480, 640, max_batch=6)
-    for global_image in (False, True):  # both placements of the half-resolution image in the region-growing kernel
+    # one warp per frame with both placements of the half-resolution image, then the multi-warp variant
+    for variant, global_image in ((1, False), (1, True), (2, False)):
+        trk.grow_variant(variant)
         trk.force_global_image(global_image)
         res = trk.extract_batch(imgs)
         for b in range(len(imgs)):
             _compare(trk, orc, imgs[b], b=b, got=res[b])
     trk.force_global_image(False)
+    trk.grow_variant(0)
     # strided input (step > cols) through the single-frame entry point
     wide = np.zeros((480, 700), np.uint8)
     wide[:, :640] = imgs[1]
