@@ -597,9 +597,10 @@ PLP_API plp_status plp_line_debug_segments(plp_line *h, int b, float *segs_out, 
 PLP_API plp_status plp_line_debug_force_global_image(plp_line *h, int on);
 /* region growing variant: 0 automatic (multi-warp for at most one wave of frames, i.e. the live-sequence case), 1 one warp
  * per frame, 2 speculative multi-warp with in-order commit; all three produce the sequential result bit for bit.
- * grow_stats: {rounds, seeds run, seeds redone after a conflict} of frame b in the last multi-warp run. */
+ * grow_stats (7 values): {rounds, seeds run, seeds redone after a conflict, then SM cycles warp 0 spent scanning for seeds,
+ * on its own seed, waiting for the slowest warp of the round, committing} of frame b in the last multi-warp run. */
 PLP_API plp_status plp_line_debug_grow_variant(plp_line *h, int variant);
-PLP_API plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out3);
+PLP_API plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out7);
 PLP_API plp_status plp_line_debug_scaled(plp_line *h, int b, uint8_t *out /* (rows/2) x (cols/2) */);
 PLP_API plp_status plp_line_debug_lbd_float(plp_line *h, int b, float *out /* n x 72 */, int cap);
 

@@ -836,9 +836,10 @@ class LineFeatureTracker:
 
     def grow_stats(self, b: int = 0):
         """{rounds, seeds run, seeds redone after a conflict} of frame b in the last multi-warp run."""
-        out = (C.c_ulonglong * 3)()
+        out = (C.c_ulonglong * 7)()
         self._ctx._check(self._lib.plp_line_debug_grow_stats(self._h, C.c_int(b), out))
-        return dict(rounds=int(out[0]), seeds_run=int(out[1]), seeds_redone=int(out[2]))
+        return dict(rounds=int(out[0]), seeds_run=int(out[1]), seeds_redone=int(out[2]), cyc_scan=int(out[3]),
+                    cyc_own=int(out[4]), cyc_wait=int(out[5]), cyc_commit=int(out[6]))
 
     def debug_segments(self, b: int) -> np.ndarray:
         cap = 20000

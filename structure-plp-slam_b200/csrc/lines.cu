@@ -750,7 +750,7 @@ struct MwCtl {
     int nfinal[kMwMaxWarps];
     int ok[kMwMaxWarps];
     float4 seg[kMwMaxWarps];
-    unsigned long long stat[4];  // rounds, seeds run, seeds redone (tuning aid, read by nobody on the hot path)
+    unsigned long long stat[8];  // rounds, seeds run, seeds redone, cycles of warp 0: scan, own seed, wait, commit (tuning aid)
 };
 
 __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D, uint32_t *reg_ovf_mw) {
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D
             for (int i = tid; i < D.npx; i += blockDim.x) s_img[i] = src[i];
         }
         for (int i = tid; i < used_pad * (W + 1); i += blockDim.x) s_used[i] = 0;
-        if (tid < 4) C.stat[tid] = 0;
+        if (tid < 8) C.stat[tid] = 0;
     }
     __syncthreads();
     GrowT<true> G;
@@ -796,6 +796,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D
     const int sw = D.sw;
     int nseg = 0, cursor = 0;  // identical in every warp
     for (;;) {
+        const long long tc0 = clock64();
         // ---- the next W seeds that are not used in the committed map (every warp scans for itself: same result)
         int my_pos = -1;       // lane i < W: position of the round's i-th seed in the order list
         uint32_t my_xy = 0;
@@ -818,6 +819,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D
             scan += 32;
         }
         if (found == 0) break;  // uniform over the CTA
+        const long long tc1 = clock64();
         // ---- phase 1: warp w runs the w-th seed
         if (warp < found) {
             const uint32_t seed_xy = __shfl_sync(kFull, my_xy, warp);
@@ -854,7 +856,9 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D
                                               (float)((R.x2 + 0.5) / 0.5), (float)((R.y2 + 0.5) / 0.5));
             }
         }
+        const long long tc2 = clock64();
         __syncthreads();
+        const long long tc3 = clock64();
         // ---- phase 2 (every warp, same result): first seed whose box meets the box of an earlier seed of the round
         int first_bad = found;
         {
@@ -896,19 +900,21 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D
             const int pos_bad = __shfl_sync(kFull, my_pos, min(first_bad, found - 1));
             cursor = first_bad < found ? pos_bad : pos_bad + 1;
         }
+        __syncthreads();
         if (tid == 0) {
             C.stat[0] += 1;
             C.stat[1] += (unsigned long long)found;
             C.stat[2] += (unsigned long long)(found - first_bad);
+            C.stat[3] += (unsigned long long)(tc1 - tc0);
+            C.stat[4] += (unsigned long long)(tc2 - tc1);
+            C.stat[5] += (unsigned long long)(tc3 - tc2);
+            C.stat[6] += (unsigned long long)(clock64() - tc3);
         }
-        __syncthreads();
     }
     if (tid == 0) {
         D.nseg[b] = min(nseg, D.seg_cap);
         if (D.mw_stat) {
-            D.mw_stat[3 * b] = C.stat[0];
-            D.mw_stat[3 * b + 1] = C.stat[1];
-            D.mw_stat[3 * b + 2] = C.stat[2];
+            for (int q = 0; q < 7; ++q) D.mw_stat[8 * b + q] = C.stat[q];
         }
     }
 }
@@ -1362,8 +1368,8 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
         if (h->mw_warps >= 2) {
             if (so == PLP_OK) so = ensure_smem_optin((const void *)lsd_grow_mw_kernel, h->mw_smem, "lsd_grow_mw_kernel");
             if (so == PLP_OK) so = dev_alloc(h, &h->d_reg_mw, (size_t)h->mw_max_batch * kMwMaxWarps * D.npx);
-            if (so == PLP_OK) so = dev_alloc(h, &h->dev.mw_stat, (size_t)3 * max_batch);
-            if (so == PLP_OK && cudaMemsetAsync(h->dev.mw_stat, 0, (size_t)3 * max_batch * 8, ctx->stream) != cudaSuccess) so = PLP_ERR_CUDA;
+            if (so == PLP_OK) so = dev_alloc(h, &h->dev.mw_stat, (size_t)8 * max_batch);
+            if (so == PLP_OK && cudaMemsetAsync(h->dev.mw_stat, 0, (size_t)8 * max_batch * 8, ctx->stream) != cudaSuccess) so = PLP_ERR_CUDA;
         }
     }
     if (so != PLP_OK) {
@@ -1445,11 +1451,11 @@ plp_status plp_line_debug_grow_variant(plp_line *h, int variant) {
 plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out3) {
     PLP_REQUIRE(h && out3, "null pointer");
     PLP_REQUIRE(b >= 0 && b < h->max_batch, "index");
-    out3[0] = out3[1] = out3[2] = 0;
+    for (int q = 0; q < 7; ++q) out3[q] = 0;
     if (!h->dev.mw_stat) return PLP_OK;
     plp_ctx *ctx = h->ctx;
     PLP_CUDA_TRY(cudaSetDevice(ctx->device));
-    PLP_CUDA_TRY(cudaMemcpyAsync(out3, h->dev.mw_stat + 3 * (size_t)b, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaMemcpyAsync(out3, h->dev.mw_stat + 8 * (size_t)b, 56, cudaMemcpyDeviceToHost, ctx->stream));
     PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return PLP_OK;
 }

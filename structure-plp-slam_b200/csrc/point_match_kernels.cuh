@@ -336,37 +336,65 @@ __global__ void __launch_bounds__(kThreads, 1)
         // candidate list, so the chains end -- without a single block barrier or work list.  The first generation re-ran
         // whole rounds separated by barriers: 46-68 % of the kernel's stall samples were 1000 threads waiting for the few
         // bumped queries of a round (profiles/source_hotspots_r02*.md).
-        for (int q0 = 0; q0 < m_pad; q0 += kGroups) {
-            const int q = q0 + grp;
-            int cur = (q < m && (J.qvalid ? (J.qvalid[q] != 0) : true)) ? q : -1;
-            int floor = -1;
-            if (gl == 0 && q < m && cur < 0) J.choice[q] = -1;
-            while (__any_sync(0xffffffffu, cur >= 0)) {
-                int k1, k2;
-                group_scan(S, J, grid, cur >= 0, cur, gl, nullptr, floor, k1, k2);
-                int next = -1, nfloor = -1;
-                if (gl == 0 && cur >= 0) {
-                    int choice = -1;
-                    if (k1 != kNoKey && (k1 >> 12) <= hamm_thr) choice = k1 & 0xfff;
-                    J.choice[cur] = choice;
-                    if (choice >= 0) {
-                        __threadfence_block();  // the choice is visible before another group can take the query over
-                        const int old = atomicMin(&owner[choice], cur);
-                        if (old < cur) {  // lost at once: continue behind this candidate
-                            next = cur;
-                            nfloor = k1;
-                        } else if (old != kNoOwner) {  // bumped `old` off this keypoint: find its next candidate
-                            uint4 o0, o1;
-                            load_desc(J.qdesc + 32 * (size_t)old, o0, o1);
-                            next = old;
-                            nfloor = (hamming256(o0, o1, S.desc[2 * choice], S.desc[2 * choice + 1]) << 12) | choice;
-                        }
+        // Queries are handed out by a shared counter (the result of deferred acceptance does not depend on the order of
+        // the proposals): a group whose chain has ended takes the next query at once, so the 8 groups of a warp stay busy
+        // while one of them follows a long chain, and only the last few chains of the frame run alone.  A proposal that
+        // loses moves on to the second-best key of the same scan before the window is scanned again.
+        int cur = -1, floor = -1;
+        const int leader = lane & ~(kGroup - 1);
+        for (;;) {
+            {
+                int q = -1;
+                if (cur < 0 && gl == 0) {
+                    q = atomicAdd(&S.flags[3], 1);
+                    while (q < m && J.qvalid && J.qvalid[q] == 0) {
+                        J.choice[q] = -1;
+                        q = atomicAdd(&S.flags[3], 1);
                     }
+                    if (q >= m) q = -1;
                 }
-                const int leader = lane & ~(kGroup - 1);
-                cur = __shfl_sync(0xffffffffu, next, leader);
-                floor = __shfl_sync(0xffffffffu, nfloor, leader);
+                const int got = __shfl_sync(0xffffffffu, q, leader);  // every lane of the warp takes part
+                if (cur < 0) {
+                    cur = got;
+                    floor = -1;
+                }
             }
+            if (!__any_sync(0xffffffffu, cur >= 0)) break;
+            int k1, k2;
+            group_scan(S, J, grid, cur >= 0, cur, gl, nullptr, floor, k1, k2);
+            int next = -1, nfloor = -1;
+            if (gl == 0 && cur >= 0) {
+                J.choice[cur] = -1;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int key = t == 0 ? k1 : k2;
+                    if (key == kNoKey || (key >> 12) > hamm_thr) {
+                        // keys come in ascending (distance, order): nothing acceptable is left, the query stays unmatched
+                        next = -1;
+                        break;
+                    }
+                    const int choice = key & 0xfff;
+                    J.choice[cur] = choice;
+                    __threadfence_block();  // the choice is visible before another group can take the query over
+                    const int old = atomicMin(&owner[choice], cur);
+                    if (old < cur) {  // lost at once: continue behind this candidate (second key, then a new scan)
+                        J.choice[cur] = -1;
+                        next = cur;
+                        nfloor = key;
+                        continue;
+                    }
+                    next = -1;
+                    if (old != kNoOwner) {  // bumped `old` off this keypoint: find its next candidate
+                        uint4 o0, o1;
+                        load_desc(J.qdesc + 32 * (size_t)old, o0, o1);
+                        next = old;
+                        nfloor = (hamming256(o0, o1, S.desc[2 * choice], S.desc[2 * choice + 1]) << 12) | choice;
+                    }
+                    break;
+                }
+            }
+            cur = __shfl_sync(0xffffffffu, next, leader);
+            floor = __shfl_sync(0xffffffffu, nfloor, leader);
         }
         __syncthreads();
     } else {
