@@ -160,8 +160,22 @@ struct Lsd {
         return n_theta <= prec;
     }
 
+    // debug trace (orc_debug_lsd_trace): bounding box / count of every pixel accepted while one seed is processed
+    bool tracing = false;
+    int tb[4] = {0, 0, 0, 0};
+    long taccepted = 0;
+    void trace_px(int x, int y) {
+        if (!tracing) return;
+        tb[0] = std::min(tb[0], x);
+        tb[1] = std::min(tb[1], y);
+        tb[2] = std::max(tb[2], x);
+        tb[3] = std::max(tb[3], y);
+        ++taccepted;
+    }
+
     void region_grow(int sx, int sy, std::vector<RegPt> &reg, double &reg_angle, double prec) {
         reg.clear();
+        trace_px(sx, sy);
         reg_angle = angles[(size_t)sy * w + sx];
         reg.push_back({sx, sy, reg_angle, modgrad[(size_t)sy * w + sx]});
         float sumdx = float(cosd(reg_angle));
@@ -177,6 +191,7 @@ struct Lsd {
                     if (u != 1 && is_aligned(xx, yy, reg_angle, prec)) {
                         const double angle = angles[(size_t)yy * w + xx];
                         u = 1;
+                        trace_px(xx, yy);
                         reg.push_back({xx, yy, angle, modgrad[(size_t)yy * w + xx]});
                         sumdx += cosf_(float(angle));
                         sumdy += sinf_(float(angle));
@@ -340,8 +355,10 @@ void scaled_image(const uint8_t *img, int w, int h, int step, std::vector<uint8_
         }
 }
 
-int lsd_detect(const uint8_t *img, int w, int h, int step, const orc_lsd_config *c, std::vector<float> &segs) {
+int lsd_detect(const uint8_t *img, int w, int h, int step, const orc_lsd_config *c, std::vector<float> &segs,
+               std::vector<int32_t> *trace = nullptr) {
     Lsd L;
+    L.tracing = trace != nullptr;
     L.cfg = {c->seed_order != 0, c->libm_float != 0, c->sum_order != 0};
     std::vector<uint8_t> scaled;
     scaled_image(img, w, h, step, scaled, L.w, L.h);
@@ -353,15 +370,38 @@ int lsd_detect(const uint8_t *img, int w, int h, int step, const orc_lsd_config 
     const size_t min_reg_size = size_t(-log_nt / std::log10(p));
     L.used.assign((size_t)L.w * L.h, 0);
     std::vector<RegPt> reg;
+    int32_t pos = -1;
     for (const NormPoint &pt : L.ordered) {
+        ++pos;
         const size_t a = (size_t)pt.y * L.w + pt.x;
         if (L.used[a] != 0 || L.angles[a] == kNotDef) continue;
         double reg_angle;
+        if (trace) {
+            L.tb[0] = L.tb[1] = 1 << 30;
+            L.tb[2] = L.tb[3] = -1;
+            L.taccepted = 0;
+        }
+        // one record per processed seed: position in the order list, x, y, first region size, pixels accepted in total
+        // (all growths), final region size (marks left), bounding box of everything accepted, segment emitted
+        auto rec_out = [&](size_t first_n, size_t final_n, int emitted) {
+            if (!trace) return;
+            const int32_t r[11] = {pos, pt.x, pt.y, (int32_t)first_n, (int32_t)L.taccepted, (int32_t)final_n,
+                                   L.tb[0], L.tb[1], L.tb[2], L.tb[3], emitted};
+            trace->insert(trace->end(), r, r + 11);
+        };
         L.region_grow(pt.x, pt.y, reg, reg_angle, prec);
-        if (reg.size() < min_reg_size) continue;
+        const size_t first_n = reg.size();
+        if (reg.size() < min_reg_size) {
+            rec_out(first_n, reg.size(), 0);
+            continue;
+        }
         Rect rec;
         L.region2rect(reg, reg_angle, prec, p, rec);
-        if (!L.refine(reg, reg_angle, prec, p, rec, kDensityTh)) continue;
+        if (!L.refine(reg, reg_angle, prec, p, rec, kDensityTh)) {
+            rec_out(first_n, reg.size(), 0);
+            continue;
+        }
+        rec_out(first_n, reg.size(), 1);
         rec.x1 += 0.5;
         rec.y1 += 0.5;
         rec.x2 += 0.5;
@@ -625,6 +665,17 @@ int orc_lsd_ll_angle(const uint8_t *scaled, int w, int h, const orc_lsd_config *
     if (order)
         for (size_t i = 0; i < L.ordered.size(); ++i) order[i] = L.ordered[i].y * w + L.ordered[i].x;
     return (int)L.ordered.size();
+}
+
+/* debug: one 11-int record per seed the sequential detector processes (see lsd_detect); returns the record count */
+int orc_debug_lsd_trace(const uint8_t *img, int w, int h, int step, const orc_lsd_config *cfg, int32_t *out, int cap_records) {
+    std::vector<float> segs;
+    std::vector<int32_t> tr;
+    lsd_detect(img, w, h, step, cfg, segs, &tr);
+    const int n = (int)(tr.size() / 11);
+    if (n > cap_records) return -n;
+    std::memcpy(out, tr.data(), tr.size() * sizeof(int32_t));
+    return n;
 }
 
 int orc_lsd_detect(const uint8_t *img, int w, int h, int step, const orc_lsd_config *cfg, float *segments, int cap) {

@@ -50,6 +50,9 @@ int orc_lsd_ll_angle(const uint8_t *scaled, int w, int h, const orc_lsd_config *
                      int32_t *bins, int32_t *order);
 /* full detector on the full-resolution image: segments as (x1,y1,x2,y2) float, in detection order */
 int orc_lsd_detect(const uint8_t *img, int w, int h, int step, const orc_lsd_config *cfg, float *segments, int cap);
+/* debug: per processed seed {order position, x, y, first region size, pixels accepted in total, final region size, bbox x0 y0
+ * x1 y1 of everything accepted, segment emitted}; returns the number of records (-needed if cap is too small) */
+int orc_debug_lsd_trace(const uint8_t *img, int w, int h, int step, const orc_lsd_config *cfg, int32_t *out, int cap_records);
 /* LSDDetectorC::detectImpl (LSDDetector_custom.cpp:225-320) for one octave */
 int orc_lsd_keylines(const uint8_t *img, int w, int h, int step, const orc_lsd_config *cfg, double min_length,
                      orc_keyline *out, int cap);

@@ -1232,7 +1232,7 @@ static plp_status line_run(plp_line *h, const uint8_t *d_imgs, int batch, size_t
     // a wave of frames or less: the frame-level parallelism cannot fill the GPU, several warps per frame (speculative, in-order
     // commit) cut the latency of a live frame instead
     const bool mw = h->mw_warps >= 2 && batch <= h->mw_max_batch && h->grow_variant != 1 &&
-                    (h->grow_variant == 2 || batch <= ctx->sm_count);
+                    (h->grow_variant == 2 || 2 * batch <= ctx->sm_count);  // half a wave: a second handle (stereo) fits beside it
     if (mw) {
         PLP_LAUNCH(ctx, lsd_grow_mw_kernel, batch, h->mw_warps * 32, h->mw_smem, D, h->d_reg_mw);
     } else if (h->img_smem_ok && 2 * batch <= h->resident_smem_frames && !h->force_global_image) {
