@@ -53,6 +53,7 @@ struct LineDev {
     uint32_t *order;     // npx packed (y<<16|x) seeds, bin desc / raster asc
     int *nseeds;
     uint32_t *reg_xy;    // npx: region entries beyond the shared-memory window
+    int direct_trig;     // bit 0: lsd_grow_mw_kernel, bit 1: lsd_grow_kernel compute the neighbour's {deg, cos, sin} directly
     unsigned long long *mw_stat;  // per frame {rounds, seeds run, seeds redone} of lsd_grow_mw_kernel (may be null)
     float4 *segs;        // seg_cap
     int *nseg;
@@ -300,6 +301,7 @@ struct GrowT {  // per-warp state
     uint32_t *reg_ovf;     // global: all entries beyond reg_cap (indexed by absolute position)
     const float4 *tab;     // global: {deg, cos, sin} by (gx, gy)
     int lane, reg_cap;
+    bool direct;           // compute {deg, cos, sin} of a neighbour instead of reading the table
     mutable int bx0, by0, bx1, by1;  // kMw: per-lane bounding box of the pixels this lane accepted (reduced by the caller)
 #ifdef PLP_LSD_PROF
     long long *pc;         // [0] iterations [1] rounds [2] cycles load phase [3] cycles resolve phase [4] on-demand loads
@@ -374,7 +376,13 @@ __device__ __forceinline__ Nb load_nb(const GrowT<kMw> &G, int e, int ddx, int d
         if (gx * gx + gy * gy > G.kthr) {
             r.nidx = idx;
             r.xy = ((uint32_t)ny << 16) | (uint32_t)nx;
-            r.t = G.tab[(gy + kGRange) * kGDim + gx + kGRange];
+            if (G.direct) {  // latency mode: ~250 dependent cycles of arithmetic instead of a table entry from L2
+                const float deg = fast_atan2_deg((float)gx, (float)-gy);
+                const double af = (double)(float)((double)deg * kDegToRads);
+                r.t = make_float4(deg, (float)det_cos(af), (float)det_sin(af), 0.f);
+            } else {
+                r.t = G.tab[(gy + kGRange) * kGDim + gx + kGRange];
+            }
         }
     }
     return r;
@@ -662,6 +670,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
     G.reg = s_reg;
     G.reg_ovf = D.reg_xy + (size_t)b * D.npx;
     G.tab = D.cstab;
+    G.direct = (D.direct_trig & 2) != 0;
 #ifdef PLP_LSD_PROF
     G.pc = s_pc;
 #endif
@@ -789,6 +798,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D
     G.reg = s_reg + (size_t)warp * kMwRegCap;
     G.reg_ovf = reg_ovf_mw + ((size_t)b * kMwMaxWarps + warp) * D.npx;
     G.tab = D.cstab;
+    G.direct = (D.direct_trig & 1) != 0;
     G.lane = lane;
     const uint32_t *order = D.order + (size_t)b * D.npx;
     float4 *segs = D.segs + (size_t)b * D.seg_cap;
@@ -1362,6 +1372,7 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
         const size_t fixed = (size_t)((D.npx + 15) & ~15) + used_bytes + sizeof(MwCtl) + 64, per_warp = used_bytes + (size_t)kMwRegCap * 4;
         const size_t budget = 227 * 1024;
         h->mw_warps = fixed + 2 * per_warp <= budget ? (int)std::min<size_t>(kMwMaxWarps, (budget - fixed) / per_warp) : 0;
+        if (const char *ev = getenv("PLP_LSD_DIRECT")) h->dev.direct_trig = atoi(ev);  // tuning aid
         if (const char *ev = getenv("PLP_LSD_MW_WARPS")) h->mw_warps = std::max(0, std::min(h->mw_warps, atoi(ev)));  // tuning aid
         h->mw_smem = fixed + (size_t)h->mw_warps * per_warp;
         h->mw_max_batch = h->mw_warps >= 2 ? std::min(max_batch, ctx->sm_count) : 0;

@@ -56,7 +56,7 @@ fi
 if [[ " $WHAT " == *" lsd "* ]]; then
   timeout 900 python -m pytest tests/test_lines_gpu.py -q -m gpu -x -s > gpurun_out/test_lines_${TAG}.log 2>&1
   echo "lines tests exit $?"; grep "\[mw\]" gpurun_out/test_lines_${TAG}.log | head -20; tail -5 gpurun_out/test_lines_${TAG}.log
-  timeout 600 python tools/lsd_latency.py 8 > gpurun_out/lsd_latency_${TAG}.log 2>&1; echo "lsd latency exit $?"; cat gpurun_out/lsd_latency_${TAG}.log
+  timeout 600 python tools/lsd_latency.py 8:0 8:3 > gpurun_out/lsd_latency_${TAG}.log 2>&1; echo "lsd latency exit $?"; cat gpurun_out/lsd_latency_${TAG}.log
 fi
 if [[ " $WHAT " == *" ba "* ]]; then
   timeout 600 python -m pytest tests/test_ba_gpu.py tests/test_plane_gpu.py -q -m gpu -x > gpurun_out/test_ba_${TAG}.log 2>&1

@@ -44,11 +44,15 @@ def kernel_ms(trk, imgs):
     return {k.split("<")[0].replace("_kernel", ""): round(v["total_ms"] / v["count"], 3) for k, v in kt.items()}
 
 
-warps_list = [int(a) for a in sys.argv[1:]] or [8]
-for warps in warps_list:
+# arguments: WARPS[:DIRECT] ...   (DIRECT = PLP_LSD_DIRECT bit mask: 1 multi-warp kernel, 2 one-warp kernel compute cos / sin)
+cfgs = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(8,)]
+warps_list = [c[0] for c in cfgs]
+for cfg in cfgs:
+    warps = cfg[0]
     os.environ["PLP_LSD_MW_WARPS"] = str(warps)
+    os.environ["PLP_LSD_DIRECT"] = str(cfg[1] if len(cfg) > 1 else 0)
     for kind, fr in frames.items():
-        for batch in (1, 8):
+        for batch in (1,):
             imgs = np.concatenate([fr] * ((batch + 7) // 8))[:batch]
             trk = plp.LineFeatureTracker(ctx, H, W, max_batch=batch)
             out = {}
@@ -57,8 +61,8 @@ for warps in warps_list:
                 out[variant] = (timed(trk, imgs), kernel_ms(trk, imgs))
             st = trk.grow_stats(0)
             n = len(trk.extract_batch(imgs)[0][0])
-            print(f"warps={warps} {kind:8s} batch={batch:3d} keylines[0]={n:4d}  one-warp: {out[1][0]:7.2f} ms/call (grow {out[1][1].get('lsd_grow')})"
+            print(f"warps={warps} direct={os.environ['PLP_LSD_DIRECT']} {kind:8s} batch={batch:3d} keylines[0]={n:4d}  one-warp: {out[1][0]:7.2f} ms/call (grow {out[1][1].get('lsd_grow')})"
                   f"   multi-warp: {out[2][0]:7.2f} ms/call (grow {out[2][1].get('lsd_grow_mw')})  stats {st}")
-            if batch == 1 and warps == warps_list[0]:
+            if batch == 1 and cfg == cfgs[0]:
                 print("    kernels (multi-warp run):", out[2][1])
             trk.close()
