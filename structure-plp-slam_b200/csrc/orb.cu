@@ -216,6 +216,55 @@ __device__ __forceinline__ int fast_m(const uint8_t *p, int t) {
     return best;
 }
 
+// The same score for TWO pixels at once on packed 16-bit halves (DPX min / max, VIMNMX3.S16x2): every difference is biased
+// by +256 so that both halves stay in [1, 511] -- plain 32-bit subtraction then never borrows across the halves and no
+// negation is needed (e' = 512 - d').  Returns (m_a + 256) | (m_b + 256) << 16 with m = max over the sixteen 9-arcs of
+// min(arc differences), both polarities; the pixel is a corner at threshold t  <=>  m > t  (a 9-arc whose pixels all
+// differ by more than t has a minimum above t and vice versa), which is the arc test of fast_m.
+__device__ __forceinline__ uint32_t fast_m_pair(const uint8_t *pa, const uint8_t *pb) {
+    const uint32_t v2 = ((uint32_t)pa[0] + 256u) | (((uint32_t)pb[0] + 256u) << 16);
+    uint32_t d[16];
+#define PLP_RING(k, off) d[k] = v2 - ((uint32_t)pa[off] | ((uint32_t)pb[off] << 16))
+    PLP_RING(0, 3 * kTilePitch);
+    PLP_RING(1, 3 * kTilePitch + 1);
+    PLP_RING(2, 2 * kTilePitch + 2);
+    PLP_RING(3, 1 * kTilePitch + 3);
+    PLP_RING(4, 3);
+    PLP_RING(5, -1 * kTilePitch + 3);
+    PLP_RING(6, -2 * kTilePitch + 2);
+    PLP_RING(7, -3 * kTilePitch + 1);
+    PLP_RING(8, -3 * kTilePitch);
+    PLP_RING(9, -3 * kTilePitch - 1);
+    PLP_RING(10, -2 * kTilePitch - 2);
+    PLP_RING(11, -1 * kTilePitch - 3);
+    PLP_RING(12, -3);
+    PLP_RING(13, 1 * kTilePitch - 3);
+    PLP_RING(14, 2 * kTilePitch - 2);
+    PLP_RING(15, 3 * kTilePitch - 1);
+#undef PLP_RING
+    uint32_t e[16], d2[16], e2[16], d4[16], e4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = 0x02000200u - d[k];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        d2[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 1) & 15]);
+        e2[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 1) & 15]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        d4[k] = __vimin3_s16x2(d2[k], d2[(k + 2) & 15], d2[(k + 2) & 15]);
+        e4[k] = __vimin3_s16x2(e2[k], e2[(k + 2) & 15], e2[(k + 2) & 15]);
+    }
+    uint32_t best = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t d9 = __vimin3_s16x2(d4[k], d4[(k + 4) & 15], d[(k + 8) & 15]);
+        const uint32_t e9 = __vimin3_s16x2(e4[k], e4[(k + 4) & 15], e[(k + 8) & 15]);
+        best = __vimax3_s16x2(best, d9, e9);
+    }
+    return best;
+}
+
 __device__ __forceinline__ bool masked(const OrbDev &P, unsigned y, unsigned x, float scale) {
     // orb_extractor.cc:333-336 is_in_mask
     return P.mask[(size_t)(int)(y * scale) * P.mask_step + (int)(x * scale)] == 0;
@@ -370,10 +419,17 @@ __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
         __syncthreads();
         // phase B: exact arc test / score for the survivors
         const int nsurv = s_nsurv;
-        for (int i = tid; i < nsurv; i += 256) {
-            const int off = s_list[i];
-            const int m = fast_m(tile + off, thr);
-            if (m > thr) score[off] = (uint8_t)(m - 1);
+        {  // a thread scores two survivors at once (packed 16-bit halves)
+            const int half = (nsurv + 1) >> 1;
+            for (int i = tid; i < half; i += 256) {
+                const int off_a = s_list[i];
+                const bool has_b = i + half < nsurv;
+                const int off_b = has_b ? s_list[i + half] : off_a;
+                const uint32_t m2 = fast_m_pair(tile + off_a, tile + off_b);
+                const int m_a = (int)(m2 & 0xffffu) - 256, m_b = (int)(m2 >> 16) - 256;
+                if (m_a > thr) score[off_a] = (uint8_t)(m_a - 1);
+                if (has_b && m_b > thr) score[off_b] = (uint8_t)(m_b - 1);
+            }
         }
         __syncthreads();
         // 3x3 non-maximum suppression over the corners only
@@ -1006,7 +1062,7 @@ __global__ void __launch_bounds__(kQtThreads, 1) quadtree_kernel(OrbDev P) {
 // =====================================================================================================
 constexpr int kDescWarps = 4;
 constexpr int kSrcDim = 45, kSrcPitch = 48;   // 39 + 2*3
-constexpr int kBlurDim = 39, kBlurPitch = 40;
+constexpr int kBlurDim = 39, kBlurPitch = 44;  // window rows are staged as 11 aligned words
 
 __device__ __forceinline__ int reflect101(int p, int len) {
     if (p < 0) p = -p;
@@ -1286,17 +1342,24 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(OrbDev P, plp
     const float ang_rad = (float)((double)angle * 3.14159265358979323846 / 180.0);
     const float ca = util_cos(ang_rad), sa = util_sin(ang_rad);
     const int bpitch = s_bpitch[l];
-    const uint8_t *bsrc = s_blur[l] + (size_t)(cy - 19) * bpitch + (cx - 19);
-    // stage the 39 x 39 blurred window with coalesced row loads, then gather the 512 samples from shared memory
+    // stage the 39 x 39 blurred window as the 4-byte-aligned superset of every row (rows of the blurred pyramid start
+    // 64-byte aligned, so an aligned word never leaves its row): two rows per step, one word per lane, 20 load / store
+    // pairs per keypoint instead of 156 byte pairs; then gather the 512 samples from shared memory
+    const int wx0 = cx - 19, woff = wx0 & 3, nwords = (woff + kBlurDim + 3) >> 2;  // 10 or 11 words
+    const uint8_t *bsrc = s_blur[l] + (size_t)(cy - 19) * bpitch + (wx0 - woff);
     uint8_t *win = s_win[warp];
     __syncwarp();
-#pragma unroll 13
-    for (int r = 0; r < kBlurDim; ++r) {
-        win[r * kBlurPitch + lane] = __ldg(bsrc + r * bpitch + lane);
-        if (lane < kBlurDim - 32) win[r * kBlurPitch + 32 + lane] = __ldg(bsrc + r * bpitch + 32 + lane);
+    {
+        const int half = lane >> 4, j = lane & 15;
+        if (j < nwords) {
+#pragma unroll 5
+            for (int r = half; r < kBlurDim; r += 2)
+                *reinterpret_cast<uint32_t *>(win + r * kBlurPitch + 4 * j) =
+                    __ldg(reinterpret_cast<const uint32_t *>(bsrc + (size_t)r * bpitch) + j);
+        }
     }
     __syncwarp();
-    const uint8_t *center = win + 19 * kBlurPitch + 19;
+    const uint8_t *center = win + 19 * kBlurPitch + 19 + woff;
     int val = 0;
     // the lane's 8 test pairs: 8 consecutive int8 per table = one 64-bit load each (the tables live in global
     // memory: lane-dependent indices into __constant__ memory would serialise)
