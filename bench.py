@@ -550,6 +550,7 @@ def bench_ba(pkg, ctx, stream, rank, world, steps, warmup, which="config4"):
     e1.record(stream)
     ctx.sync()
     ar = (comm.allreduce_count() - ar0) if comm else 0
+    collective = ("NVLink peer-memory one-shot kernel" if comm.peer_active() else "ncclAllReduce") if comm else "none"
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=torch.cuda.current_device())
     if world > 1:
@@ -568,7 +569,7 @@ def bench_ba(pkg, ctx, stream, rank, world, steps, warmup, which="config4"):
     return {"metric": "local_ba_lm_iterations_per_sec", "value": done / (ms * 1e-3), "unit": "LM iterations/s",
             "scaling": "strong", "lm_tries_timed": done, "ms_per_lm_iteration": ms / max(done, 1),
             "full_solve_ms": solve_ms, "solve_iters": [out["iters_first"], out["iters_second"], out["lm_tries"]],
-            "allreduces_per_try": (ar / launches_per_try) if comm else 0.0, "ranks": world,
+            "allreduces_per_try": (ar / launches_per_try) if comm else 0.0, "ranks": world, "collective": collective,
             "config": {"workload": f"local_bundle_adjuster {kw['n_local']} local + {kw['n_fixed']} fixed KF, {kw['n_points']} points + "
                                    f"{kw['n_lines']} lines + {kw['n_plane_pts']} plane edges",
                        "edges": edges, "parallelism": f"landmark-sharded over {world} GPU(s), packed all-reduce of the reduced camera system"},
@@ -580,7 +581,8 @@ def ba_summary(r):
     """The part of a local-BA leg that rides in `config` of the headline line (the driver keeps `config` verbatim)."""
     return {"workload": r["config"]["workload"], "edges": r["config"]["edges"], "lm_iters_per_s": round(r["value"], 1),
             "ms_per_try": round(r["ms_per_lm_iteration"], 4), "ranks": r["ranks"],
-            "allreduces_per_try": round(r["allreduces_per_try"], 3), "full_solve_ms": round(r["full_solve_ms"], 3),
+            "allreduces_per_try": round(r["allreduces_per_try"], 3), "collective": r.get("collective", "none"),
+            "full_solve_ms": round(r["full_solve_ms"], 3),
             "hbm_roofline_frac": float(f"{r['hbm_roofline_frac']:.3g}"), "scaling": "strong"}
 
 

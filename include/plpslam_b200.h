@@ -766,6 +766,10 @@ PLP_API plp_status plp_ba_comm_init(plp_ctx *ctx, const uint8_t id[128], int wor
 PLP_API void plp_ba_comm_destroy(plp_ba_comm *comm);
 /* number of ncclAllReduce calls issued through the communicator so far (measurement: all-reduces per LM try) */
 PLP_API uint64_t plp_ba_comm_allreduce_count(const plp_ba_comm *comm);
+/* 1 if the communicator's small all-reduces run as the one-shot kernel over NVLink peer memory (ranks on one node, CUDA IPC
+ * available; PLP_BA_PEER=0 forces NCCL), and how many all-reduces took that path */
+PLP_API int plp_ba_comm_peer_active(const plp_ba_comm *comm);
+PLP_API uint64_t plp_ba_comm_peer_count(const plp_ba_comm *comm);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,14 @@ class BaComm:
         self._lib.plp_ba_comm_allreduce_count.restype = C.c_uint64
         return int(self._lib.plp_ba_comm_allreduce_count(self.handle))
 
+    def peer_active(self) -> bool:
+        """True if the small all-reduces run as the one-shot kernel over NVLink peer memory instead of ncclAllReduce."""
+        return bool(self._lib.plp_ba_comm_peer_active(self.handle))
+
+    def peer_count(self) -> int:
+        self._lib.plp_ba_comm_peer_count.restype = C.c_uint64
+        return int(self._lib.plp_ba_comm_peer_count(self.handle))
+
     def close(self):
         if self.handle is not None:
             self._lib.plp_ba_comm_destroy(self.handle)

@@ -52,15 +52,18 @@ struct Carver {
 plp_status launch_try(plp_ba *b) {
     plp_ctx *ctx = b->ctx;
     BaCollective *coll = b->comm ? ba_comm_collective(b->comm) : nullptr;
-    if (ctx->timing || coll) return ba_launch_try(ctx, b->dev, coll);  // events / NCCL: plain launches
+    // events / NCCL: plain launches; the NVLink peer all-reduce is an ordinary kernel whose call counter lives in device
+    // memory, so a try that uses it is captured like a single-GPU try
+    if (ctx->timing || (coll && !coll->graph_safe(b->dev.packed_sum_len + b->dev.world))) return ba_launch_try(ctx, b->dev, coll);
     if (!b->try_graph) {
         cudaGraph_t g = nullptr;
         const uint64_t l0 = ctx->launches;
         PLP_CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        const plp_status s = ba_launch_try(ctx, b->dev, nullptr);
+        const plp_status s = ba_launch_try(ctx, b->dev, coll);
         const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
         b->try_graph_launches = (int)(ctx->launches - l0);
         ctx->launches = l0;
+        if (coll) coll->add_calls((uint64_t)0 - 2);  // the two calls counted during capture are added per replay below
         if (s != PLP_OK) return s;
         if (e != cudaSuccess) {
             set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
@@ -71,12 +74,14 @@ plp_status launch_try(plp_ba *b) {
     }
     PLP_CUDA_TRY(cudaGraphLaunch(b->try_graph, ctx->stream));
     ctx->launches += b->try_graph_launches;
+    if (coll) coll->add_calls(2);  // packed system + trial sums
     return PLP_OK;
 }
 
 plp_status read_state(plp_ba *b) {
     PLP_CUDA_TRY(cudaMemcpyAsync(b->h_state, b->dev.state, sizeof(BaState), cudaMemcpyDeviceToHost, b->ctx->stream));
     PLP_CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+    if (b->comm) PLP_TRY(ba_comm_collective(b->comm)->check());  // a peer all-reduce that timed out is an error, not a result
     return PLP_OK;
 }
 

@@ -65,6 +65,9 @@ struct BaDev {
 // multi-GPU hook: sum-all-reduce of `n` doubles in place on the context stream (ba_nccl.cu)
 struct BaCollective {
     virtual plp_status all_reduce(double *d_buf, int n) = 0;
+    virtual bool graph_safe(int n_max) const { return false; }  // may all_reduce(<= n_max doubles) be captured in a CUDA graph?
+    virtual void add_calls(uint64_t n) {}                       // a captured graph with n all-reduces was replayed
+    virtual plp_status check() { return PLP_OK; }               // after a stream synchronisation
     virtual ~BaCollective() {}
 };
 

@@ -70,6 +70,9 @@ def main():
                   f"flag mismatches {mism} iters {gathered[0]['it']} vs oracle {(o.iters_first, o.iters_second, o.lm_tries)} "
                   f"-> {'OK' if good else 'FAIL'}")
             ok = ok and good
+    if rank == 0:
+        print(f"[ba multi-gpu world={world}] collective: {'NVLink peer-memory one-shot kernel' if comm.peer_active() else 'ncclAllReduce'}"
+              f" ({comm.peer_count()} of {comm.allreduce_count()} all-reduces on the peer path)")
     comm.close()
     dist.barrier()
     dist.destroy_process_group()

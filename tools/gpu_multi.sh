@@ -16,6 +16,8 @@ for W in $WORLDS; do
   echo "run_ba_multigpu world $W exit $?"; grep "ba multi-gpu" gpurun_out/ba_multigpu_w${W}_${TAG}.log
   timeout 400 $TR --nproc-per-node $W --master-port $((29530 + W)) bench.py --gpus $W --only-ba --steps 5 --warmup 3 > gpurun_out/bench_ba_n${W}_${TAG}.json 2> gpurun_out/bench_ba_n${W}_${TAG}.err
   echo "ba n$W exit $?"; tail -1 gpurun_out/bench_ba_n${W}_${TAG}.json | cut -c1-700
+  PLP_BA_PEER=0 timeout 400 $TR --nproc-per-node $W --master-port $((29550 + W)) bench.py --gpus $W --only-ba --steps 5 --warmup 3 > gpurun_out/bench_ba_nccl_n${W}_${TAG}.json 2> gpurun_out/bench_ba_nccl_n${W}_${TAG}.err
+  echo "ba (nccl) n$W exit $?"; tail -1 gpurun_out/bench_ba_nccl_n${W}_${TAG}.json | cut -c1-500
 done
 if [[ "$FULL" == "full" ]]; then
   timeout 900 $TR --nproc-per-node $LAST --master-port 29577 bench.py --gpus $LAST --steps 10 --warmup 3 --detail gpurun_out/bench_detail_n${LAST}_${TAG}.json > gpurun_out/bench_n${LAST}_${TAG}.json 2> gpurun_out/bench_n${LAST}_${TAG}.err
