@@ -319,6 +319,13 @@ def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_b
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
+    # one live frame through the host entry point (the region growing then runs its multi-warp, in-order-commit variant)
+    lat = []
+    for i in range(6):
+        t0 = time.perf_counter()
+        trk.extract_LSD_LBD(frames[i % batch])
+        lat.append(1e3 * (time.perf_counter() - t0))
+    batch1_ms = float(np.median(lat[1:]))
     # per-kernel shares
     ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 1))
     for _ in range(min(steps, 3)):
@@ -340,7 +347,7 @@ def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_b
            "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
                    "d2h_bytes_per_step": int(kl.nbytes + lbd.nbytes + fn.nbytes + nn.nbytes)},
            "gpu_launches": int(launches), "kernel_time_shares": shares, "ms_per_launch": per_launch,
-           "algorithmic_bytes_per_step": alg, "hbm_roofline_frac": alg / (ms / steps * 1e-3) / 1e9 / peak}
+           "latency_ms_one_frame": batch1_ms, "algorithmic_bytes_per_step": alg, "hbm_roofline_frac": alg / (ms / steps * 1e-3) / 1e9 / peak}
     if cpu_baseline and rank == 0:
         import oracle_api
         orc = oracle_api.Oracle()
@@ -1114,7 +1121,8 @@ def main():
         cfg_extra["line_frontend"] = {"frames_per_s": round(r["value"], 1), "e2e_frames_per_s": round(r["e2e"]["value"], 1),
                                       "mean_keylines_per_frame": round(r["config"]["mean_keylines_per_frame"], 1),
                                       "hbm_roofline_frac": float(f"{r['hbm_roofline_frac']:.3g}"),
-                                      "frames_per_step_per_gpu": args.line_batch}
+                                      "frames_per_step_per_gpu": args.line_batch,
+                                      "latency_ms_one_frame": round(r["latency_ms_one_frame"], 2)}
         if "cpu_baseline" in r:
             cfg_extra["line_frontend"]["cpu_port_frames_per_s"] = round(r["cpu_baseline"]["value"], 1)
     if not args.no_stereo:
