@@ -47,6 +47,7 @@ ALG_BYTES = {
     "fast_cells_kernel_v2": PYR_PX,
     "pyr_resize_kernel": None,    # per level, filled below
     "blur_tiles_kernel": 2 * PYR_PX,          # pyramid read + blurred pyramid written
+    "blur_tiles_tma_kernel": 2 * PYR_PX,
     "describe_kernel": PYR_PX + 60 * 1200,
     "quadtree_kernel": 8 * 11000 + 8 * 1200,
     # match (per frame) = (M + N) x 48 B: 32 B descriptor + 16 B geometry on each side, N ~ 1200 keypoints, M ~ 1000 queries
@@ -1058,7 +1059,7 @@ def main():
     dom_name = dom[0]
     per_launch_ms = dom[1]["total_ms"] / dom[1]["count"]
     launches_per_step = dom[1]["count"] / max(args.steps, 1)
-    alg = ALG_BYTES.get(dom_name)
+    alg = ALG_BYTES.get(dom_name.split("<")[0])
     if alg is None:
         alg = PYR_PX
     # algorithmic bytes of ONE step of this kernel (all of its launches in a step together process the sub-batch once:

@@ -209,7 +209,9 @@ plp_status plp_ba_create(plp_ctx *ctx, const plp_ba_problem *p, const plp_ba_cfg
     PLP_REQUIRE(max_deg <= n_free, "a landmark is observed twice by the same keyframe");
     const int pool_cap = ba_pool_capacity(n_free, n_free * (n_free + 1) / 2, max_deg);
     const int LB = std::max(1, std::min(16, pool_cap / max_deg));
-    int G = cfg->num_ctas > 0 ? cfg->num_ctas : std::max(1, std::min(ctx->sm_count, (n_lm + 2 * LB - 1) / (2 * LB)));
+    // one batch of LB landmarks per CTA until every SM has one (a rank of an 8-GPU run owns 1/8 of the landmarks: its
+    // linearisation then takes one batch time instead of two)
+    int G = cfg->num_ctas > 0 ? cfg->num_ctas : std::max(1, std::min(ctx->sm_count, (n_lm + LB - 1) / LB));
     G = std::max(1, std::min(G, std::max(1, n_lm)));
     std::vector<int> ranges(G + 1, n_lm);
     ranges[0] = 0;

@@ -51,9 +51,10 @@ __global__ void __launch_bounds__(kPeerThreads) ba_peer_allreduce_kernel(PeerArg
     const int i0 = min(n, c * per), i1 = min(n, i0 + per);
     double *mine = A.mail[A.rank] + (size_t)parity * kPeerCap;
     for (int i = i0 + tid; i < i1; i += kPeerThreads) mine[i] = buf[i];
-    __threadfence_system();
     __syncthreads();
     if (tid < A.world) {
+        // the barrier made the CTA's stores visible to this thread; its system-scope fence orders them before the signal
+        __threadfence_system();
         // signal: "rank A.rank has published chunk c of call seq" on every rank (own included)
         *reinterpret_cast<volatile unsigned long long *>(A.flags[tid] + c * kPeerMaxWorld + A.rank) = seq;
         // wait for every rank's signal in the local flag words
@@ -65,9 +66,9 @@ __global__ void __launch_bounds__(kPeerThreads) ba_peer_allreduce_kernel(PeerArg
                 break;
             }
         }
+        __threadfence_system();
     }
     __syncthreads();
-    __threadfence_system();
     for (int i = i0 + tid; i < i1; i += kPeerThreads) {
         double s = 0.0;
         for (int r = 0; r < A.world; ++r) s += __ldcv(A.mail[r] + (size_t)parity * kPeerCap + i);  // fixed order on every rank

@@ -112,14 +112,17 @@ plp_status plp_ctx_create_ex(int device, int high_priority, plp_ctx **out) {
         return PLP_ERR_NO_DEVICE;
     }
     PLP_CUDA_TRY(cudaSetDevice(device));
-    plp_ctx *c = new plp_ctx();
-    c->device = device;
+    // everything that can fail comes before the allocation: no error path leaks the handle
     cudaDeviceProp prop;
     PLP_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
     int prio_lo = 0, prio_hi = 0;
     PLP_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // numerically lower = higher priority
-    PLP_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, high_priority ? prio_hi : prio_lo));
+    cudaStream_t stream = nullptr;
+    PLP_CUDA_TRY(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, high_priority ? prio_hi : prio_lo));
+    plp_ctx *c = new plp_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->stream = stream;
     *out = c;
     return PLP_OK;
 }

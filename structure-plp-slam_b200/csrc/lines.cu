@@ -53,6 +53,7 @@ struct LineDev {
     uint32_t *order;     // npx packed (y<<16|x) seeds, bin desc / raster asc
     int *nseeds;
     uint32_t *reg_xy;    // npx: region entries beyond the shared-memory window
+    int reg_cap_small;   // region window (entries) of lsd_grow_kernel<false>
     int direct_trig;     // bit 0: lsd_grow_mw_kernel, bit 1: lsd_grow_kernel compute the neighbour's {deg, cos, sin} directly
     unsigned long long *mw_stat;  // per frame {rounds, seeds run, seeds redone} of lsd_grow_mw_kernel (may be null)
     float4 *segs;        // seg_cap
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
     G.kthr = D.kthr;
     G.density_th = D.density_th;
     G.img = kImgSmem ? s_img : D.scaled + (size_t)b * D.npx;
-    G.reg_cap = kImgSmem ? kRegCap : kRegCapSmall;
+    G.reg_cap = kImgSmem ? kRegCap : D.reg_cap_small;
     G.used = s_used;
     G.mark = s_used;
     G.reg = s_reg;
@@ -1354,7 +1355,10 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
     ctx->launches++;
     h->sort_smem = ((size_t)kSortWarps * kBins + kBins) * sizeof(uint32_t);
     const size_t used_bytes = (size_t)((((D.npx + 31) >> 5) + 3) & ~3) * 4;
-    h->grow_smem_noimg = used_bytes + (size_t)kRegCapSmall * 4;
+    D.reg_cap_small = kRegCapSmall;
+    if (const char *ev = getenv("PLP_LSD_REGCAP")) D.reg_cap_small = std::max(64, std::min(kRegCap, atoi(ev)));  // tuning aid
+    h->dev.reg_cap_small = D.reg_cap_small;
+    h->grow_smem_noimg = used_bytes + (size_t)D.reg_cap_small * 4;
     h->grow_smem = (size_t)((D.npx + 15) & ~15) + used_bytes + (size_t)kRegCap * 4;
     h->img_smem_ok = h->grow_smem <= 227 * 1024;
     if (h->grow_smem_noimg > 227 * 1024) {

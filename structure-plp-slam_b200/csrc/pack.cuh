@@ -24,7 +24,8 @@ struct Packer {
         total += (bytes + 255) & ~(size_t)255;
         return off;
     }
-    // reserve zero-initialised / output space (not copied from host)
+    // reserve output / scratch space (not copied from the host and NOT cleared: it holds whatever the scratch slot held;
+    // every kernel writes its outputs before anything reads them)
     size_t reserve(size_t bytes) {
         size_t off = total;
         total += (bytes + 255) & ~(size_t)255;
