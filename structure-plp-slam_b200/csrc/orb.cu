@@ -99,33 +99,46 @@ __device__ __forceinline__ int level_pitch(const OrbDev &P, int l) { return l ==
 // 1. pyramid: cv::resize(INTER_LINEAR) fixed-point model
 // =====================================================================================================
 // tables: per destination column {sx0, sx1, a0, a1}, per destination row {sy0, sy1, b0, b1}
-__global__ void pyr_resize_kernel(OrbDev P, int l, const short4 *__restrict__ xtab, const short4 *__restrict__ ytab) {
+// A thread owns four destination columns of kResizeRows consecutive rows: the column taps and weights are row-independent,
+// so they are unpacked once per strip (round 1 redid the table loads, the unpacking and the 64-bit address arithmetic for
+// every row: 58 instructions per pixel).
+constexpr int kResizeRows = 8;
+__global__ void __launch_bounds__(256) pyr_resize_kernel(OrbDev P, int l, const short4 *__restrict__ xtab,
+                                                         const short4 *__restrict__ ytab) {
     const int b = blockIdx.y;
     const int dw = P.lv[l].w, dh = P.lv[l].h, dpitch = P.lv[l].pitch;
-    const int quads = (dw + 3) >> 2;
+    const int quads = (dw + 3) >> 2, strips = (dh + kResizeRows - 1) / kResizeRows;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= quads * dh) return;
-    const int y = q / quads, x0 = (q - y * quads) * 4;
+    if (q >= quads * strips) return;
+    const int strip = q / quads, x0 = (q - strip * quads) * 4;
     const uint8_t *src = level_ptr(P, b, l - 1);
     const int spitch = level_pitch(P, l - 1);
     uint8_t *dst = const_cast<uint8_t *>(level_ptr(P, b, l));
-    const short4 yt = ytab[y];
-    const uint8_t *S0 = src + (size_t)yt.x * spitch, *S1 = src + (size_t)yt.y * spitch;
-    const int b0 = yt.z, b1 = yt.w;
-    uint32_t packed = 0;
+    int sx0[4], sx1[4], a0[4], a1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int x = x0 + k;
-        if (x < dw) {
-            const short4 xt = xtab[x];
-            const int r0 = S0[xt.x] * xt.z + S0[xt.y] * xt.w;
-            const int r1 = S1[xt.x] * xt.z + S1[xt.y] * xt.w;
+        const short4 xt = xtab[min(x0 + k, dw - 1)];  // columns past dw are row padding: any value may be stored there
+        sx0[k] = xt.x;
+        sx1[k] = xt.y;
+        a0[k] = xt.z;
+        a1[k] = xt.w;
+    }
+    const int y_end = min(dh, (strip + 1) * kResizeRows);
+    for (int y = strip * kResizeRows; y < y_end; ++y) {
+        const short4 yt = ytab[y];
+        const uint8_t *S0 = src + (size_t)yt.x * spitch, *S1 = src + (size_t)yt.y * spitch;
+        const int b0 = yt.z, b1 = yt.w;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r0 = S0[sx0[k]] * a0[k] + S0[sx1[k]] * a1[k];
+            const int r1 = S1[sx0[k]] * a0[k] + S1[sx1[k]] * a1[k];
             const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
             packed |= (uint32_t)(v & 0xff) << (8 * k);
         }
+        // pitch is a multiple of 64 so the 4-byte store is aligned; pad bytes past dw are never read
+        *reinterpret_cast<uint32_t *>(dst + (size_t)y * dpitch + x0) = packed;
     }
-    // pitch is a multiple of 64 so the 4-byte store is aligned; pad bytes past dw are never read
-    *reinterpret_cast<uint32_t *>(dst + (size_t)y * dpitch + x0) = packed;
 }
 
 // =====================================================================================================
@@ -1783,7 +1796,7 @@ static plp_status orb_run(plp_orb *o, const uint8_t *d_imgs, int batch, size_t s
     o->last_step = step;
     PLP_CUDA_TRY(cudaMemsetAsync(D.status, 0, (size_t)batch * sizeof(int), ctx->stream));
     for (int l = 1; l < D.num_levels; ++l) {
-        const int quads = ((D.lv[l].w + 3) >> 2) * D.lv[l].h;
+        const int quads = ((D.lv[l].w + 3) >> 2) * ((D.lv[l].h + kResizeRows - 1) / kResizeRows);  // threads: 4 columns x 8 rows each
         if (quads <= 0) continue;
         dim3 grid(div_up(quads, 256), batch);
         PLP_LAUNCH(ctx, pyr_resize_kernel, grid, 256, 0, D, l, o->d_xtab[l], o->d_ytab[l]);
