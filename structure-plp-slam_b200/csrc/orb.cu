@@ -99,9 +99,12 @@ __device__ __forceinline__ int level_pitch(const OrbDev &P, int l) { return l ==
 // 1. pyramid: cv::resize(INTER_LINEAR) fixed-point model
 // =====================================================================================================
 // tables: per destination column {sx0, sx1, a0, a1}, per destination row {sy0, sy1, b0, b1}
-// A thread owns four destination columns of kResizeRows consecutive rows: the column taps and weights are row-independent,
-// so they are unpacked once per strip (round 1 redid the table loads, the unpacking and the 64-bit address arithmetic for
-// every row: 58 instructions per pixel).
+// A thread owns four destination columns of kResizeRows consecutive rows.  The column taps and weights are row-independent,
+// so they are unpacked once per strip, and because one destination quad reads at most 4 x 1.2 + 2 < 8 consecutive source
+// bytes of a row, a source row is fetched as THREE ALIGNED WORDS and the eight taps are picked out of them with byte
+// permutes whose selectors are also computed once per strip (round 1: 16 byte loads per row of a quad; the kernel is bound by
+// the load/store unit, not by arithmetic).  Falls back to byte loads when the source is not 4-byte aligned or the taps of a
+// quad span more than 12 bytes (scale factors above ~2).
 constexpr int kResizeRows = 8;
 __global__ void __launch_bounds__(256) pyr_resize_kernel(OrbDev P, int l, const short4 *__restrict__ xtab,
                                                          const short4 *__restrict__ ytab) {
@@ -113,8 +116,10 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(OrbDev P, int l, const 
     const int strip = q / quads, x0 = (q - strip * quads) * 4;
     const uint8_t *src = level_ptr(P, b, l - 1);
     const int spitch = level_pitch(P, l - 1);
+    const int sw = l == 1 ? P.cols : P.lv[l - 1].w;
     uint8_t *dst = const_cast<uint8_t *>(level_ptr(P, b, l));
     int sx0[4], sx1[4], a0[4], a1[4];
+    int lo = 1 << 30, hi = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const short4 xt = xtab[min(x0 + k, dw - 1)];  // columns past dw are row padding: any value may be stored there
@@ -122,19 +127,57 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(OrbDev P, int l, const 
         sx1[k] = xt.y;
         a0[k] = xt.z;
         a1[k] = xt.w;
+        lo = min(lo, min(sx0[k], sx1[k]));
+        hi = max(hi, max(sx0[k], sx1[k]));
+    }
+    const int base = lo & ~3;  // aligned start of the source span of this quad
+    // word path: source rows 4-byte aligned, all taps inside [base, base + 12), and the three words inside the row pitch
+    const bool words = (((uintptr_t)src | (uintptr_t)spitch) & 3) == 0 && hi - base < 12 && base + 12 <= ((sw + 3) & ~3) &&
+                       base + 12 <= spitch;
+    // tap p = sx - base in 0 .. 11: window (w0, w1) for p < 4 .. 7 handled by selector p, window (w1, w2) with selector p - 4
+    uint32_t sel0 = 0, sel1 = 0, win = 0;  // 4 x 4-bit selectors per tap set, bit k of win: tap k uses the upper window
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int p0 = sx0[k] - base, p1 = sx1[k] - base;
+        const int u0 = p0 >= 8, u1 = p1 >= 8;
+        sel0 |= (uint32_t)(p0 - 4 * u0) << (4 * k);
+        sel1 |= (uint32_t)(p1 - 4 * u1) << (4 * k);
+        win |= (uint32_t)u0 << k | (uint32_t)u1 << (4 + k);
     }
     const int y_end = min(dh, (strip + 1) * kResizeRows);
+#pragma unroll 2
     for (int y = strip * kResizeRows; y < y_end; ++y) {
         const short4 yt = ytab[y];
         const uint8_t *S0 = src + (size_t)yt.x * spitch, *S1 = src + (size_t)yt.y * spitch;
         const int b0 = yt.z, b1 = yt.w;
         uint32_t packed = 0;
+        if (words) {
+            const uint32_t *W0 = reinterpret_cast<const uint32_t *>(S0 + base), *W1 = reinterpret_cast<const uint32_t *>(S1 + base);
+            const uint32_t p0 = W0[0], p1 = W0[1], p2 = W0[2], q0 = W1[0], q1 = W1[1], q2 = W1[2];
+            // taps of the first window come from bytes 0 .. 7 of (w0, w1), of the second from bytes 4 .. 11 = (w1, w2)
+            const uint32_t t0a = __byte_perm(p0, p1, sel0), t0b = __byte_perm(p1, p2, sel0);
+            const uint32_t t1a = __byte_perm(p0, p1, sel1), t1b = __byte_perm(p1, p2, sel1);
+            const uint32_t u0a = __byte_perm(q0, q1, sel0), u0b = __byte_perm(q1, q2, sel0);
+            const uint32_t u1a = __byte_perm(q0, q1, sel1), u1b = __byte_perm(q1, q2, sel1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int r0 = S0[sx0[k]] * a0[k] + S0[sx1[k]] * a1[k];
-            const int r1 = S1[sx0[k]] * a0[k] + S1[sx1[k]] * a1[k];
-            const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-            packed |= (uint32_t)(v & 0xff) << (8 * k);
+            for (int k = 0; k < 4; ++k) {
+                const int s00 = (int)((((win >> k) & 1u) ? t0b : t0a) >> (8 * k)) & 0xff;
+                const int s01 = (int)((((win >> (4 + k)) & 1u) ? t1b : t1a) >> (8 * k)) & 0xff;
+                const int s10 = (int)((((win >> k) & 1u) ? u0b : u0a) >> (8 * k)) & 0xff;
+                const int s11 = (int)((((win >> (4 + k)) & 1u) ? u1b : u1a) >> (8 * k)) & 0xff;
+                const int r0 = s00 * a0[k] + s01 * a1[k];
+                const int r1 = s10 * a0[k] + s11 * a1[k];
+                const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+                packed |= (uint32_t)(v & 0xff) << (8 * k);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r0 = S0[sx0[k]] * a0[k] + S0[sx1[k]] * a1[k];
+                const int r1 = S1[sx0[k]] * a0[k] + S1[sx1[k]] * a1[k];
+                const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+                packed |= (uint32_t)(v & 0xff) << (8 * k);
+            }
         }
         // pitch is a multiple of 64 so the 4-byte store is aligned; pad bytes past dw are never read
         *reinterpret_cast<uint32_t *>(dst + (size_t)y * dpitch + x0) = packed;
