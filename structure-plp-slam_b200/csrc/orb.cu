@@ -99,12 +99,9 @@ __device__ __forceinline__ int level_pitch(const OrbDev &P, int l) { return l ==
 // 1. pyramid: cv::resize(INTER_LINEAR) fixed-point model
 // =====================================================================================================
 // tables: per destination column {sx0, sx1, a0, a1}, per destination row {sy0, sy1, b0, b1}
-// A thread owns four destination columns of kResizeRows consecutive rows.  The column taps and weights are row-independent,
-// so they are unpacked once per strip, and because one destination quad reads at most 4 x 1.2 + 2 < 8 consecutive source
-// bytes of a row, a source row is fetched as THREE ALIGNED WORDS and the eight taps are picked out of them with byte
-// permutes whose selectors are also computed once per strip (round 1: 16 byte loads per row of a quad; the kernel is bound by
-// the load/store unit, not by arithmetic).  Falls back to byte loads when the source is not 4-byte aligned or the taps of a
-// quad span more than 12 bytes (scale factors above ~2).
+// A thread owns four destination columns of kResizeRows consecutive rows: the column taps and weights are row-independent,
+// so they are unpacked once per strip (round 1 redid the table loads, the unpacking and the 64-bit address arithmetic for
+// every row: 58 instructions per pixel).
 constexpr int kResizeRows = 8;
 __global__ void __launch_bounds__(256) pyr_resize_kernel(OrbDev P, int l, const short4 *__restrict__ xtab,
                                                          const short4 *__restrict__ ytab) {
@@ -116,10 +113,8 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(OrbDev P, int l, const 
     const int strip = q / quads, x0 = (q - strip * quads) * 4;
     const uint8_t *src = level_ptr(P, b, l - 1);
     const int spitch = level_pitch(P, l - 1);
-    const int sw = l == 1 ? P.cols : P.lv[l - 1].w;
     uint8_t *dst = const_cast<uint8_t *>(level_ptr(P, b, l));
     int sx0[4], sx1[4], a0[4], a1[4];
-    int lo = 1 << 30, hi = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const short4 xt = xtab[min(x0 + k, dw - 1)];  // columns past dw are row padding: any value may be stored there
@@ -127,57 +122,19 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(OrbDev P, int l, const 
         sx1[k] = xt.y;
         a0[k] = xt.z;
         a1[k] = xt.w;
-        lo = min(lo, min(sx0[k], sx1[k]));
-        hi = max(hi, max(sx0[k], sx1[k]));
-    }
-    const int base = lo & ~3;  // aligned start of the source span of this quad
-    // word path: source rows 4-byte aligned, all taps inside [base, base + 12), and the three words inside the row pitch
-    const bool words = (((uintptr_t)src | (uintptr_t)spitch) & 3) == 0 && hi - base < 12 && base + 12 <= ((sw + 3) & ~3) &&
-                       base + 12 <= spitch;
-    // tap p = sx - base in 0 .. 11: window (w0, w1) for p < 4 .. 7 handled by selector p, window (w1, w2) with selector p - 4
-    uint32_t sel0 = 0, sel1 = 0, win = 0;  // 4 x 4-bit selectors per tap set, bit k of win: tap k uses the upper window
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int p0 = sx0[k] - base, p1 = sx1[k] - base;
-        const int u0 = p0 >= 8, u1 = p1 >= 8;
-        sel0 |= (uint32_t)(p0 - 4 * u0) << (4 * k);
-        sel1 |= (uint32_t)(p1 - 4 * u1) << (4 * k);
-        win |= (uint32_t)u0 << k | (uint32_t)u1 << (4 + k);
     }
     const int y_end = min(dh, (strip + 1) * kResizeRows);
-#pragma unroll 2
     for (int y = strip * kResizeRows; y < y_end; ++y) {
         const short4 yt = ytab[y];
         const uint8_t *S0 = src + (size_t)yt.x * spitch, *S1 = src + (size_t)yt.y * spitch;
         const int b0 = yt.z, b1 = yt.w;
         uint32_t packed = 0;
-        if (words) {
-            const uint32_t *W0 = reinterpret_cast<const uint32_t *>(S0 + base), *W1 = reinterpret_cast<const uint32_t *>(S1 + base);
-            const uint32_t p0 = W0[0], p1 = W0[1], p2 = W0[2], q0 = W1[0], q1 = W1[1], q2 = W1[2];
-            // taps of the first window come from bytes 0 .. 7 of (w0, w1), of the second from bytes 4 .. 11 = (w1, w2)
-            const uint32_t t0a = __byte_perm(p0, p1, sel0), t0b = __byte_perm(p1, p2, sel0);
-            const uint32_t t1a = __byte_perm(p0, p1, sel1), t1b = __byte_perm(p1, p2, sel1);
-            const uint32_t u0a = __byte_perm(q0, q1, sel0), u0b = __byte_perm(q1, q2, sel0);
-            const uint32_t u1a = __byte_perm(q0, q1, sel1), u1b = __byte_perm(q1, q2, sel1);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int s00 = (int)((((win >> k) & 1u) ? t0b : t0a) >> (8 * k)) & 0xff;
-                const int s01 = (int)((((win >> (4 + k)) & 1u) ? t1b : t1a) >> (8 * k)) & 0xff;
-                const int s10 = (int)((((win >> k) & 1u) ? u0b : u0a) >> (8 * k)) & 0xff;
-                const int s11 = (int)((((win >> (4 + k)) & 1u) ? u1b : u1a) >> (8 * k)) & 0xff;
-                const int r0 = s00 * a0[k] + s01 * a1[k];
-                const int r1 = s10 * a0[k] + s11 * a1[k];
-                const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-                packed |= (uint32_t)(v & 0xff) << (8 * k);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int r0 = S0[sx0[k]] * a0[k] + S0[sx1[k]] * a1[k];
-                const int r1 = S1[sx0[k]] * a0[k] + S1[sx1[k]] * a1[k];
-                const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-                packed |= (uint32_t)(v & 0xff) << (8 * k);
-            }
+        for (int k = 0; k < 4; ++k) {
+            const int r0 = S0[sx0[k]] * a0[k] + S0[sx1[k]] * a1[k];
+            const int r1 = S1[sx0[k]] * a0[k] + S1[sx1[k]] * a1[k];
+            const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            packed |= (uint32_t)(v & 0xff) << (8 * k);
         }
         // pitch is a multiple of 64 so the 4-byte store is aligned; pad bytes past dw are never read
         *reinterpret_cast<uint32_t *>(dst + (size_t)y * dpitch + x0) = packed;
@@ -571,8 +528,8 @@ __global__ void __launch_bounds__(256, 4) fast_cells_kernel_v2(OrbDev P) {
 // 3. quadtree keypoint distribution (orb_extractor.cc:468-685), array formulation
 // =====================================================================================================
 constexpr int kQtThreads = 512;
-constexpr int kNodeCap = 2048;      // >= 4 * budget + 8
-constexpr int kQtSmemCands = 8192;  // candidates per level handled entirely in shared memory
+constexpr int kNodeCap = 2048;      // >= 4 * budget + 8 (large instance)
+constexpr int kNodeCapSmall = 1024, kCandCapSmall = 3840, kCandCapLarge = 8192;  // shared-memory windows of the two instances
 
 struct QtArrays {
     uint32_t *cand;             // packed candidates in gather order
@@ -744,17 +701,19 @@ __device__ void segmented_class_scan(const QtArrays &A, int cur, int n, const Qt
     __syncthreads();
 }
 
-struct QtShared {
-    short4 rect[2][kNodeCap];
-    unsigned short start[2][kNodeCap];
-    unsigned short cnt[2][kNodeCap];
-    uint8_t leaf[2][kNodeCap];
-    uint8_t sel[kNodeCap];
-    unsigned short tot[kNodeCap * 4];
-    int newpos[kNodeCap];      // list position of the first (front-most) child / of the kept node
-    int scan[kNodeCap];        // scratch for scans over the list
-    unsigned short pool[2][kNodeCap];
-    unsigned short pool_sorted[kNodeCap];
+// NC = node capacity (>= 4 * budget + 8 of every level the kernel instance serves)
+template <int NC>
+struct QtSharedT {
+    short4 rect[2][NC];
+    unsigned short start[2][NC];
+    unsigned short cnt[2][NC];
+    uint8_t leaf[2][NC];
+    uint8_t sel[NC];
+    unsigned short tot[NC * 4];
+    int newpos[NC];      // list position of the first (front-most) child / of the kept node
+    int scan[NC];        // scratch for scans over the list
+    unsigned short pool[2][NC];
+    unsigned short pool_sorted[NC];
     unsigned long long carry_tail[kQtThreads];
     uint8_t carry_head[kQtThreads];
     int warp_tmp[17];
@@ -766,7 +725,8 @@ struct QtShared {
 // order), partitions the keypoints, builds the new pool (children with more than one keypoint, creation
 // order).  `order`: processing rank of each selected node (for phase 1 it is the list order).  Returns the
 // new list length.  proc_rank[p] (in S.scan) must hold the processing rank for selected nodes.
-__device__ int apply_division(QtShared &S, QtArrays &A, int &cur, int n_cand, int &cur_n, int len, int num_proc,
+template <int NC>
+__device__ int apply_division(QtSharedT<NC> &S, QtArrays &A, int &cur, int n_cand, int &cur_n, int len, int num_proc,
                               const unsigned short *proc_list /* selected nodes in processing order */,
                               unsigned short *rank, uint8_t *cls, int *pool_len_out, int pool_dst) {
     const int tid = threadIdx.x;
@@ -876,8 +836,15 @@ __device__ int apply_division(QtShared &S, QtArrays &A, int &cur, int n_cand, in
     return new_len;
 }
 
-__global__ void __launch_bounds__(kQtThreads, 1) quadtree_kernel(OrbDev P) {
+// Two instances: <2048 nodes, 8192 candidates in shared memory, 1 CTA per SM> serves any configuration; <1024, 3840, 2 CTAs
+// per SM> is chosen when every level's node need fits 1024 (max_num_keypts up to ~1150 at scale 1.2): the kernel is a
+// chain of block scans and barriers (14 % SM-busy with one CTA of 16 warps per SM), so a second resident CTA nearly doubles
+// its throughput.  A level with more candidates than the shared-memory window works in its global scratch block.
+template <int NC, int CC, int kMinBlocks>
+__global__ void __launch_bounds__(kQtThreads, kMinBlocks) quadtree_kernel(OrbDev P) {
     extern __shared__ __align__(16) uint8_t qsmem[];
+    using QtShared = QtSharedT<NC>;
+    constexpr int kQtSmemCands = CC;
     QtShared &S = *reinterpret_cast<QtShared *>(qsmem);
     const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const LevelInfo &LV = P.lv[l];
@@ -1484,6 +1451,7 @@ struct plp_orb {
     uint8_t *d_desc = nullptr;
     int32_t *d_n = nullptr;
     size_t qt_smem = 0;
+    bool qt_small = false;  // the <1024 nodes, 2 CTAs per SM> instance of quadtree_kernel serves this configuration
     // TMA descriptors of the pyramid levels as (x, y, frame) uint8 tensors; levels >= 1 live in d_pyr (encoded once),
     // level 0 is the caller's buffer (re-encoded when its address / pitch / batch changes)
     BlurMaps maps;
@@ -1658,6 +1626,7 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
         }
     }
     // ---- level geometry, cells (orb_extractor.cc:344-392)
+    int qt_max_slots = 0;
     size_t pyr_bytes = 0, blur_bytes = 0;
     int slot_base = 0, cell_base = 0;
     plp_status st = PLP_OK;
@@ -1696,6 +1665,7 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
         slot_base += V.slot_cap;
         V.cell_base = cell_base;
         V.num_cells = 0;
+        qt_max_slots = std::max(qt_max_slots, V.slot_cap);
         if (V.slot_cap > kNodeCap) {
             set_error("orb: level %u budget %d exceeds the quadtree node capacity", l, V.budget);
             st = PLP_ERR_CAPACITY;
@@ -1800,8 +1770,15 @@ plp_status plp_orb_create(plp_ctx *ctx, const plp_orb_params *params, int rows, 
     for (unsigned l = 1; l < L && o->maps_ok; ++l)
         o->maps_ok = encode_level_map(&o->maps.m[l], o->d_pyr + D.lv[l].offset, D.lv[l].w, D.lv[l].h, max_batch, D.lv[l].pitch,
                                       D.pyr_frame_bytes);
-    o->qt_smem = ((sizeof(QtShared) + 15) & ~(size_t)15) + (size_t)kQtSmemCands * (4 + 2 * 5 + 1) + 64;
-    const plp_status so = ensure_smem_optin((const void *)quadtree_kernel, o->qt_smem, "quadtree_kernel");
+    o->qt_small = qt_max_slots <= kNodeCapSmall && !getenv("PLP_QT_LARGE");
+    plp_status so;
+    if (o->qt_small) {
+        o->qt_smem = ((sizeof(QtSharedT<kNodeCapSmall>) + 15) & ~(size_t)15) + (size_t)kCandCapSmall * (4 + 2 * 5 + 1) + 64;
+        so = ensure_smem_optin((const void *)quadtree_kernel<kNodeCapSmall, kCandCapSmall, 2>, o->qt_smem, "quadtree_kernel<small>");
+    } else {
+        o->qt_smem = ((sizeof(QtSharedT<kNodeCap>) + 15) & ~(size_t)15) + (size_t)kCandCapLarge * (4 + 2 * 5 + 1) + 64;
+        so = ensure_smem_optin((const void *)quadtree_kernel<kNodeCap, kCandCapLarge, 1>, o->qt_smem, "quadtree_kernel<large>");
+    }
     if (so != PLP_OK) {
         plp_orb_destroy(o);
         return so;
@@ -1871,7 +1848,13 @@ static plp_status orb_run(plp_orb *o, const uint8_t *d_imgs, int batch, size_t s
     }
     {
         dim3 grid(D.num_levels, batch);
-        PLP_LAUNCH(ctx, quadtree_kernel, grid, kQtThreads, o->qt_smem, D);
+        if (ctx->timing) plp::timing_begin(ctx, "quadtree_kernel");  // (PLP_LAUNCH spelled out: one name for both instances)
+        if (o->qt_small)
+            quadtree_kernel<kNodeCapSmall, kCandCapSmall, 2><<<grid, kQtThreads, o->qt_smem, ctx->stream>>>(D);
+        else
+            quadtree_kernel<kNodeCap, kCandCapLarge, 1><<<grid, kQtThreads, o->qt_smem, ctx->stream>>>(D);
+        if (ctx->timing) plp::timing_end(ctx);
+        ctx->launches++;
     }
     {
         const int kp_est = std::max(256, (int)(3 * o->params.max_num_keypts / 2));  // warps stride the rest
