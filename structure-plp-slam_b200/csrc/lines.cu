@@ -931,6 +931,403 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K4'': region growing for one live frame, OUT OF ORDER with in-order commit (a reorder buffer, as in a CPU core).
+//
+// The round protocol above loses half of its cycles waiting for the slowest seed of a round: 72 % of the seeds grow fewer
+// than 5 pixels, 10 % grow a few hundred, and a round costs its slowest member.  Here a warp that has finished a small
+// region PARKS it (its <= kOooPark pixels and its bounding box go into the ticket's reorder-buffer entry, the private marks
+// are cleared) and takes the next seed at once, so the warps that draw small seeds run ahead -- up to kOooWindow tickets --
+// while the long regions of several lines are grown concurrently by the other warps (a region too large to park is HELD by
+// its warp until it commits).  Tickets = seeds in gradient order.  A ticket runs against the committed `used` map plus its
+// own private marks only; it records `start_head` = the commit pointer when it started.  Commit is strictly in ticket
+// order, by whichever warp finds the head entry finished: the entry is valid if the bounding box of everything it accepted
+// is disjoint from the final boxes of the tickets in [start_head, ticket) -- the tickets before start_head were committed,
+// hence fully visible, when it started; the others can only matter through pixels it accepted (see K4').  An invalid entry,
+// and an entry that was DEFERRED because its seed lay inside a region another warp was growing (most likely about to be
+// absorbed), is simply executed AT THE HEAD, where the committed map is exactly the sequential state -- so every decision that
+// is not provably the sequential one is redone sequentially, and the segments come out in ticket order, bit for bit.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kOooRing = 256;    // reorder-buffer entries (ticket % kOooRing)
+constexpr int kOooWindow = 128;  // tickets in flight (<= kOooRing / 2: an entry is not reused while a later ticket may still test it)
+constexpr int kOooPark = 24;     // pixels of a region that can be parked in its entry
+constexpr int kOooRegCap = 512;  // region window per warp in shared memory (longer regions continue in global memory)
+
+enum { kOooRunning = 1, kOooVoid = 2, kOooDeferred = 3, kOooParked = 4, kOooHeld = 5, kOooCommitted = 6 };
+
+struct OooEntry {
+    float4 seg;
+    uint32_t xy;
+    int state, start_head, owner, n, ok;
+    short bx0, by0, bx1, by1;
+    uint32_t px[kOooPark];
+};
+
+struct OooCtl {
+    int lock_dispatch, lock_commit;
+    int head, next_ticket;
+    int scan_pos, chunk_base;
+    unsigned chunk_mask;
+    int nseg;
+    uint32_t chunk_xy[32];
+    unsigned long long stat[8];  // tickets, void, deferred, parked, held, executed at the head, conflicts
+};
+
+// (every wait of this kernel is bounded: after ~2 s of SM cycles a warp gives up, raises status bit 2 and leaves -- a protocol
+// bug must not hang the device)
+constexpr long long kOooTimeout = 4000000000ll;
+__device__ __forceinline__ bool ooo_lock(int *l, int lane, long long t_start) {
+    int ok = 1;
+    if (lane == 0) {
+        while (atomicCAS(l, 0, 1) != 0) {
+            __nanosleep(40);
+            if (clock64() - t_start > kOooTimeout) {
+                ok = 0;
+                break;
+            }
+        }
+        __threadfence_block();
+    }
+    return __shfl_sync(kFull, ok, 0) != 0;
+}
+__device__ __forceinline__ bool ooo_trylock(int *l, int lane) {
+    int got = 0;
+    if (lane == 0) {
+        got = atomicCAS(l, 0, 1) == 0 ? 1 : 0;
+        if (got) __threadfence_block();
+    }
+    return __shfl_sync(kFull, got, 0) != 0;
+}
+__device__ __forceinline__ void ooo_unlock(int *l, int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        atomicExch(l, 0);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ int ooo_ld(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+
+// one seed against `G.used | G.mark`: grow, rectangle, refinement.  Returns the final region size (marks left in G.mark, list in
+// G.reg); ok / seg describe the segment; the bounding box of everything accepted is left in (x0, y0, x1, y1).
+// (G by value: a private copy whose address never escapes, so that its fields -- the bounding box above all -- live in registers)
+__device__ __forceinline__ int ooo_run_seed(const GrowT<true> G, const LineDev &D, uint32_t seed_xy, bool &okr, float4 &seg, int &x0,
+                                            int &y0, int &x1, int &y1) {
+    const int sw = D.sw, lane = G.lane;
+    const int sidx = (int)(seed_xy >> 16) * sw + (int)(seed_xy & 0xffff);
+    G.bx0 = G.by0 = 0x7fffffff;
+    G.bx1 = G.by1 = -1;
+    int gx, gy;
+    grad_at(G.img, sw, sidx, gx, gy);
+    const float seed_deg = fast_atan2_deg((float)gx, (float)-gy);
+    double reg_angle;
+    int n = region_grow(G, seed_xy, seed_deg, D.prec, reg_angle);
+    okr = false;
+    Rect R;
+    if (n >= D.min_reg_size) {
+        region2rect(G, n, reg_angle, D.prec, R);
+        okr = refine(G, n, seed_deg, reg_angle, D.prec, R);
+    }
+    x0 = G.bx0, y0 = G.by0, x1 = G.bx1, y1 = G.by1;
+    for (int off = 16; off >= 1; off >>= 1) {
+        x0 = min(x0, __shfl_xor_sync(kFull, x0, off));
+        y0 = min(y0, __shfl_xor_sync(kFull, y0, off));
+        x1 = max(x1, __shfl_xor_sync(kFull, x1, off));
+        y1 = max(y1, __shfl_xor_sync(kFull, y1, off));
+    }
+    seg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (okr)  // + 0.5 offset, then / scale (0.5)
+        seg = make_float4((float)((R.x1 + 0.5) / 0.5), (float)((R.y1 + 0.5) / 0.5), (float)((R.x2 + 0.5) / 0.5),
+                          (float)((R.y2 + 0.5) / 0.5));
+    (void)lane;
+    return n;
+}
+
+struct OooShared {
+    OooCtl *C;
+    OooEntry *ring;
+    uint32_t *used;  // committed marks
+    int used_pad, sw;
+};
+
+// region list of G (n entries) -> committed map; the private marks are cleared
+__device__ __forceinline__ void ooo_commit_list(const GrowT<true> &G, uint32_t *used, int n, int sw, bool commit) {
+    for (int i = G.lane; i < n; i += 32) {
+        const uint32_t xy = G.get(i);
+        const int pidx = (int)(xy >> 16) * sw + (int)(xy & 0xffff);
+        atomicAnd(&G.mark[pidx >> 5], ~(1u << (pidx & 31)));
+        if (commit) atomicOr(&used[pidx >> 5], 1u << (pidx & 31));
+    }
+    __syncwarp();
+}
+
+// Commit finished tickets from the head, in order (warp-collective; returns at once if another warp is draining).
+// `Gown`: the caller's context (its HELD region, if any, is committed from it); `Gsp`: the spare context that whoever holds the
+// commit lock uses to execute a ticket at the head.
+__device__ void ooo_drain(const OooShared &S, const LineDev &D, const GrowT<true> &Gown, const GrowT<true> &Gsp, int warp, float4 *segs,
+                          int b) {
+    OooCtl &C = *S.C;
+    const int lane = Gown.lane;
+    if (!ooo_trylock(&C.lock_commit, lane)) return;
+    for (;;) {
+        const int h = ooo_ld(&C.head);
+        if (h == ooo_ld(&C.next_ticket)) break;
+        OooEntry &E = S.ring[h & (kOooRing - 1)];
+        const int st = ooo_ld(&E.state);
+        if (st == kOooRunning) break;
+        if (st == kOooHeld && E.owner != warp) break;  // its owner commits it (it is spinning on this lock)
+        bool exec = st == kOooDeferred;
+        if (st == kOooParked || st == kOooHeld) {
+            // valid  <=>  box disjoint from the final boxes of the tickets that were not yet committed when it started
+            bool hit = false;
+            const int bx0 = E.bx0, by0 = E.by0, bx1 = E.bx1, by1 = E.by1;
+            for (int e = E.start_head + lane; e < h; e += 32) {
+                const OooEntry &F = S.ring[e & (kOooRing - 1)];
+                hit = hit || !(F.bx1 < bx0 || bx1 < F.bx0 || F.by1 < by0 || by1 < F.by0);  // (an empty box has bx1 = -1 < bx0)
+            }
+            if (__any_sync(kFull, hit)) {
+                exec = true;
+                if (lane == 0) C.stat[6]++;
+            }
+        }
+        int nseg = ooo_ld(&C.nseg);
+        if (st == kOooVoid) {
+            // nothing
+        } else if (exec) {
+            if (st == kOooHeld) ooo_commit_list(Gown, S.used, E.n, S.sw, false);  // drop the caller's speculative region
+            const uint32_t seed_xy = E.xy;
+            const int sidx = (int)(seed_xy >> 16) * S.sw + (int)(seed_xy & 0xffff);
+            int n = 0, x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
+            bool okr = false;
+            float4 seg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!((S.used[sidx >> 5] >> (sidx & 31)) & 1u)) {  // the committed map IS the sequential state here
+                n = ooo_run_seed(Gsp, D, seed_xy, okr, seg, x0, y0, x1, y1);
+                ooo_commit_list(Gsp, S.used, n, S.sw, true);
+            }
+            if (lane == 0) {
+                E.bx0 = (short)min(x0, 32767);
+                E.by0 = (short)min(y0, 32767);
+                E.bx1 = (short)x1;
+                E.by1 = (short)y1;
+                C.stat[5]++;
+                if (okr) {
+                    if (nseg < D.seg_cap) segs[nseg] = seg;
+                    else atomicOr(&D.status[b], 1);
+                    C.nseg = nseg + 1;
+                }
+            }
+        } else {  // a valid speculative result
+            if (st == kOooParked) {
+                if (lane < E.n) {
+                    const uint32_t xy = E.px[lane];
+                    const int pidx = (int)(xy >> 16) * S.sw + (int)(xy & 0xffff);
+                    atomicOr(&S.used[pidx >> 5], 1u << (pidx & 31));
+                }
+            } else {
+                ooo_commit_list(Gown, S.used, E.n, S.sw, true);
+            }
+            if (lane == 0 && E.ok) {
+                if (nseg < D.seg_cap) segs[nseg] = E.seg;
+                else atomicOr(&D.status[b], 1);
+                C.nseg = nseg + 1;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (st == kOooHeld) *reinterpret_cast<volatile int *>(&E.state) = kOooCommitted;  // releases the owner (the caller)
+            *reinterpret_cast<volatile int *>(&C.head) = h + 1;
+        }
+        __syncwarp();
+    }
+    ooo_unlock(&C.lock_commit, lane);
+}
+
+__global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev D, uint32_t *reg_ovf_mw) {
+    extern __shared__ uint4 s_grow[];
+    const int W = blockDim.x >> 5;
+    uint8_t *s_img = reinterpret_cast<uint8_t *>(s_grow);
+    const int img_bytes = (D.npx + 15) & ~15;
+    const int used_words = (D.npx + 31) >> 5, used_pad = (used_words + 3) & ~3;
+    uint32_t *s_used = reinterpret_cast<uint32_t *>(s_img + img_bytes);  // committed marks
+    uint32_t *s_priv = s_used + used_pad;                                // W + 1 private bitmaps (the last one: head execution)
+    uint32_t *s_reg = s_priv + (size_t)(W + 1) * used_pad;               // W + 1 region windows
+    OooEntry *ring = reinterpret_cast<OooEntry *>(s_reg + (size_t)(W + 1) * kOooRegCap);
+    OooCtl &C = *reinterpret_cast<OooCtl *>(ring + kOooRing);
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {  // stage the frame
+        const uint8_t *src = D.scaled + (size_t)b * D.npx;
+        if (((size_t)src & 15) == 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            for (int i = tid; i < D.npx / 16; i += blockDim.x) s_grow[i] = s4[i];
+            for (int i = (D.npx / 16) * 16 + tid; i < D.npx; i += blockDim.x) s_img[i] = src[i];
+        } else {
+            for (int i = tid; i < D.npx; i += blockDim.x) s_img[i] = src[i];
+        }
+        for (int i = tid; i < used_pad * (W + 2); i += blockDim.x) s_used[i] = 0;
+        uint32_t *z = reinterpret_cast<uint32_t *>(ring);
+        for (int i = tid; i < (int)((sizeof(OooEntry) * kOooRing + sizeof(OooCtl)) / 4); i += blockDim.x) z[i] = 0;
+    }
+    __syncthreads();
+    GrowT<true> G, Gsp;
+    G.sw = D.sw;
+    G.sh = D.sh;
+    G.kthr = D.kthr;
+    G.density_th = D.density_th;
+    G.img = s_img;
+    G.reg_cap = kOooRegCap;
+    G.used = s_used;
+    G.tab = D.cstab;
+    G.direct = false;
+    G.lane = lane;
+    Gsp = G;
+    G.mark = s_priv + (size_t)warp * used_pad;
+    G.reg = s_reg + (size_t)warp * kOooRegCap;
+    G.reg_ovf = reg_ovf_mw + ((size_t)b * (kMwMaxWarps + 1) + warp) * D.npx;
+    Gsp.mark = s_priv + (size_t)W * used_pad;
+    Gsp.reg = s_reg + (size_t)W * kOooRegCap;
+    Gsp.reg_ovf = reg_ovf_mw + ((size_t)b * (kMwMaxWarps + 1) + kMwMaxWarps) * D.npx;
+    OooShared S{&C, ring, s_used, used_pad, D.sw};
+    const uint32_t *order = D.order + (size_t)b * D.npx;
+    float4 *segs = D.segs + (size_t)b * D.seg_cap;
+    const int nseeds = D.nseeds[b];
+    const int sw = D.sw;
+    const long long t_start = clock64();
+    bool timed_out = false;
+    for (;;) {
+        if (clock64() - t_start > kOooTimeout) {
+            timed_out = true;
+            break;
+        }
+        // ---- take the next ticket: the next seed (in order) that is not used in the committed map
+        int t = -1;  // -1: no seed left, -2: the window is full
+        if (!ooo_lock(&C.lock_dispatch, lane, t_start)) {
+            timed_out = true;
+            break;
+        }
+        {
+            const int nt = ooo_ld(&C.next_ticket);
+            if (nt - ooo_ld(&C.head) >= kOooWindow) {
+                t = -2;
+            } else {
+                unsigned m = *reinterpret_cast<volatile unsigned *>(&C.chunk_mask);
+                int base = ooo_ld(&C.chunk_base), sp = ooo_ld(&C.scan_pos);
+                uint32_t cxy = *reinterpret_cast<volatile uint32_t *>(&C.chunk_xy[lane]);
+                while (m == 0u && sp < nseeds) {
+                    const int p = sp + lane;
+                    cxy = p < nseeds ? order[p] : 0u;
+                    const int oidx = (int)(cxy >> 16) * sw + (int)(cxy & 0xffff);
+                    m = __ballot_sync(kFull, p < nseeds && !((s_used[oidx >> 5] >> (oidx & 31)) & 1u));
+                    base = sp;
+                    sp += 32;
+                }
+                if (m != 0u) {
+                    const int l = __ffs(m) - 1;
+                    const uint32_t xy = __shfl_sync(kFull, cxy, l);
+                    t = nt;
+                    if (lane == 0) {
+                        OooEntry &E = ring[t & (kOooRing - 1)];
+                        E.xy = xy;
+                        E.start_head = ooo_ld(&C.head);
+                        E.owner = warp;
+                        E.n = 0;
+                        E.ok = 0;
+                        E.bx0 = E.by0 = 32767;
+                        E.bx1 = E.by1 = -1;
+                        *reinterpret_cast<volatile int *>(&E.state) = kOooRunning;
+                        C.stat[0]++;
+                    }
+                    m &= m - 1;
+                }
+                C.chunk_xy[lane] = cxy;
+                if (lane == 0) {
+                    C.chunk_mask = m;
+                    C.chunk_base = base;
+                    C.scan_pos = sp;
+                    if (t >= 0) {
+                        __threadfence_block();
+                        *reinterpret_cast<volatile int *>(&C.next_ticket) = t + 1;
+                    }
+                }
+            }
+        }
+        ooo_unlock(&C.lock_dispatch, lane);
+        if (t < 0) {
+            if (t == -1 && ooo_ld(&C.head) == ooo_ld(&C.next_ticket)) {
+                // every ticket is committed; a seed can only have been left behind if another warp is between its scan and
+                // its ticket, which the dispatch lock excludes
+                break;
+            }
+            ooo_drain(S, D, G, Gsp, warp, segs, b);
+            __nanosleep(100);
+            continue;
+        }
+        OooEntry &E = ring[t & (kOooRing - 1)];
+        const uint32_t seed_xy = E.xy;
+        const int sidx = (int)(seed_xy >> 16) * sw + (int)(seed_xy & 0xffff);
+        int state;
+        if ((s_used[sidx >> 5] >> (sidx & 31)) & 1u) {
+            state = kOooVoid;  // committed since the scan: by a ticket before this one, so the sequential run skips it too
+        } else {
+            // inside a region another warp is growing right now: most likely absorbed -- decided at the head instead
+            bool other = false;
+            if (lane < W && lane != warp) other = (s_priv[(size_t)lane * used_pad + (sidx >> 5)] >> (sidx & 31)) & 1u;
+            if (__any_sync(kFull, other)) {
+                state = kOooDeferred;
+            } else {
+                bool okr;
+                float4 seg;
+                int x0, y0, x1, y1;
+                const int n = ooo_run_seed(G, D, seed_xy, okr, seg, x0, y0, x1, y1);
+                if (lane == 0) {
+                    E.n = n;
+                    E.ok = okr ? 1 : 0;
+                    E.seg = seg;
+                    E.bx0 = (short)x0;
+                    E.by0 = (short)y0;
+                    E.bx1 = (short)x1;
+                    E.by1 = (short)y1;
+                }
+                if (n <= kOooPark) {
+                    if (lane < n) E.px[lane] = G.get(lane);
+                    __syncwarp();
+                    ooo_commit_list(G, s_used, n, sw, false);  // clears the private marks only
+                    state = kOooParked;
+                } else {
+                    state = kOooHeld;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            C.stat[state - 1]++;  // (counted without the lock: a tuning aid, may lose increments)
+            __threadfence_block();
+            *reinterpret_cast<volatile int *>(&E.state) = state;
+        }
+        __syncwarp();
+        if (state == kOooHeld) {
+            while (ooo_ld(&E.state) == kOooHeld) {
+                ooo_drain(S, D, G, Gsp, warp, segs, b);
+                if (ooo_ld(&E.state) == kOooHeld) __nanosleep(100);
+                if (clock64() - t_start > kOooTimeout) {
+                    timed_out = true;
+                    break;
+                }
+            }
+            if (timed_out) break;
+        } else {
+            ooo_drain(S, D, G, Gsp, warp, segs, b);
+        }
+    }
+    if (timed_out && lane == 0) atomicOr(&D.status[b], 2);
+    __syncthreads();
+    if (tid == 0) {
+        D.nseg[b] = min(C.nseg, D.seg_cap);
+        if (D.mw_stat)
+            for (int q = 0; q < 7; ++q) D.mw_stat[8 * b + q] = C.stat[q];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // K5: segments -> KeyLines (LSDDetector_custom.cpp:266-300) + 2-D line functions (line_extractor.cc:147-159)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) keyline_kernel(LineDev D, plp_keyline *kl_out, double *fn_out, int32_t *n_out) {
@@ -1202,7 +1599,9 @@ struct plp_line {
     bool img_smem_ok = true;
     int resident_smem_frames = 0;
     bool force_global_image = false;
-    int grow_variant = 0;  // 0 automatic, 1 one warp per frame, 2 speculative multi-warp (lsd_grow_mw_kernel)
+    int grow_variant = 0;  // 0 automatic, 1 one warp per frame, 2 multi-warp rounds (lsd_grow_mw_kernel), 3 out of order (lsd_grow_ooo_kernel)
+    int ooo_warps = 0;
+    size_t ooo_smem = 0;
     int mw_warps = 0, mw_max_batch = 0;
     size_t mw_smem = 0;
     uint32_t *d_reg_mw = nullptr;
@@ -1243,8 +1642,11 @@ static plp_status line_run(plp_line *h, const uint8_t *d_imgs, int batch, size_t
     // a wave of frames or less: the frame-level parallelism cannot fill the GPU, several warps per frame (speculative, in-order
     // commit) cut the latency of a live frame instead
     const bool mw = h->mw_warps >= 2 && batch <= h->mw_max_batch && h->grow_variant != 1 &&
-                    (h->grow_variant == 2 || 2 * batch <= ctx->sm_count);  // half a wave: a second handle (stereo) fits beside it
-    if (mw) {
+                    (h->grow_variant >= 2 || 2 * batch <= ctx->sm_count);  // half a wave: a second handle (stereo) fits beside it
+    const bool ooo = mw && h->ooo_warps >= 2 && h->grow_variant != 2;
+    if (ooo) {
+        PLP_LAUNCH(ctx, lsd_grow_ooo_kernel, batch, h->ooo_warps * 32, h->ooo_smem, D, h->d_reg_mw);
+    } else if (mw) {
         PLP_LAUNCH(ctx, lsd_grow_mw_kernel, batch, h->mw_warps * 32, h->mw_smem, D, h->d_reg_mw);
     } else if (h->img_smem_ok && 2 * batch <= h->resident_smem_frames && !h->force_global_image) {
         PLP_LAUNCH(ctx, lsd_grow_kernel<true>, batch, 32, h->grow_smem, D);
@@ -1382,7 +1784,15 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
         h->mw_max_batch = h->mw_warps >= 2 ? std::min(max_batch, ctx->sm_count) : 0;
         if (h->mw_warps >= 2) {
             if (so == PLP_OK) so = ensure_smem_optin((const void *)lsd_grow_mw_kernel, h->mw_smem, "lsd_grow_mw_kernel");
-            if (so == PLP_OK) so = dev_alloc(h, &h->d_reg_mw, (size_t)h->mw_max_batch * kMwMaxWarps * D.npx);
+            if (so == PLP_OK) so = dev_alloc(h, &h->d_reg_mw, (size_t)h->mw_max_batch * (kMwMaxWarps + 1) * D.npx);
+            // out-of-order variant: one more private bitmap + window (execution at the head), the reorder buffer
+            const size_t ofixed = (size_t)((D.npx + 15) & ~15) + 2 * used_bytes + (size_t)kOooRegCap * 4 + sizeof(OooEntry) * kOooRing +
+                                  sizeof(OooCtl) + 64, oper = used_bytes + (size_t)kOooRegCap * 4;
+            h->ooo_warps = ofixed + 2 * oper <= budget ? (int)std::min<size_t>(kMwMaxWarps, (budget - ofixed) / oper) : 0;
+            if (const char *ev = getenv("PLP_LSD_OOO_WARPS")) h->ooo_warps = std::max(0, std::min(h->ooo_warps, atoi(ev)));  // tuning aid
+            h->ooo_smem = ofixed + (size_t)h->ooo_warps * oper;
+            if (h->ooo_warps >= 2 && so == PLP_OK)
+                so = ensure_smem_optin((const void *)lsd_grow_ooo_kernel, h->ooo_smem, "lsd_grow_ooo_kernel");
             if (so == PLP_OK) so = dev_alloc(h, &h->dev.mw_stat, (size_t)8 * max_batch);
             if (so == PLP_OK && cudaMemsetAsync(h->dev.mw_stat, 0, (size_t)8 * max_batch * 8, ctx->stream) != cudaSuccess) so = PLP_ERR_CUDA;
         }
@@ -1457,8 +1867,9 @@ plp_status plp_line_debug_force_global_image(plp_line *h, int on) {
 }
 
 plp_status plp_line_debug_grow_variant(plp_line *h, int variant) {
-    PLP_REQUIRE(h && variant >= 0 && variant <= 2, "variant must be 0 (automatic), 1 (one warp per frame) or 2 (multi-warp)");
-    PLP_REQUIRE(variant != 2 || h->mw_warps >= 2, "the multi-warp variant does not fit the shared memory at this image size");
+    PLP_REQUIRE(h && variant >= 0 && variant <= 3, "variant must be 0 (automatic), 1 (one warp per frame), 2 (multi-warp rounds) or 3 (out of order)");
+    PLP_REQUIRE(variant < 2 || h->mw_warps >= 2, "the multi-warp variants do not fit the shared memory at this image size");
+    PLP_REQUIRE(variant != 3 || h->ooo_warps >= 2, "the out-of-order variant does not fit the shared memory at this image size");
     h->grow_variant = variant;
     return PLP_OK;
 }

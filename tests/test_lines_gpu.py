@@ -32,8 +32,9 @@ def _compare(trk, orc, img, b=0, got=None):
     return len(segs), len(kl)
 
 
-# region growing variants (lines.cu): 1 = one warp per frame, 2 = several warps per frame, speculative with in-order commit
-@pytest.mark.parametrize("variant", [1, 2])
+# region growing variants (lines.cu): 1 = one warp per frame, 2 = several warps per frame in speculative rounds with in-order commit,
+# 3 = out of order with a reorder buffer and in-order commit
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("kind,seed,shape", [("lines", 1, (480, 640)), ("lines", 2, (480, 752)), ("texture", 1234, (480, 640)),
                                              ("texture", 7, (480, 752)), ("lines", 9, (376, 1240)), ("plp", 5, (480, 640))])
 def test_line_extract_matches_oracle(ctx, orc, plp, kind, seed, shape, variant):
@@ -49,10 +50,14 @@ def test_line_extract_matches_oracle(ctx, orc, plp, kind, seed, shape, variant):
         st = trk.grow_stats(0)
         assert st["rounds"] > 0 and st["seeds_run"] >= nseg
         print(f"[mw] {kind} {shape}: {st}, {nseg} segments")
+    if variant == 3:
+        st = trk.grow_stats(0, ooo=True)
+        assert st["tickets"] >= nseg
+        print(f"[ooo] {kind} {shape}: {st}, {nseg} segments")
     trk.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_edge_cases(ctx, orc, plp, variant):
     trk = plp.LineFeatureTracker(ctx, 480, 640)
     trk.grow_variant(variant)
@@ -81,7 +86,7 @@ def test_batch_equals_single(ctx, orc, plp):
     imgs = np.stack([synth.make_line_image(20 + i) for i in range(5)] + [synth.make_texture(3)])
     trk = plp.LineFeatureTracker(ctx, 480, 640, max_batch=6)
     # one warp per frame with both placements of the half-resolution image, then the multi-warp variant
-    for variant, global_image in ((1, False), (1, True), (2, False)):
+    for variant, global_image in ((1, False), (1, True), (2, False), (3, False)):
         trk.grow_variant(variant)
         trk.force_global_image(global_image)
         res = trk.extract_batch(imgs)

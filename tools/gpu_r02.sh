@@ -56,13 +56,7 @@ fi
 if [[ " $WHAT " == *" lsd "* ]]; then
   timeout 900 python -m pytest tests/test_lines_gpu.py -q -m gpu -x -s > gpurun_out/test_lines_${TAG}.log 2>&1
   echo "lines tests exit $?"; grep "\[mw\]" gpurun_out/test_lines_${TAG}.log | head -20; tail -5 gpurun_out/test_lines_${TAG}.log
-  timeout 600 python tools/lsd_latency.py 8:0 8:3 > gpurun_out/lsd_latency_${TAG}.log 2>&1; echo "lsd latency exit $?"; cat gpurun_out/lsd_latency_${TAG}.log
-  PLP_LSD_REGCAP=512 timeout 300 python bench.py --only-lines --no-cpu-baseline --steps 4 --warmup 3 --line-batch 2812 > gpurun_out/bench_lines_regcap512_${TAG}.json 2>/dev/null
-  echo "lines throughput region window 512, batch 2812:"; python -c "import json,sys; d=json.loads(open('gpurun_out/bench_lines_regcap512_${TAG}.json').read().strip().splitlines()[-1]); print(round(d['value'],1),'frames/s', d['ms_per_launch'])"
-  for D in 0 2; do
-    PLP_LSD_DIRECT=$D timeout 300 python bench.py --only-lines --no-cpu-baseline --steps 4 --warmup 3 > gpurun_out/bench_lines_direct${D}_${TAG}.json 2>/dev/null
-    echo "lines throughput PLP_LSD_DIRECT=$D:"; python -c "import json,sys; d=json.loads(open('gpurun_out/bench_lines_direct${D}_${TAG}.json').read().strip().splitlines()[-1]); print(round(d['value'],1),'frames/s', d['ms_per_launch'])"
-  done
+  timeout 600 python tools/lsd_latency.py 8:0 > gpurun_out/lsd_latency_${TAG}.log 2>&1; echo "lsd latency exit $?"; cat gpurun_out/lsd_latency_${TAG}.log
 fi
 if [[ " $WHAT " == *" ba "* ]]; then
   timeout 600 python -m pytest tests/test_ba_gpu.py tests/test_plane_gpu.py -q -m gpu -x > gpurun_out/test_ba_${TAG}.log 2>&1

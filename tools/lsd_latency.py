@@ -56,13 +56,16 @@ for cfg in cfgs:
             imgs = np.concatenate([fr] * ((batch + 7) // 8))[:batch]
             trk = plp.LineFeatureTracker(ctx, H, W, max_batch=batch)
             out = {}
-            for variant in (1, 2):
+            for variant in (1, 2, 3):
                 trk.grow_variant(variant)
                 out[variant] = (timed(trk, imgs), kernel_ms(trk, imgs))
-            st = trk.grow_stats(0)
+                if variant == 2:
+                    st = trk.grow_stats(0)
+            st3 = trk.grow_stats(0, ooo=True)
             n = len(trk.extract_batch(imgs)[0][0])
             print(f"warps={warps} direct={os.environ['PLP_LSD_DIRECT']} {kind:8s} batch={batch:3d} keylines[0]={n:4d}  one-warp: {out[1][0]:7.2f} ms/call (grow {out[1][1].get('lsd_grow')})"
-                  f"   multi-warp: {out[2][0]:7.2f} ms/call (grow {out[2][1].get('lsd_grow_mw')})  stats {st}")
+                  f"   multi-warp: {out[2][0]:7.2f} ms/call (grow {out[2][1].get('lsd_grow_mw')})  stats {st}\n"
+                  f"          out-of-order: {out[3][0]:7.2f} ms/call (grow {out[3][1].get('lsd_grow_ooo')})  stats {st3}")
             if batch == 1 and cfg == cfgs[0]:
                 print("    kernels (multi-warp run):", out[2][1])
             trk.close()
