@@ -975,6 +975,11 @@ struct OooCtl {
 // (every wait of this kernel is bounded: after ~2 s of SM cycles a warp gives up, raises status bit 2 and leaves -- a protocol
 // bug must not hang the device)
 constexpr long long kOooTimeout = 4000000000ll;
+__device__ __forceinline__ bool ooo_expired(long long t_start) {  // one lane decides (the lanes' clocks differ by a few cycles)
+    int e = 0;
+    if ((threadIdx.x & 31) == 0) e = clock64() - t_start > kOooTimeout ? 1 : 0;
+    return __shfl_sync(kFull, e, 0) != 0;
+}
 __device__ __forceinline__ bool ooo_lock(int *l, int lane, long long t_start) {
     int ok = 1;
     if (lane == 0) {
@@ -1005,7 +1010,14 @@ __device__ __forceinline__ void ooo_unlock(int *l, int lane) {
     }
     __syncwarp();
 }
-__device__ __forceinline__ int ooo_ld(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+// A word that another warp may change at any moment is read by ONE lane and broadcast: if every lane read it for itself the
+// lanes of a warp could see different values and take different branches around warp-collective operations (this hung the
+// first version of the kernel).
+__device__ __forceinline__ int ooo_ld(const int *p) {
+    int v = 0;
+    if ((threadIdx.x & 31) == 0) v = *reinterpret_cast<const volatile int *>(p);
+    return __shfl_sync(kFull, v, 0);
+}
 
 // one seed against `G.used | G.mark`: grow, rectangle, refinement.  Returns the final region size (marks left in G.mark, list in
 // G.reg); ok / seg describe the segment; the bounding box of everything accepted is left in (x0, y0, x1, y1).
@@ -1074,7 +1086,8 @@ __device__ void ooo_drain(const OooShared &S, const LineDev &D, const GrowT<true
         OooEntry &E = S.ring[h & (kOooRing - 1)];
         const int st = ooo_ld(&E.state);
         if (st == kOooRunning) break;
-        if (st == kOooHeld && E.owner != warp) break;  // its owner commits it (it is spinning on this lock)
+        const int owner = ooo_ld(&E.owner);
+        if (st == kOooHeld && owner != warp) break;  // its owner commits it (it is spinning on this lock)
         bool exec = st == kOooDeferred;
         if (st == kOooParked || st == kOooHeld) {
             // valid  <=>  box disjoint from the final boxes of the tickets that were not yet committed when it started
@@ -1099,7 +1112,7 @@ __device__ void ooo_drain(const OooShared &S, const LineDev &D, const GrowT<true
             int n = 0, x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
             bool okr = false;
             float4 seg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!((S.used[sidx >> 5] >> (sidx & 31)) & 1u)) {  // the committed map IS the sequential state here
+            if (!((ooo_ld(reinterpret_cast<const int *>(&S.used[sidx >> 5])) >> (sidx & 31)) & 1)) {  // the committed map IS the sequential state here
                 n = ooo_run_seed(Gsp, D, seed_xy, okr, seg, x0, y0, x1, y1);
                 ooo_commit_list(Gsp, S.used, n, S.sw, true);
             }
@@ -1194,7 +1207,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
     const long long t_start = clock64();
     bool timed_out = false;
     for (;;) {
-        if (clock64() - t_start > kOooTimeout) {
+        if (ooo_expired(t_start)) {
             timed_out = true;
             break;
         }
@@ -1209,7 +1222,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
             if (nt - ooo_ld(&C.head) >= kOooWindow) {
                 t = -2;
             } else {
-                unsigned m = *reinterpret_cast<volatile unsigned *>(&C.chunk_mask);
+                unsigned m = (unsigned)ooo_ld(reinterpret_cast<const int *>(&C.chunk_mask));
                 int base = ooo_ld(&C.chunk_base), sp = ooo_ld(&C.scan_pos);
                 uint32_t cxy = *reinterpret_cast<volatile uint32_t *>(&C.chunk_xy[lane]);
                 while (m == 0u && sp < nseeds) {
@@ -1223,11 +1236,12 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
                 if (m != 0u) {
                     const int l = __ffs(m) - 1;
                     const uint32_t xy = __shfl_sync(kFull, cxy, l);
+                    const int head_now = ooo_ld(&C.head);
                     t = nt;
                     if (lane == 0) {
                         OooEntry &E = ring[t & (kOooRing - 1)];
                         E.xy = xy;
-                        E.start_head = ooo_ld(&C.head);
+                        E.start_head = head_now;
                         E.owner = warp;
                         E.n = 0;
                         E.ok = 0;
@@ -1265,7 +1279,8 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
         const uint32_t seed_xy = E.xy;
         const int sidx = (int)(seed_xy >> 16) * sw + (int)(seed_xy & 0xffff);
         int state;
-        if ((s_used[sidx >> 5] >> (sidx & 31)) & 1u) {
+        // (the committed map changes under our feet: one lane reads the word, see ooo_ld)
+        if ((ooo_ld(reinterpret_cast<const int *>(&s_used[sidx >> 5])) >> (sidx & 31)) & 1) {
             state = kOooVoid;  // committed since the scan: by a ticket before this one, so the sequential run skips it too
         } else {
             // inside a region another warp is growing right now: most likely absorbed -- decided at the head instead
@@ -1308,7 +1323,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
             while (ooo_ld(&E.state) == kOooHeld) {
                 ooo_drain(S, D, G, Gsp, warp, segs, b);
                 if (ooo_ld(&E.state) == kOooHeld) __nanosleep(100);
-                if (clock64() - t_start > kOooTimeout) {
+                if (ooo_expired(t_start)) {
                     timed_out = true;
                     break;
                 }
@@ -1601,6 +1616,7 @@ struct plp_line {
     bool force_global_image = false;
     int grow_variant = 0;  // 0 automatic, 1 one warp per frame, 2 multi-warp rounds (lsd_grow_mw_kernel), 3 out of order (lsd_grow_ooo_kernel)
     int ooo_warps = 0;
+    bool ooo_auto = false;
     size_t ooo_smem = 0;
     int mw_warps = 0, mw_max_batch = 0;
     size_t mw_smem = 0;
@@ -1643,7 +1659,8 @@ static plp_status line_run(plp_line *h, const uint8_t *d_imgs, int batch, size_t
     // commit) cut the latency of a live frame instead
     const bool mw = h->mw_warps >= 2 && batch <= h->mw_max_batch && h->grow_variant != 1 &&
                     (h->grow_variant >= 2 || 2 * batch <= ctx->sm_count);  // half a wave: a second handle (stereo) fits beside it
-    const bool ooo = mw && h->ooo_warps >= 2 && h->grow_variant != 2;
+    // (automatic mode takes the out-of-order kernel only when PLP_LSD_OOO=1: it is the newest code of the tree)
+    const bool ooo = mw && h->ooo_warps >= 2 && (h->grow_variant == 3 || (h->grow_variant == 0 && h->ooo_auto));
     if (ooo) {
         PLP_LAUNCH(ctx, lsd_grow_ooo_kernel, batch, h->ooo_warps * 32, h->ooo_smem, D, h->d_reg_mw);
     } else if (mw) {
@@ -1789,6 +1806,7 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
             const size_t ofixed = (size_t)((D.npx + 15) & ~15) + 2 * used_bytes + (size_t)kOooRegCap * 4 + sizeof(OooEntry) * kOooRing +
                                   sizeof(OooCtl) + 64, oper = used_bytes + (size_t)kOooRegCap * 4;
             h->ooo_warps = ofixed + 2 * oper <= budget ? (int)std::min<size_t>(kMwMaxWarps, (budget - ofixed) / oper) : 0;
+            if (const char *ev = getenv("PLP_LSD_OOO")) h->ooo_auto = atoi(ev) != 0;
             if (const char *ev = getenv("PLP_LSD_OOO_WARPS")) h->ooo_warps = std::max(0, std::min(h->ooo_warps, atoi(ev)));  // tuning aid
             h->ooo_smem = ofixed + (size_t)h->ooo_warps * oper;
             if (h->ooo_warps >= 2 && so == PLP_OK)

