@@ -598,10 +598,10 @@ PLP_API plp_status plp_line_debug_force_global_image(plp_line *h, int on);
 /* region growing variant: 0 automatic (multi-warp for at most half a wave of frames, i.e. the live-sequence case), 1 one warp
  * per frame, 2 speculative multi-warp rounds with in-order commit, 3 out of order with a reorder buffer and in-order commit;
  * all of them produce the sequential result bit for bit.
- * grow_stats (7 values): {rounds, seeds run, seeds redone after a conflict, then SM cycles warp 0 spent scanning for seeds,
+ * grow_stats (8 values): {rounds, seeds run, seeds redone after a conflict, then SM cycles warp 0 spent scanning for seeds,
  * on its own seed, waiting for the slowest warp of the round, committing} of frame b in the last multi-warp run. */
 PLP_API plp_status plp_line_debug_grow_variant(plp_line *h, int variant);
-PLP_API plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out7);
+PLP_API plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out8);
 PLP_API plp_status plp_line_debug_scaled(plp_line *h, int b, uint8_t *out /* (rows/2) x (cols/2) */);
 PLP_API plp_status plp_line_debug_lbd_float(plp_line *h, int b, float *out /* n x 72 */, int cap);
 

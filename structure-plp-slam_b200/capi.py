@@ -837,11 +837,11 @@ class LineFeatureTracker:
     def grow_stats(self, b: int = 0, ooo: bool = False):
         """{rounds, seeds run, seeds redone after a conflict, cycle counters} of frame b in the last multi-warp run; with ooo:
         the counters of the out-of-order variant."""
-        out = (C.c_ulonglong * 7)()
+        out = (C.c_ulonglong * 8)()
         self._ctx._check(self._lib.plp_line_debug_grow_stats(self._h, C.c_int(b), out))
         if ooo:
             return dict(tickets=int(out[0]), void=int(out[1]), deferred=int(out[2]), parked=int(out[3]), held=int(out[4]),
-                        executed_at_head=int(out[5]), conflicts=int(out[6]))
+                        executed_at_head=int(out[5]), conflicts=int(out[6]), aborted=int(out[7]))
         return dict(rounds=int(out[0]), seeds_run=int(out[1]), seeds_redone=int(out[2]), cyc_scan=int(out[3]),
                     cyc_own=int(out[4]), cyc_wait=int(out[5]), cyc_commit=int(out[6]))
 

@@ -304,6 +304,13 @@ struct GrowT {  // per-warp state
     int lane, reg_cap;
     bool direct;           // compute {deg, cos, sin} of a neighbour instead of reading the table
     mutable int bx0, by0, bx1, by1;  // kMw: per-lane bounding box of the pixels this lane accepted (reduced by the caller)
+    // out-of-order kernel only (claim == nullptr otherwise): `claim` = union of the private marks of every context in flight;
+    // a region that is about to accept a pixel claimed by an EARLIER ticket stops at once (`aborted`) and is decided at the head
+    uint32_t *claim;
+    const uint32_t *priv_base;   // the contexts' private bitmaps, `ctx_words` words apart
+    const int *ctx_ticket;       // ticket each context is working on (INT_MAX: idle)
+    int nctx, self, my_ticket, ctx_words;
+    mutable bool aborted;
 #ifdef PLP_LSD_PROF
     long long *pc;         // [0] iterations [1] rounds [2] cycles load phase [3] cycles resolve phase [4] on-demand loads
 #endif
@@ -317,8 +324,20 @@ struct GrowT {  // per-warp state
         if (kMw) w |= mark[idx >> 5];
         return (w >> (idx & 31)) & 1u;
     }
+    __device__ __forceinline__ bool claimed_by_earlier(int idx) const {
+        if (!kMw || !claim || !((claim[idx >> 5] >> (idx & 31)) & 1u)) return false;
+        bool earlier = false;
+        for (int w = 0; w < nctx; ++w)
+            if (w != self && ((priv_base[(size_t)w * ctx_words + (idx >> 5)] >> (idx & 31)) & 1u))
+                earlier = earlier || *reinterpret_cast<const volatile int *>(&ctx_ticket[w]) < my_ticket;
+        return earlier;
+    }
+    __device__ __forceinline__ void unclaim(int idx) const {
+        if (kMw && claim) atomicAnd(&claim[idx >> 5], ~(1u << (idx & 31)));
+    }
     __device__ __forceinline__ void accept(int idx, uint32_t xy) const {  // one lane: mark a pixel of the region
         mark[idx >> 5] |= 1u << (idx & 31);
+        if (kMw && claim) atomicOr(&claim[idx >> 5], 1u << (idx & 31));
         if (kMw) {
             const int x = (int)(xy & 0xffff), y = (int)(xy >> 16);
             bx0 = min(bx0, x);
@@ -435,6 +454,7 @@ __device__ int region_grow(const GrowT<kMw> &G, uint32_t seed_xy, float seed_deg
         G.pc[2] += tl1 - tl0;
 #endif
         bool cand = (g < take) && (cur.nidx >= 0) && !G.is_used(cur.nidx);
+        const bool ce = cand && G.claimed_by_earlier(cur.nidx);  // (false unless the out-of-order kernel runs)
         const double a = (double)cur.t.x * kDegToRads;
         float my_sdx = sumdx + cur.t.y, my_sdy = sumdy + cur.t.z;
         double my_theta = (double)fast_atan2_deg(my_sdy, my_sdx) * kDegToRads;
@@ -446,6 +466,11 @@ __device__ int region_grow(const GrowT<kMw> &G, uint32_t seed_xy, float seed_deg
             G.pc[1]++;
 #endif
             const int l = __ffs(m) - 1;
+            if (kMw && __shfl_sync(kFull, ce ? 1 : 0, l)) {  // the next pixel of the sequential order belongs to an earlier region in flight
+                G.aborted = true;
+                reg_angle_out = reg_angle;
+                return n;
+            }
             sumdx = __shfl_sync(kFull, my_sdx, l);
             sumdy = __shfl_sync(kFull, my_sdy, l);
             reg_angle = __shfl_sync(kFull, my_theta, l);
@@ -564,6 +589,7 @@ __device__ bool refine(const GrowT<kMw> &G, int &n, float seed_deg, double reg_a
         const int px = xy & 0xffff, py = xy >> 16;
         const int pidx = py * sw + px;
         atomicAnd(&G.mark[pidx >> 5], ~(1u << (pidx & 31)));  // NOTUSED again
+        G.unclaim(pidx);
         if (sqrt(dist2(xc, yc, (double)px, (double)py)) < R.width) {
             int gx, gy;
             grad_at(G.img, sw, pidx, gx, gy);
@@ -581,6 +607,7 @@ __device__ bool refine(const GrowT<kMw> &G, int &n, float seed_deg, double reg_a
     const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
     __syncwarp();
     n = region_grow(G, seed_xy, seed_deg, tau, reg_angle);
+    if (kMw && G.aborted) return false;
     if (n < 2) return false;
     region2rect(G, n, reg_angle, prec, R);
     density = rect_density(n, R);
@@ -602,6 +629,7 @@ __device__ bool refine(const GrowT<kMw> &G, int &n, float seed_deg, double reg_a
                 if (!keep) {
                     const int pidx = py * sw + px;
                     atomicAnd(&G.mark[pidx >> 5], ~(1u << (pidx & 31)));
+                    G.unclaim(pidx);
                 }
             }
             const unsigned km = __ballot_sync(kFull, keep);
@@ -672,6 +700,8 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(LineDev D) {
     G.reg_ovf = D.reg_xy + (size_t)b * D.npx;
     G.tab = D.cstab;
     G.direct = (D.direct_trig & 2) != 0;
+    G.claim = nullptr;
+    G.aborted = false;
 #ifdef PLP_LSD_PROF
     G.pc = s_pc;
 #endif
@@ -800,6 +830,8 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D
     G.reg_ovf = reg_ovf_mw + ((size_t)b * kMwMaxWarps + warp) * D.npx;
     G.tab = D.cstab;
     G.direct = (D.direct_trig & 1) != 0;
+    G.claim = nullptr;
+    G.aborted = false;
     G.lane = lane;
     const uint32_t *order = D.order + (size_t)b * D.npx;
     float4 *segs = D.segs + (size_t)b * D.seg_cap;
@@ -947,8 +979,8 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_mw_kernel(LineDev D
 // absorbed), is simply executed AT THE HEAD, where the committed map is exactly the sequential state -- so every decision that
 // is not provably the sequential one is redone sequentially, and the segments come out in ticket order, bit for bit.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kOooRing = 256;    // reorder-buffer entries (ticket % kOooRing)
-constexpr int kOooWindow = 128;  // tickets in flight (<= kOooRing / 2: an entry is not reused while a later ticket may still test it)
+constexpr int kOooRing = 128;    // reorder-buffer entries (ticket % kOooRing)
+constexpr int kOooWindow = 64;   // tickets in flight (<= kOooRing / 2: an entry is not reused while a later ticket may still test it)
 constexpr int kOooPark = 24;     // pixels of a region that can be parked in its entry
 constexpr int kOooRegCap = 512;  // region window per warp in shared memory (longer regions continue in global memory)
 
@@ -969,7 +1001,9 @@ struct OooCtl {
     unsigned chunk_mask;
     int nseg;
     uint32_t chunk_xy[32];
-    unsigned long long stat[8];  // tickets, void, deferred, parked, held, executed at the head, conflicts
+    int ctx_ticket[kMwMaxWarps + 1];  // ticket every context (warps + the head-execution context) works on, INT_MAX: none
+    int pad_[3];
+    unsigned long long stat[8];  // tickets, void, deferred, parked, held, executed at the head, conflicts, aborted
 };
 
 // (every wait of this kernel is bounded: after ~2 s of SM cycles a warp gives up, raises status bit 2 and leaves -- a protocol
@@ -1023,7 +1057,7 @@ __device__ __forceinline__ int ooo_ld(const int *p) {
 // G.reg); ok / seg describe the segment; the bounding box of everything accepted is left in (x0, y0, x1, y1).
 // (G by value: a private copy whose address never escapes, so that its fields -- the bounding box above all -- live in registers)
 __device__ __forceinline__ int ooo_run_seed(const GrowT<true> G, const LineDev &D, uint32_t seed_xy, bool &okr, float4 &seg, int &x0,
-                                            int &y0, int &x1, int &y1) {
+                                            int &y0, int &x1, int &y1, bool &aborted) {
     const int sw = D.sw, lane = G.lane;
     const int sidx = (int)(seed_xy >> 16) * sw + (int)(seed_xy & 0xffff);
     G.bx0 = G.by0 = 0x7fffffff;
@@ -1032,13 +1066,16 @@ __device__ __forceinline__ int ooo_run_seed(const GrowT<true> G, const LineDev &
     grad_at(G.img, sw, sidx, gx, gy);
     const float seed_deg = fast_atan2_deg((float)gx, (float)-gy);
     double reg_angle;
+    G.aborted = false;
     int n = region_grow(G, seed_xy, seed_deg, D.prec, reg_angle);
     okr = false;
     Rect R;
-    if (n >= D.min_reg_size) {
+    if (!G.aborted && n >= D.min_reg_size) {
         region2rect(G, n, reg_angle, D.prec, R);
         okr = refine(G, n, seed_deg, reg_angle, D.prec, R);
     }
+    aborted = G.aborted;
+    if (aborted) okr = false;
     x0 = G.bx0, y0 = G.by0, x1 = G.bx1, y1 = G.by1;
     for (int off = 16; off >= 1; off >>= 1) {
         x0 = min(x0, __shfl_xor_sync(kFull, x0, off));
@@ -1067,6 +1104,7 @@ __device__ __forceinline__ void ooo_commit_list(const GrowT<true> &G, uint32_t *
         const uint32_t xy = G.get(i);
         const int pidx = (int)(xy >> 16) * sw + (int)(xy & 0xffff);
         atomicAnd(&G.mark[pidx >> 5], ~(1u << (pidx & 31)));
+        G.unclaim(pidx);
         if (commit) atomicOr(&used[pidx >> 5], 1u << (pidx & 31));
     }
     __syncwarp();
@@ -1113,8 +1151,14 @@ __device__ void ooo_drain(const OooShared &S, const LineDev &D, const GrowT<true
             bool okr = false;
             float4 seg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!((ooo_ld(reinterpret_cast<const int *>(&S.used[sidx >> 5])) >> (sidx & 31)) & 1)) {  // the committed map IS the sequential state here
-                n = ooo_run_seed(Gsp, D, seed_xy, okr, seg, x0, y0, x1, y1);
+                GrowT<true> Gh = Gsp;
+                Gh.my_ticket = h;  // the lowest ticket in flight: nothing it meets can belong to an earlier one, it never stops
+                if (lane == 0) *reinterpret_cast<volatile int *>(&C.ctx_ticket[Gsp.self]) = h;
+                __syncwarp();
+                bool ab;
+                n = ooo_run_seed(Gh, D, seed_xy, okr, seg, x0, y0, x1, y1, ab);
                 ooo_commit_list(Gsp, S.used, n, S.sw, true);
+                if (lane == 0) *reinterpret_cast<volatile int *>(&C.ctx_ticket[Gsp.self]) = 0x7fffffff;
             }
             if (lane == 0) {
                 E.bx0 = (short)min(x0, 32767);
@@ -1163,7 +1207,8 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
     const int used_words = (D.npx + 31) >> 5, used_pad = (used_words + 3) & ~3;
     uint32_t *s_used = reinterpret_cast<uint32_t *>(s_img + img_bytes);  // committed marks
     uint32_t *s_priv = s_used + used_pad;                                // W + 1 private bitmaps (the last one: head execution)
-    uint32_t *s_reg = s_priv + (size_t)(W + 1) * used_pad;               // W + 1 region windows
+    uint32_t *s_claim = s_priv + (size_t)(W + 1) * used_pad;             // union of the private bitmaps (collision detector)
+    uint32_t *s_reg = s_claim + used_pad;                                // W + 1 region windows
     OooEntry *ring = reinterpret_cast<OooEntry *>(s_reg + (size_t)(W + 1) * kOooRegCap);
     OooCtl &C = *reinterpret_cast<OooCtl *>(ring + kOooRing);
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1176,7 +1221,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
         } else {
             for (int i = tid; i < D.npx; i += blockDim.x) s_img[i] = src[i];
         }
-        for (int i = tid; i < used_pad * (W + 2); i += blockDim.x) s_used[i] = 0;
+        for (int i = tid; i < used_pad * (W + 3); i += blockDim.x) s_used[i] = 0;
         uint32_t *z = reinterpret_cast<uint32_t *>(ring);
         for (int i = tid; i < (int)((sizeof(OooEntry) * kOooRing + sizeof(OooCtl)) / 4); i += blockDim.x) z[i] = 0;
     }
@@ -1192,7 +1237,16 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
     G.tab = D.cstab;
     G.direct = false;
     G.lane = lane;
+    G.claim = s_claim;
+    G.priv_base = s_priv;
+    G.ctx_ticket = C.ctx_ticket;
+    G.nctx = W + 1;
+    G.ctx_words = used_pad;
+    G.my_ticket = 0x7fffffff;
+    G.aborted = false;
+    G.self = warp;
     Gsp = G;
+    Gsp.self = W;
     G.mark = s_priv + (size_t)warp * used_pad;
     G.reg = s_reg + (size_t)warp * kOooRegCap;
     G.reg_ovf = reg_ovf_mw + ((size_t)b * (kMwMaxWarps + 1) + warp) * D.npx;
@@ -1204,6 +1258,8 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
     float4 *segs = D.segs + (size_t)b * D.seg_cap;
     const int nseeds = D.nseeds[b];
     const int sw = D.sw;
+    if (tid <= W) C.ctx_ticket[tid] = 0x7fffffff;
+    __syncthreads();
     const long long t_start = clock64();
     bool timed_out = false;
     for (;;) {
@@ -1289,10 +1345,23 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
             if (__any_sync(kFull, other)) {
                 state = kOooDeferred;
             } else {
-                bool okr;
+                bool okr, aborted;
                 float4 seg;
                 int x0, y0, x1, y1;
-                const int n = ooo_run_seed(G, D, seed_xy, okr, seg, x0, y0, x1, y1);
+                G.my_ticket = t;
+                if (lane == 0) *reinterpret_cast<volatile int *>(&C.ctx_ticket[warp]) = t;
+                __syncwarp();
+                const int n = ooo_run_seed(G, D, seed_xy, okr, seg, x0, y0, x1, y1, aborted);
+                if (aborted) {
+                    // ran into a pixel of an earlier region in flight: most likely this seed is about to be absorbed -- forget the
+                    // partial region and let the head decide
+                    ooo_commit_list(G, s_used, n, sw, false);
+                    if (lane == 0) {
+                        *reinterpret_cast<volatile int *>(&C.ctx_ticket[warp]) = 0x7fffffff;
+                        C.stat[7]++;
+                    }
+                    state = kOooDeferred;
+                } else {
                 if (lane == 0) {
                     E.n = n;
                     E.ok = okr ? 1 : 0;
@@ -1306,9 +1375,11 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
                     if (lane < n) E.px[lane] = G.get(lane);
                     __syncwarp();
                     ooo_commit_list(G, s_used, n, sw, false);  // clears the private marks only
+                    if (lane == 0) *reinterpret_cast<volatile int *>(&C.ctx_ticket[warp]) = 0x7fffffff;
                     state = kOooParked;
                 } else {
-                    state = kOooHeld;
+                    state = kOooHeld;  // (the context keeps its ticket until the region is committed)
+                }
                 }
             }
         }
@@ -1329,6 +1400,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
                 }
             }
             if (timed_out) break;
+            if (lane == 0) *reinterpret_cast<volatile int *>(&C.ctx_ticket[warp]) = 0x7fffffff;
         } else {
             ooo_drain(S, D, G, Gsp, warp, segs, b);
         }
@@ -1338,7 +1410,7 @@ __global__ void __launch_bounds__(kMwMaxWarps * 32) lsd_grow_ooo_kernel(LineDev 
     if (tid == 0) {
         D.nseg[b] = min(C.nseg, D.seg_cap);
         if (D.mw_stat)
-            for (int q = 0; q < 7; ++q) D.mw_stat[8 * b + q] = C.stat[q];
+            for (int q = 0; q < 8; ++q) D.mw_stat[8 * b + q] = C.stat[q];
     }
 }
 
@@ -1803,7 +1875,7 @@ plp_status plp_line_create(plp_ctx *ctx, int rows, int cols, int max_batch, plp_
             if (so == PLP_OK) so = ensure_smem_optin((const void *)lsd_grow_mw_kernel, h->mw_smem, "lsd_grow_mw_kernel");
             if (so == PLP_OK) so = dev_alloc(h, &h->d_reg_mw, (size_t)h->mw_max_batch * (kMwMaxWarps + 1) * D.npx);
             // out-of-order variant: one more private bitmap + window (execution at the head), the reorder buffer
-            const size_t ofixed = (size_t)((D.npx + 15) & ~15) + 2 * used_bytes + (size_t)kOooRegCap * 4 + sizeof(OooEntry) * kOooRing +
+            const size_t ofixed = (size_t)((D.npx + 15) & ~15) + 3 * used_bytes + (size_t)kOooRegCap * 4 + sizeof(OooEntry) * kOooRing +
                                   sizeof(OooCtl) + 64, oper = used_bytes + (size_t)kOooRegCap * 4;
             h->ooo_warps = ofixed + 2 * oper <= budget ? (int)std::min<size_t>(kMwMaxWarps, (budget - ofixed) / oper) : 0;
             if (const char *ev = getenv("PLP_LSD_OOO")) h->ooo_auto = atoi(ev) != 0;
@@ -1895,11 +1967,11 @@ plp_status plp_line_debug_grow_variant(plp_line *h, int variant) {
 plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out3) {
     PLP_REQUIRE(h && out3, "null pointer");
     PLP_REQUIRE(b >= 0 && b < h->max_batch, "index");
-    for (int q = 0; q < 7; ++q) out3[q] = 0;
+    for (int q = 0; q < 8; ++q) out3[q] = 0;
     if (!h->dev.mw_stat) return PLP_OK;
     plp_ctx *ctx = h->ctx;
     PLP_CUDA_TRY(cudaSetDevice(ctx->device));
-    PLP_CUDA_TRY(cudaMemcpyAsync(out3, h->dev.mw_stat + 8 * (size_t)b, 56, cudaMemcpyDeviceToHost, ctx->stream));
+    PLP_CUDA_TRY(cudaMemcpyAsync(out3, h->dev.mw_stat + 8 * (size_t)b, 64, cudaMemcpyDeviceToHost, ctx->stream));
     PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return PLP_OK;
 }
