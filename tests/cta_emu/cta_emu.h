@@ -8,6 +8,9 @@
 #pragma once
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
+#include <stdio.h>
+#include <time.h>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -35,6 +38,26 @@ static inline void __syncthreads() { pthread_barrier_wait(&g_cta_barrier); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int *a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicOr(unsigned *a, unsigned v) { return __atomic_fetch_or(a, v, __ATOMIC_SEQ_CST); }
+static inline int atomicOr(int *a, int v) { return __atomic_fetch_or(a, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicAnd(unsigned *a, unsigned v) { return __atomic_fetch_and(a, v, __ATOMIC_SEQ_CST); }
+static inline int atomicExch(int *a, int v) { return __atomic_exchange_n(a, v, __ATOMIC_SEQ_CST); }
+static inline int atomicCAS(int *a, int expected, int desired) {
+    __atomic_compare_exchange_n(a, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return expected;  // the value found, like CUDA's atomicCAS
+}
+static inline void __nanosleep(unsigned) { sched_yield(); }
+static inline long long clock64() {  // "cycles" = nanoseconds of the monotonic clock
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+struct float4 {
+    float x, y, z, w;
+};
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct short2 {
+    short x, y;
+};
 static inline int atomicMin(int *a, int v) {
     int old = __atomic_load_n(a, __ATOMIC_SEQ_CST);
     while (v < old && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {

@@ -481,3 +481,64 @@ def test_point_match_kernel_on_cpu_worklist_overflow(pmatch_emu, orc, plp):
             want[best_i] = q
     _, matched, num = _emu_point_match(pmatch_emu, grid, curr, qq, 0, 0.0, 0)
     assert np.array_equal(matched, want) and num == int((want >= 0).sum()) and num >= 40
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LSD region growing (csrc/lsd_grow_kernels.cuh): the one-warp kernel, the multi-warp round protocol and the out-of-order
+# variant (tickets, reorder buffer, in-order commit, claim bitmap) on the host.  The warps of the multi-warp variants are
+# real concurrent host threads here, so their locks and the commit order are exercised; all three must reproduce the
+# oracle's segments bit for bit, in detection order.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def lsdgrow_emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = tmp_path_factory.mktemp("emu") / "liblsdgrow_emu.so"
+    cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-shared", "-fPIC", "-ffp-contract=off",
+           f"-I{ROOT / 'structure-plp-slam_b200' / 'csrc'}", f"-I{ROOT / 'tests' / 'cta_emu'}",
+           str(ROOT / "tests" / "cta_emu" / "lsdgrow_emu.cc"), "-o", str(so)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[:3000]
+    return C.CDLL(str(so))
+
+
+def _lsd_grow_inputs(orc, img):
+    """The half-resolution image and the seed list (y << 16 | x, gradient order) the region growing kernels start from."""
+    import math
+    import oracle_api
+    scaled = np.ascontiguousarray(orc.lsd_scaled(img))
+    sh, sw = scaled.shape
+    ang, g2 = np.zeros((sh, sw), np.float32), np.zeros((sh, sw), np.int32)
+    bins, order = np.zeros((sh, sw), np.int32), np.zeros(sh * sw, np.int32)
+    cfg = oracle_api.OLsdCfg(*oracle_api.LSD_DET)
+    P = C.c_void_p
+    n = orc.lib.orc_lsd_ll_angle(scaled.ctypes.data_as(P), C.c_int(sw), C.c_int(sh), C.byref(cfg), ang.ctypes.data_as(P),
+                                 g2.ctypes.data_as(P), bins.ctypes.data_as(P), order.ctypes.data_as(P))
+    order = order[:n]
+    rho = 2.0 / math.sin(math.pi * 22.5 / 180)   # lsd.cpp: quant / sin(prec)
+    k = int(math.floor(4 * rho * rho)) + 2
+    while k > 0 and not (math.sqrt(k / 4.0) <= rho):
+        k -= 1
+    o = order[g2.ravel()[order] > k]             # pixels whose level-line angle is defined
+    return scaled, ((o // sw).astype(np.uint32) << 16 | (o % sw).astype(np.uint32)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("variant,warps", [(1, 1), (2, 4), (3, 4), (3, 6)])
+def test_lsd_region_growing_variants_equal_oracle(lsdgrow_emu, variant, warps):
+    import oracle_api
+    import synth
+    orc = oracle_api.Oracle()
+    img = synth.make_line_image(3, 96, 160)
+    scaled, oxy = _lsd_grow_inputs(orc, img)
+    ref = orc.lsd_detect(img)
+    cap = 4000
+    segs, nseg, status, stat = np.zeros((cap, 4), np.float32), C.c_int(0), C.c_int(0), (C.c_ulonglong * 8)()
+    P = C.c_void_p
+    r = lsdgrow_emu.emu_lsd_grow(C.c_int(variant), C.c_int(warps), scaled.ctypes.data_as(P), C.c_int(scaled.shape[1]),
+                                 C.c_int(scaled.shape[0]), oxy.ctypes.data_as(P), C.c_int(len(oxy)), segs.ctypes.data_as(P),
+                                 C.c_int(cap), C.byref(nseg), C.byref(status), stat)
+    assert r == 0 and status.value == 0
+    assert nseg.value == len(ref) and len(ref) > 50
+    assert np.array_equal(segs[:nseg.value], ref), "segments differ from the sequential detector"
+    if variant == 3:
+        assert stat[0] >= len(ref)  # tickets

@@ -53,6 +53,11 @@ if [[ " $WHAT " == *" proflines "* ]]; then
       python bench.py --only-lines --steps 2 --warmup 3 --line-batch 64 --no-cpu-baseline > gpurun_out/bench_lines_under_ncu_full_${TAG}.log 2>&1
   echo "line profile exit $?"
 fi
+if [[ " $WHAT " == *" ooodbg "* ]]; then
+  PLP_TEST_OOO=1 timeout 60 python -m pytest tests/test_lines_gpu.py -q -m gpu -x -s -k "lines-2-shape1-3" > gpurun_out/test_lines_ooodbg_${TAG}.log 2>&1
+  echo "ooodbg exit $?"; grep "ooo timeout\|\[ooo\]\|passed\|failed" gpurun_out/test_lines_ooodbg_${TAG}.log | head -20 | cut -c1-400
+  WHAT="$WHAT ooo"
+fi
 if [[ " $WHAT " == *" ooo "* ]]; then
   # the out-of-order region growing kernel, under short timeouts of its own
   PLP_TEST_OOO=1 timeout 150 python -m pytest tests/test_lines_gpu.py -q -m gpu -x -s > gpurun_out/test_lines_ooo_${TAG}.log 2>&1
