@@ -327,6 +327,20 @@ def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_b
         trk.extract_LSD_LBD(frames[i % batch])
         lat.append(1e3 * (time.perf_counter() - t0))
     batch1_ms = float(np.median(lat[1:]))
+    # the same with the out-of-order region growing (opt-in variant 3: tickets, reorder buffer, in-order commit; §3.6)
+    batch1_ooo = None
+    try:
+        trk.grow_variant(3)
+        lat = []
+        for i in range(6):
+            t0 = time.perf_counter()
+            trk.extract_LSD_LBD(frames[i % batch])
+            lat.append(1e3 * (time.perf_counter() - t0))
+        batch1_ooo = float(np.median(lat[1:]))
+    except Exception as e:  # an experimental variant must not take the leg down
+        batch1_ooo = f"{type(e).__name__}: {e}"
+    finally:
+        trk.grow_variant(0)
     # per-kernel shares
     ctx._check(lib.plp_ctx_kernel_timing(ctx.handle, 1))
     for _ in range(min(steps, 3)):
@@ -348,7 +362,8 @@ def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_b
            "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
                    "d2h_bytes_per_step": int(kl.nbytes + lbd.nbytes + fn.nbytes + nn.nbytes)},
            "gpu_launches": int(launches), "kernel_time_shares": shares, "ms_per_launch": per_launch,
-           "latency_ms_one_frame": batch1_ms, "algorithmic_bytes_per_step": alg, "hbm_roofline_frac": alg / (ms / steps * 1e-3) / 1e9 / peak}
+           "latency_ms_one_frame": batch1_ms, "latency_ms_one_frame_out_of_order": batch1_ooo,
+           "algorithmic_bytes_per_step": alg, "hbm_roofline_frac": alg / (ms / steps * 1e-3) / 1e9 / peak}
     if cpu_baseline and rank == 0:
         import oracle_api
         orc = oracle_api.Oracle()
@@ -1123,7 +1138,10 @@ def main():
                                       "mean_keylines_per_frame": round(r["config"]["mean_keylines_per_frame"], 1),
                                       "hbm_roofline_frac": float(f"{r['hbm_roofline_frac']:.3g}"),
                                       "frames_per_step_per_gpu": args.line_batch,
-                                      "latency_ms_one_frame": round(r["latency_ms_one_frame"], 2)}
+                                      "latency_ms_one_frame": round(r["latency_ms_one_frame"], 2),
+                                      "latency_ms_one_frame_out_of_order": (round(r["latency_ms_one_frame_out_of_order"], 2)
+                                                                            if isinstance(r["latency_ms_one_frame_out_of_order"], float)
+                                                                            else r["latency_ms_one_frame_out_of_order"])}
         if "cpu_baseline" in r:
             cfg_extra["line_frontend"]["cpu_port_frames_per_s"] = round(r["cpu_baseline"]["value"], 1)
     if not args.no_stereo:
