@@ -363,6 +363,7 @@ def bench_lines(pkg, ctx, stream, rank, world, steps, warmup, batch, seed, cpu_b
                    "d2h_bytes_per_step": int(kl.nbytes + lbd.nbytes + fn.nbytes + nn.nbytes)},
            "gpu_launches": int(launches), "kernel_time_shares": shares, "ms_per_launch": per_launch,
            "latency_ms_one_frame": batch1_ms, "latency_ms_one_frame_out_of_order": batch1_ooo,
+           "out_of_order_fallbacks": trk.ooo_fallbacks(),
            "algorithmic_bytes_per_step": alg, "hbm_roofline_frac": alg / (ms / steps * 1e-3) / 1e9 / peak}
     if cpu_baseline and rank == 0:
         import oracle_api

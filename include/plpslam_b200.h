@@ -595,13 +595,17 @@ PLP_API plp_status plp_line_debug_segments(plp_line *h, int b, float *segs_out, 
  * (2 per SM at VGA) and reads it through L2 for larger batches (6 frames per SM); this forces the second variant so that
  * the parity tests cover both */
 PLP_API plp_status plp_line_debug_force_global_image(plp_line *h, int on);
-/* region growing variant: 0 automatic (multi-warp for at most half a wave of frames, i.e. the live-sequence case), 1 one warp
+/* region growing variant: 0 automatic (multi-warp rounds for at most half a wave of frames, out of order for a live frame through
+ * the host entry point), 1 one warp
  * per frame, 2 speculative multi-warp rounds with in-order commit, 3 out of order with a reorder buffer and in-order commit;
  * all of them produce the sequential result bit for bit.
  * grow_stats (8 values): {rounds, seeds run, seeds redone after a conflict, then SM cycles warp 0 spent scanning for seeds,
  * on its own seed, waiting for the slowest warp of the round, committing} of frame b in the last multi-warp run. */
 PLP_API plp_status plp_line_debug_grow_variant(plp_line *h, int variant);
 PLP_API plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out8);
+/* host-pointer calls of at most two frames (a live frame / stereo pair) take the out-of-order kernel in automatic mode; this
+ * counts the calls that were re-run with the round protocol because that kernel gave up (expected: 0) */
+PLP_API int plp_line_debug_ooo_fallbacks(const plp_line *h);
 PLP_API plp_status plp_line_debug_scaled(plp_line *h, int b, uint8_t *out /* (rows/2) x (cols/2) */);
 PLP_API plp_status plp_line_debug_lbd_float(plp_line *h, int b, float *out /* n x 72 */, int cap);
 

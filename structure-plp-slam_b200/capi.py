@@ -834,6 +834,10 @@ class LineFeatureTracker:
         """0 automatic, 1 one warp per frame, 2 speculative multi-warp region growing (same result, bit for bit)."""
         self._ctx._check(self._lib.plp_line_debug_grow_variant(self._h, C.c_int(variant)))
 
+    def ooo_fallbacks(self) -> int:
+        """Host calls that were re-run with the round protocol because the out-of-order region growing gave up (expected 0)."""
+        return int(self._lib.plp_line_debug_ooo_fallbacks(self._h))
+
     def grow_stats(self, b: int = 0, ooo: bool = False):
         """{rounds, seeds run, seeds redone after a conflict, cycle counters} of frame b in the last multi-warp run; with ooo:
         the counters of the out-of-order variant."""

@@ -491,6 +491,9 @@ struct plp_line {
     int grow_variant = 0;  // 0 automatic, 1 one warp per frame, 2 multi-warp rounds (lsd_grow_mw_kernel), 3 out of order (lsd_grow_ooo_kernel)
     int ooo_warps = 0;
     bool ooo_auto = false;
+    bool host_call = false;   // inside the host-pointer entry point (a live frame): automatic mode may take the out-of-order kernel
+    bool used_ooo = false;    // the last run did
+    int ooo_fallbacks = 0;    // host calls that were re-run with the round protocol after an out-of-order timeout
     size_t ooo_smem = 0;
     int mw_warps = 0, mw_max_batch = 0;
     size_t mw_smem = 0;
@@ -533,8 +536,11 @@ static plp_status line_run(plp_line *h, const uint8_t *d_imgs, int batch, size_t
     // commit) cut the latency of a live frame instead
     const bool mw = h->mw_warps >= 2 && batch <= h->mw_max_batch && h->grow_variant != 1 &&
                     (h->grow_variant >= 2 || 2 * batch <= ctx->sm_count);  // half a wave: a second handle (stereo) fits beside it
-    // (automatic mode takes the out-of-order kernel only when PLP_LSD_OOO=1: it is the newest code of the tree)
-    const bool ooo = mw && h->ooo_warps >= 2 && (h->grow_variant == 3 || (h->grow_variant == 0 && h->ooo_auto));
+    // automatic mode takes the out-of-order kernel for a live frame or stereo pair through the host entry point (which re-runs
+    // the frame with the round protocol should the kernel ever give up), elsewhere only with PLP_LSD_OOO=1
+    const bool ooo = mw && h->ooo_warps >= 2 &&
+                     (h->grow_variant == 3 || (h->grow_variant == 0 && (h->ooo_auto || (h->host_call && batch <= 2))));
+    h->used_ooo = ooo;
     if (ooo) {
         PLP_LAUNCH(ctx, lsd_grow_ooo_kernel, batch, h->ooo_warps * 32, h->ooo_smem, D, h->d_reg_mw);
     } else if (mw) {
@@ -715,14 +721,32 @@ static plp_status line_extract_host(plp_line *h, const uint8_t *imgs, int batch,
     const size_t rows = h->rows, cols = h->cols, cap = h->dev.kl_cap;
     PLP_CUDA_TRY(cudaMemcpy2DAsync(h->d_img, cols, imgs, step, cols, rows * (size_t)batch, cudaMemcpyHostToDevice,
                                    ctx->stream));
-    PLP_TRY(line_run(h, h->d_img, batch, cols, h->d_kl, h->d_lbd, h->d_fn, h->d_n, nullptr));
-    PLP_CUDA_TRY(cudaMemcpyAsync(n_out, h->d_n, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PLP_CUDA_TRY(cudaMemcpyAsync(kl_out, h->d_kl, (size_t)batch * cap * sizeof(plp_keyline), cudaMemcpyDeviceToHost, ctx->stream));
-    PLP_CUDA_TRY(cudaMemcpyAsync(lbd_out, h->d_lbd, (size_t)batch * cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    PLP_CUDA_TRY(cudaMemcpyAsync(fn_out, h->d_fn, (size_t)batch * cap * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<int> status(batch);
-    PLP_CUDA_TRY(cudaMemcpyAsync(status.data(), h->dev.status, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    auto run_and_fetch = [&]() -> plp_status {
+        h->host_call = true;
+        const plp_status rs = line_run(h, h->d_img, batch, cols, h->d_kl, h->d_lbd, h->d_fn, h->d_n, nullptr);
+        h->host_call = false;
+        PLP_TRY(rs);
+        PLP_CUDA_TRY(cudaMemcpyAsync(n_out, h->d_n, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PLP_CUDA_TRY(cudaMemcpyAsync(kl_out, h->d_kl, (size_t)batch * cap * sizeof(plp_keyline), cudaMemcpyDeviceToHost, ctx->stream));
+        PLP_CUDA_TRY(cudaMemcpyAsync(lbd_out, h->d_lbd, (size_t)batch * cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        PLP_CUDA_TRY(cudaMemcpyAsync(fn_out, h->d_fn, (size_t)batch * cap * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PLP_CUDA_TRY(cudaMemcpyAsync(status.data(), h->dev.status, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PLP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return PLP_OK;
+    };
+    PLP_TRY(run_and_fetch());
+    bool gave_up = false;
+    for (int b = 0; b < batch; ++b) gave_up = gave_up || (status[b] & 2) != 0;
+    if (gave_up && h->used_ooo && h->grow_variant == 0) {
+        // the out-of-order region growing bounds every wait; should it ever give up in automatic mode, the frames are run
+        // again with the round protocol (still on the GPU) -- an explicitly selected variant 3 reports the failure instead
+        h->ooo_fallbacks++;
+        h->grow_variant = 2;
+        const plp_status r2 = run_and_fetch();
+        h->grow_variant = 0;
+        PLP_TRY(r2);
+    }
     for (int b = 0; b < batch; ++b)
         if (status[b] != 0) {
             set_error("line: capacity overflow in frame %d (code %d)", b, status[b]);
@@ -765,6 +789,8 @@ plp_status plp_line_debug_grow_variant(plp_line *h, int variant) {
     h->grow_variant = variant;
     return PLP_OK;
 }
+
+int plp_line_debug_ooo_fallbacks(const plp_line *h) { return h ? h->ooo_fallbacks : 0; }
 
 plp_status plp_line_debug_grow_stats(plp_line *h, int b, unsigned long long *out3) {
     PLP_REQUIRE(h && out3, "null pointer");
