@@ -84,3 +84,7 @@ if [[ " $WHAT " == *" profba "* ]]; then
   echo "ba profile exit $?"
 fi
 ls -la gpurun_out | tail -30
+if [[ " $WHAT " == *" lineslat "* ]]; then
+  timeout 200 python bench.py --only-lines --no-cpu-baseline --steps 4 --warmup 3 > gpurun_out/bench_lines_${TAG}.json 2> gpurun_out/bench_lines_${TAG}.err
+  echo "bench lines exit $?"; cut -c1-1500 gpurun_out/bench_lines_${TAG}.json
+fi
