@@ -61,9 +61,11 @@ def main():
         hdr, units = rows[0], rows[1]
         idx = {m: hdr.index(m) for m in METRICS if m in hdr}
         kn = hdr.index("Kernel Name")
-        (PROF / f"prof_{tag}_raw_selected.csv").write_text(
-            "\n".join([",".join(["kernel"] + list(idx))] + [",".join([short(r[kn])] + [r[i] for i in idx.values()])
-                                                             for r in rows[2:]]) + "\n")
+        with open(PROF / f"prof_{tag}_raw_selected.csv", "w", newline="") as fh:  # csv.writer quotes "kernel<1024, 3840, 2>"
+            wr = csv.writer(fh)
+            wr.writerow(["kernel"] + list(idx))
+            for r in rows[2:]:
+                wr.writerow([short(r[kn])] + [r[i] for i in idx.values()])
         lines += ["## `ncu --set full` capture of one bench step (one launch per kernel)", "",
                   "| kernel | grid x block | ms | DRAM read MB | DRAM write MB | DRAM % of peak | SM % of peak | warps active % | regs | waves/SM | inst (M) |",
                   "|---|---|---|---|---|---|---|---|---|---|---|"]
