@@ -10,8 +10,8 @@ import oracle_api
 import synth
 
 pytestmark = pytest.mark.gpu
-# variant 3 (out-of-order region growing) is exercised when PLP_TEST_OOO=1
-VARIANTS = [1, 2, 3] if os.environ.get("PLP_TEST_OOO") == "1" else [1, 2]
+# all three region-growing variants; PLP_TEST_OOO=0 leaves the out-of-order one (3) out
+VARIANTS = [1, 2] if os.environ.get("PLP_TEST_OOO") == "0" else [1, 2, 3]
 
 KL_FIELDS = ("angle", "class_id", "octave", "pt_x", "pt_y", "response", "size", "start_x", "start_y", "end_x", "end_y",
              "s_oct_x", "s_oct_y", "e_oct_x", "e_oct_y", "line_length", "num_pixels")

@@ -56,7 +56,7 @@ for cfg in cfgs:
             imgs = np.concatenate([fr] * ((batch + 7) // 8))[:batch]
             trk = plp.LineFeatureTracker(ctx, H, W, max_batch=batch)
             out = {}
-            for variant in ((1, 2, 3) if os.environ.get('PLP_TEST_OOO') == '1' else (1, 2)):
+            for variant in ((1, 2) if os.environ.get('PLP_TEST_OOO') == '0' else (1, 2, 3)):
                 trk.grow_variant(variant)
                 out[variant] = (timed(trk, imgs), kernel_ms(trk, imgs))
                 if variant == 2:
