@@ -4,7 +4,7 @@
         tests/run_ba_multigpu.py
 
 Every rank owns a contiguous block of landmarks; the ranks exchange only the packed reduced camera system
-(ncclAllReduce).  The merged result must equal the single-GPU / oracle result (1e-4 relative)."""
+(one-shot all-reduce kernel over NVLink peer memory, or ncclAllReduce).  The merged result must equal the single-GPU / oracle result (1e-4 relative)."""
 import os
 import sys
 from pathlib import Path
