@@ -144,96 +144,17 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(OrbDev P, int l, const 
 // =====================================================================================================
 // 2. FAST-9/16 per cell
 // =====================================================================================================
-// ring offsets
-__constant__ int kRingDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-__constant__ int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-
-// m = max over the sixteen 9-arcs of min(arc differences), both polarities; returns 0 early when the pixel
-// cannot be a corner at threshold `t` (then m <= t and the caller stores score 0).
-// Necessary condition for a FAST-9 corner: a 9-arc covers at least two ADJACENT compass pixels (0, 4, 8, 12), which
-// must then all be darker (or all brighter) than the centre by more than t.
-__device__ __forceinline__ bool fast_compass(const uint8_t *p, int t) {
-    const int v = p[0];
-    const int d0 = v - p[3 * kTilePitch], d4 = v - p[3], d8 = v - p[-3 * kTilePitch], d12 = v - p[-3];
-    const unsigned dk = (unsigned)(d0 > t) | ((unsigned)(d4 > t) << 1) | ((unsigned)(d8 > t) << 2) | ((unsigned)(d12 > t) << 3);
-    const unsigned br = (unsigned)(d0 < -t) | ((unsigned)(d4 < -t) << 1) | ((unsigned)(d8 < -t) << 2) | ((unsigned)(d12 < -t) << 3);
-    // adjacent pairs on the 4-cycle: (0,1) (1,2) (2,3) (3,0)
-    const unsigned dk2 = dk & ((dk >> 1) | (dk << 3)), br2 = br & ((br >> 1) | (br << 3));
-    return ((dk2 | br2) & 0xfu) != 0;
-}
-
-__device__ __forceinline__ int fast_m(const uint8_t *p, int t) {
-    const int v = p[0];
-    int d[16];
-    // a 9-arc always contains ring pixel 0 or 8, and 4 or 12
-    d[0] = v - p[3 * kTilePitch];
-    d[8] = v - p[-3 * kTilePitch];
-    if (abs(d[0]) <= t && abs(d[8]) <= t) return 0;
-    d[4] = v - p[3];
-    d[12] = v - p[-3];
-    if (abs(d[4]) <= t && abs(d[12]) <= t) return 0;
-    d[1] = v - p[3 * kTilePitch + 1];
-    d[2] = v - p[2 * kTilePitch + 2];
-    d[3] = v - p[1 * kTilePitch + 3];
-    d[5] = v - p[-1 * kTilePitch + 3];
-    d[6] = v - p[-2 * kTilePitch + 2];
-    d[7] = v - p[-3 * kTilePitch + 1];
-    d[9] = v - p[-3 * kTilePitch - 1];
-    d[10] = v - p[-2 * kTilePitch - 2];
-    d[11] = v - p[-1 * kTilePitch - 3];
-    d[13] = v - p[1 * kTilePitch - 3];
-    d[14] = v - p[2 * kTilePitch - 2];
-    d[15] = v - p[3 * kTilePitch - 1];
-    unsigned dark = 0, bright = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        dark |= (unsigned)(d[k] > t) << k;
-        bright |= (unsigned)(d[k] < -t) << k;
-    }
-    dark |= dark << 16;
-    bright |= bright << 16;
-    unsigned a = dark & (dark >> 1);
-    a &= a >> 2;
-    a &= a >> 4;
-    a &= dark >> 8;
-    unsigned c = bright & (bright >> 1);
-    c &= c >> 2;
-    c &= c >> 4;
-    c &= bright >> 8;
-    if (((a | c) & 0xffffu) == 0) return 0;
-    // exact score: sliding-window minimum of length 9 over the circular ring (doubling), once on d = v - ring
-    // (dark arcs) and once on e = ring - v (bright arcs).  NB: written with minima only -- ptxas 12.9 for
-    // sm_100a miscompiles max(a, -max(...)) (drops the negation when fusing into VIMNMX3), see DESIGN.md.
-    int e[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = -d[k];
-    int d2[16], e2[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        d2[k] = min(d[k], d[(k + 1) & 15]);
-        e2[k] = min(e[k], e[(k + 1) & 15]);
-    }
-    int d4[16], e4[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        d4[k] = min(d2[k], d2[(k + 2) & 15]);
-        e4[k] = min(e2[k], e2[(k + 2) & 15]);
-    }
-    int best = -255;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int d9 = min(min(d4[k], d4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int e9 = min(min(e4[k], e4[(k + 4) & 15]), e[(k + 8) & 15]);
-        best = max(best, max(d9, e9));
-    }
-    return best;
-}
-
-// The same score for TWO pixels at once on packed 16-bit halves (DPX min / max, VIMNMX3.S16x2): every difference is biased
+// FAST-9/16 ring: offsets (dx, dy) of ring pixel k = 0 .. 15, starting below the centre, counter-clockwise:
+//   (0,3) (1,3) (2,2) (3,1) (3,0) (3,-1) (2,-2) (1,-3) (0,-3) (-1,-3) (-2,-2) (-3,-1) (-3,0) (-3,1) (-2,2) (-1,3)
+// m = max over the sixteen 9-arcs of min(arc differences), both polarities (d = v - ring for dark arcs, e = ring - v for bright
+// ones); the sliding minimum of length 9 over the circular ring is built by doubling (2, 4, 4 + 4 + 1).  Written with minima
+// and a bias instead of negations: ptxas 12.9 for sm_100a miscompiles max(a, -max(...)) (drops the negation when fusing
+// into VIMNMX3), see DESIGN.md.
+// The score of TWO pixels at once on packed 16-bit halves (DPX min / max, VIMNMX3.S16x2): every difference is biased
 // by +256 so that both halves stay in [1, 511] -- plain 32-bit subtraction then never borrows across the halves and no
 // negation is needed (e' = 512 - d').  Returns (m_a + 256) | (m_b + 256) << 16 with m = max over the sixteen 9-arcs of
 // min(arc differences), both polarities; the pixel is a corner at threshold t  <=>  m > t  (a 9-arc whose pixels all
-// differ by more than t has a minimum above t and vice versa), which is the arc test of fast_m.
+// differ by more than t has a minimum above t and vice versa), which is the FAST-9 arc test.
 __device__ __forceinline__ uint32_t fast_m_pair(const uint8_t *pa, const uint8_t *pb) {
     const uint32_t v2 = ((uint32_t)pa[0] + 256u) | (((uint32_t)pb[0] + 256u) << 16);
     uint32_t d[16];
@@ -289,7 +210,7 @@ __device__ __forceinline__ bool masked(const OrbDev &P, unsigned y, unsigned x, 
 //   phase A  four pixels per lane on aligned 32-bit shared-memory words; the pretest is the sign-agnostic compass
 //            condition "two ADJACENT compass pixels differ from the centre by more than t" evaluated with the native
 //            VABSDIFF4 byte SIMD -- a necessary condition for a FAST-9 corner (a 9-arc covers two adjacent compass
-//            pixels, all darker or all brighter), slightly weaker than fast_compass; phase B decides exactly;
+//            pixels, all darker or all brighter), phase B decides exactly;
 //   NMS      only over the corners found (they set bits in the per-(row, half) masks with atomicOr -- a bit mask is
 //            order independent, so the row-major output order is unchanged);
 //   output   one thread per mask word walks its set bits.
@@ -1084,7 +1005,6 @@ __global__ void __launch_bounds__(kQtThreads, kMinBlocks) quadtree_kernel(OrbDev
 // 4. orientation + blur + steered BRIEF, one warp per keypoint
 // =====================================================================================================
 constexpr int kDescWarps = 4;
-constexpr int kSrcDim = 45, kSrcPitch = 48;   // 39 + 2*3
 constexpr int kBlurDim = 39, kBlurPitch = 44;  // window rows are staged as 11 aligned words
 
 __device__ __forceinline__ int reflect101(int p, int len) {
@@ -1495,7 +1415,6 @@ static bool encode_level_map(CUtensorMap *m, const uint8_t *base, int w, int h, 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int cv_round_host(double v) { return (int)lrint(v); }
 
 static void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<short4> &xt, std::vector<short4> &yt) {
     // cv::resize INTER_LINEAR 8U: 11-bit coefficients, rounded half-to-even
