@@ -30,6 +30,7 @@ static pthread_barrier_t g_cta_barrier;
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __noinline__
 #define __shared__ static
 
 #define __align__(n) __attribute__((aligned(n)))
@@ -44,6 +45,32 @@ static inline int atomicExch(int *a, int v) { return __atomic_exchange_n(a, v, _
 static inline int atomicCAS(int *a, int expected, int desired) {
     __atomic_compare_exchange_n(a, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return expected;  // the value found, like CUDA's atomicCAS
+}
+static inline unsigned atomicAdd(unsigned *a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
+static inline double atomicAdd(double *a, double v) {  // CAS loop on the bit pattern
+    unsigned long long *p = reinterpret_cast<unsigned long long *>(a), old = __atomic_load_n(p, __ATOMIC_SEQ_CST), nw;
+    double cur;
+    do {
+        __builtin_memcpy(&cur, &old, 8);
+        const double sum = cur + v;
+        __builtin_memcpy(&nw, &sum, 8);
+    } while (!__atomic_compare_exchange_n(p, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    return cur;
+}
+static inline unsigned long long atomicMax(unsigned long long *a, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(a, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+    }
+    return old;
+}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T>
+static inline T __ldcg(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+static inline double rsqrt(double v) { return 1.0 / sqrt(v); }
+static inline long long __double_as_longlong(double v) {
+    long long r;
+    __builtin_memcpy(&r, &v, 8);
+    return r;
 }
 static inline void __nanosleep(unsigned) { sched_yield(); }
 static inline long long clock64() {  // "cycles" = nanoseconds of the monotonic clock

@@ -542,3 +542,56 @@ def test_lsd_region_growing_variants_equal_oracle(lsdgrow_emu, variant, warps):
     assert np.array_equal(segs[:nseg.value], ref), "segments differ from the sequential detector"
     if variant == 3:
         assert stat[0] >= len(ref)  # tickets
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Bundle adjustment (csrc/ba_lm_kernels.cuh): the decide / linearize / reduce / solve / update / classify kernels run whole
+# local-BA solves on the host (tests/cta_emu/ba_emu.cc restates the LM try loop of ba_host.cu around them) and must follow the
+# oracle try for try.  This is how the read-after-write race on BaState::phase in the solve / decide kernels was found.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ba_emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = tmp_path_factory.mktemp("emu") / "libba_emu.so"
+    cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-shared", "-fPIC", "-ffp-contract=off",
+           f"-I{ROOT / 'structure-plp-slam_b200' / 'csrc'}", f"-I{ROOT / 'tests' / 'cta_emu'}",
+           str(ROOT / "tests" / "cta_emu" / "ba_emu.cc"), "-o", str(so)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[:3000]
+    return C.CDLL(str(so))
+
+
+def _emu_ba_solve(emu, prob, first=5, second=10, mode=0, ctas=3):
+    import synth
+    P = C.c_void_p
+    p = lambda a: np.ascontiguousarray(a).ctypes.data_as(P)
+    n_kf, n_pts, n_l = len(prob.kf_fixed), len(prob.pt_pos_w), len(prob.line_plucker)
+    kf, pts, ln = np.zeros((n_kf, 4, 4)), np.zeros((max(n_pts, 1), 3)), np.zeros((max(n_l, 1), 6))
+    po, lo = np.zeros(max(len(prob.pt_edge_kf), 1), np.uint8), np.zeros(max(len(prob.line_edge_kf), 1), np.uint8)
+    it = np.zeros(3, np.int32)
+    r = emu.emu_ba_solve(
+        C.c_double(synth.FX), C.c_double(synth.FY), C.c_double(synth.CX), C.c_double(synth.CY),
+        C.c_double(synth.BF if prob.stereo else -1.0), C.c_int(1 if prob.stereo else 0), C.c_int(n_kf), p(prob.kf_pose_cw),
+        p(prob.kf_fixed), C.c_int(n_pts), p(prob.pt_pos_w), C.c_int(len(prob.pt_edge_kf)), p(prob.pt_edge_kf), p(prob.pt_edge_lm),
+        p(prob.pt_edge_obs), p(prob.pt_edge_inv_sigma_sq), C.c_int(n_l), p(prob.line_plucker), C.c_int(len(prob.line_edge_kf)),
+        p(prob.line_edge_kf), p(prob.line_edge_lm), p(prob.line_edge_obs), p(prob.line_edge_inv_sigma_sq),
+        C.c_int(len(prob.plane_edge_lm)), p(prob.plane_edge_lm), p(prob.plane_edge_fn), C.c_int(first), C.c_int(second), C.c_int(mode),
+        C.c_int(ctas), kf.ctypes.data_as(P), pts.ctypes.data_as(P), ln.ctypes.data_as(P), po.ctypes.data_as(P), lo.ctypes.data_as(P),
+        it.ctypes.data_as(P))
+    assert r == 0
+    return kf, pts[:n_pts], ln[:n_l], po[:len(prob.pt_edge_kf)], lo[:len(prob.line_edge_kf)], tuple(int(v) for v in it)
+
+
+def test_local_ba_kernels_equal_oracle(ba_emu):
+    import ba_data
+    import oracle_api
+    orc = oracle_api.Oracle()
+    prob = ba_data.make_ba_problem(3, n_local=4, n_fixed=2, n_points=60, n_lines=12, n_plane_pts=6)
+    o = ba_data.oracle_local_ba(orc, prob)
+    kf, pts, ln, po, lo, it = _emu_ba_solve(ba_emu, prob, ctas=3)
+    assert it == (o.iters_first, o.iters_second, o.lm_tries)                       # same LM path, try for try
+    assert np.linalg.norm(kf - o.kf_pose_cw) / np.linalg.norm(o.kf_pose_cw) < 1e-6
+    assert np.abs(pts - o.pt_pos_w).max() < 1e-5
+    assert np.abs(ln - o.line_plucker[:len(ln)]).max() < 1e-3                      # numeric line Jacobians (delta = 1e-9)
+    assert np.array_equal(po, o.pt_edge_outlier[:len(po)]) and np.array_equal(lo, o.line_edge_outlier[:len(lo)])
