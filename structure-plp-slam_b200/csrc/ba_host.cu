@@ -63,7 +63,6 @@ plp_status launch_try(plp_ba *b) {
         const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
         b->try_graph_launches = (int)(ctx->launches - l0);
         ctx->launches = l0;
-        if (coll) coll->add_calls((uint64_t)0 - 2);  // the two calls counted during capture are added per replay below
         if (s != PLP_OK) return s;
         if (e != cudaSuccess) {
             set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));

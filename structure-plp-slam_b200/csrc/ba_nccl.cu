@@ -107,8 +107,12 @@ struct plp_ba_comm : public BaCollective {
             const int grid = std::max(1, std::min(kPeerChunks, (n + kPeerThreads - 1) / kPeerThreads));
             ba_peer_allreduce_kernel<<<grid, kPeerThreads, 0, ctx->stream>>>(args, d_buf, n);
             ctx->launches++;
-            calls++;
-            peer_calls++;
+            // while the LM try is being captured into its CUDA graph nothing runs: the replays are counted by add_calls()
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(ctx->stream, &cs) != cudaSuccess || cs == cudaStreamCaptureStatusNone) {
+                calls++;
+                peer_calls++;
+            }
             return PLP_OK;
         }
         const ncclResult_t r = ncclAllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, comm, ctx->stream);
